@@ -1,0 +1,84 @@
+"""
+Seeded inputs shared by ``make_golden.py`` (which runs the real reference on them) and the
+tests (which regenerate them and compare the oracle / the CUDA path with the stored
+reference outputs).  TEST INFRASTRUCTURE ONLY.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from barc4dip_b200 import synth
+
+
+def frame_cases() -> dict[str, np.ndarray]:
+    """2-D frames for the per-frame functions (F1-F4, F7-F13)."""
+    sq = synth.speckle_frame(256, grain=4.0, seed=11)
+    rect = synth.speckle_frame(128, 256, grain=5.0, seed=12)
+    odd = synth.speckle_frame(150, 200, grain=4.0, seed=13)          # non power of two (oracle only)
+    u16 = np.clip(synth.speckle_frame(128, grain=3.0, seed=14) * 8.0, 0, 65535).astype(np.uint16)
+    u16.ravel()[::997] = 65535                                        # saturated pixels
+    u16.ravel()[5::1013] = 0                                          # zero pixels
+    smooth = synth.focus_scan_stack(3, 256, grain=6.0, seed=15, noise_seed=16)[0]
+    big = synth.speckle_frame(512, grain=6.0, seed=17)
+    return {"sq256": sq, "rect128x256": rect, "odd150x200": odd, "u16_128": u16,
+            "blur256": smooth, "sq512": big}
+
+
+def nan_frame() -> np.ndarray:
+    a = synth.speckle_frame(128, grain=4.0, seed=18).copy()
+    a[3, 7] = np.nan
+    a[64, 64] = np.inf
+    a[127, 0] = -np.inf
+    return a
+
+
+def tracking_cases() -> dict[str, dict]:
+    """(template, image, slices) triples for phase correlation (F5/F6)."""
+    n = 256
+    base = synth.speckle_frame(n, grain=4.0, seed=21)
+    rng = np.random.default_rng(22)
+    full = (slice(0, n), slice(0, n))
+    cases: dict[str, dict] = {}
+
+    def add(name, dy, dx, noise=0.0, tpl=None, slices=full, subpixel=True):
+        img = synth.fourier_shift(base, dy, dx)
+        if noise:
+            img = img + rng.normal(0.0, noise * float(base.mean()), size=img.shape).astype(np.float32)
+        t = base[slices] if tpl is None else tpl
+        cases[name] = {"template": np.ascontiguousarray(t), "image": np.ascontiguousarray(img),
+                       "slices": slices, "subpixel": subpixel, "true_shift": (dy, dx)}
+
+    add("roll_2_m3", 2, -3)
+    add("sub_p3_m1", 0.3, -0.1)
+    add("sub_m5p25_7p6_noise", -5.25, 7.6, noise=0.01)
+    add("sub_12p5_m9p75_noise5", 12.5, -9.75, noise=0.05)
+    add("nosubpixel", 1.4, 2.6, subpixel=False)
+    add("zero_shift", 0, 0, noise=0.01)
+    # odd ROI, centred, slices_yx=None
+    c = n // 2
+    roi = (slice(c - 75, c + 76), slice(c - 75, c + 76))
+    add("roi151_centered", 3.3, -2.2, noise=0.01, slices=roi)
+    cases["roi151_centered"]["slices"] = None
+    # off-centre ROI with explicit slices
+    roi2 = (slice(20, 20 + 181), slice(40, 40 + 161))
+    add("roi181x161_offcentre", -1.7, 4.4, noise=0.01, slices=roi2)
+    # integer dtype inputs (converted to float32 by the tracker)
+    img_i = np.clip(synth.fourier_shift(base, 4, 6), 0, 65535).astype(np.uint16)
+    cases["uint16_roll_4_6"] = {"template": np.clip(base, 0, 65535).astype(np.uint16), "image": img_i,
+                                "slices": full, "subpixel": True, "true_shift": (4, 6)}
+    # rectangular frame
+    rb = synth.speckle_frame(128, 256, grain=4.0, seed=23)
+    cases["rect_roll_m6_9"] = {"template": rb, "image": synth.fourier_shift(rb, -6, 9),
+                               "slices": (slice(0, 128), slice(0, 256)), "subpixel": True,
+                               "true_shift": (-6, 9)}
+    return cases
+
+
+def flatfield_inputs():
+    return synth.flatfield_case(4, 128, seed=31, dead_frac=2e-3)
+
+
+def temporal_inputs():
+    raw, flat, dark = synth.flatfield_case(24, 64, seed=41, dead_frac=2e-3)
+    return raw, flat, dark

@@ -1,0 +1,176 @@
+"""
+Generate tests/golden/*.npz by running the REAL reference (imported from /root/reference)
+on the seeded inputs of ``oracle/golden_cases.py``.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden
+
+The outputs are small (scalars, 1-D cuts, 32x32 crops, and a few float32 maps at 128-256 px)
+and are committed; the inputs are regenerated from seeds by the tests.
+Recorded with numpy 2.3.5 / scipy 1.18.1 (the reference pins no versions).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import golden_cases as gc          # noqa: E402
+from oracle.load_reference import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def crop_center(a, h=16):
+    cy, cx = a.shape[0] // 2, a.shape[1] // 2
+    return np.array(a[cy - h:cy + h, cx - h:cx + h])
+
+
+def map_digest(a, prefix, store):
+    """Compact, tight pin of a 2-D map: centre crop, centre cuts, corner, global sums."""
+    a = np.asarray(a)
+    cy, cx = a.shape[0] // 2, a.shape[1] // 2
+    store[prefix + "_crop"] = crop_center(a)
+    store[prefix + "_row"] = np.array(a[cy, :])
+    store[prefix + "_col"] = np.array(a[:, cx])
+    store[prefix + "_corner"] = np.array(a[:8, :8])
+    store[prefix + "_sum"] = np.asarray(a.sum())
+    store[prefix + "_sumabs2"] = np.asarray((np.abs(a) ** 2).sum())
+
+
+def main():
+    ref = load_reference()
+    sig, met, pre = ref.signal, ref.metrics, ref.preprocessing_normalize
+    os.makedirs(OUT, exist_ok=True)
+    import scipy
+    versions = np.array([np.__version__, scipy.__version__])
+
+    # ---------------- per-frame functions ----------------
+    store = {"versions": versions}
+    for name, img in gc.frame_cases().items():
+        F, fx, fy = sig.fft2d(img)
+        map_digest(F, f"{name}/fft2d", store)
+        store[f"{name}/fft2d_dtype"] = np.array(str(F.dtype))
+        store[f"{name}/fx"] = fx
+        store[f"{name}/fy"] = fy
+        P, _, _ = sig.psd2d(img)
+        map_digest(P, f"{name}/psd2d", store)
+        store[f"{name}/psd2d_dtype"] = np.array(str(P.dtype))
+        if img.shape[0] <= 256 and img.dtype == np.float32:
+            store[f"{name}/psd2d_full"] = np.asarray(P, dtype=np.float32)
+        Pu, _, _ = sig.psd2d(img, dx=0.5, dy=2.0, scale=True)
+        store[f"{name}/psd2d_dx_row"] = np.array(Pu[Pu.shape[0] // 2, :])
+        ac, xl, yl = sig.autocorr2d(img)
+        map_digest(ac, f"{name}/autocorr2d", store)
+        store[f"{name}/autocorr2d_dtype"] = np.array(str(ac.dtype))
+        if img.shape[0] <= 256 and img.dtype == np.float32:
+            store[f"{name}/autocorr2d_full32"] = np.asarray(ac, dtype=np.float32)
+        store[f"{name}/xlag"] = xl
+        store[f"{name}/ylag"] = yl
+        acs, _, _ = sig.autocorr2d(img, remove_mean=True, standardize=True, normalize="none")
+        map_digest(acs, f"{name}/autocorr2d_std_none", store)
+        acr, _, _ = sig.autocorr2d(img, remove_mean=False, standardize=False, normalize="none")
+        map_digest(acr, f"{name}/autocorr2d_raw_none", store)
+        other = np.roll(np.asarray(img), (5, -7), axis=(0, 1))
+        xc, _, _ = sig.xcorr2d(img, other)
+        store[f"{name}/xcorr2d_iscomplex"] = np.array(np.iscomplexobj(xc))
+        map_digest(np.real(xc), f"{name}/xcorr2d_real", store)
+        store[f"{name}/xcorr2d_argmax"] = np.array(np.unravel_index(int(np.argmax(np.abs(xc))), xc.shape))
+
+        for k, v in met.distribution_moments(img).items():
+            store[f"{name}/moments/{k}"] = np.asarray(v)
+        for k, v in met.distribution_moments(img, saturation_value=None, eps=0.5).items():
+            store[f"{name}/moments_nosat/{k}"] = np.asarray(v)
+        for k, v in met.sharpness.tenengrad(img).items():
+            store[f"{name}/tenengrad/{k}"] = np.asarray(v)
+        store[f"{name}/laplacian_variance"] = np.asarray(met.sharpness.laplacian_variance(img))
+        for k, v in met.speckles.amplitude(img).items():
+            store[f"{name}/amplitude/{k}"] = np.asarray(v)
+        store[f"{name}/spectral_entropy"] = np.asarray(met.sharpness.spectral_entropy(img))
+        if min(img.shape) >= 128:
+            g = met.speckles.grain(img)
+            for k in ("lx", "ly", "leq", "r"):
+                store[f"{name}/grain/{k}"] = np.asarray(g[k])
+            map_digest(g["autocorr"], f"{name}/grain/autocorr", store)
+            rad, r = ref.maths.radial.radial_mean_interpolated(g["autocorr"])
+            store[f"{name}/grain/radial"] = rad
+            store[f"{name}/grain/radial_r"] = r
+            for k, v in met.speckles.bandwidth(img).items():
+                store[f"{name}/bandwidth/{k}"] = np.asarray(v)
+            for k, v in met.sharpness.inverse_autocorr_width(img).items():
+                store[f"{name}/inv_ac_width/{k}"] = np.asarray(v)
+
+    nanimg = gc.nan_frame()
+    for k, v in met.distribution_moments(nanimg).items():
+        store[f"nan128/moments/{k}"] = np.asarray(v)
+    for k, v in met.sharpness.tenengrad(nanimg).items():
+        store[f"nan128/tenengrad/{k}"] = np.asarray(v)
+    store["nan128/laplacian_variance"] = np.asarray(met.sharpness.laplacian_variance(nanimg))
+    const = np.full((64, 64), 7.0, dtype=np.float32)
+    for k, v in met.distribution_moments(const).items():
+        store[f"const64/moments/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "frames.npz"), **store)
+
+    # ---------------- aggregator schema (full-frame, tiles off) ----------------
+    store = {"versions": versions}
+    img = gc.frame_cases()["sq256"]
+    sp = met.speckle_stats(img, tiles=False, verbose=False)
+    for grp, d in sp["full"].items():
+        for k, v in d.items():
+            if np.ndim(v) == 0:
+                store[f"speckle_stats/full/{grp}/{k}"] = np.asarray(v)
+    sh = met.sharpness_stats(img, metrics=("stats", "gradient", "laplacian", "spectral", "autocorrelation"),
+                             tiles=False, verbose=False)
+    for grp, d in sh["full"].items():
+        for k, v in d.items():
+            store[f"sharpness_stats/full/{grp}/{k}"] = np.asarray(v)
+    stack = np.stack([gc.frame_cases()["sq256"], gc.frame_cases()["blur256"]], axis=0)
+    shs = met.sharpness_stack_stats(stack, metrics=("stats", "gradient", "laplacian"), tiles=False,
+                                    verbose=False, parallel=False)
+    for grp, d in shs["full"].items():
+        for k, v in d.items():
+            store[f"sharpness_stack_stats/full/{grp}/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "aggregators.npz"), **store)
+
+    # ---------------- tracking ----------------
+    store = {"versions": versions}
+    for name, c in gc.tracking_cases().items():
+        res = sig.phase_correlation(c["template"], c["image"], slices_yx=c["slices"],
+                                    backend="internal", subpixel=c["subpixel"], eps=1e-9)
+        store[f"{name}/result"] = np.asarray(res, dtype=np.float64)
+        res2 = sig.track_translation(c["template"], c["image"], slices_yx=c["slices"], method="phase",
+                                     backend="internal", subpixel=c["subpixel"])
+        assert tuple(res2) == tuple(res)
+    np.savez_compressed(os.path.join(OUT, "tracking.npz"), **store)
+
+    # ---------------- flat field ----------------
+    store = {"versions": versions}
+    raw, flat, dark = gc.flatfield_inputs()
+    for scale in ("flat_median", "flat_mean", "none"):
+        out = pre.flat_field_correction(raw, flats=flat, darks=dark, scale=scale)
+        store[f"ffc/{scale}/frames01"] = out[:2]
+        store[f"ffc/{scale}/sum"] = np.asarray(out.astype(np.float64).sum())
+        store[f"ffc/{scale}/dtype"] = np.array(str(out.dtype))
+    out = pre.flat_field_correction(raw, flats=flat, darks=dark, eps=50.0)
+    store["ffc/eps50/sum"] = np.asarray(out.astype(np.float64).sum())
+    store["ffc/eps50/nzero"] = np.asarray(int((out[0] == 0).sum()))
+    out = pre.flat_field_correction(raw[0], flats=np.stack([flat, flat + 2]), darks=np.stack([dark, dark]))
+    store["ffc/2d_stackflat/frame"] = out
+    out = pre.flat_field_correction(raw, darks=dark)
+    store["ffc/darkonly/sum"] = np.asarray(out.astype(np.float64).sum())
+    out = pre.flat_field_correction(raw, flats=flat)
+    store["ffc/flatonly/sum"] = np.asarray(out.astype(np.float64).sum())
+    np.savez_compressed(os.path.join(OUT, "flatfield.npz"), **store)
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
