@@ -1,0 +1,198 @@
+"""
+ctypes binding of libb4d.so (include/b4d.h) and the device plumbing around it.
+
+PyTorch is used only as plumbing: device memory, streams, pinned host buffers and (elsewhere)
+torch.distributed.  All arithmetic of the hot path happens inside libb4d.so; if the library is
+missing or no CUDA device is present the product fails loudly -- there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb4d.so")
+
+FR_NCOLS = 13
+FR = {"count": 0, "mean": 1, "m2": 2, "m3": 3, "m4": 4, "nzero": 5, "nsat": 6,
+      "sgx2": 7, "sgy2": 8, "slap": 9, "slap2": 10, "npix": 11, "nnan": 12}
+SP_NCOLS = 8
+SP = {"total": 0, "fx2": 1, "fy2": 2, "p2": 3, "all": 4, "plogp": 5, "f95": 6}
+FFT_MIN, FFT_MAX = 32, 2048
+
+
+class B4DError(RuntimeError):
+    pass
+
+
+class B4DUnsupported(NotImplementedError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_vp, _i64, _i32, _f32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/b4d.h one to one
+_SIGNATURES = {
+    "b4d_create": [_i32, C.POINTER(_vp)],
+    "b4d_destroy": [_vp],
+    "b4d_set_stream": [_vp, _vp],
+    "b4d_synchronize": [_vp],
+    "b4d_last_error": [_vp],
+    "b4d_version": [],
+    "b4d_launch_count": [_vp],
+    "b4d_device_sm_count": [_vp],
+    "b4d_malloc": [_vp, C.c_size_t, C.POINTER(_vp)],
+    "b4d_free": [_vp, _vp],
+    "b4d_memcpy_h2d": [_vp, _vp, _vp, C.c_size_t],
+    "b4d_memcpy_d2h": [_vp, _vp, _vp, C.c_size_t],
+    "b4d_frame_reductions": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _vp],
+    "b4d_select_ranks": [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp],
+    "b4d_flat_field": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _i32, _vp],
+    "b4d_flat_gain": [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp],
+    "b4d_sub": [_vp, _vp, _vp, _i64, _vp],
+    "b4d_temporal_accumulate": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
+    "b4d_temporal_pilot": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
+    "b4d_temporal_finalize": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "b4d_fft2d": [_vp, _vp, _i64, _i32, _i32, _vp],
+    "b4d_psd2d": [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp, _vp],
+    "b4d_autocorr2d": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _f64, _vp],
+    "b4d_xcorr2d": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
+    "b4d_phase_set_reference": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64],
+    "b4d_phase_track": [_vp, _vp, _i64, _i32, _i32, _i32, _f64, _vp],
+    "b4d_stack_pipeline": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64,
+                           _vp, _vp, _vp, _vp, _vp],
+}
+_RESTYPES = {"b4d_last_error": C.c_char_p, "b4d_version": C.c_char_p, "b4d_launch_count": _i64}
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen libb4d.so and attach the prototypes.  Raises B4DError when the library is absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise B4DError(
+                f"{p} not found: build it with `python -m barc4dip_b200.build` "
+                "(nvcc, sm_100a). barc4dip_b200 has no CPU fallback.")
+        lib = C.CDLL(p)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header/library drift
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, _i32)
+        if path is None:
+            _lib = lib
+        return lib
+
+
+class Context:
+    """One libb4d context = (device, stream, scratch).  Calls on one context are serialised."""
+
+    def __init__(self, device: int):
+        self.lib = load_library()
+        self.device = int(device)
+        h = _vp()
+        rc = self.lib.b4d_create(self.device, C.byref(h))
+        if rc != 0 or not h.value:
+            raise B4DError(f"b4d_create(device={device}) failed with status {rc} "
+                           "(is a CUDA device visible?)")
+        self.handle = h
+
+    def check(self, rc: int, what: str = ""):
+        if rc == 0:
+            return
+        msg = self.lib.b4d_last_error(self.handle)
+        text = msg.decode() if msg else ""
+        if rc == -3:
+            raise B4DUnsupported(f"{what}: {text}")
+        if rc == -1:
+            raise ValueError(f"{what}: {text}")
+        raise B4DError(f"{what} failed (status {rc}): {text}")
+
+    def use_current_stream(self):
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.check(self.lib.b4d_set_stream(self.handle, _vp(s)), "b4d_set_stream")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.b4d_launch_count(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and self.handle.value:
+                self.lib.b4d_destroy(self.handle)
+                self.handle = _vp()
+        except Exception:
+            pass
+
+
+_contexts: dict[int, Context] = {}
+_ctx_lock = threading.Lock()
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise B4DError("barc4dip_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                       "there is no CPU fallback on this path.")
+    return torch
+
+
+def default_device() -> int:
+    """Device index: $B4D_DEVICE, else $LOCAL_RANK (torchrun), else the current torch device."""
+    torch = require_cuda()
+    env = os.environ.get("B4D_DEVICE")
+    if env is not None:
+        return int(env)
+    return torch.cuda.current_device()
+
+
+def get_context(device: int | None = None) -> Context:
+    require_cuda()
+    dev = default_device() if device is None else int(device)
+    with _ctx_lock:
+        ctx = _contexts.get(dev)
+        if ctx is None:
+            ctx = Context(dev)
+            _contexts[dev] = ctx
+    ctx.use_current_stream()
+    return ctx
+
+
+def ptr(t) -> _vp:
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return _vp(0)
+    return _vp(t.data_ptr())
+
+
+def as_device_f32(a, device: int | None = None):
+    """numpy array / torch tensor -> contiguous float32 CUDA tensor (H2D copy when given host data)."""
+    torch = require_cuda()
+    dev = default_device() if device is None else int(device)
+    if isinstance(a, torch.Tensor):
+        t = a
+        if t.device.type != "cuda":
+            t = t.to(f"cuda:{dev}", non_blocking=True)
+        if t.dtype != torch.float32:
+            t = t.to(torch.float32)
+        return t.contiguous()
+    arr = np.asarray(a)
+    if arr.dtype == np.float32:
+        src = np.ascontiguousarray(arr)
+    else:
+        src = np.ascontiguousarray(arr, dtype=np.float32)
+    return torch.from_numpy(src).to(f"cuda:{dev}", non_blocking=False)

@@ -1,0 +1,78 @@
+// Context management and plain memory helpers of the C ABI (include/b4d.h).
+#include "common.cuh"
+
+void b4d_fft_release(b4d_ctx* ctx);   // fft.cu
+
+extern "C" const char* b4d_version(void) { return "barc4dip_b200 0.1 (sm_100a)"; }
+
+extern "C" int b4d_create(int device, b4d_ctx** out) {
+    if (!out) return B4D_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) return B4D_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return B4D_ERR_CUDA;
+    b4d_ctx* c = new (std::nothrow) b4d_ctx();
+    if (!c) return B4D_ERR_NOMEM;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return B4D_OK;
+}
+
+extern "C" int b4d_destroy(b4d_ctx* ctx) {
+    if (!ctx) return B4D_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    b4d_fft_release(ctx);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    delete ctx;
+    return B4D_OK;
+}
+
+extern "C" int b4d_set_stream(b4d_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return B4D_OK;
+}
+
+extern "C" int b4d_synchronize(b4d_ctx* ctx) {
+    if (!ctx) return B4D_ERR_INVALID;
+    B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B4D_OK;
+}
+
+extern "C" const char* b4d_last_error(b4d_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int64_t b4d_launch_count(b4d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int b4d_device_sm_count(b4d_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return B4D_ERR_INVALID;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) return b4d_fail(ctx, B4D_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return B4D_OK;
+}
+
+extern "C" int b4d_free(b4d_ctx* ctx, void* p) {
+    if (!ctx) return B4D_ERR_INVALID;
+    B4D_CUDA(ctx, cudaFree(p));
+    return B4D_OK;
+}
+
+extern "C" int b4d_memcpy_h2d(b4d_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
+    if (!ctx || !dst || !src_host) return B4D_ERR_INVALID;
+    B4D_CUDA(ctx, cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B4D_OK;
+}
+
+extern "C" int b4d_memcpy_d2h(b4d_ctx* ctx, void* dst_host, const void* src, size_t bytes) {
+    if (!ctx || !dst_host || !src) return B4D_ERR_INVALID;
+    B4D_CUDA(ctx, cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B4D_OK;
+}

@@ -1,0 +1,118 @@
+// Shared infrastructure of libb4d.so: context, error plumbing, warp/block reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b4d.h"
+
+struct FftPlanCache;   // fft.cu
+
+struct b4d_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+    // grow-only scratch arenas (device)
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    FftPlanCache* fft = nullptr;
+    std::mutex lock;
+};
+
+// scratch slot ids
+enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7 };
+
+inline int b4d_fail(b4d_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->last_error = buf;
+    }
+    return code;
+}
+
+#define B4D_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return b4d_fail((ctx), B4D_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,     \
+                            __LINE__, cudaGetErrorString(_e));                                   \
+    } while (0)
+
+#define B4D_LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            return b4d_fail((ctx), B4D_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, \
+                            __LINE__, cudaGetErrorString(_e));                                   \
+    } while (0)
+
+// Returns a device scratch buffer of at least `bytes` bytes (grow-only, stream-ordered reuse).
+inline int b4d_scratch(b4d_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            B4D_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess)
+            return b4d_fail(ctx, B4D_ERR_NOMEM, "cudaMalloc(%zu) for scratch slot %d: %s", want, slot,
+                            cudaGetErrorString(e));
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return B4D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (read-once data)
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,308 @@
+"""
+Stack-level entry points: thin, typed wrappers over the C ABI that work on HBM-resident stacks.
+
+Every function takes a (T, ny, nx) float32 CUDA tensor (``as_stack`` uploads numpy input once)
+and returns either small numpy tables (one row per frame) or CUDA tensors for maps, so that
+stacks and maps stay in HBM between stages.  The per-frame drop-in functions in
+``barc4dip_b200.signal`` / ``.metrics`` / ``.preprocessing`` are T = 1 calls of these.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import FR, FR_NCOLS, SP, SP_NCOLS, get_context, ptr, require_cuda
+
+__all__ = [
+    "as_stack", "frame_reductions", "select_quantiles", "flat_field", "flat_gain",
+    "temporal_moments", "TemporalAccumulator", "fft2d", "psd2d", "autocorr2d", "xcorr2d",
+    "PhaseTracker", "stack_pipeline", "check_fft_shape",
+]
+
+
+def as_stack(a, device: int | None = None):
+    """(ny, nx) or (T, ny, nx) array-like -> contiguous float32 CUDA tensor of shape (T, ny, nx)."""
+    t = _lib.as_device_f32(a, device)
+    if t.ndim == 2:
+        t = t.unsqueeze(0)
+    if t.ndim != 3:
+        raise ValueError(f"expected a 2D frame or a 3D stack, got ndim={t.ndim}")
+    return t
+
+
+def _dev(t) -> int:
+    return t.device.index if t.device.index is not None else 0
+
+
+def check_fft_shape(ny: int, nx: int):
+    for n in (ny, nx):
+        if n < _lib.FFT_MIN or n > _lib.FFT_MAX or (n & (n - 1)) != 0:
+            raise _lib.B4DUnsupported(
+                f"the sm_100a FFT kernels cover power-of-two sides in [{_lib.FFT_MIN}, {_lib.FFT_MAX}]; "
+                f"got (ny, nx) = ({ny}, {nx}). There is no CPU fallback on this path.")
+
+
+# ------------------------------------------------------------------------------------------
+# reductions / selection
+# ------------------------------------------------------------------------------------------
+
+def frame_reductions(stack, *, gain=None, dark=None, saturation_value: float | None = 65535.0,
+                     eps: float = 1e-6, return_device: bool = False):
+    """Per-frame single-pass reductions -> float64 table (T, FR_NCOLS) (columns: ``_lib.FR``)."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=stack.device)
+    sat = float("nan") if saturation_value is None else float(saturation_value)
+    ctx.check(ctx.lib.b4d_frame_reductions(ctx.handle, ptr(stack), T, ny, nx, ptr(gain), ptr(dark),
+                                           sat, float(eps), ptr(out)), "b4d_frame_reductions")
+    return out if return_device else out.cpu().numpy()
+
+
+def select_quantiles(stack, quantiles, *, use_abs: bool = False, return_device: bool = False):
+    """Exact order statistics bracketing each quantile.
+
+    Returns (values (T, 2*len(q)) float32, n_valid (T,) int64): for quantile q the two columns hold
+    sorted[floor(h)] and sorted[min(floor(h)+1, n-1)] with h = numpy's 'linear' virtual index.
+    """
+    torch = require_cuda()
+    T = stack.shape[0]
+    n = int(np.prod(stack.shape[1:]))
+    q = np.ascontiguousarray(np.asarray(quantiles, dtype=np.float64).ravel())
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, 2 * q.size), dtype=torch.float32, device=stack.device)
+    nv = torch.empty((T,), dtype=torch.int64, device=stack.device)
+    ctx.check(ctx.lib.b4d_select_ranks(ctx.handle, ptr(stack), T, n, q.ctypes.data_as(C.c_void_p), int(q.size),
+                                       int(bool(use_abs)), ptr(out), ptr(nv)), "b4d_select_ranks")
+    if return_device:
+        return out, nv
+    return out.cpu().numpy(), nv.cpu().numpy()
+
+
+def virtual_index(n: int, q: float) -> float:
+    """numpy's 'linear' quantile index, same expression as numpy (and as the device code)."""
+    return n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0
+
+
+def lerp_like_numpy(a: float, b: float, t: float) -> float:
+    """numpy.lib._function_base_impl._lerp: a + (b-a)t, switched to b - (b-a)(1-t) for t >= 0.5."""
+    d = b - a
+    return b - d * (1.0 - t) if t >= 0.5 else a + d * t
+
+
+def quantile_from_bracket(lo: float, hi: float, n: int, q: float) -> float:
+    h = virtual_index(n, q)
+    g = h - math.floor(h)
+    return lerp_like_numpy(float(lo), float(hi), g)
+
+
+# ------------------------------------------------------------------------------------------
+# flat field / temporal moments
+# ------------------------------------------------------------------------------------------
+
+def flat_gain(flat, dark, *, eps: float, scale_value: float):
+    torch = require_cuda()
+    ny, nx = flat.shape[-2:]
+    ctx = get_context(_dev(flat))
+    gain = torch.empty((ny, nx), dtype=torch.float32, device=flat.device)
+    ctx.check(ctx.lib.b4d_flat_gain(ctx.handle, ptr(flat), ptr(dark), ny, nx, float(eps), float(scale_value),
+                                    ptr(gain)), "b4d_flat_gain")
+    return gain
+
+
+def flat_field(stack, flat, dark, *, eps: float, scale_value: float, apply_scale: bool):
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    ctx = get_context(_dev(stack))
+    out = torch.empty_like(stack)
+    ctx.check(ctx.lib.b4d_flat_field(ctx.handle, ptr(stack), T, ny, nx, ptr(flat), ptr(dark), float(eps),
+                                     float(scale_value), int(bool(apply_scale)), ptr(out)), "b4d_flat_field")
+    return out
+
+
+def sub(a, b):
+    torch = require_cuda()
+    ctx = get_context(_dev(a))
+    out = torch.empty_like(a)
+    ctx.check(ctx.lib.b4d_sub(ctx.handle, ptr(a), ptr(b), a.numel(), ptr(out)), "b4d_sub")
+    return out
+
+
+class TemporalAccumulator:
+    """Streaming per-pixel moments over time; chunks may arrive one at a time (HBM-sized stacks).
+
+    ``shift`` must be identical on every rank when the sums are all-reduced (see parallel.py).
+    """
+
+    def __init__(self, ny: int, nx: int, *, device: int | None = None, gain=None, dark=None, shift=None):
+        torch = require_cuda()
+        self.dev = _lib.default_device() if device is None else int(device)
+        self.ny, self.nx = int(ny), int(nx)
+        self.gain, self.dark = gain, dark
+        self.sums = torch.zeros((4, ny, nx), dtype=torch.float64, device=f"cuda:{self.dev}")
+        self.shift = shift
+        self.count = 0
+
+    def pilot(self, stack, n_frames: int = 16):
+        """Set the shift map to the mean of the first n_frames (corrected) frames of ``stack``."""
+        torch = require_cuda()
+        ctx = get_context(self.dev)
+        n = min(int(n_frames), stack.shape[0])
+        self.shift = torch.empty((self.ny, self.nx), dtype=torch.float32, device=stack.device)
+        ctx.check(ctx.lib.b4d_temporal_pilot(ctx.handle, ptr(stack), n, self.ny, self.nx, ptr(self.gain),
+                                             ptr(self.dark), ptr(self.shift)), "b4d_temporal_pilot")
+        return self.shift
+
+    def update(self, stack):
+        if self.shift is None:
+            self.pilot(stack)
+        T, ny, nx = stack.shape
+        if (ny, nx) != (self.ny, self.nx):
+            raise ValueError("frame shape mismatch")
+        ctx = get_context(self.dev)
+        ctx.check(ctx.lib.b4d_temporal_accumulate(ctx.handle, ptr(stack), T, ny, nx, ptr(self.gain), ptr(self.dark),
+                                                  ptr(self.shift), ptr(self.sums)), "b4d_temporal_accumulate")
+        self.count += int(T)
+
+    def finalize(self, n_total: int | None = None, return_device: bool = False):
+        torch = require_cuda()
+        n = self.count if n_total is None else int(n_total)
+        ctx = get_context(self.dev)
+        maps = torch.empty((5, self.ny, self.nx), dtype=torch.float64, device=self.sums.device)
+        ctx.check(ctx.lib.b4d_temporal_finalize(ctx.handle, ptr(self.sums), ptr(self.shift), n, self.ny, self.nx,
+                                                ptr(maps)), "b4d_temporal_finalize")
+        if return_device:
+            return maps
+        m = maps.cpu().numpy()
+        return {"mean": m[0], "std": m[1], "variance": m[2], "skewness": m[3], "kurtosis": m[4]}
+
+
+def temporal_moments(stack, *, gain=None, dark=None, return_device: bool = False):
+    """Per-pixel mean/std/variance/skewness/kurtosis over axis 0 of an HBM-resident stack."""
+    T, ny, nx = stack.shape
+    acc = TemporalAccumulator(ny, nx, device=_dev(stack), gain=gain, dark=dark)
+    acc.update(stack)
+    return acc.finalize(return_device=return_device)
+
+
+# ------------------------------------------------------------------------------------------
+# FFT family
+# ------------------------------------------------------------------------------------------
+
+def fft2d(stack):
+    """fftshift(fft2(frame)) for every frame -> complex64 CUDA tensor (T, ny, nx)."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    check_fft_shape(ny, nx)
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, ny, nx, 2), dtype=torch.float32, device=stack.device)
+    ctx.check(ctx.lib.b4d_fft2d(ctx.handle, ptr(stack), T, ny, nx, ptr(out)), "b4d_fft2d")
+    return torch.view_as_complex(out)
+
+
+def psd2d(stack, *, scale_factor: float = 1.0, sub_mean: bool = False, zero_dc: bool = False,
+          want_map: bool = True, want_spectral: bool = False):
+    """Shifted |FFT|^2 * scale_factor per frame. Returns (psd or None, spectral table or None)."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    check_fft_shape(ny, nx)
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, ny, nx), dtype=torch.float32, device=stack.device) if want_map else None
+    spec = torch.zeros((T, SP_NCOLS), dtype=torch.float64, device=stack.device) if want_spectral else None
+    ctx.check(ctx.lib.b4d_psd2d(ctx.handle, ptr(stack), T, ny, nx, float(scale_factor), int(bool(sub_mean)),
+                                int(bool(zero_dc)), ptr(out), ptr(spec)), "b4d_psd2d")
+    return out, (spec.cpu().numpy() if spec is not None else None)
+
+
+def autocorr2d(stack, *, remove_mean: bool = True, standardize: bool = False, normalize_peak: bool = True,
+               want_map: bool = True, want_grain: bool = False, fraction: float = 1.0 / math.e):
+    """Shifted circular autocorrelation per frame (+ optional grain widths table (T, 4))."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    check_fft_shape(ny, nx)
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, ny, nx), dtype=torch.float32, device=stack.device) if want_map else None
+    grain = torch.empty((T, 4), dtype=torch.float64, device=stack.device) if want_grain else None
+    ctx.check(ctx.lib.b4d_autocorr2d(ctx.handle, ptr(stack), T, ny, nx, int(bool(remove_mean)),
+                                     int(bool(standardize)), int(bool(normalize_peak)), ptr(out), float(fraction),
+                                     ptr(grain)), "b4d_autocorr2d")
+    return out, (grain.cpu().numpy() if grain is not None else None)
+
+
+def xcorr2d(a, b, *, remove_mean: bool = True, standardize: bool = False, normalize_peak: bool = True):
+    torch = require_cuda()
+    T, ny, nx = a.shape
+    if tuple(b.shape) != (T, ny, nx):
+        raise ValueError("a and b must have the same shape.")
+    check_fft_shape(ny, nx)
+    ctx = get_context(_dev(a))
+    out = torch.empty((T, ny, nx), dtype=torch.float32, device=a.device)
+    ctx.check(ctx.lib.b4d_xcorr2d(ctx.handle, ptr(a), ptr(b), T, ny, nx, int(bool(remove_mean)),
+                                  int(bool(standardize)), int(bool(normalize_peak)), ptr(out)), "b4d_xcorr2d")
+    return out
+
+
+class PhaseTracker:
+    """Phase-correlation tracker bound to one reference template (cached as a conjugate spectrum)."""
+
+    def __init__(self, template, frame_shape, *, y0: int, x0: int, eps: float = 1e-9, device: int | None = None):
+        self.dev = _lib.default_device() if device is None else int(device)
+        self.ny, self.nx = int(frame_shape[0]), int(frame_shape[1])
+        check_fft_shape(self.ny, self.nx)
+        tpl = _lib.as_device_f32(template, self.dev)
+        if tpl.ndim != 2:
+            raise ValueError("template must be a 2D array.")
+        h, w = tpl.shape
+        if y0 < 0 or x0 < 0 or y0 + h > self.ny or x0 + w > self.nx:
+            raise ValueError("ROI exceeds image bounds.")
+        self.eps = float(eps)
+        ctx = get_context(self.dev)
+        ctx.check(ctx.lib.b4d_phase_set_reference(ctx.handle, ptr(tpl), h, w, self.ny, self.nx, int(y0), int(x0),
+                                                  self.eps), "b4d_phase_set_reference")
+
+    def track(self, stack, *, subpixel: bool = True, return_device: bool = False):
+        """(T, ny, nx) stack -> float64 table (T, 4) = dy, dx, peak, snr."""
+        torch = require_cuda()
+        T, ny, nx = stack.shape
+        if (ny, nx) != (self.ny, self.nx):
+            raise ValueError("frame shape differs from the tracker's reference frame shape")
+        ctx = get_context(self.dev)
+        out = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
+        ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(stack), T, ny, nx, int(bool(subpixel)), self.eps,
+                                          ptr(out)), "b4d_phase_track")
+        return out if return_device else out.cpu().numpy()
+
+
+def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | None = 65535.0, eps: float = 1e-6,
+                   psd_scale: float | None = None, subpixel: bool = True, track_eps: float = 1e-9,
+                   want_reductions: bool = True, want_psd: bool = True, want_autocorr: bool = True,
+                   want_grain: bool = True, want_tracking: bool = True, psd_out=None, ac_out=None):
+    """The fused north-star pass over an HBM-resident stack (see b4d_stack_pipeline in include/b4d.h).
+
+    Tracking uses the reference most recently installed by a PhaseTracker on the same device.
+    Returns a dict with device tensors: reductions (T, FR_NCOLS), psd, autocorr, grain (T,4), tracking (T,4).
+    """
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    check_fft_shape(ny, nx)
+    ctx = get_context(_dev(stack))
+    dev = stack.device
+    fr = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=dev) if want_reductions else None
+    if want_psd and psd_out is None:
+        psd_out = torch.empty((T, ny, nx), dtype=torch.float32, device=dev)
+    if want_autocorr and ac_out is None:
+        ac_out = torch.empty((T, ny, nx), dtype=torch.float32, device=dev)
+    grain = torch.empty((T, 4), dtype=torch.float64, device=dev) if want_grain else None
+    track = torch.empty((T, 4), dtype=torch.float64, device=dev) if want_tracking else None
+    sat = float("nan") if saturation_value is None else float(saturation_value)
+    scale = (1.0 / (float(nx) * float(ny))) if psd_scale is None else float(psd_scale)
+    ctx.check(ctx.lib.b4d_stack_pipeline(ctx.handle, ptr(stack), T, ny, nx, ptr(gain), ptr(dark), sat, float(eps),
+                                         scale, int(bool(subpixel)), float(track_eps), ptr(fr),
+                                         ptr(psd_out if want_psd else None), ptr(ac_out if want_autocorr else None),
+                                         ptr(grain), ptr(track)), "b4d_stack_pipeline")
+    return {"reductions": fr, "psd": psd_out if want_psd else None, "autocorr": ac_out if want_autocorr else None,
+            "grain": grain, "tracking": track}

@@ -1,0 +1,215 @@
+/*
+ * b4d.h -- C ABI of libb4d.so, the B200 (sm_100a) implementation of the barc4dip
+ * stack-analysis hot path.
+ *
+ * The reference (barc4dip, pure Python) has no FFI: its boundary for this path is the set of
+ * Python functions listed in SURVEY.md 8(b).  Each entry point below names the reference
+ * function(s) whose arithmetic it replaces (file:line under src/barc4dip/); the thin Python
+ * package `barc4dip_b200` binds them with ctypes and keeps the reference's signatures.
+ * INTEGRATION.md shows the binding a barc4dip maintainer would add.
+ *
+ * Conventions
+ *   - every array argument is a DEVICE pointer to contiguous, C-ordered data unless the name
+ *     ends in _host; frames are float32 (ny, nx), stacks float32 (T, ny, nx);
+ *   - scalar result tables are float64, one row per frame;
+ *   - the caller allocates all outputs; the context owns only scratch (twiddles, work buffers);
+ *   - every call is asynchronous on the context's stream (b4d_set_stream), except the ones
+ *     documented as synchronising;
+ *   - return value: 0 = ok, negative = error (b4d_status); text via b4d_last_error().
+ *     No C++ exception crosses this boundary.
+ */
+#ifndef B4D_H
+#define B4D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b4d_ctx b4d_ctx;
+
+typedef enum b4d_status {
+    B4D_OK = 0,
+    B4D_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported size) */
+    B4D_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    B4D_ERR_UNSUPPORTED = -3, /* size/feature outside what the sm_100a kernels cover */
+    B4D_ERR_NOMEM = -4
+} b4d_status;
+
+/* ---- context -------------------------------------------------------------------------- */
+int b4d_create(int device, b4d_ctx** out);
+int b4d_destroy(b4d_ctx* ctx);
+/* cudaStream_t to launch on (0 = legacy default stream). */
+int b4d_set_stream(b4d_ctx* ctx, void* cuda_stream);
+int b4d_synchronize(b4d_ctx* ctx);
+const char* b4d_last_error(b4d_ctx* ctx);
+const char* b4d_version(void);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t b4d_launch_count(b4d_ctx* ctx);
+int b4d_device_sm_count(b4d_ctx* ctx);
+
+/* Plain device-memory helpers so that a non-Python host can drive the library. */
+int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out);
+int b4d_free(b4d_ctx* ctx, void* p);
+int b4d_memcpy_h2d(b4d_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+int b4d_memcpy_d2h(b4d_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
+
+/* ---- per-frame single-pass reductions ------------------------------------------------- */
+/*
+ * One streaming pass per frame producing everything the reference's scalar metrics need:
+ *   distribution_moments      metrics/statistics.py:17-125
+ *   tenengrad                 metrics/sharpness.py:405-476  (scipy.ndimage.sobel, mode="reflect")
+ *   laplacian_variance        metrics/sharpness.py:482-530  (scipy.ndimage.laplace, mode="reflect")
+ *   amplitude (visibility)    metrics/speckles.py:636-645   (nanmean / nanstd)
+ * Optional fused flat field: if gain != NULL the pixel fed to the metrics is
+ * (raw - dark) * gain  (gain = scale/(flat-dark), 0 on bad pixels; preprocessing/normalize.py:104-131).
+ *
+ * out: T rows of B4D_FR_NCOLS doubles, columns B4D_FR_*.
+ */
+enum {
+    B4D_FR_COUNT = 0,   /* number of finite pixels                         */
+    B4D_FR_MEAN = 1,    /* mean over finite pixels                          */
+    B4D_FR_M2 = 2,      /* central moments (biased): variance               */
+    B4D_FR_M3 = 3,
+    B4D_FR_M4 = 4,
+    B4D_FR_NZERO = 5,   /* #finite pixels with |x| <= zero_eps              */
+    B4D_FR_NSAT = 6,    /* #finite pixels with x >= sat_value (0 if NaN)    */
+    B4D_FR_SGX2 = 7,    /* sum over finite pixels of sobel_x^2              */
+    B4D_FR_SGY2 = 8,
+    B4D_FR_SLAP = 9,    /* sum / sum of squares of the 5-point Laplacian    */
+    B4D_FR_SLAP2 = 10,
+    B4D_FR_NPIX = 11,   /* ny*nx                                            */
+    B4D_FR_NNAN = 12,   /* number of NaN pixels (infinities = NPIX - COUNT - NNAN) */
+    B4D_FR_NCOLS = 13
+};
+int b4d_frame_reductions(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                         const float* gain, const float* dark,
+                         double sat_value, double zero_eps, double* out);
+
+/* ---- exact order statistics ------------------------------------------------------------ */
+/*
+ * For each frame, the k-th smallest finite value (0-based ranks, ascending) for every k in
+ * ranks[0..n_ranks) -- the primitive behind np.nanpercentile (utils/range.py:44-54, used by
+ * amplitude, metrics/speckles.py:647) and np.median (signal/tracking.py:319,
+ * preprocessing/normalize.py:110,126).  NaNs are excluded as in nanpercentile; n_valid[t] gets the
+ * number of non-NaN values so that the host can place the fractional rank.
+ *   ranks: HOST array of n_ranks int64 (ranks are clamped to [0, n_valid-1] per frame);
+ *   if ranks_from_quantiles != NULL (HOST, n_ranks doubles in [0,1]) ranks are derived per frame
+ *   as floor(q*(n_valid-1)) and floor(q*(n_valid-1))+1 -> out has 2*n_ranks columns.
+ *   out: DEVICE float32 (n_frames, n_cols); n_valid: DEVICE int64 (n_frames) or NULL.
+ */
+int b4d_select_ranks(b4d_ctx* ctx, const float* stack, int64_t n_frames, int64_t frame_elems,
+                     const double* quantiles_host, int n_q, int use_abs,
+                     float* out, int64_t* n_valid);
+
+/* ---- flat field ------------------------------------------------------------------------ */
+/*
+ * flat_field_correction, preprocessing/normalize.py:12-145 (without the median repair):
+ *   out = ((img - dark) / den_safe) * scale ; out[bad] = 0,   bad = (flat - dark) <= eps.
+ * Same float32 operation order as the reference, so the result is bit-identical.
+ * dark may be NULL (zeros); scale_value is the already-resolved multiplier (1.0 for scale="none").
+ */
+int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frames, int ny, int nx,
+                   const float* flat, const float* dark, float eps, float scale_value,
+                   int apply_scale, float* out);
+/* gain[p] = bad ? 0 : scale/(flat-dark): the per-pixel multiplier the fused loaders use. */
+int b4d_flat_gain(b4d_ctx* ctx, const float* flat, const float* dark, int ny, int nx,
+                  float eps, float scale_value, float* gain);
+/* den = flat - dark and its count of valid (den > eps) pixels (helper for the medians). */
+int b4d_sub(b4d_ctx* ctx, const float* a, const float* b, int64_t n, float* out);
+
+/* ---- per-pixel temporal moments (lifts statistics.py:75-81 along t) - */
+/*
+ * Accumulate shifted power sums  S_k(p) += sum_t (x_t(p) - shift(p))^k , k = 1..4, over the
+ * n_frames given.  sums: DEVICE float64 (4, ny, nx), caller-zeroed before the first chunk;
+ * shift: DEVICE float32 (ny, nx), identical on every rank so that sums add across GPUs.
+ * Optional fused flat field as in b4d_frame_reductions.
+ */
+int b4d_temporal_accumulate(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                            const float* gain, const float* dark, const float* shift, double* sums);
+/* shift(p) = mean over the first n_frames frames of the (corrected) pixel: a pilot estimate. */
+int b4d_temporal_pilot(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                       const float* gain, const float* dark, float* shift);
+/* maps: DEVICE float64 (5, ny, nx) = mean, std, variance, skewness, excess kurtosis. */
+int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, int64_t n_total,
+                          int ny, int nx, double* maps);
+
+/* ---- 2-D FFT family ---------------------------------------------------------------------- */
+/*
+ * Supported frame sizes: ny, nx powers of two in [B4D_FFT_MIN, B4D_FFT_MAX].  Anything else
+ * returns B4D_ERR_UNSUPPORTED (the Python layer raises; there is no CPU fallback).
+ */
+#define B4D_FFT_MIN 32
+#define B4D_FFT_MAX 2048
+
+/* fft2d (signal/fft.py:198-237): out = fftshift(fft2(frame)), complex64 interleaved (ny, nx). */
+int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64);
+
+/*
+ * psd2d (signal/fft.py:261-309): out = |fftshift(fft2(frame - sub))|^2 * scale_factor, float32.
+ * sub_mean != 0 subtracts the frame mean first (bandwidth / spectral_entropy call sites,
+ * metrics/speckles.py:744-748, metrics/sharpness.py:593-596); zero_dc != 0 clears the DC bin.
+ * spectral (nullable): DEVICE float64 (n_frames, B4D_SP_NCOLS) sums for bandwidth()/spectral_entropy().
+ */
+enum {
+    B4D_SP_TOTAL = 0,   /* sum P                 over FR <= f_max (DC excluded)          */
+    B4D_SP_FX2 = 1,     /* sum fx^2 P            (fx, fy in cycles/pixel)                */
+    B4D_SP_FY2 = 2,
+    B4D_SP_P2 = 3,      /* sum P^2               over the same mask                      */
+    B4D_SP_ALL = 4,     /* sum P                 over all bins except DC                 */
+    B4D_SP_PLOGP = 5,   /* sum P ln P            over all bins except DC (P > 0)         */
+    B4D_SP_F95 = 6,     /* radius (cycles/pixel) where the radius-sorted cumulative PSD first reaches 0.95 */
+    B4D_SP_NCOLS = 8
+};
+int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+              float scale_factor, int sub_mean, int zero_dc, float* out_psd, double* spectral);
+
+/*
+ * autocorr2d (signal/corr.py:256-320 via xcorr2d :169-253) of each frame, float32 output:
+ *   remove_mean / standardize / normalize_peak as in the reference; zero lag at (ny//2, nx//2).
+ * grain_out (nullable): DEVICE float64 (n_frames, 4) = lx, ly, leq, lx/ly computed from the map
+ *   exactly as grain() does (metrics/speckles.py:546-575, maths/stats.py:9-155, maths/radial.py:101-169)
+ *   with threshold `fraction`.
+ * out_ac may be NULL when only grain_out is wanted (the map then lives in scratch).
+ */
+int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                   int remove_mean, int standardize, int normalize_peak,
+                   float* out_ac, double fraction, double* grain_out);
+
+/* xcorr2d (signal/corr.py:169-253) of frame pairs (a[t], b[t]); real float32 output. */
+int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx,
+                int remove_mean, int standardize, int normalize_peak, float* out);
+
+/*
+ * phase_correlation, backend="internal" (signal/tracking.py:192-297, helpers :299-375).
+ * b4d_phase_set_reference z-scores the (h, w) template over its own pixels, embeds it at
+ * (y0, x0) in a zero (ny, nx) frame and caches conj(FFT) in the context.
+ * b4d_phase_track correlates every frame of the stack against it:
+ *   out: DEVICE float64 (n_frames, 4) = dy, dx, peak, snr  (sub-pixel terms applied -- with the
+ *   reference's swapped order -- when subpixel != 0).
+ */
+int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx,
+                            int y0, int x0, double eps);
+int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                    int subpixel, double eps, double* out);
+
+/*
+ * The fused stack pass of the north-star pipeline: one read of every frame produces
+ *   fr_out   (n_frames, B4D_FR_NCOLS)  frame reductions           (nullable)
+ *   psd_out  (n_frames, ny, nx)        psd2d                      (nullable)
+ *   ac_out   (n_frames, ny, nx)        autocorr2d (defaults)      (nullable)
+ *   grain_out(n_frames, 4)             grain widths               (nullable, needs autocorr)
+ *   track_out(n_frames, 4)             phase correlation vs the cached reference (nullable)
+ */
+int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                       const float* gain, const float* dark,
+                       double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
+                       double* fr_out, float* psd_out, float* ac_out, double* grain_out,
+                       double* track_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B4D_H */
