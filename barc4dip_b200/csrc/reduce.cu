@@ -297,6 +297,9 @@ float float_at_least(double v) {
 
 }  // namespace
 
+int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                                const float* dark, double sat_value, double zero_eps, double* out);
+
 int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
                            const float* dark, float* pilot) {
     pilot_kernel<<<(unsigned)T, 256, 0, ctx->stream>>>(stack, gain, dark, npix, pilot);
@@ -309,6 +312,11 @@ extern "C" int b4d_frame_reductions(b4d_ctx* ctx, const float* stack, int64_t n_
                                     double* out) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
+    return b4d_frame_reductions_nolock(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out);
+}
+
+int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                                const float* dark, double sat_value, double zero_eps, double* out) {
     if (!stack || !out || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: bad arguments (T=%lld ny=%d nx=%d)",
                         (long long)n_frames, ny, nx);

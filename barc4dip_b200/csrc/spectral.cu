@@ -1,0 +1,1353 @@
+// The 2-D FFT family: batched real 2-D FFT with fused PSD / autocorrelation / phase-correlation
+// epilogues (signal/fft.py, signal/corr.py, signal/tracking.py of the reference).
+//
+// Decomposition of one (ny, nx) real frame (all transforms in-CTA, see fft.cuh):
+//   K1 rows_fwd : rows are paired (z = row_a + i row_b), one complex FFT per pair, split into the
+//                 two half spectra (kx = 0..nx/2-1, Nyquist packed into Im of kx = 0), written to
+//                 a blocked intermediate H[kx/8][y][kx%8] so that K2 reads contiguous 64 B runs.
+//   K2 cols     : a CTA owns 8 adjacent kx columns (all ky): FFT along y, then fused epilogues
+//                 - |F|^2 * scale with fftshift + Hermitian mirror stores (psd2d), spectral sums;
+//                 - complex spectrum out (fft2d) or conj spectrum to the blocked layout (reference
+//                   spectrum of the tracker / second operand of xcorr2d);
+//                 - |F|^2 (autocorr) or whitened F * R (phase correlation) followed, in the same
+//                   CTA, by the inverse FFT along y, written to blocked intermediates.
+//   K3 rows_inv : two half-spectrum rows (two rows of one map, or one row of two maps) form one
+//                 complex inverse FFT whose real / imaginary parts are the two real output rows;
+//                 fftshifted stores, peak normalisation, argmax partials.
+// Every frame is shifted by a pilot mean K before the FFT (K*nx*ny is added back to the DC bin),
+// so fp32 rounding is relative to the fluctuations, not to the pedestal.
+#include "common.cuh"
+#include "fft.cuh"
+
+using namespace b4dfft;
+
+int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
+                           const float* dark, float* pilot);
+int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
+                    int use_abs, float* out, int64_t* n_valid);
+
+struct FftPlanCache {
+    float2* tw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 128, 256, 512, 1024, 2048
+    // tracker reference: conj spectrum of the embedded z-scored template
+    float2* ref = nullptr;       // blocked (nx/2/8, ny, 8)
+    float2* ref_nyq = nullptr;   // (ny)
+    int ref_ny = 0, ref_nx = 0;
+    double* theta = nullptr;     // 1130 x (sin, cos)
+};
+
+namespace {
+
+constexpr int NSP = 6;    // spectral partial sums per CTA
+constexpr int NTHETA = 1130;   // int(2*pi*180), maths/radial.py:150
+
+inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+inline bool fft_size_ok(int n) { return n >= 128 && n <= 2048 && (n & (n - 1)) == 0; }
+
+template <int N>
+void fill_twiddles(std::vector<float2>& h) {
+    using P = Plan<N>;
+    h.clear();
+    auto push_stage = [&](int R, int LS) {
+        for (int m = 1; m < R; ++m)
+            for (int k = 0; k < LS; ++k) {
+                const double a = -2.0 * 3.14159265358979323846 * (double)m * (double)k / ((double)LS * (double)R);
+                h.push_back(make_float2((float)cos(a), (float)sin(a)));
+            }
+    };
+    push_stage(P::R2, P::R1);
+    if (P::R3 > 1) push_stage(P::R3, P::R1 * P::R2);
+}
+
+int get_twiddles(b4d_ctx* ctx, int n, const float2** out) {
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    const int slot = log2i(n) - 7;
+    if (!ctx->fft->tw[slot]) {
+        std::vector<float2> h;
+        switch (n) {
+            case 128: fill_twiddles<128>(h); break;
+            case 256: fill_twiddles<256>(h); break;
+            case 512: fill_twiddles<512>(h); break;
+            case 1024: fill_twiddles<1024>(h); break;
+            default: fill_twiddles<2048>(h); break;
+        }
+        B4D_CUDA(ctx, cudaMalloc(&ctx->fft->tw[slot], h.size() * sizeof(float2)));
+        B4D_CUDA(ctx, cudaMemcpy(ctx->fft->tw[slot], h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    *out = ctx->fft->tw[slot];
+    return B4D_OK;
+}
+
+// shared-memory slot functors ---------------------------------------------------------------------
+struct SlotLinear {          // one transform, contiguous
+    float2* base;
+    __device__ __forceinline__ float2& operator()(int i) const { return base[pad16(i)]; }
+};
+struct SlotBatch8 {          // 8 transforms interleaved (batch index fastest)
+    float2* base;            // already offset by the column
+    __device__ __forceinline__ float2& operator()(int i) const { return base[pad16(i) * 8]; }
+};
+
+// =================================================================================================
+// K1: rows forward
+// =================================================================================================
+struct RowsFwdArgs {
+    const float* stack;
+    const float* gain;
+    const float* dark;
+    const float* pilot;   // nullable
+    float2* H;
+    const float2* tw;
+    int ny;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
+    constexpr int TPF = NX / 16;          // threads per transform
+    constexpr int FPC = 512 / TPF;        // transforms per CTA
+    constexpr int ROWS = 2 * FPC;
+    constexpr int FS = padded_len(NX) + 8;
+    extern __shared__ float2 sm[];
+    const int tid = threadIdx.x, f = tid / TPF, j = tid % TPF;
+    const int64_t t = blockIdx.y;
+    const int y0 = blockIdx.x * ROWS;
+    const float K = a.pilot ? __ldg(a.pilot + t) : 0.f;
+    const size_t fo = (size_t)t * a.ny * NX;
+    const float* ra = a.stack + fo + (size_t)(y0 + 2 * f) * NX;
+    const float* rb = ra + NX;
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int col = j + m * TPF;
+        float va = ldg_stream1(ra + col), vb = ldg_stream1(rb + col);
+        if (a.gain) {
+            const size_t pa = (size_t)(y0 + 2 * f) * NX + col, pb = pa + NX;
+            va = (va - (a.dark ? __ldg(a.dark + pa) : 0.f)) * __ldg(a.gain + pa);
+            vb = (vb - (a.dark ? __ldg(a.dark + pb) : 0.f)) * __ldg(a.gain + pb);
+        }
+        x[m] = make_float2(va - K, vb - K);
+    }
+    fft_from_regs<NX, -1>(x, j, SlotLinear{sm + f * FS}, a.tw);
+
+    // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
+    float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
+    for (int idx = tid; idx < ROWS * (NX / 2); idx += 512) {
+        const int tile = idx / (ROWS * 8), rem = idx % (ROWS * 8);
+        const int r = rem >> 3, c = rem & 7, k = tile * 8 + c, p = r >> 1;
+        const float2* z = sm + p * FS;
+        const float2 Z = z[pad16(k)];
+        float2 v;
+        if (k == 0) {
+            const float2 Zh = z[pad16(NX / 2)];
+            v = (r & 1) ? make_float2(Z.y, Zh.y) : make_float2(Z.x, Zh.x);
+        } else {
+            const float2 Zm = z[pad16(NX - k)];
+            v = (r & 1) ? make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x))
+                        : make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
+        }
+        Hf[((size_t)tile * a.ny + y0 + r) * 8 + c] = v;
+    }
+}
+
+// =================================================================================================
+// K2: columns forward + epilogues (+ inverse along y)
+// =================================================================================================
+struct ColsArgs {
+    const float2* H;            // blocked input, per frame ny*nx/2
+    const float2* tw;
+    const float* pilot;         // nullable: DC += nx*ny*K
+    int nx;
+    int zero_dc;                // clear F[0,0] (mean removal) for every output
+    int ac_zero_dc;             // clear it for the autocorrelation branch only (fused pipeline)
+    // plain outputs
+    float2* cplx_out;           // (T, ny, nx) shifted complex spectrum (fft2d)
+    float* psd_out;             // (T, ny, nx) shifted |F|^2 * psd_scale
+    float psd_scale;
+    double* spec_partials;      // (T, ntiles, NSP)
+    float2* conj_out;           // blocked conj(F) (T, nx/2/8, ny, 8)
+    float2* conj_nyq_out;       // (T, ny)
+    // autocorrelation branch
+    float2* i2_ac;              // blocked inverse-along-y of |F|^2
+    double* ac_partials;        // (T, ntiles) sum of the full-spectrum |F|^2 owned by the tile
+    // product branch: G = F * R (optionally whitened), inverse along y -> i2_pc
+    float2* i2_pc;
+    const float2* R;            // blocked, shared by all frames (ref_stride 0) or per frame
+    const float2* Rnyq;
+    size_t r_stride, rnyq_stride;
+    int whiten;
+    float eps;
+    const double* fr;           // frame-reduction table (mean, m2) for the z-score; nullable
+    int fr_stride;
+};
+
+struct SpecAcc {
+    double total = 0, fx2 = 0, fy2 = 0, p2 = 0, all = 0, plogp = 0;
+};
+
+template <int NY>
+__device__ __forceinline__ void spec_accumulate(SpecAcc& s, float P, int ky, int kx, int nx, double w, bool is_dc) {
+    if (is_dc) return;
+    const double p = (double)P;
+    const int kys = ky <= NY / 2 ? ky : ky - NY;
+    const double fy = (double)kys / (double)NY, fx = (double)kx / (double)nx;
+    s.all += w * p;
+    if (P > 0.f) s.plogp += w * p * (double)logf(P);
+    if (fx * fx + fy * fy <= 0.25) {
+        s.total += w * p;
+        s.fx2 += w * fx * fx * p;
+        s.fy2 += w * fy * fy * p;
+        s.p2 += w * p * p;
+    }
+}
+
+template <int NY>
+__global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
+    constexpr int TPF = NY / 16;
+    constexpr int NT = NY / 2;                  // threads: 8 columns x TPF
+    constexpr int PL = padded_len(NY);
+    extern __shared__ float2 sm[];
+    float2* A = sm;                             // [PL][8]
+    float2* nyq = sm + PL * 8;                  // [PL]   (tile 0 only)
+    float* Bp = reinterpret_cast<float*>(nyq + PL);   // [PL][8] |F|^2 copy (only when both branches run)
+    __shared__ double red[32];
+    __shared__ float s_dcshift;                 // DC of the K-shifted frame (tile 0)
+
+    const int tid = threadIdx.x, c = tid & 7, j = tid >> 3;
+    const int tile = blockIdx.x, ntiles = gridDim.x;
+    const int64_t t = blockIdx.y;
+    const int nx = a.nx, hx = nx / 2;
+    const bool tile0 = tile == 0;
+    const bool want_ac = a.i2_ac != nullptr, want_pc = a.i2_pc != nullptr;
+    const float2* Hin = a.H + (size_t)t * NY * hx + (size_t)tile * NY * 8;
+
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = __ldg(Hin + (size_t)(j + m * TPF) * 8 + c);
+    fft_from_regs<NY, -1>(x, j, SlotBatch8{A + c}, a.tw);
+
+    // ---- tile 0: unpack column 0 (DC + i Nyquist rows) into F[:,0] (kept in A) and F[:,nx/2] (nyq)
+    if (tile0) {
+        float2 f0[(NY / 2 + 1 + NT - 1) / NT][2], fn[(NY / 2 + 1 + NT - 1) / NT][2];
+        int q = 0;
+        for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
+            const float2 C = A[pad16(ky) * 8], Cm = A[pad16((NY - ky) & (NY - 1)) * 8];
+            // F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i); the -ky entries are their conjugates
+            f0[q][0] = make_float2(0.5f * (C.x + Cm.x), 0.5f * (C.y - Cm.y));
+            fn[q][0] = make_float2(0.5f * (C.y + Cm.y), -0.5f * (C.x - Cm.x));
+            f0[q][1] = cconj(f0[q][0]);
+            fn[q][1] = cconj(fn[q][0]);
+        }
+        __syncthreads();
+        q = 0;
+        for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
+            const int km = (NY - ky) & (NY - 1);
+            A[pad16(ky) * 8] = f0[q][0];
+            nyq[pad16(ky)] = fn[q][0];
+            if (km != ky) {
+                A[pad16(km) * 8] = f0[q][1];
+                nyq[pad16(km)] = fn[q][1];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float2 dc = A[0];
+            s_dcshift = dc.x;
+            if (a.pilot) dc.x += (float)((double)nx * (double)NY * (double)__ldg(a.pilot + t));
+            if (a.zero_dc) dc = make_float2(0.f, 0.f);
+            A[0] = dc;
+        }
+        __syncthreads();
+    }
+
+    // ---- pass over the tile: plain outputs ------------------------------------------------------
+    SpecAcc sp;
+    double acsum = 0.0;
+    const bool need_pass = a.psd_out || a.cplx_out || a.spec_partials || a.conj_out || want_ac;
+    if (need_pass) {
+        float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx : nullptr;
+        float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx : nullptr;
+        float2* cj = a.conj_out ? a.conj_out + (size_t)t * NY * hx + (size_t)tile * NY * 8 : nullptr;
+        for (int idx = tid; idx < NY * 8; idx += NT) {
+            const int ky = idx >> 3, cc = idx & 7, kx = tile * 8 + cc;
+            const float2 F = A[pad16(ky) * 8 + cc];
+            const float P = F.x * F.x + F.y * F.y;
+            const int rs = (ky + NY / 2) & (NY - 1), rm = (NY / 2 - ky) & (NY - 1);
+            const bool mirror = kx >= 1;
+            if (psd) {
+                psd[(size_t)rs * nx + kx + hx] = P * a.psd_scale;
+                if (mirror) psd[(size_t)rm * nx + hx - kx] = P * a.psd_scale;
+            }
+            if (cpl) {
+                cpl[(size_t)rs * nx + kx + hx] = F;
+                if (mirror) cpl[(size_t)rm * nx + hx - kx] = cconj(F);
+            }
+            if (cj) cj[idx] = cconj(F);
+            if (a.spec_partials) spec_accumulate<NY>(sp, P * a.psd_scale, ky, kx, nx, mirror ? 2.0 : 1.0, ky == 0 && kx == 0);
+            if (want_ac) {
+                const float Pa = (a.ac_zero_dc && tile0 && idx == 0) ? 0.f : P;
+                acsum += (mirror ? 2.0 : 1.0) * (double)Pa;
+                if (want_pc) Bp[pad16(ky) * 8 + cc] = Pa;
+            }
+        }
+        if (tile0) {   // the Nyquist column kx = nx/2 lands in shifted column 0
+            float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
+            for (int ky = tid; ky < NY; ky += NT) {
+                const float2 F = nyq[pad16(ky)];
+                const float P = F.x * F.x + F.y * F.y;
+                const int rs = (ky + NY / 2) & (NY - 1);
+                if (psd) psd[(size_t)rs * nx] = P * a.psd_scale;
+                if (cpl) cpl[(size_t)rs * nx] = F;
+                if (cjn) cjn[ky] = cconj(F);
+                if (a.spec_partials) spec_accumulate<NY>(sp, P * a.psd_scale, ky, hx, nx, 1.0, false);
+                if (want_ac) acsum += (double)P;
+            }
+        }
+    }
+
+    // ---- block reductions of the scalar partials ------------------------------------------------
+    if (a.spec_partials || want_ac) {
+        double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, acsum};
+        const int warp = tid >> 5, lane = tid & 31, nw = NT / 32;
+#pragma unroll
+        for (int i = 0; i < NSP + 1; ++i) {
+            double s = warp_sum(v[i]);
+            __syncthreads();
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < nw; ++w) tot += red[w];
+                if (i < NSP) {
+                    if (a.spec_partials) a.spec_partials[((size_t)t * ntiles + tile) * NSP + i] = tot;
+                } else if (want_ac) {
+                    a.ac_partials[(size_t)t * ntiles + tile] = tot;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- product branch: G = F * R (whitened for phase correlation), inverse along y ---------------
+    if (want_pc) {
+        const float2* R = a.R + (size_t)t * a.r_stride + (size_t)tile * NY * 8;
+        const float2* Rn = a.Rnyq + (size_t)t * a.rnyq_stride;
+        float inv_s = 1.f;
+        if (a.fr) {
+            const double sd = sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]);
+            inv_s = (float)(1.0 / (sd + (double)a.eps));
+        }
+        for (int idx = tid; idx < NY * 8; idx += NT) {
+            const int ky = idx >> 3, cc = idx & 7;
+            float2 F = A[pad16(ky) * 8 + cc];
+            if (tile0 && idx == 0 && a.fr) {
+                // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
+                const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
+                const double n = (double)nx * (double)NY;
+                F.x = (float)((double)s_dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
+            }
+            F.x *= inv_s; F.y *= inv_s;
+            float2 G = cmul(F, __ldg(R + idx));
+            if (a.whiten) {
+                const float mag = sqrtf(G.x * G.x + G.y * G.y) + a.eps;
+                G.x = G.x / mag; G.y = G.y / mag;
+            }
+            A[pad16(ky) * 8 + cc] = G;
+        }
+        if (tile0) {
+            __syncthreads();
+            // pack: column 0 <- G[:,0] + i G[:,nx/2]
+            for (int ky = tid; ky < NY; ky += NT) {
+                float2 F = nyq[pad16(ky)];
+                F.x *= inv_s; F.y *= inv_s;
+                float2 G = cmul(F, __ldg(Rn + ky));
+                if (a.whiten) {
+                    const float mag = sqrtf(G.x * G.x + G.y * G.y) + a.eps;
+                    G.x = G.x / mag; G.y = G.y / mag;
+                }
+                const float2 G0 = A[pad16(ky) * 8];
+                A[pad16(ky) * 8] = make_float2(G0.x - G.y, G0.y + G.x);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
+        __syncthreads();
+        fft_from_regs<NY, +1>(x, j, SlotBatch8{A + c}, a.tw);
+        float2* o = a.i2_pc + (size_t)t * NY * hx + (size_t)tile * NY * 8;
+        for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
+        __syncthreads();
+    }
+
+    // ---- autocorrelation branch: G = |F|^2, inverse along y ----------------------------------------
+    if (want_ac) {
+        for (int idx = tid; idx < NY * 8; idx += NT) {
+            const int ky = idx >> 3, cc = idx & 7;
+            float P;
+            if (want_pc) P = Bp[pad16(ky) * 8 + cc];
+            else {
+                const float2 F = A[pad16(ky) * 8 + cc];
+                P = (a.ac_zero_dc && tile0 && idx == 0) ? 0.f : F.x * F.x + F.y * F.y;
+            }
+            float Pn = 0.f;
+            if (tile0 && cc == 0) { const float2 Fn = nyq[pad16(ky)]; Pn = Fn.x * Fn.x + Fn.y * Fn.y; }
+            A[pad16(ky) * 8 + cc] = make_float2(P, Pn);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
+        __syncthreads();
+        fft_from_regs<NY, +1>(x, j, SlotBatch8{A + c}, a.tw);
+        float2* o = a.i2_ac + (size_t)t * NY * hx + (size_t)tile * NY * 8;
+        for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
+    }
+}
+
+// =================================================================================================
+// K3: rows inverse (two half-spectrum rows -> two real rows)
+// =================================================================================================
+struct ArgBest {
+    float v;
+    unsigned idx;
+};
+__device__ __forceinline__ void best_update(ArgBest& b, float v, unsigned idx) {
+    if (v > b.v || (v == b.v && idx < b.idx)) { b.v = v; b.idx = idx; }
+}
+
+struct RowsInvArgs {
+    const float2* Ia;       // blocked intermediate of map A (per frame ny*nx/2)
+    const float2* Ib;       // map B (pair_maps) or nullptr
+    const float2* tw;
+    int ny;
+    int pair_maps;          // 0: rows (2p, 2p+1) of map A; 1: row y of map A and of map B
+    // map A output
+    float* outA;            // (T, ny, nx) shifted real output (nullable)
+    int kindA;              // 0: signed value * scale; 1: |value| * scale
+    const double* normA;    // per-frame partials (T, n_normA) whose sum is the peak (nullable -> 1)
+    int n_normA;
+    double norm_mult;       // value = raw * norm_mult / sum(normA)
+    double scaleA;          // extra factor (e.g. 1/(nx*ny))
+    ArgBest* bestA;         // (T, gridDim.x) argmax partials (nullable)
+    // map B output (pair_maps only)
+    float* outB;
+    int kindB;
+    double scaleB;
+    ArgBest* bestB;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
+    constexpr int TPF = NX / 16;
+    constexpr int WPG = TPF / 8;          // warps per group of 4 transforms
+    constexpr int GPC = 16 / WPG;         // groups per CTA (512 threads)
+    constexpr int FPC = 4 * GPC;
+    constexpr int FS = padded_len(NX) + 8;
+    constexpr int HX = NX / 2;
+    extern __shared__ float2 sm[];
+    __shared__ float s_scale;
+    __shared__ ArgBest s_best[2][16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
+    const int f = grp * 4 + fl, j = jt * 8 + c;
+    const int64_t t = blockIdx.y;
+    const int NY = a.ny;
+    const int rows_per_cta = a.pair_maps ? FPC : 2 * FPC;
+    const int y0 = blockIdx.x * rows_per_cta;
+    const int ya = a.pair_maps ? y0 + f : y0 + 2 * f;
+    const int yb = a.pair_maps ? ya : ya + 1;
+    const float2* Ia = a.Ia + (size_t)t * NY * HX;
+    const float2* Ib = a.pair_maps ? a.Ib + (size_t)t * NY * HX : Ia;
+
+    if (tid == 0) {
+        double s = a.scaleA;
+        if (a.normA) {
+            double tot = 0.0;
+            for (int i = 0; i < a.n_normA; ++i) tot += a.normA[(size_t)t * a.n_normA + i];
+            s = tot > 0.0 ? a.norm_mult / tot : a.scaleA;
+        }
+        s_scale = (float)s;
+    }
+
+    // gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
+    float2* z = sm + f * FS;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = j + m * TPF;
+        const size_t off = ((size_t)(k >> 3) * NY) * 8 + (k & 7);
+        const float2 ga = __ldg(Ia + off + (size_t)ya * 8), gb = __ldg(Ib + off + (size_t)yb * 8);
+        if (k == 0) {
+            // packed slot: (DC, Nyquist), both real
+            z[pad16(0)] = make_float2(ga.x, gb.x);
+            z[pad16(HX)] = make_float2(ga.y, gb.y);
+        } else {
+            z[pad16(k)] = make_float2(ga.x - gb.y, ga.y + gb.x);
+            z[pad16(NX - k)] = make_float2(ga.x + gb.y, gb.x - ga.y);
+        }
+    }
+    __syncthreads();
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
+    __syncthreads();
+    fft_from_regs<NX, +1>(x, j, SlotLinear{z}, a.tw);
+
+    // stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
+    const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
+    const int kindB = a.pair_maps ? a.kindB : a.kindA;
+    float* oA = a.outA ? a.outA + (size_t)t * NY * NX : nullptr;
+    float* oB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX : nullptr) : oA;
+    ArgBest bA = {-INFINITY, 0xffffffffu}, bB = {-INFINITY, 0xffffffffu};
+    for (int idx = tid; idx < FPC * NX; idx += 512) {
+        const int ff = idx / NX, xx = idx % NX;
+        const float2 v = sm[ff * FS + pad16(xx)];
+        const int ra_ = a.pair_maps ? y0 + ff : y0 + 2 * ff;
+        const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
+        const unsigned cs = (unsigned)((xx + HX) & (NX - 1));
+        const unsigned rsa = (unsigned)((ra_ + NY / 2) & (NY - 1)), rsb = (unsigned)((rb_ + NY / 2) & (NY - 1));
+        float va = v.x * sA, vb = v.y * sB;
+        if (a.kindA) va = fabsf(va);
+        if (kindB) vb = fabsf(vb);
+        if (oA) oA[(size_t)rsa * NX + cs] = va;
+        if (oB) oB[(size_t)rsb * NX + cs] = vb;
+        best_update(bA, va, rsa * (unsigned)NX + cs);
+        if (a.pair_maps) best_update(bB, vb, rsb * (unsigned)NX + cs);
+        else best_update(bA, vb, rsb * (unsigned)NX + cs);
+    }
+    // argmax partials (first occurrence in row-major order of the shifted map wins ties)
+    if (a.bestA || (a.pair_maps && a.bestB)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgBest oa = {__shfl_xor_sync(0xffffffffu, bA.v, o), __shfl_xor_sync(0xffffffffu, bA.idx, o)};
+            ArgBest ob = {__shfl_xor_sync(0xffffffffu, bB.v, o), __shfl_xor_sync(0xffffffffu, bB.idx, o)};
+            best_update(bA, oa.v, oa.idx);
+            best_update(bB, ob.v, ob.idx);
+        }
+        if (lane == 0) { s_best[0][warp] = bA; s_best[1][warp] = bB; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 16; ++w) { best_update(bA, s_best[0][w].v, s_best[0][w].idx); best_update(bB, s_best[1][w].v, s_best[1][w].idx); }
+            if (a.bestA) a.bestA[(size_t)t * gridDim.x + blockIdx.x] = bA;
+            if (a.pair_maps && a.bestB) a.bestB[(size_t)t * gridDim.x + blockIdx.x] = bB;
+        }
+    }
+}
+
+// =================================================================================================
+// small kernels
+// =================================================================================================
+
+// peak location from the argmax partials: out_idx[t] = shifted linear index, out_val[t] = value
+__global__ void __launch_bounds__(128) argmax_reduce_kernel(const ArgBest* __restrict__ part, int n,
+                                                            unsigned* __restrict__ out_idx, float* __restrict__ out_val) {
+    const int64_t t = blockIdx.x;
+    ArgBest b = {-INFINITY, 0xffffffffu};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) best_update(b, part[t * n + i].v, part[t * n + i].idx);
+    __shared__ ArgBest sb[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best_update(b, __shfl_xor_sync(0xffffffffu, b.v, o), __shfl_xor_sync(0xffffffffu, b.idx, o));
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w) best_update(b, sb[w].v, sb[w].idx);
+        out_idx[t] = b.idx;
+        out_val[t] = b.v;
+    }
+}
+
+// z-score the (h, w) template over its own pixels and embed it at (y0, x0) in a zero (ny, nx) frame
+// (signal/tracking.py:251-260). One CTA; the template is small next to a stack.
+__global__ void __launch_bounds__(1024) embed_template_kernel(const float* __restrict__ tpl, int h, int w, int ny, int nx,
+                                                              int y0, int x0, float eps, float* __restrict__ out) {
+    __shared__ double sh[32];
+    __shared__ double s_mean, s_std;
+    const int n = h * w;
+    // nanmean
+    double s = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = tpl[i]; if (v == v) { s += v; cnt += 1.0; } }
+    s = warp_sum(s); cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_mean = a; }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_mean = a > 0 ? s_mean / a : nan(""); s_std = a; }
+    __syncthreads();
+    const double mean = s_mean, count = s_std;
+    __syncthreads();
+    double q = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = tpl[i]; if (v == v) { const double d = (double)v - mean; q += d * d; } }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_std = count > 0 ? sqrt(a / count) : nan(""); }
+    __syncthreads();
+    const float m = (float)mean, inv = 1.f / ((float)s_std + eps);
+    for (int i = threadIdx.x; i < ny * nx; i += blockDim.x) {
+        const int y = i / nx, xq = i % nx;
+        const int ty = y - y0, tx = xq - x0;
+        float v = 0.f;
+        if (ty >= 0 && ty < h && tx >= 0 && tx < w) v = (tpl[ty * w + tx] - m) * inv;
+        out[i] = v;
+    }
+}
+
+// (dy, dx, peak, snr) per frame from the |corr| map (signal/tracking.py:283-297, 314-375)
+__global__ void phase_finalize_kernel(const float* __restrict__ mag, const unsigned* __restrict__ peak_idx, int ny, int nx,
+                                      const float* __restrict__ med2, const long long* __restrict__ nvalid, int subpixel,
+                                      double eps, double* __restrict__ out, int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* c = mag + (size_t)t * ny * nx;
+    const int i = (int)(peak_idx[t] / (unsigned)nx), j = (int)(peak_idx[t] % (unsigned)nx);
+    const float pk = c[(size_t)i * nx + j];
+    double dy = (double)(i - ny / 2), dx = (double)(j - nx / 2);
+    if (subpixel && i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+        auto C = [&](int a, int b) { return c[(size_t)a * nx + b]; };
+        // float32 scalar arithmetic, one rounding per operation, as numpy evaluates it
+        const float gy = __fdiv_rn(__fsub_rn(C(i + 1, j), C(i - 1, j)), 2.f);
+        const float gyy = __fsub_rn(__fadd_rn(C(i + 1, j), C(i - 1, j)), __fmul_rn(2.f, C(i, j)));
+        const float gx = __fdiv_rn(__fsub_rn(C(i, j + 1), C(i, j - 1)), 2.f);
+        const float gxx = __fsub_rn(__fadd_rn(C(i, j + 1), C(i, j - 1)), __fmul_rn(2.f, C(i, j)));
+        const float gxy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(C(i + 1, j + 1), C(i + 1, j - 1)), C(i - 1, j + 1)), C(i - 1, j - 1)), 4.f);
+        const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+        if (det != 0.f) {
+            const float inv = __fdiv_rn(1.f, det);
+            // NOTE: the reference returns the x step first and adds it to dy
+            const float di = __fmul_rn(-__fsub_rn(__fmul_rn(gyy, gx), __fmul_rn(gxy, gy)), inv);
+            const float dj = __fmul_rn(-__fsub_rn(__fmul_rn(gxx, gy), __fmul_rn(gxy, gx)), inv);
+            dy += (double)di;
+            dx += (double)dj;
+        }
+    }
+    // np.median of a float32 array: mean of the two middle values, rounded to float32
+    const float med = (nvalid[t] & 1) ? med2[2 * t] : __fmul_rn(__fadd_rn(med2[2 * t], med2[2 * t + 1]), 0.5f);
+    double* o = out + t * 4;
+    o[0] = dy; o[1] = dx; o[2] = (double)pk; o[3] = fabs((double)pk) / ((double)med + eps);
+}
+
+// grain(): widths of the peak-normalised autocorrelation (metrics/speckles.py:546-575)
+//   lx, ly : width_at_fraction of the row / column through the argmax (maths/stats.py:45-89)
+//   leq    : 2 * distance_at_fraction_from_peak(radial_mean_interpolated(ac)) (maths/stats.py:127-155,
+//            maths/radial.py:132-169); radii are evaluated in increasing order until the first crossing,
+//            which is all the first-crossing rule ever looks at.
+__device__ double cut_width(const float* __restrict__ p, int stride, int n, int cidx, double fraction, double* sh_i) {
+    // parallel search of the first sample below thr walking left and right from cidx
+    const double peak = (double)p[(size_t)cidx * stride], thr = peak * fraction;
+    int il = -1, ir = n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool below = (double)p[(size_t)i * stride] < thr;
+        if (below && i <= cidx) il = max(il, i);
+        if (below && i >= cidx) ir = min(ir, i);
+    }
+    __shared__ int s_l[32], s_r[32];
+    for (int o = 16; o > 0; o >>= 1) { il = max(il, __shfl_xor_sync(0xffffffffu, il, o)); ir = min(ir, __shfl_xor_sync(0xffffffffu, ir, o)); }
+    if ((threadIdx.x & 31) == 0) { s_l[threadIdx.x >> 5] = il; s_r[threadIdx.x >> 5] = ir; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { il = max(il, s_l[w]); ir = min(ir, s_r[w]); }
+        double width;
+        if (il < 0 || ir >= n) width = (double)n;
+        else {
+            double ya = p[(size_t)il * stride], yb = p[(size_t)(il + 1) * stride];
+            const double xl = (yb == ya) ? (double)il : il + (thr - ya) / (yb - ya);
+            ya = p[(size_t)(ir - 1) * stride]; yb = p[(size_t)ir * stride];
+            const double xr = (yb == ya) ? (double)ir : (ir - 1) + (thr - ya) / (yb - ya);
+            width = xr - xl;
+        }
+        *sh_i = width;
+    }
+    __syncthreads();
+    return *sh_i;
+}
+
+__global__ void __launch_bounds__(1024) grain_kernel(const float* __restrict__ ac, int n, const unsigned* __restrict__ peak_idx,
+                                                     const double* __restrict__ theta, double fraction,
+                                                     double* __restrict__ out) {
+    const int64_t t = blockIdx.x;
+    const float* a = ac + (size_t)t * n * n;
+    const int iy = (int)(peak_idx[t] / (unsigned)n), ix = (int)(peak_idx[t] % (unsigned)n);
+    __shared__ double s_w;
+    __shared__ double rad[32];
+    const double ly = cut_width(a + ix, n, n, iy, fraction, &s_w);
+    __syncthreads();
+    const double lx = cut_width(a + (size_t)iy * n, 1, n, ix, fraction, &s_w);
+    __syncthreads();
+
+    // radial profile about (n//2, n//2): r_k = k (r_max = n/2, nr = n/2 + 1 -> dr = 1 exactly for even n)
+    const int cy = n / 2, cx = n / 2;
+    const double r_max = (double)(n / 2);
+    const int nr = n / 2 + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double peak0 = 0.0, prev = 0.0, dist = (double)nr;
+    bool found = false;
+    for (int k0 = 0; k0 < nr && !found; k0 += 32) {
+        // warp w evaluates radius k0 + w
+        const int k = k0 + warp;
+        double s = 0.0;
+        if (k < nr) {
+            const double r = r_max * (double)k / (double)(nr - 1);
+            for (int m = lane; m < NTHETA; m += 32) {
+                const double yy = r * theta[2 * m] + cy, xx = r * theta[2 * m + 1] + cx;
+                if (yy >= 0.0 && yy <= (double)(n - 1) && xx >= 0.0 && xx <= (double)(n - 1)) {
+                    int y0 = min((int)floor(yy), n - 2), x0 = min((int)floor(xx), n - 2);
+                    const double ty = yy - y0, tx = xx - x0;
+                    const float* q = a + (size_t)y0 * n + x0;
+                    s += (double)q[0] * (1.0 - ty) * (1.0 - tx) + (double)q[1] * (1.0 - ty) * tx +
+                         (double)q[n] * ty * (1.0 - tx) + (double)q[n + 1] * ty * tx;
+                }
+            }
+            s = warp_sum(s) / (double)NTHETA;
+        }
+        __syncthreads();
+        if (lane == 0) rad[warp] = s;
+        __syncthreads();
+        // every thread scans the 32 new radii identically (cheap, keeps control flow uniform)
+        for (int w = 0; w < 32 && k0 + w < nr && !found; ++w) {
+            const double v = rad[w];
+            const int kk = k0 + w;
+            if (kk == 0) { peak0 = v; prev = v; continue; }
+            const double thr = peak0 * fraction;
+            if (v < thr) {
+                const double xc = (v == prev) ? (double)kk : (kk - 1) + (thr - prev) / (v - prev);
+                dist = xc;
+                found = true;
+            }
+            prev = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double dr = r_max / (double)(nr - 1);
+        double* o = out + t * 4;
+        o[0] = lx; o[1] = ly; o[2] = 2.0 * dist * dr; o[3] = ly != 0.0 ? lx / ly : INFINITY;
+    }
+}
+
+// out *= 1 / max|out| per frame (xcorr2d "peak"), max taken from the argmax partial of |values|
+__global__ void __launch_bounds__(256) scale_by_kernel(float* __restrict__ data, int64_t n, const float* __restrict__ peak,
+                                                       int use_reciprocal) {
+    const int64_t t = blockIdx.y;
+    const float m = peak[t];
+    if (!(m > 0.f)) return;
+    float* d = data + t * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = use_reciprocal ? d[i] / m : d[i] * m;
+}
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ data, int64_t n, float* __restrict__ out) {
+    const int64_t t = blockIdx.x;
+    const float* d = data + t * n;
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(d[i]));
+    m = warp_max(m);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]); out[t] = m; }
+}
+
+// spectral table (T, B4D_SP_NCOLS) from the per-tile partials, fixed summation order
+__global__ void spec_finalize_kernel(const double* __restrict__ part, int ntiles, double* __restrict__ out, int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double s[NSP] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ntiles; ++i)
+        for (int k = 0; k < NSP; ++k) s[k] += part[((size_t)t * ntiles + i) * NSP + k];
+    double* o = out + t * B4D_SP_NCOLS;
+    o[B4D_SP_TOTAL] = s[0]; o[B4D_SP_FX2] = s[1]; o[B4D_SP_FY2] = s[2]; o[B4D_SP_P2] = s[3];
+    o[B4D_SP_ALL] = s[4]; o[B4D_SP_PLOGP] = s[5];
+    o[B4D_SP_F95] = nan(""); o[B4D_SP_NCOLS - 1] = 0.0;
+}
+
+// ---- f95: radius at which the radius-sorted cumulative PSD first reaches 0.95 (speckles.py:783-790) ----
+// Two levels over integer keys r2 = kx^2 + ky^2 (square frames): coarse bins of 1024 keys, then the
+// exact key inside the crossing bin.
+__global__ void __launch_bounds__(256) f95_hist_kernel(const float* __restrict__ psd, int n, int level,
+                                                       const int* __restrict__ coarse_bin, double* __restrict__ hist, int nb) {
+    const int64_t t = blockIdx.y;
+    const float* p = psd + (size_t)t * n * n;
+    extern __shared__ double shh[];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) shh[i] = 0.0;
+    __syncthreads();
+    const int h = n / 2;
+    const int cb = level ? coarse_bin[t] : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / n), xq = (int)(i % n);
+        const int ky = y - h, kx = xq - h;
+        const long long r2 = (long long)ky * ky + (long long)kx * kx;
+        if (r2 == 0 || r2 > (long long)h * h) continue;
+        const double v = (double)p[i];
+        if (!level) atomicAdd(&shh[(int)(r2 >> 10)], v);
+        else if ((int)(r2 >> 10) == cb) atomicAdd(&shh[(int)(r2 & 1023)], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (shh[i] != 0.0) atomicAdd(hist + (size_t)t * nb + i, shh[i]);
+}
+
+__global__ void f95_scan_kernel(double* __restrict__ hist, int nb, int level, const double* __restrict__ spec_tab,
+                                int* __restrict__ coarse_bin, double* __restrict__ below, int n, double* __restrict__ out,
+                                int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double* h = hist + (size_t)t * nb;
+    const double total = spec_tab[t * B4D_SP_NCOLS + B4D_SP_TOTAL];
+    double cum = level ? below[t] : 0.0;
+    int hit = nb - 1;
+    bool found = false;
+    for (int i = 0; i < nb; ++i) {
+        if (!found && (cum + h[i]) / total >= 0.95 && h[i] != 0.0) { hit = i; found = true; }
+        if (!found) cum += h[i];
+        h[i] = 0.0;   // ready for the next use
+    }
+    if (!level) { coarse_bin[t] = hit; below[t] = cum; }
+    else {
+        const long long r2 = ((long long)coarse_bin[t] << 10) + hit;
+        out[t * B4D_SP_NCOLS + B4D_SP_F95] = sqrt((double)r2) / (double)n;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// -------------------------------------------------------------------------------------------------
+template <int NX>
+int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
+    constexpr int TPF = NX / 16, FPC = 512 / TPF, ROWS = 2 * FPC;
+    constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    if (a.ny % ROWS) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, ROWS);
+    rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+template <int NY>
+int launch_cols(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
+    constexpr int PL = padded_len(NY);
+    const bool both = a.i2_ac && a.i2_pc;
+    const size_t smem = (size_t)PL * 8 * sizeof(float2) + (size_t)PL * sizeof(float2) + (both ? (size_t)PL * 8 * sizeof(float) : 0);
+    static size_t attr = 0;
+    if (attr < smem) { B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    cols_kernel<NY><<<dim3(a.nx / 16, (unsigned)T), NY / 2, smem, ctx->stream>>>(a);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+template <int NX>
+int launch_rows_inv(b4d_ctx* ctx, const RowsInvArgs& a, int64_t T, int* n_blocks_out) {
+    constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
+    constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int rows = a.pair_maps ? FPC : 2 * FPC;
+    if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
+    if (n_blocks_out) *n_blocks_out = a.ny / rows;
+    rows_inv_kernel<NX><<<dim3(a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+int rows_inv_blocks(int nx, int ny, int pair_maps) {
+    const int tpf = nx / 16, wpg = tpf / 8, gpc = 16 / wpg, fpc = 4 * gpc;
+    return ny / (pair_maps ? fpc : 2 * fpc);
+}
+
+#define DISPATCH_N(n, CALL)                                   \
+    switch (n) {                                              \
+        case 128: { constexpr int N_ = 128; CALL; } break;    \
+        case 256: { constexpr int N_ = 256; CALL; } break;    \
+        case 512: { constexpr int N_ = 512; CALL; } break;    \
+        case 1024: { constexpr int N_ = 1024; CALL; } break;  \
+        default: { constexpr int N_ = 2048; CALL; } break;    \
+    }
+
+int check_fft_args(b4d_ctx* ctx, const char* who, const void* stack, int64_t T, int ny, int nx) {
+    if (!stack || T < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "%s: bad arguments", who);
+    if (!fft_size_ok(ny) || !fft_size_ok(nx) || T > 65535)
+        return b4d_fail(ctx, B4D_ERR_UNSUPPORTED,
+                        "%s: frames must have power-of-two sides in [128, 2048] and at most 65535 frames per call; got T=%lld (ny, nx)=(%d, %d)",
+                        who, (long long)T, ny, nx);
+    return B4D_OK;
+}
+
+// Workspace carve-up for one call (all sizes per frame, times T)
+struct Work {
+    float* pilot = nullptr;
+    float2* H = nullptr;
+    float2* I2a = nullptr;
+    float2* I2b = nullptr;
+    double* acp = nullptr;
+    double* spp = nullptr;
+    ArgBest* bestA = nullptr;
+    ArgBest* bestB = nullptr;
+    unsigned* pk_idx = nullptr;
+    float* pk_val = nullptr;
+    float* med = nullptr;
+    long long* nvalid = nullptr;
+};
+
+int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work* w) {
+    const size_t per = (size_t)ny * (nx / 2) * sizeof(float2);
+    void* p = nullptr;
+    int rc = b4d_scratch(ctx, SCR_SPEC_A, per * T, &p);
+    if (rc) return rc;
+    w->H = static_cast<float2*>(p);
+    if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * T, &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
+    if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * T, &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
+    const int ntiles = nx / 16, nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
+    size_t small = 0;
+    auto take = [&](size_t bytes) { size_t o = small; small += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
+                 o_spp = take(sizeof(double) * T * ntiles * NSP), o_ba = take(sizeof(ArgBest) * T * nblk),
+                 o_bb = take(sizeof(ArgBest) * T * nblk), o_pi = take(sizeof(unsigned) * T), o_pv = take(sizeof(float) * T),
+                 o_med = take(sizeof(float) * 2 * T), o_nv = take(sizeof(long long) * T);
+    rc = b4d_scratch(ctx, SCR_MISC, small + 1024, &p);
+    if (rc) return rc;
+    char* base = static_cast<char*>(p) + 512;   // first 512 B reserved (quantiles upload)
+    w->pilot = reinterpret_cast<float*>(base + o_pilot);
+    w->acp = reinterpret_cast<double*>(base + o_acp);
+    w->spp = reinterpret_cast<double*>(base + o_spp);
+    w->bestA = reinterpret_cast<ArgBest*>(base + o_ba);
+    w->bestB = reinterpret_cast<ArgBest*>(base + o_bb);
+    w->pk_idx = reinterpret_cast<unsigned*>(base + o_pi);
+    w->pk_val = reinterpret_cast<float*>(base + o_pv);
+    w->med = reinterpret_cast<float*>(base + o_med);
+    w->nvalid = reinterpret_cast<long long*>(base + o_nv);
+    return B4D_OK;
+}
+
+int ensure_theta(b4d_ctx* ctx) {
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    if (ctx->fft->theta) return B4D_OK;
+    std::vector<double> h(2 * NTHETA);
+    for (int m = 0; m < NTHETA; ++m) {
+        // np.linspace(0, 2*pi, ntheta, endpoint=False)[m] = m * (2*pi/ntheta)
+        const double th = (double)m * ((2.0 * 3.141592653589793) / (double)NTHETA);
+        h[2 * m] = sin(th);
+        h[2 * m + 1] = cos(th);
+    }
+    B4D_CUDA(ctx, cudaMalloc(&ctx->fft->theta, h.size() * sizeof(double)));
+    B4D_CUDA(ctx, cudaMemcpy(ctx->fft->theta, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return B4D_OK;
+}
+
+// rows forward for a batch, pilot included
+int run_rows_fwd(b4d_ctx* ctx, const float* stack, int64_t T, int ny, int nx, const float* gain, const float* dark,
+                 Work& w, bool use_pilot) {
+    int rc;
+    if (use_pilot) { rc = b4d_frame_pilot_launch(ctx, stack, T, (int64_t)ny * nx, gain, dark, w.pilot); if (rc) return rc; }
+    RowsFwdArgs a;
+    a.stack = stack; a.gain = gain; a.dark = dark; a.pilot = use_pilot ? w.pilot : nullptr; a.H = w.H; a.ny = ny;
+    rc = get_twiddles(ctx, nx, &a.tw);
+    if (rc) return rc;
+    DISPATCH_N(nx, rc = launch_rows_fwd<N_>(ctx, a, T));
+    return rc;
+}
+
+ColsArgs cols_defaults(const Work& w, int nx, bool use_pilot) {
+    ColsArgs c;
+    memset(&c, 0, sizeof(c));
+    c.H = w.H; c.pilot = use_pilot ? w.pilot : nullptr; c.nx = nx; c.psd_scale = 1.f;
+    return c;
+}
+
+int run_cols(b4d_ctx* ctx, ColsArgs& c, int64_t T, int ny) {
+    int rc = get_twiddles(ctx, ny, &c.tw);
+    if (rc) return rc;
+    DISPATCH_N(ny, rc = launch_cols<N_>(ctx, c, T));
+    return rc;
+}
+
+int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx) {
+    int rc = get_twiddles(ctx, nx, &r.tw);
+    if (rc) return rc;
+    DISPATCH_N(nx, rc = launch_rows_inv<N_>(ctx, r, T, nullptr));
+    return rc;
+}
+
+// frames per internal batch: keeps the blocked intermediates of a batch L2-sized
+int64_t batch_frames(int ny, int nx, int n_intermediates) {
+    const size_t per = (size_t)ny * (nx / 2) * sizeof(float2) * (size_t)n_intermediates;
+    int64_t b = (int64_t)((96ull << 20) / (per ? per : 1));
+    if (b < 1) b = 1;
+    if (b > 4096) b = 4096;
+    return b;
+}
+
+}  // namespace
+
+void b4d_fft_release(b4d_ctx* ctx) {
+    if (!ctx->fft) return;
+    for (int i = 0; i < 5; ++i) if (ctx->fft->tw[i]) cudaFree(ctx->fft->tw[i]);
+    if (ctx->fft->ref) cudaFree(ctx->fft->ref);
+    if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
+    if (ctx->fft->theta) cudaFree(ctx->fft->theta);
+    delete ctx->fft;
+    ctx->fft = nullptr;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_fft2d", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_fft2d: null output");
+    const int64_t B = batch_frames(ny, nx, 1);
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        Work w;
+        if ((rc = carve(ctx, tc, ny, nx, false, false, &w))) return rc;
+        if ((rc = run_rows_fwd(ctx, stack + (size_t)t0 * ny * nx, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        ColsArgs c = cols_defaults(w, nx, true);
+        c.cplx_out = reinterpret_cast<float2*>(out_c64) + (size_t)t0 * ny * nx;
+        if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+    }
+    return B4D_OK;
+}
+
+extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float scale_factor,
+                         int sub_mean, int zero_dc, float* out_psd, double* spectral) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_psd2d", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!out_psd && !spectral) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_psd2d: nothing to compute");
+    const bool want_f95 = spectral && ny == nx;
+    float* map = out_psd;
+    const int64_t B = batch_frames(ny, nx, 1);
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        Work w;
+        if ((rc = carve(ctx, tc, ny, nx, false, false, &w))) return rc;
+        float* map_b = map ? map + (size_t)t0 * ny * nx : nullptr;
+        if (want_f95 && !map) {   // f95 needs the map: keep it in scratch
+            void* p = nullptr;
+            if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)tc * ny * nx, &p))) return rc;
+            map_b = static_cast<float*>(p);
+        }
+        if ((rc = run_rows_fwd(ctx, stack + (size_t)t0 * ny * nx, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        ColsArgs c = cols_defaults(w, nx, true);
+        c.zero_dc = (sub_mean || zero_dc) ? 1 : 0;
+        c.psd_out = map_b;
+        c.psd_scale = scale_factor;
+        c.spec_partials = spectral ? w.spp : nullptr;
+        if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+        if (spectral) {
+            double* tab = spectral + t0 * B4D_SP_NCOLS;
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, nx / 16, tab, tc);
+            B4D_LAUNCH_CHECK(ctx);
+            if (want_f95) {
+                const int n = ny, nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
+                void* p = nullptr;
+                const size_t hb = sizeof(double) * (size_t)tc * (nb0 > nb1 ? nb0 : nb1);
+                if ((rc = b4d_scratch(ctx, SCR_SELECT, hb + (sizeof(int) + sizeof(double)) * tc + 256, &p))) return rc;
+                double* hist = static_cast<double*>(p);
+                double* below = reinterpret_cast<double*>(static_cast<char*>(p) + hb);
+                int* cb = reinterpret_cast<int*>(below + tc);
+                B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hb, ctx->stream));
+                int bx = (int)(((int64_t)n * n + 256 * 32 - 1) / (256 * 32));
+                if (bx > 296) bx = 296;
+                for (int level = 0; level < 2; ++level) {
+                    const int nb = level ? nb1 : nb0;
+                    f95_hist_kernel<<<dim3(bx, (unsigned)tc), 256, nb * sizeof(double), ctx->stream>>>(map_b, n, level, cb, hist, nb);
+                    B4D_LAUNCH_CHECK(ctx);
+                    f95_scan_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(hist, nb, level, tab, cb, below, n, tab, tc);
+                    B4D_LAUNCH_CHECK(ctx);
+                }
+            }
+        }
+    }
+    return B4D_OK;
+}
+
+namespace {
+
+// autocorrelation of a batch already in HBM; out_ac may live in scratch
+int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx, int use_norm, double norm_mult,
+                   float* out_ac, double fraction, double* grain_out, int zero_dc) {
+    Work w;
+    int rc;
+    if ((rc = carve(ctx, tc, ny, nx, true, false, &w))) return rc;
+    if ((rc = run_rows_fwd(ctx, stack, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+    ColsArgs c = cols_defaults(w, nx, true);
+    c.zero_dc = zero_dc;
+    c.i2_ac = w.I2a;
+    c.ac_partials = w.acp;
+    if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+    RowsInvArgs r;
+    memset(&r, 0, sizeof(r));
+    r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = out_ac; r.kindA = 0;
+    r.normA = use_norm ? w.acp : nullptr; r.n_normA = nx / 16; r.norm_mult = norm_mult;
+    r.scaleA = 1.0 / ((double)nx * (double)ny);
+    r.bestA = grain_out ? w.bestA : nullptr;
+    if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+    if (grain_out) {
+        if ((rc = ensure_theta(ctx))) return rc;
+        const int nblk = rows_inv_blocks(nx, ny, 0);
+        argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
+        B4D_LAUNCH_CHECK(ctx);
+        grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(out_ac, ny, w.pk_idx, ctx->fft->theta, fraction, grain_out);
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
+}  // namespace
+
+extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int remove_mean,
+                              int standardize, int normalize_peak, float* out_ac, double fraction, double* grain_out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!out_ac && !grain_out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_autocorr2d: nothing to compute");
+    if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_autocorr2d: grain widths need a square frame (pad_to_square first)");
+    if (grain_out && !(fraction > 0.0 && fraction < 1.0)) return b4d_fail(ctx, B4D_ERR_INVALID, "fraction must be in (0, 1).");
+    if (standardize && !normalize_peak && !remove_mean)
+        return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_autocorr2d: standardize=1 with remove_mean=0 and normalize='none' is not built");
+    // Peak normalisation cancels the /std of `standardize` exactly. Without it, the zero lag of the
+    // standardised map is n = ny*nx (n var / var), i.e. the peak-normalised map times n.
+    const int use_norm = normalize_peak || standardize;
+    const double norm_mult = (standardize && !normalize_peak) ? (double)ny * (double)nx : 1.0;
+    const int64_t B = batch_frames(ny, nx, 2);
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        float* o = out_ac ? out_ac + (size_t)t0 * ny * nx : nullptr;
+        if (!o) {
+            void* p = nullptr;
+            if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)tc * ny * nx, &p))) return rc;
+            o = static_cast<float*>(p);
+        }
+        rc = autocorr_batch(ctx, stack + (size_t)t0 * ny * nx, tc, ny, nx, use_norm, norm_mult, o, fraction,
+                            grain_out ? grain_out + t0 * 4 : nullptr, remove_mean ? 1 : 0);
+        if (rc) return rc;
+    }
+    return B4D_OK;
+}
+
+extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx, int remove_mean,
+                           int standardize, int normalize_peak, float* out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_xcorr2d", a, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!b || !out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_xcorr2d: null pointer");
+    const int64_t B = batch_frames(ny, nx, 3);
+    const size_t per = (size_t)ny * (nx / 2);
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        Work w;
+        if ((rc = carve(ctx, tc, ny, nx, true, true, &w))) return rc;
+        // conj spectrum of b -> I2b (blocked) + Nyquist columns in scratch
+        void* p = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float2) * (size_t)tc * ny + sizeof(double) * 2 * B4D_FR_NCOLS * tc, &p))) return rc;
+        float2* bnyq = static_cast<float2*>(p);
+        if ((rc = run_rows_fwd(ctx, b + (size_t)t0 * ny * nx, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        ColsArgs cb = cols_defaults(w, nx, true);
+        cb.zero_dc = remove_mean ? 1 : 0;
+        cb.conj_out = w.I2b;
+        cb.conj_nyq_out = bnyq;
+        if ((rc = run_cols(ctx, cb, tc, ny))) return rc;
+        // spectrum of a times conj spectrum of b, inverse along y -> I2a
+        if ((rc = run_rows_fwd(ctx, a + (size_t)t0 * ny * nx, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        ColsArgs ca = cols_defaults(w, nx, true);
+        ca.zero_dc = remove_mean ? 1 : 0;
+        ca.i2_pc = w.I2a;
+        ca.R = w.I2b; ca.Rnyq = bnyq; ca.r_stride = per; ca.rnyq_stride = (size_t)ny;
+        ca.whiten = 0; ca.eps = 0.f;
+        if ((rc = run_cols(ctx, ca, tc, ny))) return rc;
+        RowsInvArgs r;
+        memset(&r, 0, sizeof(r));
+        float* o = out + (size_t)t0 * ny * nx;
+        r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = o; r.kindA = 0;
+        r.scaleA = 1.0 / ((double)nx * (double)ny);
+        if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+        if (standardize && !normalize_peak)
+            return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_xcorr2d: standardize=1 with normalize='none' is applied by the host wrapper");
+        if (normalize_peak) {
+            absmax_kernel<<<(unsigned)tc, 256, 0, ctx->stream>>>(o, (int64_t)ny * nx, w.pk_val);
+            B4D_LAUNCH_CHECK(ctx);
+            scale_by_kernel<<<dim3(64, (unsigned)tc), 256, 0, ctx->stream>>>(o, (int64_t)ny * nx, w.pk_val, 1);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+    }
+    return B4D_OK;
+}
+
+extern "C" int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0,
+                                       double eps) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_phase_set_reference", tpl, 1, ny, nx);
+    if (rc) return rc;
+    if (h < 1 || w < 1 || y0 < 0 || x0 < 0 || y0 + h > ny || x0 + w > nx)
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_set_reference: template does not fit the frame");
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    FftPlanCache* f = ctx->fft;
+    if (f->ref_ny != ny || f->ref_nx != nx) {
+        if (f->ref) { B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(f->ref); cudaFree(f->ref_nyq); f->ref = nullptr; f->ref_nyq = nullptr; }
+        B4D_CUDA(ctx, cudaMalloc(&f->ref, sizeof(float2) * (size_t)ny * (nx / 2)));
+        B4D_CUDA(ctx, cudaMalloc(&f->ref_nyq, sizeof(float2) * (size_t)ny));
+        f->ref_ny = ny; f->ref_nx = nx;
+    }
+    void* p = nullptr;
+    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)ny * nx, &p))) return rc;
+    float* padded = static_cast<float*>(p);
+    embed_template_kernel<<<1, 1024, 0, ctx->stream>>>(tpl, h, w, ny, nx, y0, x0, (float)eps, padded);
+    B4D_LAUNCH_CHECK(ctx);
+    Work wk;
+    if ((rc = carve(ctx, 1, ny, nx, false, false, &wk))) return rc;
+    if ((rc = run_rows_fwd(ctx, padded, 1, ny, nx, nullptr, nullptr, wk, false))) return rc;
+    ColsArgs c = cols_defaults(wk, nx, false);
+    c.conj_out = f->ref;
+    c.conj_nyq_out = f->ref_nyq;
+    return run_cols(ctx, c, 1, ny);
+}
+
+namespace {
+
+int track_finish(b4d_ctx* ctx, Work& w, const float* mag, int64_t tc, int ny, int nx, int nblk, int subpixel, double eps,
+                 double* out) {
+    argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestB, nblk, w.pk_idx, w.pk_val);
+    B4D_LAUNCH_CHECK(ctx);
+    void* p = nullptr;
+    int rc = b4d_scratch(ctx, SCR_MISC, 1024, &p);   // already sized by carve(); first 512 B hold the quantile
+    if (rc) return rc;
+    static const double half = 0.5;
+    B4D_CUDA(ctx, cudaMemcpyAsync(p, &half, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = b4d_select_impl(ctx, mag, tc, (int64_t)ny * nx, static_cast<const double*>(p), 1, 1, w.med,
+                              reinterpret_cast<int64_t*>(w.nvalid))))
+        return rc;
+    phase_finalize_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(mag, w.pk_idx, ny, nx, w.med, w.nvalid, subpixel,
+                                                                              eps, out, tc);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+}  // namespace
+
+int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                                const float* dark, double sat_value, double zero_eps, double* out);
+
+extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps,
+                               double* out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_phase_track", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
+    if (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx)
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: call b4d_phase_set_reference for (%d, %d) frames first", ny, nx);
+    const int64_t B = batch_frames(ny, nx, 4);
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + (size_t)t0 * ny * nx;
+        Work w;
+        if ((rc = carve(ctx, tc, ny, nx, false, true, &w))) return rc;
+        void* p = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)tc * ny * nx + sizeof(double) * B4D_FR_NCOLS * tc, &p))) return rc;
+        float* mag = static_cast<float*>(p);
+        double* fr = reinterpret_cast<double*>(mag + (size_t)tc * ny * nx);
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, fr))) return rc;
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        ColsArgs c = cols_defaults(w, nx, true);
+        c.i2_pc = w.I2b;
+        c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
+        c.whiten = 1; c.eps = (float)eps;
+        c.fr = fr; c.fr_stride = B4D_FR_NCOLS;
+        if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+        RowsInvArgs r;
+        memset(&r, 0, sizeof(r));
+        r.Ia = w.I2b; r.ny = ny; r.pair_maps = 0; r.outA = mag; r.kindA = 1;
+        r.scaleA = 1.0 / ((double)nx * (double)ny);
+        r.bestA = w.bestB;
+        if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+        if ((rc = track_finish(ctx, w, mag, tc, ny, nx, rows_inv_blocks(nx, ny, 0), subpixel, eps, out + t0 * 4))) return rc;
+    }
+    return B4D_OK;
+}
+
+extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                                  const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
+                                  double eps, double* fr_out, float* psd_out, float* ac_out, double* grain_out,
+                                  double* track_out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
+    if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: grain widths need square frames");
+    const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
+    if (want_pc && (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx))
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tracking needs b4d_phase_set_reference for (%d, %d) frames", ny, nx);
+    const int64_t B = batch_frames(ny, nx, 5);
+    const size_t npix = (size_t)ny * nx;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + (size_t)t0 * npix;
+        Work w;
+        if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w))) return rc;
+        // scratch maps: |corr| always, autocorr when the caller does not keep it
+        void* p = nullptr;
+        const size_t need = sizeof(float) * npix * tc * ((want_pc ? 1 : 0) + ((want_ac && !ac_out) ? 1 : 0)) +
+                            sizeof(double) * B4D_FR_NCOLS * tc + 256;
+        if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
+        double* fr = static_cast<double*>(p);
+        float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
+        float* acm = ac_out ? ac_out + (size_t)t0 * npix : (want_pc ? mag + npix * tc : mag);
+        double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : fr;
+        if (fr_out || want_pc) {
+            if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp))) return rc;
+        }
+        if (!(psd_out || want_ac || want_pc)) continue;
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true))) return rc;
+        ColsArgs c = cols_defaults(w, nx, true);
+        c.psd_out = psd_out ? psd_out + (size_t)t0 * npix : nullptr;
+        c.psd_scale = psd_scale;
+        if (want_ac) { c.i2_ac = w.I2a; c.ac_partials = w.acp; }
+        if (want_pc) {
+            c.i2_pc = w.I2b;
+            c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
+            c.whiten = 1; c.eps = (float)eps; c.fr = frp; c.fr_stride = B4D_FR_NCOLS;
+        }
+        // psd2d keeps the DC bin, the autocorrelation (remove_mean) drops it: ac_zero_dc handles that in-kernel.
+        c.zero_dc = 0;
+        c.ac_zero_dc = 1;
+        if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+        RowsInvArgs r;
+        memset(&r, 0, sizeof(r));
+        r.ny = ny;
+        int nblk;
+        if (want_ac && want_pc) {
+            r.Ia = w.I2a; r.Ib = w.I2b; r.pair_maps = 1;
+            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 16; r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
+            r.bestA = grain_out ? w.bestA : nullptr;
+            r.outB = mag; r.kindB = 1; r.scaleB = 1.0 / ((double)nx * ny); r.bestB = w.bestB;
+            nblk = rows_inv_blocks(nx, ny, 1);
+        } else if (want_ac) {
+            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 16; r.norm_mult = 1.0;
+            r.scaleA = 1.0 / ((double)nx * ny); r.bestA = grain_out ? w.bestA : nullptr;
+            nblk = rows_inv_blocks(nx, ny, 0);
+        } else {
+            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
+            nblk = rows_inv_blocks(nx, ny, 0);
+        }
+        if (want_ac || want_pc) {
+            if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+        }
+        if (grain_out) {
+            if ((rc = ensure_theta(ctx))) return rc;
+            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
+            B4D_LAUNCH_CHECK(ctx);
+            grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx, ctx->fft->theta, 0.36787944117144233,
+                                                                 grain_out + t0 * 4);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if (want_pc) {
+            if ((rc = track_finish(ctx, w, mag, tc, ny, nx, nblk, subpixel, eps, track_out + t0 * 4))) return rc;
+        }
+    }
+    return B4D_OK;
+}

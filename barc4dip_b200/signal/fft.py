@@ -1,0 +1,52 @@
+"""
+Shifted 2-D FFT and power spectral density on the B200 path.
+
+Drop-in for barc4dip.signal.fft (fft2d :198-237, psd2d :261-309, freq_axes2d :58-96): same
+signatures, DC-centred outputs, shifted frequency axes.  float32 input gives complex64 / float32
+output like the reference on numpy >= 2; other input dtypes are computed in float32 on the device
+and returned in the dtype the reference would return (complex128 / float64).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import engine
+from .common import resolve_steps_2d
+
+
+def freq_axes2d(*, shape, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
+    ny, nx = shape
+    if ny < 1 or nx < 1:
+        raise ValueError("shape must contain positive integers.")
+    sx, sy = resolve_steps_2d(shape=shape, x=x, y=y, dx=dx, dy=dy)
+    return (np.fft.fftshift(np.fft.fftfreq(int(nx), d=sx)), np.fft.fftshift(np.fft.fftfreq(int(ny), d=sy)))
+
+
+def _out_real_dtype(img: np.ndarray):
+    return np.float32 if img.dtype == np.float32 else np.float64
+
+
+def fft2d(image, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
+    """F = fftshift(fft2(image)) with shifted (fx, fy)."""
+    img = np.asarray(image)
+    if img.ndim != 2:
+        raise ValueError("image must be a 2D array.")
+    fx, fy = freq_axes2d(shape=img.shape, x=x, y=y, dx=dx, dy=dy)
+    F = engine.fft2d(engine.as_stack(img))[0].cpu().numpy()
+    if img.dtype != np.float32:
+        F = F.astype(np.complex128)
+    return F, fx, fy
+
+
+def psd2d(image, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0, scale: bool = True):
+    """P = |fftshift(fft2(image))|^2, times dx*dy/(nx*ny) when scale is True. No mean removal."""
+    img = np.asarray(image)
+    if img.ndim != 2:
+        raise ValueError("image must be a 2D array.")
+    ny, nx = img.shape
+    sx, sy = resolve_steps_2d(shape=(ny, nx), x=x, y=y, dx=dx, dy=dy)
+    fx, fy = freq_axes2d(shape=(ny, nx), x=x, y=y, dx=dx, dy=dy)
+    factor = (sx * sy) / (float(nx) * float(ny)) if scale else 1.0
+    P, _ = engine.psd2d(engine.as_stack(img), scale_factor=factor)
+    return P[0].cpu().numpy().astype(_out_real_dtype(img), copy=False), fx, fy

@@ -1,0 +1,152 @@
+"""GPU tier: FFT / PSD / autocorrelation / tracking vs the goldens recorded from the reference and the oracle."""
+
+import numpy as np
+import pytest
+
+from oracle import golden_cases as gc
+from oracle import ref_numpy as orc
+
+pytestmark = pytest.mark.gpu
+
+POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512"]
+PEAK_TOL = 1e-5     # north_star: PSD and autocorrelation within 1e-5 relative error of peak
+
+
+@pytest.fixture(scope="module")
+def sig():
+    from barc4dip_b200 import signal
+    return signal
+
+
+def _digest_close(a, g, prefix, tol):
+    a = np.asarray(a)
+    cy, cx = a.shape[0] // 2, a.shape[1] // 2
+    peak = float(np.max(np.abs(g[prefix + "_row"])))
+    for got, key in ((a[cy - 16:cy + 16, cx - 16:cx + 16], "_crop"), (a[cy, :], "_row"), (a[:, cx], "_col"),
+                     (a[:8, :8], "_corner")):
+        np.testing.assert_allclose(got, g[prefix + key], rtol=0, atol=tol * peak, err_msg=prefix + key)
+
+
+@pytest.mark.parametrize("name", POW2)
+def test_fft2d_psd2d_vs_golden(sig, golden, name):
+    g = golden("frames")
+    img = gc.frame_cases()[name]
+    F, fx, fy = sig.fft2d(img)
+    assert str(F.dtype) == str(g[f"{name}/fft2d_dtype"])
+    np.testing.assert_array_equal(fx, g[f"{name}/fx"])
+    np.testing.assert_array_equal(fy, g[f"{name}/fy"])
+    # the DC bin dwarfs everything else; judge the rest of the spectrum on its own scale too
+    _digest_close(F, g, f"{name}/fft2d", PEAK_TOL)
+    Fo, _, _ = orc.fft2d(np.asarray(img, dtype=np.float64))
+    Fnd, Fod = F.copy(), Fo.copy()
+    cy, cx = F.shape[0] // 2, F.shape[1] // 2
+    Fnd[cy, cx] = 0
+    Fod[cy, cx] = 0
+    assert np.max(np.abs(Fnd - Fod)) <= PEAK_TOL * np.max(np.abs(Fod))
+    P, _, _ = sig.psd2d(img)
+    assert str(P.dtype) == str(g[f"{name}/psd2d_dtype"])
+    _digest_close(P, g, f"{name}/psd2d", PEAK_TOL)
+    if f"{name}/psd2d_full" in g.files:
+        full = g[f"{name}/psd2d_full"]
+        assert np.max(np.abs(P - full)) <= PEAK_TOL * full.max()
+        Pnd = P.copy(); fnd = full.copy(); Pnd[cy, cx] = 0; fnd[cy, cx] = 0
+        assert np.max(np.abs(Pnd - fnd)) <= 1e-4 * fnd.max()
+    Pu, _, _ = sig.psd2d(img, dx=0.5, dy=2.0)
+    ref_row = g[f"{name}/psd2d_dx_row"]
+    np.testing.assert_allclose(Pu[Pu.shape[0] // 2], ref_row, rtol=0, atol=PEAK_TOL * ref_row.max())
+
+
+@pytest.mark.parametrize("name", POW2)
+def test_autocorr_xcorr_vs_golden(sig, golden, name):
+    g = golden("frames")
+    img = gc.frame_cases()[name]
+    ac, xl, yl = sig.autocorr2d(img)
+    assert str(ac.dtype) == str(g[f"{name}/autocorr2d_dtype"])
+    np.testing.assert_array_equal(xl, g[f"{name}/xlag"])
+    np.testing.assert_array_equal(yl, g[f"{name}/ylag"])
+    _digest_close(ac, g, f"{name}/autocorr2d", PEAK_TOL)
+    cy, cx = ac.shape[0] // 2, ac.shape[1] // 2
+    assert abs(ac[cy, cx] - 1.0) < 1e-6 and np.argmax(ac) == cy * ac.shape[1] + cx
+    if f"{name}/autocorr2d_full32" in g.files:
+        assert np.max(np.abs(ac - g[f"{name}/autocorr2d_full32"])) <= PEAK_TOL
+    a2, _, _ = sig.autocorr2d(img, standardize=True, normalize="none")
+    _digest_close(a2, g, f"{name}/autocorr2d_std_none", PEAK_TOL)
+    a3, _, _ = sig.autocorr2d(img, remove_mean=False, normalize="none")
+    _digest_close(a3, g, f"{name}/autocorr2d_raw_none", PEAK_TOL)
+    xc, _, _ = sig.xcorr2d(img, np.roll(np.asarray(img), (5, -7), axis=(0, 1)))
+    _digest_close(xc, g, f"{name}/xcorr2d_real", PEAK_TOL)
+    assert tuple(np.unravel_index(int(np.argmax(np.abs(xc))), xc.shape)) == tuple(g[f"{name}/xcorr2d_argmax"])
+
+
+def test_fft_roundtrip_and_parseval_2048():
+    """Full-size properties that need no oracle: Parseval and the zero-lag identity at 2048^2."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    img = synth.speckle_frame(2048, grain=6.0, seed=0)
+    d = engine.as_stack(img)
+    P, _ = engine.psd2d(d, scale_factor=1.0 / img.size)
+    x64 = img.astype(np.float64)
+    np.testing.assert_allclose(float(P.double().sum()), float((x64 ** 2).sum()), rtol=1e-5)
+    ac, _ = engine.autocorr2d(d, normalize_peak=False)
+    ac = ac[0].cpu().numpy()
+    np.testing.assert_allclose(ac[1024, 1024], img.size * x64.var(), rtol=1e-5)
+    assert np.argmax(ac) == 1024 * 2048 + 1024
+    # Hermitian symmetry of the shifted PSD: P[-k] = P[k]
+    p = P[0].cpu().numpy()
+    np.testing.assert_allclose(p[1:, 1:], p[1:, 1:][::-1, ::-1], rtol=1e-6, atol=1e-6 * p.max())
+
+
+def test_unsupported_sizes_fail_loudly(sig):
+    from barc4dip_b200._lib import B4DUnsupported
+    with pytest.raises(B4DUnsupported):
+        sig.psd2d(gc.frame_cases()["odd150x200"])
+    with pytest.raises(ValueError):
+        sig.psd2d(np.zeros((4, 4, 4), np.float32))
+    with pytest.raises(ValueError):
+        sig.xcorr2d(np.zeros((128, 128), np.float32), np.zeros((128, 256), np.float32))
+    with pytest.raises(ValueError):
+        sig.autocorr2d(np.zeros((128, 128), np.float32), normalize="max")
+
+
+def test_tracking_vs_golden(sig, golden):
+    g = golden("tracking")
+    for name, c in gc.tracking_cases().items():
+        got = sig.phase_correlation(c["template"], c["image"], slices_yx=c["slices"], subpixel=c["subpixel"])
+        want = g[f"{name}/result"]
+        # displacements within 0.01 px (north_star), peak 1e-4 relative
+        np.testing.assert_allclose(got[:2], want[:2], rtol=0, atol=0.01, err_msg=name)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-4, err_msg=name)
+        if "noise" in name or name.startswith("roi") or name == "zero_shift":
+            np.testing.assert_allclose(got[3], want[3], rtol=1e-3, err_msg=name + " snr")
+        got2 = sig.track_translation(c["template"], c["image"], slices_yx=c["slices"], method="phase",
+                                     backend="internal", subpixel=c["subpixel"])
+        assert got2 == got
+
+
+def test_tracking_quirks_and_errors(sig):
+    from barc4dip_b200._lib import B4DUnsupported
+    a = np.zeros((128, 128), np.float32)
+    with pytest.raises(ValueError):
+        sig.phase_correlation(a, a, slices_yx=None)           # even template without slices (quirk 7)
+    with pytest.raises(ValueError):
+        sig.track_translation(a, a, method="nope")
+    with pytest.raises(B4DUnsupported):
+        sig.track_translation(a, a, method="template")
+    with pytest.raises(ValueError):
+        sig.phase_correlation(a[:5, :5], a, slices_yx=(slice(0, 6), slice(0, 5)))
+
+
+def test_tracking_stack_matches_per_frame_and_oracle():
+    from barc4dip_b200 import engine, synth
+    stack, shifts = synth.tracking_stack(6, 256, grain=4.0, seed=31, integer_every=3)
+    full = (slice(0, 256), slice(0, 256))
+    tr = engine.PhaseTracker(stack[0], (256, 256), y0=0, x0=0)
+    tab = tr.track(engine.as_stack(stack))
+    for t in range(6):
+        want = orc.phase_correlation(stack[0], stack[t], slices_yx=full)
+        np.testing.assert_allclose(tab[t, :2], want[:2], atol=0.01)
+        np.testing.assert_allclose(tab[t, 2], want[2], rtol=1e-4)
+        if t:
+            np.testing.assert_allclose(tab[t, 3], want[3], rtol=1e-3)
+    # integer (np.roll) frames are known answers
+    np.testing.assert_allclose(tab[3, :2], shifts[3], atol=0.01)
