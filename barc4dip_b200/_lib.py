@@ -48,6 +48,10 @@ _SIGNATURES = {
     "b4d_version": [],
     "b4d_launch_count": [_vp],
     "b4d_device_sm_count": [_vp],
+    "b4d_profile_begin": [_vp],
+    "b4d_profile_end": [_vp, _vp, _vp],
+    "b4d_profile_class_name": [_i32],
+    "b4d_set_batch_frames": [_vp, _i64],
     "b4d_malloc": [_vp, C.c_size_t, C.POINTER(_vp)],
     "b4d_free": [_vp, _vp],
     "b4d_memcpy_h2d": [_vp, _vp, _vp, C.c_size_t],
@@ -69,7 +73,7 @@ _SIGNATURES = {
     "b4d_stack_pipeline": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64,
                            _vp, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"b4d_last_error": C.c_char_p, "b4d_version": C.c_char_p, "b4d_launch_count": _i64}
+_RESTYPES = {"b4d_profile_class_name": C.c_char_p, "b4d_last_error": C.c_char_p, "b4d_version": C.c_char_p, "b4d_launch_count": _i64}
 
 
 def exported_symbols() -> list[str]:
@@ -125,6 +129,20 @@ class Context:
         import torch
         s = torch.cuda.current_stream(self.device).cuda_stream
         self.check(self.lib.b4d_set_stream(self.handle, _vp(s)), "b4d_set_stream")
+
+    def profile_begin(self):
+        self.check(self.lib.b4d_profile_begin(self.handle), "b4d_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{class name: (milliseconds, launches)} of the kernels launched since profile_begin()."""
+        n = 11
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self.check(self.lib.b4d_profile_end(self.handle, ms, cnt), "b4d_profile_end")
+        return {self.lib.b4d_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def set_batch_frames(self, frames: int):
+        self.check(self.lib.b4d_set_batch_frames(self.handle, int(frames)), "b4d_set_batch_frames")
 
     @property
     def launches(self) -> int:

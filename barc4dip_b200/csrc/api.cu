@@ -28,6 +28,8 @@ extern "C" int b4d_destroy(b4d_ctx* ctx) {
     b4d_fft_release(ctx);
     for (int i = 0; i < 8; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;
     return B4D_OK;
 }
@@ -50,6 +52,44 @@ extern "C" const char* b4d_last_error(b4d_ctx* ctx) { return ctx ? ctx->last_err
 extern "C" int64_t b4d_launch_count(b4d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int b4d_device_sm_count(b4d_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int b4d_profile_begin(b4d_ctx* ctx) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    for (auto& sp : ctx->prof_spans) { ctx->prof_pool.push_back(sp.a); ctx->prof_pool.push_back(sp.b); }
+    ctx->prof_spans.clear();
+    ctx->prof_on = true;
+    return B4D_OK;
+}
+
+extern "C" int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* launches_per_class) {
+    if (!ctx || !ms_per_class || !launches_per_class) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->prof_on = false;
+    B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < KC_COUNT; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+    for (auto& sp : ctx->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { ms_per_class[sp.klass] += ms; launches_per_class[sp.klass]++; }
+        ctx->prof_pool.push_back(sp.a);
+        ctx->prof_pool.push_back(sp.b);
+    }
+    ctx->prof_spans.clear();
+    return B4D_OK;
+}
+
+extern "C" const char* b4d_profile_class_name(int k) {
+    static const char* names[KC_COUNT] = {"pilot", "frame_reduce", "rows_fwd", "cols", "rows_inv", "select_hist",
+                                          "select_scan", "grain", "temporal", "flatfield", "small"};
+    return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
+}
+
+extern "C" int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames) {
+    if (!ctx || frames < 0) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->batch_override = frames;
+    return B4D_OK;
+}
 
 extern "C" int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return B4D_ERR_INVALID;

@@ -13,7 +13,18 @@
 
 #include "../../include/b4d.h"
 
-struct FftPlanCache;   // fft.cu
+struct FftPlanCache;   // spectral.cu
+
+// kernel classes for the optional CUDA-event profile (b4d_profile_*)
+enum {
+    KC_PILOT = 0, KC_FRAME_REDUCE, KC_ROWS_FWD, KC_COLS, KC_ROWS_INV, KC_SELECT_HIST, KC_SELECT_SCAN, KC_GRAIN,
+    KC_TEMPORAL, KC_FLATFIELD, KC_SMALL, KC_COUNT
+};
+
+struct ProfSpan {
+    int klass;
+    cudaEvent_t a, b;
+};
 
 struct b4d_ctx {
     int device = 0;
@@ -25,7 +36,33 @@ struct b4d_ctx {
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     FftPlanCache* fft = nullptr;
+    int64_t batch_override = 0;       // frames per internal batch of the FFT pipeline (0 = automatic)
+    bool prof_on = false;
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+    int cur_class = KC_SMALL;
     std::mutex lock;
+};
+
+// Brackets the next launches with CUDA events when profiling is on (events live on ctx->stream).
+struct ProfScope {
+    b4d_ctx* c;
+    ProfSpan s;
+    bool on;
+    ProfScope(b4d_ctx* ctx, int klass) : c(ctx), on(ctx->prof_on) {
+        if (!on) return;
+        s.klass = klass;
+        for (cudaEvent_t* e : {&s.a, &s.b}) {
+            if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(s.a, c->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(s.b, c->stream);
+        c->prof_spans.push_back(s);
+    }
 };
 
 // scratch slot ids

@@ -302,6 +302,7 @@ int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_fram
 
 int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
                            const float* dark, float* pilot) {
+    ProfScope ps(ctx, KC_PILOT);
     pilot_kernel<<<(unsigned)T, 256, 0, ctx->stream>>>(stack, gain, dark, npix, pilot);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -355,9 +356,13 @@ int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_fram
         b.pilot = pilot + t0;
         b.partials = a.partials + (size_t)t0 * nblocks * FR_NACC;
         dim3 grid((unsigned)nblocks, (unsigned)tc);
-        if (vec) frame_reduce_kernel<true><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
-        else frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+        {
+            ProfScope ps(ctx, KC_FRAME_REDUCE);
+            if (vec) frame_reduce_kernel<true><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+            else frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+        }
         B4D_LAUNCH_CHECK(ctx);
+        ProfScope ps2(ctx, KC_SMALL);
         frame_finalize_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(b.partials, nblocks, b.pilot,
                                                                      (double)ny * (double)nx,
                                                                      out + t0 * B4D_FR_NCOLS);

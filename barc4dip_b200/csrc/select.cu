@@ -185,17 +185,23 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
         SelState* st0 = st + t0;
         float* o0 = out + t0 * nr;
         long long* nv0 = n_valid ? reinterpret_cast<long long*>(n_valid) + t0 : nullptr;
-        sel_hist_kernel<0><<<grid, SEL_THREADS, SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0);
+        { ProfScope ps(ctx, KC_SELECT_HIST);
+        sel_hist_kernel<0><<<grid, SEL_THREADS, SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
         B4D_LAUNCH_CHECK(ctx);
-        sel_scan_kernel<0><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0);
+        { ProfScope ps(ctx, KC_SELECT_SCAN);
+        sel_scan_kernel<0><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
         B4D_LAUNCH_CHECK(ctx);
-        sel_hist_kernel<1><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0);
+        { ProfScope ps(ctx, KC_SELECT_HIST);
+        sel_hist_kernel<1><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
         B4D_LAUNCH_CHECK(ctx);
-        sel_scan_kernel<1><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0);
+        { ProfScope ps(ctx, KC_SELECT_SCAN);
+        sel_scan_kernel<1><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
         B4D_LAUNCH_CHECK(ctx);
-        sel_hist_kernel<2><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0);
+        { ProfScope ps(ctx, KC_SELECT_HIST);
+        sel_hist_kernel<2><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
         B4D_LAUNCH_CHECK(ctx);
-        sel_scan_kernel<2><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0);
+        { ProfScope ps(ctx, KC_SELECT_SCAN);
+        sel_scan_kernel<2><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
         B4D_LAUNCH_CHECK(ctx);
     }
     return B4D_OK;

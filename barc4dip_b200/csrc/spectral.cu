@@ -815,6 +815,7 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     static bool attr = false;
     if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     if (a.ny % ROWS) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, ROWS);
+    ProfScope ps(ctx, KC_ROWS_FWD);
     rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -827,6 +828,7 @@ int launch_cols(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     const size_t smem = (size_t)PL * 8 * sizeof(float2) + (size_t)PL * sizeof(float2) + (both ? (size_t)PL * 8 * sizeof(float) : 0);
     static size_t attr = 0;
     if (attr < smem) { B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    ProfScope ps(ctx, KC_COLS);
     cols_kernel<NY><<<dim3(a.nx / 16, (unsigned)T), NY / 2, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -841,6 +843,7 @@ int launch_rows_inv(b4d_ctx* ctx, const RowsInvArgs& a, int64_t T, int* n_blocks
     const int rows = a.pair_maps ? FPC : 2 * FPC;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     if (n_blocks_out) *n_blocks_out = a.ny / rows;
+    ProfScope ps(ctx, KC_ROWS_INV);
     rows_inv_kernel<NX><<<dim3(a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -965,7 +968,8 @@ int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx) {
 }
 
 // frames per internal batch: keeps the blocked intermediates of a batch L2-sized
-int64_t batch_frames(int ny, int nx, int n_intermediates) {
+int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
+    if (ctx->batch_override > 0) return ctx->batch_override;
     const size_t per = (size_t)ny * (nx / 2) * sizeof(float2) * (size_t)n_intermediates;
     int64_t b = (int64_t)((96ull << 20) / (per ? per : 1));
     if (b < 1) b = 1;
@@ -994,7 +998,7 @@ extern "C" int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
     int rc = check_fft_args(ctx, "b4d_fft2d", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_fft2d: null output");
-    const int64_t B = batch_frames(ny, nx, 1);
+    const int64_t B = batch_frames(ctx, ny, nx, 1);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         Work w;
@@ -1016,7 +1020,7 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
     if (!out_psd && !spectral) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_psd2d: nothing to compute");
     const bool want_f95 = spectral && ny == nx;
     float* map = out_psd;
-    const int64_t B = batch_frames(ny, nx, 1);
+    const int64_t B = batch_frames(ctx, ny, nx, 1);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         Work w;
@@ -1088,6 +1092,7 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
         const int nblk = rows_inv_blocks(nx, ny, 0);
         argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
         B4D_LAUNCH_CHECK(ctx);
+        ProfScope ps(ctx, KC_GRAIN);
         grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(out_ac, ny, w.pk_idx, ctx->fft->theta, fraction, grain_out);
         B4D_LAUNCH_CHECK(ctx);
     }
@@ -1111,7 +1116,7 @@ extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames
     // standardised map is n = ny*nx (n var / var), i.e. the peak-normalised map times n.
     const int use_norm = normalize_peak || standardize;
     const double norm_mult = (standardize && !normalize_peak) ? (double)ny * (double)nx : 1.0;
-    const int64_t B = batch_frames(ny, nx, 2);
+    const int64_t B = batch_frames(ctx, ny, nx, 2);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         float* o = out_ac ? out_ac + (size_t)t0 * ny * nx : nullptr;
@@ -1134,7 +1139,7 @@ extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t
     int rc = check_fft_args(ctx, "b4d_xcorr2d", a, n_frames, ny, nx);
     if (rc) return rc;
     if (!b || !out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_xcorr2d: null pointer");
-    const int64_t B = batch_frames(ny, nx, 3);
+    const int64_t B = batch_frames(ctx, ny, nx, 3);
     const size_t per = (size_t)ny * (nx / 2);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
@@ -1240,7 +1245,7 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
     if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
     if (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: call b4d_phase_set_reference for (%d, %d) frames first", ny, nx);
-    const int64_t B = batch_frames(ny, nx, 4);
+    const int64_t B = batch_frames(ctx, ny, nx, 4);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         const float* s0 = stack + (size_t)t0 * ny * nx;
@@ -1282,7 +1287,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
     const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
     if (want_pc && (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tracking needs b4d_phase_set_reference for (%d, %d) frames", ny, nx);
-    const int64_t B = batch_frames(ny, nx, 5);
+    const int64_t B = batch_frames(ctx, ny, nx, 5);
     const size_t npix = (size_t)ny * nx;
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
@@ -1341,6 +1346,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
             if ((rc = ensure_theta(ctx))) return rc;
             argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
             B4D_LAUNCH_CHECK(ctx);
+            ProfScope ps(ctx, KC_GRAIN);
             grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx, ctx->fft->theta, 0.36787944117144233,
                                                                  grain_out + t0 * 4);
             B4D_LAUNCH_CHECK(ctx);

@@ -204,6 +204,7 @@ extern "C" int b4d_temporal_accumulate(b4d_ctx* ctx, const float* stack, int64_t
     const int64_t npix = (int64_t)ny * nx;
     const bool vec = npix % 4 == 0 && aligned16(stack) && aligned16(shift) && aligned16(sums) &&
                      (!gain || aligned16(gain)) && (!dark || aligned16(dark));
+    ProfScope ps(ctx, KC_TEMPORAL);
     if (vec) {
         const int64_t quads = npix / 4;
         const unsigned gx = (unsigned)((quads + 255) / 256);
@@ -259,6 +260,7 @@ extern "C" int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frame
     const int64_t npix = (int64_t)ny * nx;
     const unsigned gx = (unsigned)((npix + 255) / 256);
     unsigned gy = (unsigned)(n_frames < 64 ? n_frames : 64);
+    ProfScope ps(ctx, KC_FLATFIELD);
     flat_field_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(images, n_frames, npix, flat, dark, eps, scale_value,
                                                              apply_scale, out);
     B4D_LAUNCH_CHECK(ctx);

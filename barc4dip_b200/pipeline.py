@@ -1,0 +1,213 @@
+"""
+The public stack-analysis call: host stack in, host results out, frames resident in HBM in between.
+
+    analyzer = StackAnalyzer((ny, nx), reference=frame0)        # reference frame for the tracker
+    res = analyzer.run(stack)                                    # numpy (T, ny, nx) or CUDA tensor
+
+One fused pass per chunk of frames (b4d_stack_pipeline) produces, per frame,
+  * the single-pass reductions (distribution moments, Tenengrad, Laplacian variance, visibility),
+  * the exact 0.05 / 99.95 percentile contrast (amplitude),
+  * the PSD map (psd2d) and the peak-normalised autocorrelation map (autocorr2d) with the grain widths,
+  * the phase-correlation displacement against the reference frame (dy, dx, peak, snr).
+Host input is staged through pinned memory in chunks; the H2D copy of chunk c+1 and the D2H copy of chunk
+c-1 overlap the kernels of chunk c on separate CUDA streams.
+
+This is the reference's per-frame Python loop (metrics/speckles.py:300-325, :347-386) collapsed into batched
+kernels; results use the reference's names and conventions.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine, stack as blocks
+from ._lib import FR_NCOLS, get_context, require_cuda
+
+
+class StackAnalyzer:
+    def __init__(self, frame_shape, *, reference=None, device: int | None = None, chunk_frames: int = 16,
+                 want_maps: bool = True, want_contrast: bool = True, saturation_value: float | None = 65535.0,
+                 eps: float = 1e-6, subpixel: bool = True, flats=None, darks=None, scale: str = "flat_median",
+                 flat_eps: float | None = None):
+        torch = require_cuda()
+        from ._lib import default_device
+        self.dev = default_device() if device is None else int(device)
+        self.ny, self.nx = int(frame_shape[0]), int(frame_shape[1])
+        engine.check_fft_shape(self.ny, self.nx)
+        self.chunk = int(chunk_frames)
+        self.want_maps, self.want_contrast = bool(want_maps), bool(want_contrast)
+        self.sat, self.eps, self.subpixel = saturation_value, float(eps), bool(subpixel)
+        self.device = torch.device(f"cuda:{self.dev}")
+        self.gain = self.dark = self.flat = None
+        self._ff = None
+        if flats is not None:
+            from .preprocessing.normalize import _collapse, resolve_flat_field
+            flat, dark = _collapse(flats, self.dev), _collapse(darks, self.dev)
+            e, s, apply_scale = resolve_flat_field(flat, dark, scale=scale, eps=flat_eps)
+            self.flat, self.dark = flat, (dark if dark is not None else torch.zeros_like(flat))
+            self._ff = dict(eps=e, scale_value=s, apply_scale=apply_scale)
+            # per-pixel multiplier used by the fused loaders: (raw - dark) * gain
+            self.gain = engine.flat_gain(flat, dark, eps=e, scale_value=s if apply_scale else 1.0)
+        self.tracker = None
+        if reference is not None:
+            self.set_reference(reference)
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]   # h2d, compute, d2h
+        self._stage = None
+
+    # the reference frame is corrected like every other frame when a flat field is installed
+    def set_reference(self, frame, *, slices_yx=None):
+        torch = require_cuda()
+        ref = engine.as_stack(frame, self.dev)
+        if self.gain is not None:
+            ref = engine.flat_field(ref, self.flat, self.dark, **self._ff)
+        ref = ref[0]
+        if slices_yx is None:
+            y0 = x0 = 0
+            tpl = ref
+        else:
+            sy, sx = slices_yx
+            y0, x0 = int(sy.start), int(sx.start)
+            tpl = ref[sy, sx].contiguous()
+        self.tracker = engine.PhaseTracker(tpl, (self.ny, self.nx), y0=y0, x0=x0, device=self.dev)
+
+    def _buffers(self, pinned_out: bool):
+        torch = require_cuda()
+        if self._stage is None:
+            c, ny, nx = self.chunk, self.ny, self.nx
+            dev = self.device
+            self._stage = {
+                "in": [torch.empty((c, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)],
+                "psd": [torch.empty((c, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)] if self.want_maps else None,
+                "ac": [torch.empty((c, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)] if self.want_maps else None,
+            }
+        return self._stage
+
+    def run_device(self, dev_stack, *, psd_out=None, ac_out=None) -> dict:
+        """Analyse an HBM-resident (T, ny, nx) float32 stack; everything stays on the device."""
+        res = engine.stack_pipeline(dev_stack, gain=self.gain, dark=self.dark, saturation_value=self.sat, eps=self.eps,
+                                    subpixel=self.subpixel, want_psd=self.want_maps or psd_out is not None,
+                                    want_autocorr=True, want_grain=True, want_tracking=self.tracker is not None,
+                                    psd_out=psd_out, ac_out=ac_out)
+        if self.want_contrast:
+            src = dev_stack
+            if self.gain is not None:      # percentiles need the corrected pixels materialised once
+                src = engine.flat_field(dev_stack, self.flat, self.dark, **self._ff)
+            res["quantiles"], res["n_valid"] = engine.select_quantiles(src, [0.05 / 100.0, 99.95 / 100.0],
+                                                                      return_device=True)
+        return res
+
+    def run(self, stack, *, keep_maps_on_device: bool = False) -> dict:
+        """(T, ny, nx) numpy (or CUDA tensor) -> dict of numpy results (maps as float32 arrays, or device tensors)."""
+        torch = require_cuda()
+        is_host = not (isinstance(stack, torch.Tensor) and stack.device.type == "cuda")
+        T = int(stack.shape[0])
+        if tuple(stack.shape[1:]) != (self.ny, self.nx):
+            raise ValueError("frame shape differs from the analyzer's")
+        ny, nx, c = self.ny, self.nx, self.chunk
+        h2d, comp, d2h = self._streams
+        st = self._buffers(True)
+        if is_host:
+            src = stack if isinstance(stack, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(stack, dtype=np.float32))
+        fr_all = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=self.device)
+        grain_all = torch.empty((T, 4), dtype=torch.float64, device=self.device)
+        track_all = torch.empty((T, 4), dtype=torch.float64, device=self.device) if self.tracker is not None else None
+        q_all = torch.empty((T, 4), dtype=torch.float32, device=self.device) if self.want_contrast else None
+        nv_all = torch.empty((T,), dtype=torch.int64, device=self.device) if self.want_contrast else None
+        maps_host = None
+        if self.want_maps and not keep_maps_on_device:
+            # pinned result buffers are cached per stack length: pinning 34 MB per frame is not free
+            cache = getattr(self, "_host_maps", None)
+            if cache is None or cache["psd"].shape[0] != T:
+                cache = {k: torch.empty((T, ny, nx), dtype=torch.float32, pin_memory=True) for k in ("psd", "ac")}
+                self._host_maps = cache
+            maps_host = cache
+        maps_dev = {k: torch.empty((T, ny, nx), dtype=torch.float32, device=self.device) for k in ("psd", "ac")} \
+            if (self.want_maps and keep_maps_on_device) else None
+
+        ctx = get_context(self.dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        n_chunks = (T + c - 1) // c
+        for i in range(n_chunks):
+            a, b = i * c, min(T, (i + 1) * c)
+            n = b - a
+            s = i & 1
+            if is_host:
+                with torch.cuda.stream(h2d):
+                    if i >= 2:
+                        h2d.wait_event(ev_done[s])          # the kernels that read this staging buffer have finished
+                    st["in"][s][:n].copy_(src[a:b], non_blocking=True)
+                    ev_in[s].record(h2d)
+                frames = st["in"][s][:n]
+            else:
+                frames = stack[a:b]
+            with torch.cuda.stream(comp):
+                if is_host:
+                    comp.wait_event(ev_in[s])
+                if self.want_maps and not keep_maps_on_device and i >= 2:
+                    comp.wait_event(ev_out[s])              # the D2H that drained this map buffer has finished
+                ctx.use_current_stream()
+                if self.want_maps:
+                    po = maps_dev["psd"][a:b] if keep_maps_on_device else st["psd"][s][:n]
+                    ao = maps_dev["ac"][a:b] if keep_maps_on_device else st["ac"][s][:n]
+                else:
+                    po = ao = None
+                res = self.run_device(frames, psd_out=po, ac_out=ao)
+                fr_all[a:b].copy_(res["reductions"])
+                grain_all[a:b].copy_(res["grain"])
+                if track_all is not None:
+                    track_all[a:b].copy_(res["tracking"])
+                if q_all is not None:
+                    q_all[a:b].copy_(res["quantiles"])
+                    nv_all[a:b].copy_(res["n_valid"])
+                ev_done[s].record(comp)
+            if maps_host is not None:
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev_done[s])
+                    maps_host["psd"][a:b].copy_(st["psd"][s][:n], non_blocking=True)
+                    maps_host["ac"][a:b].copy_(st["ac"][s][:n], non_blocking=True)
+                    ev_out[s].record(d2h)
+        for s_ in self._streams:
+            s_.synchronize()
+        ctx.use_current_stream()
+
+        fr = fr_all.cpu().numpy()
+        out = {"stats": blocks.moments_block(fr, self.sat), "gradient": blocks.gradient_block(fr),
+               "laplacian": blocks.laplacian_block(fr), "table": fr}
+        g = grain_all.cpu().numpy()
+        out["grain"] = {"lx": g[:, 0], "ly": g[:, 1], "leq": g[:, 2], "r": g[:, 3]}
+        with np.errstate(invalid="ignore", divide="ignore"):
+            vis = np.sqrt(fr[:, 2]) / fr[:, 1]
+        amp = {"visibility": vis}
+        if q_all is not None:
+            q, nv = q_all.cpu().numpy(), nv_all.cpu().numpy()
+            con = np.empty(T)
+            for t in range(T):
+                lo = engine.quantile_from_bracket(q[t, 0], q[t, 1], int(nv[t]), 0.05 / 100.0)
+                hi = engine.quantile_from_bracket(q[t, 2], q[t, 3], int(nv[t]), 99.95 / 100.0)
+                con[t] = (hi - lo) / (hi + lo) if (hi + lo) > 0 else np.nan
+            amp["contrast"] = con
+        out["amplitude"] = amp
+        if track_all is not None:
+            tr = track_all.cpu().numpy()
+            out["tracking"] = {"dy": tr[:, 0], "dx": tr[:, 1], "peak": tr[:, 2], "snr": tr[:, 3]}
+        if maps_host is not None:
+            out["psd"], out["autocorr"] = maps_host["psd"].numpy(), maps_host["ac"].numpy()
+        elif maps_dev is not None:
+            out["psd"], out["autocorr"] = maps_dev["psd"], maps_dev["ac"]
+        return out
+
+    def bytes_per_frame(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes per frame of run() with host input."""
+        npix = self.ny * self.nx
+        d2h = (FR_NCOLS + 4 + (4 if self.tracker is not None else 0)) * 8 + (4 * 4 + 8 if self.want_contrast else 0)
+        if self.want_maps:
+            d2h += 2 * npix * 4
+        return npix * 4, d2h
+
+
+def analyze_stack(stack, *, reference=None, **kw) -> dict:
+    """Convenience wrapper: analyse a (T, ny, nx) stack against `reference` (default: its first frame)."""
+    a = StackAnalyzer(stack.shape[1:], reference=stack[0] if reference is None else reference, **kw)
+    return a.run(stack)

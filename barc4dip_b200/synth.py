@@ -89,7 +89,9 @@ def tracking_stack(t: int, n: int, *, grain: float = 6.0, seed: int = 0,
                    walk_seed: int = 2, noise_seed: int = 3, step_sigma: float = 0.3,
                    clip: float = 20.0, noise_frac: float = 0.01,
                    integer_every: int = 0) -> tuple[np.ndarray, np.ndarray]:
-    """Config-4 style stack: frame t = frame 0 translated along a 2-D random walk + 1 % noise.
+    """Config-4 style stack: frame t = a clean speckle translated along a 2-D random walk + 1 % noise
+    (independent noise on every frame, frame 0 included: a noise-free band-limited reference would leave the
+    phase of its empty spectral bins to FFT rounding noise and make the tracker's output ill-conditioned).
 
     Returns (stack (t, n, n) float32, shifts (t, 2) float64 as (dy, dx)); shifts[0] = (0, 0).
     If integer_every > 0 every such frame gets an integer (np.roll) shift: a known-answer case.
@@ -105,7 +107,7 @@ def tracking_stack(t: int, n: int, *, grain: float = 6.0, seed: int = 0,
         shifts[0] = 0.0
     sigma = noise_frac * float(base.mean())
     out = np.empty((t, n, n), dtype=np.float32)
-    out[0] = base
+    out[0] = base + nrng.normal(0.0, sigma, size=(n, n)).astype(np.float32)   # the reference frame is noisy too
     for k in range(1, t):
         fr = fourier_shift(base, shifts[k, 0], shifts[k, 1])
         out[k] = fr + nrng.normal(0.0, sigma, size=(n, n)).astype(np.float32)

@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""
+Benchmark of the barc4dip stack-analysis hot path on B200 (and of the reference's CPU path).
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (N > 1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): stack frames/s at 2048^2 for the fused FFT-PSD + tracking + metrics pipeline.
+A step = one pass of the hot path over one batch of synthetic frames per GPU:
+    frame reductions (moments, Tenengrad, Laplacian variance, visibility) + percentile contrast
+    + psd2d map + autocorr2d map with grain widths + phase-correlation tracking against a broadcast
+    reference frame.
+`value` is measured with the batch resident in HBM; `e2e` goes through the public API (StackAnalyzer.run)
+from pinned host memory, host<->device copies of inputs and of every result inside the timed region.
+One JSON line is printed by rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stack frames/sec at 2048^2 (FFT-PSD+tracking+metrics)"
+UNIT = "frames/s"
+MB = 1e6
+ALGO_BYTES_PER_FRAME = {          # compulsory HBM traffic per frame, SURVEY.md 8(d) / DESIGN.md section 4
+    "step": 3 * 2048 * 2048 * 4,            # read frame + write PSD + write autocorrelation = 50.33 MB
+    "frame_reduce": 2048 * 2048 * 4,        # one streaming read
+    "rows_fwd": 2048 * 2048 * 4,            # reads the frame, writes an L2-resident intermediate
+    "cols": 2048 * 2048 * 4,                # writes the PSD map; intermediates and reference spectrum in L2
+    "rows_inv": 2048 * 2048 * 4,            # writes the autocorrelation map
+    "select_hist": 2048 * 2048 * 4,         # one pass over a frame-sized map
+}
+FFT_FLOPS_2048 = 5.0 * 2048 * 11            # 5 N log2 N per complex transform of 2048 points
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--frames", type=int, default=16, help="frames per step per GPU")
+    p.add_argument("--size", type=int, default=2048)
+    p.add_argument("--batch", type=int, default=0, help="frames per internal FFT batch (0 = automatic)")
+    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = automatic)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic workload
+# --------------------------------------------------------------------------------------------
+
+def make_shifts(n_frames: int, seed: int) -> np.ndarray:
+    """Integer 2-D random walk (known answers), clipped to +-20 px; frame 0 unshifted."""
+    rng = np.random.default_rng(seed)
+    steps = rng.integers(-2, 3, size=(n_frames, 2))
+    steps[0] = 0
+    return np.clip(np.cumsum(steps, axis=0), -20, 20)
+
+
+def cpu_stack(base: np.ndarray, shifts: np.ndarray, noise_seed: int) -> np.ndarray:
+    """Host stack: rolled copies of `base` + 1 % Gaussian noise on every frame (same recipe as the device one)."""
+    rng = np.random.default_rng(noise_seed)
+    sigma = 0.01 * float(base.mean())
+    out = np.empty((len(shifts),) + base.shape, np.float32)
+    for t, (dy, dx) in enumerate(shifts):
+        out[t] = np.roll(base, (int(dy), int(dx)), axis=(0, 1)) + rng.normal(0, sigma, base.shape).astype(np.float32)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's per-frame path, joblib threads
+# --------------------------------------------------------------------------------------------
+
+def cpu_frame_work(frame: np.ndarray, ref: np.ndarray):
+    from oracle import ref_numpy as orc
+    n0, n1 = frame.shape
+    m = orc.distribution_moments(frame)
+    tg = orc.tenengrad(frame)
+    lv = orc.laplacian_variance(frame)
+    am = orc.amplitude(frame)
+    P, _, _ = orc.psd2d(frame)
+    g = orc.grain(frame)
+    tr = orc.phase_correlation(ref, frame, slices_yx=(slice(0, n0), slice(0, n1)))
+    return m["mean"], tg["tenengrad"], lv, am["contrast"], float(P[0, 0]), g["lx"], tr[0], tr[1]
+
+
+def cpu_pipeline(stack: np.ndarray, ref: np.ndarray, n_jobs: int):
+    """The reference drives frames with joblib threads (metrics/speckles.py:323, metrics/sharpness.py:361)."""
+    from joblib import Parallel, delayed
+    return Parallel(n_jobs=n_jobs, prefer="threads")(delayed(cpu_frame_work)(stack[t], ref) for t in range(stack.shape[0]))
+
+
+def time_cpu(size: int, frames: int, steps: int, warmup: int):
+    from barc4dip_b200 import synth
+    cores = os.cpu_count() or 1
+    base = synth.speckle_frame(size, grain=6.0, seed=0)
+    stack = cpu_stack(base, make_shifts(frames, 2), 3)
+    ref = stack[0]
+    for _ in range(warmup):
+        cpu_pipeline(stack[: max(1, min(frames, cores))], ref, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pipeline(stack, ref, cores)
+    dt = time.perf_counter() - t0
+    return frames * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = args.cpu_frames or max(8, min(32, cores))
+    fps, sec_per_step, cores = time_cpu(args.size, frames, max(1, args.steps), min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"fused stack pipeline (moments+tenengrad+laplacian+amplitude+psd2d+grain/autocorr2d+phase_correlation), "
+                               f"{args.size}x{args.size} float32 frames", "frames_per_step": frames,
+                   "note": "oracle port of the reference's numpy/scipy path (oracle/ref_numpy.py), joblib threads over frames"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{frames} frames of {args.size}^2 per step, {args.steps} steps"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [x for x in sm if x >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from barc4dip_b200 import engine, parallel, synth
+    from barc4dip_b200._lib import get_context
+    from barc4dip_b200.pipeline import StackAnalyzer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, F = args.size, args.frames
+    ctx = get_context(local)
+    if args.batch:
+        ctx.set_batch_frames(args.batch)
+
+    # ---- synthetic stack, resident in HBM: rolled copies of one speckle + independent 1 % noise per frame -----
+    base = synth.speckle_frame(n, grain=6.0, seed=0)
+    shifts = make_shifts(F, seed=2 + rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    base_d = torch.from_numpy(base).to(dev)
+    stack = torch.empty((F, n, n), dtype=torch.float32, device=dev)
+    sigma = 0.01 * float(base.mean())
+    for t in range(F):
+        stack[t] = torch.roll(base_d, (int(shifts[t, 0]), int(shifts[t, 1])), dims=(0, 1)) + \
+            sigma * torch.randn((n, n), generator=g, device=dev)
+    # reference frame = frame 0 of rank 0, broadcast over NCCL (the path's one exchange for tracking)
+    ref = stack[0].clone()
+    analyzer = StackAnalyzer((n, n), device=local, chunk_frames=F, want_maps=True, want_contrast=True)
+    psd_out = torch.empty((F, n, n), dtype=torch.float32, device=dev)
+    ac_out = torch.empty((F, n, n), dtype=torch.float32, device=dev)
+
+    def step():
+        parallel.broadcast_reference(ref, src=0)
+        analyzer.set_reference(ref)
+        return analyzer.run_device(stack, psd_out=psd_out, ac_out=ac_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+        res = step()
+    barrier()
+    # sanity: the tracker must recover the integer shifts relative to rank 0's frame 0
+    tr = res["tracking"].cpu().numpy()
+    err = float(np.max(np.abs(tr[:, :2] - (shifts - (0 if rank == 0 else 0)))))
+    if rank == 0 and err > 0.05:
+        raise SystemExit(f"tracking sanity check failed: max |shift error| = {err:.3f} px")
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launches
+    ctx.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    prof = ctx.profile_end()
+    launches = ctx.launches - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    fps = world * F * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public API: pinned host stack -> results on the host ------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((F, n, n), dtype=torch.float32, pin_memory=True)
+        host.copy_(stack)
+        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, F // 4), want_maps=True, want_contrast=True)
+        ref_host = host[0].clone()
+
+        def e2e_step():
+            an2.set_reference(ref_host)
+            return an2.run(host)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d_b, d2h_b = an2.bytes_per_frame()
+        e2e = {"value": world * F * args.e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d_b * F + n * n * 4), "d2h_bytes_per_step": int(d2h_b * F),
+               "steps": args.e2e_steps, "note": "StackAnalyzer.run on a pinned host stack; PSD + autocorrelation maps and all tables copied back"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the CUDA-event profile of the timed region --------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kern = {k: v for k, v in prof.items() if v[1] > 0}
+    tot_kernel_ms = sum(v[0] for v in kern.values())
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms, dom_launches = kern[dom]
+    frames_total = F * args.steps
+    scale = (n * n) / (2048.0 * 2048.0)
+    algo = ALGO_BYTES_PER_FRAME.get(dom, ALGO_BYTES_PER_FRAME["frame_reduce"]) * scale
+    per_launch_frames = frames_total / dom_launches if dom in ("rows_fwd", "cols", "rows_inv", "frame_reduce") else None
+    achieved = algo * frames_total / (dom_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": dom_ms / dom_launches, "frames_per_launch": per_launch_frames,
+                "algorithmic_bytes_per_frame": algo, "share_of_kernel_time": dom_ms / tot_kernel_ms}
+    step_bytes = ALGO_BYTES_PER_FRAME["step"] * scale
+    step_roof = {"bound": "hbm", "achieved": step_bytes * fps / world / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": step_bytes * fps / world / 1e9 / hbm_peak, "algorithmic_bytes_per_frame": step_bytes,
+                 "note": "whole step per GPU: frame read once + PSD + autocorrelation maps written once"}
+    lg = np.log2(n)
+    fft_flops = 6144.0 * scale * (5.0 * n * lg) * (2048.0 / n)      # 6144 complex transforms of length n at 2048^2
+    fp32 = {"achieved_tflops": fft_flops * fps / world / 1e12, "peak_tflops": 74.4,
+            "frac": fft_flops * fps / world / 1e12 / 74.4, "note": "5 N log2 N flops, 1 forward + 2 inverse real 2-D FFTs per frame; "
+            "peak = 148 SMs x 128 lanes x 2 x 1.965 GHz (non-tensor FP32)"}
+    kernel_table = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                        "share": v[0] / tot_kernel_ms} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        cf = args.cpu_frames or max(8, min(32, cores))
+        cfps, csec, cores = time_cpu(n, cf, 1, 0)
+        cpu = {"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cf} frames of {n}^2, one pass of the oracle port (numpy/scipy, joblib threads) of the same per-frame work"}
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"fused stack pipeline (frame reductions + percentile contrast + psd2d map + autocorr2d map + grain + "
+                               f"phase-correlation tracking vs broadcast reference), {n}x{n} float32 frames (BASELINE configs[1..3] fused)",
+                   "frames_per_step_per_gpu": F, "frame": [n, n], "parallelism": f"frame-sharded x{world}",
+                   "l2": f"inputs per step {F * n * n * 4 / MB:.0f} MB + {2 * F * n * n * 4 / MB:.0f} MB of maps written: larger than the 126 MB L2, no flush needed",
+                   "internal_batch_frames": args.batch or "auto"},
+        "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "step_roofline": step_roof, "fft_fp32": fp32, "kernels": kernel_table, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,18 @@ const char* b4d_version(void);
 int64_t b4d_launch_count(b4d_ctx* ctx);
 int b4d_device_sm_count(b4d_ctx* ctx);
 
+/*
+ * Optional per-kernel-class timing with CUDA events on the context's stream (used by bench.py to report
+ * the dominant kernel's duration inside the timed region).  b4d_profile_end synchronises the stream and
+ * returns, per class, the summed device time in milliseconds and the number of bracketed launches.
+ */
+#define B4D_PROF_NCLASS 11
+int b4d_profile_begin(b4d_ctx* ctx);
+int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
+const char* b4d_profile_class_name(int klass);
+/* Frames per internal batch of the FFT pipeline (0 = automatic, sized so intermediates stay in L2). */
+int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames);
+
 /* Plain device-memory helpers so that a non-Python host can drive the library. */
 int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out);
 int b4d_free(b4d_ctx* ctx, void* p);

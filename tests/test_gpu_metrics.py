@@ -1,0 +1,149 @@
+"""GPU tier: the drop-in metric functions and aggregators vs the goldens recorded from the reference."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import golden_cases as gc
+from oracle import ref_numpy as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512"]
+
+
+@pytest.fixture(scope="module")
+def dip():
+    import barc4dip_b200 as dip
+    return dip
+
+
+@pytest.mark.parametrize("name", POW2)
+def test_frame_metric_functions_vs_golden(dip, golden, name):
+    g = golden("frames")
+    img = gc.frame_cases()[name]
+    m = dip.metrics.distribution_moments(img)
+    for k, v in m.items():
+        np.testing.assert_allclose(v, g[f"{name}/moments/{k}"], rtol=RTOL, atol=1e-12, err_msg=k)
+    for k, v in dip.metrics.sharpness.tenengrad(img).items():
+        np.testing.assert_allclose(v, g[f"{name}/tenengrad/{k}"], rtol=RTOL, err_msg=k)
+    np.testing.assert_allclose(dip.metrics.sharpness.laplacian_variance(img), g[f"{name}/laplacian_variance"], rtol=RTOL)
+    for k, v in dip.metrics.speckles.amplitude(img).items():
+        np.testing.assert_allclose(v, g[f"{name}/amplitude/{k}"], rtol=RTOL, err_msg=k)
+    np.testing.assert_allclose(dip.metrics.sharpness.spectral_entropy(img), g[f"{name}/spectral_entropy"], rtol=RTOL)
+    gr = dip.metrics.speckles.grain(img)
+    for k in ("lx", "ly", "leq", "r"):
+        np.testing.assert_allclose(gr[k], g[f"{name}/grain/{k}"], rtol=RTOL, err_msg=k)
+    n = max(img.shape)
+    assert gr["autocorr"].shape == (n, n) and gr["autocorr"].dtype == np.float64
+    np.testing.assert_allclose(gr["autocorr"][n // 2], g[f"{name}/grain/autocorr_row"], atol=1e-5)
+    np.testing.assert_array_equal(gr["xlag"], np.arange(n) - n // 2)
+    for k, v in dip.metrics.speckles.bandwidth(img).items():
+        np.testing.assert_allclose(v, g[f"{name}/bandwidth/{k}"], rtol=RTOL, err_msg=k)
+    for k, v in dip.metrics.sharpness.inverse_autocorr_width(img).items():
+        np.testing.assert_allclose(v, g[f"{name}/inv_ac_width/{k}"], rtol=RTOL, err_msg=k)
+
+
+def test_aggregators_vs_golden(dip, golden):
+    g = golden("aggregators")
+    img = gc.frame_cases()["sq256"]
+    sp = dip.metrics.speckle_stats(img, tiles=False, verbose=False)
+    assert sp["meta"]["kind"] == "speckles" and sp["meta"]["input_shape"] == (256, 256)
+    assert sp["meta"]["requested_groups"] == ["amplitude", "bandwidth", "grain", "stats"]
+    n = 0
+    for key in g.files:
+        if key.startswith("speckle_stats/full/"):
+            _, _, grp, k = key.split("/")
+            np.testing.assert_allclose(sp["full"][grp][k], g[key], rtol=RTOL, atol=1e-12, err_msg=key)
+            n += 1
+    assert n >= 20
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sh = dip.metrics.sharpness_stats(img, metrics=("stats", "gradient", "laplacian", "spectral", "autocorrelation"),
+                                         tiles=False, verbose=False)
+    for key in g.files:
+        if key.startswith("sharpness_stats/full/"):
+            _, _, grp, k = key.split("/")
+            np.testing.assert_allclose(sh["full"][grp][k], g[key], rtol=RTOL, atol=1e-12, err_msg=key)
+    stack = np.stack([gc.frame_cases()["sq256"], gc.frame_cases()["blur256"]], axis=0)
+    shs = dip.metrics.sharpness_stack_stats(stack, metrics=("stats", "gradient", "laplacian"), tiles=False, verbose=False)
+    assert shs["meta"]["stack_shape"] == (2, 256, 256) and shs["meta"]["n_frames"] == 2
+    for key in g.files:
+        if key.startswith("sharpness_stack_stats/full/"):
+            _, _, grp, k = key.split("/")
+            assert shs["full"][grp][k].shape == (2,)
+            np.testing.assert_allclose(shs["full"][grp][k], g[key], rtol=RTOL, atol=1e-12, err_msg=key)
+
+
+def test_aggregator_errors_and_schema(dip):
+    from barc4dip_b200._lib import B4DUnsupported
+    img = gc.frame_cases()["sq256"]
+    with pytest.raises(TypeError):
+        dip.metrics.speckle_stats(img.tolist())
+    with pytest.raises(ValueError):
+        dip.metrics.speckle_stats(img[None])
+    with pytest.raises(ValueError):
+        dip.metrics.speckle_stats(img, metrics="nope", tiles=False)
+    with pytest.raises(ValueError):
+        dip.metrics.sharpness_stats(img, tiles=False, display_origin="left")
+    with pytest.raises(B4DUnsupported):
+        dip.metrics.sharpness_stats(img, metrics="eigenvalues", tiles=False)
+    with pytest.raises(B4DUnsupported):
+        dip.metrics.speckle_stats(gc.frame_cases()["sq512"], tiles=True, verbose=False)   # 512//3 >= 128 -> tiles wanted
+    with pytest.warns(RuntimeWarning):
+        out = dip.metrics.sharpness_stats(img, tiles=False, verbose=False)                # "all" skips eigenvalues
+    assert set(out["full"]) == {"stats", "gradient", "laplacian", "spectral", "autocorrelation"}
+    with pytest.raises(ValueError):
+        dip.metrics.speckles.grain(np.ones((64, 64), np.float32))
+    with pytest.raises(ValueError):
+        dip.metrics.speckles.amplitude(-np.ones((128, 128), np.float32))
+
+
+def test_flat_field_function_vs_golden(dip, golden):
+    g = golden("flatfield")
+    raw, flat, dark = gc.flatfield_inputs()
+    ffc = dip.preprocessing.flat_field_correction
+    for scale in ("flat_median", "none"):
+        out = ffc(raw, flats=flat, darks=dark, scale=scale)
+        assert out.dtype == np.float32 and out.shape == raw.shape
+        np.testing.assert_array_equal(out[:2], g[f"ffc/{scale}/frames01"])
+    out = ffc(raw, flats=flat, darks=dark, scale="flat_mean")
+    np.testing.assert_allclose(out[:2], g["ffc/flat_mean/frames01"], rtol=3e-7)
+    out = ffc(raw, flats=flat, darks=dark, eps=50.0)
+    np.testing.assert_allclose(out.astype(np.float64).sum(), g["ffc/eps50/sum"], rtol=1e-12)
+    assert int((out[0] == 0).sum()) == int(g["ffc/eps50/nzero"])
+    out = ffc(raw[0], flats=np.stack([flat, flat + 2]), darks=np.stack([dark, dark]))
+    np.testing.assert_array_equal(out, g["ffc/2d_stackflat/frame"])
+    np.testing.assert_allclose(ffc(raw, darks=dark).astype(np.float64).sum(), g["ffc/darkonly/sum"], rtol=1e-12)
+    np.testing.assert_allclose(ffc(raw, flats=flat).astype(np.float64).sum(), g["ffc/flatonly/sum"], rtol=1e-12)
+    np.testing.assert_array_equal(ffc(raw), raw)
+    with pytest.raises(ValueError):
+        ffc(raw, flats=flat, scale="bogus")
+
+
+def test_speckle_stack_stats_phase_tracking(dip):
+    """Stack aggregator with the phase/internal tracker against the oracle's per-ROI phase correlation."""
+    from barc4dip_b200 import synth
+    stack, _ = synth.tracking_stack(3, 256, grain=8.0, seed=51, step_sigma=0.8)
+    out = dip.metrics.speckle_stack_stats(stack, metrics=("amplitude", "stats", "grain"), tiles=False,
+                                          tracking_method="phase", tracking_backend="internal", verbose=False)
+    assert out["meta"]["kind"] == "speckle_stack_stats" and out["full"]["stats"]["mean"].shape == (3,)
+    roi = out["meta"]["tracking"]["roi_size_yx"][0]
+    step = out["meta"]["tracking"]["roi_step_yx"][0]
+    g0 = orc.grain(stack[0])
+    assert roi % 2 == 1 and roi >= int(np.ceil(3.0 * max(g0["lx"], g0["ly"], g0["leq"])))
+    # oracle for one ROI (centre) and t = 2, absolute and incremental
+    c = 128
+    sl = (slice(c - roi // 2, c + roi // 2 + 1),) * 2
+    want_abs = np.array([[orc.phase_correlation(stack[0][(slice(c + dy * step - roi // 2, c + dy * step + roi // 2 + 1),
+                                                          slice(c + dx * step - roi // 2, c + dx * step + roi // 2 + 1))],
+                                                 stack[2],
+                                                 slices_yx=(slice(c + dy * step - roi // 2, c + dy * step + roi // 2 + 1),
+                                                            slice(c + dx * step - roi // 2, c + dx * step + roi // 2 + 1)))[:2]
+                          for dx in (-1, 0, 1)] for dy in (-1, 0, 1)])
+    np.testing.assert_allclose(out["temporal"]["abs"]["dy"][2], np.float32(want_abs[..., 0].astype(np.float32).mean()), atol=0.01)
+    np.testing.assert_allclose(out["temporal"]["abs"]["dx"][2], np.float32(want_abs[..., 1].astype(np.float32).mean()), atol=0.01)
+    assert out["temporal"]["inc"]["dx"].dtype == np.float32 and out["temporal"]["inc"]["dx"].shape == (3,)
+    for k in ("mean", "std", "skewness"):
+        np.testing.assert_allclose(out["full"]["stats"][k][1], orc.distribution_moments(stack[1])[k], rtol=RTOL)

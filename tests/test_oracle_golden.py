@@ -117,7 +117,7 @@ def test_tracking_matches_reference(golden):
 def test_tracking_quirks(golden):
     g = golden("tracking")
     # quirk 1: sub-pixel terms come back swapped: true (+0.3, -0.1) is reported as ~(-0.1, +0.3)
-    dy, dx = g["sub_p3_m1/result"][:2]
+    dy, dx = g["sub_p3_m1_noise/result"][:2]
     assert abs(dy - (-0.1)) < abs(dy - 0.3) and abs(dx - 0.3) < abs(dx - (-0.1)) and dy < 0 < dx
     # integer rolls come back as integers to a few 1e-3
     np.testing.assert_allclose(g["roll_2_m3/result"][:2], (2, -3), atol=5e-3)
