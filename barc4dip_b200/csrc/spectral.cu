@@ -465,6 +465,10 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
         }
         s_scale = (float)s;
     }
+    __syncthreads();
+    // The two rows share one complex transform, so they are brought to their final scale BEFORE it: a raw
+    // autocorrelation (~1e13) packed next to a raw phase correlation (~1e6) would bury the latter in rounding.
+    const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
 
     // gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
     float2* z = sm + f * FS;
@@ -472,7 +476,8 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
     for (int m = 0; m < 8; ++m) {
         const int k = j + m * TPF;
         const size_t off = ((size_t)(k >> 3) * NY) * 8 + (k & 7);
-        const float2 ga = __ldg(Ia + off + (size_t)ya * 8), gb = __ldg(Ib + off + (size_t)yb * 8);
+        float2 ga = __ldg(Ia + off + (size_t)ya * 8), gb = __ldg(Ib + off + (size_t)yb * 8);
+        ga.x *= sA; ga.y *= sA; gb.x *= sB; gb.y *= sB;
         if (k == 0) {
             // packed slot: (DC, Nyquist), both real
             z[pad16(0)] = make_float2(ga.x, gb.x);
@@ -490,7 +495,6 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
     fft_from_regs<NX, +1>(x, j, SlotLinear{z}, a.tw);
 
     // stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
-    const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
     const int kindB = a.pair_maps ? a.kindB : a.kindA;
     float* oA = a.outA ? a.outA + (size_t)t * NY * NX : nullptr;
     float* oB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX : nullptr) : oA;
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
         const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
         const unsigned cs = (unsigned)((xx + HX) & (NX - 1));
         const unsigned rsa = (unsigned)((ra_ + NY / 2) & (NY - 1)), rsb = (unsigned)((rb_ + NY / 2) & (NY - 1));
-        float va = v.x * sA, vb = v.y * sB;
+        float va = v.x, vb = v.y;
         if (a.kindA) va = fabsf(va);
         if (kindB) vb = fabsf(vb);
         if (oA) oA[(size_t)rsa * NX + cs] = va;

@@ -1,0 +1,222 @@
+"""CPU tier: ABI completeness, host-side logic and loud failure without a GPU (no compute calls)."""
+
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "b4d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b4d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from barc4dip_b200 import _lib
+    lib = _lib.load_library()
+    declared = _header_functions()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b4d.h but not exported by libb4d.so"
+    # the ctypes table mirrors the header one to one
+    assert sorted(_lib.exported_symbols()) == declared
+    assert b"sm_100a" in lib.b4d_version()
+
+
+def test_library_contains_sm100a_code():
+    from barc4dip_b200 import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import barc4dip_b200 as dip
+    from barc4dip_b200._lib import B4DError
+    img = np.ones((128, 128), np.float32)
+    for call in (lambda: dip.signal.psd2d(img), lambda: dip.metrics.distribution_moments(img),
+                 lambda: dip.metrics.speckles.grain(img), lambda: dip.signal.phase_correlation(img[:127, :127], img),
+                 lambda: dip.preprocessing.flat_field_correction(img, flats=img)):
+        with pytest.raises(B4DError):
+            call()
+
+
+def test_product_never_imports_the_oracle():
+    """No module of the product imports oracle/ or a CPU implementation of the path (scipy, numpy FFTs).
+
+    smoke.py is the driver's checker and synth.py only generates synthetic test/bench inputs."""
+    pkg = os.path.join(ROOT, "barc4dip_b200")
+    bad_import = re.compile(r"^\s*(?:import|from)\s+(?:oracle|scipy|joblib|cv2|skimage)\b", re.M)
+    cpu_fft = re.compile(r"np\.fft\.(?:fft2|ifft2|rfft2|irfft2|fft|ifft)\(")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py") and f not in ("smoke.py", "synth.py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not bad_import.search(src), f"{f} imports a CPU implementation"
+                assert not cpu_fft.search(src), f"{f} calls a numpy FFT"
+
+
+def test_argument_validation_happens_before_the_device():
+    import barc4dip_b200 as dip
+    with pytest.raises(ValueError):
+        dip.signal.psd2d(np.zeros((2, 3, 4)))
+    with pytest.raises(ValueError):
+        dip.signal.psd2d(np.zeros((8, 8)), dx=-1.0)
+    with pytest.raises(ValueError):
+        dip.signal.psd2d(np.zeros((8, 8)), x=np.arange(8.0))
+    with pytest.raises(ValueError):
+        dip.signal.xcorr2d(np.zeros((8, 8)), np.zeros((8, 9)))
+    with pytest.raises(ValueError):
+        dip.metrics.distribution_moments(np.zeros((0,)))
+    with pytest.raises(TypeError):
+        dip.metrics.speckle_stats([[1.0]])
+    with pytest.raises(TypeError):
+        dip.metrics.sharpness_stack_stats([[1.0]])
+    with pytest.raises(ValueError):
+        dip.metrics.speckle_stack_stats(np.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        dip.preprocessing.flat_field_correction(np.zeros((4, 4)), scale="x")
+    with pytest.raises(ValueError):
+        dip.signal.track_translation(np.zeros((5, 5)), np.zeros((9, 9)), method="warp")
+
+
+def test_host_blocks_match_oracle_definitions():
+    """moments/gradient/laplacian blocks turn a reduction table into the reference's dicts."""
+    from barc4dip_b200 import stack as blocks
+    from barc4dip_b200._lib import FR, FR_NCOLS
+    from oracle import ref_numpy as orc
+    rng = np.random.default_rng(0)
+    img = rng.gamma(2.0, 300.0, size=(48, 40)).astype(np.float32)
+    x = img.astype(np.float64).ravel()
+    gx, gy = orc.sobel_reflect(img)
+    lap = orc.laplace_reflect(img)
+    row = np.zeros((1, FR_NCOLS))
+    mu = x.mean()
+    row[0, FR["count"]] = x.size; row[0, FR["npix"]] = x.size; row[0, FR["mean"]] = mu
+    for k, name in ((2, "m2"), (3, "m3"), (4, "m4")):
+        row[0, FR[name]] = np.mean((x - mu) ** k)
+    row[0, FR["nzero"]] = 3; row[0, FR["nsat"]] = 5
+    row[0, FR["sgx2"]] = (gx ** 2).sum(); row[0, FR["sgy2"]] = (gy ** 2).sum()
+    row[0, FR["slap"]] = lap.sum(); row[0, FR["slap2"]] = (lap ** 2).sum()
+    want = orc.distribution_moments(img)
+    got = blocks.moments_block(row, 65535.0)
+    for k in ("mean", "std", "variance", "skewness", "kurtosis", "SNRdB"):
+        np.testing.assert_allclose(got[k][0], want[k], rtol=1e-10)
+    assert got["frac_zero"][0] == 3 / x.size and got["frac_sat"][0] == 5 / x.size
+    assert np.isnan(blocks.moments_block(row, None)["frac_sat"][0])
+    ten = orc.tenengrad(img)
+    g = blocks.gradient_block(row)
+    for k in ten:
+        np.testing.assert_allclose(g[k][0], ten[k], rtol=1e-10)
+    np.testing.assert_allclose(blocks.laplacian_block(row)["laplacian_variance"][0], orc.laplacian_variance(img), rtol=1e-10)
+    # constant frame: std 0 -> SNRdB inf
+    row[0, FR["m2"]] = 0.0
+    assert blocks.moments_block(row, 65535.0)["SNRdB"][0] == np.inf
+
+
+def test_quantile_helpers_match_numpy():
+    from barc4dip_b200 import engine
+    rng = np.random.default_rng(1)
+    for n in (7, 100, 4097):
+        s = np.sort(rng.exponential(size=n))
+        for q in (0.0005, 0.5, 0.9995, 0.0, 1.0):
+            h = engine.virtual_index(n, q)
+            lo = min(max(int(np.floor(h)), 0), n - 1)
+            hi = min(lo + 1, n - 1)
+            got = engine.quantile_from_bracket(s[lo], s[hi], n, q)
+            np.testing.assert_allclose(got, np.percentile(s, 100 * q), rtol=1e-14)
+
+
+def test_frame_sharding_partition():
+    from barc4dip_b200 import parallel
+    for T in (1, 7, 4000, 10000):
+        for G in (1, 2, 4, 8):
+            seen = []
+            for r in range(G):
+                lo, hi = parallel.frame_range(T, r, G)
+                seen.extend(range(lo, hi))
+                hlo, hhi = parallel.inc_halo_range(T, r, G)
+                assert hhi == hi and hlo == max(lo - 1, 0)
+            assert seen == list(range(T))
+            if T >= G:
+                assert parallel.owner_of(0, T, G) == 0 and parallel.owner_of(T - 1, T, G) == G - 1
+    with pytest.raises(ValueError):
+        parallel.frame_range(10, 3, 2)
+
+
+def test_shifted_power_sums_merge_like_the_allreduce():
+    """Shifted power sums against a COMMON shift add across shards; finalising the sum gives the global moments."""
+    from barc4dip_b200 import parallel
+    from oracle import ref_numpy as orc
+    rng = np.random.default_rng(2)
+    stack = rng.exponential(1000.0, size=(40, 6, 5))
+    shift = stack[:4].mean(axis=0)
+    parts = []
+    for r in range(4):
+        lo, hi = parallel.frame_range(40, r, 4)
+        d = stack[lo:hi] - shift
+        parts.append(np.stack([(d ** k).sum(axis=0) for k in (1, 2, 3, 4)]))
+    S = parallel.merge_power_sums(parts)
+    n = 40.0
+    a1, a2, a3, a4 = (S[k] / n for k in range(4))
+    m2 = a2 - a1 ** 2
+    m3 = a3 - 3 * a1 * a2 + 2 * a1 ** 3
+    m4 = a4 - 4 * a1 * a3 + 6 * a1 ** 2 * a2 - 3 * a1 ** 4
+    want = orc.temporal_moments(stack)
+    np.testing.assert_allclose(shift + a1, want["mean"], rtol=1e-12)
+    np.testing.assert_allclose(m2, want["variance"], rtol=1e-10)
+    np.testing.assert_allclose(m3 / m2 ** 1.5, want["skewness"], rtol=1e-9)
+    np.testing.assert_allclose(m4 / m2 ** 2 - 3, want["kurtosis"], rtol=1e-9)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from barc4dip_b200 import parallel
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = parallel.dist_info()
+assert world == 2
+T = 11
+lo, hi = parallel.frame_range(T, rank, world)
+# broadcast of the reference frame from the owner of frame 0
+ref = torch.full((4, 4), float(rank + 1))
+parallel.broadcast_reference(ref, src=parallel.owner_of(0, T, world))
+assert float(ref[0, 0]) == 1.0
+# all-reduce of temporal sums
+class Acc: pass
+acc = Acc(); acc.sums = torch.ones((4, 2, 2), dtype=torch.float64) * (rank + 1); acc.count = hi - lo
+parallel.allreduce_temporal(acc, T)
+assert acc.count == T and float(acc.sums[0, 0, 0]) == 3.0
+# gather of ragged per-frame tables in rank order
+local = torch.arange(lo, hi, dtype=torch.float64).view(-1, 1).repeat(1, 3)
+full = parallel.gather_rows(local, T)
+assert full.shape == (T, 3) and torch.equal(full[:, 0], torch.arange(T, dtype=torch.float64))
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_two_rank_gloo_exchange(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29571")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, out
