@@ -76,67 +76,72 @@ struct Acc {
     int nfin = 0, nzero = 0, nsat = 0, nnan = 0;
 };
 
+// Raw loads of one row for a lane: its four pixels (flat-field applied) and, for the two edge lanes of a
+// strip, the neighbouring strip's pixel. Nothing here depends on another lane, so several rows can be in
+// flight before the first shuffle.
+struct RawRow {
+    float x[4];
+    float hl, hr;
+};
+
 template <bool VEC>
-__device__ __forceinline__ RowWin load_row(const FrArgs& a, const float* frame, int r, int j0, int lane,
-                                           float K, bool in_band, Acc& acc) {
+__device__ __forceinline__ RawRow fetch_row(const FrArgs& a, const float* frame, int r, int j0, int lane) {
     const int rr = min(max(r, 0), a.ny - 1);          // "reflect" = duplicate the edge sample
     const size_t rowoff = (size_t)rr * a.nx;
     const float* row = frame + rowoff;
-    RowWin w;
-    float x[4];
-    bool valid[4];
+    RawRow w;
     if (VEC) {
-        const bool on = j0 < a.nx;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on) {
-            v = ldg_stream4(row + j0);
+        if (j0 < a.nx) {
+            v = __ldcs(reinterpret_cast<const float4*>(row + j0));
             if (a.gain) {
-                float4 g = __ldg(reinterpret_cast<const float4*>(a.gain + rowoff + j0));
-                float4 dk = a.dark ? __ldg(reinterpret_cast<const float4*>(a.dark + rowoff + j0))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 g = __ldg(reinterpret_cast<const float4*>(a.gain + rowoff + j0));
+                const float4 dk = a.dark ? __ldg(reinterpret_cast<const float4*>(a.dark + rowoff + j0))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 v.x = (v.x - dk.x) * g.x; v.y = (v.y - dk.y) * g.y;
                 v.z = (v.z - dk.z) * g.z; v.w = (v.w - dk.w) * g.w;
             }
         }
-        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        valid[0] = valid[1] = valid[2] = valid[3] = on;
+        w.x[0] = v.x; w.x[1] = v.y; w.x[2] = v.z; w.x[3] = v.w;
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int j = j0 + k;
-            valid[k] = j < a.nx;
-            int jc = min(j, a.nx - 1);
-            x[k] = ff_apply(__ldg(row + jc), a.gain, a.dark, rowoff + jc);   // clamped: right reflect for free
+            const int jc = min(j0 + k, a.nx - 1);   // clamped: the right reflection comes for free
+            w.x[k] = ff_apply(__ldg(row + jc), a.gain, a.dark, rowoff + jc);
         }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w.c[k + 1] = x[k] - K;
+    w.hl = 0.f;
+    w.hr = 0.f;
+    if (lane == 0 && j0 > 0 && j0 < a.nx) w.hl = ff_apply(__ldg(row + j0 - 1), a.gain, a.dark, rowoff + j0 - 1);
+    if (lane == 31 && j0 + 4 < a.nx) w.hr = ff_apply(__ldg(row + j0 + 4), a.gain, a.dark, rowoff + j0 + 4);
+    return w;
+}
 
-    // halo columns: neighbours' values through shuffles, strip edges from memory / reflection
+// Shift by K, exchange the halo columns through shuffles, accumulate the pointwise statistics.
+__device__ __forceinline__ RowWin finish_row(const FrArgs& a, const RawRow& raw, int j0, int lane, float K,
+                                             bool in_band, Acc& acc) {
+    RowWin w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w.c[k + 1] = raw.x[k] - K;
     float left = __shfl_up_sync(0xffffffffu, w.c[4], 1);
     float right = __shfl_down_sync(0xffffffffu, w.c[1], 1);
-    if (lane == 0) {
-        if (j0 == 0) left = w.c[1];
-        else left = ff_apply(__ldg(row + j0 - 1), a.gain, a.dark, rowoff + j0 - 1) - K;
-    }
-    if (VEC) {
-        if (j0 + 4 >= a.nx) right = w.c[4];
-        else if (lane == 31) right = ff_apply(__ldg(row + j0 + 4), a.gain, a.dark, rowoff + j0 + 4) - K;
-    } else {
-        if (lane == 31 || j0 + 4 >= a.nx) {
-            int jc = min(j0 + 4, a.nx - 1);
-            right = (j0 < a.nx) ? ff_apply(__ldg(row + jc), a.gain, a.dark, rowoff + jc) - K : 0.f;
-        }
+    if (lane == 0) left = (j0 == 0) ? w.c[1] : raw.hl - K;
+    // first column past the frame reflects onto the last valid one
+    const int last = a.nx - 1 - j0;                   // index of the last valid pixel in this lane, if 0..3
+    if (j0 + 4 >= a.nx) right = w.c[1 + min(max(last, 0), 3)];
+    else if (lane == 31) right = raw.hr - K;
+    if (last >= 0 && last < 3) {                      // ragged last lane (nx % 4 != 0): reflect inside the lane
+#pragma unroll
+        for (int k = 1; k < 4; ++k) if (k > last) w.c[k + 1] = w.c[1 + last];
     }
     w.c[0] = left;
     w.c[5] = right;
-
-    // pointwise statistics of the rows this item owns
     if (in_band) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float xv = x[k];
-            const bool fin = valid[k] && (fabsf(xv) <= 3.402823466e38f);   // false for NaN / inf
+            const float xv = raw.x[k];
+            const bool valid = j0 + k < a.nx;
+            const bool fin = valid && (fabsf(xv) <= 3.402823466e38f);   // false for NaN / inf
             if (fin) {
                 const float d = w.c[k + 1];
                 const float d2 = d * d;
@@ -147,7 +152,7 @@ __device__ __forceinline__ RowWin load_row(const FrArgs& a, const float* frame, 
                 acc.nfin++;
                 acc.nzero += (fabsf(xv) <= a.zeps) ? 1 : 0;
                 acc.nsat += (a.has_sat && xv >= a.sat) ? 1 : 0;
-            } else if (valid[k] && xv != xv) {
+            } else if (valid && xv != xv) {
                 acc.nnan++;
             }
         }
@@ -199,21 +204,27 @@ __global__ void __launch_bounds__(FR_WARPS * 32) frame_reduce_kernel(FrArgs a) {
         const int r0 = band * FR_BAND;
         const int r1 = min(r0 + FR_BAND, a.ny);
         Acc acc;
-        RowWin up = load_row<VEC>(a, frame, r0 - 1, j0, lane, K, false, acc);
-        RowWin mid = load_row<VEC>(a, frame, r0, j0, lane, K, true, acc);
-        for (int rb = r0; rb < r1; rb += 4) {
-            // issue the next four row loads before any stencil consumes them (memory-level parallelism)
-            RowWin nxt[4];
+        RawRow raw0 = fetch_row<VEC>(a, frame, r0 - 1, j0, lane), raw1 = fetch_row<VEC>(a, frame, r0, j0, lane);
+        RawRow raw[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int r = rb + 1 + q;
-                nxt[q] = load_row<VEC>(a, frame, r, j0, lane, K, r < r1, acc);
+        for (int q = 0; q < 4; ++q) raw[q] = fetch_row<VEC>(a, frame, r0 + 1 + q, j0, lane);
+        RowWin up = finish_row(a, raw0, j0, lane, K, false, acc);
+        RowWin mid = finish_row(a, raw1, j0, lane, K, true, acc);
+        for (int rb = r0; rb < r1; rb += 4) {
+            // the four rows fetched one iteration ago are consumed while the next four are already in flight
+            RawRow cur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cur[q] = raw[q];
+            if (rb + 4 < r1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) raw[q] = fetch_row<VEC>(a, frame, rb + 5 + q, j0, lane);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (rb + q < r1) stencil_row(up, mid, nxt[q], j0, a.nx, acc);
+                const RowWin nxt = finish_row(a, cur[q], j0, lane, K, rb + 1 + q < r1, acc);
+                if (rb + q < r1) stencil_row(up, mid, nxt, j0, a.nx, acc);
                 up = mid;
-                mid = nxt[q];
+                mid = nxt;
             }
             if (((rb - r0) & 4) != 0 || rb + 4 >= r1) {   // fold fp32 partials into fp64 every 8 rows
                 d[0] += acc.nfin; d[1] += acc.s1; d[2] += acc.s2; d[3] += acc.s3; d[4] += acc.s4;

@@ -1,26 +1,43 @@
-// Exact order statistics per frame by radix select on the float bit patterns.
+// Exact order statistics per frame.
 //
 // Behind np.nanpercentile(img, 0.05 / 99.95) in amplitude() (metrics/speckles.py:647 via
 // utils/range.py:51-54), np.median(|corr|) in the tracker's SNR (signal/tracking.py:319) and the
 // two medians of flat_field_correction (preprocessing/normalize.py:110,126).
 //
-// Three histogram passes over the frame (11 + 11 + 10 key bits). After each pass a one-CTA-per-
-// frame kernel walks the cumulative histogram and narrows every requested rank to a key prefix.
-// Keys are order-preserving uint32 images of the floats; NaNs are skipped (nanpercentile
-// semantics) and counted out of n_valid. Hot bins (speckle intensities share a few exponents)
-// are handled with warp-aggregated shared-memory atomics.
+// Fast path (frames of >= 64 K elements): ONE streaming pass per frame.
+//   1. sel_sample_kernel : 16384 strided samples per frame are sorted in shared memory; for every requested
+//      quantile a key bracket [L, U] is taken +-6 sigma (binomial) around the sample quantile.
+//   2. sel_collect_kernel: one pass over the frame counts the valid (non-NaN) elements, the elements below L,
+//      and appends the elements inside [L, U] (0.2 % .. 5 % of the frame) to a candidate list.
+//   3. sel_final_kernel  : the two target ranks (numpy's 'linear' method: floor(h), floor(h)+1) are located
+//      inside the candidate list by a shared-memory radix select. If a rank falls outside the bracket (or the
+//      list overflowed) the frame is flagged and
+// Fallback (flagged frames and small frames): three histogram passes over the frame (11 + 11 + 10 key bits)
+// with a one-CTA scan after each. Both paths are exact.
+// Keys are order-preserving uint32 images of the floats; NaNs are skipped (nanpercentile semantics).
 #include "common.cuh"
 
 namespace {
 
 constexpr int SEL_MAXR = 4;           // ranks per frame (2 per quantile)
+constexpr int SEL_MAXQ = 2;
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_THREADS = 256;
+constexpr int SEL_SAMPLES = 16384;
+constexpr int64_t SEL_FAST_MIN = 65536;
 
-struct SelState {                     // per frame, device resident
+struct SelState {                     // per frame, device resident (radix path)
     unsigned prefix[SEL_MAXR];        // key bits fixed so far (left aligned)
     long long rank[SEL_MAXR];         // residual rank inside the prefix bucket
     long long n_valid;
+};
+
+struct SelFast {                      // per frame, device resident (bracket path)
+    unsigned L[SEL_MAXQ], U[SEL_MAXQ];
+    unsigned long long below[SEL_MAXQ];
+    unsigned ncand[SEL_MAXQ];
+    unsigned long long n_valid;
+    int need_fallback;
 };
 
 __device__ __forceinline__ unsigned key_of(float v, int use_abs) {
@@ -33,19 +50,273 @@ __device__ __forceinline__ float value_of(unsigned k, int use_abs) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// numpy's linear method: h = n*q + (1 + q*(1-1-1)) - 1, lo = floor(h), hi = min(lo+1, n-1)
+__device__ __forceinline__ void target_ranks(unsigned long long n, double q, long long& lo, long long& hi) {
+    lo = hi = 0;
+    if (n == 0) return;
+    const double hh = __dadd_rn(__dadd_rn(__dmul_rn((double)n, q), __dadd_rn(1.0, __dmul_rn(q, -1.0))), -1.0);
+    lo = (long long)floor(hh);
+    if (lo < 0) lo = 0;
+    if (lo > (long long)n - 1) lo = (long long)n - 1;
+    hi = lo + 1 > (long long)n - 1 ? (long long)n - 1 : lo + 1;
+}
+
 __device__ __forceinline__ void hist_add(unsigned* h, unsigned bin) {
     const unsigned m = __match_any_sync(__activemask(), bin);
     if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(h + bin, (unsigned)__popc(m));
 }
 
+// =================================================================================================
+// fast path
+// =================================================================================================
+__global__ void __launch_bounds__(1024) sel_sample_kernel(const float* __restrict__ stack, int64_t n, int n_q,
+                                                          const double* __restrict__ quant, int use_abs,
+                                                          SelFast* __restrict__ st) {
+    extern __shared__ unsigned keys[];              // SEL_SAMPLES
+    __shared__ int s_valid;
+    const int64_t t = blockIdx.x;
+    const float* f = stack + t * n;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int nv = 0;
+    for (int i = threadIdx.x; i < SEL_SAMPLES; i += blockDim.x) {
+        const int64_t p = (int64_t)(((__int128)i * n) / SEL_SAMPLES);
+        const float v = __ldg(f + p);
+        const bool ok = v == v;
+        keys[i] = ok ? key_of(v, use_abs) : 0xffffffffu;     // NaNs sort last
+        nv += ok;
+    }
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_valid, nv);
+    __syncthreads();
+    // bitonic sort of SEL_SAMPLES keys
+    for (int k = 2; k <= SEL_SAMPLES; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < SEL_SAMPLES / 2; i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const unsigned a = keys[lo], b = keys[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        SelFast s;
+        const int m = s_valid;
+        for (int q = 0; q < SEL_MAXQ; ++q) { s.L[q] = 0u; s.U[q] = 0xfffffffeu; s.below[q] = 0ull; s.ncand[q] = 0u; }
+        s.n_valid = 0ull;
+        s.need_fallback = 0;
+        if (m >= 1024) {
+            for (int q = 0; q < n_q; ++q) {
+                const double qq = quant[q];
+                const double c = qq * (double)(m - 1);
+                const double d = 6.0 * sqrt(qq * (1.0 - qq) * (double)m) + 8.0;
+                const long long il = (long long)floor(c - d), iu = (long long)ceil(c + d);
+                s.L[q] = il <= 0 ? 0u : keys[il];
+                s.U[q] = iu >= m - 1 ? 0xfffffffeu : keys[iu];
+            }
+        }
+        st[t] = s;
+    }
+}
+
+// One pass over the frame. A CTA works through chunks of COL_CHUNK elements: candidates are appended to a
+// shared-memory list (warp-aggregated shared atomics), then one thread reserves a range of the frame's global
+// candidate list and the CTA copies the chunk's candidates out coalesced -- one global atomic per chunk and
+// bracket instead of one per warp.
+constexpr int COL_THREADS = 256;
+constexpr int COL_VEC = 4;
+constexpr int COL_ITERS = 4;
+constexpr int COL_CHUNK = COL_THREADS * COL_VEC * COL_ITERS;     // 4096 elements
+
+__global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* __restrict__ stack, int64_t n, int n_q,
+                                                                  int use_abs, SelFast* __restrict__ st,
+                                                                  unsigned* __restrict__ cand, unsigned cap) {
+    __shared__ unsigned buf[SEL_MAXQ][COL_CHUNK];
+    __shared__ unsigned cnt[SEL_MAXQ], gbase[SEL_MAXQ];
+    __shared__ unsigned long long tot[3];
+    const int64_t t = blockIdx.y;
+    const float* f = stack + t * n;
+    SelFast* s = st + t;
+    unsigned L[SEL_MAXQ], U[SEL_MAXQ];
+#pragma unroll
+    for (int q = 0; q < SEL_MAXQ; ++q) { L[q] = s->L[q]; U[q] = s->U[q]; }
+    unsigned nvalid = 0, below[SEL_MAXQ] = {0u, 0u};
+    const int lane = threadIdx.x & 31;
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+    if (threadIdx.x < 3) tot[threadIdx.x] = 0ull;
+    const int64_t nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        if (threadIdx.x < SEL_MAXQ) cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        const int64_t e0 = ch * COL_CHUNK;
+        float v[COL_ITERS][COL_VEC];
+#pragma unroll
+        for (int it = 0; it < COL_ITERS; ++it) {
+            const int64_t e = e0 + ((int64_t)it * COL_THREADS + threadIdx.x) * COL_VEC;
+            if (vec && e + COL_VEC <= n) {
+                const float4 x = __ldcs(reinterpret_cast<const float4*>(f + e));
+                v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < COL_VEC; ++k) v[it][k] = (e + k < n) ? __ldcs(f + e + k) : __uint_as_float(0x7fc00000u);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < COL_ITERS; ++it) {
+#pragma unroll
+            for (int k = 0; k < COL_VEC; ++k) {
+                const float x = v[it][k];
+                const bool ok = x == x;
+                const unsigned key = ok ? key_of(x, use_abs) : 0u;
+                nvalid += ok;
+#pragma unroll
+                for (int q = 0; q < SEL_MAXQ; ++q) {
+                    if (q < n_q) {
+                        const bool lt = ok && key < L[q];
+                        const bool in = ok && !lt && key <= U[q];
+                        below[q] += lt;
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
+                        if (m) {
+                            unsigned base = 0;
+                            const int leader = __ffs(m) - 1;
+                            if (lane == leader) base = atomicAdd(&cnt[q], (unsigned)__popc(m));
+                            base = __shfl_sync(0xffffffffu, base, leader);
+                            if (in) buf[q][base + __popc(m & ((1u << lane) - 1u))] = key;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < n_q && cnt[threadIdx.x]) gbase[threadIdx.x] = atomicAdd(&s->ncand[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+        for (int q = 0; q < n_q; ++q) {
+            const unsigned c = cnt[q], g0 = gbase[q];
+            unsigned* dst = cand + ((size_t)t * SEL_MAXQ + q) * cap;
+            for (unsigned i = threadIdx.x; i < c; i += COL_THREADS)
+                if (g0 + i < cap) dst[g0 + i] = buf[q][i];
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+        below[0] += __shfl_xor_sync(0xffffffffu, below[0], o);
+        below[1] += __shfl_xor_sync(0xffffffffu, below[1], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        atomicAdd(&tot[0], (unsigned long long)nvalid);
+        atomicAdd(&tot[1], (unsigned long long)below[0]);
+        atomicAdd(&tot[2], (unsigned long long)below[1]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&s->n_valid, tot[0]);
+        atomicAdd(&s->below[0], tot[1]);
+        atomicAdd(&s->below[1], tot[2]);
+    }
+}
+
+// Rank r among c keys that all lie in [L, U]: whole CTA (1024 threads) cooperates. Digits are taken from
+// k - L, which is spread almost uniformly over [0, U - L] (the bracket is a narrow slice of the density), so the
+// shared-memory histogram sees no hot bin. Returns the key.
+__device__ unsigned cta_bracket_select(const unsigned* __restrict__ keys, unsigned c, unsigned r, unsigned L, unsigned U,
+                                       unsigned* hist /*2048 smem*/, unsigned* s_tmp /*34 smem*/) {
+    const unsigned range = U - L;                        // keys' offsets are in [0, range]
+    int width = 32 - __clz(range | 1u);                  // bits needed for an offset
+    unsigned base = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    while (true) {
+        const int s = width > 11 ? width - 11 : 0;
+        for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < c; i += blockDim.x) {
+            const unsigned long long off = (unsigned long long)(keys[i] - L) - (unsigned long long)base;
+            if (keys[i] - L >= base && (off >> width) == 0ull) atomicAdd(&hist[(unsigned)(off >> s)], 1u);
+        }
+        __syncthreads();
+        // block-wide exclusive scan of the 2048 bins (2 per thread), then locate the bin holding rank r
+        const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_tmp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = s_tmp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            s_tmp[lane] = w;                              // inclusive totals per warp
+        }
+        __syncthreads();
+        const unsigned before = (warp ? s_tmp[warp - 1] : 0u) + incl - (h0 + h1);   // exclusive prefix of bin 2*tid
+        if (r >= before && r < before + h0) { s_tmp[32] = 2 * threadIdx.x; s_tmp[33] = r - before; }
+        else if (r >= before + h0 && r < before + h0 + h1) { s_tmp[32] = 2 * threadIdx.x + 1; s_tmp[33] = r - before - h0; }
+        __syncthreads();
+        base += s_tmp[32] << s;
+        r = s_tmp[33];
+        width = s;
+        __syncthreads();
+        if (s == 0) break;
+    }
+    return base + L;
+}
+
+__global__ void __launch_bounds__(1024) sel_final_kernel(SelFast* __restrict__ st, const unsigned* __restrict__ cand, unsigned cap,
+                                                         int n_q, const double* __restrict__ quant, int use_abs,
+                                                         float* __restrict__ out, long long* __restrict__ n_valid_out,
+                                                         int* __restrict__ need) {
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned bc[34];
+    const int64_t t = blockIdx.x;
+    SelFast* s = st + t;
+    const unsigned long long nv = s->n_valid;
+    bool ok = nv > 0;
+    long long lo[SEL_MAXQ], hi[SEL_MAXQ];
+    for (int q = 0; q < n_q; ++q) {
+        target_ranks(nv, quant[q], lo[q], hi[q]);
+        const long long b = (long long)s->below[q], c = (long long)s->ncand[q];
+        ok = ok && c <= (long long)cap && lo[q] >= b && hi[q] < b + c;
+    }
+    if (!ok) {
+        if (threadIdx.x == 0) { need[t] = 1; if (n_valid_out) n_valid_out[t] = (long long)nv; }
+        return;
+    }
+    for (int q = 0; q < n_q; ++q) {
+        const unsigned* keys = cand + ((size_t)t * SEL_MAXQ + q) * cap;
+        const unsigned c = s->ncand[q];
+        const unsigned a = cta_bracket_select(keys, c, (unsigned)(lo[q] - (long long)s->below[q]), s->L[q], s->U[q], hist, bc);
+        const unsigned b = (hi[q] == lo[q]) ? a
+                         : cta_bracket_select(keys, c, (unsigned)(hi[q] - (long long)s->below[q]), s->L[q], s->U[q], hist, bc);
+        if (threadIdx.x == 0) {
+            out[t * 2 * n_q + 2 * q] = value_of(a, use_abs);
+            out[t * 2 * n_q + 2 * q + 1] = value_of(b, use_abs);
+        }
+    }
+    if (threadIdx.x == 0) { need[t] = 0; if (n_valid_out) n_valid_out[t] = (long long)nv; }
+}
+
+// =================================================================================================
+// radix path (small frames, flagged frames)
+// =================================================================================================
 // PASS 0: bits 31..21, PASS 1: bits 20..10 (given 11-bit prefix), PASS 2: bits 9..0 (given 22-bit prefix)
 template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS) sel_hist_kernel(const float* __restrict__ stack, int64_t n,
                                                                int nr, int use_abs,
                                                                const SelState* __restrict__ st,
-                                                               unsigned* __restrict__ hist) {
+                                                               unsigned* __restrict__ hist, const int* __restrict__ need) {
     extern __shared__ unsigned sh[];                      // nr_eff * SEL_BINS
     const int64_t t = blockIdx.y;
+    if (need && !need[t]) return;
     const int nre = (PASS == 0) ? 1 : nr;
     for (int i = threadIdx.x; i < nre * SEL_BINS; i += blockDim.x) sh[i] = 0;
     unsigned pre[SEL_MAXR];
@@ -87,10 +358,13 @@ template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS) sel_scan_kernel(unsigned* __restrict__ hist, int nr, int n_q,
                                                                const double* __restrict__ quant, int use_abs,
                                                                SelState* __restrict__ st, float* __restrict__ out,
-                                                               long long* __restrict__ n_valid_out) {
+                                                               long long* __restrict__ n_valid_out,
+                                                               const int* __restrict__ need) {
     const int64_t t = blockIdx.x;
+    if (need && !need[t]) return;
     unsigned* g = hist + (size_t)t * SEL_MAXR * SEL_BINS;
     __shared__ unsigned long long cum[SEL_BINS];
+    __shared__ unsigned long long part[SEL_THREADS];
     __shared__ SelState s;
     constexpr int PSHIFT = (PASS == 1) ? 21 : 10;
     constexpr int SHIFT = (PASS == 0) ? 21 : (PASS == 1 ? 10 : 0);
@@ -103,11 +377,9 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_scan_kernel(unsigned* __restr
         if (PASS == 0) owner = 0;
         else for (int q = r - 1; q >= 0; --q) if ((s.prefix[q] >> PSHIFT) == (s.prefix[r] >> PSHIFT)) owner = q;
         const unsigned* h = g + owner * SEL_BINS;
-        // inclusive scan of 2048 bins by 256 threads (8 bins each) -- sizes are tiny, keep it simple
         unsigned long long loc[8], run = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { run += h[threadIdx.x * 8 + i]; loc[i] = run; }
-        __shared__ unsigned long long part[SEL_THREADS];
         part[threadIdx.x] = run;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -115,17 +387,9 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_scan_kernel(unsigned* __restr
             for (int i = 0; i < SEL_THREADS; ++i) { unsigned long long v = part[i]; part[i] = a; a += v; }
             if (PASS == 0 && r == 0) {
                 s.n_valid = (long long)a;
-                // numpy's linear method: h = n*q + (1 + q*(1-1-1)) - 1, lo = floor(h), hi = min(lo+1, n-1)
                 for (int q = 0; q < n_q; ++q) {
-                    long long lo = 0, hi = 0;
-                    if (a > 0) {
-                        const double qq = quant[q];
-                        const double hh = __dadd_rn(__dadd_rn(__dmul_rn((double)a, qq), __dadd_rn(1.0, __dmul_rn(qq, -1.0))), -1.0);
-                        lo = (long long)floor(hh);
-                        if (lo < 0) lo = 0;
-                        if (lo > (long long)a - 1) lo = (long long)a - 1;
-                        hi = lo + 1 > (long long)a - 1 ? (long long)a - 1 : lo + 1;
-                    }
+                    long long lo, hi;
+                    target_ranks(a, quant[q], lo, hi);
                     s.rank[2 * q] = lo; s.rank[2 * q + 1] = hi;
                     s.prefix[2 * q] = 0; s.prefix[2 * q + 1] = 0;
                 }
@@ -155,54 +419,91 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_scan_kernel(unsigned* __restr
         }
     }
     __syncthreads();
-    // clear for the next pass
-    for (int i = threadIdx.x; i < SEL_MAXR * SEL_BINS; i += blockDim.x) g[i] = 0;
+    for (int i = threadIdx.x; i < SEL_MAXR * SEL_BINS; i += blockDim.x) g[i] = 0;   // clear for the next pass
+}
+
+int radix_path(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q, int use_abs, float* out,
+               long long* n_valid, const int* need, unsigned* hist, SelState* st) {
+    const int nr = 2 * n_q;
+    int bpf = (int)((n + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
+    const int cap = ctx->sm_count * 8;
+    if ((int64_t)bpf * T > cap) bpf = (int)((cap + T - 1) / T);
+    if (bpf < 1) bpf = 1;
+    dim3 grid((unsigned)bpf, (unsigned)T);
+    const unsigned tc = (unsigned)T;
+    { ProfScope ps(ctx, KC_SELECT_HIST);
+      sel_hist_kernel<0><<<grid, SEL_THREADS, SEL_BINS * sizeof(unsigned), ctx->stream>>>(stack, n, nr, use_abs, st, hist, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    { ProfScope ps(ctx, KC_SELECT_SCAN);
+      sel_scan_kernel<0><<<tc, SEL_THREADS, 0, ctx->stream>>>(hist, nr, n_q, q_dev, use_abs, st, out, n_valid, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    { ProfScope ps(ctx, KC_SELECT_HIST);
+      sel_hist_kernel<1><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(stack, n, nr, use_abs, st, hist, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    { ProfScope ps(ctx, KC_SELECT_SCAN);
+      sel_scan_kernel<1><<<tc, SEL_THREADS, 0, ctx->stream>>>(hist, nr, n_q, q_dev, use_abs, st, out, n_valid, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    { ProfScope ps(ctx, KC_SELECT_HIST);
+      sel_hist_kernel<2><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(stack, n, nr, use_abs, st, hist, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    { ProfScope ps(ctx, KC_SELECT_SCAN);
+      sel_scan_kernel<2><<<tc, SEL_THREADS, 0, ctx->stream>>>(hist, nr, n_q, q_dev, use_abs, st, out, n_valid, need); }
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
 }
 
 }  // namespace
 
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid) {
-    const int nr = 2 * n_q;
-    void* p = nullptr;
-    const size_t hist_bytes = (size_t)T * SEL_MAXR * SEL_BINS * sizeof(unsigned);
-    const size_t st_bytes = (size_t)T * sizeof(SelState);
-    int rc = b4d_scratch(ctx, SCR_SELECT, hist_bytes + st_bytes, &p);
-    if (rc) return rc;
-    unsigned* hist = static_cast<unsigned*>(p);
-    SelState* st = reinterpret_cast<SelState*>(static_cast<char*>(p) + hist_bytes);
-    B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hist_bytes + st_bytes, ctx->stream));
-
-    int bpf = (int)((n + SEL_THREADS * 16 - 1) / (SEL_THREADS * 16));
-    const int cap = ctx->sm_count * 8;
-    if ((int64_t)bpf * T > cap) bpf = (int)((cap + T - 1) / T);
-    if (bpf < 1) bpf = 1;
-    for (int64_t t0 = 0; t0 < T; t0 += 32768) {
-        const unsigned tc = (unsigned)((T - t0 < 32768) ? T - t0 : 32768);
-        dim3 grid((unsigned)bpf, tc);
+    static int sample_attr = 0;
+    const bool fast = n >= SEL_FAST_MIN;
+    const unsigned cap = fast ? (unsigned)(n / 8) : 0u;
+    const int64_t TC = 16384;
+    for (int64_t t0 = 0; t0 < T; t0 += TC) {
+        const int64_t tc = T - t0 < TC ? T - t0 : TC;
+        void* p = nullptr;
+        const size_t hist_bytes = (size_t)tc * SEL_MAXR * SEL_BINS * sizeof(unsigned);
+        const size_t st_bytes = ((size_t)tc * sizeof(SelState) + 255) & ~size_t(255);
+        const size_t fast_bytes = ((size_t)tc * sizeof(SelFast) + 255) & ~size_t(255);
+        const size_t need_bytes = ((size_t)tc * sizeof(int) + 255) & ~size_t(255);
+        const size_t cand_bytes = (size_t)tc * SEL_MAXQ * cap * sizeof(unsigned);
+        int rc = b4d_scratch(ctx, SCR_SELECT, hist_bytes + st_bytes + fast_bytes + need_bytes + cand_bytes, &p);
+        if (rc) return rc;
+        char* base = static_cast<char*>(p);
+        unsigned* hist = reinterpret_cast<unsigned*>(base);
+        SelState* st = reinterpret_cast<SelState*>(base + hist_bytes);
+        SelFast* sf = reinterpret_cast<SelFast*>(base + hist_bytes + st_bytes);
+        int* need = reinterpret_cast<int*>(base + hist_bytes + st_bytes + fast_bytes);
+        unsigned* cand = reinterpret_cast<unsigned*>(base + hist_bytes + st_bytes + fast_bytes + need_bytes);
+        B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hist_bytes + st_bytes + fast_bytes + need_bytes, ctx->stream));
         const float* s0 = stack + t0 * n;
-        unsigned* h0 = hist + (size_t)t0 * SEL_MAXR * SEL_BINS;
-        SelState* st0 = st + t0;
-        float* o0 = out + t0 * nr;
+        float* o0 = out + t0 * 2 * n_q;
         long long* nv0 = n_valid ? reinterpret_cast<long long*>(n_valid) + t0 : nullptr;
-        { ProfScope ps(ctx, KC_SELECT_HIST);
-        sel_hist_kernel<0><<<grid, SEL_THREADS, SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
-        B4D_LAUNCH_CHECK(ctx);
-        { ProfScope ps(ctx, KC_SELECT_SCAN);
-        sel_scan_kernel<0><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
-        B4D_LAUNCH_CHECK(ctx);
-        { ProfScope ps(ctx, KC_SELECT_HIST);
-        sel_hist_kernel<1><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
-        B4D_LAUNCH_CHECK(ctx);
-        { ProfScope ps(ctx, KC_SELECT_SCAN);
-        sel_scan_kernel<1><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
-        B4D_LAUNCH_CHECK(ctx);
-        { ProfScope ps(ctx, KC_SELECT_HIST);
-        sel_hist_kernel<2><<<grid, SEL_THREADS, nr * SEL_BINS * sizeof(unsigned), ctx->stream>>>(s0, n, nr, use_abs, st0, h0); }
-        B4D_LAUNCH_CHECK(ctx);
-        { ProfScope ps(ctx, KC_SELECT_SCAN);
-        sel_scan_kernel<2><<<tc, SEL_THREADS, 0, ctx->stream>>>(h0, nr, n_q, q_dev, use_abs, st0, o0, nv0); }
-        B4D_LAUNCH_CHECK(ctx);
+        if (fast) {
+            if (!sample_attr) {
+                B4D_CUDA(ctx, cudaFuncSetAttribute(sel_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(SEL_SAMPLES * sizeof(unsigned))));
+                sample_attr = 1;
+            }
+            { ProfScope ps(ctx, KC_SELECT_SAMPLE);
+              sel_sample_kernel<<<(unsigned)tc, 1024, SEL_SAMPLES * sizeof(unsigned), ctx->stream>>>(s0, n, n_q, q_dev, use_abs, sf); }
+            B4D_LAUNCH_CHECK(ctx);
+            int bpf = (int)((n + COL_CHUNK - 1) / COL_CHUNK);
+            const int capb = ctx->sm_count * 12;
+            if ((int64_t)bpf * tc > capb) bpf = (int)((capb + tc - 1) / tc);
+            if (bpf < 1) bpf = 1;
+            { ProfScope ps(ctx, KC_SELECT_COLLECT);
+              sel_collect_kernel<<<dim3((unsigned)bpf, (unsigned)tc), 256, 0, ctx->stream>>>(s0, n, n_q, use_abs, sf, cand, cap); }
+            B4D_LAUNCH_CHECK(ctx);
+            { ProfScope ps(ctx, KC_SELECT_FINAL);
+              sel_final_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(sf, cand, cap, n_q, q_dev, use_abs, o0, nv0, need); }
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        // frames the bracket did not resolve (or every frame when they are small) take the three-pass radix select;
+        // resolved frames return at the first instruction of each kernel
+        rc = radix_path(ctx, s0, tc, n, q_dev, n_q, use_abs, o0, nv0, fast ? need : nullptr, hist, st);
+        if (rc) return rc;
     }
     return B4D_OK;
 }
@@ -211,8 +512,8 @@ extern "C" int b4d_select_ranks(b4d_ctx* ctx, const float* stack, int64_t n_fram
                                 const double* quantiles_host, int n_q, int use_abs, float* out, int64_t* n_valid) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
-    if (!stack || !out || !quantiles_host || n_frames < 1 || frame_elems < 1 || n_q < 1 || 2 * n_q > SEL_MAXR)
-        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_select_ranks: bad arguments (n_q must be 1..%d)", SEL_MAXR / 2);
+    if (!stack || !out || !quantiles_host || n_frames < 1 || frame_elems < 1 || n_q < 1 || n_q > SEL_MAXQ)
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_select_ranks: bad arguments (n_q must be 1..%d)", SEL_MAXQ);
     for (int i = 0; i < n_q; ++i)
         if (!(quantiles_host[i] >= 0.0 && quantiles_host[i] <= 1.0))
             return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_select_ranks: quantile %d outside [0, 1]", i);

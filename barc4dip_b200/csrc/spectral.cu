@@ -25,6 +25,8 @@ int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t 
                            const float* dark, float* pilot);
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid);
+int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                                const float* dark, double sat_value, double zero_eps, double* out);
 
 struct FftPlanCache {
     float2* tw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 128, 256, 512, 1024, 2048
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
         const int col = j + m * TPF;
-        float va = ldg_stream1(ra + col), vb = ldg_stream1(rb + col);
+        float va = __ldcs(ra + col), vb = __ldcs(rb + col);
         if (a.gain) {
             const size_t pa = (size_t)(y0 + 2 * f) * NX + col, pb = pa + NX;
             va = (va - (a.dark ? __ldg(a.dark + pa) : 0.f)) * __ldg(a.gain + pa);
@@ -557,36 +559,14 @@ __global__ void __launch_bounds__(128) argmax_reduce_kernel(const ArgBest* __res
 }
 
 // z-score the (h, w) template over its own pixels and embed it at (y0, x0) in a zero (ny, nx) frame
-// (signal/tracking.py:251-260). One CTA; the template is small next to a stack.
-__global__ void __launch_bounds__(1024) embed_template_kernel(const float* __restrict__ tpl, int h, int w, int ny, int nx,
-                                                              int y0, int x0, float eps, float* __restrict__ out) {
-    __shared__ double sh[32];
-    __shared__ double s_mean, s_std;
-    const int n = h * w;
-    // nanmean
-    double s = 0.0, cnt = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = tpl[i]; if (v == v) { s += v; cnt += 1.0; } }
-    s = warp_sum(s); cnt = warp_sum(cnt);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_mean = a; }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_mean = a > 0 ? s_mean / a : nan(""); s_std = a; }
-    __syncthreads();
-    const double mean = s_mean, count = s_std;
-    __syncthreads();
-    double q = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = tpl[i]; if (v == v) { const double d = (double)v - mean; q += d * d; } }
-    q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = q;
-    __syncthreads();
-    if (threadIdx.x == 0) { double a = 0; for (int i = 0; i < 32; ++i) a += sh[i]; s_std = count > 0 ? sqrt(a / count) : nan(""); }
-    __syncthreads();
-    const float m = (float)mean, inv = 1.f / ((float)s_std + eps);
-    for (int i = threadIdx.x; i < ny * nx; i += blockDim.x) {
-        const int y = i / nx, xq = i % nx;
+// (signal/tracking.py:251-260). mean / variance come from the frame-reduction table of the template.
+__global__ void __launch_bounds__(256) embed_template_kernel(const float* __restrict__ tpl, int h, int w, int ny, int nx,
+                                                             int y0, int x0, float eps, const double* __restrict__ fr,
+                                                             float* __restrict__ out) {
+    const float m = (float)fr[B4D_FR_MEAN];
+    const float inv = 1.f / ((float)sqrt(fr[B4D_FR_M2]) + eps);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ny * nx; i += gridDim.x * blockDim.x) {
+        const int y = i / nx, xq = i - y * nx;
         const int ty = y - y0, tx = xq - x0;
         float v = 0.f;
         if (ty >= 0 && ty < h && tx >= 0 && tx < w) v = (tpl[ty * w + tx] - m) * inv;
@@ -1202,9 +1182,11 @@ extern "C" int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, in
         f->ref_ny = ny; f->ref_nx = nx;
     }
     void* p = nullptr;
-    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)ny * nx, &p))) return rc;
+    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)ny * nx + sizeof(double) * B4D_FR_NCOLS, &p))) return rc;
     float* padded = static_cast<float*>(p);
-    embed_template_kernel<<<1, 1024, 0, ctx->stream>>>(tpl, h, w, ny, nx, y0, x0, (float)eps, padded);
+    double* tfr = reinterpret_cast<double*>(padded + (size_t)ny * nx);
+    if ((rc = b4d_frame_reductions_nolock(ctx, tpl, 1, h, w, nullptr, nullptr, nan(""), 0.0, tfr))) return rc;
+    embed_template_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(tpl, h, w, ny, nx, y0, x0, (float)eps, tfr, padded);
     B4D_LAUNCH_CHECK(ctx);
     Work wk;
     if ((rc = carve(ctx, 1, ny, nx, false, false, &wk))) return rc;
@@ -1236,9 +1218,6 @@ int track_finish(b4d_ctx* ctx, Work& w, const float* mag, int64_t tc, int ny, in
 }
 
 }  // namespace
-
-int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                                const float* dark, double sat_value, double zero_eps, double* out);
 
 extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps,
                                double* out) {
