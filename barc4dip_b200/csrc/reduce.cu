@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) pilot_kernel(const float* __restrict__ st
 // shifted by K (d = x - K).
 struct RowWin {
     float c[6];
+    bool clean;   // all four pixels exist, are finite and are neither zero- nor saturation-candidates
 };
 
 struct Acc {
@@ -136,24 +137,45 @@ __device__ __forceinline__ RowWin finish_row(const FrArgs& a, const RawRow& raw,
     }
     w.c[0] = left;
     w.c[5] = right;
+    // Lane-level screening (a handful of instructions per four pixels) so that ordinary pixels skip every
+    // per-pixel test: the |x| sum is non-finite iff some pixel is NaN/inf (or absurdly large), min|x| > zeps
+    // rules out zero-candidates, max x < sat rules out saturation-candidates.
+    const float a0 = fabsf(raw.x[0]), a1 = fabsf(raw.x[1]), a2 = fabsf(raw.x[2]), a3 = fabsf(raw.x[3]);
+    bool clean = (j0 + 4 <= a.nx) && ((a0 + a1) + (a2 + a3) <= 3.402823466e38f) &&
+                 (fminf(fminf(a0, a1), fminf(a2, a3)) > a.zeps);
+    if (a.has_sat) clean = clean && (fmaxf(fmaxf(raw.x[0], raw.x[1]), fmaxf(raw.x[2], raw.x[3])) < a.sat);
+    w.clean = clean;
     if (in_band) {
+        if (clean) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float xv = raw.x[k];
-            const bool valid = j0 + k < a.nx;
-            const bool fin = valid && (fabsf(xv) <= 3.402823466e38f);   // false for NaN / inf
-            if (fin) {
+            for (int k = 0; k < 4; ++k) {
                 const float d = w.c[k + 1];
                 const float d2 = d * d;
                 acc.s1 += d;
                 acc.s2 += d2;
                 acc.s3 = fmaf(d2, d, acc.s3);
                 acc.s4 = fmaf(d2, d2, acc.s4);
-                acc.nfin++;
-                acc.nzero += (fabsf(xv) <= a.zeps) ? 1 : 0;
-                acc.nsat += (a.has_sat && xv >= a.sat) ? 1 : 0;
-            } else if (valid && xv != xv) {
-                acc.nnan++;
+            }
+            acc.nfin += 4;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xv = raw.x[k];
+                const bool valid = j0 + k < a.nx;
+                const bool fin = valid && (fabsf(xv) <= 3.402823466e38f);   // false for NaN / inf
+                if (fin) {
+                    const float d = w.c[k + 1];
+                    const float d2 = d * d;
+                    acc.s1 += d;
+                    acc.s2 += d2;
+                    acc.s3 = fmaf(d2, d, acc.s3);
+                    acc.s4 = fmaf(d2, d2, acc.s4);
+                    acc.nfin++;
+                    acc.nzero += (fabsf(xv) <= a.zeps) ? 1 : 0;
+                    acc.nsat += (a.has_sat && xv >= a.sat) ? 1 : 0;
+                } else if (valid && xv != xv) {
+                    acc.nnan++;
+                }
             }
         }
     }
@@ -173,11 +195,11 @@ __device__ __forceinline__ void stencil_row(const RowWin& up, const RowWin& mid,
         const float ctr = mid.c[k + 1];
         // the reference averages over pixels whose own value is finite; non-finite neighbours
         // propagate into the sums exactly as they do through scipy.ndimage.
-        const bool fin = (j0 + k < nx) && (fabsf(ctr) <= 3.402823466e38f);
+        const bool fin = mid.clean || ((j0 + k < nx) && (fabsf(ctr) <= 3.402823466e38f));
         if (fin) {
             const float gx = s[k + 2] - s[k];
-            const float gy = dv[k] + 2.f * dv[k + 1] + dv[k + 2];
-            const float lp = (up.c[k + 1] + dn.c[k + 1]) + (mid.c[k] + mid.c[k + 2]) - 4.f * ctr;
+            const float gy = fmaf(2.f, dv[k + 1], dv[k] + dv[k + 2]);
+            const float lp = fmaf(-4.f, ctr, (up.c[k + 1] + dn.c[k + 1]) + (mid.c[k] + mid.c[k + 2]));
             acc.gx2 = fmaf(gx, gx, acc.gx2);
             acc.gy2 = fmaf(gy, gy, acc.gy2);
             acc.lap += lp;
@@ -187,7 +209,7 @@ __device__ __forceinline__ void stencil_row(const RowWin& up, const RowWin& mid,
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(FR_WARPS * 32) frame_reduce_kernel(FrArgs a) {
+__global__ void __launch_bounds__(FR_WARPS * 32, 2) frame_reduce_kernel(FrArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * FR_WARPS + warp;
     const int64_t t = blockIdx.y;

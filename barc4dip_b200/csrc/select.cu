@@ -40,9 +40,11 @@ struct SelFast {                      // per frame, device resident (bracket pat
     int need_fallback;
 };
 
+// order-preserving key; -0.0 maps onto +0.0 so that key order and float order agree for every non-NaN value
 __device__ __forceinline__ unsigned key_of(float v, int use_abs) {
     unsigned b = __float_as_uint(v);
     if (use_abs) return b & 0x7fffffffu;
+    if (b == 0x80000000u) b = 0u;
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 __device__ __forceinline__ float value_of(unsigned k, int use_abs) {
@@ -69,157 +71,6 @@ __device__ __forceinline__ void hist_add(unsigned* h, unsigned bin) {
 // =================================================================================================
 // fast path
 // =================================================================================================
-__global__ void __launch_bounds__(1024) sel_sample_kernel(const float* __restrict__ stack, int64_t n, int n_q,
-                                                          const double* __restrict__ quant, int use_abs,
-                                                          SelFast* __restrict__ st) {
-    extern __shared__ unsigned keys[];              // SEL_SAMPLES
-    __shared__ int s_valid;
-    const int64_t t = blockIdx.x;
-    const float* f = stack + t * n;
-    if (threadIdx.x == 0) s_valid = 0;
-    __syncthreads();
-    int nv = 0;
-    for (int i = threadIdx.x; i < SEL_SAMPLES; i += blockDim.x) {
-        const int64_t p = (int64_t)(((__int128)i * n) / SEL_SAMPLES);
-        const float v = __ldg(f + p);
-        const bool ok = v == v;
-        keys[i] = ok ? key_of(v, use_abs) : 0xffffffffu;     // NaNs sort last
-        nv += ok;
-    }
-    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_valid, nv);
-    __syncthreads();
-    // bitonic sort of SEL_SAMPLES keys
-    for (int k = 2; k <= SEL_SAMPLES; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < SEL_SAMPLES / 2; i += blockDim.x) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const unsigned a = keys[lo], b = keys[hi];
-                const bool up = (lo & k) == 0;
-                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x == 0) {
-        SelFast s;
-        const int m = s_valid;
-        for (int q = 0; q < SEL_MAXQ; ++q) { s.L[q] = 0u; s.U[q] = 0xfffffffeu; s.below[q] = 0ull; s.ncand[q] = 0u; }
-        s.n_valid = 0ull;
-        s.need_fallback = 0;
-        if (m >= 1024) {
-            for (int q = 0; q < n_q; ++q) {
-                const double qq = quant[q];
-                const double c = qq * (double)(m - 1);
-                const double d = 6.0 * sqrt(qq * (1.0 - qq) * (double)m) + 8.0;
-                const long long il = (long long)floor(c - d), iu = (long long)ceil(c + d);
-                s.L[q] = il <= 0 ? 0u : keys[il];
-                s.U[q] = iu >= m - 1 ? 0xfffffffeu : keys[iu];
-            }
-        }
-        st[t] = s;
-    }
-}
-
-// One pass over the frame. A CTA works through chunks of COL_CHUNK elements: candidates are appended to a
-// shared-memory list (warp-aggregated shared atomics), then one thread reserves a range of the frame's global
-// candidate list and the CTA copies the chunk's candidates out coalesced -- one global atomic per chunk and
-// bracket instead of one per warp.
-constexpr int COL_THREADS = 256;
-constexpr int COL_VEC = 4;
-constexpr int COL_ITERS = 4;
-constexpr int COL_CHUNK = COL_THREADS * COL_VEC * COL_ITERS;     // 4096 elements
-
-__global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* __restrict__ stack, int64_t n, int n_q,
-                                                                  int use_abs, SelFast* __restrict__ st,
-                                                                  unsigned* __restrict__ cand, unsigned cap) {
-    __shared__ unsigned buf[SEL_MAXQ][COL_CHUNK];
-    __shared__ unsigned cnt[SEL_MAXQ], gbase[SEL_MAXQ];
-    __shared__ unsigned long long tot[3];
-    const int64_t t = blockIdx.y;
-    const float* f = stack + t * n;
-    SelFast* s = st + t;
-    unsigned L[SEL_MAXQ], U[SEL_MAXQ];
-#pragma unroll
-    for (int q = 0; q < SEL_MAXQ; ++q) { L[q] = s->L[q]; U[q] = s->U[q]; }
-    unsigned nvalid = 0, below[SEL_MAXQ] = {0u, 0u};
-    const int lane = threadIdx.x & 31;
-    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
-    if (threadIdx.x < 3) tot[threadIdx.x] = 0ull;
-    const int64_t nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
-    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        if (threadIdx.x < SEL_MAXQ) cnt[threadIdx.x] = 0u;
-        __syncthreads();
-        const int64_t e0 = ch * COL_CHUNK;
-        float v[COL_ITERS][COL_VEC];
-#pragma unroll
-        for (int it = 0; it < COL_ITERS; ++it) {
-            const int64_t e = e0 + ((int64_t)it * COL_THREADS + threadIdx.x) * COL_VEC;
-            if (vec && e + COL_VEC <= n) {
-                const float4 x = __ldcs(reinterpret_cast<const float4*>(f + e));
-                v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < COL_VEC; ++k) v[it][k] = (e + k < n) ? __ldcs(f + e + k) : __uint_as_float(0x7fc00000u);
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < COL_ITERS; ++it) {
-#pragma unroll
-            for (int k = 0; k < COL_VEC; ++k) {
-                const float x = v[it][k];
-                const bool ok = x == x;
-                const unsigned key = ok ? key_of(x, use_abs) : 0u;
-                nvalid += ok;
-#pragma unroll
-                for (int q = 0; q < SEL_MAXQ; ++q) {
-                    if (q < n_q) {
-                        const bool lt = ok && key < L[q];
-                        const bool in = ok && !lt && key <= U[q];
-                        below[q] += lt;
-                        const unsigned m = __ballot_sync(0xffffffffu, in);
-                        if (m) {
-                            unsigned base = 0;
-                            const int leader = __ffs(m) - 1;
-                            if (lane == leader) base = atomicAdd(&cnt[q], (unsigned)__popc(m));
-                            base = __shfl_sync(0xffffffffu, base, leader);
-                            if (in) buf[q][base + __popc(m & ((1u << lane) - 1u))] = key;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < n_q && cnt[threadIdx.x]) gbase[threadIdx.x] = atomicAdd(&s->ncand[threadIdx.x], cnt[threadIdx.x]);
-        __syncthreads();
-        for (int q = 0; q < n_q; ++q) {
-            const unsigned c = cnt[q], g0 = gbase[q];
-            unsigned* dst = cand + ((size_t)t * SEL_MAXQ + q) * cap;
-            for (unsigned i = threadIdx.x; i < c; i += COL_THREADS)
-                if (g0 + i < cap) dst[g0 + i] = buf[q][i];
-        }
-        __syncthreads();
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-        below[0] += __shfl_xor_sync(0xffffffffu, below[0], o);
-        below[1] += __shfl_xor_sync(0xffffffffu, below[1], o);
-    }
-    __syncthreads();
-    if (lane == 0) {
-        atomicAdd(&tot[0], (unsigned long long)nvalid);
-        atomicAdd(&tot[1], (unsigned long long)below[0]);
-        atomicAdd(&tot[2], (unsigned long long)below[1]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(&s->n_valid, tot[0]);
-        atomicAdd(&s->below[0], tot[1]);
-        atomicAdd(&s->below[1], tot[2]);
-    }
-}
-
 // Rank r among c keys that all lie in [L, U]: whole CTA (1024 threads) cooperates. Digits are taken from
 // k - L, which is spread almost uniformly over [0, U - L] (the bracket is a narrow slice of the density), so the
 // shared-memory histogram sees no hot bin. Returns the key.
@@ -269,6 +120,183 @@ __device__ unsigned cta_bracket_select(const unsigned* __restrict__ keys, unsign
         if (s == 0) break;
     }
     return base + L;
+}
+
+__global__ void __launch_bounds__(1024) sel_sample_kernel(const float* __restrict__ stack, int64_t n, int n_q,
+                                                          const double* __restrict__ quant, int use_abs,
+                                                          SelFast* __restrict__ st) {
+    extern __shared__ unsigned keys[];              // SEL_SAMPLES
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned tmp[34];
+    __shared__ unsigned s_min, s_max;
+    __shared__ int s_valid;
+    const int64_t t = blockIdx.x;
+    const float* f = stack + t * n;
+    if (threadIdx.x == 0) { s_valid = 0; s_min = 0xffffffffu; s_max = 0u; }
+    __syncthreads();
+    int nv = 0;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    for (int i = threadIdx.x; i < SEL_SAMPLES; i += blockDim.x) {
+        const int64_t p = (int64_t)(((__int128)i * n) / SEL_SAMPLES);
+        const float v = __ldg(f + p);
+        const bool ok = v == v;
+        const unsigned k = ok ? key_of(v, use_abs) : 0xffffffffu;     // NaNs sort last (and are never selected)
+        keys[i] = k;
+        nv += ok;
+        if (ok) { kmin = min(kmin, k); kmax = max(kmax, k); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_valid, nv); atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+    __syncthreads();
+    const int m = s_valid;
+    const unsigned lo_key = s_min, hi_key = s_max;
+    // bracket [L, U] = sample order statistics +-6 sigma (binomial) around each quantile, found by selection
+    unsigned Lq[SEL_MAXQ], Uq[SEL_MAXQ];
+    for (int q = 0; q < SEL_MAXQ; ++q) { Lq[q] = 0u; Uq[q] = 0xfffffffeu; }
+    if (m >= 1024) {
+        for (int q = 0; q < n_q; ++q) {
+            const double qq = quant[q];
+            const double c = qq * (double)(m - 1);
+            const double d = 6.0 * sqrt(qq * (1.0 - qq) * (double)m) + 8.0;
+            const long long il = (long long)floor(c - d), iu = (long long)ceil(c + d);
+            if (il > 0) Lq[q] = cta_bracket_select(keys, SEL_SAMPLES, (unsigned)il, lo_key, hi_key, hist, tmp);
+            if (iu < m - 1) Uq[q] = cta_bracket_select(keys, SEL_SAMPLES, (unsigned)iu, lo_key, hi_key, hist, tmp);
+        }
+    }
+    if (threadIdx.x == 0) {
+        SelFast s;
+        for (int q = 0; q < SEL_MAXQ; ++q) { s.L[q] = Lq[q]; s.U[q] = Uq[q]; s.below[q] = 0ull; s.ncand[q] = 0u; }
+        s.n_valid = 0ull;
+        s.need_fallback = 0;
+        st[t] = s;
+    }
+}
+
+// One pass over the frame. A CTA works through chunks of COL_CHUNK elements. Phase 1 screens in float space
+// (key order == float order) and counts, per lane, the valid elements, the elements below each bracket and the
+// candidates inside it. A warp scan + a tiny CTA scan turn the per-lane counts into write offsets and ONE global
+// atomic per chunk and bracket reserves the range in the frame's candidate list; phase 2 re-tests the lane's
+// elements and writes the candidates' keys straight to their slots.
+constexpr int COL_THREADS = 256;
+constexpr int COL_WARPS = COL_THREADS / 32;
+constexpr int COL_VEC = 4;
+constexpr int COL_ITERS = 4;
+constexpr int COL_CHUNK = COL_THREADS * COL_VEC * COL_ITERS;     // 4096 elements
+
+__global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* __restrict__ stack, int64_t n, int n_q,
+                                                                  int use_abs, SelFast* __restrict__ st,
+                                                                  unsigned* __restrict__ cand, unsigned cap) {
+    __shared__ unsigned wtot[SEL_MAXQ][COL_WARPS], woff[SEL_MAXQ][COL_WARPS], gbase[SEL_MAXQ], btot[SEL_MAXQ];
+    __shared__ unsigned long long tot[3];
+    const int64_t t = blockIdx.y;
+    const float* f = stack + t * n;
+    SelFast* s = st + t;
+    float Lf[SEL_MAXQ], Uf[SEL_MAXQ];
+#pragma unroll
+    for (int q = 0; q < SEL_MAXQ; ++q) {
+        // L = 0 / U = 0xfffffffe are the open ends of a bracket
+        Lf[q] = s->L[q] == 0u ? -INFINITY : value_of(s->L[q], use_abs);
+        Uf[q] = s->U[q] == 0xfffffffeu ? INFINITY : value_of(s->U[q], use_abs);
+    }
+    unsigned nvalid = 0, below[SEL_MAXQ] = {0u, 0u};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+    if (threadIdx.x < 3) tot[threadIdx.x] = 0ull;
+    const int64_t nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t e0 = ch * COL_CHUNK;
+        float v[COL_ITERS][COL_VEC];
+#pragma unroll
+        for (int it = 0; it < COL_ITERS; ++it) {
+            const int64_t e = e0 + ((int64_t)it * COL_THREADS + threadIdx.x) * COL_VEC;
+            if (vec && e + COL_VEC <= n) {
+                const float4 x = __ldcs(reinterpret_cast<const float4*>(f + e));
+                v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < COL_VEC; ++k) v[it][k] = (e + k < n) ? __ldcs(f + e + k) : __uint_as_float(0x7fc00000u);
+            }
+            if (use_abs) {
+#pragma unroll
+                for (int k = 0; k < COL_VEC; ++k) v[it][k] = fabsf(v[it][k]);
+            }
+        }
+        unsigned c[SEL_MAXQ] = {0u, 0u};
+#pragma unroll
+        for (int it = 0; it < COL_ITERS; ++it)
+#pragma unroll
+            for (int k = 0; k < COL_VEC; ++k) {
+                const float x = v[it][k];
+                nvalid += (x == x);
+#pragma unroll
+                for (int q = 0; q < SEL_MAXQ; ++q)
+                    if (q < n_q) {
+                        below[q] += (x < Lf[q]);
+                        c[q] += (x >= Lf[q] && x <= Uf[q]);
+                    }
+            }
+        unsigned excl[SEL_MAXQ];
+#pragma unroll
+        for (int q = 0; q < SEL_MAXQ; ++q) {
+            unsigned incl = c[q];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            excl[q] = incl - c[q];
+            if (lane == 31) wtot[q][warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < SEL_MAXQ) {
+            const int q = threadIdx.x;
+            unsigned run = 0;
+#pragma unroll
+            for (int w = 0; w < COL_WARPS; ++w) { woff[q][w] = run; run += wtot[q][w]; }
+            btot[q] = run;
+            if (run && q < n_q) gbase[q] = atomicAdd(&s->ncand[q], run);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < SEL_MAXQ; ++q) {
+            if (q < n_q && c[q]) {
+                unsigned pos = gbase[q] + woff[q][warp] + excl[q];
+                unsigned* dst = cand + ((size_t)t * SEL_MAXQ + q) * cap;
+#pragma unroll
+                for (int it = 0; it < COL_ITERS; ++it)
+#pragma unroll
+                    for (int k = 0; k < COL_VEC; ++k) {
+                        const float x = v[it][k];
+                        if (x >= Lf[q] && x <= Uf[q]) {
+                            if (pos < cap) dst[pos] = key_of(x, use_abs);
+                            ++pos;
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+        below[0] += __shfl_xor_sync(0xffffffffu, below[0], o);
+        below[1] += __shfl_xor_sync(0xffffffffu, below[1], o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        atomicAdd(&tot[0], (unsigned long long)nvalid);
+        atomicAdd(&tot[1], (unsigned long long)below[0]);
+        atomicAdd(&tot[2], (unsigned long long)below[1]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&s->n_valid, tot[0]);
+        atomicAdd(&s->below[0], tot[1]);
+        atomicAdd(&s->below[1], tot[2]);
+    }
 }
 
 __global__ void __launch_bounds__(1024) sel_final_kernel(SelFast* __restrict__ st, const unsigned* __restrict__ cand, unsigned cap,
