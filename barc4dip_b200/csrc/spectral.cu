@@ -79,16 +79,6 @@ int get_twiddles(b4d_ctx* ctx, int n, const float2** out) {
     return B4D_OK;
 }
 
-// shared-memory slot functors ---------------------------------------------------------------------
-struct SlotLinear {          // one transform, contiguous
-    float2* base;
-    __device__ __forceinline__ float2& operator()(int i) const { return base[pad16(i)]; }
-};
-struct SlotBatch8 {          // 8 transforms interleaved (batch index fastest)
-    float2* base;            // already offset by the column
-    __device__ __forceinline__ float2& operator()(int i) const { return base[pad16(i) * 8]; }
-};
-
 // =================================================================================================
 // K1: rows forward
 // =================================================================================================
@@ -128,7 +118,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
         }
         x[m] = make_float2(va - K, vb - K);
     }
-    fft_from_regs<NX, -1>(x, j, SlotLinear{sm + f * FS}, a.tw);
+    fft_from_regs<NX, -1, 1>(x, j, sm + f * FS, a.tw);
 
     // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
     float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
@@ -224,7 +214,7 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
     float2 x[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) x[m] = __ldg(Hin + (size_t)(j + m * TPF) * 8 + c);
-    fft_from_regs<NY, -1>(x, j, SlotBatch8{A + c}, a.tw);
+    fft_from_regs<NY, -1, 8>(x, j, A + c, a.tw);
 
     // ---- tile 0: unpack column 0 (DC + i Nyquist rows) into F[:,0] (kept in A) and F[:,nx/2] (nyq)
     if (tile0) {
@@ -373,7 +363,7 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
 #pragma unroll
         for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
         __syncthreads();
-        fft_from_regs<NY, +1>(x, j, SlotBatch8{A + c}, a.tw);
+        fft_from_regs<NY, +1, 8>(x, j, A + c, a.tw);
         float2* o = a.i2_pc + (size_t)t * NY * hx + (size_t)tile * NY * 8;
         for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
         __syncthreads();
@@ -397,7 +387,7 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
 #pragma unroll
         for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
         __syncthreads();
-        fft_from_regs<NY, +1>(x, j, SlotBatch8{A + c}, a.tw);
+        fft_from_regs<NY, +1, 8>(x, j, A + c, a.tw);
         float2* o = a.i2_ac + (size_t)t * NY * hx + (size_t)tile * NY * 8;
         for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
     }
@@ -494,7 +484,7 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
 #pragma unroll
     for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
     __syncthreads();
-    fft_from_regs<NX, +1>(x, j, SlotLinear{z}, a.tw);
+    fft_from_regs<NX, +1, 1>(x, j, z, a.tw);
 
     // stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
     const int kindB = a.pair_maps ? a.kindB : a.kindA;
