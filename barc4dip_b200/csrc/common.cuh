@@ -33,8 +33,8 @@ struct b4d_ctx {
     std::string last_error;
     int64_t launches = 0;
     // grow-only scratch arenas (device)
-    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* scratch[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FftPlanCache* fft = nullptr;
     int64_t batch_override = 0;       // frames per internal batch of the FFT pipeline (0 = automatic)
     bool prof_on = false;
@@ -66,7 +66,7 @@ struct ProfScope {
 };
 
 // scratch slot ids
-enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7 };
+enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7, SCR_NYQ = 8 };
 
 inline int b4d_fail(b4d_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {

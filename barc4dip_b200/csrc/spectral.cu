@@ -82,6 +82,8 @@ int get_twiddles(b4d_ctx* ctx, int n, const float2** out) {
 // =================================================================================================
 // K1: rows forward
 // =================================================================================================
+constexpr int TC = 8;     // columns per K2 CTA = width of a tile of the blocked intermediates [kx/TC][y][kx%TC]
+
 struct RowsFwdArgs {
     const float* stack;
     const float* gain;
@@ -123,8 +125,8 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
     // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
     float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
     for (int idx = tid; idx < ROWS * (NX / 2); idx += 512) {
-        const int tile = idx / (ROWS * 8), rem = idx % (ROWS * 8);
-        const int r = rem >> 3, c = rem & 7, k = tile * 8 + c, p = r >> 1;
+        const int tile = idx / (ROWS * TC), rem = idx % (ROWS * TC);
+        const int r = rem / TC, c = rem % TC, k = tile * TC + c, p = r >> 1;
         const float2* z = sm + p * FS;
         const float2 Z = z[pad16(k)];
         float2 v;
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
             v = (r & 1) ? make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x))
                         : make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
         }
-        Hf[((size_t)tile * a.ny + y0 + r) * 8 + c] = v;
+        Hf[((size_t)tile * a.ny + y0 + r) * TC + c] = v;
     }
 }
 
@@ -147,6 +149,7 @@ struct ColsArgs {
     const float2* H;            // blocked input, per frame ny*nx/2
     const float2* tw;
     const float* pilot;         // nullable: DC += nx*ny*K
+    float2* nyq_scratch;        // (T, ny) global scratch for the Nyquist column (tile 0 only)
     int nx;
     int zero_dc;                // clear F[0,0] (mean removal) for every output
     int ac_zero_dc;             // clear it for the autocorrelation branch only (fused pipeline)
@@ -155,7 +158,7 @@ struct ColsArgs {
     float* psd_out;             // (T, ny, nx) shifted |F|^2 * psd_scale
     float psd_scale;
     double* spec_partials;      // (T, ntiles, NSP)
-    float2* conj_out;           // blocked conj(F) (T, nx/2/8, ny, 8)
+    float2* conj_out;           // blocked conj(F) (T, nx/2/TC, ny, TC)
     float2* conj_nyq_out;       // (T, ny)
     // autocorrelation branch
     float2* i2_ac;              // blocked inverse-along-y of |F|^2
@@ -191,37 +194,56 @@ __device__ __forceinline__ void spec_accumulate(SpecAcc& s, float P, int ky, int
     }
 }
 
-template <int NY>
-__global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
-    constexpr int TPF = NY / 16;
-    constexpr int NT = NY / 2;                  // threads: 8 columns x TPF
-    constexpr int PL = padded_len(NY);
-    extern __shared__ float2 sm[];
-    float2* A = sm;                             // [PL][8]
-    float2* nyq = sm + PL * 8;                  // [PL]   (tile 0 only)
-    float* Bp = reinterpret_cast<float*>(nyq + PL);   // [PL][8] |F|^2 copy (only when both branches run)
-    __shared__ double red[32];
-    __shared__ float s_dcshift;                 // DC of the K-shifted frame (tile 0)
+__device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
+    if (whiten) {
+        const float mag = sqrtf(G.x * G.x + G.y * G.y) + eps;
+        G.x = G.x / mag;
+        G.y = G.y / mag;
+    }
+    return G;
+}
 
-    const int tid = threadIdx.x, c = tid & 7, j = tid >> 3;
+// Every phase of the kernel works on the same ownership: thread (j, c) holds the 16 elements ky = j + m*T of
+// column c, so that all shared-memory and global offsets are "per-thread base + compile-time constant".
+template <int NY, bool SPEC>
+__global__ void __launch_bounds__(NY / 16 * TC) cols_kernel(ColsArgs a) {
+    constexpr int T = NY / 16;
+    constexpr int NT = T * TC;
+    constexpr int PL = padded_len(NY);
+    constexpr bool FAST = (T % 16) == 0;
+    constexpr int MS = FAST ? (T / 16) * 17 : 0;     // padded distance between a thread's consecutive elements
+    extern __shared__ float2 sm[];
+    float2* A = sm;                                   // [PL][TC]
+    float* Bp = reinterpret_cast<float*>(sm + PL * TC);   // [PL][TC] |F|^2 copy (only when both branches run)
+    __shared__ double red[32];
+    __shared__ float s_dcshift;                       // DC of the K-shifted frame (tile 0)
+
+    const int tid = threadIdx.x, c = tid % TC, j = tid / TC;
     const int tile = blockIdx.x, ntiles = gridDim.x;
     const int64_t t = blockIdx.y;
-    const int nx = a.nx, hx = nx / 2;
+    const int nx = a.nx, hx = nx / 2, kx = tile * TC + c;
     const bool tile0 = tile == 0;
     const bool want_ac = a.i2_ac != nullptr, want_pc = a.i2_pc != nullptr;
-    const float2* Hin = a.H + (size_t)t * NY * hx + (size_t)tile * NY * 8;
+    const size_t tile_off = (size_t)t * NY * hx + (size_t)tile * NY * TC;
+    const int gbase = j * TC + c;                     // element m lives at tile_off + gbase + m*T*TC in global memory
+    const int sbase = pad16(j) * TC + c;              // ... and at A[sbase + m*MS*TC] in shared memory (natural order)
+    auto sidx = [&](int m) { return FAST ? sbase + m * MS * TC : pad16(j + m * T) * TC + c; };
+    float2* nyq = a.nyq_scratch + (size_t)t * NY;
 
     float2 x[16];
+    {
+        const float2* Hin = a.H + tile_off + gbase;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = __ldg(Hin + (size_t)(j + m * TPF) * 8 + c);
-    fft_from_regs<NY, -1, 8>(x, j, A + c, a.tw);
+        for (int m = 0; m < 16; ++m) x[m] = __ldg(Hin + m * T * TC);
+    }
+    fft_from_regs<NY, -1, TC>(x, j, A + c, a.tw);
 
-    // ---- tile 0: unpack column 0 (DC + i Nyquist rows) into F[:,0] (kept in A) and F[:,nx/2] (nyq)
+    // ---- tile 0: unpack column 0 (DC + i Nyquist rows) into F[:,0] (kept in A) and F[:,nx/2] (global scratch)
     if (tile0) {
         float2 f0[(NY / 2 + 1 + NT - 1) / NT][2], fn[(NY / 2 + 1 + NT - 1) / NT][2];
         int q = 0;
         for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
-            const float2 C = A[pad16(ky) * 8], Cm = A[pad16((NY - ky) & (NY - 1)) * 8];
+            const float2 C = A[pad16(ky) * TC], Cm = A[pad16((NY - ky) & (NY - 1)) * TC];
             // F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i); the -ky entries are their conjugates
             f0[q][0] = make_float2(0.5f * (C.x + Cm.x), 0.5f * (C.y - Cm.y));
             fn[q][0] = make_float2(0.5f * (C.y + Cm.y), -0.5f * (C.x - Cm.x));
@@ -232,11 +254,11 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
         q = 0;
         for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
             const int km = (NY - ky) & (NY - 1);
-            A[pad16(ky) * 8] = f0[q][0];
-            nyq[pad16(ky)] = fn[q][0];
+            A[pad16(ky) * TC] = f0[q][0];
+            nyq[ky] = fn[q][0];
             if (km != ky) {
-                A[pad16(km) * 8] = f0[q][1];
-                nyq[pad16(km)] = fn[q][1];
+                A[pad16(km) * TC] = f0[q][1];
+                nyq[km] = fn[q][1];
             }
         }
         __syncthreads();
@@ -250,20 +272,31 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
         __syncthreads();
     }
 
-    // ---- pass over the tile: plain outputs ------------------------------------------------------
+    // ---- one pass over the thread's own 16 elements: plain outputs, partial sums, product / |F|^2 into x[]
     SpecAcc sp;
     double acsum = 0.0;
-    const bool need_pass = a.psd_out || a.cplx_out || a.spec_partials || a.conj_out || want_ac;
-    if (need_pass) {
+    float inv_s = 1.f;
+    if (want_pc) {
+        const float2* R = a.R + (size_t)t * a.r_stride + (size_t)tile * NY * TC + gbase;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = __ldg(R + m * T * TC);   // all reference loads in flight before first use
+        if (a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
+    }
+    {
         float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx : nullptr;
         float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx : nullptr;
-        float2* cj = a.conj_out ? a.conj_out + (size_t)t * NY * hx + (size_t)tile * NY * 8 : nullptr;
-        for (int idx = tid; idx < NY * 8; idx += NT) {
-            const int ky = idx >> 3, cc = idx & 7, kx = tile * 8 + cc;
-            const float2 F = A[pad16(ky) * 8 + cc];
+        float2* cj = a.conj_out ? a.conj_out + tile_off + gbase : nullptr;
+        float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
+        const float2* Rn = want_pc ? a.Rnyq + (size_t)t * a.rnyq_stride : nullptr;
+        const bool mirror = kx >= 1;
+        const bool nyq_owner = tile0 && c == 0;
+        const double wgt = mirror ? 2.0 : 1.0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int ky = j + m * T;
+            float2 F = A[sidx(m)];
             const float P = F.x * F.x + F.y * F.y;
             const int rs = (ky + NY / 2) & (NY - 1), rm = (NY / 2 - ky) & (NY - 1);
-            const bool mirror = kx >= 1;
             if (psd) {
                 psd[(size_t)rs * nx + kx + hx] = P * a.psd_scale;
                 if (mirror) psd[(size_t)rm * nx + hx - kx] = P * a.psd_scale;
@@ -272,35 +305,50 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
                 cpl[(size_t)rs * nx + kx + hx] = F;
                 if (mirror) cpl[(size_t)rm * nx + hx - kx] = cconj(F);
             }
-            if (cj) cj[idx] = cconj(F);
-            if (a.spec_partials) spec_accumulate<NY>(sp, P * a.psd_scale, ky, kx, nx, mirror ? 2.0 : 1.0, ky == 0 && kx == 0);
-            if (want_ac) {
-                const float Pa = (a.ac_zero_dc && tile0 && idx == 0) ? 0.f : P;
-                acsum += (mirror ? 2.0 : 1.0) * (double)Pa;
-                if (want_pc) Bp[pad16(ky) * 8 + cc] = Pa;
+            if (cj) cj[m * T * TC] = cconj(F);
+            if (SPEC) spec_accumulate<NY>(sp, P * a.psd_scale, ky, kx, nx, wgt, ky == 0 && kx == 0);
+            float Pa = P, Pn = 0.f;
+            float2 Fn = make_float2(0.f, 0.f);
+            if (nyq_owner) {                         // the Nyquist column kx = nx/2 lands in shifted column 0
+                Fn = nyq[ky];
+                Pn = Fn.x * Fn.x + Fn.y * Fn.y;
+                if (psd) psd[(size_t)rs * nx] = Pn * a.psd_scale;
+                if (cpl) cpl[(size_t)rs * nx] = Fn;
+                if (cjn) cjn[ky] = cconj(Fn);
+                if (SPEC) spec_accumulate<NY>(sp, Pn * a.psd_scale, ky, hx, nx, 1.0, false);
             }
-        }
-        if (tile0) {   // the Nyquist column kx = nx/2 lands in shifted column 0
-            float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
-            for (int ky = tid; ky < NY; ky += NT) {
-                const float2 F = nyq[pad16(ky)];
-                const float P = F.x * F.x + F.y * F.y;
-                const int rs = (ky + NY / 2) & (NY - 1);
-                if (psd) psd[(size_t)rs * nx] = P * a.psd_scale;
-                if (cpl) cpl[(size_t)rs * nx] = F;
-                if (cjn) cjn[ky] = cconj(F);
-                if (a.spec_partials) spec_accumulate<NY>(sp, P * a.psd_scale, ky, hx, nx, 1.0, false);
-                if (want_ac) acsum += (double)P;
+            if (want_ac) {
+                if (a.ac_zero_dc && nyq_owner && ky == 0) Pa = 0.f;
+                acsum += wgt * (double)Pa + (double)Pn;
+                if (want_pc) Bp[sidx(m)] = Pa;
+            }
+            if (want_pc) {
+                if (nyq_owner && ky == 0 && a.fr) {
+                    // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
+                    const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
+                    const double n = (double)nx * (double)NY;
+                    F.x = (float)((double)s_dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
+                }
+                F.x *= inv_s; F.y *= inv_s;
+                float2 G = whiten_if(cmul(F, x[m]), a.whiten, a.eps);
+                if (nyq_owner) {                     // pack: column 0 <- G[:,0] + i G[:,nx/2]
+                    Fn.x *= inv_s; Fn.y *= inv_s;
+                    const float2 Gn = whiten_if(cmul(Fn, __ldg(Rn + ky)), a.whiten, a.eps);
+                    G = make_float2(G.x - Gn.y, G.y + Gn.x);
+                }
+                x[m] = G;
+            } else if (want_ac) {
+                x[m] = make_float2(Pa, Pn);
             }
         }
     }
 
     // ---- block reductions of the scalar partials ------------------------------------------------
-    if (a.spec_partials || want_ac) {
+    if (SPEC || want_ac) {
         double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, acsum};
-        const int warp = tid >> 5, lane = tid & 31, nw = NT / 32;
+        const int warp = tid >> 5, lane = tid & 31, nw = (NT + 31) / 32;
 #pragma unroll
-        for (int i = 0; i < NSP + 1; ++i) {
+        for (int i = SPEC ? 0 : NSP; i < NSP + 1; ++i) {
             double s = warp_sum(v[i]);
             __syncthreads();
             if (lane == 0) red[warp] = s;
@@ -315,81 +363,29 @@ __global__ void __launch_bounds__(NY / 2) cols_kernel(ColsArgs a) {
                 }
             }
         }
-        __syncthreads();
     }
+    if (!want_pc && !want_ac) return;
 
-    // ---- product branch: G = F * R (whitened for phase correlation), inverse along y ---------------
-    if (want_pc) {
-        const float2* R = a.R + (size_t)t * a.r_stride + (size_t)tile * NY * 8;
-        const float2* Rn = a.Rnyq + (size_t)t * a.rnyq_stride;
-        float inv_s = 1.f;
-        if (a.fr) {
-            const double sd = sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]);
-            inv_s = (float)(1.0 / (sd + (double)a.eps));
-        }
-        for (int idx = tid; idx < NY * 8; idx += NT) {
-            const int ky = idx >> 3, cc = idx & 7;
-            float2 F = A[pad16(ky) * 8 + cc];
-            if (tile0 && idx == 0 && a.fr) {
-                // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
-                const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
-                const double n = (double)nx * (double)NY;
-                F.x = (float)((double)s_dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
-            }
-            F.x *= inv_s; F.y *= inv_s;
-            float2 G = cmul(F, __ldg(R + idx));
-            if (a.whiten) {
-                const float mag = sqrtf(G.x * G.x + G.y * G.y) + a.eps;
-                G.x = G.x / mag; G.y = G.y / mag;
-            }
-            A[pad16(ky) * 8 + cc] = G;
-        }
-        if (tile0) {
-            __syncthreads();
-            // pack: column 0 <- G[:,0] + i G[:,nx/2]
-            for (int ky = tid; ky < NY; ky += NT) {
-                float2 F = nyq[pad16(ky)];
-                F.x *= inv_s; F.y *= inv_s;
-                float2 G = cmul(F, __ldg(Rn + ky));
-                if (a.whiten) {
-                    const float mag = sqrtf(G.x * G.x + G.y * G.y) + a.eps;
-                    G.x = G.x / mag; G.y = G.y / mag;
-                }
-                const float2 G0 = A[pad16(ky) * 8];
-                A[pad16(ky) * 8] = make_float2(G0.x - G.y, G0.y + G.x);
-            }
-        }
-        __syncthreads();
+    // ---- inverse along y of the product (or of |F|^2 when there is no product branch) ----------------
+    __syncthreads();                                  // every thread has finished reading F out of A
+    fft_from_regs<NY, +1, TC>(x, j, A + c, a.tw);
+    {
+        float2* o = (want_pc ? a.i2_pc : a.i2_ac) + tile_off + gbase;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
-        __syncthreads();
-        fft_from_regs<NY, +1, 8>(x, j, A + c, a.tw);
-        float2* o = a.i2_pc + (size_t)t * NY * hx + (size_t)tile * NY * 8;
-        for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
-        __syncthreads();
+        for (int m = 0; m < 16; ++m) o[m * T * TC] = A[sidx(m)];
     }
-
-    // ---- autocorrelation branch: G = |F|^2, inverse along y ----------------------------------------
-    if (want_ac) {
-        for (int idx = tid; idx < NY * 8; idx += NT) {
-            const int ky = idx >> 3, cc = idx & 7;
-            float P;
-            if (want_pc) P = Bp[pad16(ky) * 8 + cc];
-            else {
-                const float2 F = A[pad16(ky) * 8 + cc];
-                P = (a.ac_zero_dc && tile0 && idx == 0) ? 0.f : F.x * F.x + F.y * F.y;
-            }
+    if (want_pc && want_ac) {                         // second inverse: |F|^2 kept in Bp
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
             float Pn = 0.f;
-            if (tile0 && cc == 0) { const float2 Fn = nyq[pad16(ky)]; Pn = Fn.x * Fn.x + Fn.y * Fn.y; }
-            A[pad16(ky) * 8 + cc] = make_float2(P, Pn);
+            if (tile0 && c == 0) { const float2 Fn = nyq[j + m * T]; Pn = Fn.x * Fn.x + Fn.y * Fn.y; }
+            x[m] = make_float2(Bp[sidx(m)], Pn);
         }
         __syncthreads();
+        fft_from_regs<NY, +1, TC>(x, j, A + c, a.tw);
+        float2* o = a.i2_ac + tile_off + gbase;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) x[m] = A[pad16(j + m * TPF) * 8 + c];
-        __syncthreads();
-        fft_from_regs<NY, +1, 8>(x, j, A + c, a.tw);
-        float2* o = a.i2_ac + (size_t)t * NY * hx + (size_t)tile * NY * 8;
-        for (int idx = tid; idx < NY * 8; idx += NT) o[idx] = A[pad16(idx >> 3) * 8 + (idx & 7)];
+        for (int m = 0; m < 16; ++m) o[m * T * TC] = A[sidx(m)];
     }
 }
 
@@ -448,35 +444,45 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
     const float2* Ia = a.Ia + (size_t)t * NY * HX;
     const float2* Ib = a.pair_maps ? a.Ib + (size_t)t * NY * HX : Ia;
 
-    if (tid == 0) {
+    // issue the gather loads first; the scale they are multiplied with is resolved meanwhile
+    float2 ga[8], gb[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = j + m * TPF;
+        const size_t off = ((size_t)(k / TC) * NY) * TC + (k % TC);
+        ga[m] = __ldg(Ia + off + (size_t)ya * TC);
+        gb[m] = __ldg(Ib + off + (size_t)yb * TC);
+    }
+    if (warp == 0) {
         double s = a.scaleA;
         if (a.normA) {
-            double tot = 0.0;
-            for (int i = 0; i < a.n_normA; ++i) tot += a.normA[(size_t)t * a.n_normA + i];
-            s = tot > 0.0 ? a.norm_mult / tot : a.scaleA;
+            // fixed-order reduction of the per-tile partials: lane-strided chunks, then a shuffle tree
+            double part = 0.0;
+            for (int i = lane; i < a.n_normA; i += 32) part += a.normA[(size_t)t * a.n_normA + i];
+            part = warp_sum(part);
+            s = part > 0.0 ? a.norm_mult / part : a.scaleA;
         }
-        s_scale = (float)s;
+        if (lane == 0) s_scale = (float)s;
     }
     __syncthreads();
     // The two rows share one complex transform, so they are brought to their final scale BEFORE it: a raw
     // autocorrelation (~1e13) packed next to a raw phase correlation (~1e6) would bury the latter in rounding.
     const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
 
-    // gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
+    // each thread holds Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
     float2* z = sm + f * FS;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const int k = j + m * TPF;
-        const size_t off = ((size_t)(k >> 3) * NY) * 8 + (k & 7);
-        float2 ga = __ldg(Ia + off + (size_t)ya * 8), gb = __ldg(Ib + off + (size_t)yb * 8);
-        ga.x *= sA; ga.y *= sA; gb.x *= sB; gb.y *= sB;
+        float2 g1 = ga[m], g2 = gb[m];
+        g1.x *= sA; g1.y *= sA; g2.x *= sB; g2.y *= sB;
         if (k == 0) {
             // packed slot: (DC, Nyquist), both real
-            z[pad16(0)] = make_float2(ga.x, gb.x);
-            z[pad16(HX)] = make_float2(ga.y, gb.y);
+            z[pad16(0)] = make_float2(g1.x, g2.x);
+            z[pad16(HX)] = make_float2(g1.y, g2.y);
         } else {
-            z[pad16(k)] = make_float2(ga.x - gb.y, ga.y + gb.x);
-            z[pad16(NX - k)] = make_float2(ga.x + gb.y, gb.x - ga.y);
+            z[pad16(k)] = make_float2(g1.x - g2.y, g1.y + g2.x);
+            z[pad16(NX - k)] = make_float2(g1.x + g2.y, g2.x - g1.y);
         }
     }
     __syncthreads();
@@ -491,21 +497,36 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
     float* oA = a.outA ? a.outA + (size_t)t * NY * NX : nullptr;
     float* oB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX : nullptr) : oA;
     ArgBest bA = {-INFINITY, 0xffffffffu}, bB = {-INFINITY, 0xffffffffu};
-    for (int idx = tid; idx < FPC * NX; idx += 512) {
-        const int ff = idx / NX, xx = idx % NX;
-        const float2 v = sm[ff * FS + pad16(xx)];
+    auto emit = [&](int ff, int xx, float2 v) {
         const int ra_ = a.pair_maps ? y0 + ff : y0 + 2 * ff;
         const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
         const unsigned cs = (unsigned)((xx + HX) & (NX - 1));
-        const unsigned rsa = (unsigned)((ra_ + NY / 2) & (NY - 1)), rsb = (unsigned)((rb_ + NY / 2) & (NY - 1));
+        const unsigned ia = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX + cs;
+        const unsigned ib = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX + cs;
         float va = v.x, vb = v.y;
         if (a.kindA) va = fabsf(va);
         if (kindB) vb = fabsf(vb);
-        if (oA) oA[(size_t)rsa * NX + cs] = va;
-        if (oB) oB[(size_t)rsb * NX + cs] = vb;
-        best_update(bA, va, rsa * (unsigned)NX + cs);
-        if (a.pair_maps) best_update(bB, vb, rsb * (unsigned)NX + cs);
-        else best_update(bA, vb, rsb * (unsigned)NX + cs);
+        if (oA) oA[ia] = va;
+        if (oB) oB[ib] = vb;
+        best_update(bA, va, ia);
+        if (a.pair_maps) best_update(bB, vb, ib);
+        else best_update(bA, vb, ib);
+    };
+    if (NX >= 512) {
+        // idx = tid + i*512: transform ff = (i*512)/NX and column xx = tid + (i*512)%NX are compile-time + tid
+        constexpr int IT = FPC * NX / 512;
+        const int ptid = pad16(tid);
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ff = (i * 512) / NX, xo = (i * 512) % NX;
+            emit(ff, tid + xo, sm[ff * FS + ptid + (xo / 16) * 17]);
+        }
+    } else {
+        for (int idx = tid; idx < FPC * NX; idx += 512) {
+            const int ff = idx / NX, xx = idx % NX;
+            emit(ff, xx, sm[ff * FS + pad16(xx)]);
+        }
     }
     // argmax partials (first occurrence in row-major order of the shifted map wins ties)
     if (a.bestA || (a.pair_maps && a.bestB)) {
@@ -796,14 +817,25 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
 }
 
 template <int NY>
-int launch_cols(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
+int launch_cols(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
     constexpr int PL = padded_len(NY);
     const bool both = a.i2_ac && a.i2_pc;
-    const size_t smem = (size_t)PL * 8 * sizeof(float2) + (size_t)PL * sizeof(float2) + (both ? (size_t)PL * 8 * sizeof(float) : 0);
-    static size_t attr = 0;
-    if (attr < smem) { B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    const size_t smem = (size_t)PL * TC * sizeof(float2) + (both ? (size_t)PL * TC * sizeof(float) : 0);
+    static size_t attr[2] = {0, 0};
+    const int spec = a.spec_partials ? 1 : 0;
+    if (attr[spec] < smem) {
+        if (spec) B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr[spec] = smem;
+    }
+    void* p = nullptr;
+    int rc = b4d_scratch(ctx, SCR_NYQ, sizeof(float2) * (size_t)NY * (size_t)T, &p);
+    if (rc) return rc;
+    a.nyq_scratch = static_cast<float2*>(p);
     ProfScope ps(ctx, KC_COLS);
-    cols_kernel<NY><<<dim3(a.nx / 16, (unsigned)T), NY / 2, smem, ctx->stream>>>(a);
+    const dim3 grid(a.nx / 2 / TC, (unsigned)T);
+    if (spec) cols_kernel<NY, true><<<grid, NY / 16 * TC, smem, ctx->stream>>>(a);
+    else cols_kernel<NY, false><<<grid, NY / 16 * TC, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
@@ -870,7 +902,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->H = static_cast<float2*>(p);
     if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * T, &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
     if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * T, &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
-    const int ntiles = nx / 16, nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
+    const int ntiles = nx / 2 / TC, nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
     size_t small = 0;
     auto take = [&](size_t bytes) { size_t o = small; small += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
@@ -1014,7 +1046,7 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
         if ((rc = run_cols(ctx, c, tc, ny))) return rc;
         if (spectral) {
             double* tab = spectral + t0 * B4D_SP_NCOLS;
-            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, nx / 16, tab, tc);
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, nx / 2 / TC, tab, tc);
             B4D_LAUNCH_CHECK(ctx);
             if (want_f95) {
                 const int n = ny, nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
@@ -1057,7 +1089,7 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
     RowsInvArgs r;
     memset(&r, 0, sizeof(r));
     r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = out_ac; r.kindA = 0;
-    r.normA = use_norm ? w.acp : nullptr; r.n_normA = nx / 16; r.norm_mult = norm_mult;
+    r.normA = use_norm ? w.acp : nullptr; r.n_normA = nx / 2 / TC; r.norm_mult = norm_mult;
     r.scaleA = 1.0 / ((double)nx * (double)ny);
     r.bestA = grain_out ? w.bestA : nullptr;
     if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
@@ -1300,12 +1332,12 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         int nblk;
         if (want_ac && want_pc) {
             r.Ia = w.I2a; r.Ib = w.I2b; r.pair_maps = 1;
-            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 16; r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
+            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 2 / TC; r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
             r.bestA = grain_out ? w.bestA : nullptr;
             r.outB = mag; r.kindB = 1; r.scaleB = 1.0 / ((double)nx * ny); r.bestB = w.bestB;
             nblk = rows_inv_blocks(nx, ny, 1);
         } else if (want_ac) {
-            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 16; r.norm_mult = 1.0;
+            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 2 / TC; r.norm_mult = 1.0;
             r.scaleA = 1.0 / ((double)nx * ny); r.bestA = grain_out ? w.bestA : nullptr;
             nblk = rows_inv_blocks(nx, ny, 0);
         } else {
