@@ -249,4 +249,189 @@ __device__ __forceinline__ void fft_from_regs(float2* x, int j, float2* __restri
     }
 }
 
+
+// ================================================================================================
+// Register-to-register transform (v2 core).
+//
+// Input : x[m] = data[j + m*T], T = N/16 (thread j of the transform, natural strided ownership).
+// Output: x[s] = DFT(data)[j + s*T]  -- the SAME ownership, so epilogues and the next transform of a chain work
+//         straight from registers: only the two inner exchanges go through shared memory (the last stage of a
+//         Stockham pass writes element v + q*LS with LS*R = N, i.e. thread-local slots).
+// Twiddles: per stage the thread loads the base powers w^1, w^2, w^4 (, w^8) of its own k from a small table
+//         (two LDG.128 issued BEFORE the exchange barrier, while x[] is dead) and forms the other powers by
+//         at most two complex multiplications (error <= 7 ulp).
+// Table layout (float2): [0, 64)            stage 2: k in [0,16)   -> (w1, w2, w4, w8), base 16*R2
+//                        [64, 64 + 4*LS3)   stage 3: k in [0,LS3)  -> (w1, w2, w4, 0),  base N
+// Synchronisation: a __syncthreads() is issued on entry (z may still be read by a previous user); on return
+//         other threads may still be reading z, so the caller synchronises before writing z itself.
+// ================================================================================================
+template <int N>
+__host__ __device__ constexpr int twiddle_base_count() {
+    return 64 + (Plan<N>::R3 > 1 ? 4 * Plan<N>::R1 * Plan<N>::R2 : 0);
+}
+
+template <int DIR>
+__device__ __forceinline__ float2 tw_dir(float2 w) { return DIR > 0 ? make_float2(w.x, -w.y) : w; }
+
+// x[m] *= w^m for m = 1..R-1 given the base powers (already conjugated for DIR > 0)
+template <int R>
+__device__ __forceinline__ void apply_twiddle_powers(float2* x, float2 w1, float2 w2, float2 w4, float2 w8) {
+    x[1] = cmul(x[1], w1);
+    if (R > 2) {
+        const float2 w3 = cmul(w1, w2);
+        x[2] = cmul(x[2], w2);
+        x[3] = cmul(x[3], w3);
+        if (R > 4) {
+            x[4] = cmul(x[4], w4);
+            x[5] = cmul(x[5], cmul(w4, w1));
+            x[6] = cmul(x[6], cmul(w4, w2));
+            const float2 w7 = cmul(w4, w3);
+            x[7] = cmul(x[7], w7);
+            if (R > 8) {
+                x[8] = cmul(x[8], w8);
+                x[9] = cmul(x[9], cmul(w8, w1));
+                x[10] = cmul(x[10], cmul(w8, w2));
+                x[11] = cmul(x[11], cmul(w8, w3));
+                x[12] = cmul(x[12], cmul(w8, w4));
+                x[13] = cmul(x[13], cmul(w8, cmul(w4, w1)));
+                x[14] = cmul(x[14], cmul(w8, cmul(w4, w2)));
+                x[15] = cmul(x[15], cmul(w8, w7));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void ldg_tw4(const float2* p, float2& a, float2& b, float2& c, float2& d) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    a = make_float2(u.x, u.y); b = make_float2(u.z, u.w); c = make_float2(v.x, v.y); d = make_float2(v.z, v.w);
+}
+
+template <int N, int DIR, int BATCH>
+__device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ twb) {
+    using P = Plan<N>;
+    constexpr int T = N / 16;
+    constexpr bool FAST = (T % 16) == 0;
+    constexpr int R2 = P::R2, NB2 = 16 / R2;
+    constexpr bool HAS3 = P::R3 > 1;
+    constexpr int R3 = HAS3 ? P::R3 : 2, NB3 = 16 / R3, LS3 = 16 * R2;
+    const int pj = pad16(j);
+
+    // ---- stage 1: radix 16, LS = 1 -> element 16 j + q at padded index 17 j + q
+    bfly16<DIR>(x);
+    __syncthreads();
+    {
+        float2* w = z + 17 * j * BATCH;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) w[q * BATCH] = x[q];
+    }
+    // stage-2 base twiddles of every block of this thread, in flight across the barrier
+    float2 b1[NB2], b2[NB2], b4[NB2], b8[NB2];
+#pragma unroll
+    for (int b = 0; b < NB2; ++b) {
+        const int k = FAST ? (j & 15) : ((j + b * T) & 15);
+        if (FAST && b > 0) { b1[b] = b1[0]; b2[b] = b2[0]; b4[b] = b4[0]; b8[b] = b8[0]; }
+        else ldg_tw4(twb + 4 * k, b1[b], b2[b], b4[b], b8[b]);
+    }
+    __syncthreads();
+
+    // ---- stage 2: radix R2, LS = 16
+    {
+        if (FAST) {
+            const float2* r = z + pj * BATCH;
+#pragma unroll
+            for (int b = 0; b < NB2; ++b)
+#pragma unroll
+                for (int m = 0; m < R2; ++m) x[b * R2 + m] = r[((b * T + m * (N / R2)) / 16 * 17) * BATCH];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB2; ++b)
+#pragma unroll
+                for (int m = 0; m < R2; ++m) x[b * R2 + m] = z[pad16(j + b * T + m * (N / R2)) * BATCH];
+        }
+#pragma unroll
+        for (int b = 0; b < NB2; ++b) {
+            apply_twiddle_powers<R2>(x + b * R2, tw_dir<DIR>(b1[b]), tw_dir<DIR>(b2[b]), tw_dir<DIR>(b4[b]), tw_dir<DIR>(b8[b]));
+            bfly<R2, DIR>(x + b * R2);
+        }
+    }
+    if constexpr (!HAS3) {
+        // last stage: block b, output q is element j + T (b + NB2 q)
+        float2 y[16];
+#pragma unroll
+        for (int b = 0; b < NB2; ++b)
+#pragma unroll
+            for (int q = 0; q < R2; ++q) y[b + NB2 * q] = x[b * R2 + q];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) x[s] = y[s];
+    } else {
+        __syncthreads();
+        if (FAST) {
+            const int k = j & 15;
+            float2* w = z + (((j - k) / 16) * 17 * R2 + k) * BATCH;
+#pragma unroll
+            for (int b = 0; b < NB2; ++b)
+#pragma unroll
+                for (int q = 0; q < R2; ++q) w[((b * T / 16) * 17 * R2 + 17 * q) * BATCH] = x[b * R2 + q];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB2; ++b) {
+                const int v = j + b * T, kk = v & 15;
+#pragma unroll
+                for (int q = 0; q < R2; ++q) z[pad16((v - kk) * R2 + kk + q * 16) * BATCH] = x[b * R2 + q];
+            }
+        }
+        float2 c1[NB3], c2[NB3], c4[NB3], c8[NB3];
+#pragma unroll
+        for (int b = 0; b < NB3; ++b) ldg_tw4(twb + 64 + 4 * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
+        __syncthreads();
+
+        // ---- stage 3: radix R3, LS = 16 R2 = N / R3: k = v = j + b T
+        if (FAST) {
+            const float2* r = z + pj * BATCH;
+#pragma unroll
+            for (int b = 0; b < NB3; ++b)
+#pragma unroll
+                for (int m = 0; m < R3; ++m) x[b * R3 + m] = r[((b * T + m * (N / R3)) / 16 * 17) * BATCH];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB3; ++b)
+#pragma unroll
+                for (int m = 0; m < R3; ++m) x[b * R3 + m] = z[pad16(j + b * T + m * (N / R3)) * BATCH];
+        }
+#pragma unroll
+        for (int b = 0; b < NB3; ++b) {
+            apply_twiddle_powers<R3>(x + b * R3, tw_dir<DIR>(c1[b]), tw_dir<DIR>(c2[b]), tw_dir<DIR>(c4[b]), tw_dir<DIR>(c8[b]));
+            bfly<R3, DIR>(x + b * R3);
+        }
+        // block b, output q is element v + q LS3 = j + T (b + NB3 q)
+        float2 y[16];
+#pragma unroll
+        for (int b = 0; b < NB3; ++b)
+#pragma unroll
+            for (int q = 0; q < R3; ++q) y[b + NB3 * q] = x[b * R3 + q];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) x[s] = y[s];
+        (void)LS3;
+    }
+}
+
+// v2 core + write-back: on return the transform sits in shared memory in natural order (element i at
+// z[pad16(i) * BATCH]) and a __syncthreads() has been issued.
+template <int N, int DIR, int BATCH>
+__device__ __forceinline__ void fft_regs_to_smem(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ twb) {
+    constexpr int T = N / 16;
+    fft_regs<N, DIR, BATCH>(x, j, z, twb);
+    __syncthreads();
+    if ((T % 16) == 0) {
+        float2* w = z + pad16(j) * BATCH;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) w[(s * T / 16 * 17) * BATCH] = x[s];
+    } else {
+#pragma unroll
+        for (int s = 0; s < 16; ++s) z[pad16(j + s * T) * BATCH] = x[s];
+    }
+    __syncthreads();
+}
+
 }  // namespace b4dfft

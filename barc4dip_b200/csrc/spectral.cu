@@ -30,6 +30,7 @@ int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_fram
 
 struct FftPlanCache {
     float2* tw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 128, 256, 512, 1024, 2048
+    float2* twb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power tables of the v2 core
     // tracker reference: conj spectrum of the embedded z-scored template
     float2* ref = nullptr;       // blocked (nx/2/8, ny, 8)
     float2* ref_nyq = nullptr;   // (ny)
@@ -79,10 +80,48 @@ int get_twiddles(b4d_ctx* ctx, int n, const float2** out) {
     return B4D_OK;
 }
 
+// base powers (w, w^2, w^4, w^8) per stage and k, see fft.cuh (v2 core)
+template <int N>
+void fill_twiddle_bases(std::vector<float2>& h) {
+    using P = Plan<N>;
+    h.assign(twiddle_base_count<N>(), make_float2(0.f, 0.f));
+    auto put = [&](size_t at, int k, double base, int npow) {
+        for (int p = 0; p < npow; ++p) {
+            const double a = -2.0 * 3.14159265358979323846 * (double)(1 << p) * (double)k / base;
+            h[at + p] = make_float2((float)cos(a), (float)sin(a));
+        }
+    };
+    for (int k = 0; k < 16; ++k) put(4 * (size_t)k, k, 16.0 * P::R2, 4);
+    if (P::R3 > 1)
+        for (int k = 0; k < 16 * P::R2; ++k) put(64 + 4 * (size_t)k, k, (double)N, 3);
+}
+
+int get_twiddle_bases(b4d_ctx* ctx, int n, const float2** out) {
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    const int slot = log2i(n) - 7;
+    if (!ctx->fft->twb[slot]) {
+        std::vector<float2> h;
+        switch (n) {
+            case 128: fill_twiddle_bases<128>(h); break;
+            case 256: fill_twiddle_bases<256>(h); break;
+            case 512: fill_twiddle_bases<512>(h); break;
+            case 1024: fill_twiddle_bases<1024>(h); break;
+            default: fill_twiddle_bases<2048>(h); break;
+        }
+        B4D_CUDA(ctx, cudaMalloc(&ctx->fft->twb[slot], h.size() * sizeof(float2)));
+        B4D_CUDA(ctx, cudaMemcpy(ctx->fft->twb[slot], h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    *out = ctx->fft->twb[slot];
+    return B4D_OK;
+}
+
 // =================================================================================================
 // K1: rows forward
 // =================================================================================================
-constexpr int TC = 8;     // columns per K2 CTA = width of a tile of the blocked intermediates [kx/TC][y][kx%TC]
+constexpr int TC = 8;     // width of a tile of the blocked intermediates [kx/TC][y][kx%TC]
+#ifndef B4D_COLS_CW_2048
+#define B4D_COLS_CW_2048 4   // columns per K2 CTA at ny = 2048 (4: two CTAs per SM; 8: one)
+#endif
 
 struct RowsFwdArgs {
     const float* stack;
@@ -149,7 +188,6 @@ struct ColsArgs {
     const float2* H;            // blocked input, per frame ny*nx/2
     const float2* tw;
     const float* pilot;         // nullable: DC += nx*ny*K
-    float2* nyq_scratch;        // (T, ny) global scratch for the Nyquist column (tile 0 only)
     int nx;
     int zero_dc;                // clear F[0,0] (mean removal) for every output
     int ac_zero_dc;             // clear it for the autocorrelation branch only (fused pipeline)
@@ -196,78 +234,55 @@ __device__ __forceinline__ void spec_accumulate(SpecAcc& s, float P, int ky, int
 
 __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
     if (whiten) {
-        const float mag = sqrtf(G.x * G.x + G.y * G.y) + eps;
-        G.x = G.x / mag;
-        G.y = G.y / mag;
+        const float inv = __frcp_rn(sqrtf(G.x * G.x + G.y * G.y) + eps);
+        G.x *= inv;
+        G.y *= inv;
     }
     return G;
 }
 
-// Every phase of the kernel works on the same ownership: thread (j, c) holds the 16 elements ky = j + m*T of
-// column c, so that all shared-memory and global offsets are "per-thread base + compile-time constant".
-template <int NY, bool SPEC>
-__global__ void __launch_bounds__(NY / 16 * TC) cols_kernel(ColsArgs a) {
+// Thread (j, c) owns the 16 elements ky = j + s*T (T = NY/16) of column c of the CTA's CW columns, in every phase:
+// the loads, the forward transform (register to register, fft.cuh v2 core), the epilogues, the inverse transforms
+// and the stores. Shared memory carries only the two inner exchanges of each transform, the |F|^2 copy that
+// feeds the second inverse transform, and (tile 0) the mirror exchange that unpacks the DC / Nyquist column.
+// CW (4 or 8) columns per CTA out of a layout tile of TC = 8: CW = 4 halves the footprint so that two CTAs
+// share an SM and one's loads overlap the other's butterflies.
+template <int NY, int CW, bool SPEC, bool AC, bool PC>
+__global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a) {
     constexpr int T = NY / 16;
-    constexpr int NT = T * TC;
+    constexpr int NT = T * CW;
     constexpr int PL = padded_len(NY);
-    constexpr bool FAST = (T % 16) == 0;
-    constexpr int MS = FAST ? (T / 16) * 17 : 0;     // padded distance between a thread's consecutive elements
+    constexpr int GS = T * TC;                        // global distance (float2) between a thread's consecutive elements
     extern __shared__ float2 sm[];
-    float2* A = sm;                                   // [PL][TC]
-    float* Bp = reinterpret_cast<float*>(sm + PL * TC);   // [PL][TC] |F|^2 copy (only when both branches run)
+    float2* A = sm;                                   // [PL][CW] exchange buffer
+    float* Bp = reinterpret_cast<float*>(sm + PL * CW);   // [NY][CW] |F|^2 (AC && PC)
+    float* Pns = Bp + NY * CW;                        // [NY] |F_nyquist|^2 (AC && PC, tile 0)
     __shared__ double red[32];
-    __shared__ float s_dcshift;                       // DC of the K-shifted frame (tile 0)
 
-    const int tid = threadIdx.x, c = tid % TC, j = tid / TC;
+    const int tid = threadIdx.x, c = tid % CW, j = tid / CW;
     const int tile = blockIdx.x, ntiles = gridDim.x;
     const int64_t t = blockIdx.y;
-    const int nx = a.nx, hx = nx / 2, kx = tile * TC + c;
+    const int nx = a.nx, hx = nx / 2, kx = tile * CW + c;
     const bool tile0 = tile == 0;
-    const bool want_ac = a.i2_ac != nullptr, want_pc = a.i2_pc != nullptr;
-    const size_t tile_off = (size_t)t * NY * hx + (size_t)tile * NY * TC;
-    const int gbase = j * TC + c;                     // element m lives at tile_off + gbase + m*T*TC in global memory
-    const int sbase = pad16(j) * TC + c;              // ... and at A[sbase + m*MS*TC] in shared memory (natural order)
-    auto sidx = [&](int m) { return FAST ? sbase + m * MS * TC : pad16(j + m * T) * TC + c; };
-    float2* nyq = a.nyq_scratch + (size_t)t * NY;
+    const bool nyq_owner = tile0 && c == 0;
+    // element s of this thread lives at g0 + s*GS inside a frame's blocked half spectrum
+    const size_t g0 = (size_t)t * NY * hx + (size_t)(kx / TC) * NY * TC + (size_t)j * TC + (kx % TC);
 
     float2 x[16];
     {
-        const float2* Hin = a.H + tile_off + gbase;
+        const float2* Hin = a.H + g0;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) x[m] = __ldg(Hin + m * T * TC);
+        for (int s = 0; s < 16; ++s) x[s] = __ldcs(Hin + s * GS);
     }
-    fft_from_regs<NY, -1, TC>(x, j, A + c, a.tw);
+    fft_regs<NY, -1, CW>(x, j, A + c, a.tw);
 
-    // ---- tile 0: unpack column 0 (DC + i Nyquist rows) into F[:,0] (kept in A) and F[:,nx/2] (global scratch)
+    // ---- tile 0: column 0 carries C = F[:,0] + i F[:,nx/2]; publish it so that its owners can read C[-ky]
+    float2* A0 = A;                                   // natural order, [NY]
     if (tile0) {
-        float2 f0[(NY / 2 + 1 + NT - 1) / NT][2], fn[(NY / 2 + 1 + NT - 1) / NT][2];
-        int q = 0;
-        for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
-            const float2 C = A[pad16(ky) * TC], Cm = A[pad16((NY - ky) & (NY - 1)) * TC];
-            // F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i); the -ky entries are their conjugates
-            f0[q][0] = make_float2(0.5f * (C.x + Cm.x), 0.5f * (C.y - Cm.y));
-            fn[q][0] = make_float2(0.5f * (C.y + Cm.y), -0.5f * (C.x - Cm.x));
-            f0[q][1] = cconj(f0[q][0]);
-            fn[q][1] = cconj(fn[q][0]);
-        }
         __syncthreads();
-        q = 0;
-        for (int ky = tid; ky <= NY / 2; ky += NT, ++q) {
-            const int km = (NY - ky) & (NY - 1);
-            A[pad16(ky) * TC] = f0[q][0];
-            nyq[ky] = fn[q][0];
-            if (km != ky) {
-                A[pad16(km) * TC] = f0[q][1];
-                nyq[km] = fn[q][1];
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float2 dc = A[0];
-            s_dcshift = dc.x;
-            if (a.pilot) dc.x += (float)((double)nx * (double)NY * (double)__ldg(a.pilot + t));
-            if (a.zero_dc) dc = make_float2(0.f, 0.f);
-            A[0] = dc;
+        if (c == 0) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) A0[j + s * T] = x[s];
         }
         __syncthreads();
     }
@@ -276,116 +291,123 @@ __global__ void __launch_bounds__(NY / 16 * TC) cols_kernel(ColsArgs a) {
     SpecAcc sp;
     double acsum = 0.0;
     float inv_s = 1.f;
-    if (want_pc) {
-        const float2* R = a.R + (size_t)t * a.r_stride + (size_t)tile * NY * TC + gbase;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) x[m] = __ldg(R + m * T * TC);   // all reference loads in flight before first use
-        if (a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
-    }
+    if (PC && a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
     {
         float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx : nullptr;
         float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx : nullptr;
-        float2* cj = a.conj_out ? a.conj_out + tile_off + gbase : nullptr;
+        float2* cj = a.conj_out ? a.conj_out + g0 : nullptr;
         float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
-        const float2* Rn = want_pc ? a.Rnyq + (size_t)t * a.rnyq_stride : nullptr;
+        const float2* R = PC ? a.R + (size_t)t * a.r_stride + (g0 - (size_t)t * NY * hx) : nullptr;
+        const float2* Rn = PC ? a.Rnyq + (size_t)t * a.rnyq_stride : nullptr;
         const bool mirror = kx >= 1;
-        const bool nyq_owner = tile0 && c == 0;
         const double wgt = mirror ? 2.0 : 1.0;
+        const float ps = a.psd_scale;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int ky = j + m * T;
-            float2 F = A[sidx(m)];
+        for (int s = 0; s < 16; ++s) {
+            const int ky = j + s * T;
+            float2 F = x[s];
+            float2 Rv = make_float2(0.f, 0.f);
+            if (PC) Rv = __ldg(R + s * GS);
+            float2 Fn = make_float2(0.f, 0.f);
+            float dcshift = 0.f;
+            if (nyq_owner) {
+                // F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i) with Cm = C[-ky]
+                const float2 Cm = A0[(NY - ky) & (NY - 1)];
+                Fn = make_float2(0.5f * (F.y + Cm.y), -0.5f * (F.x - Cm.x));
+                F = make_float2(0.5f * (F.x + Cm.x), 0.5f * (F.y - Cm.y));
+                if (ky == 0) {
+                    dcshift = F.x;
+                    if (a.pilot) F.x += (float)((double)nx * (double)NY * (double)__ldg(a.pilot + t));
+                    if (a.zero_dc) F = make_float2(0.f, 0.f);
+                }
+            }
             const float P = F.x * F.x + F.y * F.y;
             const int rs = (ky + NY / 2) & (NY - 1), rm = (NY / 2 - ky) & (NY - 1);
             if (psd) {
-                psd[(size_t)rs * nx + kx + hx] = P * a.psd_scale;
-                if (mirror) psd[(size_t)rm * nx + hx - kx] = P * a.psd_scale;
+                __stcs(psd + (size_t)rs * nx + kx + hx, P * ps);
+                if (mirror) __stcs(psd + (size_t)rm * nx + hx - kx, P * ps);
             }
             if (cpl) {
-                cpl[(size_t)rs * nx + kx + hx] = F;
-                if (mirror) cpl[(size_t)rm * nx + hx - kx] = cconj(F);
+                __stcs(cpl + (size_t)rs * nx + kx + hx, F);
+                if (mirror) __stcs(cpl + (size_t)rm * nx + hx - kx, cconj(F));
             }
-            if (cj) cj[m * T * TC] = cconj(F);
-            if (SPEC) spec_accumulate<NY>(sp, P * a.psd_scale, ky, kx, nx, wgt, ky == 0 && kx == 0);
+            if (cj) cj[s * GS] = cconj(F);
+            if (SPEC) spec_accumulate<NY>(sp, P * ps, ky, kx, nx, wgt, ky == 0 && kx == 0);
             float Pa = P, Pn = 0.f;
-            float2 Fn = make_float2(0.f, 0.f);
-            if (nyq_owner) {                         // the Nyquist column kx = nx/2 lands in shifted column 0
-                Fn = nyq[ky];
+            if (nyq_owner) {                          // the Nyquist column kx = nx/2 lands in shifted column 0
                 Pn = Fn.x * Fn.x + Fn.y * Fn.y;
-                if (psd) psd[(size_t)rs * nx] = Pn * a.psd_scale;
-                if (cpl) cpl[(size_t)rs * nx] = Fn;
+                if (psd) __stcs(psd + (size_t)rs * nx, Pn * ps);
+                if (cpl) __stcs(cpl + (size_t)rs * nx, Fn);
                 if (cjn) cjn[ky] = cconj(Fn);
-                if (SPEC) spec_accumulate<NY>(sp, Pn * a.psd_scale, ky, hx, nx, 1.0, false);
+                if (SPEC) spec_accumulate<NY>(sp, Pn * ps, ky, hx, nx, 1.0, false);
             }
-            if (want_ac) {
+            if (AC) {
                 if (a.ac_zero_dc && nyq_owner && ky == 0) Pa = 0.f;
                 acsum += wgt * (double)Pa + (double)Pn;
-                if (want_pc) Bp[sidx(m)] = Pa;
+                if (PC) {
+                    Bp[tid + s * NT] = Pa;
+                    if (nyq_owner) Pns[ky] = Pn;
+                }
             }
-            if (want_pc) {
+            if (PC) {
                 if (nyq_owner && ky == 0 && a.fr) {
                     // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
                     const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
                     const double n = (double)nx * (double)NY;
-                    F.x = (float)((double)s_dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
+                    F.x = (float)((double)dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
                 }
                 F.x *= inv_s; F.y *= inv_s;
-                float2 G = whiten_if(cmul(F, x[m]), a.whiten, a.eps);
-                if (nyq_owner) {                     // pack: column 0 <- G[:,0] + i G[:,nx/2]
+                float2 G = whiten_if(cmul(F, Rv), a.whiten, a.eps);
+                if (nyq_owner) {                      // pack: column 0 <- G[:,0] + i G[:,nx/2]
                     Fn.x *= inv_s; Fn.y *= inv_s;
                     const float2 Gn = whiten_if(cmul(Fn, __ldg(Rn + ky)), a.whiten, a.eps);
                     G = make_float2(G.x - Gn.y, G.y + Gn.x);
                 }
-                x[m] = G;
-            } else if (want_ac) {
-                x[m] = make_float2(Pa, Pn);
+                x[s] = G;
+            } else if (AC) {
+                x[s] = make_float2(Pa, Pn);
             }
         }
     }
 
     // ---- block reductions of the scalar partials ------------------------------------------------
-    if (SPEC || want_ac) {
+    if (SPEC || AC) {
         double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, acsum};
         const int warp = tid >> 5, lane = tid & 31, nw = (NT + 31) / 32;
 #pragma unroll
         for (int i = SPEC ? 0 : NSP; i < NSP + 1; ++i) {
-            double s = warp_sum(v[i]);
+            if (i == NSP && !AC) break;
+            double r = warp_sum(v[i]);
             __syncthreads();
-            if (lane == 0) red[warp] = s;
+            if (lane == 0) red[warp] = r;
             __syncthreads();
             if (tid == 0) {
                 double tot = 0.0;
                 for (int w = 0; w < nw; ++w) tot += red[w];
                 if (i < NSP) {
                     if (a.spec_partials) a.spec_partials[((size_t)t * ntiles + tile) * NSP + i] = tot;
-                } else if (want_ac) {
+                } else {
                     a.ac_partials[(size_t)t * ntiles + tile] = tot;
                 }
             }
         }
     }
-    if (!want_pc && !want_ac) return;
+    if (!PC && !AC) return;
 
     // ---- inverse along y of the product (or of |F|^2 when there is no product branch) ----------------
-    __syncthreads();                                  // every thread has finished reading F out of A
-    fft_from_regs<NY, +1, TC>(x, j, A + c, a.tw);
+    fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
     {
-        float2* o = (want_pc ? a.i2_pc : a.i2_ac) + tile_off + gbase;
+        float2* o = (PC ? a.i2_pc : a.i2_ac) + g0;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) o[m * T * TC] = A[sidx(m)];
+        for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
     }
-    if (want_pc && want_ac) {                         // second inverse: |F|^2 kept in Bp
+    if (PC && AC) {                                   // second inverse: |F|^2 kept in Bp
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            float Pn = 0.f;
-            if (tile0 && c == 0) { const float2 Fn = nyq[j + m * T]; Pn = Fn.x * Fn.x + Fn.y * Fn.y; }
-            x[m] = make_float2(Bp[sidx(m)], Pn);
-        }
-        __syncthreads();
-        fft_from_regs<NY, +1, TC>(x, j, A + c, a.tw);
-        float2* o = a.i2_ac + tile_off + gbase;
+        for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[tid + s * NT], nyq_owner ? Pns[j + s * T] : 0.f);
+        fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
+        float2* o = a.i2_ac + g0;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) o[m * T * TC] = A[sidx(m)];
+        for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
     }
 }
 
@@ -816,28 +838,46 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     return B4D_OK;
 }
 
-template <int NY>
-int launch_cols(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
-    constexpr int PL = padded_len(NY);
-    const bool both = a.i2_ac && a.i2_pc;
-    const size_t smem = (size_t)PL * TC * sizeof(float2) + (both ? (size_t)PL * TC * sizeof(float) : 0);
-    static size_t attr[2] = {0, 0};
-    const int spec = a.spec_partials ? 1 : 0;
-    if (attr[spec] < smem) {
-        if (spec) B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr[spec] = smem;
+template <int NY, int CW, bool SPEC, bool AC, bool PC>
+int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
+    constexpr size_t smem = (size_t)padded_len(NY) * CW * sizeof(float2) +
+                            ((AC && PC) ? (size_t)NY * CW * sizeof(float) + (size_t)NY * sizeof(float) : 0);
+    static bool attr = false;
+    if (!attr) {
+        B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, CW, SPEC, AC, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
     }
-    void* p = nullptr;
-    int rc = b4d_scratch(ctx, SCR_NYQ, sizeof(float2) * (size_t)NY * (size_t)T, &p);
-    if (rc) return rc;
-    a.nyq_scratch = static_cast<float2*>(p);
     ProfScope ps(ctx, KC_COLS);
-    const dim3 grid(a.nx / 2 / TC, (unsigned)T);
-    if (spec) cols_kernel<NY, true><<<grid, NY / 16 * TC, smem, ctx->stream>>>(a);
-    else cols_kernel<NY, false><<<grid, NY / 16 * TC, smem, ctx->stream>>>(a);
+    cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
+}
+
+// columns per CTA at ny = 2048 (experiment knob: B4D_COLS_CW=4|8)
+int cols_cw_2048() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("B4D_COLS_CW"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 4 ? 4 : B4D_COLS_CW_2048); }
+    return v;
+}
+
+template <int NY, int CW>
+int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T);
+
+template <int NY>
+int launch_cols(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
+    if (NY >= 2048 && cols_cw_2048() == 4) return launch_cols_cw<NY, (NY >= 2048 ? 4 : TC)>(ctx, a, T);
+    return launch_cols_cw<NY, TC>(ctx, a, T);
+}
+
+template <int NY, int CW>
+int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
+    const bool spec = a.spec_partials != nullptr, ac = a.i2_ac != nullptr, pc = a.i2_pc != nullptr;
+    if (spec && (ac || pc)) return b4d_fail(ctx, B4D_ERR_INVALID, "cols: spectral sums cannot be combined with inverse branches");
+    if (spec) return launch_cols_inst<NY, CW, true, false, false>(ctx, a, T);
+    if (ac && pc) return launch_cols_inst<NY, CW, false, true, true>(ctx, a, T);
+    if (ac) return launch_cols_inst<NY, CW, false, true, false>(ctx, a, T);
+    if (pc) return launch_cols_inst<NY, CW, false, false, true>(ctx, a, T);
+    return launch_cols_inst<NY, CW, false, false, false>(ctx, a, T);
 }
 
 template <int NX>
@@ -854,6 +894,10 @@ int launch_rows_inv(b4d_ctx* ctx, const RowsInvArgs& a, int64_t T, int* n_blocks
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
+
+// CTAs per frame of the column pass (= number of per-frame partial sums it leaves behind)
+int cols_cw_2048();
+int cols_tiles(int ny, int nx) { return nx / 2 / (ny >= 2048 ? cols_cw_2048() : TC); }
 
 int rows_inv_blocks(int nx, int ny, int pair_maps) {
     const int tpf = nx / 16, wpg = tpf / 8, gpc = 16 / wpg, fpc = 4 * gpc;
@@ -902,7 +946,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->H = static_cast<float2*>(p);
     if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * T, &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
     if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * T, &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
-    const int ntiles = nx / 2 / TC, nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
+    const int ntiles = cols_tiles(ny, nx), nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
     size_t small = 0;
     auto take = [&](size_t bytes) { size_t o = small; small += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
@@ -960,7 +1004,7 @@ ColsArgs cols_defaults(const Work& w, int nx, bool use_pilot) {
 }
 
 int run_cols(b4d_ctx* ctx, ColsArgs& c, int64_t T, int ny) {
-    int rc = get_twiddles(ctx, ny, &c.tw);
+    int rc = get_twiddle_bases(ctx, ny, &c.tw);
     if (rc) return rc;
     DISPATCH_N(ny, rc = launch_cols<N_>(ctx, c, T));
     return rc;
@@ -988,6 +1032,7 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
 void b4d_fft_release(b4d_ctx* ctx) {
     if (!ctx->fft) return;
     for (int i = 0; i < 5; ++i) if (ctx->fft->tw[i]) cudaFree(ctx->fft->tw[i]);
+    for (int i = 0; i < 5; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
     if (ctx->fft->theta) cudaFree(ctx->fft->theta);
@@ -1046,7 +1091,7 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
         if ((rc = run_cols(ctx, c, tc, ny))) return rc;
         if (spectral) {
             double* tab = spectral + t0 * B4D_SP_NCOLS;
-            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, nx / 2 / TC, tab, tc);
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx), tab, tc);
             B4D_LAUNCH_CHECK(ctx);
             if (want_f95) {
                 const int n = ny, nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
@@ -1089,7 +1134,7 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
     RowsInvArgs r;
     memset(&r, 0, sizeof(r));
     r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = out_ac; r.kindA = 0;
-    r.normA = use_norm ? w.acp : nullptr; r.n_normA = nx / 2 / TC; r.norm_mult = norm_mult;
+    r.normA = use_norm ? w.acp : nullptr; r.n_normA = cols_tiles(ny, nx); r.norm_mult = norm_mult;
     r.scaleA = 1.0 / ((double)nx * (double)ny);
     r.bestA = grain_out ? w.bestA : nullptr;
     if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
@@ -1332,12 +1377,12 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         int nblk;
         if (want_ac && want_pc) {
             r.Ia = w.I2a; r.Ib = w.I2b; r.pair_maps = 1;
-            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 2 / TC; r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
+            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = cols_tiles(ny, nx); r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
             r.bestA = grain_out ? w.bestA : nullptr;
             r.outB = mag; r.kindB = 1; r.scaleB = 1.0 / ((double)nx * ny); r.bestB = w.bestB;
             nblk = rows_inv_blocks(nx, ny, 1);
         } else if (want_ac) {
-            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = nx / 2 / TC; r.norm_mult = 1.0;
+            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = cols_tiles(ny, nx); r.norm_mult = 1.0;
             r.scaleA = 1.0 / ((double)nx * ny); r.bestA = grain_out ? w.bestA : nullptr;
             nblk = rows_inv_blocks(nx, ny, 0);
         } else {
