@@ -11,8 +11,7 @@
 // Reads are unit-stride in v for every stage; writes are made conflict-free by padding the
 // array by one element every 16 (pad16).  For N >= 256 every index above is "a per-thread base
 // + a compile-time constant" (N/16 is a multiple of 16, so pad16(j + C) = pad16(j) + 17C/16), which
-// turns the exchanges into LDS/STS with immediate offsets.  Twiddles come from per-stage tables
-// laid out [m-1][k] so that a warp reads consecutive entries.
+// turns the exchanges into LDS/STS with immediate offsets.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -144,111 +143,6 @@ template <> struct Plan<1024> { static constexpr int R1 = 16, R2 = 16, R3 = 4; }
 template <> struct Plan<512>  { static constexpr int R1 = 16, R2 = 8,  R3 = 4; };
 template <> struct Plan<256>  { static constexpr int R1 = 16, R2 = 16, R3 = 1; };
 template <> struct Plan<128>  { static constexpr int R1 = 16, R2 = 8,  R3 = 1; };
-
-// Twiddle tables for one N: stage 2 at tw, stage 3 at tw + (R2-1)*R1. Entry [(m-1)*LS + k] =
-// exp(-2 pi i m k / (LS*R)) (forward sign; inverse transforms conjugate on the fly).
-template <int N>
-__host__ __device__ constexpr int twiddle_count() {
-    return (Plan<N>::R2 - 1) * Plan<N>::R1 + (Plan<N>::R3 > 1 ? (Plan<N>::R3 - 1) * Plan<N>::R1 * Plan<N>::R2 : 0);
-}
-
-// Full transform of data already sitting in registers for stage 1 (x[m] = data[j + m*N/16]).
-// z: shared-memory base of this transform (already offset by the batch column), element i lives at
-// z[pad16(i) * BATCH]. On return the transform is in shared memory in natural order and a
-// __syncthreads() has been issued after the last store.
-template <int N, int DIR, int BATCH>
-__device__ __forceinline__ void fft_from_regs(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ tw) {
-    using P = Plan<N>;
-    constexpr int T = N / 16;                      // threads per transform
-    constexpr bool FAST = (T % 16) == 0;           // N >= 256: all indices are base + constant
-    constexpr int R2 = P::R2, NB2 = 16 / R2, LS2 = 16;
-    constexpr int R3 = P::R3 > 1 ? P::R3 : 2, NB3 = 16 / R3, LS3 = 16 * R2;
-    const int pj = pad16(j);
-
-    // ---- stage 1: radix 16, LS = 1 -> element 16 j + q at padded index 17 j + q
-    bfly16<DIR>(x);
-    {
-        float2* w = z + 17 * j * BATCH;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) w[q * BATCH] = x[q];
-    }
-    __syncthreads();
-
-    // ---- stage 2: radix R2, LS = 16
-    {
-        const int k = j & 15;
-        if (FAST) {
-            const float2* r = z + pj * BATCH;
-#pragma unroll
-            for (int b = 0; b < NB2; ++b)
-#pragma unroll
-                for (int m = 0; m < R2; ++m) x[b * R2 + m] = r[((b * T + m * (N / R2)) / 16 * 17) * BATCH];
-        } else {
-#pragma unroll
-            for (int b = 0; b < NB2; ++b)
-#pragma unroll
-                for (int m = 0; m < R2; ++m) x[b * R2 + m] = z[pad16(j + b * T + m * (N / R2)) * BATCH];
-        }
-        const float2* t2 = tw + (FAST ? k : 0);
-#pragma unroll
-        for (int b = 0; b < NB2; ++b) {
-            const int kk = FAST ? 0 : ((j + b * T) & 15);
-#pragma unroll
-            for (int m = 1; m < R2; ++m) {
-                float2 w = __ldg(t2 + (m - 1) * LS2 + kk);
-                if (DIR > 0) w.y = -w.y;
-                x[b * R2 + m] = cmul(x[b * R2 + m], w);
-            }
-            bfly<R2, DIR>(x + b * R2);
-        }
-        __syncthreads();
-        if (FAST) {
-            // out = (v - k) R2 + k + 16 q, v = j + b T, k = j & 15  ->  padded (v - k) R2 17/16 + k + 17 q
-            float2* w = z + (((j - k) / 16) * 17 * R2 + k) * BATCH;
-#pragma unroll
-            for (int b = 0; b < NB2; ++b)
-#pragma unroll
-                for (int q = 0; q < R2; ++q) w[((b * T / 16) * 17 * R2 + 17 * q) * BATCH] = x[b * R2 + q];
-        } else {
-#pragma unroll
-            for (int b = 0; b < NB2; ++b) {
-                const int v = j + b * T, kk = v & 15;
-#pragma unroll
-                for (int q = 0; q < R2; ++q) z[pad16((v - kk) * R2 + kk + q * LS2) * BATCH] = x[b * R2 + q];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- stage 3: radix R3, LS = 16 R2 = N / R3, so every virtual thread v < LS and k = v
-    if constexpr (P::R3 > 1) {
-        const float2* r = z + pj * BATCH;
-#pragma unroll
-        for (int b = 0; b < NB3; ++b)
-#pragma unroll
-            for (int m = 0; m < R3; ++m) x[b * R3 + m] = r[((b * T + m * (N / R3)) / 16 * 17) * BATCH];
-        const float2* t3 = tw + (R2 - 1) * 16 + j;
-#pragma unroll
-        for (int b = 0; b < NB3; ++b) {
-#pragma unroll
-            for (int m = 1; m < R3; ++m) {
-                float2 w = __ldg(t3 + (m - 1) * LS3 + b * T);
-                if (DIR > 0) w.y = -w.y;
-                x[b * R3 + m] = cmul(x[b * R3 + m], w);
-            }
-            bfly<R3, DIR>(x + b * R3);
-        }
-        __syncthreads();
-        // out = v + q LS3 -> padded pad16(v) + q LS3 17/16
-        float2* w = z + pj * BATCH;
-#pragma unroll
-        for (int b = 0; b < NB3; ++b)
-#pragma unroll
-            for (int q = 0; q < R3; ++q) w[((b * T + q * LS3) / 16 * 17) * BATCH] = x[b * R3 + q];
-        __syncthreads();
-    }
-}
-
 
 // ================================================================================================
 // Register-to-register transform (v2 core).

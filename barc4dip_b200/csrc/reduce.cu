@@ -272,6 +272,274 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 2) frame_reduce_kernel(FrArgs a
     }
 }
 
+// =================================================================================================
+// v2 kernel (nx % 4 == 0, 16-byte aligned rows): overlapping strips, packed f32x2 arithmetic, fused tail collection
+// =================================================================================================
+// A warp marches down a strip of 30 x 4 = 120 own columns; lanes 0 and 31 load the 4 columns on either side and
+// only serve as the halo of lanes 1 and 30, so every horizontal neighbour comes from one shuffle and no lane
+// issues extra loads. Pixel pairs (c1,c2) and (c3,c4) of a lane live in float2 registers: the column-direction
+// parts of the Sobel / Laplacian stencils and all accumulations are FADD2 / FMUL2 / FFMA2.
+// Tail collection (the 0.05 / 99.95 percentiles of amplitude(), metrics/speckles.py:647): every pixel <= thr_lo
+// or >= thr_hi (thresholds from a 16 K sample, ~0.2 % of the frame each) is staged in shared memory and flushed
+// to a per-frame candidate list, from which tails_final_kernel reads the exact order statistics.
+constexpr int F2_WARPS = 8;
+constexpr int F2_STRIP = 120;
+constexpr int F2_BAND = 64;
+constexpr int F2_CAP = 1024;
+
+struct Fr2Args {
+    const float* stack;
+    const float* gain;
+    const float* dark;
+    const float* pilot;       // per frame K
+    const float* thr;         // per frame (thr_lo, thr_hi); nullable = no tail collection
+    double* partials;         // (T, blocks_per_frame, FR_NACC)
+    float* cand;              // (T, 2, gcap)
+    unsigned* cand_cnt;       // (T, 2), zeroed by the caller
+    int* flag;                // (T) set when a staging buffer or a candidate list overflowed
+    unsigned gcap;
+    int ny, nx;
+    int nstrips, nitems;
+    float sat, zeps;
+    int has_sat;
+};
+
+struct Win2 {
+    float2 q0, q1;            // own pixels (c1,c2), (c3,c4), shifted by K
+    float c0, c5;             // halo columns
+    bool clean;
+};
+
+struct Acc2 {
+    float2 s1, s2, s3, s4, gx2, gy2, lap, lap2;
+    int nfin, nzero, nsat, nnan;
+    __device__ __forceinline__ void clear() {
+        s1 = s2 = s3 = s4 = gx2 = gy2 = lap = lap2 = make_float2(0.f, 0.f);
+        nfin = nzero = nsat = nnan = 0;
+    }
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <bool HAS_GAIN>
+__device__ __forceinline__ float4 fetch2(const Fr2Args& a, const float* frame, int r, int j0, bool ld_ok) {
+    const int rr = min(max(r, 0), a.ny - 1);          // "reflect" = duplicate the edge sample
+    const size_t off = (size_t)rr * a.nx + j0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ld_ok) {
+        v = __ldcs(reinterpret_cast<const float4*>(frame + off));
+        if (HAS_GAIN) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(a.gain + off));
+            const float4 dk = a.dark ? __ldg(reinterpret_cast<const float4*>(a.dark + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x = (v.x - dk.x) * g.x; v.y = (v.y - dk.y) * g.y;
+            v.z = (v.z - dk.z) * g.z; v.w = (v.w - dk.w) * g.w;
+        }
+    }
+    return v;
+}
+
+template <bool TAILS>
+__device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, float K, bool edge_l, bool edge_r, bool count,
+                                        float thr_lo, float thr_hi, Acc2& acc, float* s_buf, unsigned* s_cnt) {
+    Win2 w;
+    w.q0 = __fadd2_rn(f2(raw.x, raw.y), f2(-K, -K));
+    w.q1 = __fadd2_rn(f2(raw.z, raw.w), f2(-K, -K));
+    const float left = __shfl_up_sync(0xffffffffu, w.q1.y, 1);
+    const float right = __shfl_down_sync(0xffffffffu, w.q0.x, 1);
+    w.c0 = edge_l ? w.q0.x : left;
+    w.c5 = edge_r ? w.q1.y : right;
+    // lane-level screening so that ordinary pixels skip every per-pixel test
+    const float sumabs = (fabsf(raw.x) + fabsf(raw.y)) + (fabsf(raw.z) + fabsf(raw.w));
+    const float minabs = fminf(fminf(fabsf(raw.x), fabsf(raw.y)), fminf(fabsf(raw.z), fabsf(raw.w)));
+    const float mx = fmaxf(fmaxf(raw.x, raw.y), fmaxf(raw.z, raw.w));
+    bool clean = (sumabs <= 3.402823466e38f) && (minabs > a.zeps);
+    if (a.has_sat) clean = clean && (mx < a.sat);
+    w.clean = clean;
+    if (count) {
+        if (clean) {
+            const float2 da = __fmul2_rn(w.q0, w.q0), db = __fmul2_rn(w.q1, w.q1);
+            acc.s1 = __fadd2_rn(acc.s1, __fadd2_rn(w.q0, w.q1));
+            acc.s2 = __fadd2_rn(acc.s2, __fadd2_rn(da, db));
+            acc.s3 = __ffma2_rn(da, w.q0, acc.s3);
+            acc.s3 = __ffma2_rn(db, w.q1, acc.s3);
+            acc.s4 = __ffma2_rn(da, da, acc.s4);
+            acc.s4 = __ffma2_rn(db, db, acc.s4);
+            acc.nfin += 4;
+        } else {
+            const float xs[4] = {raw.x, raw.y, raw.z, raw.w};
+            const float ds[4] = {w.q0.x, w.q0.y, w.q1.x, w.q1.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xv = xs[k];
+                if (fabsf(xv) <= 3.402823466e38f) {          // false for NaN / inf
+                    const float d = ds[k], d2 = d * d;
+                    acc.s1.x += d;
+                    acc.s2.x += d2;
+                    acc.s3.x = fmaf(d2, d, acc.s3.x);
+                    acc.s4.x = fmaf(d2, d2, acc.s4.x);
+                    acc.nfin++;
+                    acc.nzero += (fabsf(xv) <= a.zeps) ? 1 : 0;
+                    acc.nsat += (a.has_sat && xv >= a.sat) ? 1 : 0;
+                } else if (xv != xv) {
+                    acc.nnan++;
+                }
+            }
+        }
+        if (TAILS) {
+            const float mn = fminf(fminf(raw.x, raw.y), fminf(raw.z, raw.w));
+            if (mn <= thr_lo || mx >= thr_hi) {
+                const float xs[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (xs[k] <= thr_lo) { const unsigned p = atomicAdd(s_cnt, 1u); if (p < F2_CAP) s_buf[p] = xs[k]; }
+                    if (xs[k] >= thr_hi) { const unsigned p = atomicAdd(s_cnt + 1, 1u); if (p < F2_CAP) s_buf[F2_CAP + p] = xs[k]; }
+                }
+            }
+        }
+    }
+    return w;
+}
+
+__device__ __forceinline__ void stencil2(const Win2& up, const Win2& mid, const Win2& dn, Acc2& acc) {
+    const float2 V0 = __fadd2_rn(up.q0, dn.q0), V1 = __fadd2_rn(up.q1, dn.q1);
+    const float2 S0 = __ffma2_rn(f2(2.f, 2.f), mid.q0, V0), S1 = __ffma2_rn(f2(2.f, 2.f), mid.q1, V1);
+    const float s0 = fmaf(2.f, mid.c0, up.c0 + dn.c0), s5 = fmaf(2.f, mid.c5, up.c5 + dn.c5);
+    const float2 D0 = __fadd2_rn(dn.q0, f2(-up.q0.x, -up.q0.y)), D1 = __fadd2_rn(dn.q1, f2(-up.q1.x, -up.q1.y));
+    const float d0 = dn.c0 - up.c0, d5 = dn.c5 - up.c5;
+    const float2 GXa = f2(S0.y - s0, S1.x - S0.x), GXb = f2(S1.y - S0.y, s5 - S1.x);
+    const float2 GYa = f2(fmaf(2.f, D0.x, d0 + D0.y), fmaf(2.f, D0.y, D0.x + D1.x));
+    const float2 GYb = f2(fmaf(2.f, D1.x, D0.y + D1.y), fmaf(2.f, D1.y, D1.x + d5));
+    const float2 Ha = f2(mid.c0 + mid.q0.y, mid.q0.x + mid.q1.x), Hb = f2(mid.q0.y + mid.q1.y, mid.q1.x + mid.c5);
+    const float2 LPa = __ffma2_rn(f2(-4.f, -4.f), mid.q0, __fadd2_rn(V0, Ha));
+    const float2 LPb = __ffma2_rn(f2(-4.f, -4.f), mid.q1, __fadd2_rn(V1, Hb));
+    if (mid.clean) {
+        acc.gx2 = __ffma2_rn(GXa, GXa, acc.gx2);
+        acc.gx2 = __ffma2_rn(GXb, GXb, acc.gx2);
+        acc.gy2 = __ffma2_rn(GYa, GYa, acc.gy2);
+        acc.gy2 = __ffma2_rn(GYb, GYb, acc.gy2);
+        acc.lap = __fadd2_rn(acc.lap, __fadd2_rn(LPa, LPb));
+        acc.lap2 = __ffma2_rn(LPa, LPa, acc.lap2);
+        acc.lap2 = __ffma2_rn(LPb, LPb, acc.lap2);
+    } else {
+        // the reference averages over pixels whose own value is finite; non-finite neighbours propagate into the
+        // sums exactly as they do through scipy.ndimage.
+        const float ctr[4] = {mid.q0.x, mid.q0.y, mid.q1.x, mid.q1.y};
+        const float gx[4] = {GXa.x, GXa.y, GXb.x, GXb.y}, gy[4] = {GYa.x, GYa.y, GYb.x, GYb.y};
+        const float lp[4] = {LPa.x, LPa.y, LPb.x, LPb.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (fabsf(ctr[k]) <= 3.402823466e38f) {
+                acc.gx2.x = fmaf(gx[k], gx[k], acc.gx2.x);
+                acc.gy2.x = fmaf(gy[k], gy[k], acc.gy2.x);
+                acc.lap.x += lp[k];
+                acc.lap2.x = fmaf(lp[k], lp[k], acc.lap2.x);
+            }
+        }
+    }
+}
+
+template <bool HAS_GAIN, bool TAILS>
+__global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * F2_WARPS + warp;
+    const int64_t t = blockIdx.y;
+    const float* frame = a.stack + (size_t)t * a.ny * a.nx;
+    const float K = __ldg(a.pilot + t);
+    float thr_lo = -INFINITY, thr_hi = INFINITY;
+    __shared__ float s_buf[TAILS ? 2 * F2_CAP : 2];
+    __shared__ unsigned s_cnt[2];
+    __shared__ unsigned s_base[2];
+    if (TAILS) {
+        thr_lo = __ldg(a.thr + 2 * t);
+        thr_hi = __ldg(a.thr + 2 * t + 1);
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+    }
+
+    double d[FR_NACC];
+#pragma unroll
+    for (int i = 0; i < FR_NACC; ++i) d[i] = 0.0;
+
+    if (item < a.nitems) {
+        const int strip = item % a.nstrips, band = item / a.nstrips;
+        const int j0 = strip * F2_STRIP + (lane - 1) * 4;
+        const bool ld_ok = j0 >= 0 && j0 < a.nx;
+        const bool own = lane >= 1 && lane <= 30 && j0 < a.nx;
+        const bool edge_l = j0 == 0, edge_r = j0 + 4 == a.nx;
+        const int r0 = band * F2_BAND;
+        const int r1 = min(r0 + F2_BAND, a.ny);
+        Acc2 acc;
+        acc.clear();
+        float4 raw[4];
+        const float4 rawm = fetch2<HAS_GAIN>(a, frame, r0 - 1, j0, ld_ok), raw0 = fetch2<HAS_GAIN>(a, frame, r0, j0, ld_ok);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) raw[q] = fetch2<HAS_GAIN>(a, frame, r0 + 1 + q, j0, ld_ok);
+        Win2 up = finish2<TAILS>(a, rawm, K, edge_l, edge_r, false, thr_lo, thr_hi, acc, s_buf, s_cnt);
+        Win2 mid = finish2<TAILS>(a, raw0, K, edge_l, edge_r, own, thr_lo, thr_hi, acc, s_buf, s_cnt);
+        for (int rb = r0; rb < r1; rb += 4) {
+            // the four rows fetched one iteration ago are consumed while the next four are already in flight
+            float4 cur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cur[q] = raw[q];
+            if (rb + 4 < r1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) raw[q] = fetch2<HAS_GAIN>(a, frame, rb + 5 + q, j0, ld_ok);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const Win2 nxt = finish2<TAILS>(a, cur[q], K, edge_l, edge_r, own && (rb + 1 + q < r1), thr_lo, thr_hi, acc, s_buf, s_cnt);
+                if (own && rb + q < r1) stencil2(up, mid, nxt, acc);
+                up = mid;
+                mid = nxt;
+            }
+            if (((rb - r0) & 4) != 0 || rb + 4 >= r1) {   // fold fp32 partials into fp64 every 8 rows
+                d[0] += acc.nfin; d[1] += (double)acc.s1.x + (double)acc.s1.y; d[2] += (double)acc.s2.x + (double)acc.s2.y;
+                d[3] += (double)acc.s3.x + (double)acc.s3.y; d[4] += (double)acc.s4.x + (double)acc.s4.y;
+                d[5] += acc.nzero; d[6] += acc.nsat;
+                d[7] += (double)acc.gx2.x + (double)acc.gx2.y; d[8] += (double)acc.gy2.x + (double)acc.gy2.y;
+                d[9] += (double)acc.lap.x + (double)acc.lap.y; d[10] += (double)acc.lap2.x + (double)acc.lap2.y;
+                d[11] += acc.nnan;
+                acc.clear();
+            }
+        }
+    }
+
+    __shared__ double sm[F2_WARPS][FR_NACC];
+#pragma unroll
+    for (int i = 0; i < FR_NACC; ++i) {
+        double v = warp_sum(d[i]);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < FR_NACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < F2_WARPS; ++w) v += sm[w][threadIdx.x];
+        a.partials[((size_t)t * gridDim.x + blockIdx.x) * FR_NACC + threadIdx.x] = v;
+    }
+    if (TAILS) {
+        // flush the staged candidates: one reservation per CTA and tail
+        if (threadIdx.x < 2) {
+            const unsigned n = s_cnt[threadIdx.x];
+            unsigned base = 0;
+            if (n > F2_CAP) a.flag[t] = 1;
+            else if (n) {
+                base = atomicAdd(a.cand_cnt + 2 * t + threadIdx.x, n);
+                if (base + n > a.gcap) a.flag[t] = 1;
+            }
+            s_base[threadIdx.x] = base;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tail = 0; tail < 2; ++tail) {
+            const unsigned n = min(s_cnt[tail], (unsigned)F2_CAP), base = s_base[tail];
+            float* dst = a.cand + ((size_t)t * 2 + tail) * a.gcap;
+            for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
+                if (base + i < a.gcap) dst[base + i] = s_buf[tail * F2_CAP + i];
+        }
+    }
+}
+
 // ---- finalize: fixed-order sum of the per-CTA partials, re-centre the moments ------------------
 __global__ void __launch_bounds__(128) frame_finalize_kernel(const double* __restrict__ partials, int nblocks,
                                                             const float* __restrict__ pilot, double npix,
@@ -330,8 +598,21 @@ float float_at_least(double v) {
 
 }  // namespace
 
+struct FrTails {              // optional fused tail percentiles (amplitude contrast)
+    double q_lo, q_hi;
+    float* quant_out;          // (T, 4): (v[lo], v[hi]) of q_lo, then of q_hi
+    int64_t* nvalid_out;       // (T): non-NaN pixels, -1 = unresolved (use b4d_select_ranks for that frame)
+};
+int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
+                            float* pilot_out);
 int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                 const float* dark, double sat_value, double zero_eps, double* out);
+unsigned b4d_tails_gcap();
+int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain, const float* dark,
+                           double q_lo, double q_hi, float* thr);
+int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const int* flag, const double* fr, int64_t T,
+                           double q_lo, double q_hi, float* out, int64_t* nvalid_out);
 
 int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
                            const float* dark, float* pilot) {
@@ -351,55 +632,103 @@ extern "C" int b4d_frame_reductions(b4d_ctx* ctx, const float* stack, int64_t n_
 
 int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                 const float* dark, double sat_value, double zero_eps, double* out) {
+    return b4d_frame_reductions_ex(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out, nullptr, nullptr);
+}
+
+extern "C" int b4d_frame_reductions_tails(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                                          const float* gain, const float* dark, double sat_value, double zero_eps,
+                                          double q_lo, double q_hi, double* out, float* quant_out, int64_t* nvalid_out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    if (!quant_out || !nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0))
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions_tails: need 0 <= q_lo < q_hi <= 1 and both outputs");
+    FrTails tl = {q_lo, q_hi, quant_out, nvalid_out};
+    return b4d_frame_reductions_ex(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out, &tl, nullptr);
+}
+
+int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
+                            float* pilot_out) {
     if (!stack || !out || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: bad arguments (T=%lld ny=%d nx=%d)",
                         (long long)n_frames, ny, nx);
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: dark given without gain");
-    FrArgs a;
-    a.stack = stack; a.gain = gain; a.dark = dark;
-    a.ny = ny; a.nx = nx;
-    a.nstrips = (nx + FR_STRIP - 1) / FR_STRIP;
-    const int nbands = (ny + FR_BAND - 1) / FR_BAND;
-    a.nitems = a.nstrips * nbands;
-    const int nblocks = (a.nitems + FR_WARPS - 1) / FR_WARPS;
-    a.has_sat = !(sat_value != sat_value);
-    a.sat = a.has_sat ? float_at_least(sat_value) : 0.f;
-    a.zeps = float_at_most(zero_eps);
+    const bool has_sat = !(sat_value != sat_value);
+    const float sat = has_sat ? float_at_least(sat_value) : 0.f;
+    const float zeps = float_at_most(zero_eps);
     const bool vec = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(stack) & 15) == 0) &&
                      (!gain || (reinterpret_cast<uintptr_t>(gain) & 15) == 0) &&
                      (!dark || (reinterpret_cast<uintptr_t>(dark) & 15) == 0);
+    const int64_t npix = (int64_t)ny * nx;
+    // the fused tails need the v2 kernel; frames it does not cover are reported as unresolved
+    const bool fuse_tails = tails && vec && npix >= 65536;
+
+    const int nstrips = vec ? (nx + F2_STRIP - 1) / F2_STRIP : (nx + FR_STRIP - 1) / FR_STRIP;
+    const int nbands = (ny + FR_BAND - 1) / FR_BAND;
+    const int nitems = nstrips * nbands;
+    const int nblocks = (nitems + FR_WARPS - 1) / FR_WARPS;
+    static_assert(F2_BAND == FR_BAND && F2_WARPS == FR_WARPS, "the two reduce kernels share the item decomposition");
 
     void* p = nullptr;
     const int64_t chunk_max = 32768;   // gridDim.y limit is 65535
-    int rc = b4d_scratch(ctx, SCR_PILOT, sizeof(float) * (size_t)n_frames, &p);
+    int rc = b4d_scratch(ctx, SCR_PILOT, sizeof(float) * 3 * (size_t)n_frames, &p);
     if (rc) return rc;
-    float* pilot = static_cast<float*>(p);
-    rc = b4d_scratch(ctx, SCR_REDUCE, sizeof(double) * FR_NACC * (size_t)nblocks * (size_t)n_frames, &p);
+    float* pilot = pilot_out ? pilot_out : static_cast<float*>(p);
+    float* thr = static_cast<float*>(p) + n_frames;
+    const unsigned gcap = b4d_tails_gcap();
+    const size_t part_bytes = (sizeof(double) * FR_NACC * (size_t)nblocks * (size_t)n_frames + 255) & ~size_t(255);
+    const size_t cnt_bytes = fuse_tails ? (((size_t)n_frames * 3 * sizeof(unsigned) + 255) & ~size_t(255)) : 0;
+    const size_t cand_bytes = fuse_tails ? (size_t)n_frames * 2 * gcap * sizeof(float) : 0;
+    rc = b4d_scratch(ctx, SCR_REDUCE, part_bytes + cnt_bytes + cand_bytes, &p);
     if (rc) return rc;
-    a.partials = static_cast<double*>(p);
-    a.pilot = pilot;
+    double* partials = static_cast<double*>(p);
+    unsigned* cnt = reinterpret_cast<unsigned*>(static_cast<char*>(p) + part_bytes);
+    int* flag = reinterpret_cast<int*>(cnt + 2 * n_frames);
+    float* cand = reinterpret_cast<float*>(static_cast<char*>(p) + part_bytes + cnt_bytes);
+    if (fuse_tails) B4D_CUDA(ctx, cudaMemsetAsync(cnt, 0, cnt_bytes, ctx->stream));
 
     for (int64_t t0 = 0; t0 < n_frames; t0 += chunk_max) {
         const int64_t tc = (n_frames - t0 < chunk_max) ? n_frames - t0 : chunk_max;
         const float* s0 = stack + (size_t)t0 * ny * nx;
-        rc = b4d_frame_pilot_launch(ctx, s0, tc, (int64_t)ny * nx, gain, dark, pilot + t0);
+        rc = b4d_frame_pilot_launch(ctx, s0, tc, npix, gain, dark, pilot + t0);
         if (rc) return rc;
-        FrArgs b = a;
-        b.stack = s0;
-        b.pilot = pilot + t0;
-        b.partials = a.partials + (size_t)t0 * nblocks * FR_NACC;
+        if (fuse_tails && (rc = b4d_tails_probe_launch(ctx, s0, tc, npix, gain, dark, tails->q_lo, tails->q_hi, thr + 2 * t0))) return rc;
         dim3 grid((unsigned)nblocks, (unsigned)tc);
-        {
+        double* part0 = partials + (size_t)t0 * nblocks * FR_NACC;
+        if (vec) {
+            Fr2Args b;
+            b.stack = s0; b.gain = gain; b.dark = dark; b.pilot = pilot + t0; b.thr = fuse_tails ? thr + 2 * t0 : nullptr;
+            b.partials = part0; b.cand = cand + (size_t)t0 * 2 * gcap; b.cand_cnt = cnt + 2 * t0; b.flag = flag + t0; b.gcap = gcap;
+            b.ny = ny; b.nx = nx; b.nstrips = nstrips; b.nitems = nitems; b.sat = sat; b.zeps = zeps; b.has_sat = has_sat;
             ProfScope ps(ctx, KC_FRAME_REDUCE);
-            if (vec) frame_reduce_kernel<true><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
-            else frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+            if (gain) {
+                if (fuse_tails) frame_reduce2_kernel<true, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+                else frame_reduce2_kernel<true, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+            } else {
+                if (fuse_tails) frame_reduce2_kernel<false, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+                else frame_reduce2_kernel<false, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+            }
+        } else {
+            FrArgs b;
+            b.stack = s0; b.gain = gain; b.dark = dark; b.pilot = pilot + t0; b.partials = part0;
+            b.ny = ny; b.nx = nx; b.nstrips = nstrips; b.nitems = nitems; b.sat = sat; b.zeps = zeps; b.has_sat = has_sat;
+            ProfScope ps(ctx, KC_FRAME_REDUCE);
+            frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
         }
         B4D_LAUNCH_CHECK(ctx);
-        ProfScope ps2(ctx, KC_SMALL);
-        frame_finalize_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(b.partials, nblocks, b.pilot,
-                                                                     (double)ny * (double)nx,
-                                                                     out + t0 * B4D_FR_NCOLS);
-        B4D_LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps2(ctx, KC_SMALL);
+            frame_finalize_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(part0, nblocks, pilot + t0, (double)ny * (double)nx,
+                                                                         out + t0 * B4D_FR_NCOLS);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if (fuse_tails) {
+            rc = b4d_tails_final_launch(ctx, cand + (size_t)t0 * 2 * gcap, cnt + 2 * t0, flag + t0, out + t0 * B4D_FR_NCOLS, tc,
+                                        tails->q_lo, tails->q_hi, tails->quant_out + 4 * t0, tails->nvalid_out + t0);
+            if (rc) return rc;
+        } else if (tails) {
+            B4D_CUDA(ctx, cudaMemsetAsync(tails->nvalid_out + t0, 0xff, sizeof(int64_t) * tc, ctx->stream));   // -1: unresolved
+        }
     }
     return B4D_OK;
 }

@@ -334,6 +334,106 @@ __global__ void __launch_bounds__(1024) sel_final_kernel(SelFast* __restrict__ s
 }
 
 // =================================================================================================
+// tails: thresholds for the fused tail collection of frame_reduce2_kernel, and the final order statistics
+// =================================================================================================
+// thr[t] = (thr_lo, thr_hi): every pixel <= thr_lo / >= thr_hi is a candidate. They are the sample order statistics
+// +-6 sigma (binomial) beyond the sample quantiles, so the wanted ranks fall inside the candidate lists unless the
+// sample was unlucky (then tails_final_kernel flags the frame).
+__global__ void __launch_bounds__(1024) tails_probe_kernel(const float* __restrict__ stack, const float* __restrict__ gain,
+                                                           const float* __restrict__ dark, int64_t n, double q_lo, double q_hi,
+                                                           float* __restrict__ thr) {
+    extern __shared__ unsigned keys[];              // SEL_SAMPLES
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned tmp[34];
+    __shared__ unsigned s_min, s_max;
+    __shared__ int s_valid;
+    const int64_t t = blockIdx.x;
+    const float* f = stack + t * n;
+    if (threadIdx.x == 0) { s_valid = 0; s_min = 0xffffffffu; s_max = 0u; }
+    __syncthreads();
+    int nv = 0;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    for (int i = threadIdx.x; i < SEL_SAMPLES; i += blockDim.x) {
+        const int64_t p = (int64_t)(((__int128)i * n) / SEL_SAMPLES);
+        float v = __ldg(f + p);
+        if (gain) v = (v - (dark ? __ldg(dark + p) : 0.f)) * __ldg(gain + p);
+        const bool ok = v == v;
+        const unsigned k = ok ? key_of(v, 0) : 0xffffffffu;
+        keys[i] = k;
+        nv += ok;
+        if (ok) { kmin = min(kmin, k); kmax = max(kmax, k); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_valid, nv); atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+    __syncthreads();
+    const int m = s_valid;
+    float lo = INFINITY, hi = -INFINITY;            // degenerate sample: everything is a candidate -> overflow -> flagged
+    if (m >= 1024) {
+        const double cl = q_lo * (double)(m - 1), dl = 6.0 * sqrt(q_lo * (1.0 - q_lo) * (double)m) + 8.0;
+        const double ch = q_hi * (double)(m - 1), dh = 6.0 * sqrt(q_hi * (1.0 - q_hi) * (double)m) + 8.0;
+        const long long iu = (long long)ceil(cl + dl), il = (long long)floor(ch - dh);
+        if (iu < m - 1) lo = value_of(cta_bracket_select(keys, SEL_SAMPLES, (unsigned)iu, s_min, s_max, hist, tmp), 0);
+        if (il > 0) hi = value_of(cta_bracket_select(keys, SEL_SAMPLES, (unsigned)il, s_min, s_max, hist, tmp), 0);
+    }
+    if (threadIdx.x == 0) { thr[2 * t] = lo; thr[2 * t + 1] = hi; }
+}
+
+constexpr unsigned TAIL_GCAP = 16384;   // candidates per frame and tail (64 KB of keys in shared memory)
+
+// out[t] = (v[lo], v[hi]) of q_lo, (v[lo], v[hi]) of q_hi (numpy 'linear' neighbours); nvalid_out[t] = number of
+// non-NaN pixels, or -1 when the frame's candidate lists do not contain the wanted ranks.
+__global__ void __launch_bounds__(1024) tails_final_kernel(const float* __restrict__ cand, const unsigned* __restrict__ cnt,
+                                                           const int* __restrict__ flag, const double* __restrict__ fr,
+                                                           double q_lo, double q_hi, float* __restrict__ out,
+                                                           long long* __restrict__ nvalid_out) {
+    extern __shared__ unsigned keys[];              // TAIL_GCAP
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned tmp[34];
+    __shared__ unsigned s_min, s_max;
+    const int64_t t = blockIdx.x;
+    const long long nv = (long long)(fr[t * B4D_FR_NCOLS + B4D_FR_NPIX] - fr[t * B4D_FR_NCOLS + B4D_FR_NNAN]);
+    bool ok = nv > 0 && !flag[t];
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tail = 0; tail < 2 && ok; ++tail) {
+        const unsigned c = cnt[2 * t + tail];
+        long long lo, hi;
+        target_ranks((unsigned long long)nv, tail ? q_hi : q_lo, lo, hi);
+        // ascending ranks inside the candidate list
+        const long long off = tail ? nv - (long long)c : 0;
+        lo -= off; hi -= off;
+        if (c == 0 || c > TAIL_GCAP || lo < 0 || hi >= (long long)c) { ok = false; break; }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_min = 0xffffffffu; s_max = 0u; }
+        __syncthreads();
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        const float* src = cand + ((size_t)t * 2 + tail) * TAIL_GCAP;
+        for (unsigned i = threadIdx.x; i < c; i += blockDim.x) {
+            const unsigned k = key_of(src[i], 0);
+            keys[i] = k;
+            kmin = min(kmin, k); kmax = max(kmax, k);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+        __syncthreads();
+        const unsigned a = cta_bracket_select(keys, c, (unsigned)lo, s_min, s_max, hist, tmp);
+        const unsigned b = hi == lo ? a : cta_bracket_select(keys, c, (unsigned)hi, s_min, s_max, hist, tmp);
+        res[2 * tail] = value_of(a, 0);
+        res[2 * tail + 1] = value_of(b, 0);
+    }
+    if (threadIdx.x == 0) {
+        nvalid_out[t] = ok ? nv : -1;
+        for (int i = 0; i < 4; ++i) out[4 * t + i] = ok ? res[i] : __uint_as_float(0x7fc00000u);
+    }
+}
+
+// =================================================================================================
 // radix path (small frames, flagged frames)
 // =================================================================================================
 // PASS 0: bits 31..21, PASS 1: bits 20..10 (given 11-bit prefix), PASS 2: bits 9..0 (given 22-bit prefix)
@@ -481,6 +581,39 @@ int radix_path(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const dou
 }
 
 }  // namespace
+
+
+// ---- tails (called from reduce.cu) ------------------------------------------------------------------
+unsigned b4d_tails_gcap() { return TAIL_GCAP; }
+
+int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain, const float* dark,
+                           double q_lo, double q_hi, float* thr) {
+    static int attr = 0;
+    if (!attr) {
+        B4D_CUDA(ctx, cudaFuncSetAttribute(tails_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(SEL_SAMPLES * sizeof(unsigned))));
+        attr = 1;
+    }
+    ProfScope ps(ctx, KC_SELECT_SAMPLE);
+    tails_probe_kernel<<<(unsigned)T, 1024, SEL_SAMPLES * sizeof(unsigned), ctx->stream>>>(stack, gain, dark, npix, q_lo, q_hi, thr);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const int* flag, const double* fr, int64_t T,
+                           double q_lo, double q_hi, float* out, int64_t* nvalid_out) {
+    static int attr = 0;
+    if (!attr) {
+        B4D_CUDA(ctx, cudaFuncSetAttribute(tails_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(TAIL_GCAP * sizeof(unsigned))));
+        attr = 1;
+    }
+    ProfScope ps(ctx, KC_SELECT_FINAL);
+    tails_final_kernel<<<(unsigned)T, 1024, TAIL_GCAP * sizeof(unsigned), ctx->stream>>>(cand, cnt, flag, fr, q_lo, q_hi, out,
+                                                                                      reinterpret_cast<long long*>(nvalid_out));
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
 
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid) {

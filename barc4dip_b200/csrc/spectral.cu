@@ -27,10 +27,13 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
                     int use_abs, float* out, int64_t* n_valid);
 int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                 const float* dark, double sat_value, double zero_eps, double* out);
+struct FrTails { double q_lo, q_hi; float* quant_out; int64_t* nvalid_out; };   // reduce.cu
+int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
+                            float* pilot_out);
 
 struct FftPlanCache {
-    float2* tw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // 128, 256, 512, 1024, 2048
-    float2* twb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power tables of the v2 core
+    float2* twb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power twiddle tables: 128, 256, 512, 1024, 2048
     // tracker reference: conj spectrum of the embedded z-scored template
     float2* ref = nullptr;       // blocked (nx/2/8, ny, 8)
     float2* ref_nyq = nullptr;   // (ny)
@@ -45,40 +48,6 @@ constexpr int NTHETA = 1130;   // int(2*pi*180), maths/radial.py:150
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 inline bool fft_size_ok(int n) { return n >= 128 && n <= 2048 && (n & (n - 1)) == 0; }
-
-template <int N>
-void fill_twiddles(std::vector<float2>& h) {
-    using P = Plan<N>;
-    h.clear();
-    auto push_stage = [&](int R, int LS) {
-        for (int m = 1; m < R; ++m)
-            for (int k = 0; k < LS; ++k) {
-                const double a = -2.0 * 3.14159265358979323846 * (double)m * (double)k / ((double)LS * (double)R);
-                h.push_back(make_float2((float)cos(a), (float)sin(a)));
-            }
-    };
-    push_stage(P::R2, P::R1);
-    if (P::R3 > 1) push_stage(P::R3, P::R1 * P::R2);
-}
-
-int get_twiddles(b4d_ctx* ctx, int n, const float2** out) {
-    if (!ctx->fft) ctx->fft = new FftPlanCache();
-    const int slot = log2i(n) - 7;
-    if (!ctx->fft->tw[slot]) {
-        std::vector<float2> h;
-        switch (n) {
-            case 128: fill_twiddles<128>(h); break;
-            case 256: fill_twiddles<256>(h); break;
-            case 512: fill_twiddles<512>(h); break;
-            case 1024: fill_twiddles<1024>(h); break;
-            default: fill_twiddles<2048>(h); break;
-        }
-        B4D_CUDA(ctx, cudaMalloc(&ctx->fft->tw[slot], h.size() * sizeof(float2)));
-        B4D_CUDA(ctx, cudaMemcpy(ctx->fft->tw[slot], h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    }
-    *out = ctx->fft->tw[slot];
-    return B4D_OK;
-}
 
 // base powers (w, w^2, w^4, w^8) per stage and k, see fft.cuh (v2 core)
 template <int N>
@@ -159,7 +128,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
         }
         x[m] = make_float2(va - K, vb - K);
     }
-    fft_from_regs<NX, -1, 1>(x, j, sm + f * FS, a.tw);
+    fft_regs_to_smem<NX, -1, 1>(x, j, sm + f * FS, a.tw);
 
     // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
     float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
@@ -443,10 +412,14 @@ struct RowsInvArgs {
     ArgBest* bestB;
 };
 
+// Two thread mappings. The gather uses lanes (c = lane & 7, fl = lane >> 3): 8 adjacent kx of 4 rows, i.e. whole
+// 64-byte runs of the blocked intermediates. The transform and everything after it use the natural mapping
+// (f = tid / TPF, j = tid % TPF): the v2 core leaves x-position j + TPF*s in slot s, so the two real output rows
+// are stored straight from registers, 128 contiguous bytes per warp and slot.
 template <int NX>
-__global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
+__global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     constexpr int TPF = NX / 16;
-    constexpr int WPG = TPF / 8;          // warps per group of 4 transforms
+    constexpr int WPG = TPF / 8;          // warps per group of 4 transforms (gather mapping)
     constexpr int GPC = 16 / WPG;         // groups per CTA (512 threads)
     constexpr int FPC = 4 * GPC;
     constexpr int FS = padded_len(NX) + 8;
@@ -455,99 +428,90 @@ __global__ void __launch_bounds__(512) rows_inv_kernel(RowsInvArgs a) {
     __shared__ float s_scale;
     __shared__ ArgBest s_best[2][16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
-    const int f = grp * 4 + fl, j = jt * 8 + c;
     const int64_t t = blockIdx.y;
     const int NY = a.ny;
     const int rows_per_cta = a.pair_maps ? FPC : 2 * FPC;
     const int y0 = blockIdx.x * rows_per_cta;
-    const int ya = a.pair_maps ? y0 + f : y0 + 2 * f;
-    const int yb = a.pair_maps ? ya : ya + 1;
     const float2* Ia = a.Ia + (size_t)t * NY * HX;
     const float2* Ib = a.pair_maps ? a.Ib + (size_t)t * NY * HX : Ia;
 
-    // issue the gather loads first; the scale they are multiplied with is resolved meanwhile
-    float2 ga[8], gb[8];
+    // ---- gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
+    {
+        const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
+        const int f = grp * 4 + fl, jg = jt * 8 + c;
+        const int ya = a.pair_maps ? y0 + f : y0 + 2 * f;
+        const int yb = a.pair_maps ? ya : ya + 1;
+        float2 ga[8], gb[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = j + m * TPF;
-        const size_t off = ((size_t)(k / TC) * NY) * TC + (k % TC);
-        ga[m] = __ldg(Ia + off + (size_t)ya * TC);
-        gb[m] = __ldg(Ib + off + (size_t)yb * TC);
-    }
-    if (warp == 0) {
-        double s = a.scaleA;
-        if (a.normA) {
-            // fixed-order reduction of the per-tile partials: lane-strided chunks, then a shuffle tree
-            double part = 0.0;
-            for (int i = lane; i < a.n_normA; i += 32) part += a.normA[(size_t)t * a.n_normA + i];
-            part = warp_sum(part);
-            s = part > 0.0 ? a.norm_mult / part : a.scaleA;
+        for (int m = 0; m < 8; ++m) {
+            const int k = jg + m * TPF;
+            const size_t off = ((size_t)(k / TC) * NY) * TC + (k % TC);
+            ga[m] = __ldcs(Ia + off + (size_t)ya * TC);
+            gb[m] = __ldcs(Ib + off + (size_t)yb * TC);
         }
-        if (lane == 0) s_scale = (float)s;
+        if (warp == 0) {
+            double sc = a.scaleA;
+            if (a.normA) {
+                // fixed-order reduction of the per-tile partials: lane-strided chunks, then a shuffle tree
+                double part = 0.0;
+                for (int i = lane; i < a.n_normA; i += 32) part += a.normA[(size_t)t * a.n_normA + i];
+                part = warp_sum(part);
+                sc = part > 0.0 ? a.norm_mult / part : a.scaleA;
+            }
+            if (lane == 0) s_scale = (float)sc;
+        }
+        __syncthreads();
+        // The two rows share one complex transform, so they are brought to their final scale BEFORE it: a raw
+        // autocorrelation (~1e13) packed next to a raw phase correlation (~1e6) would bury the latter in rounding.
+        const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
+        float2* z = sm + f * FS;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int k = jg + m * TPF;
+            float2 g1 = ga[m], g2 = gb[m];
+            g1.x *= sA; g1.y *= sA; g2.x *= sB; g2.y *= sB;
+            if (k == 0) {
+                // packed slot: (DC, Nyquist), both real
+                z[pad16(0)] = make_float2(g1.x, g2.x);
+                z[pad16(HX)] = make_float2(g1.y, g2.y);
+            } else {
+                z[pad16(k)] = make_float2(g1.x - g2.y, g1.y + g2.x);
+                z[pad16(NX - k)] = make_float2(g1.x + g2.y, g2.x - g1.y);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // The two rows share one complex transform, so they are brought to their final scale BEFORE it: a raw
-    // autocorrelation (~1e13) packed next to a raw phase correlation (~1e6) would bury the latter in rounding.
-    const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
 
-    // each thread holds Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
+    // ---- transform (natural mapping), outputs stay in registers
+    const int f = tid / TPF, j = tid % TPF;
     float2* z = sm + f * FS;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = j + m * TPF;
-        float2 g1 = ga[m], g2 = gb[m];
-        g1.x *= sA; g1.y *= sA; g2.x *= sB; g2.y *= sB;
-        if (k == 0) {
-            // packed slot: (DC, Nyquist), both real
-            z[pad16(0)] = make_float2(g1.x, g2.x);
-            z[pad16(HX)] = make_float2(g1.y, g2.y);
-        } else {
-            z[pad16(k)] = make_float2(g1.x - g2.y, g1.y + g2.x);
-            z[pad16(NX - k)] = make_float2(g1.x + g2.y, g2.x - g1.y);
-        }
-    }
-    __syncthreads();
     float2 x[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
-    __syncthreads();
-    fft_from_regs<NX, +1, 1>(x, j, z, a.tw);
+    fft_regs<NX, +1, 1>(x, j, z, a.tw);
 
-    // stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
+    // ---- stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
     const int kindB = a.pair_maps ? a.kindB : a.kindA;
     float* oA = a.outA ? a.outA + (size_t)t * NY * NX : nullptr;
     float* oB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX : nullptr) : oA;
     ArgBest bA = {-INFINITY, 0xffffffffu}, bB = {-INFINITY, 0xffffffffu};
-    auto emit = [&](int ff, int xx, float2 v) {
-        const int ra_ = a.pair_maps ? y0 + ff : y0 + 2 * ff;
+    {
+        const int ra_ = a.pair_maps ? y0 + f : y0 + 2 * f;
         const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
-        const unsigned cs = (unsigned)((xx + HX) & (NX - 1));
-        const unsigned ia = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX + cs;
-        const unsigned ib = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX + cs;
-        float va = v.x, vb = v.y;
-        if (a.kindA) va = fabsf(va);
-        if (kindB) vb = fabsf(vb);
-        if (oA) oA[ia] = va;
-        if (oB) oB[ib] = vb;
-        best_update(bA, va, ia);
-        if (a.pair_maps) best_update(bB, vb, ib);
-        else best_update(bA, vb, ib);
-    };
-    if (NX >= 512) {
-        // idx = tid + i*512: transform ff = (i*512)/NX and column xx = tid + (i*512)%NX are compile-time + tid
-        constexpr int IT = FPC * NX / 512;
-        const int ptid = pad16(tid);
+        const unsigned rowA = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX;
+        const unsigned rowB = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX;
 #pragma unroll
-        for (int i = 0; i < IT; ++i) {
-            constexpr int dummy = 0; (void)dummy;
-            const int ff = (i * 512) / NX, xo = (i * 512) % NX;
-            emit(ff, tid + xo, sm[ff * FS + ptid + (xo / 16) * 17]);
-        }
-    } else {
-        for (int idx = tid; idx < FPC * NX; idx += 512) {
-            const int ff = idx / NX, xx = idx % NX;
-            emit(ff, xx, sm[ff * FS + pad16(xx)]);
+        for (int s = 0; s < 16; ++s) {
+            const unsigned cs = (unsigned)(j + TPF * ((s + 8) & 15));   // fftshift along x
+            const unsigned ia = rowA + cs, ib = rowB + cs;
+            float va = x[s].x, vb = x[s].y;
+            if (a.kindA) va = fabsf(va);
+            if (kindB) vb = fabsf(vb);
+            if (oA) oA[ia] = va;
+            if (oB) oB[ib] = vb;
+            best_update(bA, va, ia);
+            if (a.pair_maps) best_update(bB, vb, ib);
+            else best_update(bA, vb, ib);
         }
     }
     // argmax partials (first occurrence in row-major order of the shifted map wins ties)
@@ -985,12 +949,12 @@ int ensure_theta(b4d_ctx* ctx) {
 
 // rows forward for a batch, pilot included
 int run_rows_fwd(b4d_ctx* ctx, const float* stack, int64_t T, int ny, int nx, const float* gain, const float* dark,
-                 Work& w, bool use_pilot) {
+                 Work& w, bool use_pilot, bool pilot_ready = false) {
     int rc;
-    if (use_pilot) { rc = b4d_frame_pilot_launch(ctx, stack, T, (int64_t)ny * nx, gain, dark, w.pilot); if (rc) return rc; }
+    if (use_pilot && !pilot_ready) { rc = b4d_frame_pilot_launch(ctx, stack, T, (int64_t)ny * nx, gain, dark, w.pilot); if (rc) return rc; }
     RowsFwdArgs a;
     a.stack = stack; a.gain = gain; a.dark = dark; a.pilot = use_pilot ? w.pilot : nullptr; a.H = w.H; a.ny = ny;
-    rc = get_twiddles(ctx, nx, &a.tw);
+    rc = get_twiddle_bases(ctx, nx, &a.tw);
     if (rc) return rc;
     DISPATCH_N(nx, rc = launch_rows_fwd<N_>(ctx, a, T));
     return rc;
@@ -1011,7 +975,7 @@ int run_cols(b4d_ctx* ctx, ColsArgs& c, int64_t T, int ny) {
 }
 
 int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx) {
-    int rc = get_twiddles(ctx, nx, &r.tw);
+    int rc = get_twiddle_bases(ctx, nx, &r.tw);
     if (rc) return rc;
     DISPATCH_N(nx, rc = launch_rows_inv<N_>(ctx, r, T, nullptr));
     return rc;
@@ -1031,7 +995,6 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
 
 void b4d_fft_release(b4d_ctx* ctx) {
     if (!ctx->fft) return;
-    for (int i = 0; i < 5; ++i) if (ctx->fft->tw[i]) cudaFree(ctx->fft->tw[i]);
     for (int i = 0; i < 5; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
@@ -1326,14 +1289,16 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
 
 extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                   const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
-                                  double eps, double* fr_out, float* psd_out, float* ac_out, double* grain_out,
-                                  double* track_out) {
+                                  double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
+                                  int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
     int rc = check_fft_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
     if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: grain widths need square frames");
+    if (quant_out && (!nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0)))
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tail percentiles need 0 <= q_lo < q_hi <= 1 and nvalid_out");
     const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
     if (want_pc && (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tracking needs b4d_phase_set_reference for (%d, %d) frames", ny, nx);
@@ -1353,11 +1318,15 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
         float* acm = ac_out ? ac_out + (size_t)t0 * npix : (want_pc ? mag + npix * tc : mag);
         double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : fr;
-        if (fr_out || want_pc) {
-            if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp))) return rc;
+        const bool reduced = fr_out || want_pc || quant_out;
+        if (reduced) {
+            FrTails tl = {q_lo, q_hi, quant_out ? quant_out + 4 * t0 : nullptr, quant_out ? nvalid_out + t0 : nullptr};
+            if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp, quant_out ? &tl : nullptr,
+                                              w.pilot)))
+                return rc;
         }
         if (!(psd_out || want_ac || want_pc)) continue;
-        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true))) return rc;
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true, reduced))) return rc;
         ColsArgs c = cols_defaults(w, nx, true);
         c.psd_out = psd_out ? psd_out + (size_t)t0 * npix : nullptr;
         c.psd_scale = psd_scale;

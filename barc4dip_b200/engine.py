@@ -280,10 +280,14 @@ class PhaseTracker:
 def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | None = 65535.0, eps: float = 1e-6,
                    psd_scale: float | None = None, subpixel: bool = True, track_eps: float = 1e-9,
                    want_reductions: bool = True, want_psd: bool = True, want_autocorr: bool = True,
-                   want_grain: bool = True, want_tracking: bool = True, psd_out=None, ac_out=None):
+                   want_grain: bool = True, want_tracking: bool = True, psd_out=None, ac_out=None,
+                   tail_quantiles=None):
     """The fused north-star pass over an HBM-resident stack (see b4d_stack_pipeline in include/b4d.h).
 
     Tracking uses the reference most recently installed by a PhaseTracker on the same device.
+    tail_quantiles=(q_lo, q_hi) (fractions) adds the order statistics bracketing the two percentiles, collected in
+    the reduction pass: "quantiles" (T, 4) float32 and "n_valid" (T,) int64 (-1 = unresolved frame, see
+    resolve_tail_quantiles).
     Returns a dict with device tensors: reductions (T, FR_NCOLS), psd, autocorr, grain (T,4), tracking (T,4).
     """
     torch = require_cuda()
@@ -300,9 +304,46 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
     track = torch.empty((T, 4), dtype=torch.float64, device=dev) if want_tracking else None
     sat = float("nan") if saturation_value is None else float(saturation_value)
     scale = (1.0 / (float(nx) * float(ny))) if psd_scale is None else float(psd_scale)
+    quant = nvalid = None
+    q_lo = q_hi = 0.0
+    if tail_quantiles is not None:
+        q_lo, q_hi = float(tail_quantiles[0]), float(tail_quantiles[1])
+        quant = torch.empty((T, 4), dtype=torch.float32, device=dev)
+        nvalid = torch.empty((T,), dtype=torch.int64, device=dev)
     ctx.check(ctx.lib.b4d_stack_pipeline(ctx.handle, ptr(stack), T, ny, nx, ptr(gain), ptr(dark), sat, float(eps),
-                                         scale, int(bool(subpixel)), float(track_eps), ptr(fr),
-                                         ptr(psd_out if want_psd else None), ptr(ac_out if want_autocorr else None),
-                                         ptr(grain), ptr(track)), "b4d_stack_pipeline")
+                                         scale, int(bool(subpixel)), float(track_eps), q_lo, q_hi, ptr(fr), ptr(quant),
+                                         ptr(nvalid), ptr(psd_out if want_psd else None),
+                                         ptr(ac_out if want_autocorr else None), ptr(grain), ptr(track)),
+              "b4d_stack_pipeline")
     return {"reductions": fr, "psd": psd_out if want_psd else None, "autocorr": ac_out if want_autocorr else None,
-            "grain": grain, "tracking": track}
+            "grain": grain, "tracking": track, "quantiles": quant, "n_valid": nvalid}
+
+
+def frame_reductions_tails(stack, q_lo: float, q_hi: float, *, gain=None, dark=None,
+                           saturation_value: float | None = 65535.0, eps: float = 1e-6):
+    """Frame reductions + the tail order statistics of the same pass (b4d_frame_reductions_tails).
+    Returns device tensors (table (T, FR_NCOLS) f64, quantiles (T, 4) f32, n_valid (T,) i64)."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    ctx = get_context(_dev(stack))
+    dev = stack.device
+    fr = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=dev)
+    quant = torch.empty((T, 4), dtype=torch.float32, device=dev)
+    nvalid = torch.empty((T,), dtype=torch.int64, device=dev)
+    sat = float("nan") if saturation_value is None else float(saturation_value)
+    ctx.check(ctx.lib.b4d_frame_reductions_tails(ctx.handle, ptr(stack), T, ny, nx, ptr(gain), ptr(dark), sat, float(eps),
+                                                 float(q_lo), float(q_hi), ptr(fr), ptr(quant), ptr(nvalid)),
+              "b4d_frame_reductions_tails")
+    return fr, quant, nvalid
+
+
+def resolve_tail_quantiles(stack, quant, nvalid, q_lo: float, q_hi: float):
+    """Frames the fused tail collection flagged (n_valid == -1: the sample bracket missed, or the tails are not small)
+    are redone by the exact stand-alone select; `stack` must hold the corrected pixels of those frames.  In place."""
+    torch = require_cuda()
+    bad = torch.nonzero(nvalid < 0).flatten()
+    if bad.numel():
+        q, nv = select_quantiles(stack[bad].contiguous(), [q_lo, q_hi], return_device=True)
+        quant[bad] = q
+        nvalid[bad] = nv
+    return quant, nvalid

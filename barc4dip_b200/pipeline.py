@@ -82,18 +82,25 @@ class StackAnalyzer:
             }
         return self._stage
 
-    def run_device(self, dev_stack, *, psd_out=None, ac_out=None) -> dict:
+    def run_device(self, dev_stack, *, psd_out=None, ac_out=None, resolve_tails: bool = True) -> dict:
         """Analyse an HBM-resident (T, ny, nx) float32 stack; everything stays on the device."""
+        q_lo, q_hi = 0.05 / 100.0, 99.95 / 100.0      # amplitude(): percentile_minmax_range defaults
         res = engine.stack_pipeline(dev_stack, gain=self.gain, dark=self.dark, saturation_value=self.sat, eps=self.eps,
                                     subpixel=self.subpixel, want_psd=self.want_maps or psd_out is not None,
                                     want_autocorr=True, want_grain=True, want_tracking=self.tracker is not None,
-                                    psd_out=psd_out, ac_out=ac_out)
-        if self.want_contrast:
-            src = dev_stack
-            if self.gain is not None:      # percentiles need the corrected pixels materialised once
-                src = engine.flat_field(dev_stack, self.flat, self.dark, **self._ff)
-            res["quantiles"], res["n_valid"] = engine.select_quantiles(src, [0.05 / 100.0, 99.95 / 100.0],
-                                                                      return_device=True)
+                                    psd_out=psd_out, ac_out=ac_out,
+                                    tail_quantiles=(q_lo, q_hi) if self.want_contrast else None)
+        if self.want_contrast and resolve_tails:
+            # the tails are collected inside the reduction pass; a frame the sample bracket missed (n_valid == -1) is
+            # redone by the stand-alone exact select (host sync: one tiny D2H per chunk)
+            nv = res["n_valid"]
+            if bool((nv < 0).any()):
+                src = dev_stack
+                if self.gain is not None:  # the stand-alone select needs the corrected pixels materialised
+                    bad = (nv < 0).nonzero().flatten()
+                    src = dev_stack.clone()
+                    src[bad] = engine.flat_field(dev_stack[bad].contiguous(), self.flat, self.dark, **self._ff)
+                engine.resolve_tail_quantiles(src, res["quantiles"], nv, q_lo, q_hi)
         return res
 
     def run(self, stack, *, keep_maps_on_device: bool = False) -> dict:
@@ -153,7 +160,7 @@ class StackAnalyzer:
                     ao = maps_dev["ac"][a:b] if keep_maps_on_device else st["ac"][s][:n]
                 else:
                     po = ao = None
-                res = self.run_device(frames, psd_out=po, ac_out=ao)
+                res = self.run_device(frames, psd_out=po, ac_out=ao, resolve_tails=False)
                 fr_all[a:b].copy_(res["reductions"])
                 grain_all[a:b].copy_(res["grain"])
                 if track_all is not None:
@@ -171,6 +178,15 @@ class StackAnalyzer:
         for s_ in self._streams:
             s_.synchronize()
         ctx.use_current_stream()
+        if nv_all is not None and bool((nv_all < 0).any()):
+            # frames whose tails the fused collection did not resolve: exact stand-alone select on those frames only
+            bad = (nv_all < 0).nonzero().flatten()
+            frames = (src[bad.cpu()] if is_host else stack[bad]).to(self.device, dtype=torch.float32).contiguous()
+            if self.gain is not None:
+                frames = engine.flat_field(frames, self.flat, self.dark, **self._ff)
+            q, nv = engine.select_quantiles(frames, [0.05 / 100.0, 99.95 / 100.0], return_device=True)
+            q_all[bad] = q
+            nv_all[bad] = nv
 
         fr = fr_all.cpu().numpy()
         out = {"stats": blocks.moments_block(fr, self.sat), "gradient": blocks.gradient_block(fr),

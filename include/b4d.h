@@ -100,6 +100,15 @@ int b4d_frame_reductions(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
                          const float* gain, const float* dark,
                          double sat_value, double zero_eps, double* out);
 
+/*
+ * b4d_frame_reductions plus, from the same pass, the order statistics that bracket two tail percentiles
+ * (amplitude(): np.nanpercentile(img, 0.05 / 99.95), metrics/speckles.py:647).  quant_out / nvalid_out as in
+ * b4d_stack_pipeline.  Meant for small tails (each side of the frame up to ~0.3 % of the pixels).
+ */
+int b4d_frame_reductions_tails(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
+                               const float* gain, const float* dark, double sat_value, double zero_eps,
+                               double q_lo, double q_hi, double* out, float* quant_out, int64_t* nvalid_out);
+
 /* ---- exact order statistics ------------------------------------------------------------ */
 /*
  * For each frame, the k-th smallest finite value (0-based ranks, ascending) for every k in
@@ -208,18 +217,23 @@ int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, 
                     int subpixel, double eps, double* out);
 
 /*
- * The fused stack pass of the north-star pipeline: one read of every frame produces
- *   fr_out   (n_frames, B4D_FR_NCOLS)  frame reductions           (nullable)
- *   psd_out  (n_frames, ny, nx)        psd2d                      (nullable)
- *   ac_out   (n_frames, ny, nx)        autocorr2d (defaults)      (nullable)
- *   grain_out(n_frames, 4)             grain widths               (nullable, needs autocorr)
- *   track_out(n_frames, 4)             phase correlation vs the cached reference (nullable)
+ * The fused stack pass of the north-star pipeline: one call per chunk of frames produces
+ *   fr_out    (n_frames, B4D_FR_NCOLS)  frame reductions           (nullable)
+ *   quant_out (n_frames, 4) float32     the two order statistics bracketing the q_lo and the q_hi percentile
+ *                                       (numpy 'linear' neighbours v[floor(h)], v[floor(h)+1]; amplitude(),
+ *                                       metrics/speckles.py:647, utils/range.py:51-54), collected inside the
+ *                                       reduction pass; nvalid_out (n_frames) int64 = non-NaN pixels, or -1 for a
+ *                                       frame whose tails were not resolved (run b4d_select_ranks on it). (nullable)
+ *   psd_out   (n_frames, ny, nx)        psd2d                      (nullable)
+ *   ac_out    (n_frames, ny, nx)        autocorr2d (defaults)      (nullable)
+ *   grain_out (n_frames, 4)             grain widths               (nullable, needs autocorr)
+ *   track_out (n_frames, 4)             phase correlation vs the cached reference (nullable)
  */
 int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
-                       const float* gain, const float* dark,
-                       double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
-                       double* fr_out, float* psd_out, float* ac_out, double* grain_out,
-                       double* track_out);
+                       const float* gain, const float* dark, double sat_value, double zero_eps,
+                       float psd_scale, int subpixel, double eps, double q_lo, double q_hi,
+                       double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out,
+                       double* grain_out, double* track_out);
 
 #ifdef __cplusplus
 }

@@ -185,3 +185,69 @@ def test_temporal_moments_chunked_equals_single(eng):
     for k in want:
         np.testing.assert_allclose(many[k], one[k], rtol=1e-5, atol=1e-6)   # fp32 batches fall on other frames
         np.testing.assert_allclose(many[k], want[k], rtol=RTOL, atol=1e-6)
+
+
+def _tail_brackets(frame, q):
+    f = frame.ravel().astype(np.float32)
+    s = np.sort(f[~np.isnan(f)])
+    n = s.size
+    h = n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0
+    lo = int(np.clip(np.floor(h), 0, n - 1))
+    return s[lo], s[min(lo + 1, n - 1)], n
+
+
+@pytest.mark.parametrize("shape", [(3, 512, 512), (2, 1024, 1024), (1, 256, 2048)])
+def test_fused_tail_percentiles_exact(eng, shape):
+    """The order statistics collected inside the reduction pass are the exact np.nanpercentile neighbours."""
+    rng = np.random.default_rng(21)
+    stack = rng.exponential(1000.0, size=shape).astype(np.float32)
+    stack[0, 0, :5] = np.nan
+    stack[0, 3, 7] = -np.inf
+    stack[0, 5, 9] = np.inf
+    stack[0, 1, 1] = -3.5
+    stack[-1, 10, :40] = 0.0                       # zero candidates (slow path of the screening)
+    stack[-1, 11, :40] = 70000.0                   # saturated pixels
+    q_lo, q_hi = 0.0005, 0.9995
+    tab, quant, nv = eng.frame_reductions_tails(eng.as_stack(stack), q_lo, q_hi)
+    tab, quant, nv = tab.cpu().numpy(), quant.cpu().numpy(), nv.cpu().numpy()
+    ref_tab = eng.frame_reductions(eng.as_stack(stack))
+    np.testing.assert_allclose(tab, ref_tab, rtol=0, atol=0, equal_nan=True)      # same kernel with and without the tails
+    for t in range(shape[0]):
+        a0, a1, n = _tail_brackets(stack[t], q_lo)
+        b0, b1, _ = _tail_brackets(stack[t], q_hi)
+        assert nv[t] == n
+        assert (quant[t, 0], quant[t, 1], quant[t, 2], quant[t, 3]) == (a0, a1, b0, b1)
+        lo = eng.quantile_from_bracket(quant[t, 0], quant[t, 1], int(nv[t]), q_lo)
+        hi = eng.quantile_from_bracket(quant[t, 2], quant[t, 3], int(nv[t]), q_hi)
+        want = np.nanpercentile(stack[t].astype(np.float64), [100 * q_lo, 100 * q_hi])
+        np.testing.assert_allclose([lo, hi], want, rtol=1e-6)
+
+
+def test_fused_tail_percentiles_flag_and_fallback(eng):
+    """A frame whose tails are not small (constant frame: every pixel is a candidate) is flagged, never wrong."""
+    const = np.full((2, 512, 512), 5.0, dtype=np.float32)
+    const[1] = np.random.default_rng(2).normal(100.0, 5.0, size=(512, 512)).astype(np.float32)
+    d = eng.as_stack(const)
+    _, quant, nv = eng.frame_reductions_tails(d, 0.0005, 0.9995)
+    assert int(nv[0]) == -1 and int(nv[1]) == 512 * 512
+    eng.resolve_tail_quantiles(d, quant, nv, 0.0005, 0.9995)
+    assert int(nv[0]) == 512 * 512 and tuple(quant[0].cpu().numpy()) == (5.0, 5.0, 5.0, 5.0)
+
+
+def test_fused_tail_percentiles_with_flat_field(eng):
+    import torch
+    from barc4dip_b200 import synth
+    raw, flat, dark = synth.flatfield_case(2, 512, seed=33, dead_frac=2e-4)
+    den = flat - dark
+    eps = 1e-6 * float(np.median(den))
+    s = float(np.median(den[den > eps]))
+    d_raw, d_flat, d_dark = (eng.as_stack(raw), torch.from_numpy(flat).cuda(), torch.from_numpy(dark).cuda())
+    gain = eng.flat_gain(d_flat, d_dark, eps=eps, scale_value=s)
+    _, quant, nv = eng.frame_reductions_tails(d_raw, 0.0005, 0.9995, gain=gain, dark=d_dark)
+    corr = eng.flat_field(d_raw, d_flat, d_dark, eps=eps, scale_value=s, apply_scale=True)
+    want, nv2 = eng.select_quantiles(corr, [0.0005, 0.9995], return_device=True)
+    ok = (nv >= 0)
+    assert bool(ok.any())
+    # the fused loader evaluates (raw - dark) * gain, the materialising kernel (raw - dark) / den * s: 1-ulp differences
+    np.testing.assert_allclose(quant[ok].cpu().numpy(), want[ok].cpu().numpy(), rtol=1e-6)
+    assert bool((nv[ok] == nv2[ok]).all())
