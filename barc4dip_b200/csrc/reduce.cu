@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 2) frame_reduce_kernel(FrArgs a
 constexpr int F2_WARPS = 8;
 constexpr int F2_STRIP = 120;
 constexpr int F2_BAND = 64;
-constexpr int F2_CAP = 1024;
+constexpr int F2_CAP = 1024;      // staged tail candidates per CTA and tail
+constexpr int F2_QCAP = 1024;     // queued pixel quads (lanes whose min / max crossed a threshold) per CTA
 
 struct Fr2Args {
     const float* stack;
@@ -324,7 +325,7 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 template <bool HAS_GAIN>
 __device__ __forceinline__ float4 fetch2(const Fr2Args& a, const float* frame, int r, int j0, bool ld_ok) {
     const int rr = min(max(r, 0), a.ny - 1);          // "reflect" = duplicate the edge sample
-    const size_t off = (size_t)rr * a.nx + j0;
+    const unsigned off = (unsigned)rr * (unsigned)a.nx + (unsigned)j0;   // a frame has fewer than 2^32 pixels
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ld_ok) {
         v = __ldcs(reinterpret_cast<const float4*>(frame + off));
@@ -340,7 +341,7 @@ __device__ __forceinline__ float4 fetch2(const Fr2Args& a, const float* frame, i
 
 template <bool TAILS>
 __device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, float K, bool edge_l, bool edge_r, bool count,
-                                        float thr_lo, float thr_hi, Acc2& acc, float* s_buf, unsigned* s_cnt) {
+                                        float thr_lo, float thr_hi, Acc2& acc, float4* s_queue, unsigned* s_qn) {
     Win2 w;
     w.q0 = __fadd2_rn(f2(raw.x, raw.y), f2(-K, -K));
     w.q1 = __fadd2_rn(f2(raw.z, raw.w), f2(-K, -K));
@@ -386,14 +387,11 @@ __device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, floa
             }
         }
         if (TAILS) {
+            // rare (~1.6 % of the lanes): park the quad, the per-pixel tests run densely after the main loop
             const float mn = fminf(fminf(raw.x, raw.y), fminf(raw.z, raw.w));
             if (mn <= thr_lo || mx >= thr_hi) {
-                const float xs[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (xs[k] <= thr_lo) { const unsigned p = atomicAdd(s_cnt, 1u); if (p < F2_CAP) s_buf[p] = xs[k]; }
-                    if (xs[k] >= thr_hi) { const unsigned p = atomicAdd(s_cnt + 1, 1u); if (p < F2_CAP) s_buf[F2_CAP + p] = xs[k]; }
-                }
+                const unsigned p = atomicAdd(s_qn, 1u);
+                if (p < F2_QCAP) s_queue[p] = raw;
             }
         }
     }
@@ -447,12 +445,15 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
     const float K = __ldg(a.pilot + t);
     float thr_lo = -INFINITY, thr_hi = INFINITY;
     __shared__ float s_buf[TAILS ? 2 * F2_CAP : 2];
+    __shared__ float4 s_queue[TAILS ? F2_QCAP : 1];
     __shared__ unsigned s_cnt[2];
     __shared__ unsigned s_base[2];
+    __shared__ unsigned s_qn;
     if (TAILS) {
         thr_lo = __ldg(a.thr + 2 * t);
         thr_hi = __ldg(a.thr + 2 * t + 1);
         if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+        if (threadIdx.x == 2) s_qn = 0u;
         __syncthreads();
     }
 
@@ -474,8 +475,8 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
         const float4 rawm = fetch2<HAS_GAIN>(a, frame, r0 - 1, j0, ld_ok), raw0 = fetch2<HAS_GAIN>(a, frame, r0, j0, ld_ok);
 #pragma unroll
         for (int q = 0; q < 4; ++q) raw[q] = fetch2<HAS_GAIN>(a, frame, r0 + 1 + q, j0, ld_ok);
-        Win2 up = finish2<TAILS>(a, rawm, K, edge_l, edge_r, false, thr_lo, thr_hi, acc, s_buf, s_cnt);
-        Win2 mid = finish2<TAILS>(a, raw0, K, edge_l, edge_r, own, thr_lo, thr_hi, acc, s_buf, s_cnt);
+        Win2 up = finish2<TAILS>(a, rawm, K, edge_l, edge_r, false, thr_lo, thr_hi, acc, s_queue, &s_qn);
+        Win2 mid = finish2<TAILS>(a, raw0, K, edge_l, edge_r, own, thr_lo, thr_hi, acc, s_queue, &s_qn);
         for (int rb = r0; rb < r1; rb += 4) {
             // the four rows fetched one iteration ago are consumed while the next four are already in flight
             float4 cur[4];
@@ -487,12 +488,12 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const Win2 nxt = finish2<TAILS>(a, cur[q], K, edge_l, edge_r, own && (rb + 1 + q < r1), thr_lo, thr_hi, acc, s_buf, s_cnt);
+                const Win2 nxt = finish2<TAILS>(a, cur[q], K, edge_l, edge_r, own && (rb + 1 + q < r1), thr_lo, thr_hi, acc, s_queue, &s_qn);
                 if (own && rb + q < r1) stencil2(up, mid, nxt, acc);
                 up = mid;
                 mid = nxt;
             }
-            if (((rb - r0) & 4) != 0 || rb + 4 >= r1) {   // fold fp32 partials into fp64 every 8 rows
+            if (((rb - r0) & 12) == 12 || rb + 4 >= r1) {   // fold fp32 partials into fp64 every 16 rows (32 values each)
                 d[0] += acc.nfin; d[1] += (double)acc.s1.x + (double)acc.s1.y; d[2] += (double)acc.s2.x + (double)acc.s2.y;
                 d[3] += (double)acc.s3.x + (double)acc.s3.y; d[4] += (double)acc.s4.x + (double)acc.s4.y;
                 d[5] += acc.nzero; d[6] += acc.nsat;
@@ -518,8 +519,21 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
         a.partials[((size_t)t * gridDim.x + blockIdx.x) * FR_NACC + threadIdx.x] = v;
     }
     if (TAILS) {
+        // per-pixel tests of the parked quads (the barrier above made the queue visible)
+        const unsigned nq = min(s_qn, (unsigned)F2_QCAP);
+        for (unsigned i = threadIdx.x; i < nq; i += blockDim.x) {
+            const float4 v = s_queue[i];
+            const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (xs[k] <= thr_lo) { const unsigned p = atomicAdd(s_cnt, 1u); if (p < F2_CAP) s_buf[p] = xs[k]; }
+                if (xs[k] >= thr_hi) { const unsigned p = atomicAdd(s_cnt + 1, 1u); if (p < F2_CAP) s_buf[F2_CAP + p] = xs[k]; }
+            }
+        }
+        __syncthreads();
         // flush the staged candidates: one reservation per CTA and tail
         if (threadIdx.x < 2) {
+            if (s_qn > F2_QCAP) a.flag[t] = 1;
             const unsigned n = s_cnt[threadIdx.x];
             unsigned base = 0;
             if (n > F2_CAP) a.flag[t] = 1;

@@ -176,21 +176,29 @@ __global__ void __launch_bounds__(1024) sel_sample_kernel(const float* __restric
     }
 }
 
-// One pass over the frame. A CTA works through chunks of COL_CHUNK elements. Phase 1 screens in float space
-// (key order == float order) and counts, per lane, the valid elements, the elements below each bracket and the
-// candidates inside it. A warp scan + a tiny CTA scan turn the per-lane counts into write offsets and ONE global
-// atomic per chunk and bracket reserves the range in the frame's candidate list; phase 2 re-tests the lane's
-// elements and writes the candidates' keys straight to their slots.
+// One pass over the frame. A CTA works through chunks of COL_CHUNK elements and keeps, per bracket, the number of
+// elements below it and a shared-memory stage of the candidates' keys: the lanes of a warp that hold a candidate are
+// compacted by one ballot and one shared atomic per element slot. At the end the stage is flushed with ONE global
+// reservation per bracket; the flush also counts the candidates into a 2048-bin histogram over the bracket, which
+// lets sel_final_kernel go straight to the bins that hold the wanted ranks.
 constexpr int COL_THREADS = 256;
-constexpr int COL_WARPS = COL_THREADS / 32;
 constexpr int COL_VEC = 4;
 constexpr int COL_ITERS = 4;
 constexpr int COL_CHUNK = COL_THREADS * COL_VEC * COL_ITERS;     // 4096 elements
+constexpr int COL_STAGE = 4096;                                  // staged candidates per CTA and bracket
+
+// bin of a candidate inside its bracket [L, U]: (key - L) >> shift with the smallest shift that fits SEL_BINS bins
+__device__ __forceinline__ int bracket_shift(unsigned L, unsigned U) {
+    const int width = 32 - __clz((U - L) | 1u);
+    return width > 11 ? width - 11 : 0;
+}
 
 __global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* __restrict__ stack, int64_t n, int n_q,
                                                                   int use_abs, SelFast* __restrict__ st,
-                                                                  unsigned* __restrict__ cand, unsigned cap) {
-    __shared__ unsigned wtot[SEL_MAXQ][COL_WARPS], woff[SEL_MAXQ][COL_WARPS], gbase[SEL_MAXQ], btot[SEL_MAXQ];
+                                                                  unsigned* __restrict__ cand, unsigned cap,
+                                                                  unsigned* __restrict__ hist) {
+    __shared__ unsigned s_keys[SEL_MAXQ][COL_STAGE];
+    __shared__ unsigned s_n[SEL_MAXQ], s_base[SEL_MAXQ];
     __shared__ unsigned long long tot[3];
     const int64_t t = blockIdx.y;
     const float* f = stack + t * n;
@@ -203,9 +211,11 @@ __global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* _
         Uf[q] = s->U[q] == 0xfffffffeu ? INFINITY : value_of(s->U[q], use_abs);
     }
     unsigned nvalid = 0, below[SEL_MAXQ] = {0u, 0u};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
     if (threadIdx.x < 3) tot[threadIdx.x] = 0ull;
+    if (threadIdx.x < SEL_MAXQ) s_n[threadIdx.x] = 0u;
+    __syncthreads();
     const int64_t nchunks = (n + COL_CHUNK - 1) / COL_CHUNK;
     for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const int64_t e0 = ch * COL_CHUNK;
@@ -220,72 +230,66 @@ __global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* _
 #pragma unroll
                 for (int k = 0; k < COL_VEC; ++k) v[it][k] = (e + k < n) ? __ldcs(f + e + k) : __uint_as_float(0x7fc00000u);
             }
-            if (use_abs) {
+        }
+        if (use_abs) {
+#pragma unroll
+            for (int it = 0; it < COL_ITERS; ++it)
 #pragma unroll
                 for (int k = 0; k < COL_VEC; ++k) v[it][k] = fabsf(v[it][k]);
-            }
         }
-        unsigned c[SEL_MAXQ] = {0u, 0u};
+        // NaN census per quad: the sum of magnitudes is NaN iff one of them is
 #pragma unroll
-        for (int it = 0; it < COL_ITERS; ++it)
-#pragma unroll
-            for (int k = 0; k < COL_VEC; ++k) {
-                const float x = v[it][k];
-                nvalid += (x == x);
-#pragma unroll
-                for (int q = 0; q < SEL_MAXQ; ++q)
-                    if (q < n_q) {
-                        below[q] += (x < Lf[q]);
-                        c[q] += (x >= Lf[q] && x <= Uf[q]);
-                    }
-            }
-        unsigned excl[SEL_MAXQ];
+        for (int it = 0; it < COL_ITERS; ++it) {
+            const float sm4 = (fabsf(v[it][0]) + fabsf(v[it][1])) + (fabsf(v[it][2]) + fabsf(v[it][3]));
+            if (sm4 == sm4) nvalid += 4;
+            else nvalid += (v[it][0] == v[it][0]) + (v[it][1] == v[it][1]) + (v[it][2] == v[it][2]) + (v[it][3] == v[it][3]);
+        }
 #pragma unroll
         for (int q = 0; q < SEL_MAXQ; ++q) {
-            unsigned incl = c[q];
+            if (q >= n_q) continue;
+            // per-lane census, one warp scan and one shared atomic per chunk and bracket, then the lane's own writes
+            const float L = Lf[q], U = Uf[q];
+            unsigned c = 0;
+#pragma unroll
+            for (int it = 0; it < COL_ITERS; ++it)
+#pragma unroll
+                for (int k = 0; k < COL_VEC; ++k) {
+                    const float x = v[it][k];
+                    below[q] += (x < L);
+                    c += (x >= L && x <= U);
+                }
+            unsigned incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += u;
             }
-            excl[q] = incl - c[q];
-            if (lane == 31) wtot[q][warp] = incl;
-        }
-        __syncthreads();
-        if (threadIdx.x < SEL_MAXQ) {
-            const int q = threadIdx.x;
-            unsigned run = 0;
+            const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtot) {
+                unsigned base = 0;
+                if (lane == 31) base = atomicAdd(&s_n[q], wtot);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                if (c) {
+                    unsigned pos = base + incl - c;
 #pragma unroll
-            for (int w = 0; w < COL_WARPS; ++w) { woff[q][w] = run; run += wtot[q][w]; }
-            btot[q] = run;
-            if (run && q < n_q) gbase[q] = atomicAdd(&s->ncand[q], run);
-        }
-        __syncthreads();
+                    for (int it = 0; it < COL_ITERS; ++it)
 #pragma unroll
-        for (int q = 0; q < SEL_MAXQ; ++q) {
-            if (q < n_q && c[q]) {
-                unsigned pos = gbase[q] + woff[q][warp] + excl[q];
-                unsigned* dst = cand + ((size_t)t * SEL_MAXQ + q) * cap;
-#pragma unroll
-                for (int it = 0; it < COL_ITERS; ++it)
-#pragma unroll
-                    for (int k = 0; k < COL_VEC; ++k) {
-                        const float x = v[it][k];
-                        if (x >= Lf[q] && x <= Uf[q]) {
-                            if (pos < cap) dst[pos] = key_of(x, use_abs);
-                            ++pos;
+                        for (int k = 0; k < COL_VEC; ++k) {
+                            const float x = v[it][k];
+                            if (x >= L && x <= U) {
+                                if (pos < COL_STAGE) s_keys[q][pos] = key_of(x, use_abs);
+                                ++pos;
+                            }
                         }
-                    }
+                }
             }
         }
-        __syncthreads();
     }
     for (int o = 16; o > 0; o >>= 1) {
         nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
         below[0] += __shfl_xor_sync(0xffffffffu, below[0], o);
         below[1] += __shfl_xor_sync(0xffffffffu, below[1], o);
     }
-    __syncthreads();
     if (lane == 0) {
         atomicAdd(&tot[0], (unsigned long long)nvalid);
         atomicAdd(&tot[1], (unsigned long long)below[0]);
@@ -297,40 +301,124 @@ __global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* _
         atomicAdd(&s->below[0], tot[1]);
         atomicAdd(&s->below[1], tot[2]);
     }
+    // flush: one reservation per bracket, keys + their histogram
+    if (threadIdx.x < SEL_MAXQ && threadIdx.x < n_q) {
+        const int q = threadIdx.x;
+        const unsigned cnt = s_n[q];
+        unsigned base = 0;
+        if (cnt > COL_STAGE) s->need_fallback = 1;
+        else if (cnt) base = atomicAdd(&s->ncand[q], cnt);
+        s_base[q] = base;
+    }
+    __syncthreads();
+    for (int q = 0; q < n_q; ++q) {
+        const unsigned cnt = min(s_n[q], (unsigned)COL_STAGE), base = s_base[q];
+        const unsigned L = s->L[q];
+        const int shift = bracket_shift(L, s->U[q]);
+        unsigned* dst = cand + ((size_t)t * SEL_MAXQ + q) * cap;
+        unsigned* h = hist + ((size_t)t * SEL_MAXQ + q) * SEL_BINS;
+        for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const unsigned key = s_keys[q][i];
+            if (base + i < cap) dst[base + i] = key;
+            atomicAdd(h + ((key - L) >> shift), 1u);
+        }
+    }
 }
 
+// Final ranks of one frame from its candidate lists. The histogram of the bracket names the bin of each wanted rank;
+// one pass over the candidates gathers the keys of those bins (a few dozen) into shared memory, where the ranks are
+// resolved by the bracket select. Frames whose bracket missed (or whose lists / bins overflowed) are flagged.
+constexpr int FIN_CAP = 4096;
 __global__ void __launch_bounds__(1024) sel_final_kernel(SelFast* __restrict__ st, const unsigned* __restrict__ cand, unsigned cap,
-                                                         int n_q, const double* __restrict__ quant, int use_abs,
+                                                         const unsigned* __restrict__ hist, int n_q,
+                                                         const double* __restrict__ quant, int use_abs,
                                                          float* __restrict__ out, long long* __restrict__ n_valid_out,
                                                          int* __restrict__ need) {
-    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned shist[SEL_BINS];
     __shared__ unsigned bc[34];
+    __shared__ unsigned s_keys[FIN_CAP];
+    __shared__ unsigned s_n;
+    __shared__ unsigned s_bin[2], s_before[2];
     const int64_t t = blockIdx.x;
     SelFast* s = st + t;
     const unsigned long long nv = s->n_valid;
-    bool ok = nv > 0;
+    bool ok = nv > 0 && !s->need_fallback;
     long long lo[SEL_MAXQ], hi[SEL_MAXQ];
     for (int q = 0; q < n_q; ++q) {
         target_ranks(nv, quant[q], lo[q], hi[q]);
         const long long b = (long long)s->below[q], c = (long long)s->ncand[q];
         ok = ok && c <= (long long)cap && lo[q] >= b && hi[q] < b + c;
     }
-    if (!ok) {
-        if (threadIdx.x == 0) { need[t] = 1; if (n_valid_out) n_valid_out[t] = (long long)nv; }
-        return;
-    }
-    for (int q = 0; q < n_q; ++q) {
-        const unsigned* keys = cand + ((size_t)t * SEL_MAXQ + q) * cap;
-        const unsigned c = s->ncand[q];
-        const unsigned a = cta_bracket_select(keys, c, (unsigned)(lo[q] - (long long)s->below[q]), s->L[q], s->U[q], hist, bc);
-        const unsigned b = (hi[q] == lo[q]) ? a
-                         : cta_bracket_select(keys, c, (unsigned)(hi[q] - (long long)s->below[q]), s->L[q], s->U[q], hist, bc);
-        if (threadIdx.x == 0) {
-            out[t * 2 * n_q + 2 * q] = value_of(a, use_abs);
-            out[t * 2 * n_q + 2 * q + 1] = value_of(b, use_abs);
+    float res[2 * SEL_MAXQ];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = 0; q < n_q && ok; ++q) {
+        const unsigned L = s->L[q], U = s->U[q], c = s->ncand[q];
+        const int shift = bracket_shift(L, U);
+        const unsigned ra = (unsigned)(lo[q] - (long long)s->below[q]), rb = (unsigned)(hi[q] - (long long)s->below[q]);
+        // exclusive scan of the bracket histogram (2 bins per thread), locate the bins of both ranks
+        const unsigned* h = hist + ((size_t)t * SEL_MAXQ + q) * SEL_BINS;
+        const unsigned h0 = h[2 * threadIdx.x], h1 = h[2 * threadIdx.x + 1];
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
+        __syncthreads();
+        if (lane == 31) bc[warp] = incl;
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = bc[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            bc[lane] = w;
+        }
+        __syncthreads();
+        const unsigned before = (warp ? bc[warp - 1] : 0u) + incl - (h0 + h1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const unsigned rk = r ? rb : ra;
+            if (rk >= before && rk < before + h0) { s_bin[r] = 2 * threadIdx.x; s_before[r] = before; }
+            else if (rk >= before + h0 && rk < before + h0 + h1) { s_bin[r] = 2 * threadIdx.x + 1; s_before[r] = before + h0; }
+        }
+        __syncthreads();
+        const unsigned bin_a = s_bin[0], bin_b = s_bin[1];
+        unsigned ka, kb;
+        if (shift == 0) {                     // one key per bin: the bin is the answer
+            ka = L + bin_a;
+            kb = L + bin_b;
+        } else {
+            const unsigned* keys = cand + ((size_t)t * SEL_MAXQ + q) * cap;
+            for (unsigned i = threadIdx.x; i < c; i += blockDim.x) {
+                const unsigned key = keys[i], b = (key - L) >> shift;
+                if (b == bin_a || b == bin_b) {
+                    const unsigned p = atomicAdd(&s_n, 1u);
+                    if (p < FIN_CAP) s_keys[p] = key;
+                }
+            }
+            __syncthreads();
+            const unsigned m = s_n;
+            if (m > FIN_CAP) { ok = false; break; }      // heavy ties inside one bin: the radix path resolves them
+            // ranks inside the gathered set: the keys of bin_a precede those of bin_b
+            const unsigned la = ra - s_before[0];
+            const unsigned lb = bin_b == bin_a ? rb - s_before[0] : h[bin_a] + (rb - s_before[1]);
+            const unsigned Lb = L + (bin_a << shift), Ub = L + (((bin_b + 1u) << shift) - 1u);
+            ka = cta_bracket_select(s_keys, m, la, Lb, Ub < Lb ? 0xffffffffu : Ub, shist, bc);
+            kb = (rb == ra) ? ka : cta_bracket_select(s_keys, m, lb, Lb, Ub < Lb ? 0xffffffffu : Ub, shist, bc);
+        }
+        res[2 * q] = value_of(ka, use_abs);
+        res[2 * q + 1] = value_of(kb, use_abs);
     }
-    if (threadIdx.x == 0) { need[t] = 0; if (n_valid_out) n_valid_out[t] = (long long)nv; }
+    if (threadIdx.x == 0) {
+        need[t] = ok ? 0 : 1;
+        if (n_valid_out) n_valid_out[t] = (long long)nv;
+        if (ok)
+            for (int i = 0; i < 2 * n_q; ++i) out[t * 2 * n_q + i] = res[i];
+    }
 }
 
 // =================================================================================================
@@ -629,15 +717,17 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
         const size_t fast_bytes = ((size_t)tc * sizeof(SelFast) + 255) & ~size_t(255);
         const size_t need_bytes = ((size_t)tc * sizeof(int) + 255) & ~size_t(255);
         const size_t cand_bytes = (size_t)tc * SEL_MAXQ * cap * sizeof(unsigned);
-        int rc = b4d_scratch(ctx, SCR_SELECT, hist_bytes + st_bytes + fast_bytes + need_bytes + cand_bytes, &p);
+        const size_t bh_bytes = fast ? (size_t)tc * SEL_MAXQ * SEL_BINS * sizeof(unsigned) : 0;   // bracket histograms
+        int rc = b4d_scratch(ctx, SCR_SELECT, hist_bytes + st_bytes + fast_bytes + need_bytes + bh_bytes + cand_bytes, &p);
         if (rc) return rc;
         char* base = static_cast<char*>(p);
         unsigned* hist = reinterpret_cast<unsigned*>(base);
         SelState* st = reinterpret_cast<SelState*>(base + hist_bytes);
         SelFast* sf = reinterpret_cast<SelFast*>(base + hist_bytes + st_bytes);
         int* need = reinterpret_cast<int*>(base + hist_bytes + st_bytes + fast_bytes);
-        unsigned* cand = reinterpret_cast<unsigned*>(base + hist_bytes + st_bytes + fast_bytes + need_bytes);
-        B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hist_bytes + st_bytes + fast_bytes + need_bytes, ctx->stream));
+        unsigned* bhist = reinterpret_cast<unsigned*>(base + hist_bytes + st_bytes + fast_bytes + need_bytes);
+        unsigned* cand = reinterpret_cast<unsigned*>(base + hist_bytes + st_bytes + fast_bytes + need_bytes + bh_bytes);
+        B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hist_bytes + st_bytes + fast_bytes + need_bytes + bh_bytes, ctx->stream));
         const float* s0 = stack + t0 * n;
         float* o0 = out + t0 * 2 * n_q;
         long long* nv0 = n_valid ? reinterpret_cast<long long*>(n_valid) + t0 : nullptr;
@@ -655,10 +745,10 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
             if ((int64_t)bpf * tc > capb) bpf = (int)((capb + tc - 1) / tc);
             if (bpf < 1) bpf = 1;
             { ProfScope ps(ctx, KC_SELECT_COLLECT);
-              sel_collect_kernel<<<dim3((unsigned)bpf, (unsigned)tc), 256, 0, ctx->stream>>>(s0, n, n_q, use_abs, sf, cand, cap); }
+              sel_collect_kernel<<<dim3((unsigned)bpf, (unsigned)tc), 256, 0, ctx->stream>>>(s0, n, n_q, use_abs, sf, cand, cap, bhist); }
             B4D_LAUNCH_CHECK(ctx);
             { ProfScope ps(ctx, KC_SELECT_FINAL);
-              sel_final_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(sf, cand, cap, n_q, q_dev, use_abs, o0, nv0, need); }
+              sel_final_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(sf, cand, cap, bhist, n_q, q_dev, use_abs, o0, nv0, need); }
             B4D_LAUNCH_CHECK(ctx);
         }
         // frames the bracket did not resolve (or every frame when they are small) take the three-pass radix select;
