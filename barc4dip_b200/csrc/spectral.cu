@@ -203,7 +203,10 @@ __device__ __forceinline__ void spec_accumulate(SpecAcc& s, float P, int ky, int
 
 __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
     if (whiten) {
-        const float inv = __frcp_rn(sqrtf(G.x * G.x + G.y * G.y) + eps);
+        // 1 / (|G| + eps) from MUFU.RSQ and MUFU.RCP (a few ulp; the reference divides in float32 as well)
+        const float s2 = G.x * G.x + G.y * G.y;
+        const float mag = s2 > 0.f ? s2 * rsqrtf(s2) : 0.f;
+        const float inv = __fdividef(1.f, mag + eps);
         G.x *= inv;
         G.y *= inv;
     }
@@ -218,22 +221,22 @@ __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
 // share an SM and one's loads overlap the other's butterflies.
 template <int NY, int CW, bool SPEC, bool AC, bool PC>
 __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a) {
+    extern __shared__ float2 sm[];
+    __shared__ double red[32];
     constexpr int T = NY / 16;
     constexpr int NT = T * CW;
     constexpr int PL = padded_len(NY);
     constexpr int GS = T * TC;                        // global distance (float2) between a thread's consecutive elements
-    extern __shared__ float2 sm[];
     float2* A = sm;                                   // [PL][CW] exchange buffer
     float* Bp = reinterpret_cast<float*>(sm + PL * CW);   // [NY][CW] |F|^2 (AC && PC)
     float* Pns = Bp + NY * CW;                        // [NY] |F_nyquist|^2 (AC && PC, tile 0)
-    __shared__ double red[32];
 
     const int tid = threadIdx.x, c = tid % CW, j = tid / CW;
     const int tile = blockIdx.x, ntiles = gridDim.x;
     const int64_t t = blockIdx.y;
     const int nx = a.nx, hx = nx / 2, kx = tile * CW + c;
-    const bool tile0 = tile == 0;
-    const bool nyq_owner = tile0 && c == 0;
+    const bool TILE0 = tile == 0;                     // block-uniform: the CTA owns column 0
+    const bool nyq_owner = TILE0 && c == 0;
     // element s of this thread lives at g0 + s*GS inside a frame's blocked half spectrum
     const size_t g0 = (size_t)t * NY * hx + (size_t)(kx / TC) * NY * TC + (size_t)j * TC + (kx % TC);
 
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
 
     // ---- tile 0: column 0 carries C = F[:,0] + i F[:,nx/2]; publish it so that its owners can read C[-ky]
     float2* A0 = A;                                   // natural order, [NY]
-    if (tile0) {
+    if (TILE0) {
         __syncthreads();
         if (c == 0) {
 #pragma unroll
@@ -256,92 +259,121 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
         __syncthreads();
     }
 
-    // ---- one pass over the thread's own 16 elements: plain outputs, partial sums, product / |F|^2 into x[]
+    // ---- epilogue, two sweeps over the thread's own 16 elements so that the output pointers of the first and the
+    //      reference values of the second never compete for the 64 registers a thread has:
+    //      (1) plain outputs, partial sums, |F|^2 for the autocorrelation branch; (2) product with the reference.
     SpecAcc sp;
-    double acsum = 0.0;
-    float inv_s = 1.f;
-    if (PC && a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
+    float acsum = 0.f;                                // 16 terms in fp32, tiles and frames are summed in fp64
+    // column 0 of tile 0: F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i) with Cm = C[-ky]
+    auto unpack0 = [&](int s, float2& F, float2& Fn, float& dcshift) {
+        const int ky = j + s * T;
+        const float2 Cm = A0[(NY - ky) & (NY - 1)];
+        Fn = make_float2(0.5f * (F.y + Cm.y), -0.5f * (F.x - Cm.x));
+        F = make_float2(0.5f * (F.x + Cm.x), 0.5f * (F.y - Cm.y));
+        if (ky == 0) {
+            dcshift = F.x;
+            if (a.pilot) F.x += (float)((double)nx * (double)NY * (double)__ldg(a.pilot + t));
+            if (a.zero_dc) F = make_float2(0.f, 0.f);
+        }
+    };
     {
-        float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx : nullptr;
-        float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx : nullptr;
+        // shifted output rows: main (ky + NY/2) mod NY = j + T ((s + 8) & 15); mirror (NY/2 - ky) mod NY = (NY - j) +
+        // T (((8 - s) & 15) - 16), except s = 8 where it is (NY - j) mod NY. Both are "thread base + constant * T rows".
+        const size_t rstride = (size_t)T * nx;        // elements between output rows T apart
+        float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx + (size_t)j * nx + (kx + hx) : nullptr;
+        float* psdm = a.psd_out ? a.psd_out + (size_t)t * NY * nx + (size_t)(NY - j) * nx + (hx - kx) : nullptr;
+        float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx + (size_t)j * nx + (kx + hx) : nullptr;
+        float2* cplm = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx + (size_t)(NY - j) * nx + (hx - kx) : nullptr;
         float2* cj = a.conj_out ? a.conj_out + g0 : nullptr;
         float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
-        const float2* R = PC ? a.R + (size_t)t * a.r_stride + (g0 - (size_t)t * NY * hx) : nullptr;
-        const float2* Rn = PC ? a.Rnyq + (size_t)t * a.rnyq_stride : nullptr;
-        const bool mirror = kx >= 1;
-        const double wgt = mirror ? 2.0 : 1.0;
+        const bool mirror = !TILE0 || kx >= 1;
+        const float wgt = mirror ? 2.f : 1.f;
         const float ps = a.psd_scale;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
             const int ky = j + s * T;
+            const int um = (s + 8) & 15;                                                  // relative to row j
+            const int ur = s == 8 ? (j == 0 ? -16 : 0) : ((8 - s) & 15) - 16;             // relative to row NY - j
             float2 F = x[s];
-            float2 Rv = make_float2(0.f, 0.f);
-            if (PC) Rv = __ldg(R + s * GS);
             float2 Fn = make_float2(0.f, 0.f);
             float dcshift = 0.f;
-            if (nyq_owner) {
-                // F0[ky] = (C + conj(Cm))/2, Fn[ky] = (C - conj(Cm))/(2i) with Cm = C[-ky]
-                const float2 Cm = A0[(NY - ky) & (NY - 1)];
-                Fn = make_float2(0.5f * (F.y + Cm.y), -0.5f * (F.x - Cm.x));
-                F = make_float2(0.5f * (F.x + Cm.x), 0.5f * (F.y - Cm.y));
-                if (ky == 0) {
-                    dcshift = F.x;
-                    if (a.pilot) F.x += (float)((double)nx * (double)NY * (double)__ldg(a.pilot + t));
-                    if (a.zero_dc) F = make_float2(0.f, 0.f);
-                }
-            }
+            if (nyq_owner) unpack0(s, F, Fn, dcshift);
             const float P = F.x * F.x + F.y * F.y;
-            const int rs = (ky + NY / 2) & (NY - 1), rm = (NY / 2 - ky) & (NY - 1);
             if (psd) {
-                __stcs(psd + (size_t)rs * nx + kx + hx, P * ps);
-                if (mirror) __stcs(psd + (size_t)rm * nx + hx - kx, P * ps);
+                __stcs(psd + (ptrdiff_t)um * (ptrdiff_t)rstride, P * ps);
+                if (mirror) __stcs(psdm + (ptrdiff_t)ur * (ptrdiff_t)rstride, P * ps);
             }
             if (cpl) {
-                __stcs(cpl + (size_t)rs * nx + kx + hx, F);
-                if (mirror) __stcs(cpl + (size_t)rm * nx + hx - kx, cconj(F));
+                __stcs(cpl + (ptrdiff_t)um * (ptrdiff_t)rstride, F);
+                if (mirror) __stcs(cplm + (ptrdiff_t)ur * (ptrdiff_t)rstride, cconj(F));
             }
             if (cj) cj[s * GS] = cconj(F);
-            if (SPEC) spec_accumulate<NY>(sp, P * ps, ky, kx, nx, wgt, ky == 0 && kx == 0);
+            if (SPEC) spec_accumulate<NY>(sp, P * ps, ky, kx, nx, (double)wgt, TILE0 && ky == 0 && kx == 0);
             float Pa = P, Pn = 0.f;
             if (nyq_owner) {                          // the Nyquist column kx = nx/2 lands in shifted column 0
                 Pn = Fn.x * Fn.x + Fn.y * Fn.y;
-                if (psd) __stcs(psd + (size_t)rs * nx, Pn * ps);
-                if (cpl) __stcs(cpl + (size_t)rs * nx, Fn);
+                const size_t rs = (size_t)((ky + NY / 2) & (NY - 1)) * nx;
+                if (a.psd_out) __stcs(a.psd_out + (size_t)t * NY * nx + rs, Pn * ps);
+                if (a.cplx_out) __stcs(a.cplx_out + (size_t)t * NY * nx + rs, Fn);
                 if (cjn) cjn[ky] = cconj(Fn);
                 if (SPEC) spec_accumulate<NY>(sp, Pn * ps, ky, hx, nx, 1.0, false);
             }
             if (AC) {
                 if (a.ac_zero_dc && nyq_owner && ky == 0) Pa = 0.f;
-                acsum += wgt * (double)Pa + (double)Pn;
+                acsum += fmaf(wgt, Pa, Pn);
                 if (PC) {
                     Bp[tid + s * NT] = Pa;
                     if (nyq_owner) Pns[ky] = Pn;
+                } else {
+                    x[s] = make_float2(Pa, Pn);
                 }
             }
-            if (PC) {
-                if (nyq_owner && ky == 0 && a.fr) {
-                    // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
-                    const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
-                    const double n = (double)nx * (double)NY;
-                    F.x = (float)((double)dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
+        }
+    }
+    if (PC) {
+        float inv_s = 1.f;
+        if (a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
+        const float2* R = a.R + (size_t)t * a.r_stride + (g0 - (size_t)t * NY * hx);
+        const float2* Rn = a.Rnyq + (size_t)t * a.rnyq_stride;
+        // the reference spectrum is fetched eight elements at a time (a compiler barrier keeps the second half from
+        // being hoisted over the first, which would spill)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 Rv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Rv[i] = __ldg(R + (8 * h + i) * GS);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int s = 8 * h + i;
+                const int ky = j + s * T;
+                float2 F = x[s];
+                float2 Fn = make_float2(0.f, 0.f);
+                float dcshift = 0.f;
+                if (nyq_owner) {
+                    unpack0(s, F, Fn, dcshift);
+                    if (ky == 0 && a.fr) {
+                        // DC of the mean-removed frame: sum(x - K) + n (K - mean), formed without cancellation
+                        const double K = a.pilot ? (double)__ldg(a.pilot + t) : 0.0;
+                        const double n = (double)nx * (double)NY;
+                        F.x = (float)((double)dcshift + n * (K - a.fr[(size_t)t * a.fr_stride + B4D_FR_MEAN]));
+                    }
                 }
                 F.x *= inv_s; F.y *= inv_s;
-                float2 G = whiten_if(cmul(F, Rv), a.whiten, a.eps);
+                float2 G = whiten_if(cmul(F, Rv[i]), a.whiten, a.eps);
                 if (nyq_owner) {                      // pack: column 0 <- G[:,0] + i G[:,nx/2]
                     Fn.x *= inv_s; Fn.y *= inv_s;
                     const float2 Gn = whiten_if(cmul(Fn, __ldg(Rn + ky)), a.whiten, a.eps);
                     G = make_float2(G.x - Gn.y, G.y + Gn.x);
                 }
                 x[s] = G;
-            } else if (AC) {
-                x[s] = make_float2(Pa, Pn);
             }
+            asm volatile("" ::: "memory");
         }
     }
 
     // ---- block reductions of the scalar partials ------------------------------------------------
     if (SPEC || AC) {
-        double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, acsum};
+        double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, (double)acsum};
         const int warp = tid >> 5, lane = tid & 31, nw = (NT + 31) / 32;
 #pragma unroll
         for (int i = SPEC ? 0 : NSP; i < NSP + 1; ++i) {
@@ -371,6 +403,7 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
         for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
     }
     if (PC && AC) {                                   // second inverse: |F|^2 kept in Bp
+        asm volatile("" ::: "memory");                // the loads below must not be hoisted over the first inverse
 #pragma unroll
         for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[tid + s * NT], nyq_owner ? Pns[j + s * T] : 0.f);
         fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
