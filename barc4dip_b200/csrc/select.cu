@@ -740,9 +740,13 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
             { ProfScope ps(ctx, KC_SELECT_SAMPLE);
               sel_sample_kernel<<<(unsigned)tc, 1024, SEL_SAMPLES * sizeof(unsigned), ctx->stream>>>(s0, n, n_q, q_dev, use_abs, sf); }
             B4D_LAUNCH_CHECK(ctx);
+            // CTAs per frame: enough to fill the GPU, and never more than 8 chunks (32 K elements) per CTA -- the widest
+            // bracket (the median's, +-6 sigma of a 16 K sample) holds < 5 % of them, well inside the CTA's stage
             int bpf = (int)((n + COL_CHUNK - 1) / COL_CHUNK);
             const int capb = ctx->sm_count * 12;
             if ((int64_t)bpf * tc > capb) bpf = (int)((capb + tc - 1) / tc);
+            const int bmin = (int)((n + 8 * COL_CHUNK - 1) / (8 * COL_CHUNK));
+            if (bpf < bmin) bpf = bmin;
             if (bpf < 1) bpf = 1;
             { ProfScope ps(ctx, KC_SELECT_COLLECT);
               sel_collect_kernel<<<dim3((unsigned)bpf, (unsigned)tc), 256, 0, ctx->stream>>>(s0, n, n_q, use_abs, sf, cand, cap, bhist); }

@@ -1014,13 +1014,19 @@ int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx) {
     return rc;
 }
 
-// frames per internal batch: keeps the blocked intermediates of a batch L2-sized
+// Frames per internal batch. The kernels of this path are bound by the SM's load/store pipe, not by L2 hits, and the
+// per-batch kernels that run one CTA per frame (sampling, final selects, grain) want many frames per launch: batches
+// are as large as a scratch budget allows (a quarter of the free HBM, at most 128 frames).
 int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
     if (ctx->batch_override > 0) return ctx->batch_override;
     const size_t per = (size_t)ny * (nx / 2) * sizeof(float2) * (size_t)n_intermediates;
-    int64_t b = (int64_t)((96ull << 20) / (per ? per : 1));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+    size_t held = 0;                                  // scratch already owned by this context counts as available
+    for (int i = 0; i < 10; ++i) held += ctx->scratch_bytes[i];
+    int64_t b = (int64_t)(((free_b + held) / 4) / (per ? per : 1));
     if (b < 1) b = 1;
-    if (b > 4096) b = 4096;
+    if (b > 128) b = 128;
     return b;
 }
 

@@ -51,7 +51,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--frames", type=int, default=16, help="frames per step per GPU")
+    p.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
     p.add_argument("--size", type=int, default=2048)
     p.add_argument("--batch", type=int, default=0, help="frames per internal FFT batch (0 = automatic)")
     p.add_argument("--e2e-steps", type=int, default=3)
@@ -282,7 +282,7 @@ def run_b200(args):
     if not args.no_e2e:
         host = torch.empty((F, n, n), dtype=torch.float32, pin_memory=True)
         host.copy_(stack)
-        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, F // 4), want_maps=True, want_contrast=True)
+        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(16, F // 4)), want_maps=True, want_contrast=True)
         ref_host = host[0].clone()
 
         def e2e_step():
