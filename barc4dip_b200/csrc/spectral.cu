@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
         }
         x[m] = make_float2(va - K, vb - K);
     }
-    fft_regs_to_smem<NX, -1, 1>(x, j, sm + f * FS, a.tw);
+    fft_regs_to_smem<NX, -1, 1, (NX >= 1024)>(x, j, sm + f * FS, a.tw, f);
 
     // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
     float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
@@ -475,12 +475,16 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         const int ya = a.pair_maps ? y0 + f : y0 + 2 * f;
         const int yb = a.pair_maps ? ya : ya + 1;
         float2 ga[8], gb[8];
+        {
+            // k = jg + m TPF lives in tile jg/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads
+            const size_t tstride = (size_t)(TPF / TC) * NY * TC;
+            const float2* pa = Ia + ((size_t)(jg / TC) * NY + ya) * TC + (jg % TC);
+            const float2* pb = Ib + ((size_t)(jg / TC) * NY + yb) * TC + (jg % TC);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int k = jg + m * TPF;
-            const size_t off = ((size_t)(k / TC) * NY) * TC + (k % TC);
-            ga[m] = __ldcs(Ia + off + (size_t)ya * TC);
-            gb[m] = __ldcs(Ib + off + (size_t)yb * TC);
+            for (int m = 0; m < 8; ++m) {
+                ga[m] = __ldcs(pa + m * tstride);
+                gb[m] = __ldcs(pb + m * tstride);
+            }
         }
         if (warp == 0) {
             double sc = a.scaleA;
@@ -521,40 +525,46 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     float2 x[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
-    fft_regs<NX, +1, 1>(x, j, z, a.tw);
+    fft_regs<NX, +1, 1, (NX >= 1024)>(x, j, z, a.tw, f);
 
-    // ---- stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya)
+    // ---- stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya). Slot s holds x-position
+    //      j + TPF s, i.e. shifted column j + TPF ((s + 8) & 15): a per-thread pointer plus a compile-time offset.
     const int kindB = a.pair_maps ? a.kindB : a.kindA;
-    float* oA = a.outA ? a.outA + (size_t)t * NY * NX : nullptr;
-    float* oB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX : nullptr) : oA;
-    ArgBest bA = {-INFINITY, 0xffffffffu}, bB = {-INFINITY, 0xffffffffu};
-    {
-        const int ra_ = a.pair_maps ? y0 + f : y0 + 2 * f;
-        const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
-        const unsigned rowA = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX;
-        const unsigned rowB = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX;
+    const int ra_ = a.pair_maps ? y0 + f : y0 + 2 * f;
+    const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
+    const unsigned rowA = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX;
+    const unsigned rowB = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX;
+    float* pA = a.outA ? a.outA + (size_t)t * NY * NX + rowA + j : nullptr;
+    float* pB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX + rowB + j : nullptr)
+                            : (a.outA ? a.outA + (size_t)t * NY * NX + rowB + j : nullptr);
+    // Running maxima with the slot they came from. Slots are visited in increasing column order (s = 8..15, 0..7) and
+    // rowA < rowB never matters inside a thread (ties across the two rows are settled by best_update below), so a
+    // strict '>' keeps the first occurrence.
+    float mA = -INFINITY, mB = -INFINITY;
+    int sA_ = 8, sB_ = 8;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            const unsigned cs = (unsigned)(j + TPF * ((s + 8) & 15));   // fftshift along x
-            const unsigned ia = rowA + cs, ib = rowB + cs;
-            float va = x[s].x, vb = x[s].y;
-            if (a.kindA) va = fabsf(va);
-            if (kindB) vb = fabsf(vb);
-            if (oA) oA[ia] = va;
-            if (oB) oB[ib] = vb;
-            best_update(bA, va, ia);
-            if (a.pair_maps) best_update(bB, vb, ib);
-            else best_update(bA, vb, ib);
-        }
+    for (int o = 0; o < 16; ++o) {
+        const int s = (o + 8) & 15;
+        float va = x[s].x, vb = x[s].y;
+        if (a.kindA) va = fabsf(va);
+        if (kindB) vb = fabsf(vb);
+        if (pA) pA[TPF * o] = va;
+        if (pB) pB[TPF * o] = vb;
+        if (va > mA) { mA = va; sA_ = o; }
+        if (vb > mB) { mB = vb; sB_ = o; }
     }
     // argmax partials (first occurrence in row-major order of the shifted map wins ties)
     if (a.bestA || (a.pair_maps && a.bestB)) {
+        ArgBest bA = {mA, rowA + (unsigned)(j + TPF * sA_)}, bB = {mB, rowB + (unsigned)(j + TPF * sB_)};
+        if (!a.pair_maps) best_update(bA, bB.v, bB.idx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ArgBest oa = {__shfl_xor_sync(0xffffffffu, bA.v, o), __shfl_xor_sync(0xffffffffu, bA.idx, o)};
-            ArgBest ob = {__shfl_xor_sync(0xffffffffu, bB.v, o), __shfl_xor_sync(0xffffffffu, bB.idx, o)};
             best_update(bA, oa.v, oa.idx);
-            best_update(bB, ob.v, ob.idx);
+            if (a.pair_maps) {
+                ArgBest ob = {__shfl_xor_sync(0xffffffffu, bB.v, o), __shfl_xor_sync(0xffffffffu, bB.idx, o)};
+                best_update(bB, ob.v, ob.idx);
+            }
         }
         if (lane == 0) { s_best[0][warp] = bA; s_best[1][warp] = bB; }
         __syncthreads();
