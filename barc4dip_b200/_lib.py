@@ -52,6 +52,7 @@ _SIGNATURES = {
     "b4d_profile_end": [_vp, _vp, _vp],
     "b4d_profile_class_name": [_i32],
     "b4d_set_batch_frames": [_vp, _i64],
+    "b4d_set_fused_median": [_vp, _i32],
     "b4d_malloc": [_vp, C.c_size_t, C.POINTER(_vp)],
     "b4d_free": [_vp, _vp],
     "b4d_memcpy_h2d": [_vp, _vp, _vp, C.c_size_t],
@@ -144,6 +145,9 @@ class Context:
 
     def set_batch_frames(self, frames: int):
         self.check(self.lib.b4d_set_batch_frames(self.handle, int(frames)), "b4d_set_batch_frames")
+
+    def set_fused_median(self, on: bool):
+        self.check(self.lib.b4d_set_fused_median(self.handle, int(bool(on))), "b4d_set_fused_median")
 
     @property
     def launches(self) -> int:

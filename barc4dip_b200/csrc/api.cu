@@ -92,6 +92,13 @@ extern "C" int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames) {
     return B4D_OK;
 }
 
+extern "C" int b4d_set_fused_median(b4d_ctx* ctx, int on) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->fused_median = on != 0;
+    return B4D_OK;
+}
+
 extern "C" int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return B4D_ERR_INVALID;
     cudaError_t e = cudaMalloc(out, bytes);

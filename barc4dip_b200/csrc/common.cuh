@@ -37,6 +37,7 @@ struct b4d_ctx {
     size_t scratch_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FftPlanCache* fft = nullptr;
     int64_t batch_override = 0;       // frames per internal batch of the FFT pipeline (0 = automatic)
+    bool fused_median = true;         // tracker SNR: median of |corr| taken inside the inverse row pass (no map)
     bool prof_on = false;
     std::vector<ProfSpan> prof_spans;
     std::vector<cudaEvent_t> prof_pool;

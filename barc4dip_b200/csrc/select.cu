@@ -16,52 +16,9 @@
 // with a one-CTA scan after each. Both paths are exact.
 // Keys are order-preserving uint32 images of the floats; NaNs are skipped (nanpercentile semantics).
 #include "common.cuh"
+#include "select.cuh"
 
 namespace {
-
-constexpr int SEL_MAXR = 4;           // ranks per frame (2 per quantile)
-constexpr int SEL_MAXQ = 2;
-constexpr int SEL_BINS = 2048;
-constexpr int SEL_THREADS = 256;
-constexpr int SEL_SAMPLES = 16384;
-constexpr int64_t SEL_FAST_MIN = 65536;
-
-struct SelState {                     // per frame, device resident (radix path)
-    unsigned prefix[SEL_MAXR];        // key bits fixed so far (left aligned)
-    long long rank[SEL_MAXR];         // residual rank inside the prefix bucket
-    long long n_valid;
-};
-
-struct SelFast {                      // per frame, device resident (bracket path)
-    unsigned L[SEL_MAXQ], U[SEL_MAXQ];
-    unsigned long long below[SEL_MAXQ];
-    unsigned ncand[SEL_MAXQ];
-    unsigned long long n_valid;
-    int need_fallback;
-};
-
-// order-preserving key; -0.0 maps onto +0.0 so that key order and float order agree for every non-NaN value
-__device__ __forceinline__ unsigned key_of(float v, int use_abs) {
-    unsigned b = __float_as_uint(v);
-    if (use_abs) return b & 0x7fffffffu;
-    if (b == 0x80000000u) b = 0u;
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float value_of(unsigned k, int use_abs) {
-    if (use_abs) return __uint_as_float(k);
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-// numpy's linear method: h = n*q + (1 + q*(1-1-1)) - 1, lo = floor(h), hi = min(lo+1, n-1)
-__device__ __forceinline__ void target_ranks(unsigned long long n, double q, long long& lo, long long& hi) {
-    lo = hi = 0;
-    if (n == 0) return;
-    const double hh = __dadd_rn(__dadd_rn(__dmul_rn((double)n, q), __dadd_rn(1.0, __dmul_rn(q, -1.0))), -1.0);
-    lo = (long long)floor(hh);
-    if (lo < 0) lo = 0;
-    if (lo > (long long)n - 1) lo = (long long)n - 1;
-    hi = lo + 1 > (long long)n - 1 ? (long long)n - 1 : lo + 1;
-}
 
 __device__ __forceinline__ void hist_add(unsigned* h, unsigned bin) {
     const unsigned m = __match_any_sync(__activemask(), bin);
@@ -186,12 +143,6 @@ constexpr int COL_VEC = 4;
 constexpr int COL_ITERS = 4;
 constexpr int COL_CHUNK = COL_THREADS * COL_VEC * COL_ITERS;     // 4096 elements
 constexpr int COL_STAGE = 4096;                                  // staged candidates per CTA and bracket
-
-// bin of a candidate inside its bracket [L, U]: (key - L) >> shift with the smallest shift that fits SEL_BINS bins
-__device__ __forceinline__ int bracket_shift(unsigned L, unsigned U) {
-    const int width = 32 - __clz((U - L) | 1u);
-    return width > 11 ? width - 11 : 0;
-}
 
 __global__ void __launch_bounds__(COL_THREADS) sel_collect_kernel(const float* __restrict__ stack, int64_t n, int n_q,
                                                                   int use_abs, SelFast* __restrict__ st,
@@ -418,6 +369,198 @@ __global__ void __launch_bounds__(1024) sel_final_kernel(SelFast* __restrict__ s
         if (n_valid_out) n_valid_out[t] = (long long)nv;
         if (ok)
             for (int i = 0; i < 2 * n_q; ++i) out[t * 2 * n_q + i] = res[i];
+    }
+}
+
+// =================================================================================================
+// fused median of a map that is never materialised (the tracker's |corr|, signal/tracking.py:319)
+// =================================================================================================
+// rows_inv_kernel first produces a few sample rows of every frame; this kernel turns them into the bracket [L, U]
+// around the wanted quantile (same +-6 sigma rule as sel_sample_kernel) and takes the census of the sample rows
+// themselves. The main rows_inv launch then counts / collects every other value against the bracket in its epilogue
+// (census_values_global) and sel_final_kernel reads the exact order statistics from the candidates.
+__global__ void __launch_bounds__(1024) sel_bracket_samples_kernel(const float* __restrict__ samples, int m,
+                                                                   const double* __restrict__ quant,
+                                                                   SelFast* __restrict__ st, unsigned* __restrict__ cand,
+                                                                   int regions, unsigned* __restrict__ bhist) {
+    extern __shared__ unsigned keys[];              // m
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned tmp[34];
+    __shared__ unsigned s_min, s_max, s_cnt, s_below;
+    __shared__ int s_valid;
+    const int64_t t = blockIdx.x;
+    const float* f = samples + t * m;
+    if (threadIdx.x == 0) { s_valid = 0; s_min = 0xffffffffu; s_max = 0u; s_cnt = 0u; s_below = 0u; }
+    __syncthreads();
+    int nv = 0;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const float v = f[i];
+        const bool ok = v == v;
+        const unsigned k = ok ? key_of(v, 1) : 0xffffffffu;
+        keys[i] = k;
+        nv += ok;
+        if (ok) { kmin = min(kmin, k); kmax = max(kmax, k); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_valid, nv); atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+    __syncthreads();
+    const int mv = s_valid;
+    unsigned L = 0u, U = 0xfffffffeu;
+    if (mv >= 1024) {
+        const double qq = quant[0];
+        const double c = qq * (double)(mv - 1);
+        const double d = 6.0 * sqrt(qq * (1.0 - qq) * (double)mv) + 8.0;
+        const long long il = (long long)floor(c - d), iu = (long long)ceil(c + d);
+        if (il > 0) L = cta_bracket_select(keys, (unsigned)m, (unsigned)il, s_min, s_max, hist, tmp);
+        if (iu < mv - 1) U = cta_bracket_select(keys, (unsigned)m, (unsigned)iu, s_min, s_max, hist, tmp);
+    }
+    // census of the sample rows themselves: their keys go to the tail of the frame's candidate store
+    const int shift = bracket_shift(L, U);
+    unsigned* dst = cand + (size_t)t * ((size_t)regions * FM_REGION + FM_SAMPLE_CAP) + (size_t)regions * FM_REGION;
+    unsigned* h = bhist + (size_t)t * SEL_BINS;
+    unsigned below = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned k = keys[i];
+        below += (k < L);
+        if (k >= L && k <= U) {
+            const unsigned p = atomicAdd(&s_cnt, 1u);
+            if (p < FM_SAMPLE_CAP) dst[p] = k;
+            atomicAdd(h + min((k - L) >> shift, (unsigned)(SEL_BINS - 1)), 1u);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_below, below);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        SelFast* s = st + t;
+        s->L[0] = L; s->U[0] = U;
+        s->ncand[0] = s_cnt;
+        s->below[0] = (unsigned long long)s_below;
+        s->n_valid = (unsigned long long)mv;
+    }
+}
+
+// Exact ranks of the fused median: totals from the per-region counters, bins of the wanted ranks from the bracket
+// histogram, one pass over the region store for the keys of those bins, bracket select among them.
+// out[t] = the two middle order statistics; need[t] = 1 where the bracket missed or a region / bin overflowed.
+__global__ void __launch_bounds__(1024) fused_median_final_kernel(const SelFast* __restrict__ st, const unsigned* __restrict__ cnt3,
+                                                                  const unsigned* __restrict__ cand, int regions,
+                                                                  const unsigned* __restrict__ bhist,
+                                                                  const double* __restrict__ quant, float* __restrict__ out,
+                                                                  long long* __restrict__ n_valid_out, int* __restrict__ need) {
+    __shared__ unsigned shist[SEL_BINS];
+    __shared__ unsigned bc[34];
+    __shared__ unsigned s_keys[FIN_CAP];
+    __shared__ unsigned s_n;
+    __shared__ unsigned s_bin[2], s_before[2];
+    __shared__ unsigned long long s_tot[3];
+    __shared__ int s_over;
+    const int64_t t = blockIdx.x;
+    const SelFast* s = st + t;
+    const unsigned* c3 = cnt3 + (size_t)t * regions * 3;
+    const unsigned* store = cand + (size_t)t * ((size_t)regions * FM_REGION + FM_SAMPLE_CAP);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) { s_over = 0; s_n = 0u; }
+    __syncthreads();
+    // 1. totals (fixed data, order-independent integer sums)
+    unsigned long long a0 = 0, a1 = 0, a2 = 0;
+    int over = 0;
+    for (int r = threadIdx.x; r < regions; r += blockDim.x) {
+        const unsigned c = c3[3 * r];
+        a0 += c; a1 += c3[3 * r + 1]; a2 += c3[3 * r + 2];
+        over |= c > (unsigned)FM_REGION;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) { atomicAdd(&s_tot[0], a0); atomicAdd(&s_tot[1], a1); atomicAdd(&s_tot[2], a2); }
+    if (over) s_over = 1;
+    __syncthreads();
+    const unsigned sc = s->ncand[0];
+    const unsigned long long ncand = s_tot[0] + sc, below = s_tot[1] + s->below[0], nv = s_tot[2] + s->n_valid;
+    bool ok = nv > 0 && !s_over && sc <= (unsigned)FM_SAMPLE_CAP;
+    long long lo, hi;
+    target_ranks(nv, quant[0], lo, hi);
+    ok = ok && lo >= (long long)below && hi < (long long)(below + ncand);
+    float res[2] = {0.f, 0.f};
+    if (ok) {
+        const unsigned L = s->L[0], U = s->U[0];
+        const int shift = bracket_shift(L, U);
+        const unsigned ra = (unsigned)(lo - (long long)below), rb = (unsigned)(hi - (long long)below);
+        const unsigned* h = bhist + (size_t)t * SEL_BINS;
+        const unsigned h0 = h[2 * threadIdx.x], h1 = h[2 * threadIdx.x + 1];
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) bc[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = bc[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            bc[lane] = w;
+        }
+        __syncthreads();
+        const unsigned before = (warp ? bc[warp - 1] : 0u) + incl - (h0 + h1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const unsigned rk = r ? rb : ra;
+            if (rk >= before && rk < before + h0) { s_bin[r] = 2 * threadIdx.x; s_before[r] = before; }
+            else if (rk >= before + h0 && rk < before + h0 + h1) { s_bin[r] = 2 * threadIdx.x + 1; s_before[r] = before + h0; }
+        }
+        __syncthreads();
+        const unsigned bin_a = s_bin[0], bin_b = s_bin[1];
+        unsigned ka, kb;
+        if (shift == 0) {                     // one key per bin: the bin is the answer
+            ka = L + bin_a;
+            kb = L + bin_b;
+        } else {
+            auto take = [&](unsigned key) {
+                const unsigned b = min((key - L) >> shift, (unsigned)(SEL_BINS - 1));
+                if (b == bin_a || b == bin_b) {
+                    const unsigned p = atomicAdd(&s_n, 1u);
+                    if (p < FIN_CAP) s_keys[p] = key;
+                }
+            };
+            // a warp walks a region: its count, then up to FM_REGION keys (two per lane)
+            for (int r = warp; r < regions; r += 32) {
+                const unsigned c = c3[3 * r];
+                if (lane < (int)c) take(store[(size_t)r * FM_REGION + lane]);
+                if (lane + 32 < (int)c) take(store[(size_t)r * FM_REGION + lane + 32]);
+            }
+            for (unsigned i = threadIdx.x; i < sc; i += blockDim.x) take(store[(size_t)regions * FM_REGION + i]);
+            __syncthreads();
+            const unsigned m = s_n;
+            if (m > FIN_CAP) ok = false;      // heavy ties inside one bin: the map-based path resolves them
+            else {
+                const unsigned la = ra - s_before[0];
+                const unsigned lb = bin_b == bin_a ? rb - s_before[0] : h[bin_a] + (rb - s_before[1]);
+                const unsigned Lb = L + (bin_a << shift), Ub = L + (((bin_b + 1u) << shift) - 1u);
+                ka = cta_bracket_select(s_keys, m, la, Lb, Ub < Lb ? 0xffffffffu : max(Ub, U), shist, bc);
+                kb = (rb == ra) ? ka : cta_bracket_select(s_keys, m, lb, Lb, Ub < Lb ? 0xffffffffu : max(Ub, U), shist, bc);
+            }
+        }
+        if (ok) { res[0] = __uint_as_float(ka); res[1] = __uint_as_float(kb); }
+    }
+    if (threadIdx.x == 0) {
+        need[t] = ok ? 0 : 1;
+        n_valid_out[t] = (long long)nv;
+        out[2 * t] = ok ? res[0] : __uint_as_float(0x7fc00000u);
+        out[2 * t + 1] = ok ? res[1] : __uint_as_float(0x7fc00000u);
     }
 }
 
@@ -699,6 +842,54 @@ int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt,
     ProfScope ps(ctx, KC_SELECT_FINAL);
     tails_final_kernel<<<(unsigned)T, 1024, TAIL_GCAP * sizeof(unsigned), ctx->stream>>>(cand, cnt, flag, fr, q_lo, q_hi, out,
                                                                                       reinterpret_cast<long long*>(nvalid_out));
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+// ---- fused median (called from spectral.cu) -----------------------------------------------------------
+// Scratch of one batch: bracket state, fallback flags, bracket histograms and region counters (zeroed), region store.
+int b4d_fused_median_begin(b4d_ctx* ctx, int64_t T, int regions, FusedMedian* fm) {
+    const size_t st_bytes = ((size_t)T * sizeof(SelFast) + 255) & ~size_t(255);
+    const size_t need_bytes = ((size_t)T * sizeof(int) + 255) & ~size_t(255);
+    const size_t bh_bytes = (size_t)T * SEL_BINS * sizeof(unsigned);
+    const size_t c3_bytes = ((size_t)T * regions * 3 * sizeof(unsigned) + 255) & ~size_t(255);
+    const size_t cand_bytes = (size_t)T * ((size_t)regions * FM_REGION + FM_SAMPLE_CAP) * sizeof(unsigned);
+    void* p = nullptr;
+    int rc = b4d_scratch(ctx, SCR_SELECT, 256 + st_bytes + need_bytes + bh_bytes + c3_bytes + cand_bytes, &p);
+    if (rc) return rc;
+    char* base = static_cast<char*>(p);
+    fm->q_dev = reinterpret_cast<double*>(base);
+    fm->st = reinterpret_cast<SelFast*>(base + 256);
+    fm->need = reinterpret_cast<int*>(base + 256 + st_bytes);
+    fm->bhist = reinterpret_cast<unsigned*>(base + 256 + st_bytes + need_bytes);
+    fm->cnt3 = reinterpret_cast<unsigned*>(base + 256 + st_bytes + need_bytes + bh_bytes);
+    fm->cand = reinterpret_cast<unsigned*>(base + 256 + st_bytes + need_bytes + bh_bytes + c3_bytes);
+    fm->regions = regions;
+    B4D_CUDA(ctx, cudaMemsetAsync(p, 0, 256 + st_bytes + need_bytes + bh_bytes + c3_bytes, ctx->stream));
+    static const double half = 0.5;
+    B4D_CUDA(ctx, cudaMemcpyAsync(fm->q_dev, &half, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return B4D_OK;
+}
+
+int b4d_fused_median_bracket(b4d_ctx* ctx, const FusedMedian& fm, const float* samples, int m, int64_t T) {
+    static int attr = 0;
+    if (m > 32768) return b4d_fail(ctx, B4D_ERR_INVALID, "fused median: at most 32768 samples per frame");
+    if (!attr) {
+        B4D_CUDA(ctx, cudaFuncSetAttribute(sel_bracket_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+        attr = 1;
+    }
+    ProfScope ps(ctx, KC_SELECT_SAMPLE);
+    sel_bracket_samples_kernel<<<(unsigned)T, 1024, (size_t)m * sizeof(unsigned), ctx->stream>>>(samples, m, fm.q_dev, fm.st, fm.cand,
+                                                                                                fm.regions, fm.bhist);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+// out (T, 2): the two middle order statistics; nvalid (T); fm.need[t] = 1 where the bracket missed
+int b4d_fused_median_final(b4d_ctx* ctx, const FusedMedian& fm, int64_t T, float* out, int64_t* nvalid) {
+    ProfScope ps(ctx, KC_SELECT_FINAL);
+    fused_median_final_kernel<<<(unsigned)T, 1024, 0, ctx->stream>>>(fm.st, fm.cnt3, fm.cand, fm.regions, fm.bhist, fm.q_dev, out,
+                                                                    reinterpret_cast<long long*>(nvalid), fm.need);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }

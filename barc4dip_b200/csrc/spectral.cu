@@ -18,6 +18,7 @@
 // so fp32 rounding is relative to the fluctuations, not to the pedestal.
 #include "common.cuh"
 #include "fft.cuh"
+#include "select.cuh"
 
 using namespace b4dfft;
 
@@ -39,6 +40,8 @@ struct FftPlanCache {
     float2* ref_nyq = nullptr;   // (ny)
     int ref_ny = 0, ref_nx = 0;
     double* theta = nullptr;     // 1130 x (sin, cos)
+    int* blk_list = nullptr;     // fused median: sample row blocks first, then all the others
+    int blk_n = 0, blk_ns = 0;
 };
 
 namespace {
@@ -443,6 +446,19 @@ struct RowsInvArgs {
     int kindB;
     double scaleB;
     ArgBest* bestB;
+    // row-block selection: blockIdx.x -> row block of the frame (identity when both are null)
+    int nblk;               // row blocks per frame (stride of the argmax partials)
+    const int* blk_map;     // shared by all frames (gridDim.x entries)
+    const int* blk_map_pf;  // per frame (T, gridDim.x)
+    // destination of the |.| map (map B in pair mode, map A otherwise):
+    //   0 full map; 1 compact rows: (T, gridDim.x * rows_per_cta, nx) in launch order; 2 none, census against the
+    //   frame's bracket instead (fused median, select.cuh)
+    int mag_mode;
+    const SelFast* sel;     // per frame bracket
+    unsigned* cand;         // (T, regions * FM_REGION + FM_SAMPLE_CAP) region store
+    unsigned* cnt3;         // (T, regions, 3)
+    unsigned* bhist;        // (T, SEL_BINS)
+    int regions;            // warp regions per frame = row blocks * 16 warps * (pair_maps ? 1 : 2)
 };
 
 // Two thread mappings. The gather uses lanes (c = lane & 7, fl = lane >> 3): 8 adjacent kx of 4 rows, i.e. whole
@@ -464,9 +480,12 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     const int64_t t = blockIdx.y;
     const int NY = a.ny;
     const int rows_per_cta = a.pair_maps ? FPC : 2 * FPC;
-    const int y0 = blockIdx.x * rows_per_cta;
+    const int blk = a.blk_map_pf ? a.blk_map_pf[(size_t)t * gridDim.x + blockIdx.x] : (a.blk_map ? a.blk_map[blockIdx.x] : (int)blockIdx.x);
+    const int y0 = blk * rows_per_cta;
     const float2* Ia = a.Ia + (size_t)t * NY * HX;
     const float2* Ib = a.pair_maps ? a.Ib + (size_t)t * NY * HX : Ia;
+    unsigned Lk = 0u, Uk = 0xfffffffeu;               // fused median: the frame's bracket, fetched early
+    if (a.mag_mode == 2) { Lk = a.sel[t].L[0]; Uk = a.sel[t].U[0]; }
 
     // ---- gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
     {
@@ -537,6 +556,15 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     float* pA = a.outA ? a.outA + (size_t)t * NY * NX + rowA + j : nullptr;
     float* pB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX + rowB + j : nullptr)
                             : (a.outA ? a.outA + (size_t)t * NY * NX + rowB + j : nullptr);
+    if (a.mag_mode == 1) {
+        // compact rows in launch order (sample rows of the fused median, 3x3 window of the peak)
+        const size_t crow = (size_t)t * gridDim.x * rows_per_cta + (size_t)blockIdx.x * rows_per_cta;
+        if (a.pair_maps) pB = a.outB + (crow + f) * NX + j;
+        else { pA = a.outA + (crow + 2 * f) * NX + j; pB = pA + NX; }
+    } else if (a.mag_mode == 2) {
+        if (a.pair_maps) pB = nullptr;
+        else pA = pB = nullptr;
+    }
     // Running maxima with the slot they came from. Slots are visited in increasing column order (s = 8..15, 0..7) and
     // rowA < rowB never matters inside a thread (ties across the two rows are settled by best_update below), so a
     // strict '>' keeps the first occurrence.
@@ -548,10 +576,31 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         float va = x[s].x, vb = x[s].y;
         if (a.kindA) va = fabsf(va);
         if (kindB) vb = fabsf(vb);
+        x[s] = make_float2(va, vb);
         if (pA) pA[TPF * o] = va;
         if (pB) pB[TPF * o] = vb;
         if (va > mA) { mA = va; sA_ = o; }
         if (vb > mB) { mB = vb; sB_ = o; }
+    }
+    if (a.mag_mode == 2) {
+        // fused median: census of the |.| values against the frame's bracket, straight from the registers, into this
+        // warp's own region(s) of the frame's candidate store
+        const float Lf = Lk == 0u ? -INFINITY : __uint_as_float(Lk), Uf = Uk == 0xfffffffeu ? INFINITY : __uint_as_float(Uk);
+        const int shift = bracket_shift(Lk, Uk);
+        const int calls = a.pair_maps ? 1 : 2;
+        const size_t reg = ((size_t)blk * 16 + warp) * calls;
+        unsigned* store = a.cand + (size_t)t * ((size_t)a.regions * FM_REGION + FM_SAMPLE_CAP);
+        unsigned* c3 = a.cnt3 + (size_t)t * a.regions * 3;
+        unsigned* hq = a.bhist + (size_t)t * SEL_BINS;
+        float v[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) v[s] = x[s].y;
+        census_values_region<16>(v, Lf, Uf, Lk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
+        if (!a.pair_maps) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) v[s] = x[s].x;
+            census_values_region<16>(v, Lf, Uf, Lk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
+        }
     }
     // argmax partials (first occurrence in row-major order of the shifted map wins ties)
     if (a.bestA || (a.pair_maps && a.bestB)) {
@@ -570,8 +619,8 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         __syncthreads();
         if (tid == 0) {
             for (int w = 1; w < 16; ++w) { best_update(bA, s_best[0][w].v, s_best[0][w].idx); best_update(bB, s_best[1][w].v, s_best[1][w].idx); }
-            if (a.bestA) a.bestA[(size_t)t * gridDim.x + blockIdx.x] = bA;
-            if (a.pair_maps && a.bestB) a.bestB[(size_t)t * gridDim.x + blockIdx.x] = bB;
+            if (a.bestA) a.bestA[(size_t)t * a.nblk + blk] = bA;
+            if (a.pair_maps && a.bestB) a.bestB[(size_t)t * a.nblk + blk] = bB;
         }
     }
 }
@@ -646,6 +695,62 @@ __global__ void phase_finalize_kernel(const float* __restrict__ mag, const unsig
     const float med = (nvalid[t] & 1) ? med2[2 * t] : __fmul_rn(__fadd_rn(med2[2 * t], med2[2 * t + 1]), 0.5f);
     double* o = out + t * 4;
     o[0] = dy; o[1] = dx; o[2] = (double)pk; o[3] = fabs((double)pk) / ((double)med + eps);
+}
+
+// Row blocks (of rpc rows, unshifted order) that hold the shifted rows i-1, i, i+1 around every frame's peak
+__global__ void window_blocks_kernel(const unsigned* __restrict__ peak_idx, int ny, int nx, int rpc, int* __restrict__ blk3,
+                                     int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int i = (int)(peak_idx[t] / (unsigned)nx);
+    for (int d = -1; d <= 1; ++d) {
+        const int rs = min(max(i + d, 0), ny - 1);
+        const int y = (rs + ny / 2) & (ny - 1);
+        blk3[t * 3 + d + 1] = y / rpc;
+    }
+}
+
+// phase_finalize_kernel for the fused median: the 3x3 neighbourhood of the peak comes from the compact window
+// (T, 3 * rpc, nx) that rows_inv_kernel recomputed for the blocks named in blk3; frames whose median bracket missed
+// (need[t]) report snr = NaN and are redone by the caller through the map-based path.
+__global__ void phase_finalize_window_kernel(const float* __restrict__ win, const int* __restrict__ blk3, int rpc,
+                                             const unsigned* __restrict__ peak_idx, int ny, int nx,
+                                             const float* __restrict__ med2, const long long* __restrict__ nvalid,
+                                             const int* __restrict__ need, int subpixel, double eps,
+                                             double* __restrict__ out, int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* wt = win + (size_t)t * 3 * rpc * nx;
+    const int* b3 = blk3 + t * 3;
+    auto C = [&](int a, int b) {
+        const int y = (a + ny / 2) & (ny - 1), blk = y / rpc, r = y % rpc;
+        const int slot = b3[0] == blk ? 0 : (b3[1] == blk ? 1 : 2);
+        return wt[((size_t)slot * rpc + r) * nx + b];
+    };
+    const int i = (int)(peak_idx[t] / (unsigned)nx), j = (int)(peak_idx[t] % (unsigned)nx);
+    const float pk = C(i, j);
+    double dy = (double)(i - ny / 2), dx = (double)(j - nx / 2);
+    if (subpixel && i > 0 && i < ny - 1 && j > 0 && j < nx - 1) {
+        // float32 scalar arithmetic, one rounding per operation, as numpy evaluates it
+        const float gy = __fdiv_rn(__fsub_rn(C(i + 1, j), C(i - 1, j)), 2.f);
+        const float gyy = __fsub_rn(__fadd_rn(C(i + 1, j), C(i - 1, j)), __fmul_rn(2.f, C(i, j)));
+        const float gx = __fdiv_rn(__fsub_rn(C(i, j + 1), C(i, j - 1)), 2.f);
+        const float gxx = __fsub_rn(__fadd_rn(C(i, j + 1), C(i, j - 1)), __fmul_rn(2.f, C(i, j)));
+        const float gxy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(C(i + 1, j + 1), C(i + 1, j - 1)), C(i - 1, j + 1)), C(i - 1, j - 1)), 4.f);
+        const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+        if (det != 0.f) {
+            const float inv = __fdiv_rn(1.f, det);
+            // NOTE: the reference returns the x step first and adds it to dy
+            const float di = __fmul_rn(-__fsub_rn(__fmul_rn(gyy, gx), __fmul_rn(gxy, gy)), inv);
+            const float dj = __fmul_rn(-__fsub_rn(__fmul_rn(gxx, gy), __fmul_rn(gxy, gx)), inv);
+            dy += (double)di;
+            dx += (double)dj;
+        }
+    }
+    const float med = (nvalid[t] & 1) ? med2[2 * t] : __fmul_rn(__fadd_rn(med2[2 * t], med2[2 * t + 1]), 0.5f);
+    double* o = out + t * 4;
+    o[0] = dy; o[1] = dx; o[2] = (double)pk;
+    o[3] = need[t] ? nan("") : fabs((double)pk) / ((double)med + eps);
 }
 
 // grain(): widths of the peak-normalised autocorrelation (metrics/speckles.py:546-575)
@@ -887,17 +992,18 @@ int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
     return launch_cols_inst<NY, CW, false, false, false>(ctx, a, T);
 }
 
+// grid_blocks: row blocks per frame this launch covers (0 = all of them; otherwise a.blk_map / a.blk_map_pf name them)
 template <int NX>
-int launch_rows_inv(b4d_ctx* ctx, const RowsInvArgs& a, int64_t T, int* n_blocks_out) {
+int launch_rows_inv(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
     constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
     constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
     static bool attr = false;
     if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int rows = a.pair_maps ? FPC : 2 * FPC;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
-    if (n_blocks_out) *n_blocks_out = a.ny / rows;
+    a.nblk = a.ny / rows;
     ProfScope ps(ctx, KC_ROWS_INV);
-    rows_inv_kernel<NX><<<dim3(a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    rows_inv_kernel<NX><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
@@ -1017,10 +1123,10 @@ int run_cols(b4d_ctx* ctx, ColsArgs& c, int64_t T, int ny) {
     return rc;
 }
 
-int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx) {
+int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx, int grid_blocks = 0) {
     int rc = get_twiddle_bases(ctx, nx, &r.tw);
     if (rc) return rc;
-    DISPATCH_N(nx, rc = launch_rows_inv<N_>(ctx, r, T, nullptr));
+    DISPATCH_N(nx, rc = launch_rows_inv<N_>(ctx, r, T, grid_blocks));
     return rc;
 }
 
@@ -1048,6 +1154,7 @@ void b4d_fft_release(b4d_ctx* ctx) {
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
     if (ctx->fft->theta) cudaFree(ctx->fft->theta);
+    if (ctx->fft->blk_list) cudaFree(ctx->fft->blk_list);
     delete ctx->fft;
     ctx->fft = nullptr;
 }
@@ -1298,6 +1405,80 @@ int track_finish(b4d_ctx* ctx, Work& w, const float* mag, int64_t tc, int ny, in
 
 }  // namespace
 
+int b4d_fused_median_begin(b4d_ctx* ctx, int64_t T, int regions, FusedMedian* fm);
+int b4d_fused_median_bracket(b4d_ctx* ctx, const FusedMedian& fm, const float* samples, int m, int64_t T);
+int b4d_fused_median_final(b4d_ctx* ctx, const FusedMedian& fm, int64_t T, float* out, int64_t* nvalid);
+
+namespace {
+
+// number of sample row blocks for the fused median (0: the frame is too small, use the map-based path)
+int fused_sample_blocks(int ny, int nx, int pair_maps) {
+    const int nblk = rows_inv_blocks(nx, ny, pair_maps), rpc = ny / nblk;
+    if ((int64_t)ny * nx < 65536 || nblk < 4) return 0;
+    int ns = 32768 / (rpc * nx);
+    if (ns > nblk / 2) ns = nblk / 2;
+    return ns < 1 ? 0 : ns;
+}
+
+// Inverse rows + tracker results with the |corr| map never written (fused median). `r` is set up for the full launch:
+// map A outputs as usual in pair mode; the |.| map is map B (pair) or map A (single), its argmax partials in w.bestB.
+int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int ny, int nx, int ns, float* scratch,
+                         int subpixel, double eps, double* out) {
+    const int pair = r.pair_maps, nblk = rows_inv_blocks(nx, ny, pair), rpc = ny / nblk;
+    const int m = ns * rpc * nx;
+    FftPlanCache* f = ctx->fft;
+    if (f->blk_n != nblk || f->blk_ns != ns) {
+        std::vector<int> h;
+        std::vector<char> used(nblk, 0);
+        for (int i = 0; i < ns; ++i) { const int b = (int)(((int64_t)(2 * i + 1) * nblk) / (2 * ns)); h.push_back(b); used[b] = 1; }
+        for (int b = 0; b < nblk; ++b) if (!used[b]) h.push_back(b);
+        if (f->blk_list) { B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(f->blk_list); f->blk_list = nullptr; }
+        B4D_CUDA(ctx, cudaMalloc(&f->blk_list, sizeof(int) * nblk));
+        B4D_CUDA(ctx, cudaMemcpy(f->blk_list, h.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice));
+        f->blk_n = nblk; f->blk_ns = ns;
+    }
+    float* samples = scratch;                                   // (tc, m)
+    float* window = samples + (size_t)tc * m;                   // (tc, 3 * rpc, nx)
+    int* blk3 = reinterpret_cast<int*>(window + (size_t)tc * 3 * rpc * nx);   // (tc, 3)
+    FusedMedian fm;
+    int rc;
+    if ((rc = b4d_fused_median_begin(ctx, tc, nblk * 16 * (pair ? 1 : 2), &fm))) return rc;
+    // 1. sample rows: map A as usual, |.| rows into the compact sample buffer
+    RowsInvArgs r1 = r;
+    r1.blk_map = f->blk_list; r1.mag_mode = 1;
+    if (pair) r1.outB = samples; else r1.outA = samples;
+    if ((rc = run_rows_inv(ctx, r1, tc, nx, ns))) return rc;
+    // 2. bracket around the median + census of the sample rows
+    if ((rc = b4d_fused_median_bracket(ctx, fm, samples, m, tc))) return rc;
+    // 3. every other row block: census in the epilogue, no |.| map
+    RowsInvArgs r2 = r;
+    r2.blk_map = f->blk_list + ns; r2.mag_mode = 2;
+    r2.sel = fm.st; r2.cand = fm.cand; r2.cnt3 = fm.cnt3; r2.bhist = fm.bhist; r2.regions = fm.regions;
+    if ((rc = run_rows_inv(ctx, r2, tc, nx, nblk - ns))) return rc;
+    // 4. peak, then the three row blocks around it once more for the 3x3 neighbourhood
+    argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestB, nblk, w.pk_idx, w.pk_val);
+    B4D_LAUNCH_CHECK(ctx);
+    window_blocks_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(w.pk_idx, ny, nx, rpc, blk3, tc);
+    B4D_LAUNCH_CHECK(ctx);
+    RowsInvArgs r3 = r;
+    r3.blk_map_pf = blk3; r3.mag_mode = 1; r3.bestA = nullptr; r3.bestB = nullptr;
+    if (pair) { r3.outA = nullptr; r3.outB = window; } else r3.outA = window;
+    if ((rc = run_rows_inv(ctx, r3, tc, nx, 3))) return rc;
+    // 5. exact median from the candidates, results
+    if ((rc = b4d_fused_median_final(ctx, fm, tc, w.med, reinterpret_cast<int64_t*>(w.nvalid)))) return rc;
+    phase_finalize_window_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(window, blk3, rpc, w.pk_idx, ny, nx, w.med,
+                                                                                     w.nvalid, fm.need, subpixel, eps, out, tc);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+size_t fused_scratch_floats(int ny, int nx, int pair_maps, int ns, int64_t tc) {
+    const int nblk = rows_inv_blocks(nx, ny, pair_maps), rpc = ny / nblk;
+    return (size_t)tc * ((size_t)ns * rpc * nx + (size_t)3 * rpc * nx + 4);
+}
+
+}  // namespace
+
 extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps,
                                double* out) {
     if (!ctx) return B4D_ERR_INVALID;
@@ -1313,12 +1494,14 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
         const float* s0 = stack + (size_t)t0 * ny * nx;
         Work w;
         if ((rc = carve(ctx, tc, ny, nx, false, true, &w))) return rc;
+        const int ns = ctx->fused_median ? fused_sample_blocks(ny, nx, 0) : 0;
         void* p = nullptr;
-        if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (size_t)tc * ny * nx + sizeof(double) * B4D_FR_NCOLS * tc, &p))) return rc;
-        float* mag = static_cast<float*>(p);
-        double* fr = reinterpret_cast<double*>(mag + (size_t)tc * ny * nx);
-        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, fr))) return rc;
-        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w, true))) return rc;
+        const size_t map_floats = ns ? fused_scratch_floats(ny, nx, 0, ns, tc) : (size_t)tc * ny * nx;
+        if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(double) * B4D_FR_NCOLS * tc + sizeof(float) * map_floats + 256, &p))) return rc;
+        double* fr = static_cast<double*>(p);
+        float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
+        if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, fr, nullptr, w.pilot))) return rc;
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w, true, true))) return rc;
         ColsArgs c = cols_defaults(w, nx, true);
         c.i2_pc = w.I2b;
         c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
@@ -1330,8 +1513,12 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
         r.Ia = w.I2b; r.ny = ny; r.pair_maps = 0; r.outA = mag; r.kindA = 1;
         r.scaleA = 1.0 / ((double)nx * (double)ny);
         r.bestA = w.bestB;
-        if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
-        if ((rc = track_finish(ctx, w, mag, tc, ny, nx, rows_inv_blocks(nx, ny, 0), subpixel, eps, out + t0 * 4))) return rc;
+        if (ns) {
+            if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, out + t0 * 4))) return rc;
+        } else {
+            if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+            if ((rc = track_finish(ctx, w, mag, tc, ny, nx, rows_inv_blocks(nx, ny, 0), subpixel, eps, out + t0 * 4))) return rc;
+        }
     }
     return B4D_OK;
 }
@@ -1360,12 +1547,15 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w))) return rc;
         // scratch maps: |corr| always, autocorr when the caller does not keep it
         void* p = nullptr;
-        const size_t need = sizeof(float) * npix * tc * ((want_pc ? 1 : 0) + ((want_ac && !ac_out) ? 1 : 0)) +
+        // tracker: fused median (sample rows + 3x3 window instead of the |corr| map) unless the frame is too small
+        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx, want_ac ? 1 : 0) : 0;
+        const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, want_ac ? 1 : 0, ns, tc) + 63) & ~size_t(63)) : npix * tc);
+        const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) +
                             sizeof(double) * B4D_FR_NCOLS * tc + 256;
         if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
         double* fr = static_cast<double*>(p);
         float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
-        float* acm = ac_out ? ac_out + (size_t)t0 * npix : (want_pc ? mag + npix * tc : mag);
+        float* acm = ac_out ? ac_out + (size_t)t0 * npix : mag + mag_floats;
         double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : fr;
         const bool reduced = fr_out || want_pc || quant_out;
         if (reduced) {
@@ -1407,7 +1597,9 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
             r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
             nblk = rows_inv_blocks(nx, ny, 0);
         }
-        if (want_ac || want_pc) {
+        if (want_pc && ns) {
+            if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4))) return rc;
+        } else if (want_ac || want_pc) {
             if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
         }
         if (grain_out) {
@@ -1419,7 +1611,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
                                                                  grain_out + t0 * 4);
             B4D_LAUNCH_CHECK(ctx);
         }
-        if (want_pc) {
+        if (want_pc && !ns) {
             if ((rc = track_finish(ctx, w, mag, tc, ny, nx, nblk, subpixel, eps, track_out + t0 * 4))) return rc;
         }
     }

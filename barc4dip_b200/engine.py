@@ -274,7 +274,32 @@ class PhaseTracker:
         out = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
         ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(stack), T, ny, nx, int(bool(subpixel)), self.eps,
                                           ptr(out)), "b4d_phase_track")
+        resolve_tracking(stack, out, subpixel=subpixel, eps=self.eps)
         return out if return_device else out.cpu().numpy()
+
+
+def resolve_tracking(stack, track, *, subpixel: bool = True, eps: float = 1e-9, gain=None, dark=None, flat_field_fn=None):
+    """Frames whose fused median bracket missed carry snr = NaN (include/b4d.h, b4d_set_fused_median): redo them through the
+    map-based exact path. `stack` holds the frames as the tracker saw them (raw when gain/dark were fused into the
+    loaders: then `flat_field_fn` materialises the corrected frames). In place; returns the number of frames redone."""
+    torch = require_cuda()
+    bad = torch.nonzero(torch.isnan(track[:, 3])).flatten()
+    if not bad.numel():
+        return 0
+    frames = stack[bad].contiguous()
+    if flat_field_fn is not None:
+        frames = flat_field_fn(frames)
+    ctx = get_context(_dev(stack))
+    T, ny, nx = frames.shape
+    redo = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
+    ctx.set_fused_median(False)
+    try:
+        ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(frames), T, ny, nx, int(bool(subpixel)), float(eps), ptr(redo)),
+                  "b4d_phase_track")
+    finally:
+        ctx.set_fused_median(True)
+    track[bad] = redo
+    return int(bad.numel())
 
 
 def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | None = 65535.0, eps: float = 1e-6,

@@ -90,6 +90,10 @@ class StackAnalyzer:
                                     want_autocorr=True, want_grain=True, want_tracking=self.tracker is not None,
                                     psd_out=psd_out, ac_out=ac_out,
                                     tail_quantiles=(q_lo, q_hi) if self.want_contrast else None)
+        if resolve_tails and res["tracking"] is not None:
+            # same contract for the tracker: snr = NaN marks a frame whose fused median bracket missed
+            ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None
+            engine.resolve_tracking(dev_stack, res["tracking"], subpixel=self.subpixel, flat_field_fn=ff)
         if self.want_contrast and resolve_tails:
             # the tails are collected inside the reduction pass; a frame the sample bracket missed (n_valid == -1) is
             # redone by the stand-alone exact select (host sync: one tiny D2H per chunk)
@@ -178,6 +182,14 @@ class StackAnalyzer:
         for s_ in self._streams:
             s_.synchronize()
         ctx.use_current_stream()
+        if track_all is not None and bool(torch.isnan(track_all[:, 3]).any()):
+            # frames whose fused median bracket missed: redo them through the map-based tracker
+            bad = torch.isnan(track_all[:, 3]).nonzero().flatten()
+            frames = (src[bad.cpu()] if is_host else stack[bad]).to(self.device, dtype=torch.float32).contiguous()
+            sub = track_all[bad].clone()
+            ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None
+            engine.resolve_tracking(frames, sub, subpixel=self.subpixel, flat_field_fn=ff)
+            track_all[bad] = sub
         if nv_all is not None and bool((nv_all < 0).any()):
             # frames whose tails the fused collection did not resolve: exact stand-alone select on those frames only
             bad = (nv_all < 0).nonzero().flatten()

@@ -211,6 +211,14 @@ int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, 
  *   out: DEVICE float64 (n_frames, 4) = dy, dx, peak, snr  (sub-pixel terms applied -- with the
  *   reference's swapped order -- when subpixel != 0).
  */
+/*
+ * Tracker SNR = |peak| / (median(|corr|) + eps) (signal/tracking.py:314-321).  By default the exact median is taken
+ * inside the inverse row pass, without ever writing the |corr| map: a few sample rows fix a bracket around the
+ * median, every other value is counted / collected against it from registers.  A frame whose bracket missed reports
+ * snr = NaN (dy, dx, peak stay valid); redo such frames with b4d_set_fused_median(ctx, 0), which selects the
+ * map-based path (|corr| map written, stand-alone exact select).
+ */
+int b4d_set_fused_median(b4d_ctx* ctx, int on);
 int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx,
                             int y0, int x0, double eps);
 int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
