@@ -158,3 +158,54 @@ def test_tracking_stack_matches_per_frame_and_oracle():
             np.testing.assert_allclose(tab[t, 3], want[3], rtol=2e-3)
     # integer (np.roll) frames are known answers
     np.testing.assert_allclose(tab[3, :2], shifts[3], atol=0.05)
+
+
+@pytest.mark.parametrize("n", [256, 1024])
+def test_fused_median_equals_map_based_path(n):
+    """The tracker's median taken inside the inverse row pass (no |corr| map) is the same exact order statistic as the
+    map-based select: both paths must return identical tables (b4d_set_fused_median)."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    from barc4dip_b200._lib import get_context
+    stack, _ = synth.tracking_stack(5, n, grain=5.0, seed=7, integer_every=2)
+    d = engine.as_stack(stack)
+    tr = engine.PhaseTracker(stack[0], (n, n), y0=0, x0=0)
+    ctx = get_context()
+    fused = tr.track(d, return_device=True).clone()
+    ctx.set_fused_median(False)
+    try:
+        plain = tr.track(d, return_device=True).clone()
+    finally:
+        ctx.set_fused_median(True)
+    assert not bool(torch.isnan(fused[1:, 3]).any())
+    np.testing.assert_array_equal(fused[1:].cpu().numpy(), plain[1:].cpu().numpy())
+    # the fused pipeline packs autocorrelation and |corr| rows into shared inverse transforms: same numbers up to
+    # float32 rounding of a different operation order
+    res = engine.stack_pipeline(d, want_psd=False, tail_quantiles=None)
+    got, want = res["tracking"][1:].cpu().numpy(), plain[1:].cpu().numpy()
+    np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(got[:, 2:], want[:, 2:], rtol=1e-5)
+
+
+def test_fused_median_flags_degenerate_frames_and_falls_back():
+    """A constant frame z-scores to zeros: |corr| is one big tie, the warp regions overflow, the frame is flagged
+    (snr = NaN at the C ABI) and the host wrapper redoes it through the map-based path."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    from barc4dip_b200._lib import get_context, ptr
+    n = 256
+    stack, _ = synth.tracking_stack(3, n, grain=5.0, seed=9, integer_every=2)
+    stack[1] = 7.0
+    d = engine.as_stack(stack)
+    tr = engine.PhaseTracker(stack[0], (n, n), y0=0, x0=0)
+    ctx = get_context()
+    raw = torch.empty((3, 4), dtype=torch.float64, device=d.device)
+    ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(d), 3, n, n, 1, 1e-9, ptr(raw)), "b4d_phase_track")
+    assert bool(torch.isnan(raw[1, 3])) and not bool(torch.isnan(raw[2, 3]))
+    tab = tr.track(d)                       # wrapper resolves the flagged frame
+    ctx.set_fused_median(False)
+    try:
+        plain = tr.track(d)
+    finally:
+        ctx.set_fused_median(True)
+    np.testing.assert_array_equal(tab[1:], plain[1:])
