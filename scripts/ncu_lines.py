@@ -15,7 +15,15 @@ for r in rows:
     elif r and r[0] == "Address": cur["hdr"] = r
     elif r and cur is not None: cur["rows"].append(r)
 norm = lambda s: re.sub(r"[^A-Za-z0-9<>,]", "", s.replace("(int)", "").replace("(bool)", ""))
-blk = next(b for b in blocks if norm(filt) in norm(b["name"]))
+nth = int(sys.argv[sys.argv.index("--nth") + 1]) if "--nth" in sys.argv else 0
+cands = [b for b in blocks if norm(filt) in norm(b["name"])]
+if "--biggest" in sys.argv:
+    def _tot(b):
+        i = b["hdr"].index("Instructions Executed")
+        return sum(float(r[i] or 0) for r in b["rows"])
+    blk = max(cands, key=_tot)
+else:
+    blk = cands[nth]
 ix = {h: i for i, h in enumerate(blk["hdr"])}
 # mangled pattern from 'name<args>'
 m = re.match(r"(\w+)<(.*)>", filt.strip())
