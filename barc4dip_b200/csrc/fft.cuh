@@ -201,18 +201,21 @@ __device__ __forceinline__ void ldg_tw4(const float2* p, float2& a, float2& b, f
     a = make_float2(u.x, u.y); b = make_float2(u.z, u.w); c = make_float2(v.x, v.y); d = make_float2(v.z, v.w);
 }
 
-// Barrier of one transform's threads. GROUP = false: the whole CTA (__syncthreads). GROUP = true: the N/16 threads
-// of the transform only (named barrier 1 + group), legal when they are whole warps (BATCH == 1, N >= 512): the
-// independent transforms of a CTA then stop waiting for one another at every exchange.
-template <int N, bool GROUP>
+// Barrier of the threads that share an exchange buffer. GROUP = 0: the whole CTA (__syncthreads). GROUP = 1: the N/16
+// threads of one transform only (named barrier 1 + group), legal when they are whole warps (BATCH == 1, N >= 512): the
+// independent transforms of a CTA then stop waiting for one another at every exchange. GROUP = 2: the first
+// BATCH * N/16 threads of the CTA (named barrier 15), the others having left for good or for other work.
+template <int N, int GROUP, int BATCH>
 __device__ __forceinline__ void fft_sync(int group) {
-    if (GROUP) asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(N / 16) : "memory");
+    if (GROUP == 1) asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(N / 16) : "memory");
+    else if (GROUP == 2) asm volatile("bar.sync 15, %0;" ::"n"(BATCH * (N / 16)) : "memory");
     else __syncthreads();
 }
 
-template <int N, int DIR, int BATCH, bool GROUP = false>
+template <int N, int DIR, int BATCH, int GROUP = 0>
 __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ twb, int group = 0) {
-    static_assert(!GROUP || (BATCH == 1 && N >= 512), "group barriers need warp-aligned transforms");
+    static_assert(GROUP != 1 || (BATCH == 1 && N >= 512), "group barriers need warp-aligned transforms");
+    static_assert(GROUP != 2 || (BATCH * (N / 16)) % 32 == 0, "sub-CTA barriers need whole warps");
     using P = Plan<N>;
     constexpr int T = N / 16;
     constexpr bool FAST = (T % 16) == 0;
@@ -223,7 +226,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
 
     // ---- stage 1: radix 16, LS = 1 -> element 16 j + q at padded index 17 j + q
     bfly16<DIR>(x);
-    fft_sync<N, GROUP>(group);
+    fft_sync<N, GROUP, BATCH>(group);
     {
         float2* w = z + 17 * j * BATCH;
 #pragma unroll
@@ -237,7 +240,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
         if (FAST && b > 0) { b1[b] = b1[0]; b2[b] = b2[0]; b4[b] = b4[0]; b8[b] = b8[0]; }
         else ldg_tw4(twb + 4 * k, b1[b], b2[b], b4[b], b8[b]);
     }
-    fft_sync<N, GROUP>(group);
+    fft_sync<N, GROUP, BATCH>(group);
 
     // ---- stage 2: radix R2, LS = 16
     {
@@ -269,7 +272,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
 #pragma unroll
         for (int s = 0; s < 16; ++s) x[s] = y[s];
     } else {
-        fft_sync<N, GROUP>(group);
+        fft_sync<N, GROUP, BATCH>(group);
         if (FAST) {
             const int k = j & 15;
             float2* w = z + (((j - k) / 16) * 17 * R2 + k) * BATCH;
@@ -288,7 +291,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
         float2 c1[NB3], c2[NB3], c4[NB3], c8[NB3];
 #pragma unroll
         for (int b = 0; b < NB3; ++b) ldg_tw4(twb + 64 + 4 * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
-        fft_sync<N, GROUP>(group);
+        fft_sync<N, GROUP, BATCH>(group);
 
         // ---- stage 3: radix R3, LS = 16 R2 = N / R3: k = v = j + b T
         if (FAST) {
@@ -322,11 +325,11 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
 
 // v2 core + write-back: on return the transform sits in shared memory in natural order (element i at
 // z[pad16(i) * BATCH]) and a __syncthreads() has been issued.
-template <int N, int DIR, int BATCH, bool GROUP = false>
+template <int N, int DIR, int BATCH, int GROUP = 0>
 __device__ __forceinline__ void fft_regs_to_smem(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ twb, int group = 0) {
     constexpr int T = N / 16;
     fft_regs<N, DIR, BATCH, GROUP>(x, j, z, twb, group);
-    fft_sync<N, GROUP>(group);
+    fft_sync<N, GROUP, BATCH>(group);
     if ((T % 16) == 0) {
         float2* w = z + pad16(j) * BATCH;
 #pragma unroll

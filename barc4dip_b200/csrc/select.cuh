@@ -131,44 +131,35 @@ constexpr int FM_REGION = 64;          // keys per warp and call (a warp holds 5
 constexpr int FM_SAMPLE_CAP = 4096;    // keys the sample rows may contribute
 
 template <int NV>
-__device__ __forceinline__ void census_values_region(const float (&v)[NV], float Lf, float Uf, unsigned Lkey, int shift,
+__device__ __forceinline__ void census_values_region(const float (&v)[NV], unsigned Lkey, unsigned Ukey, int shift,
                                                      unsigned* __restrict__ region, unsigned* __restrict__ cnt3,
                                                      unsigned* __restrict__ hist_q, int lane) {
-    unsigned c = 0, below = 0, nvalid = 0;
-    float sum = 0.f;
+    // The values are magnitudes (non-negative or NaN), so their bit patterns are the order-preserving keys and one
+    // subtraction d = key - L gives both tests: below the bracket <=> bit 31 of d (keys and L are < 2^31), inside <=>
+    // d <= U - L (unsigned). The keys inside are compacted slot by slot with a warp vote: a slot nobody is inside of
+    // costs five instructions.
+    const unsigned W = min(Ukey, 0x7fffffffu) - Lkey;
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    unsigned below = 0, base = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        below += (v[i] < Lf);
-        c += (v[i] >= Lf && v[i] <= Uf);
-        sum += fabsf(v[i]);
-    }
-    if (sum == sum) nvalid = NV;                      // the sum of magnitudes is NaN iff one of them is
-    else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) nvalid += (v[i] == v[i]);
-    }
-    unsigned incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        below += __shfl_xor_sync(0xffffffffu, below, o);
-        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-    }
-    if (lane == 31) { cnt3[0] = incl; cnt3[1] = below; cnt3[2] = nvalid; }
-    if (c) {
-        unsigned pos = incl - c;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            if (v[i] >= Lf && v[i] <= Uf) {
-                const unsigned key = key_of(v[i], 1);
-                if (pos < FM_REGION) region[pos] = key;
-                atomicAdd(hist_q + min((key - Lkey) >> shift, (unsigned)(SEL_BINS - 1)), 1u);
-                ++pos;
+        const unsigned d = __float_as_uint(v[i]) - Lkey;
+        below += d >> 31;
+        const bool in = d <= W;
+        if (__any_sync(0xffffffffu, in)) {
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned pos = base + __popc(m & lt);
+                if (pos < FM_REGION) region[pos] = d + Lkey;
+                atomicAdd(hist_q + min(d >> shift, (unsigned)(SEL_BINS - 1)), 1u);
             }
+            base += __popc(m);
         }
     }
+    // A NaN anywhere in the frame reaches every output of its inverse transform, so one value per lane tells whether the
+    // warp's values are valid.
+    const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, v[0] == v[0])) * (unsigned)NV;
+    below = __reduce_add_sync(0xffffffffu, below);
+    if (lane == 31) { cnt3[0] = base; cnt3[1] = below; cnt3[2] = nvalid; }
 }

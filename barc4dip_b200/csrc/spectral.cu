@@ -207,9 +207,10 @@ __device__ __forceinline__ void spec_accumulate(SpecAcc& s, float P, int ky, int
 __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
     if (whiten) {
         // 1 / (|G| + eps) from MUFU.RSQ and MUFU.RCP (a few ulp; the reference divides in float32 as well)
-        const float s2 = G.x * G.x + G.y * G.y;
-        const float mag = s2 > 0.f ? s2 * rsqrtf(s2) : 0.f;
-        const float inv = __fdividef(1.f, mag + eps);
+        const float s2 = fmaf(G.x, G.x, G.y * G.y);
+        float rs, inv;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s2, 1e-37f)));   // |G| = s2 * rsqrt(s2); 0 stays 0
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(s2, rs, eps)));
         G.x *= inv;
         G.y *= inv;
     }
@@ -585,7 +586,6 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     if (a.mag_mode == 2) {
         // fused median: census of the |.| values against the frame's bracket, straight from the registers, into this
         // warp's own region(s) of the frame's candidate store
-        const float Lf = Lk == 0u ? -INFINITY : __uint_as_float(Lk), Uf = Uk == 0xfffffffeu ? INFINITY : __uint_as_float(Uk);
         const int shift = bracket_shift(Lk, Uk);
         const int calls = a.pair_maps ? 1 : 2;
         const size_t reg = ((size_t)blk * 16 + warp) * calls;
@@ -595,11 +595,11 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         float v[16];
 #pragma unroll
         for (int s = 0; s < 16; ++s) v[s] = x[s].y;
-        census_values_region<16>(v, Lf, Uf, Lk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
+        census_values_region<16>(v, Lk, Uk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
         if (!a.pair_maps) {
 #pragma unroll
             for (int s = 0; s < 16; ++s) v[s] = x[s].x;
-            census_values_region<16>(v, Lf, Uf, Lk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
+            census_values_region<16>(v, Lk, Uk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
         }
     }
     // argmax partials (first occurrence in row-major order of the shifted map wins ties)

@@ -48,7 +48,7 @@ FFT_FLOPS_2048 = 5.0 * 2048 * 11            # 5 N log2 N per complex transform o
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
@@ -58,6 +58,7 @@ def parse_args():
     p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = automatic)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--prewarm", type=float, default=1.5, help="seconds of untimed load before the warm-up steps (clock ramp)")
     return p.parse_args()
 
 
@@ -251,7 +252,13 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     begin_stack()
-    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+    # clock ramp: a fresh box idles at low SM clocks and needs ~1 s of load to reach its steady state; these passes are
+    # neither warm-up steps nor timed steps (reported as config.prewarm_s)
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.prewarm:
+        step()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
         res = step()
     barrier()
     # sanity: the tracker must recover the integer shifts relative to rank 0's frame 0
@@ -345,8 +352,22 @@ def run_b200(args):
     algo = ALGO_BYTES_PER_FRAME.get(dom, ALGO_BYTES_PER_FRAME["frame_reduce"]) * scale
     per_launch_frames = frames_total / dom_launches if dom in ("rows_fwd", "cols", "rows_inv", "frame_reduce") else None
     achieved = algo * frames_total / (dom_ms / 1e3) / 1e9
+    # DRAM bytes the same kernel really moved (ncu --set full capture of this command, profiles/ncu_traffic.json)
+    traffic = traffic_pf = traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        names = {"cols": "cols_kernel", "rows_inv": "rows_inv_kernel", "rows_fwd": "rows_fwd_kernel", "frame_reduce": "frame_reduce2_kernel"}
+        ent = tj["kernels"].get(names.get(dom, dom))
+        if ent and n == 2048:
+            traffic_pf = float(ent["dram_bytes_per_frame"])
+            traffic = traffic_pf * (per_launch_frames or F)
+            traffic_src = tj.get("source")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_bytes_per_frame": traffic_pf, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "avg_launch_ms": dom_ms / dom_launches, "frames_per_launch": per_launch_frames,
                 "algorithmic_bytes_per_frame": algo, "share_of_kernel_time": dom_ms / tot_kernel_ms}
     step_bytes = ALGO_BYTES_PER_FRAME["step"] * scale
@@ -377,7 +398,7 @@ def run_b200(args):
                                f"phase-correlation tracking vs broadcast reference), {n}x{n} float32 frames (BASELINE configs[1..3] fused)",
                    "frames_per_step_per_gpu": F, "frame": [n, n], "parallelism": f"frame-sharded x{world}",
                    "l2": f"inputs per step {F * n * n * 4 / MB:.0f} MB + {2 * F * n * n * 4 / MB:.0f} MB of maps written: larger than the 126 MB L2, no flush needed",
-                   "internal_batch_frames": args.batch or "auto",
+                   "internal_batch_frames": args.batch or "auto", "prewarm_s": args.prewarm,
                    "tail_percentile_frames_needing_fallback": unresolved, "tracker_median_frames_needing_fallback": snr_unresolved},
         "clocks": clock_info, "e2e": e2e, "e2e_maps_to_host": e2e_maps, "gpu_launches": int(launches),
         "roofline": roofline, "step_roofline": step_roof, "fft_fp32": fp32, "kernels": kernel_table, "cpu_baseline": cpu,
