@@ -137,7 +137,7 @@ class Context:
 
     def profile_end(self) -> dict:
         """{class name: (milliseconds, launches)} of the kernels launched since profile_begin()."""
-        n = 14
+        n = 15   # B4D_PROF_NCLASS
         ms = (C.c_double * n)()
         cnt = (C.c_int64 * n)()
         self.check(self.lib.b4d_profile_end(self.handle, ms, cnt), "b4d_profile_end")

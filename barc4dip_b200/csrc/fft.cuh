@@ -202,19 +202,20 @@ __device__ __forceinline__ void ldg_tw4(const float2* p, float2& a, float2& b, f
 }
 
 // Barrier of the threads that share an exchange buffer. GROUP = 0: the whole CTA (__syncthreads). GROUP = 1: the N/16
-// threads of one transform only (named barrier 1 + group), legal when they are whole warps (BATCH == 1, N >= 512): the
-// independent transforms of a CTA then stop waiting for one another at every exchange. GROUP = 2: the first
+// threads of one transform only (named barrier 1 + group), legal when they are whole warps (BATCH == 1; for N < 512 the
+// caller pads the group to one warp with threads that repeat the work of the first N/16): the independent transforms
+// of a CTA then stop waiting for one another at every exchange. GROUP = 2: the first
 // BATCH * N/16 threads of the CTA (named barrier 15), the others having left for good or for other work.
 template <int N, int GROUP, int BATCH>
 __device__ __forceinline__ void fft_sync(int group) {
-    if (GROUP == 1) asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(N / 16) : "memory");
+    if (GROUP == 1) asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(N / 16 < 32 ? 32 : N / 16) : "memory");
     else if (GROUP == 2) asm volatile("bar.sync 15, %0;" ::"n"(BATCH * (N / 16)) : "memory");
     else __syncthreads();
 }
 
 template <int N, int DIR, int BATCH, int GROUP = 0>
 __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ z, const float2* __restrict__ twb, int group = 0) {
-    static_assert(GROUP != 1 || (BATCH == 1 && N >= 512), "group barriers need warp-aligned transforms");
+    static_assert(GROUP != 1 || BATCH == 1, "group barriers: one transform per group (N < 512: the caller pads the group to a warp)");
     static_assert(GROUP != 2 || (BATCH * (N / 16)) % 32 == 0, "sub-CTA barriers need whole warps");
     using P = Plan<N>;
     constexpr int T = N / 16;

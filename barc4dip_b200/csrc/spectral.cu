@@ -171,7 +171,8 @@ struct ColsArgs {
     float2* conj_out;           // blocked conj(F) (T, nx/2/TC, ny, TC)
     float2* conj_nyq_out;       // (T, ny)
     // autocorrelation branch
-    float2* i2_ac;              // blocked inverse-along-y of |F|^2
+    float2* i2_ac;              // blocked inverse-along-y of |F|^2 (with a product branch: column pairs packed, see below)
+    float2* i2_ac_nyq;          // (T, ny) inverse-along-y of the Nyquist column's |F|^2 (packed variant only)
     double* ac_partials;        // (T, ntiles) sum of the full-spectrum |F|^2 owned by the tile
     // product branch: G = F * R (optionally whitened), inverse along y -> i2_pc
     float2* i2_pc;
@@ -406,14 +407,36 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
 #pragma unroll
         for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
     }
-    if (PC && AC) {                                   // second inverse: |F|^2 kept in Bp
+    if (PC && AC) {
+        // Second inverse: |F|^2 kept in Bp. Its columns are real, so two of them (c2 and c2 + CW/2) share one complex
+        // transform, z = IFFT_y(P_a) + i IFFT_y(P_b); each part is Hermitian in y and rows_inv_ac_kernel separates them
+        // from rows y and -y. Only the first half of the CTA (whole warps) carries these CW/2 transforms; in tile 0 four
+        // more warps transform the Nyquist column. The packed intermediate has nx/4 columns: tile-major, column
+        // tile * CW/2 + c2 in the usual blocked layout.
+        constexpr int CH = CW / 2, NTH = T * CH;
         asm volatile("" ::: "memory");                // the loads below must not be hoisted over the first inverse
+        __syncthreads();                              // everybody is done with A
+        if (tid < NTH) {
+            const int c2 = tid % CH, j2 = tid / CH;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[tid + s * NT], nyq_owner ? Pns[j + s * T] : 0.f);
-        fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
-        float2* o = a.i2_ac + g0;
+            for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[j2 * CW + c2 + s * NT], Bp[j2 * CW + c2 + CH + s * NT]);
+            fft_regs<NY, +1, CH, 2>(x, j2, A + c2, a.tw);
+            const int pc = tile * CH + c2;
+            float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + (size_t)j2 * TC + (pc % TC);
 #pragma unroll
-        for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
+            for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
+        } else if (TILE0 && tid < NTH + (T < 32 ? 32 : T)) {
+            // (T < 32: the group is padded to a warp, the extra threads repeat the work of the first T)
+            const int j3 = (tid - NTH) % T;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) x[s] = make_float2(Pns[j3 + s * T], 0.f);
+            fft_regs<NY, +1, 1, 1>(x, j3, A + PL * CH, a.tw, 1);
+            if (tid - NTH < T) {
+                float2* o = a.i2_ac_nyq + (size_t)t * NY + j3;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) o[s * T] = x[s];
+            }
+        }
     }
 }
 
@@ -621,6 +644,172 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
             for (int w = 1; w < 16; ++w) { best_update(bA, s_best[0][w].v, s_best[0][w].idx); best_update(bB, s_best[1][w].v, s_best[1][w].idx); }
             if (a.bestA) a.bestA[(size_t)t * a.nblk + blk] = bA;
             if (a.pair_maps && a.bestB) a.bestB[(size_t)t * a.nblk + blk] = bB;
+        }
+    }
+}
+
+// =================================================================================================
+// K3b: rows inverse of the packed autocorrelation intermediate (fused pipeline)
+// =================================================================================================
+// cols_kernel<.., AC, PC> leaves z = IFFT_y(P_a) + i IFFT_y(P_b) for the column pairs (a, b = a + cw/2) of every tile
+// of cw columns. P is real, so g_a(y) = IFFT_y(P_a) is Hermitian in y and
+//     g_a(y) = (z(y) + conj z(-y)) / 2,      g_b(y) = (z(y) - conj z(-y)) / (2i).
+// The autocorrelation is point symmetric, ac(-y, -x) = ac(y, x): only the rows y = 0 .. ny/2 are transformed (two rows
+// per complex transform, as in rows_inv_kernel) and every row is stored twice, as it is and mirrored.
+struct RowsInvAcArgs {
+    const float2* Iz;       // packed blocked intermediate (T, nx/4/TC, ny, TC)
+    const float2* Inyq;     // (T, ny) inverse-along-y of the Nyquist column
+    const float2* tw;
+    int ny;
+    int ch_log2;            // log2(cw / 2): pairing distance of the column pass
+    float* out;             // (T, ny, nx) shifted map
+    const double* norm;     // per-frame partials whose sum is the peak (nullable -> scale)
+    int n_norm;
+    double norm_mult;
+    double scale;
+    ArgBest* best;          // (T, gridDim.x) argmax partials (nullable)
+};
+
+template <int NX>
+__global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
+    constexpr int TPF = NX / 16;
+    constexpr int WPG = TPF / 8;
+    constexpr int GPC = 16 / WPG;
+    constexpr int FPC = 4 * GPC;
+    constexpr int FS = padded_len(NX) + 2;            // transforms 4 words apart in bank space (the gather writes pairs)
+    constexpr int HX = NX / 2;
+    extern __shared__ float2 sm[];
+    __shared__ float s_scale;
+    __shared__ float s_max[16];
+    __shared__ unsigned s_idx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t t = blockIdx.y;
+    const int NY = a.ny;
+    const int y0 = blockIdx.x * 2 * FPC;
+    const float2* Iz = a.Iz + (size_t)t * NY * (HX / 2);
+    if (tid == 0) s_idx = 0xffffffffu;
+
+    // ---- gather: each thread fetches z(ya), z(-ya), z(yb), z(-yb) of 4 packed columns, i.e. 8 values of k
+    {
+        const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
+        const int f = grp * 4 + fl, jg = jt * 8 + c;
+        const int ya = y0 + 2 * f, yb = ya + 1;
+        const int ma = (NY - ya) & (NY - 1), mb = NY - yb;
+        float2 za[4], zam[4], zb[4], zbm[4];
+        {
+            const size_t tstride = (size_t)(TPF / TC) * NY * TC;
+            const float2* p = Iz + (size_t)(jg / TC) * NY * TC + (jg % TC);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                za[m] = __ldcs(p + m * tstride + (size_t)ya * TC);
+                zam[m] = __ldcs(p + m * tstride + (size_t)ma * TC);
+                zb[m] = __ldcs(p + m * tstride + (size_t)yb * TC);
+                zbm[m] = __ldcs(p + m * tstride + (size_t)mb * TC);
+            }
+        }
+        float nya = 0.f, nyb = 0.f;
+        if (jg == 0) {
+            nya = a.Inyq[(size_t)t * NY + ya].x;
+            nyb = a.Inyq[(size_t)t * NY + yb].x;
+        }
+        if (warp == 0) {
+            double sc = a.scale;
+            if (a.norm) {
+                double part = 0.0;
+                for (int i = lane; i < a.n_norm; i += 32) part += a.norm[(size_t)t * a.n_norm + i];
+                part = warp_sum(part);
+                sc = part > 0.0 ? a.norm_mult / part : a.scale;
+            }
+            if (lane == 0) s_scale = (float)sc;
+        }
+        __syncthreads();
+        const float sA = s_scale, sH = 0.5f * sA;
+        float2* z = sm + f * FS;
+        const int chm = (1 << a.ch_log2) - 1;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int pc = jg + m * TPF;
+            const int ka = ((pc >> a.ch_log2) << (a.ch_log2 + 1)) + (pc & chm), kb = ka + chm + 1;
+            // rows ya (g1) and yb (g2) of the two columns
+            const float2 g1a = make_float2(sH * (za[m].x + zam[m].x), sH * (za[m].y - zam[m].y));
+            const float2 g1b = make_float2(sH * (za[m].y + zam[m].y), sH * (zam[m].x - za[m].x));
+            const float2 g2a = make_float2(sH * (zb[m].x + zbm[m].x), sH * (zb[m].y - zbm[m].y));
+            const float2 g2b = make_float2(sH * (zb[m].y + zbm[m].y), sH * (zbm[m].x - zb[m].x));
+            if (ka == 0) {
+                z[pad16(0)] = make_float2(g1a.x, g2a.x);
+                z[pad16(HX)] = make_float2(sA * nya, sA * nyb);
+            } else {
+                z[pad16(ka)] = make_float2(g1a.x - g2a.y, g1a.y + g2a.x);
+                z[pad16(NX - ka)] = make_float2(g1a.x + g2a.y, g2a.x - g1a.y);
+            }
+            z[pad16(kb)] = make_float2(g1b.x - g2b.y, g1b.y + g2b.x);
+            z[pad16(NX - kb)] = make_float2(g1b.x + g2b.y, g2b.x - g1b.y);
+        }
+        __syncthreads();
+    }
+
+    // ---- transform (natural mapping), outputs stay in registers
+    const int f = tid / TPF, j = tid % TPF;
+    float2* z = sm + f * FS;
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
+    fft_regs<NX, +1, 1, (NX >= 1024)>(x, j, z, a.tw, f);
+
+    // ---- stores: real part -> row ya, imaginary part -> row yb, each also mirrored through the centre of the shifted
+    //      map: (r, c) -> ((ny - r) % ny, (nx - c) % nx). Rows 0 and ny/2 (shifted ny/2 and 0) are their own mirrors.
+    const int ya = y0 + 2 * f, yb = ya + 1;
+    const bool mainA = ya <= NY / 2, mirA = ya >= 1 && ya < NY / 2, mainB = yb <= NY / 2, mirB = yb < NY / 2;
+    const unsigned rA = (unsigned)((ya + NY / 2) & (NY - 1)), rB = (unsigned)((yb + NY / 2) & (NY - 1));
+    const unsigned rAm = (unsigned)((NY - rA) & (NY - 1)), rBm = (unsigned)((NY - rB) & (NY - 1));
+    float* o = a.out + (size_t)t * NY * NX;
+    float* pA = o + (size_t)rA * NX + j;
+    float* pB = o + (size_t)rB * NX + j;
+    float* pAm = o + (size_t)rAm * NX + (NX - j);     // slot o >= 1 lands at pAm[-TPF o]; slot 0 at column (NX - j) % NX
+    float* pBm = o + (size_t)rBm * NX + (NX - j);
+    const int wrap0 = j == 0 ? -NX : 0;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int oo = 0; oo < 16; ++oo) {
+        const int s = (oo + 8) & 15;
+        const float va = x[s].x, vb = x[s].y;
+        const int mo = oo == 0 ? wrap0 : -TPF * oo;
+        if (mainA) { pA[TPF * oo] = va; mx = fmaxf(mx, va); }
+        if (mirA) pAm[mo] = va;
+        if (mainB) { pB[TPF * oo] = vb; mx = fmaxf(mx, vb); }
+        if (mirB) pBm[mo] = vb;
+    }
+    // ---- argmax partial: block maximum first, then the smallest linear index (of either copy) that holds it
+    if (a.best) {
+        float wm = mx;
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, q));
+        if (lane == 0) s_max[warp] = wm;
+        __syncthreads();
+        float bm = s_max[0];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) bm = fmaxf(bm, s_max[w]);
+        if (mx == bm) {
+            unsigned best = 0xffffffffu;
+#pragma unroll
+            for (int oo = 0; oo < 16; ++oo) {
+                const int s = (oo + 8) & 15;
+                const unsigned col = (unsigned)(j + TPF * oo), colm = (unsigned)((NX - (int)col) & (NX - 1));
+                if (mainA && x[s].x == bm) {
+                    best = min(best, rA * (unsigned)NX + col);
+                    if (mirA) best = min(best, rAm * (unsigned)NX + colm);
+                }
+                if (mainB && x[s].y == bm) {
+                    best = min(best, rB * (unsigned)NX + col);
+                    if (mirB) best = min(best, rBm * (unsigned)NX + colm);
+                }
+            }
+            atomicMin(&s_idx, best);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ArgBest b = {bm, s_idx};
+            a.best[(size_t)t * gridDim.x + blockIdx.x] = b;
         }
     }
 }
@@ -1008,9 +1197,25 @@ int launch_rows_inv(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
     return B4D_OK;
 }
 
+template <int NX>
+int launch_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& a, int64_t T, int* nblk_out) {
+    constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
+    constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 2) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_ac_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int rows = 2 * FPC, nblk = (a.ny / 2 + 1 + rows - 1) / rows;
+    if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
+    ProfScope ps(ctx, KC_ROWS_INV_AC);
+    rows_inv_ac_kernel<NX><<<dim3(nblk, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    B4D_LAUNCH_CHECK(ctx);
+    *nblk_out = nblk;
+    return B4D_OK;
+}
+
 // CTAs per frame of the column pass (= number of per-frame partial sums it leaves behind)
 int cols_cw_2048();
-int cols_tiles(int ny, int nx) { return nx / 2 / (ny >= 2048 ? cols_cw_2048() : TC); }
+int cols_cw(int ny) { return ny >= 2048 ? cols_cw_2048() : TC; }
+int cols_tiles(int ny, int nx) { return nx / 2 / cols_cw(ny); }
 
 int rows_inv_blocks(int nx, int ny, int pair_maps) {
     const int tpf = nx / 16, wpg = tpf / 8, gpc = 16 / wpg, fpc = 4 * gpc;
@@ -1041,6 +1246,7 @@ struct Work {
     float2* H = nullptr;
     float2* I2a = nullptr;
     float2* I2b = nullptr;
+    float2* I2nyq = nullptr;    // (T, ny) Nyquist column of the packed autocorrelation intermediate
     double* acp = nullptr;
     double* spp = nullptr;
     ArgBest* bestA = nullptr;
@@ -1065,7 +1271,8 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
                  o_spp = take(sizeof(double) * T * ntiles * NSP), o_ba = take(sizeof(ArgBest) * T * nblk),
                  o_bb = take(sizeof(ArgBest) * T * nblk), o_pi = take(sizeof(unsigned) * T), o_pv = take(sizeof(float) * T),
-                 o_med = take(sizeof(float) * 2 * T), o_nv = take(sizeof(long long) * T);
+                 o_med = take(sizeof(float) * 2 * T), o_nv = take(sizeof(long long) * T),
+                 o_nyq = take(sizeof(float2) * T * ny);
     rc = b4d_scratch(ctx, SCR_MISC, small + 1024, &p);
     if (rc) return rc;
     char* base = static_cast<char*>(p) + 512;   // first 512 B reserved (quantiles upload)
@@ -1078,6 +1285,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->pk_val = reinterpret_cast<float*>(base + o_pv);
     w->med = reinterpret_cast<float*>(base + o_med);
     w->nvalid = reinterpret_cast<long long*>(base + o_nv);
+    w->I2nyq = reinterpret_cast<float2*>(base + o_nyq);
     return B4D_OK;
 }
 
@@ -1127,6 +1335,13 @@ int run_rows_inv(b4d_ctx* ctx, RowsInvArgs& r, int64_t T, int nx, int grid_block
     int rc = get_twiddle_bases(ctx, nx, &r.tw);
     if (rc) return rc;
     DISPATCH_N(nx, rc = launch_rows_inv<N_>(ctx, r, T, grid_blocks));
+    return rc;
+}
+
+int run_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& r, int64_t T, int nx, int* nblk) {
+    int rc = get_twiddle_bases(ctx, nx, &r.tw);
+    if (rc) return rc;
+    DISPATCH_N(nx, rc = launch_rows_inv_ac<N_>(ctx, r, T, nblk));
     return rc;
 }
 
@@ -1548,8 +1763,8 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         // scratch maps: |corr| always, autocorr when the caller does not keep it
         void* p = nullptr;
         // tracker: fused median (sample rows + 3x3 window instead of the |corr| map) unless the frame is too small
-        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx, want_ac ? 1 : 0) : 0;
-        const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, want_ac ? 1 : 0, ns, tc) + 63) & ~size_t(63)) : npix * tc);
+        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx, 0) : 0;
+        const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, 0, ns, tc) + 63) & ~size_t(63)) : npix * tc);
         const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) +
                             sizeof(double) * B4D_FR_NCOLS * tc + 256;
         if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
@@ -1569,7 +1784,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         ColsArgs c = cols_defaults(w, nx, true);
         c.psd_out = psd_out ? psd_out + (size_t)t0 * npix : nullptr;
         c.psd_scale = psd_scale;
-        if (want_ac) { c.i2_ac = w.I2a; c.ac_partials = w.acp; }
+        if (want_ac) { c.i2_ac = w.I2a; c.i2_ac_nyq = w.I2nyq; c.ac_partials = w.acp; }
         if (want_pc) {
             c.i2_pc = w.I2b;
             c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
@@ -1582,13 +1797,18 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
         r.ny = ny;
-        int nblk;
+        int nblk, nblk_ac = 0;
         if (want_ac && want_pc) {
-            r.Ia = w.I2a; r.Ib = w.I2b; r.pair_maps = 1;
-            r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = cols_tiles(ny, nx); r.norm_mult = 1.0; r.scaleA = 1.0 / ((double)nx * ny);
-            r.bestA = grain_out ? w.bestA : nullptr;
-            r.outB = mag; r.kindB = 1; r.scaleB = 1.0 / ((double)nx * ny); r.bestB = w.bestB;
-            nblk = rows_inv_blocks(nx, ny, 1);
+            // the column pass left the autocorrelation branch packed (two real columns per transform): its own row pass
+            // over the rows 0 .. ny/2, then the tracker's rows on their own (two rows per transform)
+            RowsInvAcArgs ra;
+            memset(&ra, 0, sizeof(ra));
+            ra.Iz = w.I2a; ra.Inyq = w.I2nyq; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny) / 2);
+            ra.out = acm; ra.norm = w.acp; ra.n_norm = cols_tiles(ny, nx); ra.norm_mult = 1.0; ra.scale = 1.0 / ((double)nx * ny);
+            ra.best = grain_out ? w.bestA : nullptr;
+            if ((rc = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac))) return rc;
+            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
+            nblk = rows_inv_blocks(nx, ny, 0);
         } else if (want_ac) {
             r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = cols_tiles(ny, nx); r.norm_mult = 1.0;
             r.scaleA = 1.0 / ((double)nx * ny); r.bestA = grain_out ? w.bestA : nullptr;
@@ -1604,7 +1824,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         }
         if (grain_out) {
             if ((rc = ensure_theta(ctx))) return rc;
-            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
+            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac ? nblk_ac : nblk, w.pk_idx, w.pk_val);
             B4D_LAUNCH_CHECK(ctx);
             ProfScope ps(ctx, KC_GRAIN);
             grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx, ctx->fft->theta, 0.36787944117144233,

@@ -209,3 +209,39 @@ def test_fused_median_flags_degenerate_frames_and_falls_back():
     finally:
         ctx.set_fused_median(True)
     np.testing.assert_array_equal(tab[1:], plain[1:])
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 256), (512, 512), (256, 1024), (1024, 128), (2048, 2048)])
+def test_pipeline_autocorr_packed_path_vs_oracle(shape):
+    """With tracking on, the fused pipeline packs two real |F|^2 columns per inverse transform and transforms only the
+    rows 0..ny/2 of the autocorrelation, mirroring the rest (point symmetry). The map must equal the reference's
+    autocorr2d within 1e-5 of the peak (north_star), agree with the unpacked b4d_autocorr2d path, be exactly point
+    symmetric off the two self-mirrored rows, and give the same grain widths."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 7 + nx)
+    if ny == nx:
+        stack, _ = synth.tracking_stack(3, ny, grain=5.0, seed=11, integer_every=2)
+    else:
+        stack = (1000.0 + 200.0 * rng.standard_normal((3, ny, nx))).astype(np.float32)
+        stack += 50.0 * np.sin(np.arange(nx) * 0.05)[None, None, :].astype(np.float32)
+    d = engine.as_stack(stack)
+    engine.PhaseTracker(stack[0], (ny, nx), y0=0, x0=0)
+    res = engine.stack_pipeline(d, want_psd=False, want_grain=(ny == nx), tail_quantiles=None)
+    got = res["autocorr"].cpu().numpy()
+    plain, grain_plain = engine.autocorr2d(d, want_grain=(ny == nx))
+    plain = plain.cpu().numpy()
+    for t in range(3):
+        want = orc.autocorr2d(stack[t])[0]
+        assert np.max(np.abs(got[t] - want)) <= 1e-5, (shape, t)
+        assert np.max(np.abs(got[t] - plain[t])) <= 2e-6
+        assert abs(got[t, ny // 2, nx // 2] - 1.0) <= 1e-6
+        # point symmetry through the centre of the shifted map: (r, c) <-> (-r mod ny, -c mod nx); copies are bit-equal
+        mir = np.roll(got[t][::-1, ::-1], (1, 1), axis=(0, 1))
+        rows = np.ones(ny, bool)
+        rows[[0, ny // 2]] = False
+        np.testing.assert_array_equal(got[t][rows], mir[rows])
+        assert np.max(np.abs(got[t] - mir)) <= 1e-6
+    if ny == nx:
+        np.testing.assert_allclose(res["grain"].cpu().numpy(), grain_plain, rtol=1e-5)
