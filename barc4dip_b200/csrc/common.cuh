@@ -37,6 +37,8 @@ struct b4d_ctx {
     size_t scratch_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FftPlanCache* fft = nullptr;
     int64_t batch_override = 0;       // frames per internal batch of the FFT pipeline (0 = automatic)
+    size_t batch_key[4] = {0, 0, 0, 0};   // automatic batch sizes already worked out: per-frame scratch bytes -> frames
+    int64_t batch_val[4] = {0, 0, 0, 0};
     bool fused_median = true;         // tracker SNR: median of |corr| taken inside the inverse row pass (no map)
     bool prof_on = false;
     std::vector<ProfSpan> prof_spans;

@@ -103,10 +103,12 @@ struct RowsFwdArgs {
     float2* H;
     const float2* tw;
     int ny;
+    double* mom;          // nullable: (T, gridDim.x, 2) per-CTA sums of d = x - K and of d^2 (z-score of the tracker)
 };
 
 template <int NX>
 __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
+    __shared__ double s_mom[16][2];
     constexpr int TPF = NX / 16;          // threads per transform
     constexpr int FPC = 512 / TPF;        // transforms per CTA
     constexpr int ROWS = 2 * FPC;
@@ -131,7 +133,22 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
         }
         x[m] = make_float2(va - K, vb - K);
     }
+    if (a.mom) {
+        // the tracker z-scores the frame (tracking.py:308-311): its mean and standard deviation come from these sums,
+        // 32 pixels in fp32 per thread, fp64 from there on, fixed order
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) { s1 = __fadd2_rn(s1, x[m]); s2 = __ffma2_rn(x[m], x[m], s2); }
+        const double w1 = warp_sum((double)s1.x + (double)s1.y), w2 = warp_sum((double)s2.x + (double)s2.y);
+        if ((tid & 31) == 0) { s_mom[tid >> 5][0] = w1; s_mom[tid >> 5][1] = w2; }
+    }
     fft_regs_to_smem<NX, -1, 1, (NX >= 1024)>(x, j, sm + f * FS, a.tw, f);
+    if (a.mom && tid < 2) {                           // (fft_regs_to_smem ends with a __syncthreads)
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) v += s_mom[w][tid];
+        a.mom[((size_t)t * gridDim.x + blockIdx.x) * 2 + tid] = v;
+    }
 
     // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
     float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
@@ -171,7 +188,7 @@ struct ColsArgs {
     float2* conj_out;           // blocked conj(F) (T, nx/2/TC, ny, TC)
     float2* conj_nyq_out;       // (T, ny)
     // autocorrelation branch
-    float2* i2_ac;              // blocked inverse-along-y of |F|^2 (with a product branch: column pairs packed, see below)
+    float2* i2_ac;              // inverse-along-y of |F|^2, column pairs packed (see the end of cols_kernel): (T, nx/4/TC, ny, TC)
     float2* i2_ac_nyq;          // (T, ny) inverse-along-y of the Nyquist column's |F|^2 (packed variant only)
     double* ac_partials;        // (T, ntiles) sum of the full-spectrum |F|^2 owned by the tile
     // product branch: G = F * R (optionally whitened), inverse along y -> i2_pc
@@ -233,8 +250,8 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
     constexpr int PL = padded_len(NY);
     constexpr int GS = T * TC;                        // global distance (float2) between a thread's consecutive elements
     float2* A = sm;                                   // [PL][CW] exchange buffer
-    float* Bp = reinterpret_cast<float*>(sm + PL * CW);   // [NY][CW] |F|^2 (AC && PC)
-    float* Pns = Bp + NY * CW;                        // [NY] |F_nyquist|^2 (AC && PC, tile 0)
+    float* Bp = reinterpret_cast<float*>(sm + PL * CW);   // [NY][CW] |F|^2 (AC)
+    float* Pns = Bp + NY * CW;                        // [NY] |F_nyquist|^2 (AC, tile 0)
 
     const int tid = threadIdx.x, c = tid % CW, j = tid / CW;
     const int tile = blockIdx.x, ntiles = gridDim.x;
@@ -326,12 +343,8 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
             if (AC) {
                 if (a.ac_zero_dc && nyq_owner && ky == 0) Pa = 0.f;
                 acsum += fmaf(wgt, Pa, Pn);
-                if (PC) {
-                    Bp[tid + s * NT] = Pa;
-                    if (nyq_owner) Pns[ky] = Pn;
-                } else {
-                    x[s] = make_float2(Pa, Pn);
-                }
+                Bp[tid + s * NT] = Pa;
+                if (nyq_owner) Pns[ky] = Pn;
             }
         }
     }
@@ -400,15 +413,15 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
     }
     if (!PC && !AC) return;
 
-    // ---- inverse along y of the product (or of |F|^2 when there is no product branch) ----------------
-    fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
-    {
-        float2* o = (PC ? a.i2_pc : a.i2_ac) + g0;
+    // ---- inverse along y of the product ---------------------------------------------------------
+    if (PC) {
+        fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
+        float2* o = a.i2_pc + g0;
 #pragma unroll
         for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
     }
-    if (PC && AC) {
-        // Second inverse: |F|^2 kept in Bp. Its columns are real, so two of them (c2 and c2 + CW/2) share one complex
+    if (AC) {
+        // Inverse along y of |F|^2, kept in Bp. Its columns are real, so two of them (c2 and c2 + CW/2) share one complex
         // transform, z = IFFT_y(P_a) + i IFFT_y(P_b); each part is Hermitian in y and rows_inv_ac_kernel separates them
         // from rows y and -y. Only the first half of the CTA (whole warps) carries these CW/2 transforms; in tile 0 four
         // more warps transform the Nyquist column. The packed intermediate has nx/4 columns: tile-major, column
@@ -817,6 +830,27 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
 // =================================================================================================
 // small kernels
 // =================================================================================================
+// mean and variance of a frame from the per-CTA sums of rows_fwd_kernel, into the frame-reduction table columns the
+// column pass reads (B4D_FR_MEAN, B4D_FR_M2); fixed summation order
+__global__ void __launch_bounds__(32) rows_moments_finalize_kernel(const double* __restrict__ mom, int nblk, const float* __restrict__ pilot,
+                                                                   double npix, double* __restrict__ fr) {
+    const int64_t t = blockIdx.x;
+    const int lane = threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < nblk; b += 32) { s1 += mom[((size_t)t * nblk + b) * 2]; s2 += mom[((size_t)t * nblk + b) * 2 + 1]; }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+        const double a1 = s1 / npix, a2 = s2 / npix;
+        double m2 = a2 - a1 * a1;
+        if (m2 < 0) m2 = 0;
+        double* o = fr + t * B4D_FR_NCOLS;
+        for (int i = 0; i < B4D_FR_NCOLS; ++i) o[i] = nan("");
+        o[B4D_FR_COUNT] = npix; o[B4D_FR_NPIX] = npix;
+        o[B4D_FR_MEAN] = (double)pilot[t] + a1;
+        o[B4D_FR_M2] = m2;
+    }
+}
+
 
 // peak location from the argmax partials: out_idx[t] = shifted linear index, out_val[t] = value
 __global__ void __launch_bounds__(128) argmax_reduce_kernel(const ArgBest* __restrict__ part, int n,
@@ -1142,7 +1176,7 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
 template <int NY, int CW, bool SPEC, bool AC, bool PC>
 int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     constexpr size_t smem = (size_t)padded_len(NY) * CW * sizeof(float2) +
-                            ((AC && PC) ? (size_t)NY * CW * sizeof(float) + (size_t)NY * sizeof(float) : 0);
+                            (AC ? (size_t)NY * CW * sizeof(float) + (size_t)NY * sizeof(float) : 0);
     static bool attr = false;
     if (!attr) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, CW, SPEC, AC, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1247,6 +1281,7 @@ struct Work {
     float2* I2a = nullptr;
     float2* I2b = nullptr;
     float2* I2nyq = nullptr;    // (T, ny) Nyquist column of the packed autocorrelation intermediate
+    double* mom = nullptr;      // (T, ny, 2) generous: per-CTA moment sums of the forward row pass
     double* acp = nullptr;
     double* spp = nullptr;
     ArgBest* bestA = nullptr;
@@ -1272,7 +1307,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
                  o_spp = take(sizeof(double) * T * ntiles * NSP), o_ba = take(sizeof(ArgBest) * T * nblk),
                  o_bb = take(sizeof(ArgBest) * T * nblk), o_pi = take(sizeof(unsigned) * T), o_pv = take(sizeof(float) * T),
                  o_med = take(sizeof(float) * 2 * T), o_nv = take(sizeof(long long) * T),
-                 o_nyq = take(sizeof(float2) * T * ny);
+                 o_nyq = take(sizeof(float2) * T * ny), o_mom = take(sizeof(double) * 2 * T * ny);
     rc = b4d_scratch(ctx, SCR_MISC, small + 1024, &p);
     if (rc) return rc;
     char* base = static_cast<char*>(p) + 512;   // first 512 B reserved (quantiles upload)
@@ -1286,6 +1321,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->med = reinterpret_cast<float*>(base + o_med);
     w->nvalid = reinterpret_cast<long long*>(base + o_nv);
     w->I2nyq = reinterpret_cast<float2*>(base + o_nyq);
+    w->mom = reinterpret_cast<double*>(base + o_mom);
     return B4D_OK;
 }
 
@@ -1305,16 +1341,23 @@ int ensure_theta(b4d_ctx* ctx) {
 }
 
 // rows forward for a batch, pilot included
+// fr_moments: the row pass also sums x - K and (x - K)^2 and the table's mean / variance columns are filled from them
 int run_rows_fwd(b4d_ctx* ctx, const float* stack, int64_t T, int ny, int nx, const float* gain, const float* dark,
-                 Work& w, bool use_pilot, bool pilot_ready = false) {
+                 Work& w, bool use_pilot, bool pilot_ready = false, double* fr_moments = nullptr) {
     int rc;
     if (use_pilot && !pilot_ready) { rc = b4d_frame_pilot_launch(ctx, stack, T, (int64_t)ny * nx, gain, dark, w.pilot); if (rc) return rc; }
     RowsFwdArgs a;
     a.stack = stack; a.gain = gain; a.dark = dark; a.pilot = use_pilot ? w.pilot : nullptr; a.H = w.H; a.ny = ny;
+    a.mom = fr_moments ? w.mom : nullptr;
     rc = get_twiddle_bases(ctx, nx, &a.tw);
     if (rc) return rc;
     DISPATCH_N(nx, rc = launch_rows_fwd<N_>(ctx, a, T));
-    return rc;
+    if (rc || !fr_moments) return rc;
+    if (!use_pilot) return b4d_fail(ctx, B4D_ERR_INVALID, "rows_fwd: moments need the pilot shift");
+    const int tpf = nx / 16, rows = 2 * (512 / tpf);
+    rows_moments_finalize_kernel<<<(unsigned)T, 32, 0, ctx->stream>>>(w.mom, ny / rows, w.pilot, (double)ny * nx, fr_moments);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
 }
 
 ColsArgs cols_defaults(const Work& w, int nx, bool use_pilot) {
@@ -1351,6 +1394,8 @@ int run_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& r, int64_t T, int nx, int* nblk
 int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
     if (ctx->batch_override > 0) return ctx->batch_override;
     const size_t per = (size_t)ny * (nx / 2) * sizeof(float2) * (size_t)n_intermediates;
+    // cudaMemGetInfo takes driver-wide locks (milliseconds now and then): ask once per scratch footprint
+    for (int i = 0; i < 4; ++i) if (ctx->batch_key[i] == per && ctx->batch_val[i] > 0) return ctx->batch_val[i];
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
     size_t held = 0;                                  // scratch already owned by this context counts as available
@@ -1358,6 +1403,7 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
     int64_t b = (int64_t)(((free_b + held) / 4) / (per ? per : 1));
     if (b < 1) b = 1;
     if (b > 128) b = 128;
+    for (int i = 0; i < 4; ++i) if (ctx->batch_val[i] == 0 || i == 3) { ctx->batch_key[i] = per; ctx->batch_val[i] = b; break; }
     return b;
 }
 
@@ -1463,18 +1509,19 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
     ColsArgs c = cols_defaults(w, nx, true);
     c.zero_dc = zero_dc;
     c.i2_ac = w.I2a;
+    c.i2_ac_nyq = w.I2nyq;
     c.ac_partials = w.acp;
     if ((rc = run_cols(ctx, c, tc, ny))) return rc;
-    RowsInvArgs r;
+    RowsInvAcArgs r;
     memset(&r, 0, sizeof(r));
-    r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = out_ac; r.kindA = 0;
-    r.normA = use_norm ? w.acp : nullptr; r.n_normA = cols_tiles(ny, nx); r.norm_mult = norm_mult;
-    r.scaleA = 1.0 / ((double)nx * (double)ny);
-    r.bestA = grain_out ? w.bestA : nullptr;
-    if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+    r.Iz = w.I2a; r.Inyq = w.I2nyq; r.ny = ny; r.ch_log2 = log2i(cols_cw(ny) / 2); r.out = out_ac;
+    r.norm = use_norm ? w.acp : nullptr; r.n_norm = cols_tiles(ny, nx); r.norm_mult = norm_mult;
+    r.scale = 1.0 / ((double)nx * (double)ny);
+    r.best = grain_out ? w.bestA : nullptr;
+    int nblk = 0;
+    if ((rc = run_rows_inv_ac(ctx, r, tc, nx, &nblk))) return rc;
     if (grain_out) {
         if ((rc = ensure_theta(ctx))) return rc;
-        const int nblk = rows_inv_blocks(nx, ny, 0);
         argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk, w.pk_idx, w.pk_val);
         B4D_LAUNCH_CHECK(ctx);
         ProfScope ps(ctx, KC_GRAIN);
@@ -1715,8 +1762,8 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
         if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(double) * B4D_FR_NCOLS * tc + sizeof(float) * map_floats + 256, &p))) return rc;
         double* fr = static_cast<double*>(p);
         float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
-        if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, fr, nullptr, w.pilot))) return rc;
-        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w, true, true))) return rc;
+        // mean and standard deviation for the z-score come out of the forward row pass (no separate reduction pass)
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w, true, false, fr))) return rc;
         ColsArgs c = cols_defaults(w, nx, true);
         c.i2_pc = w.I2b;
         c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
@@ -1797,34 +1844,29 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
         r.ny = ny;
-        int nblk, nblk_ac = 0;
-        if (want_ac && want_pc) {
+        int nblk = 0, nblk_ac = 0;
+        if (want_ac) {
             // the column pass left the autocorrelation branch packed (two real columns per transform): its own row pass
-            // over the rows 0 .. ny/2, then the tracker's rows on their own (two rows per transform)
+            // over the rows 0 .. ny/2; the tracker's rows go on their own (two rows per transform)
             RowsInvAcArgs ra;
             memset(&ra, 0, sizeof(ra));
             ra.Iz = w.I2a; ra.Inyq = w.I2nyq; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny) / 2);
             ra.out = acm; ra.norm = w.acp; ra.n_norm = cols_tiles(ny, nx); ra.norm_mult = 1.0; ra.scale = 1.0 / ((double)nx * ny);
             ra.best = grain_out ? w.bestA : nullptr;
             if ((rc = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac))) return rc;
-            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
-            nblk = rows_inv_blocks(nx, ny, 0);
-        } else if (want_ac) {
-            r.Ia = w.I2a; r.pair_maps = 0; r.outA = acm; r.kindA = 0; r.normA = w.acp; r.n_normA = cols_tiles(ny, nx); r.norm_mult = 1.0;
-            r.scaleA = 1.0 / ((double)nx * ny); r.bestA = grain_out ? w.bestA : nullptr;
-            nblk = rows_inv_blocks(nx, ny, 0);
-        } else {
-            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
-            nblk = rows_inv_blocks(nx, ny, 0);
         }
-        if (want_pc && ns) {
-            if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4))) return rc;
-        } else if (want_ac || want_pc) {
-            if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+        if (want_pc) {
+            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
+            nblk = rows_inv_blocks(nx, ny, 0);
+            if (ns) {
+                if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4))) return rc;
+            } else {
+                if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+            }
         }
         if (grain_out) {
             if ((rc = ensure_theta(ctx))) return rc;
-            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac ? nblk_ac : nblk, w.pk_idx, w.pk_val);
+            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac, w.pk_idx, w.pk_val);
             B4D_LAUNCH_CHECK(ctx);
             ProfScope ps(ctx, KC_GRAIN);
             grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx, ctx->fft->theta, 0.36787944117144233,

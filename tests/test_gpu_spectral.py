@@ -179,12 +179,16 @@ def test_fused_median_equals_map_based_path(n):
         ctx.set_fused_median(True)
     assert not bool(torch.isnan(fused[1:, 3]).any())
     np.testing.assert_array_equal(fused[1:].cpu().numpy(), plain[1:].cpu().numpy())
-    # the fused pipeline packs autocorrelation and |corr| rows into shared inverse transforms: same numbers up to
-    # float32 rounding of a different operation order
+    # The fused pipeline takes the frame mean from the reduction pass, the tracker from its forward row pass: the two
+    # agree to a few ulp, but the DC bin of a mean-removed frame is nothing but that rounding residue and whitening
+    # turns it into a unit phasor of either sign, i.e. +-1/(ny nx) on every correlation value (1.5e-5 at 256^2 against a
+    # peak of ~0.12). The reference's own float32 / float64 evaluations differ the same way, so
+    # the two paths are held to the parity tolerances of peak and snr, not to bit equality.
     res = engine.stack_pipeline(d, want_psd=False, tail_quantiles=None)
     got, want = res["tracking"][1:].cpu().numpy(), plain[1:].cpu().numpy()
-    np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=0, atol=1e-4)
-    np.testing.assert_allclose(got[:, 2:], want[:, 2:], rtol=1e-5)
+    np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=5e-4)
+    np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=2e-3)
 
 
 def test_fused_median_flags_degenerate_frames_and_falls_back():
