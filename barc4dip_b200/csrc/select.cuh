@@ -130,8 +130,8 @@ __device__ __forceinline__ void census_flush(SelFast* s, int q, const unsigned* 
 constexpr int FM_REGION = 64;          // keys per warp and call (a warp holds 512 values, < 5 % of them inside a bracket)
 constexpr int FM_SAMPLE_CAP = 4096;    // keys the sample rows may contribute
 
-template <int NV>
-__device__ __forceinline__ void census_values_region(const float (&v)[NV], unsigned Lkey, unsigned Ukey, int shift,
+template <int NV, int COMP>
+__device__ __forceinline__ void census_values_region(const float2 (&x)[NV], unsigned Lkey, unsigned Ukey, int shift,
                                                      unsigned* __restrict__ region, unsigned* __restrict__ cnt3,
                                                      unsigned* __restrict__ hist_q, int lane) {
     // The values are magnitudes (non-negative or NaN), so their bit patterns are the order-preserving keys and one
@@ -144,7 +144,7 @@ __device__ __forceinline__ void census_values_region(const float (&v)[NV], unsig
     unsigned below = 0, base = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        const unsigned d = __float_as_uint(v[i]) - Lkey;
+        const unsigned d = __float_as_uint(COMP ? x[i].y : x[i].x) - Lkey;
         below += d >> 31;
         const bool in = d <= W;
         if (__any_sync(0xffffffffu, in)) {
@@ -159,7 +159,8 @@ __device__ __forceinline__ void census_values_region(const float (&v)[NV], unsig
     }
     // A NaN anywhere in the frame reaches every output of its inverse transform, so one value per lane tells whether the
     // warp's values are valid.
-    const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, v[0] == v[0])) * (unsigned)NV;
+    const float v0 = COMP ? x[0].y : x[0].x;
+    const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, v0 == v0)) * (unsigned)NV;
     below = __reduce_add_sync(0xffffffffu, below);
     if (lane == 31) { cnt3[0] = base; cnt3[1] = below; cnt3[2] = nvalid; }
 }

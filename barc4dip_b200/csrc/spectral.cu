@@ -465,44 +465,38 @@ __device__ __forceinline__ void best_update(ArgBest& b, float v, unsigned idx) {
 }
 
 struct RowsInvArgs {
-    const float2* Ia;       // blocked intermediate of map A (per frame ny*nx/2)
-    const float2* Ib;       // map B (pair_maps) or nullptr
+    const float2* Ia;       // blocked intermediate (per frame ny*nx/2)
     const float2* tw;
     int ny;
-    int pair_maps;          // 0: rows (2p, 2p+1) of map A; 1: row y of map A and of map B
-    // map A output
-    float* outA;            // (T, ny, nx) shifted real output (nullable)
+    float* outA;            // shifted real output: (T, ny, nx) full map, or compact rows (mag_mode 1); nullable
     int kindA;              // 0: signed value * scale; 1: |value| * scale
     const double* normA;    // per-frame partials (T, n_normA) whose sum is the peak (nullable -> 1)
     int n_normA;
     double norm_mult;       // value = raw * norm_mult / sum(normA)
     double scaleA;          // extra factor (e.g. 1/(nx*ny))
-    ArgBest* bestA;         // (T, gridDim.x) argmax partials (nullable)
-    // map B output (pair_maps only)
-    float* outB;
-    int kindB;
-    double scaleB;
-    ArgBest* bestB;
+    ArgBest* bestA;         // (T, nblk) argmax partials (nullable)
     // row-block selection: blockIdx.x -> row block of the frame (identity when both are null)
     int nblk;               // row blocks per frame (stride of the argmax partials)
     const int* blk_map;     // shared by all frames (gridDim.x entries)
     const int* blk_map_pf;  // per frame (T, gridDim.x)
-    // destination of the |.| map (map B in pair mode, map A otherwise):
-    //   0 full map; 1 compact rows: (T, gridDim.x * rows_per_cta, nx) in launch order; 2 none, census against the
-    //   frame's bracket instead (fused median, select.cuh)
+    // destination of the map:
+    //   0 full map; 1 compact rows: (T, gridDim.x * rows_per_cta, nx) in launch order; 2 none, census of the |.| values
+    //   against the frame's bracket instead (fused median, select.cuh)
     int mag_mode;
     const SelFast* sel;     // per frame bracket
     unsigned* cand;         // (T, regions * FM_REGION + FM_SAMPLE_CAP) region store
     unsigned* cnt3;         // (T, regions, 3)
     unsigned* bhist;        // (T, SEL_BINS)
-    int regions;            // warp regions per frame = row blocks * 16 warps * (pair_maps ? 1 : 2)
+    int regions;            // warp regions per frame = row blocks * 16 warps * 2
 };
 
-// Two thread mappings. The gather uses lanes (c = lane & 7, fl = lane >> 3): 8 adjacent kx of 4 rows, i.e. whole
-// 64-byte runs of the blocked intermediates. The transform and everything after it use the natural mapping
-// (f = tid / TPF, j = tid % TPF): the v2 core leaves x-position j + TPF*s in slot s, so the two real output rows
-// are stored straight from registers, 128 contiguous bytes per warp and slot.
-template <int NX>
+// One complex inverse transform yields rows 2p and 2p + 1 of the map. Two thread mappings: the gather uses lanes
+// (c = lane & 7, fl = lane >> 3): 8 adjacent kx of 4 transforms, i.e. whole 64-byte runs of the blocked intermediate
+// (16-byte loads: both rows at once would need them adjacent, they are 64 B apart). The transform and everything
+// after it use the natural mapping (f = tid / TPF, j = tid % TPF): the v2 core leaves x-position j + TPF*s in slot s,
+// so the two real output rows are stored straight from registers, 128 contiguous bytes per warp and slot.
+// MODE = a.mag_mode and ABS = a.kindA are compile-time copies of the two switches the epilogue turns on.
+template <int NX, int MODE, bool ABS>
 __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     constexpr int TPF = NX / 16;
     constexpr int WPG = TPF / 8;          // warps per group of 4 transforms (gather mapping)
@@ -510,36 +504,35 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     constexpr int FPC = 4 * GPC;
     constexpr int FS = padded_len(NX) + 8;
     constexpr int HX = NX / 2;
+    constexpr int RPC = 2 * FPC;          // rows per CTA
     extern __shared__ float2 sm[];
     __shared__ float s_scale;
-    __shared__ ArgBest s_best[2][16];
+    __shared__ float s_max[16];
+    __shared__ unsigned s_idx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t t = blockIdx.y;
     const int NY = a.ny;
-    const int rows_per_cta = a.pair_maps ? FPC : 2 * FPC;
     const int blk = a.blk_map_pf ? a.blk_map_pf[(size_t)t * gridDim.x + blockIdx.x] : (a.blk_map ? a.blk_map[blockIdx.x] : (int)blockIdx.x);
-    const int y0 = blk * rows_per_cta;
+    const int y0 = blk * RPC;
     const float2* Ia = a.Ia + (size_t)t * NY * HX;
-    const float2* Ib = a.pair_maps ? a.Ib + (size_t)t * NY * HX : Ia;
     unsigned Lk = 0u, Uk = 0xfffffffeu;               // fused median: the frame's bracket, fetched early
-    if (a.mag_mode == 2) { Lk = a.sel[t].L[0]; Uk = a.sel[t].U[0]; }
+    if (MODE == 2) { Lk = a.sel[t].L[0]; Uk = a.sel[t].U[0]; }
+    if (tid == 0) s_idx = 0xffffffffu;
 
     // ---- gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
     {
         const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
         const int f = grp * 4 + fl, jg = jt * 8 + c;
-        const int ya = a.pair_maps ? y0 + f : y0 + 2 * f;
-        const int yb = a.pair_maps ? ya : ya + 1;
+        const int ya = y0 + 2 * f;
         float2 ga[8], gb[8];
         {
             // k = jg + m TPF lives in tile jg/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads
             const size_t tstride = (size_t)(TPF / TC) * NY * TC;
             const float2* pa = Ia + ((size_t)(jg / TC) * NY + ya) * TC + (jg % TC);
-            const float2* pb = Ib + ((size_t)(jg / TC) * NY + yb) * TC + (jg % TC);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 ga[m] = __ldcs(pa + m * tstride);
-                gb[m] = __ldcs(pb + m * tstride);
+                gb[m] = __ldcs(pa + m * tstride + TC);
             }
         }
         if (warp == 0) {
@@ -554,15 +547,13 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
             if (lane == 0) s_scale = (float)sc;
         }
         __syncthreads();
-        // The two rows share one complex transform, so they are brought to their final scale BEFORE it: a raw
-        // autocorrelation (~1e13) packed next to a raw phase correlation (~1e6) would bury the latter in rounding.
-        const float sA = s_scale, sB = a.pair_maps ? (float)a.scaleB : sA;
+        const float sA = s_scale;
         float2* z = sm + f * FS;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int k = jg + m * TPF;
             float2 g1 = ga[m], g2 = gb[m];
-            g1.x *= sA; g1.y *= sA; g2.x *= sB; g2.y *= sB;
+            g1.x *= sA; g1.y *= sA; g2.x *= sA; g2.y *= sA;
             if (k == 0) {
                 // packed slot: (DC, Nyquist), both real
                 z[pad16(0)] = make_float2(g1.x, g2.x);
@@ -583,81 +574,70 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
     fft_regs<NX, +1, 1, (NX >= 1024)>(x, j, z, a.tw, f);
 
-    // ---- stores: real part -> map A row ya, imaginary part -> (map A row yb | map B row ya). Slot s holds x-position
-    //      j + TPF s, i.e. shifted column j + TPF ((s + 8) & 15): a per-thread pointer plus a compile-time offset.
-    const int kindB = a.pair_maps ? a.kindB : a.kindA;
-    const int ra_ = a.pair_maps ? y0 + f : y0 + 2 * f;
-    const int rb_ = a.pair_maps ? ra_ : ra_ + 1;
+    // ---- stores: real part -> row ya, imaginary part -> row ya + 1. Slot s holds x-position j + TPF s, i.e. shifted
+    //      column j + TPF ((s + 8) & 15): a per-thread pointer plus a compile-time offset.
+    const int ra_ = y0 + 2 * f, rb_ = ra_ + 1;
     const unsigned rowA = (unsigned)((ra_ + NY / 2) & (NY - 1)) * (unsigned)NX;
     const unsigned rowB = (unsigned)((rb_ + NY / 2) & (NY - 1)) * (unsigned)NX;
-    float* pA = a.outA ? a.outA + (size_t)t * NY * NX + rowA + j : nullptr;
-    float* pB = a.pair_maps ? (a.outB ? a.outB + (size_t)t * NY * NX + rowB + j : nullptr)
-                            : (a.outA ? a.outA + (size_t)t * NY * NX + rowB + j : nullptr);
-    if (a.mag_mode == 1) {
+    float* pA = nullptr;
+    float* pB = nullptr;
+    if (MODE == 0 && a.outA) { pA = a.outA + (size_t)t * NY * NX + rowA + j; pB = a.outA + (size_t)t * NY * NX + rowB + j; }
+    if (MODE == 1) {
         // compact rows in launch order (sample rows of the fused median, 3x3 window of the peak)
-        const size_t crow = (size_t)t * gridDim.x * rows_per_cta + (size_t)blockIdx.x * rows_per_cta;
-        if (a.pair_maps) pB = a.outB + (crow + f) * NX + j;
-        else { pA = a.outA + (crow + 2 * f) * NX + j; pB = pA + NX; }
-    } else if (a.mag_mode == 2) {
-        if (a.pair_maps) pB = nullptr;
-        else pA = pB = nullptr;
+        pA = a.outA + ((size_t)t * gridDim.x * RPC + (size_t)blockIdx.x * RPC + 2 * f) * NX + j;
+        pB = pA + NX;
     }
-    // Running maxima with the slot they came from. Slots are visited in increasing column order (s = 8..15, 0..7) and
-    // rowA < rowB never matters inside a thread (ties across the two rows are settled by best_update below), so a
-    // strict '>' keeps the first occurrence.
-    float mA = -INFINITY, mB = -INFINITY;
-    int sA_ = 8, sB_ = 8;
+    float mx = -INFINITY;
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
         const int s = (o + 8) & 15;
         float va = x[s].x, vb = x[s].y;
-        if (a.kindA) va = fabsf(va);
-        if (kindB) vb = fabsf(vb);
+        if (ABS) { va = fabsf(va); vb = fabsf(vb); }
         x[s] = make_float2(va, vb);
-        if (pA) pA[TPF * o] = va;
-        if (pB) pB[TPF * o] = vb;
-        if (va > mA) { mA = va; sA_ = o; }
-        if (vb > mB) { mB = vb; sB_ = o; }
+        if (MODE != 2 && pA) { pA[TPF * o] = va; pB[TPF * o] = vb; }
+        mx = fmaxf(mx, fmaxf(va, vb));
     }
-    if (a.mag_mode == 2) {
+    // ---- argmax partial: block maximum first, then the smallest linear index that holds it (first occurrence in
+    //      row-major order of the shifted map wins ties)
+    if (a.bestA) {
+        float wm = mx;
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, q));
+        if (lane == 0) s_max[warp] = wm;
+        __syncthreads();
+        float bm = s_max[0];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) bm = fmaxf(bm, s_max[w]);
+        if (mx == bm) {
+            unsigned best = 0xffffffffu;
+#pragma unroll
+            for (int o = 15; o >= 0; --o) {
+                const int s = (o + 8) & 15;
+                if (x[s].y == bm) best = rowB + (unsigned)(j + TPF * o);
+            }
+#pragma unroll
+            for (int o = 15; o >= 0; --o) {
+                const int s = (o + 8) & 15;
+                if (x[s].x == bm) best = min(best, rowA + (unsigned)(j + TPF * o));
+            }
+            atomicMin(&s_idx, best);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ArgBest b = {bm, s_idx == 0xffffffffu ? 0u : s_idx};     // (an all-NaN block has no maximum)
+            a.bestA[(size_t)t * a.nblk + blk] = b;
+        }
+    }
+    if (MODE == 2) {
         // fused median: census of the |.| values against the frame's bracket, straight from the registers, into this
-        // warp's own region(s) of the frame's candidate store
+        // warp's own two regions of the frame's candidate store
         const int shift = bracket_shift(Lk, Uk);
-        const int calls = a.pair_maps ? 1 : 2;
-        const size_t reg = ((size_t)blk * 16 + warp) * calls;
+        const size_t reg = ((size_t)blk * 16 + warp) * 2;
         unsigned* store = a.cand + (size_t)t * ((size_t)a.regions * FM_REGION + FM_SAMPLE_CAP);
         unsigned* c3 = a.cnt3 + (size_t)t * a.regions * 3;
         unsigned* hq = a.bhist + (size_t)t * SEL_BINS;
-        float v[16];
-#pragma unroll
-        for (int s = 0; s < 16; ++s) v[s] = x[s].y;
-        census_values_region<16>(v, Lk, Uk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
-        if (!a.pair_maps) {
-#pragma unroll
-            for (int s = 0; s < 16; ++s) v[s] = x[s].x;
-            census_values_region<16>(v, Lk, Uk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
-        }
-    }
-    // argmax partials (first occurrence in row-major order of the shifted map wins ties)
-    if (a.bestA || (a.pair_maps && a.bestB)) {
-        ArgBest bA = {mA, rowA + (unsigned)(j + TPF * sA_)}, bB = {mB, rowB + (unsigned)(j + TPF * sB_)};
-        if (!a.pair_maps) best_update(bA, bB.v, bB.idx);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ArgBest oa = {__shfl_xor_sync(0xffffffffu, bA.v, o), __shfl_xor_sync(0xffffffffu, bA.idx, o)};
-            best_update(bA, oa.v, oa.idx);
-            if (a.pair_maps) {
-                ArgBest ob = {__shfl_xor_sync(0xffffffffu, bB.v, o), __shfl_xor_sync(0xffffffffu, bB.idx, o)};
-                best_update(bB, ob.v, ob.idx);
-            }
-        }
-        if (lane == 0) { s_best[0][warp] = bA; s_best[1][warp] = bB; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 16; ++w) { best_update(bA, s_best[0][w].v, s_best[0][w].idx); best_update(bB, s_best[1][w].v, s_best[1][w].idx); }
-            if (a.bestA) a.bestA[(size_t)t * a.nblk + blk] = bA;
-            if (a.pair_maps && a.bestB) a.bestB[(size_t)t * a.nblk + blk] = bB;
-        }
+        census_values_region<16, 1>(x, Lk, Uk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
+        census_values_region<16, 0>(x, Lk, Uk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
     }
 }
 
@@ -1216,19 +1196,27 @@ int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
 }
 
 // grid_blocks: row blocks per frame this launch covers (0 = all of them; otherwise a.blk_map / a.blk_map_pf name them)
-template <int NX>
-int launch_rows_inv(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
+template <int NX, int MODE, bool ABS>
+int launch_rows_inv_inst(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
     constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
     constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
     static bool attr = false;
-    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const int rows = a.pair_maps ? FPC : 2 * FPC;
+    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX, MODE, ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int rows = 2 * FPC;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     a.nblk = a.ny / rows;
     ProfScope ps(ctx, KC_ROWS_INV);
-    rows_inv_kernel<NX><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    rows_inv_kernel<NX, MODE, ABS><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
+}
+
+template <int NX>
+int launch_rows_inv(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
+    if (a.mag_mode == 2) return launch_rows_inv_inst<NX, 2, true>(ctx, a, T, grid_blocks);
+    if (a.mag_mode == 1) return launch_rows_inv_inst<NX, 1, true>(ctx, a, T, grid_blocks);
+    if (a.kindA) return launch_rows_inv_inst<NX, 0, true>(ctx, a, T, grid_blocks);
+    return launch_rows_inv_inst<NX, 0, false>(ctx, a, T, grid_blocks);
 }
 
 template <int NX>
@@ -1251,9 +1239,9 @@ int cols_cw_2048();
 int cols_cw(int ny) { return ny >= 2048 ? cols_cw_2048() : TC; }
 int cols_tiles(int ny, int nx) { return nx / 2 / cols_cw(ny); }
 
-int rows_inv_blocks(int nx, int ny, int pair_maps) {
+int rows_inv_blocks(int nx, int ny) {
     const int tpf = nx / 16, wpg = tpf / 8, gpc = 16 / wpg, fpc = 4 * gpc;
-    return ny / (pair_maps ? fpc : 2 * fpc);
+    return ny / (2 * fpc);
 }
 
 #define DISPATCH_N(n, CALL)                                   \
@@ -1598,7 +1586,7 @@ extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
         float* o = out + (size_t)t0 * ny * nx;
-        r.Ia = w.I2a; r.ny = ny; r.pair_maps = 0; r.outA = o; r.kindA = 0;
+        r.Ia = w.I2a; r.ny = ny; r.outA = o; r.kindA = 0;
         r.scaleA = 1.0 / ((double)nx * (double)ny);
         if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
         if (standardize && !normalize_peak)
@@ -1674,8 +1662,8 @@ int b4d_fused_median_final(b4d_ctx* ctx, const FusedMedian& fm, int64_t T, float
 namespace {
 
 // number of sample row blocks for the fused median (0: the frame is too small, use the map-based path)
-int fused_sample_blocks(int ny, int nx, int pair_maps) {
-    const int nblk = rows_inv_blocks(nx, ny, pair_maps), rpc = ny / nblk;
+int fused_sample_blocks(int ny, int nx) {
+    const int nblk = rows_inv_blocks(nx, ny), rpc = ny / nblk;
     if ((int64_t)ny * nx < 65536 || nblk < 4) return 0;
     int ns = 32768 / (rpc * nx);
     if (ns > nblk / 2) ns = nblk / 2;
@@ -1686,7 +1674,7 @@ int fused_sample_blocks(int ny, int nx, int pair_maps) {
 // map A outputs as usual in pair mode; the |.| map is map B (pair) or map A (single), its argmax partials in w.bestB.
 int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int ny, int nx, int ns, float* scratch,
                          int subpixel, double eps, double* out) {
-    const int pair = r.pair_maps, nblk = rows_inv_blocks(nx, ny, pair), rpc = ny / nblk;
+    const int nblk = rows_inv_blocks(nx, ny), rpc = ny / nblk;
     const int m = ns * rpc * nx;
     FftPlanCache* f = ctx->fft;
     if (f->blk_n != nblk || f->blk_ns != ns) {
@@ -1704,11 +1692,11 @@ int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int n
     int* blk3 = reinterpret_cast<int*>(window + (size_t)tc * 3 * rpc * nx);   // (tc, 3)
     FusedMedian fm;
     int rc;
-    if ((rc = b4d_fused_median_begin(ctx, tc, nblk * 16 * (pair ? 1 : 2), &fm))) return rc;
+    if ((rc = b4d_fused_median_begin(ctx, tc, nblk * 16 * 2, &fm))) return rc;
     // 1. sample rows: map A as usual, |.| rows into the compact sample buffer
     RowsInvArgs r1 = r;
     r1.blk_map = f->blk_list; r1.mag_mode = 1;
-    if (pair) r1.outB = samples; else r1.outA = samples;
+    r1.outA = samples;
     if ((rc = run_rows_inv(ctx, r1, tc, nx, ns))) return rc;
     // 2. bracket around the median + census of the sample rows
     if ((rc = b4d_fused_median_bracket(ctx, fm, samples, m, tc))) return rc;
@@ -1723,8 +1711,8 @@ int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int n
     window_blocks_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(w.pk_idx, ny, nx, rpc, blk3, tc);
     B4D_LAUNCH_CHECK(ctx);
     RowsInvArgs r3 = r;
-    r3.blk_map_pf = blk3; r3.mag_mode = 1; r3.bestA = nullptr; r3.bestB = nullptr;
-    if (pair) { r3.outA = nullptr; r3.outB = window; } else r3.outA = window;
+    r3.blk_map_pf = blk3; r3.mag_mode = 1; r3.bestA = nullptr;
+    r3.outA = window;
     if ((rc = run_rows_inv(ctx, r3, tc, nx, 3))) return rc;
     // 5. exact median from the candidates, results
     if ((rc = b4d_fused_median_final(ctx, fm, tc, w.med, reinterpret_cast<int64_t*>(w.nvalid)))) return rc;
@@ -1734,8 +1722,8 @@ int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int n
     return B4D_OK;
 }
 
-size_t fused_scratch_floats(int ny, int nx, int pair_maps, int ns, int64_t tc) {
-    const int nblk = rows_inv_blocks(nx, ny, pair_maps), rpc = ny / nblk;
+size_t fused_scratch_floats(int ny, int nx, int ns, int64_t tc) {
+    const int nblk = rows_inv_blocks(nx, ny), rpc = ny / nblk;
     return (size_t)tc * ((size_t)ns * rpc * nx + (size_t)3 * rpc * nx + 4);
 }
 
@@ -1756,9 +1744,9 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
         const float* s0 = stack + (size_t)t0 * ny * nx;
         Work w;
         if ((rc = carve(ctx, tc, ny, nx, false, true, &w))) return rc;
-        const int ns = ctx->fused_median ? fused_sample_blocks(ny, nx, 0) : 0;
+        const int ns = ctx->fused_median ? fused_sample_blocks(ny, nx) : 0;
         void* p = nullptr;
-        const size_t map_floats = ns ? fused_scratch_floats(ny, nx, 0, ns, tc) : (size_t)tc * ny * nx;
+        const size_t map_floats = ns ? fused_scratch_floats(ny, nx, ns, tc) : (size_t)tc * ny * nx;
         if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(double) * B4D_FR_NCOLS * tc + sizeof(float) * map_floats + 256, &p))) return rc;
         double* fr = static_cast<double*>(p);
         float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
@@ -1772,14 +1760,14 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
         if ((rc = run_cols(ctx, c, tc, ny))) return rc;
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
-        r.Ia = w.I2b; r.ny = ny; r.pair_maps = 0; r.outA = mag; r.kindA = 1;
+        r.Ia = w.I2b; r.ny = ny; r.outA = mag; r.kindA = 1;
         r.scaleA = 1.0 / ((double)nx * (double)ny);
         r.bestA = w.bestB;
         if (ns) {
             if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, out + t0 * 4))) return rc;
         } else {
             if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
-            if ((rc = track_finish(ctx, w, mag, tc, ny, nx, rows_inv_blocks(nx, ny, 0), subpixel, eps, out + t0 * 4))) return rc;
+            if ((rc = track_finish(ctx, w, mag, tc, ny, nx, rows_inv_blocks(nx, ny), subpixel, eps, out + t0 * 4))) return rc;
         }
     }
     return B4D_OK;
@@ -1810,8 +1798,8 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         // scratch maps: |corr| always, autocorr when the caller does not keep it
         void* p = nullptr;
         // tracker: fused median (sample rows + 3x3 window instead of the |corr| map) unless the frame is too small
-        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx, 0) : 0;
-        const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, 0, ns, tc) + 63) & ~size_t(63)) : npix * tc);
+        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx) : 0;
+        const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, ns, tc) + 63) & ~size_t(63)) : npix * tc);
         const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) +
                             sizeof(double) * B4D_FR_NCOLS * tc + 256;
         if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
@@ -1856,8 +1844,8 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
             if ((rc = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac))) return rc;
         }
         if (want_pc) {
-            r.Ia = w.I2b; r.pair_maps = 0; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
-            nblk = rows_inv_blocks(nx, ny, 0);
+            r.Ia = w.I2b; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
+            nblk = rows_inv_blocks(nx, ny);
             if (ns) {
                 if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4))) return rc;
             } else {
