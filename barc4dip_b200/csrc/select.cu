@@ -848,6 +848,22 @@ int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt,
 
 // ---- fused median (called from spectral.cu) -----------------------------------------------------------
 // Scratch of one batch: bracket state, fallback flags, bracket histograms and region counters (zeroed), region store.
+// A few doubles from the host to device memory as kernel arguments: a cudaMemcpyAsync from pageable memory would queue
+// on the copy engine behind whatever bulk host->device transfer another stream has in flight (StackAnalyzer.run
+// overlaps the next chunk's upload with these kernels) and stall the whole compute stream for its duration.
+__global__ void put_doubles_kernel(double* dst, int n, double a, double b, double c, double d) {
+    const double v[4] = {a, b, c, d};
+    if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
+}
+int b4d_put_doubles(b4d_ctx* ctx, double* dst, const double* src_host, int n) {
+    if (n < 1 || n > 4) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_put_doubles: 1..4 values");
+    double v[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) v[i] = src_host[i];
+    put_doubles_kernel<<<1, 4, 0, ctx->stream>>>(dst, n, v[0], v[1], v[2], v[3]);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
 int b4d_fused_median_begin(b4d_ctx* ctx, int64_t T, int regions, FusedMedian* fm) {
     const size_t st_bytes = ((size_t)T * sizeof(SelFast) + 255) & ~size_t(255);
     const size_t need_bytes = ((size_t)T * sizeof(int) + 255) & ~size_t(255);
@@ -867,8 +883,7 @@ int b4d_fused_median_begin(b4d_ctx* ctx, int64_t T, int regions, FusedMedian* fm
     fm->regions = regions;
     B4D_CUDA(ctx, cudaMemsetAsync(p, 0, 256 + st_bytes + need_bytes + bh_bytes + c3_bytes, ctx->stream));
     static const double half = 0.5;
-    B4D_CUDA(ctx, cudaMemcpyAsync(fm->q_dev, &half, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    return B4D_OK;
+    return b4d_put_doubles(ctx, fm->q_dev, &half, 1);
 }
 
 int b4d_fused_median_bracket(b4d_ctx* ctx, const FusedMedian& fm, const float* samples, int m, int64_t T) {
@@ -966,6 +981,6 @@ extern "C" int b4d_select_ranks(b4d_ctx* ctx, const float* stack, int64_t n_fram
     void* p = nullptr;
     int rc = b4d_scratch(ctx, SCR_MISC, 64 * sizeof(double), &p);
     if (rc) return rc;
-    B4D_CUDA(ctx, cudaMemcpyAsync(p, quantiles_host, n_q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = b4d_put_doubles(ctx, static_cast<double*>(p), quantiles_host, n_q))) return rc;
     return b4d_select_impl(ctx, stack, n_frames, frame_elems, static_cast<const double*>(p), n_q, use_abs, out, n_valid);
 }

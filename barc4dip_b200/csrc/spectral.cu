@@ -26,6 +26,7 @@ int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t 
                            const float* dark, float* pilot);
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid);
+int b4d_put_doubles(b4d_ctx* ctx, double* dst, const double* src_host, int n);
 int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                 const float* dark, double sat_value, double zero_eps, double* out);
 struct FrTails { double q_lo, q_hi; float* quant_out; int64_t* nvalid_out; };   // reduce.cu
@@ -1643,7 +1644,7 @@ int track_finish(b4d_ctx* ctx, Work& w, const float* mag, int64_t tc, int ny, in
     int rc = b4d_scratch(ctx, SCR_MISC, 1024, &p);   // already sized by carve(); first 512 B hold the quantile
     if (rc) return rc;
     static const double half = 0.5;
-    B4D_CUDA(ctx, cudaMemcpyAsync(p, &half, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = b4d_put_doubles(ctx, static_cast<double*>(p), &half, 1))) return rc;
     if ((rc = b4d_select_impl(ctx, mag, tc, (int64_t)ny * nx, static_cast<const double*>(p), 1, 1, w.med,
                               reinterpret_cast<int64_t*>(w.nvalid))))
         return rc;

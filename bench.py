@@ -54,7 +54,7 @@ def parse_args():
     p.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
     p.add_argument("--size", type=int, default=2048)
     p.add_argument("--batch", type=int, default=0, help="frames per internal FFT batch (0 = automatic)")
-    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = automatic)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -306,16 +306,21 @@ def run_b200(args):
             def e2e_step():
                 an2.set_reference(ref_host)
                 return an2.run(host, keep_maps_on_device=keep)
-            e2e_step()
+            # two untimed calls: staging buffers, scratch arenas and the caching allocator's blocks for the result maps
+            # are created on the first, reused from the second on (a result is released before the next call, as a
+            # caller looping over stacks would)
+            for _ in range(2):
+                out = e2e_step()
+                del out
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 out = e2e_step()
+                del out
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            del out
             return world * F * args.e2e_steps / float(dt.item())
 
         h2d_b, d2h_b = an2.bytes_per_frame()
