@@ -57,6 +57,7 @@ _SIGNATURES = {
     "b4d_free": [_vp, _vp],
     "b4d_memcpy_h2d": [_vp, _vp, _vp, C.c_size_t],
     "b4d_memcpy_d2h": [_vp, _vp, _vp, C.c_size_t],
+    "b4d_cast_to_f32": [_vp, _vp, _i32, _vp, _i64],
     "b4d_frame_reductions": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _vp],
     "b4d_select_ranks": [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp],
     "b4d_flat_field": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _i32, _vp],
@@ -202,10 +203,35 @@ def ptr(t) -> _vp:
     return _vp(t.data_ptr())
 
 
+# integer types b4d_cast_to_f32 widens on the device (enum b4d_dtype in include/b4d.h)
+NATIVE_INT_CODES = {"uint8": 0, "uint16": 1, "int16": 2, "int32": 3, "uint32": 4}
+
+
+def native_int_code(dtype) -> int | None:
+    """b4d_dtype code of a numpy / torch integer dtype the device cast accepts, else None."""
+    name = str(dtype).replace("torch.", "")
+    return NATIVE_INT_CODES.get(name)
+
+
+def cast_to_f32(raw_bytes, code: int, out):
+    """raw_bytes: CUDA uint8 tensor holding `out.numel()` elements of integer type `code`; out: float32 CUDA tensor."""
+    ctx = get_context(out.device.index or 0)
+    ctx.check(ctx.lib.b4d_cast_to_f32(ctx.handle, ptr(raw_bytes), int(code), ptr(out), int(out.numel())), "b4d_cast_to_f32")
+    return out
+
+
 def as_device_f32(a, device: int | None = None):
-    """numpy array / torch tensor -> contiguous float32 CUDA tensor (H2D copy when given host data)."""
+    """numpy array / torch tensor -> contiguous float32 CUDA tensor (H2D copy when given host data). Integer detector
+    types (uint8/uint16/int16/int32/uint32) cross PCIe in their own width and are widened on the device."""
     torch = require_cuda()
     dev = default_device() if device is None else int(device)
+    if not isinstance(a, torch.Tensor):
+        arr = np.asarray(a)
+        code = native_int_code(arr.dtype)
+        if code is not None and arr.size >= 4096:
+            src = np.ascontiguousarray(arr)
+            raw = torch.from_numpy(src.reshape(-1).view(np.uint8)).to(f"cuda:{dev}")
+            return cast_to_f32(raw, code, torch.empty(src.shape, dtype=torch.float32, device=raw.device))
     if isinstance(a, torch.Tensor):
         t = a
         if t.device.type != "cuda":

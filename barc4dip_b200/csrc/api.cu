@@ -124,3 +124,50 @@ extern "C" int b4d_memcpy_d2h(b4d_ctx* ctx, void* dst_host, const void* src, siz
     B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B4D_OK;
 }
+
+// ---- stack ingestion: detector-native integer frames are uploaded as they are and widened on the device ------------
+// (the reference casts integer images to float32 / float64 on the host: signal/tracking.py:299-305, metrics/*.py)
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    // 8 elements per thread: one 16-byte (or narrower) load of the source type, two float4 stores
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 + 8 <= n) {
+        T v[8];
+        if (sizeof(T) == 2) *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(src + i0));
+        else if (sizeof(T) == 1) *reinterpret_cast<uint2*>(v) = __ldcs(reinterpret_cast<const uint2*>(src + i0));
+        else { *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(src + i0)); *reinterpret_cast<uint4*>(v + 4) = __ldcs(reinterpret_cast<const uint4*>(src + i0 + 4)); }
+        float4 a = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        float4 b = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+        reinterpret_cast<float4*>(dst + i0)[0] = a;
+        reinterpret_cast<float4*>(dst + i0)[1] = b;
+    } else {
+        for (int64_t i = i0; i < n; ++i) dst[i] = (float)src[i];
+    }
+}
+template <typename T>
+int launch_cast(b4d_ctx* ctx, const void* src, float* dst, int64_t n) {
+    const int64_t threads = (n + 7) / 8;
+    ProfScope ps(ctx, KC_SMALL);
+    cast_to_f32_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(static_cast<const T*>(src), dst, n);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+}  // namespace
+
+extern "C" int b4d_cast_to_f32(b4d_ctx* ctx, const void* src, int dtype, float* dst, int64_t n) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    if (!src || !dst || n < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_cast_to_f32: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_cast_to_f32: pointers must be 16-byte aligned");
+    if (n > ((int64_t)1 << 40)) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_cast_to_f32: too many elements");
+    switch (dtype) {
+        case B4D_U8: return launch_cast<uint8_t>(ctx, src, dst, n);
+        case B4D_U16: return launch_cast<uint16_t>(ctx, src, dst, n);
+        case B4D_I16: return launch_cast<int16_t>(ctx, src, dst, n);
+        case B4D_I32: return launch_cast<int32_t>(ctx, src, dst, n);
+        case B4D_U32: return launch_cast<uint32_t>(ctx, src, dst, n);
+        default: return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_cast_to_f32: dtype code %d", dtype);
+    }
+}

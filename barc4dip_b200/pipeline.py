@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import engine, stack as blocks
-from ._lib import FR_NCOLS, get_context, require_cuda
+from ._lib import FR_NCOLS, cast_to_f32, get_context, native_int_code, require_cuda
 
 
 class StackAnalyzer:
@@ -117,8 +117,22 @@ class StackAnalyzer:
         ny, nx, c = self.ny, self.nx, self.chunk
         h2d, comp, d2h = self._streams
         st = self._buffers(True)
+        code = None
         if is_host:
-            src = stack if isinstance(stack, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(stack, dtype=np.float32))
+            # float32 stacks are staged as they are; integer detector types travel in their own width and are widened
+            # on the device (b4d_cast_to_f32); anything else is converted to float32 on the host first
+            code = native_int_code(stack.dtype)
+            if isinstance(stack, torch.Tensor):
+                src = stack.contiguous() if (code is not None or stack.dtype == torch.float32) else stack.to(torch.float32)
+            elif code is not None:
+                src = torch.from_numpy(np.ascontiguousarray(stack).reshape(T, -1).view(np.uint8))
+            else:
+                src = torch.from_numpy(np.ascontiguousarray(stack, dtype=np.float32))
+            if code is not None:
+                if isinstance(stack, torch.Tensor):
+                    src = src.reshape(T, -1).view(torch.uint8)
+                if st.get("raw") is None or st["raw"][0].shape[1] != src.shape[1]:
+                    st["raw"] = [torch.empty((c, src.shape[1]), dtype=torch.uint8, device=self.device) for _ in range(2)]
         fr_all = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=self.device)
         grain_all = torch.empty((T, 4), dtype=torch.float64, device=self.device)
         track_all = torch.empty((T, 4), dtype=torch.float64, device=self.device) if self.tracker is not None else None
@@ -148,7 +162,7 @@ class StackAnalyzer:
                 with torch.cuda.stream(h2d):
                     if i >= 2:
                         h2d.wait_event(ev_done[s])          # the kernels that read this staging buffer have finished
-                    st["in"][s][:n].copy_(src[a:b], non_blocking=True)
+                    (st["raw"] if code is not None else st["in"])[s][:n].copy_(src[a:b], non_blocking=True)
                     ev_in[s].record(h2d)
                 frames = st["in"][s][:n]
             else:
@@ -159,6 +173,8 @@ class StackAnalyzer:
                 if self.want_maps and not keep_maps_on_device and i >= 2:
                     comp.wait_event(ev_out[s])              # the D2H that drained this map buffer has finished
                 ctx.use_current_stream()
+                if code is not None:
+                    cast_to_f32(st["raw"][s][:n], code, frames)
                 if self.want_maps:
                     po = maps_dev["psd"][a:b] if keep_maps_on_device else st["psd"][s][:n]
                     ao = maps_dev["ac"][a:b] if keep_maps_on_device else st["ac"][s][:n]
@@ -185,7 +201,7 @@ class StackAnalyzer:
         if track_all is not None and bool(torch.isnan(track_all[:, 3]).any()):
             # frames whose fused median bracket missed: redo them through the map-based tracker
             bad = torch.isnan(track_all[:, 3]).nonzero().flatten()
-            frames = (src[bad.cpu()] if is_host else stack[bad]).to(self.device, dtype=torch.float32).contiguous()
+            frames = self._frames_of(stack, bad)
             sub = track_all[bad].clone()
             ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None
             engine.resolve_tracking(frames, sub, subpixel=self.subpixel, flat_field_fn=ff)
@@ -193,7 +209,7 @@ class StackAnalyzer:
         if nv_all is not None and bool((nv_all < 0).any()):
             # frames whose tails the fused collection did not resolve: exact stand-alone select on those frames only
             bad = (nv_all < 0).nonzero().flatten()
-            frames = (src[bad.cpu()] if is_host else stack[bad]).to(self.device, dtype=torch.float32).contiguous()
+            frames = self._frames_of(stack, bad)
             if self.gain is not None:
                 frames = engine.flat_field(frames, self.flat, self.dark, **self._ff)
             q, nv = engine.select_quantiles(frames, [0.05 / 100.0, 99.95 / 100.0], return_device=True)
@@ -225,6 +241,13 @@ class StackAnalyzer:
         elif maps_dev is not None:
             out["psd"], out["autocorr"] = maps_dev["psd"], maps_dev["ac"]
         return out
+
+    def _frames_of(self, stack, idx):
+        """Frames `idx` (1-D index tensor) of the caller's stack as a float32 device stack (fallback paths only)."""
+        torch = require_cuda()
+        if isinstance(stack, torch.Tensor):
+            return stack[idx.to(stack.device)].to(self.device).to(torch.float32).contiguous()
+        return engine.as_stack(np.asarray(stack)[idx.cpu().numpy()], self.dev)
 
     def bytes_per_frame(self) -> tuple[int, int]:
         """(host->device, device->host) bytes per frame of run() with host input."""

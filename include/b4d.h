@@ -68,6 +68,16 @@ int b4d_free(b4d_ctx* ctx, void* p);
 int b4d_memcpy_h2d(b4d_ctx* ctx, void* dst, const void* src_host, size_t bytes);
 int b4d_memcpy_d2h(b4d_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
 
+/*
+ * Stack ingestion: integer detector frames (uint8 / uint16 / int16 / int32 / uint32) are uploaded in their own type
+ * (half or a quarter of the PCIe bytes of float32) and widened to float32 on the device, the way the reference's
+ * entry points cast integer images on the host (signal/tracking.py:299-305 -> float32; the metrics cast further to
+ * float64, which this path evaluates in float32 anyway). src and dst: device pointers, 16-byte
+ * aligned; n elements.
+ */
+enum b4d_dtype { B4D_U8 = 0, B4D_U16 = 1, B4D_I16 = 2, B4D_I32 = 3, B4D_U32 = 4 };
+int b4d_cast_to_f32(b4d_ctx* ctx, const void* src, int dtype, float* dst, int64_t n);
+
 /* ---- per-frame single-pass reductions ------------------------------------------------- */
 /*
  * One streaming pass per frame producing everything the reference's scalar metrics need:

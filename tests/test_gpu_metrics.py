@@ -147,3 +147,30 @@ def test_speckle_stack_stats_phase_tracking(dip):
     assert out["temporal"]["inc"]["dx"].dtype == np.float32 and out["temporal"]["inc"]["dx"].shape == (3,)
     for k in ("mean", "std", "skewness"):
         np.testing.assert_allclose(out["full"]["stats"][k][1], orc.distribution_moments(stack[1])[k], rtol=RTOL)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8, np.int16, np.int32])
+def test_stack_analyzer_native_integer_stacks(dtype):
+    """Integer detector stacks cross PCIe in their own width and are widened on the device (b4d_cast_to_f32): the
+    results are those of the same values handed over as float32, bit for bit."""
+    from barc4dip_b200 import engine, synth
+    from barc4dip_b200.pipeline import StackAnalyzer
+    n, T = 256, 5
+    stack, _ = synth.tracking_stack(T, n, grain=5.0, seed=13, integer_every=2)
+    hi = {np.uint16: 60000.0, np.uint8: 250.0, np.int16: 30000.0, np.int32: 2.0e6}[dtype]
+    ints = np.clip(np.rint(stack / stack.max() * hi), 0, hi).astype(dtype)
+    if dtype in (np.int16, np.int32):
+        ints[:, ::7, ::5] *= -1                      # signed types keep their sign
+    as_f32 = ints.astype(np.float32)
+    np.testing.assert_array_equal(engine.as_stack(ints).cpu().numpy(), as_f32)
+    outs = []
+    for data in (ints, as_f32):
+        an = StackAnalyzer((n, n), reference=as_f32[0], chunk_frames=2, saturation_value=None)
+        outs.append(an.run(data))
+    a, b = outs
+    np.testing.assert_array_equal(a["table"], b["table"])
+    np.testing.assert_array_equal(a["psd"], b["psd"])
+    np.testing.assert_array_equal(a["autocorr"], b["autocorr"])
+    for k in ("dy", "dx", "peak", "snr"):
+        np.testing.assert_array_equal(a["tracking"][k], b["tracking"][k])
+    np.testing.assert_array_equal(a["amplitude"]["contrast"], b["amplitude"]["contrast"])
