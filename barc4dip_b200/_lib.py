@@ -138,7 +138,7 @@ class Context:
 
     def profile_end(self) -> dict:
         """{class name: (milliseconds, launches)} of the kernels launched since profile_begin()."""
-        n = 15   # B4D_PROF_NCLASS
+        n = 16   # B4D_PROF_NCLASS
         ms = (C.c_double * n)()
         cnt = (C.c_int64 * n)()
         self.check(self.lib.b4d_profile_end(self.handle, ms, cnt), "b4d_profile_end")

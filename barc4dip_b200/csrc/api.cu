@@ -81,7 +81,7 @@ extern "C" int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* laun
 extern "C" const char* b4d_profile_class_name(int k) {
     static const char* names[KC_COUNT] = {"pilot", "frame_reduce", "rows_fwd", "cols", "rows_inv", "select_hist",
                                           "select_scan", "grain", "temporal", "flatfield", "small", "select_sample", "select_collect",
-                                          "select_final", "rows_inv_ac"};
+                                          "select_final", "rows_inv_ac", "generic_dft"};
     return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 

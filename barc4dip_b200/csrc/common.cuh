@@ -18,7 +18,7 @@ struct FftPlanCache;   // spectral.cu
 // kernel classes for the optional CUDA-event profile (b4d_profile_*)
 enum {
     KC_PILOT = 0, KC_FRAME_REDUCE, KC_ROWS_FWD, KC_COLS, KC_ROWS_INV, KC_SELECT_HIST, KC_SELECT_SCAN, KC_GRAIN,
-    KC_TEMPORAL, KC_FLATFIELD, KC_SMALL, KC_SELECT_SAMPLE, KC_SELECT_COLLECT, KC_SELECT_FINAL, KC_ROWS_INV_AC, KC_COUNT
+    KC_TEMPORAL, KC_FLATFIELD, KC_SMALL, KC_SELECT_SAMPLE, KC_SELECT_COLLECT, KC_SELECT_FINAL, KC_ROWS_INV_AC, KC_GENERIC, KC_COUNT
 };
 
 struct ProfSpan {

@@ -43,6 +43,7 @@ struct FftPlanCache {
     double* theta = nullptr;     // 1130 x (sin, cos)
     int* blk_list = nullptr;     // fused median: sample row blocks first, then all the others
     int blk_n = 0, blk_ns = 0;
+    void* gen = nullptr;         // GenCache*: chirp tables of the arbitrary-length path (generic_dft.cuh)
 };
 
 namespace {
@@ -1396,10 +1397,187 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
     return b;
 }
 
+// -------------------------------------------------------------------------------------------------
+// arbitrary frame sides (Bluestein), see generic_dft.cuh
+// -------------------------------------------------------------------------------------------------
+#include "generic_dft.cuh"
+
+GenCache*& gen_cache(b4d_ctx* ctx) {
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    return reinterpret_cast<GenCache*&>(ctx->fft->gen);
+}
+
+// f95 of B4D_SP_*: two-level histogram over the integer radius keys of a shifted square PSD map (tab: (tc, B4D_SP_NCOLS))
+int run_f95(b4d_ctx* ctx, const float* map_b, int n, int64_t tc, double* tab) {
+    const int nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
+    void* p = nullptr;
+    const size_t hb = sizeof(double) * (size_t)tc * (nb0 > nb1 ? nb0 : nb1);
+    int rc = b4d_scratch(ctx, SCR_SELECT, hb + (sizeof(int) + sizeof(double)) * tc + 256, &p);
+    if (rc) return rc;
+    double* hist = static_cast<double*>(p);
+    double* below = reinterpret_cast<double*>(static_cast<char*>(p) + hb);
+    int* cb = reinterpret_cast<int*>(below + tc);
+    B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hb, ctx->stream));
+    int bx = (int)(((int64_t)n * n + 256 * 32 - 1) / (256 * 32));
+    if (bx > 296) bx = 296;
+    for (int level = 0; level < 2; ++level) {
+        const int nb = level ? nb1 : nb0;
+        f95_hist_kernel<<<dim3(bx, (unsigned)tc), 256, nb * sizeof(double), ctx->stream>>>(map_b, n, level, cb, hist, nb);
+        B4D_LAUNCH_CHECK(ctx);
+        f95_scan_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(hist, nb, level, tab, cb, below, n, tab, tc);
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
+bool pow2_sides(int ny, int nx) { return fft_size_ok(ny) && fft_size_ok(nx); }
+
+int check_gen_args(b4d_ctx* ctx, const char* who, const void* stack, int64_t T, int ny, int nx) {
+    if (!stack || T < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "%s: bad arguments", who);
+    if (!gen_size_ok(ny) || !gen_size_ok(nx) || T > ((int64_t)1 << 24))
+        return b4d_fail(ctx, B4D_ERR_UNSUPPORTED,
+                        "%s: frames need power-of-two sides in [128, 2048] or any sides in [2, 1024]; got T=%lld (ny, nx)=(%d, %d)",
+                        who, (long long)T, ny, nx);
+    return B4D_OK;
+}
+
+struct GenWork {
+    float2* A = nullptr;
+    float2* Bf = nullptr;
+    double* fr = nullptr;
+    double* spp = nullptr;
+    unsigned* pk = nullptr;
+    int nblk = 0;
+};
+
+int64_t gen_batch(int ny, int nx) {
+    int64_t b = ((int64_t)512 << 20) / ((int64_t)16 * ny * nx);
+    if (b < 1) b = 1;
+    if (b > 32768) b = 32768;       // gridDim.y
+    return b;
+}
+
+int gen_carve(b4d_ctx* ctx, int64_t tc, int ny, int nx, GenWork* w) {
+    const size_t per = (size_t)ny * nx * sizeof(float2);
+    void* p = nullptr;
+    int rc;
+    if ((rc = b4d_scratch(ctx, SCR_SPEC_A, per * tc, &p))) return rc;
+    w->A = static_cast<float2*>(p);
+    if ((rc = b4d_scratch(ctx, SCR_SPEC_B, per * tc, &p))) return rc;
+    w->Bf = static_cast<float2*>(p);
+    int nblk = (int)(((int64_t)ny * nx + 2047) / 2048);
+    if (nblk > 64) nblk = 64;
+    w->nblk = nblk;
+    const size_t fr_b = (sizeof(double) * B4D_FR_NCOLS * tc + 255) & ~size_t(255);
+    const size_t sp_b = (sizeof(double) * NSP * nblk * tc + 255) & ~size_t(255);
+    if ((rc = b4d_scratch(ctx, SCR_NYQ, fr_b + sp_b + sizeof(unsigned) * tc + 256, &p))) return rc;
+    w->fr = static_cast<double*>(p);
+    w->spp = reinterpret_cast<double*>(static_cast<char*>(p) + fr_b);
+    w->pk = reinterpret_cast<unsigned*>(static_cast<char*>(p) + fr_b + sp_b);
+    return B4D_OK;
+}
+
+int gen_epilogue(b4d_ctx* ctx, const GenWork& w, int64_t tc, int ny, int nx, int dc_mode, float scale, float* psd, float2* cplx,
+                 int sqmag, bool spectral) {
+    GenEpiArgs e;
+    memset(&e, 0, sizeof(e));
+    e.F = w.A; e.fr = w.fr; e.ny = ny; e.nx = nx; e.dc_mode = dc_mode; e.scale = scale; e.psd_out = psd; e.cplx_out = cplx;
+    e.sqmag_inplace = sqmag; e.spec_partials = spectral ? w.spp : nullptr;
+    ProfScope ps(ctx, KC_GENERIC);
+    gen_epilogue_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(e);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+int gen_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64) {
+    const int64_t B = gen_batch(ny, nx);
+    const size_t npix = (size_t)ny * nx;
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        const float* s0 = stack + t0 * npix;
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), s0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        if ((rc = gen_epilogue(ctx, w, tc, ny, nx, 0, 1.f, nullptr, reinterpret_cast<float2*>(out_c64) + t0 * npix, 0, false))) return rc;
+    }
+    return B4D_OK;
+}
+
+int gen_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float scale_factor, int sub_mean, int zero_dc,
+              float* out_psd, double* spectral) {
+    const int64_t B = gen_batch(ny, nx);
+    const size_t npix = (size_t)ny * nx;
+    const bool want_f95 = spectral && ny == nx;
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        const float* s0 = stack + t0 * npix;
+        float* map_b = out_psd ? out_psd + t0 * npix : nullptr;
+        if (want_f95 && !map_b) {
+            void* p = nullptr;
+            if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * npix * tc, &p))) return rc;
+            map_b = static_cast<float*>(p);
+        }
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), s0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        if ((rc = gen_epilogue(ctx, w, tc, ny, nx, (sub_mean || zero_dc) ? 1 : 0, scale_factor, map_b, nullptr, 0, spectral != nullptr))) return rc;
+        if (spectral) {
+            double* tab = spectral + t0 * B4D_SP_NCOLS;
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, w.nblk, tab, tc);
+            B4D_LAUNCH_CHECK(ctx);
+            if (want_f95 && (rc = run_f95(ctx, map_b, ny, tc, tab))) return rc;
+        }
+    }
+    return B4D_OK;
+}
+
+int gen_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int use_norm, double norm_mult,
+                   int remove_mean, float* out_ac, double fraction, double* grain_out) {
+    const int64_t B = gen_batch(ny, nx);
+    const size_t npix = (size_t)ny * nx;
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        const float* s0 = stack + t0 * npix;
+        float* o = out_ac ? out_ac + t0 * npix : nullptr;
+        if (!o) {
+            void* p = nullptr;
+            if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * npix * tc, &p))) return rc;
+            o = static_cast<float*>(p);
+        }
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), s0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        if ((rc = gen_epilogue(ctx, w, tc, ny, nx, remove_mean ? 1 : 0, 1.f, nullptr, nullptr, 1, false))) return rc;
+        if ((rc = gen_inverse(ctx, gen_cache(ctx), tc, ny, nx, w.A, w.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_autocorr_out_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, ny, nx, use_norm, norm_mult,
+                                                                                        1.0 / ((double)nx * (double)ny), o);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if (grain_out) {
+            if ((rc = ensure_theta(ctx))) return rc;
+            gen_argmax_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(o, (int64_t)npix, w.pk);
+            B4D_LAUNCH_CHECK(ctx);
+            ProfScope ps(ctx, KC_GRAIN);
+            grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(o, ny, w.pk, ctx->fft->theta, fraction, grain_out + t0 * 4);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+    }
+    return B4D_OK;
+}
+
 }  // namespace
 
 void b4d_fft_release(b4d_ctx* ctx) {
     if (!ctx->fft) return;
+    gen_release(static_cast<GenCache*>(ctx->fft->gen));
     for (int i = 0; i < 5; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
@@ -1415,9 +1593,13 @@ void b4d_fft_release(b4d_ctx* ctx) {
 extern "C" int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
+    if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_fft2d: null output");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_fft2d", stack, n_frames, ny, nx);
+        return rcg ? rcg : gen_fft2d(ctx, stack, n_frames, ny, nx, out_c64);
+    }
     int rc = check_fft_args(ctx, "b4d_fft2d", stack, n_frames, ny, nx);
     if (rc) return rc;
-    if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_fft2d: null output");
     const int64_t B = batch_frames(ctx, ny, nx, 1);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
@@ -1435,9 +1617,13 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
                          int sub_mean, int zero_dc, float* out_psd, double* spectral) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
+    if (!out_psd && !spectral) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_psd2d: nothing to compute");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_psd2d", stack, n_frames, ny, nx);
+        return rcg ? rcg : gen_psd2d(ctx, stack, n_frames, ny, nx, scale_factor, sub_mean, zero_dc, out_psd, spectral);
+    }
     int rc = check_fft_args(ctx, "b4d_psd2d", stack, n_frames, ny, nx);
     if (rc) return rc;
-    if (!out_psd && !spectral) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_psd2d: nothing to compute");
     const bool want_f95 = spectral && ny == nx;
     float* map = out_psd;
     const int64_t B = batch_frames(ctx, ny, nx, 1);
@@ -1462,25 +1648,7 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
             double* tab = spectral + t0 * B4D_SP_NCOLS;
             spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx), tab, tc);
             B4D_LAUNCH_CHECK(ctx);
-            if (want_f95) {
-                const int n = ny, nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
-                void* p = nullptr;
-                const size_t hb = sizeof(double) * (size_t)tc * (nb0 > nb1 ? nb0 : nb1);
-                if ((rc = b4d_scratch(ctx, SCR_SELECT, hb + (sizeof(int) + sizeof(double)) * tc + 256, &p))) return rc;
-                double* hist = static_cast<double*>(p);
-                double* below = reinterpret_cast<double*>(static_cast<char*>(p) + hb);
-                int* cb = reinterpret_cast<int*>(below + tc);
-                B4D_CUDA(ctx, cudaMemsetAsync(p, 0, hb, ctx->stream));
-                int bx = (int)(((int64_t)n * n + 256 * 32 - 1) / (256 * 32));
-                if (bx > 296) bx = 296;
-                for (int level = 0; level < 2; ++level) {
-                    const int nb = level ? nb1 : nb0;
-                    f95_hist_kernel<<<dim3(bx, (unsigned)tc), 256, nb * sizeof(double), ctx->stream>>>(map_b, n, level, cb, hist, nb);
-                    B4D_LAUNCH_CHECK(ctx);
-                    f95_scan_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(hist, nb, level, tab, cb, below, n, tab, tc);
-                    B4D_LAUNCH_CHECK(ctx);
-                }
-            }
+            if (want_f95 && (rc = run_f95(ctx, map_b, ny, tc, tab))) return rc;
         }
     }
     return B4D_OK;
@@ -1526,7 +1694,9 @@ extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames
                               int standardize, int normalize_peak, float* out_ac, double fraction, double* grain_out) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
-    int rc = check_fft_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx);
+    const bool generic = !pow2_sides(ny, nx);
+    int rc = generic ? check_gen_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx)
+                     : check_fft_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (!out_ac && !grain_out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_autocorr2d: nothing to compute");
     if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_autocorr2d: grain widths need a square frame (pad_to_square first)");
@@ -1537,6 +1707,7 @@ extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames
     // standardised map is n = ny*nx (n var / var), i.e. the peak-normalised map times n.
     const int use_norm = normalize_peak || standardize;
     const double norm_mult = (standardize && !normalize_peak) ? (double)ny * (double)nx : 1.0;
+    if (generic) return gen_autocorr2d(ctx, stack, n_frames, ny, nx, use_norm, norm_mult, remove_mean ? 1 : 0, out_ac, fraction, grain_out);
     const int64_t B = batch_frames(ctx, ny, nx, 2);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;

@@ -38,12 +38,16 @@ def _dev(t) -> int:
     return t.device.index if t.device.index is not None else 0
 
 
-def check_fft_shape(ny: int, nx: int):
-    for n in (ny, nx):
-        if n < _lib.FFT_MIN or n > _lib.FFT_MAX or (n & (n - 1)) != 0:
-            raise _lib.B4DUnsupported(
-                f"the sm_100a FFT kernels cover power-of-two sides in [{_lib.FFT_MIN}, {_lib.FFT_MAX}]; "
-                f"got (ny, nx) = ({ny}, {nx}). There is no CPU fallback on this path.")
+def check_fft_shape(ny: int, nx: int, generic_ok: bool = False):
+    """Power-of-two sides in [128, 2048] run the hot-path kernels. fft2d / psd2d / autocorr2d (generic_ok) also take any
+    sides in [2, 1024] through the Bluestein path (csrc/generic_dft.cuh); tracking and the fused pipeline do not."""
+    pow2 = all(128 <= n <= _lib.FFT_MAX and (n & (n - 1)) == 0 for n in (ny, nx))
+    if pow2 or (generic_ok and all(2 <= n <= 1024 for n in (ny, nx))):
+        return
+    raise _lib.B4DUnsupported(
+        f"the sm_100a FFT kernels cover power-of-two sides in [128, {_lib.FFT_MAX}]"
+        + (" or any sides in [2, 1024]" if generic_ok else "")
+        + f"; got (ny, nx) = ({ny}, {nx}). There is no CPU fallback on this path.")
 
 
 # ------------------------------------------------------------------------------------------
@@ -197,7 +201,7 @@ def fft2d(stack):
     """fftshift(fft2(frame)) for every frame -> complex64 CUDA tensor (T, ny, nx)."""
     torch = require_cuda()
     T, ny, nx = stack.shape
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(stack))
     out = torch.empty((T, ny, nx, 2), dtype=torch.float32, device=stack.device)
     ctx.check(ctx.lib.b4d_fft2d(ctx.handle, ptr(stack), T, ny, nx, ptr(out)), "b4d_fft2d")
@@ -209,7 +213,7 @@ def psd2d(stack, *, scale_factor: float = 1.0, sub_mean: bool = False, zero_dc: 
     """Shifted |FFT|^2 * scale_factor per frame. Returns (psd or None, spectral table or None)."""
     torch = require_cuda()
     T, ny, nx = stack.shape
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(stack))
     out = torch.empty((T, ny, nx), dtype=torch.float32, device=stack.device) if want_map else None
     spec = torch.zeros((T, SP_NCOLS), dtype=torch.float64, device=stack.device) if want_spectral else None
@@ -223,7 +227,7 @@ def autocorr2d(stack, *, remove_mean: bool = True, standardize: bool = False, no
     """Shifted circular autocorrelation per frame (+ optional grain widths table (T, 4))."""
     torch = require_cuda()
     T, ny, nx = stack.shape
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(stack))
     out = torch.empty((T, ny, nx), dtype=torch.float32, device=stack.device) if want_map else None
     grain = torch.empty((T, 4), dtype=torch.float64, device=stack.device) if want_grain else None

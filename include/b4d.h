@@ -55,7 +55,7 @@ int b4d_device_sm_count(b4d_ctx* ctx);
  * the dominant kernel's duration inside the timed region).  b4d_profile_end synchronises the stream and
  * returns, per class, the summed device time in milliseconds and the number of bracketed launches.
  */
-#define B4D_PROF_NCLASS 15
+#define B4D_PROF_NCLASS 16
 int b4d_profile_begin(b4d_ctx* ctx);
 int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
 const char* b4d_profile_class_name(int klass);

@@ -249,3 +249,43 @@ def test_pipeline_autocorr_packed_path_vs_oracle(shape):
         assert np.max(np.abs(got[t] - mir)) <= 1e-6
     if ny == nx:
         np.testing.assert_allclose(res["grain"].cpu().numpy(), grain_plain, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(227, 228), (228, 228), (227, 227), (130, 301), (96, 64), (640, 500), (1000, 1024), (7, 5)])
+def test_arbitrary_sides_bluestein_vs_oracle(sig, shape):
+    """Frame sides that are not powers of two (the 227 / 228 px sub-tiles of the tiling executor, or any frame up to
+    1024 px a side) go through the Bluestein path: fft2d / psd2d / autocorr2d against the reference's numpy evaluation,
+    same tolerances as the power-of-two kernels (1e-5 of peak)."""
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 1009 + nx)
+    img = (800.0 + 150.0 * rng.standard_normal((ny, nx)) + 60.0 * np.sin(np.arange(nx) * 0.21)[None, :]).astype(np.float32)
+    F, fx, fy = sig.fft2d(img, dx=0.5, dy=2.0)
+    Fw, fxw, fyw = orc.fft2d(img, dx=0.5, dy=2.0)
+    np.testing.assert_allclose(fx, fxw)
+    np.testing.assert_allclose(fy, fyw)
+    peak = float(np.max(np.abs(Fw)))
+    assert np.max(np.abs(F - Fw)) <= 2e-6 * peak
+    P, _, _ = sig.psd2d(img)
+    Pw, _, _ = orc.psd2d(img)
+    assert P.dtype == Pw.dtype and np.max(np.abs(P - Pw)) <= PEAK_TOL * float(Pw.max())
+    ac, xl, yl = sig.autocorr2d(img)
+    acw, xlw, ylw = orc.autocorr2d(img)
+    np.testing.assert_allclose(xl, xlw)
+    np.testing.assert_allclose(yl, ylw)
+    assert ac.shape == acw.shape and np.max(np.abs(ac - acw)) <= PEAK_TOL
+    assert abs(ac[ny // 2, nx // 2] - 1.0) <= 1e-6
+
+
+def test_arbitrary_sides_metrics_vs_oracle():
+    """bandwidth / grain / spectral entropy / inverse autocorrelation width on a 227 x 228 tile (pad_to_square -> 228)."""
+    from barc4dip_b200 import metrics, synth
+    base = synth.speckle_frame(512, grain=6.0, seed=4)
+    tile = np.ascontiguousarray(base[100:327, 50:278])
+    assert tile.shape == (227, 228)
+    for name, got, want in (("bandwidth", metrics.speckles.bandwidth(tile), orc.bandwidth(tile)),
+                            ("grain", metrics.speckles.grain(tile), orc.grain(tile)),
+                            ("iaw", metrics.sharpness.inverse_autocorr_width(tile), orc.inverse_autocorr_width(tile))):
+        for k, v in want.items():
+            if np.ndim(v) == 0:
+                np.testing.assert_allclose(got[k], v, rtol=1e-4, err_msg=f"{name}.{k}")
+    np.testing.assert_allclose(metrics.sharpness.spectral_entropy(tile), orc.spectral_entropy(tile), rtol=1e-4)
