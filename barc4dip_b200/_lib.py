@@ -22,7 +22,7 @@ FR = {"count": 0, "mean": 1, "m2": 2, "m3": 3, "m4": 4, "nzero": 5, "nsat": 6,
       "sgx2": 7, "sgy2": 8, "slap": 9, "slap2": 10, "npix": 11, "nnan": 12}
 SP_NCOLS = 8
 SP = {"total": 0, "fx2": 1, "fy2": 2, "p2": 3, "all": 4, "plogp": 5, "f95": 6}
-FFT_MIN, FFT_MAX = 32, 2048
+FFT_MIN, FFT_MAX = 128, 2048
 
 
 class B4DError(RuntimeError):

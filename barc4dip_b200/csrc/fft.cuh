@@ -138,6 +138,7 @@ __device__ __forceinline__ void bfly(float2* x) {
 
 // ---- radix plan -------------------------------------------------------------------------------
 template <int N> struct Plan;
+template <> struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };   // Bluestein convolutions only
 template <> struct Plan<2048> { static constexpr int R1 = 16, R2 = 16, R3 = 8; };
 template <> struct Plan<1024> { static constexpr int R1 = 16, R2 = 16, R3 = 4; };
 template <> struct Plan<512>  { static constexpr int R1 = 16, R2 = 8,  R3 = 4; };
@@ -155,7 +156,7 @@ template <> struct Plan<128>  { static constexpr int R1 = 16, R2 = 8,  R3 = 1; }
 //         (two LDG.128 issued BEFORE the exchange barrier, while x[] is dead) and forms the other powers by
 //         at most two complex multiplications (error <= 7 ulp).
 // Table layout (float2): [0, 64)            stage 2: k in [0,16)   -> (w1, w2, w4, w8), base 16*R2
-//                        [64, 64 + 4*LS3)   stage 3: k in [0,LS3)  -> (w1, w2, w4, 0),  base N
+//                        [64, 64 + 4*LS3)   stage 3: k in [0,LS3)  -> (w1, w2, w4, w8 or 0),  base N
 // Synchronisation: a __syncthreads() is issued on entry (z may still be read by a previous user); on return
 //         other threads may still be reading z, so the caller synchronises before writing z itself.
 // ================================================================================================

@@ -1,10 +1,10 @@
 // Frames whose sides are not powers of two (the 227 / 228-pixel sub-tiles of the reference's 9 x 9 tiling executor,
-// metrics/common.py:75-106, :278-378, or any frame up to 1024 pixels a side): 2-D DFTs by Bluestein's chirp-z
+// metrics/common.py:75-106, :278-378, or any frame up to 2048 pixels a side): 2-D DFTs by Bluestein's chirp-z
 // algorithm on top of the power-of-two register FFT core (fft.cuh).
 //
 //   X[k] = w[k] * sum_n (x[n] w[n]) conj(w[k - n]),   w[n] = exp(-i pi n^2 / N)
 //
-// is a linear convolution, evaluated as a circular one of length M >= 2N - 1 (M = 512, 1024 or 2048):
+// is a linear convolution, evaluated as a circular one of length M >= 2N - 1 (M = 512 ... 4096):
 // FFT_M(x w) * B, inverse FFT_M, times w[k] / M, with B = FFT_M of the wrapped conj chirp (host, double precision,
 // cached per N). One kernel performs the whole 1-D transform of a row: M/16 threads, two in-register FFTs, nothing
 // but the row itself crosses HBM. A 2-D transform is rows, transpose, rows; inverse transforms conjugate on the way
@@ -22,8 +22,8 @@ struct GenCache {
     std::vector<GenPlan> plans;
 };
 
-inline bool gen_size_ok(int n) { return n >= 2 && n <= 1024; }
-inline int gen_conv_len(int n) { return n <= 256 ? 512 : (n <= 512 ? 1024 : 2048); }
+inline bool gen_size_ok(int n) { return n >= 2 && n <= 2048; }
+inline int gen_conv_len(int n) { return n <= 256 ? 512 : (n <= 512 ? 1024 : (n <= 1024 ? 2048 : 4096)); }
 
 // iterative radix-2 FFT in double precision (host; tables only)
 inline void host_fft(std::vector<double>& re, std::vector<double>& im) {
@@ -276,7 +276,8 @@ int gen_rows(b4d_ctx* ctx, GenCache*& cache, BluArgs a) {
     switch (p->M) {
         case 512: return launch_bluestein<512>(ctx, a);
         case 1024: return launch_bluestein<1024>(ctx, a);
-        default: return launch_bluestein<2048>(ctx, a);
+        case 2048: return launch_bluestein<2048>(ctx, a);
+        default: return launch_bluestein<4096>(ctx, a);
     }
 }
 

@@ -35,7 +35,7 @@ int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, 
                             float* pilot_out);
 
 struct FftPlanCache {
-    float2* twb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power twiddle tables: 128, 256, 512, 1024, 2048
+    float2* twb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power twiddle tables: 128 ... 4096
     // tracker reference: conj spectrum of the embedded z-scored template
     float2* ref = nullptr;       // blocked (nx/2/8, ny, 8)
     float2* ref_nyq = nullptr;   // (ny)
@@ -67,7 +67,7 @@ void fill_twiddle_bases(std::vector<float2>& h) {
     };
     for (int k = 0; k < 16; ++k) put(4 * (size_t)k, k, 16.0 * P::R2, 4);
     if (P::R3 > 1)
-        for (int k = 0; k < 16 * P::R2; ++k) put(64 + 4 * (size_t)k, k, (double)N, 3);
+        for (int k = 0; k < 16 * P::R2; ++k) put(64 + 4 * (size_t)k, k, (double)N, P::R3 > 8 ? 4 : 3);
 }
 
 int get_twiddle_bases(b4d_ctx* ctx, int n, const float2** out) {
@@ -80,6 +80,7 @@ int get_twiddle_bases(b4d_ctx* ctx, int n, const float2** out) {
             case 256: fill_twiddle_bases<256>(h); break;
             case 512: fill_twiddle_bases<512>(h); break;
             case 1024: fill_twiddle_bases<1024>(h); break;
+            case 4096: fill_twiddle_bases<4096>(h); break;
             default: fill_twiddle_bases<2048>(h); break;
         }
         B4D_CUDA(ctx, cudaMalloc(&ctx->fft->twb[slot], h.size() * sizeof(float2)));
@@ -1436,7 +1437,7 @@ int check_gen_args(b4d_ctx* ctx, const char* who, const void* stack, int64_t T, 
     if (!stack || T < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "%s: bad arguments", who);
     if (!gen_size_ok(ny) || !gen_size_ok(nx) || T > ((int64_t)1 << 24))
         return b4d_fail(ctx, B4D_ERR_UNSUPPORTED,
-                        "%s: frames need power-of-two sides in [128, 2048] or any sides in [2, 1024]; got T=%lld (ny, nx)=(%d, %d)",
+                        "%s: frames need sides in [2, 2048]; got T=%lld (ny, nx)=(%d, %d)",
                         who, (long long)T, ny, nx);
     return B4D_OK;
 }
@@ -1578,7 +1579,7 @@ int gen_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, i
 void b4d_fft_release(b4d_ctx* ctx) {
     if (!ctx->fft) return;
     gen_release(static_cast<GenCache*>(ctx->fft->gen));
-    for (int i = 0; i < 5; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
+    for (int i = 0; i < 6; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
     if (ctx->fft->theta) cudaFree(ctx->fft->theta);

@@ -17,7 +17,8 @@ import numpy as np
 
 from .. import engine, stack as blocks
 from .._lib import B4DUnsupported
-from .common import apply_display_origin, normalize_display_origin, normalize_groups, reject_tiles
+from .common import (apply_display_origin, choose_tiling_mode, normalize_display_origin, normalize_groups, tiled_blocks,
+                     tiles_meta)
 
 logger = logging.getLogger(__name__)
 
@@ -149,8 +150,8 @@ def sharpness_stats(image, *, metrics="all", tiles: bool = True, display_origin:
     image = apply_display_origin(image, display_origin=display_origin)
     h, w = image.shape
     groups = _resolve_groups(metrics)
-    reject_tiles(tiles, h, w)
-    full = _full_blocks(engine.as_stack(np.ascontiguousarray(image)), groups, saturation_value, eps)
+    dev = engine.as_stack(np.ascontiguousarray(image))
+    full = _full_blocks(dev, groups, saturation_value, eps)
     out = {"meta": {"kind": "sharpness", "display_origin": display_origin, "input_shape": (int(h), int(w)),
                     "requested_groups": sorted(groups), "units": _SHARPNESS_UNITS, "tile_mode": "off"},
            "full": {}}
@@ -158,9 +159,21 @@ def sharpness_stats(image, *, metrics="all", tiles: bool = True, display_origin:
     for grp in order:
         if grp in full:
             out["full"][grp] = _scalar(full[grp])
+    mode, tile_shape_px = choose_tiling_mode(h, w, tiles=tiles)
+    if mode != "off":
+        out["meta"].update(tiles_meta(h, w, tile_mode=mode, tile_shape_px=tile_shape_px))
+        tl = _tiles(dev, mode, groups, saturation_value, eps)
+        if tl:
+            out["tiles"] = {g: {k: {"mean": v["mean"][0], "std": v["std"][0]} for k, v in f.items()} for g, f in tl.items()}
     if verbose:
         logger.info("\nsharpness stats for a (h x w: %.0f x %.0f) image: %s", h, w, sorted(groups))
     return out
+
+
+def _tiles(dev_oriented, mode, groups, saturation_value, eps) -> dict:
+    """{group: {field: {"mean": (T, 3, 3), "std": (T, 3, 3)}}} of a display-oriented device stack (sharpness.py:213-282)."""
+    res = tiled_blocks(dev_oriented, tile_mode=mode, block_fn=lambda tl: _full_blocks(tl, groups, saturation_value, eps))
+    return {g: res[g] for g in ("stats", "gradient", "laplacian", "spectral", "autocorrelation") if g in res}
 
 
 def sharpness_stack_stats(stack, *, metrics="all", tiles: bool = True, display_origin: str = "lower",
@@ -180,15 +193,22 @@ def sharpness_stack_stats(stack, *, metrics="all", tiles: bool = True, display_o
         raise ValueError("stack must contain at least one frame.")
     normalize_display_origin(display_origin)
     groups = _resolve_groups(metrics)
-    reject_tiles(tiles, H, W)
     # full-frame scalars do not depend on the row flip of display_origin="lower" 
-    full = _full_blocks(engine.as_stack(stack), groups, saturation_value, eps)
+    dev = engine.as_stack(stack)
+    full = _full_blocks(dev, groups, saturation_value, eps)
     serial = (not parallel) or (n_jobs is not None and int(n_jobs) <= 1)
     meta = {"kind": "sharpness_stack_stats", "input_shape": (H, W), "stack_shape": (T, H, W), "n_frames": T,
             "display_origin": display_origin, "requested_groups": sorted(groups), "units": _SHARPNESS_UNITS,
             "parallel": {"enabled": bool(not serial), "n_jobs": None if serial else (-1 if n_jobs is None else n_jobs)},
-            "tile_mode": "off"}
+            }
     out_full = {grp: full[grp] for grp in ("stats", "gradient", "laplacian", "spectral", "autocorrelation") if grp in full}
+    out = {"meta": meta, "full": out_full}
+    mode, _ = choose_tiling_mode(H, W, tiles=tiles)
+    if mode != "off":
+        oriented = dev.flip(1) if normalize_display_origin(display_origin) == "lower" else dev
+        tl = _tiles(oriented, mode, groups, saturation_value, eps)
+        if tl:
+            out["tiles"] = tl
     if verbose:
         logger.info("> sharpness_stack_stats | frames=%d | device=cuda", T)
-    return {"meta": meta, "full": out_full}
+    return out

@@ -15,7 +15,8 @@ import numpy as np
 from .. import engine, stack as blocks
 from .._lib import B4DUnsupported
 from ..signal.common import lag_axis
-from .common import apply_display_origin, normalize_display_origin, normalize_groups, reject_tiles
+from .common import (apply_display_origin, choose_tiling_mode, normalize_display_origin, normalize_groups, tiled_blocks,
+                     tiles_meta)
 
 logger = logging.getLogger(__name__)
 
@@ -113,8 +114,8 @@ def speckle_stats(image, *, metrics="all", tiles: bool = True, display_origin: s
     image = apply_display_origin(image, display_origin=display_origin)
     h, w = image.shape
     groups = normalize_groups(metrics, all_groups=_ALL_SPECKLE_GROUPS, context="speckles", param_name="metrics")
-    reject_tiles(tiles, h, w)
-    full = _full_blocks(engine.as_stack(np.ascontiguousarray(image)), groups, saturation_value, eps, keep_maps=True)
+    dev = engine.as_stack(np.ascontiguousarray(image))
+    full = _full_blocks(dev, groups, saturation_value, eps, keep_maps=True)
     out = {"meta": {"kind": "speckles", "display_origin": display_origin, "input_shape": (int(h), int(w)),
                     "requested_groups": sorted(groups), "units": _SPECKLE_UNITS, "tile_mode": "off"}, "full": {}}
     for grp in ("amplitude", "grain", "stats", "bandwidth"):
@@ -129,9 +130,22 @@ def speckle_stats(image, *, metrics="all", tiles: bool = True, display_origin: s
             else:
                 blk[k] = float(v[0])
         out["full"][grp] = blk
+    mode, tile_shape_px = choose_tiling_mode(h, w, tiles=tiles)
+    if mode != "off":
+        out["meta"].update(tiles_meta(h, w, tile_mode=mode, tile_shape_px=tile_shape_px))
+        tl = _tiles(dev, mode, groups, saturation_value, eps)
+        if tl:
+            out["tiles"] = {g: {k: {"mean": v["mean"][0], "std": v["std"][0]} for k, v in f.items()} for g, f in tl.items()}
     if verbose:
         logger.info("\nspeckle stats for a (h x w: %.0f x %.0f) image: %s", h, w, sorted(groups))
     return out
+
+
+def _tiles(dev_oriented, mode, groups, saturation_value, eps) -> dict:
+    """{group: {field: {"mean": (T, 3, 3), "std": (T, 3, 3)}}} of a display-oriented device stack (speckles.py:192-250)."""
+    res = tiled_blocks(dev_oriented, tile_mode=mode,
+                       block_fn=lambda tl: _full_blocks(tl, groups, saturation_value, eps, keep_maps=False))
+    return {g: res[g] for g in ("amplitude", "grain", "stats", "bandwidth") if g in res}
 
 
 def _odd_size(n: float, min_size: int = 3) -> int:
@@ -177,7 +191,6 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
         raise ValueError("stack must contain at least one frame.")
     normalize_display_origin(display_origin)
     groups = normalize_groups(metrics, all_groups=_ALL_SPECKLE_GROUPS, context="speckles", param_name="metrics")
-    reject_tiles(tiles, H, W)
     if str(tracking_method).strip().lower() != "phase" or tracking_backend != "internal":
         raise B4DUnsupported("speckle_stack_stats on the B200 path tracks with tracking_method='phase', "
                              "tracking_backend='internal'; the template/skimage/opencv trackers are not built")
@@ -235,9 +248,16 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
                      "roi_labels": np.array([["NW", "N", "NE"], ["W", "C", "E"], ["SW", "S", "SE"]], dtype=object),
                      "roi_order": "row-major"},
         "parallel": {"enabled": bool(not serial), "joblib_verbose": 0},
-        "tile_mode": "off",
     }
     out_full = {grp: full[grp] for grp in ("amplitude", "grain", "stats", "bandwidth") if grp in full}
+    out = {"meta": meta, "full": out_full, "temporal": temporal}
+    # tiles: the reference evaluates speckle_stats(frame, tiles=...) per frame, i.e. on the display-oriented frame
+    mode, _ = choose_tiling_mode(H, W, tiles=tiles)
+    if mode != "off":
+        oriented = dev.flip(1) if normalize_display_origin(display_origin) == "lower" else dev
+        tl = _tiles(oriented, mode, groups, saturation_value, eps)
+        if tl:
+            out["tiles"] = tl
     if verbose:
         logger.info("> speckle_stack_stats | frames=%d | roi=%dx%d | step=%d | device=cuda", T, roi, roi, step)
-    return {"meta": meta, "full": out_full, "temporal": temporal}
+    return out

@@ -169,10 +169,13 @@ int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, 
 
 /* ---- 2-D FFT family ---------------------------------------------------------------------- */
 /*
- * Supported frame sizes: ny, nx powers of two in [B4D_FFT_MIN, B4D_FFT_MAX].  Anything else
- * returns B4D_ERR_UNSUPPORTED (the Python layer raises; there is no CPU fallback).
+ * Frame sizes. Powers of two in [B4D_FFT_MIN, B4D_FFT_MAX] run the hot-path kernels (every entry point below).
+ * b4d_fft2d, b4d_psd2d and b4d_autocorr2d also accept ANY sides in [2, B4D_FFT_MAX] (the 227 / 228-pixel sub-tiles of
+ * the reference's tiling executor, metrics/common.py:278-378): those go through Bluestein's algorithm on the same FFT
+ * core (csrc/generic_dft.cuh). Cross-correlation, tracking and the fused pipeline are built for powers of two only.
+ * Anything else returns B4D_ERR_UNSUPPORTED (the Python layer raises; there is no CPU fallback).
  */
-#define B4D_FFT_MIN 32
+#define B4D_FFT_MIN 128
 #define B4D_FFT_MAX 2048
 
 /* fft2d (signal/fft.py:198-237): out = fftshift(fft2(frame)), complex64 interleaved (ny, nx). */

@@ -95,3 +95,13 @@ def flatfield_inputs():
 def temporal_inputs():
     raw, flat, dark = synth.flatfield_case(24, 64, seed=41, dead_frac=2e-3)
     return raw, flat, dark
+
+
+def tile_cases() -> dict[str, np.ndarray]:
+    """Frames for the 3x3 / 9x9 tiling executor (metrics/common.py:278-378): 512^2 -> tiles_3x3 with 170 / 171 px tiles;
+    1170 x 1200 -> subtiles_9x9 with 130 px x 133 / 134 px sub-tiles (none a power of two)."""
+    return {"t3_512": synth.speckle_frame(512, grain=6.0, seed=17),
+            "t9_1170x1200": synth.speckle_frame(1170, 1200, grain=5.0, seed=19)}
+
+
+SHARPNESS_TILE_GROUPS = ("stats", "gradient", "laplacian", "spectral", "autocorrelation")

@@ -44,12 +44,40 @@ def map_digest(a, prefix, store):
     store[prefix + "_sumabs2"] = np.asarray((np.abs(a) ** 2).sum())
 
 
+def tiles_golden(met, versions):
+    """tiles.npz: the reference's tiling executor on the frames of golden_cases.tile_cases()."""
+    store = {"versions": versions}
+    for name, img in gc.tile_cases().items():
+        sp = met.speckle_stats(img, tiles=True, verbose=False)
+        sh = met.sharpness_stats(img, metrics=gc.SHARPNESS_TILE_GROUPS, tiles=True, verbose=False)
+        for tag, res in (("speckle", sp), ("sharpness", sh)):
+            store[f"{name}/{tag}/tile_mode"] = np.array(res["meta"]["tile_mode"])
+            store[f"{name}/{tag}/tile_shape_px"] = np.asarray(res["meta"]["tile_shape_px"])
+            for grp, fields in res["tiles"].items():
+                for k, v in fields.items():
+                    store[f"{name}/{tag}/{grp}/{k}/mean"] = np.asarray(v["mean"], dtype=np.float64)
+                    store[f"{name}/{tag}/{grp}/{k}/std"] = np.asarray(v["std"], dtype=np.float64)
+    # stack variant: leading T axis, per-frame display orientation
+    img = gc.tile_cases()["t3_512"]
+    stack = np.stack([img, np.ascontiguousarray(img[::-1, ::-1]) * 0.5 + 3.0], axis=0)
+    shs = met.sharpness_stack_stats(stack, metrics=("stats", "gradient", "spectral"), tiles=True, verbose=False, parallel=False)
+    for grp, fields in shs["tiles"].items():
+        for k, v in fields.items():
+            store[f"stack/sharpness/{grp}/{k}/mean"] = np.asarray(v["mean"], dtype=np.float64)
+            store[f"stack/sharpness/{grp}/{k}/std"] = np.asarray(v["std"], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "tiles.npz"), **store)
+
+
 def main():
     ref = load_reference()
     sig, met, pre = ref.signal, ref.metrics, ref.preprocessing_normalize
     os.makedirs(OUT, exist_ok=True)
     import scipy
     versions = np.array([np.__version__, scipy.__version__])
+    if "--only-tiles" in sys.argv:
+        tiles_golden(met, versions)
+        print("tiles.npz", os.path.getsize(os.path.join(OUT, "tiles.npz")) // 1024, "KiB")
+        return
 
     # ---------------- per-frame functions ----------------
     store = {"versions": versions}
@@ -167,6 +195,8 @@ def main():
     out = pre.flat_field_correction(raw, flats=flat)
     store["ffc/flatonly/sum"] = np.asarray(out.astype(np.float64).sum())
     np.savez_compressed(os.path.join(OUT, "flatfield.npz"), **store)
+
+    tiles_golden(met, versions)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

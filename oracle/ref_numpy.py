@@ -604,3 +604,81 @@ def temporal_moments(stack):
     std = x.std(axis=0)
     return {"mean": x.mean(axis=0), "std": std, "variance": std * std,
             "skewness": np.asarray(d.skewness), "kurtosis": np.asarray(d.kurtosis)}
+
+
+# --------------------------------------------------------------------------------------
+# tiling executor (metrics/common.py)
+# --------------------------------------------------------------------------------------
+
+def split_edges(length, n_parts):
+    """ref: metrics/common.py:75-106 -- edges at round(linspace(0, length, n_parts + 1)), last stop = length."""
+    edges = np.linspace(0, length, n_parts + 1)
+    out = []
+    for i in range(n_parts):
+        a = int(round(float(edges[i])))
+        b = max(int(round(float(edges[i + 1]))), a + 1)
+        out.append((a, b))
+    out[-1] = (out[-1][0], length)
+    return out
+
+
+def choose_tiling_mode(h, w, min_tile_px=128):
+    """ref: metrics/common.py:109-170 (tiles=True branch)."""
+    if h // 9 >= min_tile_px and w // 9 >= min_tile_px:
+        return "subtiles_9x9"
+    if h // 3 >= min_tile_px and w // 3 >= min_tile_px:
+        return "tiles_3x3"
+    return "off"
+
+
+def tiled_scalar_fields(image, tile_mode, compute_fn):
+    """ref: metrics/common.py:278-378 -- {field: {"mean": 3x3, "std": 3x3}}; tiles_3x3: values and NaN; subtiles_9x9:
+    np.mean / np.std(ddof=0) of each 3x3 block of the 9x9 sub-tile grid (:248-275)."""
+    img = np.asarray(image)
+    h, w = img.shape
+    n = 3 if tile_mode == "tiles_3x3" else 9
+    ye, xe = split_edges(h, n), split_edges(w, n)
+    grids = {}
+    for r, (y0, y1) in enumerate(ye):
+        for c, (x0, x1) in enumerate(xe):
+            for k, v in compute_fn(img[y0:y1, x0:x1]).items():
+                grids.setdefault(k, np.empty((n, n)))[r, c] = float(v)
+    out = {}
+    for k, g in grids.items():
+        if n == 3:
+            out[k] = {"mean": g, "std": np.full((3, 3), np.nan)}
+        else:
+            mean, std = np.empty((3, 3)), np.empty((3, 3))
+            for r in range(3):
+                for c in range(3):
+                    blk = g[3 * r:3 * r + 3, 3 * c:3 * c + 3]
+                    mean[r, c], std[r, c] = np.mean(blk), np.std(blk, ddof=0)
+            out[k] = {"mean": mean, "std": std}
+    return out
+
+
+def speckle_tiles(image, display_origin="lower", saturation_value=65535.0, eps=1e-6):
+    """ref: metrics/speckles.py:148,192-250 -- the "tiles" block of speckle_stats(image, tiles=True), all groups."""
+    img = np.asarray(image)[::-1, :] if display_origin == "lower" else np.asarray(image)
+    mode = choose_tiling_mode(*img.shape)
+    scal = lambda d, keys: {k: float(d[k]) for k in keys}
+    return mode, {
+        "amplitude": tiled_scalar_fields(img, mode, lambda t: scal(amplitude(t), ("visibility", "contrast"))),
+        "grain": tiled_scalar_fields(img, mode, lambda t: scal(grain(t), ("lx", "ly", "leq", "r"))),
+        "stats": tiled_scalar_fields(img, mode, lambda t: distribution_moments(t, saturation_value=saturation_value, eps=eps)),
+        "bandwidth": tiled_scalar_fields(img, mode, lambda t: scal(bandwidth(t), ("spr", "feq", "f95", "sig_fx", "sig_fy", "rf"))),
+    }
+
+
+def sharpness_tiles(image, display_origin="lower", saturation_value=65535.0, eps=1e-6):
+    """ref: metrics/sharpness.py:163,213-282 -- the "tiles" block of sharpness_stats(image, tiles=True) without eigenvalues."""
+    img = np.asarray(image)[::-1, :] if display_origin == "lower" else np.asarray(image)
+    mode = choose_tiling_mode(*img.shape)
+    scal = lambda d, keys: {k: float(d[k]) for k in keys}
+    return mode, {
+        "stats": tiled_scalar_fields(img, mode, lambda t: distribution_moments(t, saturation_value=saturation_value, eps=eps)),
+        "gradient": tiled_scalar_fields(img, mode, lambda t: scal(tenengrad(t), ("tenengrad", "ex", "ey", "re"))),
+        "laplacian": tiled_scalar_fields(img, mode, lambda t: {"laplacian_variance": laplacian_variance(t)}),
+        "spectral": tiled_scalar_fields(img, mode, lambda t: {"spectral_entropy": spectral_entropy(t)}),
+        "autocorrelation": tiled_scalar_fields(img, mode, lambda t: scal(inverse_autocorr_width(t), ("sx", "sy", "seq", "r"))),
+    }

@@ -10,7 +10,7 @@ from oracle import ref_numpy as orc
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4
-POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512"]
+POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512", "odd150x200"]   # odd150x200: the Bluestein path
 
 
 @pytest.fixture(scope="module")
@@ -89,8 +89,9 @@ def test_aggregator_errors_and_schema(dip):
         dip.metrics.sharpness_stats(img, tiles=False, display_origin="left")
     with pytest.raises(B4DUnsupported):
         dip.metrics.sharpness_stats(img, metrics="eigenvalues", tiles=False)
-    with pytest.raises(B4DUnsupported):
-        dip.metrics.speckle_stats(gc.frame_cases()["sq512"], tiles=True, verbose=False)   # 512//3 >= 128 -> tiles wanted
+    with pytest.warns(RuntimeWarning, match="too small for tiling"):
+        small = dip.metrics.speckle_stats(img, metrics="stats", tiles=True, verbose=False)   # 256//3 < 128
+    assert "tiles" not in small
     with pytest.warns(RuntimeWarning):
         out = dip.metrics.sharpness_stats(img, tiles=False, verbose=False)                # "all" skips eigenvalues
     assert set(out["full"]) == {"stats", "gradient", "laplacian", "spectral", "autocorrelation"}
@@ -174,3 +175,50 @@ def test_stack_analyzer_native_integer_stacks(dtype):
     for k in ("dy", "dx", "peak", "snr"):
         np.testing.assert_array_equal(a["tracking"][k], b["tracking"][k])
     np.testing.assert_array_equal(a["amplitude"]["contrast"], b["amplitude"]["contrast"])
+
+
+def _check_tiles(tiles, g, prefix, squeeze=None):
+    for grp, fields in tiles.items():
+        for k, v in fields.items():
+            mean, std = np.asarray(v["mean"]), np.asarray(v["std"])
+            wm, ws = g[f"{prefix}/{grp}/{k}/mean"], g[f"{prefix}/{grp}/{k}/std"]
+            assert mean.shape == wm.shape and std.shape == ws.shape, (grp, k)
+            np.testing.assert_allclose(mean, wm, rtol=RTOL, atol=1e-12, err_msg=f"{prefix} {grp}.{k} mean")
+            # a spread over nine sub-tiles is a difference of nearly equal numbers: held to RTOL of the level it is about
+            scale = np.maximum(np.abs(wm), 1e-300)
+            assert np.all(np.isnan(std) == np.isnan(ws)), (grp, k)
+            ok = ~np.isnan(ws)
+            assert np.all(np.abs(std[ok] - ws[ok]) <= 3 * RTOL * scale[ok] + RTOL * np.abs(ws[ok])), f"{prefix} {grp}.{k} std"
+
+
+@pytest.mark.parametrize("name", ["t3_512", "t9_1170x1200"])
+def test_tiles_vs_golden(dip, golden, name):
+    """speckle_stats / sharpness_stats(tiles=True) against the reference's tiling executor: 3x3 tiles of 170 / 171 px and
+    9x9 sub-tiles of 130 x 133 / 134 px -- none a power of two, so every spectral metric runs on the Bluestein path."""
+    g = golden("tiles")
+    img = gc.tile_cases()[name]
+    sp = dip.metrics.speckle_stats(img, tiles=True, verbose=False)
+    assert sp["meta"]["tile_mode"] == str(g[f"{name}/speckle/tile_mode"])
+    assert tuple(sp["meta"]["tile_shape_px"]) == tuple(int(v) for v in g[f"{name}/speckle/tile_shape_px"])
+    assert sp["meta"]["used_subtiles"] == (name.startswith("t9"))
+    assert set(sp["tiles"]) == {"amplitude", "grain", "stats", "bandwidth"}
+    _check_tiles(sp["tiles"], g, f"{name}/speckle")
+    with pytest.warns(RuntimeWarning):      # "all" skips eigenvalues
+        sh = dip.metrics.sharpness_stats(img, tiles=True, verbose=False)
+    assert set(sh["tiles"]) == set(gc.SHARPNESS_TILE_GROUPS)
+    _check_tiles(sh["tiles"], g, f"{name}/sharpness")
+
+
+def test_stack_tiles_vs_golden(dip, golden):
+    """Stack aggregator: every tile leaf gets a leading T axis and each frame is display-oriented before tiling."""
+    g = golden("tiles")
+    img = gc.tile_cases()["t3_512"]
+    stack = np.stack([img, np.ascontiguousarray(img[::-1, ::-1]) * 0.5 + 3.0], axis=0)
+    shs = dip.metrics.sharpness_stack_stats(stack, metrics=("stats", "gradient", "spectral"), tiles=True, verbose=False)
+    assert shs["tiles"]["stats"]["mean"]["mean"].shape == (2, 3, 3)
+    _check_tiles(shs["tiles"], g, "stack/sharpness")
+    # and the single-frame call on frame 1 agrees with the stack's second slice
+    one = dip.metrics.sharpness_stats(stack[1], metrics=("stats", "gradient", "spectral"), tiles=True, verbose=False)
+    for grp, fields in one["tiles"].items():
+        for k, v in fields.items():
+            np.testing.assert_allclose(v["mean"], shs["tiles"][grp][k]["mean"][1], rtol=1e-12)

@@ -8,7 +8,7 @@ from oracle import ref_numpy as orc
 
 pytestmark = pytest.mark.gpu
 
-POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512"]
+POW2 = ["sq256", "rect128x256", "u16_128", "blur256", "sq512", "odd150x200"]   # odd150x200: the Bluestein path
 PEAK_TOL = 1e-5     # north_star: PSD and autocorrelation within 1e-5 relative error of peak
 
 
@@ -73,6 +73,8 @@ def test_autocorr_xcorr_vs_golden(sig, golden, name):
     _digest_close(a2, g, f"{name}/autocorr2d_std_none", PEAK_TOL)
     a3, _, _ = sig.autocorr2d(img, remove_mean=False, normalize="none")
     _digest_close(a3, g, f"{name}/autocorr2d_raw_none", PEAK_TOL)
+    if name.startswith("odd"):
+        return                                  # cross-correlation is built for power-of-two frames only
     xc, _, _ = sig.xcorr2d(img, np.roll(np.asarray(img), (5, -7), axis=(0, 1)))
     _digest_close(xc, g, f"{name}/xcorr2d_real", PEAK_TOL)
     assert tuple(np.unravel_index(int(np.argmax(np.abs(xc))), xc.shape)) == tuple(g[f"{name}/xcorr2d_argmax"])
@@ -99,7 +101,12 @@ def test_fft_roundtrip_and_parseval_2048():
 def test_unsupported_sizes_fail_loudly(sig):
     from barc4dip_b200._lib import B4DUnsupported
     with pytest.raises(B4DUnsupported):
-        sig.psd2d(gc.frame_cases()["odd150x200"])
+        sig.psd2d(np.zeros((16, 2050), np.float32))                   # sides above 2048 are not built
+    odd = gc.frame_cases()["odd150x200"]
+    with pytest.raises(B4DUnsupported):
+        sig.xcorr2d(odd, odd)                                         # cross-correlation and tracking: powers of two only
+    with pytest.raises(B4DUnsupported):
+        sig.phase_correlation(odd, odd, slices_yx=(slice(0, 150), slice(0, 200)))
     with pytest.raises(ValueError):
         sig.psd2d(np.zeros((4, 4, 4), np.float32))
     with pytest.raises(ValueError):

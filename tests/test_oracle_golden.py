@@ -184,3 +184,21 @@ def test_known_answers():
     assert not edge and abs(w - 2 * np.sqrt(2) * 9.0) < 0.02
     w, edge = orc.width_at_fraction(np.ones(17))
     assert edge and w == 17.0
+
+
+def test_tiling_executor_matches_reference(golden):
+    """The oracle's tiling executor (split_edges, 3x3 / 9x9 policy, 9x9 -> 3x3 aggregation) against tiles.npz, recorded
+    from the reference's speckle_stats / sharpness_stats(tiles=True) on 170/171 px tiles and 130 x 133/134 px sub-tiles."""
+    g = golden("tiles")
+    assert orc.split_edges(2048, 9) == [(0, 228), (228, 455), (455, 683), (683, 910), (910, 1138), (1138, 1365),
+                                        (1365, 1593), (1593, 1820), (1820, 2048)]
+    for name, img in gc.tile_cases().items():
+        for tag, fn in (("speckle", orc.speckle_tiles), ("sharpness", orc.sharpness_tiles)):
+            mode, tiles = fn(img)
+            assert mode == str(g[f"{name}/{tag}/tile_mode"])
+            for grp, fields in tiles.items():
+                for k, v in fields.items():
+                    np.testing.assert_allclose(v["mean"], g[f"{name}/{tag}/{grp}/{k}/mean"], rtol=1e-9, atol=1e-12,
+                                               err_msg=f"{name} {tag} {grp}.{k} mean")
+                    np.testing.assert_allclose(v["std"], g[f"{name}/{tag}/{grp}/{k}/std"], rtol=1e-7, atol=1e-12,
+                                               err_msg=f"{name} {tag} {grp}.{k} std")
