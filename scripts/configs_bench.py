@@ -64,3 +64,29 @@ gain = engine.flat_gain(d_flat, d_dark, eps=eps, scale_value=float(np.median(den
 st1 = torch.from_numpy(raw).to(dev).repeat(F1 // 8, 1, 1)
 ms = timed(lambda: engine.temporal_moments(st1, gain=gain, dark=d_dark, return_device=True))
 line("C5 temporal moments 1024^2 + flat field", st1.shape[0], ms, m * m * 4, "one streaming read per frame")
+del st1
+# C1: one 2048^2 frame through the barc4dip-speckles path (speckle_stats: stats, amplitude, grain, bandwidth), full frame
+# and with the reference's default 9x9 sub-tile grid (227 / 228 px tiles: Bluestein FFT path); latency, host array in,
+# result dict out. CPU: the oracle port of the same call on this box (one pass each).
+import time
+import barc4dip_b200 as dip
+from oracle import ref_numpy as orc
+frame = synth.speckle_frame(2048, grain=6.0, seed=0)
+for tiles in (False, True):
+    for _ in range(2):
+        dip.metrics.speckle_stats(frame, tiles=tiles, verbose=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        dip.metrics.speckle_stats(frame, tiles=tiles, verbose=False)
+    torch.cuda.synchronize()
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    flipped = frame[::-1, :]
+    orc.amplitude(flipped); orc.grain(flipped); orc.distribution_moments(flipped); orc.bandwidth(flipped)
+    if tiles:
+        orc.speckle_tiles(frame)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"config": f"C1 speckle_stats 2048^2 tiles={tiles}", "gpu_ms": round(gpu_ms, 2), "cpu_port_ms": round(cpu_ms, 1),
+                      "speedup": round(cpu_ms / gpu_ms, 1), "note": "latency of one call, host numpy in, result dict out; CPU = oracle port, 1 thread"}), flush=True)
