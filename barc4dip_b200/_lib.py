@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b4d_frame_reductions": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _vp],
     "b4d_select_ranks": [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp],
     "b4d_flat_field": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _i32, _vp],
+    "b4d_bad_pixel_repair": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32],
     "b4d_flat_gain": [_vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp],
     "b4d_sub": [_vp, _vp, _vp, _i64, _vp],
     "b4d_temporal_accumulate": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],

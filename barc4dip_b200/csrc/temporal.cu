@@ -176,6 +176,43 @@ __global__ void __launch_bounds__(256) flat_field_kernel(const float* __restrict
     }
 }
 
+// 3x3 median repair of the bad pixels (preprocessing/normalize.py:134-140): out[bad] = median_filter(out, size=3)[bad],
+// scipy's default 'reflect' border (the edge sample repeated). The filter sees the UNREPAIRED frame, in which every bad
+// pixel is 0 -- so a bad neighbour contributes 0 whether or not its own repair has already been written, and the repair
+// can run in place.
+__device__ __forceinline__ void cswap(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+
+__global__ void __launch_bounds__(256) bad_pixel_repair_kernel(float* __restrict__ frames, int64_t T, int ny, int nx,
+                                                               const float* __restrict__ flat, const float* __restrict__ dark,
+                                                               float eps) {
+    const int64_t npix = (int64_t)ny * nx;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    auto is_bad = [&](int64_t q) { return flat[q] - (dark ? dark[q] : 0.f) <= eps; };
+    if (!is_bad(p)) return;
+    const int y = (int)(p / nx), x = (int)(p % nx);
+    int64_t nb[9];
+    bool nbad[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = min(max(y + k / 3 - 1, 0), ny - 1), xx = min(max(x + k % 3 - 1, 0), nx - 1);
+        nb[k] = (int64_t)yy * nx + xx;
+        nbad[k] = is_bad(nb[k]);
+    }
+    for (int64_t t = blockIdx.y; t < T; t += gridDim.y) {
+        float* f = frames + t * npix;
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = nbad[k] ? 0.f : f[nb[k]];
+        // median of nine by the 19-exchange network
+        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+        cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+        cswap(v[4], v[2]);
+        f[p] = v[4];
+    }
+}
+
 __global__ void __launch_bounds__(256) flat_gain_kernel(const float* __restrict__ flat, const float* __restrict__ dark,
                                                         int64_t npix, float eps, float s, float* __restrict__ gain) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,6 +300,20 @@ extern "C" int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frame
     ProfScope ps(ctx, KC_FLATFIELD);
     flat_field_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(images, n_frames, npix, flat, dark, eps, scale_value,
                                                              apply_scale, out);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
+extern "C" int b4d_bad_pixel_repair(b4d_ctx* ctx, float* frames, int64_t n_frames, int ny, int nx, const float* flat,
+                                    const float* dark, float eps) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    if (!frames || !flat || n_frames < 1 || ny < 1 || nx < 1)
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_bad_pixel_repair: bad arguments");
+    const int64_t npix = (int64_t)ny * nx;
+    const unsigned gy = (unsigned)(n_frames < 64 ? n_frames : 64);
+    ProfScope ps(ctx, KC_FLATFIELD);
+    bad_pixel_repair_kernel<<<dim3((unsigned)((npix + 255) / 256), gy), 256, 0, ctx->stream>>>(frames, n_frames, ny, nx, flat, dark, eps);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }

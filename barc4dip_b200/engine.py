@@ -20,7 +20,7 @@ from ._lib import FR, FR_NCOLS, SP, SP_NCOLS, get_context, ptr, require_cuda
 __all__ = [
     "as_stack", "frame_reductions", "select_quantiles", "flat_field", "flat_gain",
     "temporal_moments", "TemporalAccumulator", "fft2d", "psd2d", "autocorr2d", "xcorr2d",
-    "PhaseTracker", "stack_pipeline", "check_fft_shape",
+    "PhaseTracker", "stack_pipeline", "check_fft_shape", "bad_pixel_repair",
 ]
 
 
@@ -126,6 +126,15 @@ def flat_field(stack, flat, dark, *, eps: float, scale_value: float, apply_scale
     ctx.check(ctx.lib.b4d_flat_field(ctx.handle, ptr(stack), T, ny, nx, ptr(flat), ptr(dark), float(eps),
                                      float(scale_value), int(bool(apply_scale)), ptr(out)), "b4d_flat_field")
     return out
+
+
+def bad_pixel_repair(frames, flat, dark, *, eps: float):
+    """In place: frames[:, bad] = 3x3 median (reflect border) of the flat-field-corrected frames (b4d_bad_pixel_repair)."""
+    T, ny, nx = frames.shape
+    ctx = get_context(_dev(frames))
+    ctx.check(ctx.lib.b4d_bad_pixel_repair(ctx.handle, ptr(frames), T, ny, nx, ptr(flat), ptr(dark), float(eps)),
+              "b4d_bad_pixel_repair")
+    return frames
 
 
 def sub(a, b):

@@ -64,8 +64,6 @@ def flat_field_correction(images, *, flats=None, darks=None, scale: str = "flat_
     images = np.asarray(images)
     if images.ndim not in (2, 3):
         raise ValueError("images must be 2D or 3D")
-    if bad_pixel_removal:
-        raise B4DUnsupported("flat_field_correction(bad_pixel_removal=True) (3x3 median repair) is not built on the B200 path")
     img = images.astype(np.float32, copy=False)
     if flats is None and darks is None:
         return img.copy()
@@ -80,5 +78,7 @@ def flat_field_correction(images, *, flats=None, darks=None, scale: str = "flat_
     else:
         eps_v, s, apply_scale = resolve_flat_field(flat, dark, scale=scale, eps=eps)
         out = engine.flat_field(dev_img, flat, dark, eps=eps_v, scale_value=s, apply_scale=apply_scale)
+        if bad_pixel_removal:
+            engine.bad_pixel_repair(out, flat, dark, eps=eps_v)
     res = out.cpu().numpy()
     return res[0] if images.ndim == 2 else res

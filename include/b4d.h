@@ -145,6 +145,12 @@ int b4d_select_ranks(b4d_ctx* ctx, const float* stack, int64_t n_frames, int64_t
 int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frames, int ny, int nx,
                    const float* flat, const float* dark, float eps, float scale_value,
                    int apply_scale, float* out);
+/*
+ * bad_pixel_removal=True (preprocessing/normalize.py:134-140): frames[:, bad] = median_filter(frames, 3x3)[:, bad] with
+ * scipy's 'reflect' border, in place on the output of b4d_flat_field (bad pixels are 0 there); same flat / dark / eps.
+ */
+int b4d_bad_pixel_repair(b4d_ctx* ctx, float* frames, int64_t n_frames, int ny, int nx,
+                         const float* flat, const float* dark, float eps);
 /* gain[p] = bad ? 0 : scale/(flat-dark): the per-pixel multiplier the fused loaders use. */
 int b4d_flat_gain(b4d_ctx* ctx, const float* flat, const float* dark, int ny, int nx,
                   float eps, float scale_value, float* gain);

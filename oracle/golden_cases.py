@@ -92,6 +92,16 @@ def flatfield_inputs():
     return synth.flatfield_case(4, 128, seed=31, dead_frac=2e-3)
 
 
+def flatfield_repair_inputs():
+    """3 frames of 96 x 80 with 1 % dead pixels, some of them adjacent to one another and on the borders / corners
+    (the median filter's 'reflect' border and the "bad neighbours count as 0" rule both get exercised)."""
+    raw, flat, dark = synth.flatfield_case(3, 96, seed=33, dead_frac=1e-2)
+    raw, flat, dark = raw[:, :, :80].copy(), flat[:, :80].copy(), dark[:, :80].copy()
+    for (y, x) in ((0, 0), (0, 1), (1, 0), (95, 79), (95, 40), (50, 0), (50, 1), (51, 1), (20, 79), (60, 30), (60, 31), (61, 30)):
+        flat[y, x] = dark[y, x]                       # den = 0 -> bad
+    return raw, flat, dark
+
+
 def temporal_inputs():
     raw, flat, dark = synth.flatfield_case(24, 64, seed=41, dead_frac=2e-3)
     return raw, flat, dark

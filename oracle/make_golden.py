@@ -44,6 +44,17 @@ def map_digest(a, prefix, store):
     store[prefix + "_sumabs2"] = np.asarray((np.abs(a) ** 2).sum())
 
 
+def repair_golden(pre, versions):
+    """flatfield_repair.npz: flat_field_correction(bad_pixel_removal=True) of the reference (3x3 median repair)."""
+    raw, flat, dark = gc.flatfield_repair_inputs()
+    store = {"versions": versions}
+    out = pre.flat_field_correction(raw, flats=flat, darks=dark, bad_pixel_removal=True)
+    store["stack"] = out
+    store["single"] = pre.flat_field_correction(raw[1], flats=flat, darks=dark, scale="none", bad_pixel_removal=True)
+    np.savez_compressed(os.path.join(OUT, "flatfield_repair.npz"), **store)
+    print("flatfield_repair.npz", os.path.getsize(os.path.join(OUT, "flatfield_repair.npz")) // 1024, "KiB")
+
+
 def tiles_golden(met, versions):
     """tiles.npz: the reference's tiling executor on the frames of golden_cases.tile_cases()."""
     store = {"versions": versions}
@@ -74,6 +85,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     import scipy
     versions = np.array([np.__version__, scipy.__version__])
+    if "--only-repair" in sys.argv:
+        repair_golden(pre, versions)
+        return
     if "--only-tiles" in sys.argv:
         tiles_golden(met, versions)
         print("tiles.npz", os.path.getsize(os.path.join(OUT, "tiles.npz")) // 1024, "KiB")
@@ -197,6 +211,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "flatfield.npz"), **store)
 
     tiles_golden(met, versions)
+    repair_golden(pre, versions)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

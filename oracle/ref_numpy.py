@@ -547,7 +547,7 @@ def spectral_entropy(image, eps=1e-30):
 # preprocessing.normalize
 # --------------------------------------------------------------------------------------
 
-def flat_field_correction(images, flats=None, darks=None, scale="flat_median", eps=None):
+def flat_field_correction(images, flats=None, darks=None, scale="flat_median", eps=None, bad_pixel_removal=False):
     """(I - D) / (F - D) * s in float32 with a bad-pixel mask (no median repair).  ref: preprocessing/normalize.py:12-145."""
     if scale not in {"none", "flat_mean", "flat_median"}:
         raise ValueError(f"Invalid scale option: {scale}")
@@ -583,6 +583,10 @@ def flat_field_correction(images, flats=None, darks=None, scale="flat_median", e
     if scale != "none":
         out *= np.mean(den[~bad]) if scale == "flat_mean" else np.median(den[~bad])
     out[..., bad] = 0.0
+    if bad_pixel_removal:
+        # ref: preprocessing/normalize.py:134-140 -- 3x3 median (scipy default 'reflect') of the frame with zeroed bad pixels
+        rep = ndimage.median_filter(out, size=(1, 3, 3) if out.ndim == 3 else (3, 3))
+        out[..., bad] = rep[..., bad]
     return out.astype(np.float32, copy=False)
 
 

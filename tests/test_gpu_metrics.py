@@ -222,3 +222,14 @@ def test_stack_tiles_vs_golden(dip, golden):
     for grp, fields in one["tiles"].items():
         for k, v in fields.items():
             np.testing.assert_allclose(v["mean"], shs["tiles"][grp][k]["mean"][1], rtol=1e-12)
+
+
+def test_bad_pixel_repair_bit_exact(dip, golden):
+    """flat_field_correction(bad_pixel_removal=True): bad pixels replaced by the 3x3 median (reflect border) of the frame in
+    which bad pixels are zero -- bit-identical to the reference, clusters of bad pixels and borders included."""
+    g = golden("flatfield_repair")
+    raw, flat, dark = gc.flatfield_repair_inputs()
+    ffc = dip.preprocessing.flat_field_correction
+    np.testing.assert_array_equal(ffc(raw, flats=flat, darks=dark, bad_pixel_removal=True), g["stack"])
+    np.testing.assert_array_equal(ffc(raw[1], flats=flat, darks=dark, scale="none", bad_pixel_removal=True), g["single"])
+    assert np.count_nonzero(g["stack"] != ffc(raw, flats=flat, darks=dark)) > 0      # the repair does change pixels

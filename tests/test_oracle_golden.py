@@ -202,3 +202,10 @@ def test_tiling_executor_matches_reference(golden):
                                                err_msg=f"{name} {tag} {grp}.{k} mean")
                     np.testing.assert_allclose(v["std"], g[f"{name}/{tag}/{grp}/{k}/std"], rtol=1e-7, atol=1e-12,
                                                err_msg=f"{name} {tag} {grp}.{k} std")
+
+
+def test_bad_pixel_repair_matches_reference(golden):
+    g = golden("flatfield_repair")
+    raw, flat, dark = gc.flatfield_repair_inputs()
+    np.testing.assert_array_equal(orc.flat_field_correction(raw, flat, dark, bad_pixel_removal=True), g["stack"])
+    np.testing.assert_array_equal(orc.flat_field_correction(raw[1], flat, dark, scale="none", bad_pixel_removal=True), g["single"])
