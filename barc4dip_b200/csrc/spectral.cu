@@ -1399,6 +1399,122 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// template matching (normalised cross-correlation, signal/tracking.py:82-188 -> cv2.TM_CCOEFF_NORMED)
+// -------------------------------------------------------------------------------------------------
+// result(y, x) = sum_ij T'(i,j) I(y+i, x+j) / sqrt(sum T'^2 * sum_window (I - mean_window)^2),  (ny-h+1, nx-w+1) values.
+// Numerator: circular correlation with the zero-mean template embedded at the origin (no wrap-around inside the valid
+// range), through the FFT kernels above. Window sums: double-precision integral images of (I - K) and (I - K)^2, K the
+// frame's pilot mean (the quotient does not depend on K), as cv2 takes them from integral(CV_64F).
+
+// inclusive scans along x: one warp per row, P1 = sum v, P2 = sum v^2 (v = frame - K)
+__global__ void __launch_bounds__(256) tm_scan_rows_kernel(const float* __restrict__ stack, const float* __restrict__ pilot, int ny, int nx,
+                                                           double* __restrict__ P1, double* __restrict__ P2, int64_t rows) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float K = pilot[row / ny];
+    const float* src = stack + row * nx;
+    double* d1 = P1 + row * nx;
+    double* d2 = P2 + row * nx;
+    const int per = (nx + 31) / 32, x0 = lane * per, x1 = min(x0 + per, nx);
+    double s1 = 0.0, s2 = 0.0;
+    for (int x = x0; x < x1; ++x) { const double v = (double)(src[x] - K); s1 += v; s2 += v * v; }
+    double o1 = s1, o2 = s2;                          // exclusive prefix over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double a = __shfl_up_sync(0xffffffffu, o1, o), b = __shfl_up_sync(0xffffffffu, o2, o);
+        if (lane >= o) { o1 += a; o2 += b; }
+    }
+    o1 -= s1; o2 -= s2;
+    for (int x = x0; x < x1; ++x) {
+        const double v = (double)(src[x] - K);
+        o1 += v; o2 += v * v;
+        d1[x] = o1; d2[x] = o2;
+    }
+}
+
+// in-place inclusive scans along y: one thread per column
+__global__ void __launch_bounds__(256) tm_scan_cols_kernel(double* __restrict__ P1, double* __restrict__ P2, int ny, int nx) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = blockIdx.y;
+    if (x >= nx) return;
+    double* p1 = P1 + (size_t)t * ny * nx + x;
+    double* p2 = P2 + (size_t)t * ny * nx + x;
+    double a = 0.0, b = 0.0;
+    for (int y = 0; y < ny; ++y) {
+        a += p1[(size_t)y * nx]; b += p2[(size_t)y * nx];
+        p1[(size_t)y * nx] = a; p2[(size_t)y * nx] = b;
+    }
+}
+
+// compact result map (T, oy, ox) from the shifted correlation map and the integral images (cv2's common_matchTemplate)
+__global__ void __launch_bounds__(256) tm_normalise_kernel(const float* __restrict__ corr, const double* __restrict__ P1,
+                                                           const double* __restrict__ P2, int ny, int nx, int h, int w,
+                                                           const double* __restrict__ tfr, double eps, float* __restrict__ out) {
+    const int64_t t = blockIdx.y;
+    const int oy = ny - h + 1, ox = nx - w + 1;
+    const double area = (double)h * (double)w;
+    // tpl_z = (tpl - mean) / (std + eps): its own standard deviation, and cv2's templNorm = sdv * sqrt(area)
+    const double sd = sqrt(tfr[B4D_FR_M2]);
+    const double tnorm = (sd / (sd + eps)) * sqrt(area);
+    const float* c = corr + (size_t)t * ny * nx;
+    const double* p1 = P1 + (size_t)t * ny * nx;
+    const double* p2 = P2 + (size_t)t * ny * nx;
+    auto box = [&](const double* p, int y, int xq) {
+        const int ya = y - 1, yb = y + h - 1, xa = xq - 1, xb = xq + w - 1;
+        double s = p[(size_t)yb * nx + xb];
+        if (ya >= 0) s -= p[(size_t)ya * nx + xb];
+        if (xa >= 0) s -= p[(size_t)yb * nx + xa];
+        if (ya >= 0 && xa >= 0) s += p[(size_t)ya * nx + xa];
+        return s;
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)oy * ox; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / ox), xq = (int)(i % ox);
+        double num = (double)c[(size_t)((y + ny / 2) & (ny - 1)) * nx + ((xq + nx / 2) & (nx - 1))];
+        const double s1 = box(p1, y, xq), s2 = box(p2, y, xq);
+        const double diff2 = fmax(s2 - s1 * s1 / area, 0.0);
+        const double tt = diff2 <= 1.1920929e-6 * s2 ? 0.0 : sqrt(diff2) * tnorm;      // flat window: avoid rounding noise
+        if (fabs(num) < tt) num /= tt;
+        else if (fabs(num) < tt * 1.125) num = num > 0 ? 1.0 : -1.0;
+        else num = 0.0;
+        out[(size_t)t * oy * ox + i] = (float)num;
+    }
+}
+
+// (dy, dx, peak, snr) from the compact result map (signal/tracking.py:170-188): argmax, float32 3x3 Taylor step with the
+// reference's swapped terms, match position = peak + (h-1)/2 against the template's reference centre
+__global__ void tm_finalize_kernel(const float* __restrict__ res, const unsigned* __restrict__ peak_idx, int oy, int ox, int h, int w,
+                                   double ref_y, double ref_x, const float* __restrict__ med2, const long long* __restrict__ nvalid,
+                                   int subpixel, double eps, double* __restrict__ out, int64_t T) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* c = res + (size_t)t * oy * ox;
+    const int i = (int)(peak_idx[t] / (unsigned)ox), j = (int)(peak_idx[t] % (unsigned)ox);
+    const float pk = c[(size_t)i * ox + j];
+    double py = (double)i, px = (double)j;
+    if (subpixel && i > 0 && i < oy - 1 && j > 0 && j < ox - 1) {
+        auto C = [&](int a, int b) { return c[(size_t)a * ox + b]; };
+        const float gy = __fdiv_rn(__fsub_rn(C(i + 1, j), C(i - 1, j)), 2.f);
+        const float gyy = __fsub_rn(__fadd_rn(C(i + 1, j), C(i - 1, j)), __fmul_rn(2.f, C(i, j)));
+        const float gx = __fdiv_rn(__fsub_rn(C(i, j + 1), C(i, j - 1)), 2.f);
+        const float gxx = __fsub_rn(__fadd_rn(C(i, j + 1), C(i, j - 1)), __fmul_rn(2.f, C(i, j)));
+        const float gxy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(C(i + 1, j + 1), C(i + 1, j - 1)), C(i - 1, j + 1)), C(i - 1, j - 1)), 4.f);
+        const float det = __fsub_rn(__fmul_rn(gxx, gyy), __fmul_rn(gxy, gxy));
+        if (det != 0.f) {
+            const float inv = __fdiv_rn(1.f, det);
+            py += (double)__fmul_rn(-__fsub_rn(__fmul_rn(gyy, gx), __fmul_rn(gxy, gy)), inv);
+            px += (double)__fmul_rn(-__fsub_rn(__fmul_rn(gxx, gy), __fmul_rn(gxy, gx)), inv);
+        }
+    }
+    const float med = (nvalid[t] & 1) ? med2[2 * t] : __fmul_rn(__fadd_rn(med2[2 * t], med2[2 * t + 1]), 0.5f);
+    double* o = out + t * 4;
+    o[0] = py + (double)(h - 1) / 2.0 - ref_y;
+    o[1] = px + (double)(w - 1) / 2.0 - ref_x;
+    o[2] = (double)pk;
+    o[3] = fabs((double)pk) / ((double)med + eps);
+}
+
+// -------------------------------------------------------------------------------------------------
 // arbitrary frame sides (Bluestein), see generic_dft.cuh
 // -------------------------------------------------------------------------------------------------
 #include "generic_dft.cuh"
@@ -2037,6 +2153,88 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         if (want_pc && !ns) {
             if ((rc = track_finish(ctx, w, mag, tc, ny, nx, nblk, subpixel, eps, track_out + t0 * 4))) return rc;
         }
+    }
+    return B4D_OK;
+}
+
+extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int h, int w, const float* stack, int64_t n_frames, int ny, int nx,
+                                  double ref_y, double ref_x, int subpixel, double eps, double* out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    int rc = check_fft_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
+    if (rc) return rc;
+    if (!tpl || !out || h < 1 || w < 1 || h > ny || w > nx)
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_template_match: template shape (%d, %d) must fit inside image shape (%d, %d)", h, w, ny, nx);
+    const size_t npix = (size_t)ny * nx, half = (size_t)ny * (nx / 2);
+    const int oy = ny - h + 1, ox = nx - w + 1;
+    const size_t nres = (size_t)oy * ox;
+    // batch: correlation map + result map (float) and two integral images (double) per frame, at most ~1.5 GB
+    int64_t B = ((int64_t)1536 << 20) / (int64_t)(npix * 24);
+    if (B < 1) B = 1;
+    const int64_t Bfft = batch_frames(ctx, ny, nx, 2);
+    if (B > Bfft) B = Bfft;
+    if (B > n_frames) B = n_frames;
+    // template: z-scored over the ROI (tracking.py:151, :308-311), embedded at the origin, conjugate spectrum
+    void* p = nullptr;
+    if ((rc = b4d_scratch(ctx, SCR_NYQ, sizeof(float2) * (half + ny) + sizeof(double) * B4D_FR_NCOLS + 256, &p))) return rc;
+    float2* tref = static_cast<float2*>(p);
+    float2* tref_nyq = tref + half;
+    double* tfr = reinterpret_cast<double*>(tref_nyq + ny);
+    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (npix + nres) * B + sizeof(double) * 2 * npix * B + 256, &p))) return rc;
+    float* corr = static_cast<float*>(p);
+    float* res = corr + npix * B;
+    double* P1 = reinterpret_cast<double*>(res + ((nres * B + 1) & ~size_t(1)));
+    double* P2 = P1 + npix * B;
+    if ((rc = b4d_frame_reductions_nolock(ctx, tpl, 1, h, w, nullptr, nullptr, nan(""), 0.0, tfr))) return rc;
+    embed_template_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(tpl, h, w, ny, nx, 0, 0, (float)eps, tfr, corr);
+    B4D_LAUNCH_CHECK(ctx);
+    {
+        Work wk;
+        if ((rc = carve(ctx, 1, ny, nx, false, false, &wk))) return rc;
+        if ((rc = run_rows_fwd(ctx, corr, 1, ny, nx, nullptr, nullptr, wk, false))) return rc;
+        ColsArgs c = cols_defaults(wk, nx, false);
+        c.conj_out = tref;
+        c.conj_nyq_out = tref_nyq;
+        if ((rc = run_cols(ctx, c, 1, ny))) return rc;
+    }
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + t0 * npix;
+        Work w_;
+        if ((rc = carve(ctx, tc, ny, nx, true, false, &w_))) return rc;
+        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w_, true))) return rc;      // frames - pilot
+        ColsArgs c = cols_defaults(w_, nx, false);                                                  // (no DC add-back)
+        c.i2_pc = w_.I2a;
+        c.R = tref; c.Rnyq = tref_nyq; c.r_stride = 0; c.rnyq_stride = 0; c.whiten = 0; c.eps = 0.f;
+        if ((rc = run_cols(ctx, c, tc, ny))) return rc;
+        RowsInvArgs r;
+        memset(&r, 0, sizeof(r));
+        r.Ia = w_.I2a; r.ny = ny; r.outA = corr; r.kindA = 0; r.scaleA = 1.0 / ((double)nx * (double)ny);
+        if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+        {
+            ProfScope ps(ctx, KC_SMALL);
+            const int64_t rows = tc * ny;
+            tm_scan_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(s0, w_.pilot, ny, nx, P1, P2, rows);
+            B4D_LAUNCH_CHECK(ctx);
+            tm_scan_cols_kernel<<<dim3((nx + 255) / 256, (unsigned)tc), 256, 0, ctx->stream>>>(P1, P2, ny, nx);
+            B4D_LAUNCH_CHECK(ctx);
+            int bx = (int)((nres + 2047) / 2048);
+            if (bx > 592) bx = 592;
+            tm_normalise_kernel<<<dim3(bx, (unsigned)tc), 256, 0, ctx->stream>>>(corr, P1, P2, ny, nx, h, w, tfr, eps, res);
+            B4D_LAUNCH_CHECK(ctx);
+            gen_argmax_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(res, (int64_t)nres, w_.pk_idx);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        void* q = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MISC, 1024, &q))) return rc;    // sized by carve(); first 512 B hold the quantile
+        static const double half_q = 0.5;
+        if ((rc = b4d_put_doubles(ctx, static_cast<double*>(q), &half_q, 1))) return rc;
+        if ((rc = b4d_select_impl(ctx, res, tc, (int64_t)nres, static_cast<const double*>(q), 1, 1, w_.med,
+                                  reinterpret_cast<int64_t*>(w_.nvalid))))
+            return rc;
+        tm_finalize_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(res, w_.pk_idx, oy, ox, h, w, ref_y, ref_x, w_.med,
+                                                                               w_.nvalid, subpixel, eps, out + t0 * 4, tc);
+        B4D_LAUNCH_CHECK(ctx);
     }
     return B4D_OK;
 }

@@ -20,7 +20,7 @@ from ._lib import FR, FR_NCOLS, SP, SP_NCOLS, get_context, ptr, require_cuda
 __all__ = [
     "as_stack", "frame_reductions", "select_quantiles", "flat_field", "flat_gain",
     "temporal_moments", "TemporalAccumulator", "fft2d", "psd2d", "autocorr2d", "xcorr2d",
-    "PhaseTracker", "stack_pipeline", "check_fft_shape", "bad_pixel_repair",
+    "PhaseTracker", "stack_pipeline", "check_fft_shape", "bad_pixel_repair", "template_match",
 ]
 
 
@@ -289,6 +289,24 @@ class PhaseTracker:
                                           ptr(out)), "b4d_phase_track")
         resolve_tracking(stack, out, subpixel=subpixel, eps=self.eps)
         return out if return_device else out.cpu().numpy()
+
+
+def template_match(template, stack, *, ref_center_yx, subpixel: bool = True, eps: float = 1e-9, return_device: bool = False):
+    """Normalised cross-correlation matching of one (h, w) template against every frame of a (T, ny, nx) stack
+    (b4d_template_match). ref_center_yx: centre of the template's reference position. -> (T, 4) = dy, dx, peak, snr."""
+    torch = require_cuda()
+    T, ny, nx = stack.shape
+    check_fft_shape(ny, nx)
+    tpl = as_stack(template, _dev(stack))[0].contiguous()
+    h, w = (int(v) for v in tpl.shape)
+    if h > ny or w > nx:
+        raise ValueError(f"template shape {(h, w)} must fit inside image shape {(ny, nx)}")
+    ctx = get_context(_dev(stack))
+    out = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
+    ctx.check(ctx.lib.b4d_template_match(ctx.handle, ptr(tpl), h, w, ptr(stack), T, ny, nx, float(ref_center_yx[0]),
+                                         float(ref_center_yx[1]), int(bool(subpixel)), float(eps), ptr(out)),
+              "b4d_template_match")
+    return out if return_device else out.cpu().numpy()
 
 
 def resolve_tracking(stack, track, *, subpixel: bool = True, eps: float = 1e-9, gain=None, dark=None, flat_field_fn=None):

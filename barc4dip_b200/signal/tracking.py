@@ -81,6 +81,24 @@ def phase_correlation(template, image, *, slices_yx=None, backend: str = "intern
 @_register("template")
 def template_matching(template, image, *, slices_yx=None, backend: str = "opencv", subpixel: bool = True,
                       eps: float = 1e-9):
-    from .._lib import B4DUnsupported
-    raise B4DUnsupported("template_matching (cv2 / skimage matchTemplate, signal/tracking.py:82-188) is not built on "
-                         "the B200 path (SURVEY.md 8(f) rank 3); use method='phase', backend='internal'.")
+    """(dy, dx, peak, snr) by normalised cross-correlation of the z-scored template against the image.
+
+    Both of the reference's backends evaluate the same quantity -- cv2.matchTemplate(TM_CCOEFF_NORMED) and
+    skimage.feature.match_template(pad_input=False) -- and the B200 path computes it once for either name (FFT
+    correlation + double-precision window sums, csrc/spectral.cu); parity is pinned against the opencv backend, the
+    only one runnable where the goldens were recorded."""
+    tpl = _as_float2d(template, name="template")
+    img = _as_float2d(image, name="image")
+    H, W = img.shape
+    h, w = tpl.shape
+    if h > H or w > W:
+        raise ValueError(f"template shape {(h, w)} must fit inside image shape {(H, W)}")
+    if backend not in ("opencv", "skimage"):
+        raise ValueError("backend must be 'opencv' or 'skimage'.")
+    if slices_yx is None:
+        slices_yx = centered_slices((H, W), (h, w))
+    sy, sx = slices_yx
+    y0 = (sy.start + sy.stop - 1) / 2.0
+    x0 = (sx.start + sx.stop - 1) / 2.0
+    dy, dx, peak, snr = engine.template_match(tpl, engine.as_stack(img), ref_center_yx=(y0, x0), subpixel=subpixel, eps=eps)[0]
+    return float(dy), float(dx), float(peak), float(snr)

@@ -115,3 +115,28 @@ def tile_cases() -> dict[str, np.ndarray]:
 
 
 SHARPNESS_TILE_GROUPS = ("stats", "gradient", "laplacian", "spectral", "autocorrelation")
+
+
+def template_cases() -> dict[str, dict]:
+    """(template, image, slices) triples for template_matching (signal/tracking.py:82-188, opencv backend)."""
+    n = 256
+    base = synth.speckle_frame(n, grain=4.0, seed=61)
+    rng = np.random.default_rng(62)
+    noise = lambda: (0.02 * float(base.mean()) * rng.standard_normal((n, n))).astype(np.float32)
+    cases = {}
+    sl = (slice(100, 125), slice(140, 165))                      # 25 x 25 ROI
+    cases["roll_25"] = dict(template=base[sl].copy(), image=np.roll(base, (3, -5), axis=(0, 1)) + noise(), slices=sl, subpixel=True)
+    sub = synth.fourier_shift(base, 1.37, -2.62) if hasattr(synth, "fourier_shift") else None
+    if sub is None:
+        F = np.fft.fft2(base.astype(np.float64))
+        ky = np.fft.fftfreq(n)[:, None]; kx = np.fft.fftfreq(n)[None, :]
+        sub = np.real(np.fft.ifft2(F * np.exp(-2j * np.pi * (ky * 1.37 + kx * -2.62)))).astype(np.float32)
+    cases["subpx_25"] = dict(template=base[sl].copy(), image=sub + noise(), slices=sl, subpixel=True)
+    cases["subpx_25_nosub"] = dict(template=base[sl].copy(), image=sub + noise(), slices=sl, subpixel=False)
+    sl2 = (slice(60, 161), slice(30, 105))                       # 101 x 75 ROI
+    cases["rect_101x75"] = dict(template=base[sl2].copy(), image=np.roll(base, (-7, 4), axis=(0, 1)) + noise(), slices=sl2, subpixel=True)
+    cases["centered_31"] = dict(template=base[112:143, 112:143].copy(), image=np.roll(base, (2, 2), axis=(0, 1)) + noise(),
+                                slices=None, subpixel=True)
+    u16 = np.clip(base * 20.0, 0, 65535).astype(np.uint16)
+    cases["u16_25"] = dict(template=u16[sl].copy(), image=np.roll(u16, (1, 6), axis=(0, 1)), slices=sl, subpixel=True)
+    return cases

@@ -44,6 +44,24 @@ def map_digest(a, prefix, store):
     store[prefix + "_sumabs2"] = np.asarray((np.abs(a) ** 2).sum())
 
 
+def template_golden(sig, versions):
+    """template.npz: template_matching(backend="opencv") of the reference (cv2.matchTemplate TM_CCOEFF_NORMED)."""
+    import cv2
+    store = {"versions": versions, "cv2": np.array(cv2.__version__)}
+    for name, c in gc.template_cases().items():
+        res = sig.template_matching(c["template"], c["image"], slices_yx=c["slices"], backend="opencv", subpixel=c["subpixel"])
+        store[f"{name}/result"] = np.asarray(res, dtype=np.float64)
+        res2 = sig.track_translation(c["template"], c["image"], slices_yx=c["slices"], method="template", backend="opencv",
+                                     subpixel=c["subpixel"])
+        assert tuple(res2) == tuple(res)
+    c = gc.template_cases()["roll_25"]
+    tz = sig.tracking._zscore2d(c["template"].astype(np.float32), eps=1e-9).astype(np.float32)
+    iz = sig.tracking._zscore2d(c["image"].astype(np.float32), eps=1e-9).astype(np.float32)
+    store["roll_25/map"] = cv2.matchTemplate(iz, tz, method=cv2.TM_CCOEFF_NORMED)
+    np.savez_compressed(os.path.join(OUT, "template.npz"), **store)
+    print("template.npz", os.path.getsize(os.path.join(OUT, "template.npz")) // 1024, "KiB")
+
+
 def repair_golden(pre, versions):
     """flatfield_repair.npz: flat_field_correction(bad_pixel_removal=True) of the reference (3x3 median repair)."""
     raw, flat, dark = gc.flatfield_repair_inputs()
@@ -85,6 +103,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     import scipy
     versions = np.array([np.__version__, scipy.__version__])
+    if "--only-template" in sys.argv:
+        template_golden(sig, versions)
+        return
     if "--only-repair" in sys.argv:
         repair_golden(pre, versions)
         return
@@ -212,6 +233,7 @@ def main():
 
     tiles_golden(met, versions)
     repair_golden(pre, versions)
+    template_golden(sig, versions)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -686,3 +686,59 @@ def sharpness_tiles(image, display_origin="lower", saturation_value=65535.0, eps
         "spectral": tiled_scalar_fields(img, mode, lambda t: {"spectral_entropy": spectral_entropy(t)}),
         "autocorrelation": tiled_scalar_fields(img, mode, lambda t: scal(inverse_autocorr_width(t), ("sx", "sy", "seq", "r"))),
     }
+
+
+# --------------------------------------------------------------------------------------
+# signal.tracking.template_matching (opencv backend: cv2.matchTemplate TM_CCOEFF_NORMED)
+# --------------------------------------------------------------------------------------
+
+def ncc_valid(img, tpl):
+    """cv2.matchTemplate(img, tpl, TM_CCOEFF_NORMED), restated: result (H-h+1, W-w+1) float32.
+
+    OpenCV (modules/imgproc/src/templmatch.cpp, common_matchTemplate; opencv-python is an unpinned dependency of the
+    reference, 4.13.0 where the goldens were recorded): numerator = cross-correlation - window_sum * mean(tpl);
+    denominator = sqrt(max(window_sqsum - window_sum^2 / area, 0)) * std(tpl) * sqrt(area), window sums from
+    double-precision integral images; |num| < den -> num / den, |num| < 1.125 den -> +-1, else 0."""
+    I = np.asarray(img, dtype=np.float64)
+    T = np.asarray(tpl, dtype=np.float64)
+    H, W = I.shape
+    h, w = T.shape
+    area = float(h * w)
+    Tz = T - T.mean()
+    fi = np.fft.rfft2(I)
+    ft = np.fft.rfft2(Tz, s=(H, W))
+    num = np.fft.irfft2(fi * np.conj(ft), s=(H, W))[:H - h + 1, :W - w + 1]
+    def box(a):
+        P = np.zeros((H + 1, W + 1))
+        P[1:, 1:] = a.cumsum(0).cumsum(1)
+        return P[h:, w:] - P[:-h, w:] - P[h:, :-w] + P[:-h, :-w]
+    s1, s2 = box(I), box(I * I)
+    diff2 = np.maximum(s2 - s1 * s1 / area, 0.0)
+    t = np.where(diff2 <= np.minimum(0.5, 10 * np.finfo(np.float32).eps * s2), 0.0, np.sqrt(diff2) * T.std() * math.sqrt(area))
+    out = np.where(np.abs(num) < t, num / np.where(t > 0, t, 1.0), np.where(np.abs(num) < 1.125 * t, np.sign(num), 0.0))
+    return out.astype(np.float32)
+
+
+def template_matching(template, image, slices_yx=None, subpixel=True, eps=1e-9):
+    """ref: signal/tracking.py:82-188 (backend="opencv")."""
+    tpl, img = _float2d(template, "template"), _float2d(image, "image")
+    H, W = img.shape
+    h, w = tpl.shape
+    if h > H or w > W:
+        raise ValueError(f"template shape {(h, w)} must fit inside image shape {(H, W)}")
+    if slices_yx is None:
+        slices_yx = centered_roi_slices((H, W), (h, w))
+    sy, sx = slices_yx
+    y0, x0 = (sy.start + sy.stop - 1) / 2.0, (sx.start + sx.stop - 1) / 2.0
+    tz = zscore2d(tpl, eps).astype(np.float32)
+    iz = zscore2d(img, eps).astype(np.float32)
+    corr = ncc_valid(iz, tz)
+    i, j = np.unravel_index(int(np.argmax(corr)), corr.shape)
+    peak = float(corr[i, j])
+    snr = float(abs(peak) / (float(np.median(np.abs(corr))) + eps))
+    py, px = float(i), float(j)
+    if subpixel:
+        di, dj = peak_subpixel_taylor(corr, i, j)
+        py += float(di)
+        px += float(dj)
+    return float(py + (h - 1) / 2.0 - y0), float(px + (w - 1) / 2.0 - x0), peak, snr

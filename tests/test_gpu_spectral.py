@@ -145,8 +145,8 @@ def test_tracking_quirks_and_errors(sig):
         sig.phase_correlation(a, a, slices_yx=None)           # even template without slices (quirk 7)
     with pytest.raises(ValueError):
         sig.track_translation(a, a, method="nope")
-    with pytest.raises(B4DUnsupported):
-        sig.track_translation(a, a, method="template")
+    with pytest.raises(ValueError):
+        sig.track_translation(a[:5, :5], a, method="template", backend="nope")
     with pytest.raises(ValueError):
         sig.phase_correlation(a[:5, :5], a, slices_yx=(slice(0, 6), slice(0, 5)))
 
@@ -296,3 +296,38 @@ def test_arbitrary_sides_metrics_vs_oracle():
             if np.ndim(v) == 0:
                 np.testing.assert_allclose(got[k], v, rtol=1e-4, err_msg=f"{name}.{k}")
     np.testing.assert_allclose(metrics.sharpness.spectral_entropy(tile), orc.spectral_entropy(tile), rtol=1e-4)
+
+
+def test_template_matching_vs_golden(sig, golden):
+    """template_matching / track_translation(method="template") against the reference's opencv backend (cv2
+    TM_CCOEFF_NORMED): displacements within 0.01 px (north_star), peak 1e-4, snr 1e-3; either backend name is served."""
+    g = golden("template")
+    for name, c in gc.template_cases().items():
+        want = g[f"{name}/result"]
+        got = sig.template_matching(c["template"], c["image"], slices_yx=c["slices"], backend="opencv", subpixel=c["subpixel"])
+        np.testing.assert_allclose(got[:2], want[:2], rtol=0, atol=0.01, err_msg=name)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-4, err_msg=name + " peak")
+        np.testing.assert_allclose(got[3], want[3], rtol=1e-3, err_msg=name + " snr")
+        got2 = sig.track_translation(c["template"], c["image"], slices_yx=c["slices"], method="template", backend="skimage",
+                                     subpixel=c["subpixel"])
+        assert got2 == got
+    with pytest.raises(ValueError):
+        sig.template_matching(np.zeros((300, 10), np.float32), np.zeros((256, 256), np.float32))
+
+
+def test_template_matching_stack_2048():
+    """Whole-stack call at the benchmark frame size: integer rolls are recovered, oracle agreement on one frame."""
+    from barc4dip_b200 import engine, synth
+    n = 2048
+    base = synth.speckle_frame(n, grain=6.0, seed=0)
+    rng = np.random.default_rng(5)
+    shifts = [(0, 0), (3, -2), (-11, 7)]
+    stack = np.stack([np.roll(base, s, axis=(0, 1)) + (10.0 * rng.standard_normal((n, n))).astype(np.float32) for s in shifts])
+    sl = (slice(1000, 1023), slice(900, 923))
+    tab = engine.template_match(base[sl], engine.as_stack(stack), ref_center_yx=((1000 + 1022) / 2.0, (900 + 922) / 2.0))
+    for t, s in enumerate(shifts):
+        np.testing.assert_allclose(tab[t, :2], s, atol=0.1)
+    want = orc.template_matching(base[sl], stack[2], slices_yx=sl)
+    np.testing.assert_allclose(tab[2, :2], want[:2], atol=0.01)
+    np.testing.assert_allclose(tab[2, 2], want[2], rtol=1e-4)
+    np.testing.assert_allclose(tab[2, 3], want[3], rtol=2e-3)

@@ -209,3 +209,19 @@ def test_bad_pixel_repair_matches_reference(golden):
     raw, flat, dark = gc.flatfield_repair_inputs()
     np.testing.assert_array_equal(orc.flat_field_correction(raw, flat, dark, bad_pixel_removal=True), g["stack"])
     np.testing.assert_array_equal(orc.flat_field_correction(raw[1], flat, dark, scale="none", bad_pixel_removal=True), g["single"])
+
+
+def test_template_matching_matches_reference(golden):
+    """Oracle NCC (float64 restatement of cv2's TM_CCOEFF_NORMED) against the reference's template_matching(opencv): cv2
+    evaluates the map in float32, so the map agrees to ~1e-6 and the 3x3 Taylor step to ~1e-3 px."""
+    g = golden("template")
+    c = gc.template_cases()["roll_25"]
+    tz = orc.zscore2d(c["template"].astype(np.float32), 1e-9).astype(np.float32)
+    iz = orc.zscore2d(c["image"].astype(np.float32), 1e-9).astype(np.float32)
+    np.testing.assert_allclose(orc.ncc_valid(iz, tz), g["roll_25/map"], rtol=0, atol=5e-6)
+    for name, c in gc.template_cases().items():
+        got = orc.template_matching(c["template"], c["image"], slices_yx=c["slices"], subpixel=c["subpixel"])
+        want = g[f"{name}/result"]
+        np.testing.assert_allclose(got[:2], want[:2], rtol=0, atol=5e-3, err_msg=name)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-5, err_msg=name + " peak")
+        np.testing.assert_allclose(got[3], want[3], rtol=1e-4, err_msg=name + " snr")
