@@ -71,7 +71,7 @@ _SIGNATURES = {
     "b4d_psd2d": [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp, _vp],
     "b4d_autocorr2d": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _f64, _vp],
     "b4d_xcorr2d": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],
-    "b4d_template_match": [_vp, _vp, _i32, _i32, _vp, _i64, _i32, _i32, _f64, _f64, _i32, _f64, _vp],
+    "b4d_template_match": [_vp, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _f64, _f64, _i32, _f64, _vp],
     "b4d_phase_set_reference": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64],
     "b4d_phase_track": [_vp, _vp, _i64, _i32, _i32, _i32, _f64, _vp],
     "b4d_stack_pipeline": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64, _f64, _f64,

@@ -855,9 +855,13 @@ __global__ void __launch_bounds__(128) argmax_reduce_kernel(const ArgBest* __res
 
 // z-score the (h, w) template over its own pixels and embed it at (y0, x0) in a zero (ny, nx) frame
 // (signal/tracking.py:251-260). mean / variance come from the frame-reduction table of the template.
+// blockIdx.y = template index (one padded frame each); the templates are h*w apart, their reduction rows B4D_FR_NCOLS
 __global__ void __launch_bounds__(256) embed_template_kernel(const float* __restrict__ tpl, int h, int w, int ny, int nx,
                                                              int y0, int x0, float eps, const double* __restrict__ fr,
                                                              float* __restrict__ out) {
+    tpl += (size_t)blockIdx.y * h * w;
+    fr += (size_t)blockIdx.y * B4D_FR_NCOLS;
+    out += (size_t)blockIdx.y * ny * nx;
     const float m = (float)fr[B4D_FR_MEAN];
     const float inv = 1.f / ((float)sqrt(fr[B4D_FR_M2]) + eps);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ny * nx; i += gridDim.x * blockDim.x) {
@@ -1450,8 +1454,10 @@ __global__ void __launch_bounds__(256) tm_scan_cols_kernel(double* __restrict__ 
 // compact result map (T, oy, ox) from the shifted correlation map and the integral images (cv2's common_matchTemplate)
 __global__ void __launch_bounds__(256) tm_normalise_kernel(const float* __restrict__ corr, const double* __restrict__ P1,
                                                            const double* __restrict__ P2, int ny, int nx, int h, int w,
-                                                           const double* __restrict__ tfr, double eps, float* __restrict__ out) {
+                                                           const double* __restrict__ tfr, int tfr_stride, double eps,
+                                                           float* __restrict__ out) {
     const int64_t t = blockIdx.y;
+    tfr += (size_t)t * tfr_stride;
     const int oy = ny - h + 1, ox = nx - w + 1;
     const double area = (double)h * (double)w;
     // tpl_z = (tpl - mean) / (std + eps): its own standard deviation, and cv2's templNorm = sdv * sqrt(area)
@@ -2157,8 +2163,8 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
     return B4D_OK;
 }
 
-extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int h, int w, const float* stack, int64_t n_frames, int ny, int nx,
-                                  double ref_y, double ref_x, int subpixel, double eps, double* out) {
+extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame, int h, int w, const float* stack, int64_t n_frames,
+                                  int ny, int nx, double ref_y, double ref_x, int subpixel, double eps, double* out) {
     if (!ctx) return B4D_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->lock);
     int rc = check_fft_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
@@ -2168,44 +2174,50 @@ extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int h, int w, 
     const size_t npix = (size_t)ny * nx, half = (size_t)ny * (nx / 2);
     const int oy = ny - h + 1, ox = nx - w + 1;
     const size_t nres = (size_t)oy * ox;
-    // batch: correlation map + result map (float) and two integral images (double) per frame, at most ~1.5 GB
-    int64_t B = ((int64_t)1536 << 20) / (int64_t)(npix * 24);
+    // batch: correlation map + result map (float), two integral images (double) and, with one template per frame, its
+    // conjugate spectrum, per frame; at most ~1.5 GB
+    int64_t B = ((int64_t)1536 << 20) / (int64_t)(npix * (per_frame ? 28 : 24));
     if (B < 1) B = 1;
     const int64_t Bfft = batch_frames(ctx, ny, nx, 2);
     if (B > Bfft) B = Bfft;
     if (B > n_frames) B = n_frames;
-    // template: z-scored over the ROI (tracking.py:151, :308-311), embedded at the origin, conjugate spectrum
+    const int64_t nt = per_frame ? B : 1;               // template spectra alive at a time
     void* p = nullptr;
-    if ((rc = b4d_scratch(ctx, SCR_NYQ, sizeof(float2) * (half + ny) + sizeof(double) * B4D_FR_NCOLS + 256, &p))) return rc;
+    if ((rc = b4d_scratch(ctx, SCR_NYQ, sizeof(float2) * (half + ny) * nt + sizeof(double) * B4D_FR_NCOLS * nt + 256, &p))) return rc;
     float2* tref = static_cast<float2*>(p);
-    float2* tref_nyq = tref + half;
-    double* tfr = reinterpret_cast<double*>(tref_nyq + ny);
+    float2* tref_nyq = tref + half * nt;
+    double* tfr = reinterpret_cast<double*>(tref_nyq + (size_t)ny * nt);
     if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (npix + nres) * B + sizeof(double) * 2 * npix * B + 256, &p))) return rc;
     float* corr = static_cast<float*>(p);
     float* res = corr + npix * B;
     double* P1 = reinterpret_cast<double*>(res + ((nres * B + 1) & ~size_t(1)));
     double* P2 = P1 + npix * B;
-    if ((rc = b4d_frame_reductions_nolock(ctx, tpl, 1, h, w, nullptr, nullptr, nan(""), 0.0, tfr))) return rc;
-    embed_template_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(tpl, h, w, ny, nx, 0, 0, (float)eps, tfr, corr);
-    B4D_LAUNCH_CHECK(ctx);
-    {
+    // templates: z-scored over the ROI (tracking.py:151, :308-311), embedded at the origin, conjugate spectra
+    auto template_spectra = [&](const float* tp, int64_t count) -> int {
+        int r = b4d_frame_reductions_nolock(ctx, tp, count, h, w, nullptr, nullptr, nan(""), 0.0, tfr);
+        if (r) return r;
+        embed_template_kernel<<<dim3(ctx->sm_count * 2, (unsigned)count), 256, 0, ctx->stream>>>(tp, h, w, ny, nx, 0, 0, (float)eps, tfr, corr);
+        B4D_LAUNCH_CHECK(ctx);
         Work wk;
-        if ((rc = carve(ctx, 1, ny, nx, false, false, &wk))) return rc;
-        if ((rc = run_rows_fwd(ctx, corr, 1, ny, nx, nullptr, nullptr, wk, false))) return rc;
+        if ((r = carve(ctx, count, ny, nx, false, false, &wk))) return r;
+        if ((r = run_rows_fwd(ctx, corr, count, ny, nx, nullptr, nullptr, wk, false))) return r;
         ColsArgs c = cols_defaults(wk, nx, false);
         c.conj_out = tref;
         c.conj_nyq_out = tref_nyq;
-        if ((rc = run_cols(ctx, c, 1, ny))) return rc;
-    }
+        return run_cols(ctx, c, count, ny);
+    };
+    if (!per_frame && (rc = template_spectra(tpl, 1))) return rc;
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         const float* s0 = stack + t0 * npix;
+        if (per_frame && (rc = template_spectra(tpl + (size_t)t0 * h * w, tc))) return rc;
         Work w_;
         if ((rc = carve(ctx, tc, ny, nx, true, false, &w_))) return rc;
         if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, nullptr, nullptr, w_, true))) return rc;      // frames - pilot
         ColsArgs c = cols_defaults(w_, nx, false);                                                  // (no DC add-back)
         c.i2_pc = w_.I2a;
-        c.R = tref; c.Rnyq = tref_nyq; c.r_stride = 0; c.rnyq_stride = 0; c.whiten = 0; c.eps = 0.f;
+        c.R = tref; c.Rnyq = tref_nyq; c.r_stride = per_frame ? half : 0; c.rnyq_stride = per_frame ? (size_t)ny : 0;
+        c.whiten = 0; c.eps = 0.f;
         if ((rc = run_cols(ctx, c, tc, ny))) return rc;
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
@@ -2220,7 +2232,8 @@ extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int h, int w, 
             B4D_LAUNCH_CHECK(ctx);
             int bx = (int)((nres + 2047) / 2048);
             if (bx > 592) bx = 592;
-            tm_normalise_kernel<<<dim3(bx, (unsigned)tc), 256, 0, ctx->stream>>>(corr, P1, P2, ny, nx, h, w, tfr, eps, res);
+            tm_normalise_kernel<<<dim3(bx, (unsigned)tc), 256, 0, ctx->stream>>>(corr, P1, P2, ny, nx, h, w, tfr,
+                                                                               per_frame ? B4D_FR_NCOLS : 0, eps, res);
             B4D_LAUNCH_CHECK(ctx);
             gen_argmax_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(res, (int64_t)nres, w_.pk_idx);
             B4D_LAUNCH_CHECK(ctx);

@@ -292,18 +292,21 @@ class PhaseTracker:
 
 
 def template_match(template, stack, *, ref_center_yx, subpixel: bool = True, eps: float = 1e-9, return_device: bool = False):
-    """Normalised cross-correlation matching of one (h, w) template against every frame of a (T, ny, nx) stack
-    (b4d_template_match). ref_center_yx: centre of the template's reference position. -> (T, 4) = dy, dx, peak, snr."""
+    """Normalised cross-correlation matching of one (h, w) template against every frame of a (T, ny, nx) stack, or of a
+    (T, h, w) template stack frame by frame (b4d_template_match). ref_center_yx: centre of the template's reference position. -> (T, 4) = dy, dx, peak, snr."""
     torch = require_cuda()
     T, ny, nx = stack.shape
     check_fft_shape(ny, nx)
-    tpl = as_stack(template, _dev(stack))[0].contiguous()
-    h, w = (int(v) for v in tpl.shape)
+    tpl = as_stack(template, _dev(stack)).contiguous()
+    per_frame = tpl.shape[0] != 1 or getattr(template, "ndim", 2) == 3
+    if per_frame and tpl.shape[0] != T:
+        raise ValueError("a template stack needs one template per frame")
+    h, w = (int(v) for v in tpl.shape[1:])
     if h > ny or w > nx:
         raise ValueError(f"template shape {(h, w)} must fit inside image shape {(ny, nx)}")
     ctx = get_context(_dev(stack))
     out = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
-    ctx.check(ctx.lib.b4d_template_match(ctx.handle, ptr(tpl), h, w, ptr(stack), T, ny, nx, float(ref_center_yx[0]),
+    ctx.check(ctx.lib.b4d_template_match(ctx.handle, ptr(tpl), int(per_frame), h, w, ptr(stack), T, ny, nx, float(ref_center_yx[0]),
                                          float(ref_center_yx[1]), int(bool(subpixel)), float(eps), ptr(out)),
               "b4d_template_match")
     return out if return_device else out.cpu().numpy()

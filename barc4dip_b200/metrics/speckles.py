@@ -177,10 +177,10 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
                         parallel: bool = True, n_jobs: int | None = None, keep_autocorr: bool = False) -> dict:
     """Per-frame speckle metrics of a (T, H, W) stack plus 3x3-ROI translation tracking (abs / inc).
 
-    Differences from the reference, all explicit: tracking runs with method="phase", backend="internal"
-    only (the reference's default template/skimage tracker is a SURVEY.md 8(f) "next" row and raises);
-    the per-frame (T, N, N) float64 autocorrelation stack is returned only with keep_autocorr=True
-    (32 MB per 2048^2 frame on the host, SURVEY.md section 7 "hard parts").
+    Trackers: "template" (the reference's default; both of its backend names are served by the same normalised
+    cross-correlation kernels, pinned against opencv) and "phase" / "internal". Difference from the reference, explicit:
+    the per-frame (T, N, N) float64 autocorrelation stack is returned only with keep_autocorr=True (32 MB per 2048^2
+    frame on the host, SURVEY.md section 7 "hard parts").
     """
     if not isinstance(stack, np.ndarray):
         raise TypeError("speckle_stack_stats expects a numpy.ndarray")
@@ -191,9 +191,13 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
         raise ValueError("stack must contain at least one frame.")
     normalize_display_origin(display_origin)
     groups = normalize_groups(metrics, all_groups=_ALL_SPECKLE_GROUPS, context="speckles", param_name="metrics")
-    if str(tracking_method).strip().lower() != "phase" or tracking_backend != "internal":
-        raise B4DUnsupported("speckle_stack_stats on the B200 path tracks with tracking_method='phase', "
-                             "tracking_backend='internal'; the template/skimage/opencv trackers are not built")
+    method = str(tracking_method).strip().lower()
+    if method not in ("phase", "template"):
+        raise ValueError(f"Unsupported tracking method: {tracking_method!r}. Supported: phase, template")
+    if method == "phase" and tracking_backend != "internal":
+        raise B4DUnsupported("phase tracking on the B200 path implements tracking_backend='internal' only")
+    if method == "template" and tracking_backend not in ("opencv", "skimage"):
+        raise ValueError("backend must be 'opencv' or 'skimage'.")
     dev = engine.as_stack(stack)
     full = _full_blocks(dev, groups, saturation_value, eps, keep_maps=keep_autocorr)
     if "grain" in full and keep_autocorr:
@@ -214,9 +218,19 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     dy_abs = np.empty((T, 3, 3), np.float32)
     dx_inc = np.empty((T, 3, 3), np.float32)
     dy_inc = np.empty((T, 3, 3), np.float32)
+    prev = np.maximum(np.arange(T) - 1, 0)
     for iy in range(3):
         for ix in range(3):
             sy, sx = grid[iy][ix]
+            if method == "template":
+                # the reference's default tracker: normalised cross-correlation of the ROI against the full frame; absolute
+                # = ROI of frame 0 against every frame, incremental = ROI of frame t-1 against frame t, both batched
+                centre = ((sy.start + sy.stop - 1) / 2.0, (sx.start + sx.stop - 1) / 2.0)
+                tab = engine.template_match(dev[0, sy, sx], dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
+                dy_abs[:, iy, ix], dx_abs[:, iy, ix] = tab[:, 0], tab[:, 1]
+                tab = engine.template_match(dev[prev][:, sy, sx].contiguous(), dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
+                dy_inc[:, iy, ix], dx_inc[:, iy, ix] = tab[:, 0], tab[:, 1]
+                continue
             # absolute: one reference (ROI of frame 0) against the whole stack
             tr = engine.PhaseTracker(dev[0, sy, sx].contiguous(), (H, W), y0=sy.start, x0=sx.start, eps=1e-9)
             tab = tr.track(dev, subpixel=subpixel)

@@ -222,11 +222,13 @@ int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, i
  * template_matching (signal/tracking.py:82-188, cv2.matchTemplate TM_CCOEFF_NORMED on the z-scored template): for every
  * frame the normalised cross-correlation map of shape (ny-h+1, nx-w+1), its first-occurrence argmax, the reference's
  * 3x3 Taylor step and (dy, dx, peak, snr) with dy = peak_y + (h-1)/2 - ref_y, snr = |peak| / (median|map| + eps).
- * tpl: DEVICE (h, w) float32 (raw: the z-score is applied here); ref_y, ref_x: centre of the template's reference
- * position, (start + stop - 1) / 2 of its slices. Power-of-two frames. out: DEVICE float64 (n_frames, 4).
+ * tpl: DEVICE float32, raw (the z-score is applied here): one (h, w) template for every frame (per_frame = 0) or
+ * (n_frames, h, w), template t matched against frame t (per_frame = 1: the incremental tracking of speckle_stack_stats,
+ * metrics/speckles.py:373-384). ref_y, ref_x: centre of the template's reference position, (start + stop - 1) / 2 of
+ * its slices. Power-of-two frames. out: DEVICE float64 (n_frames, 4).
  */
-int b4d_template_match(b4d_ctx* ctx, const float* tpl, int h, int w, const float* stack, int64_t n_frames, int ny, int nx,
-                       double ref_y, double ref_x, int subpixel, double eps, double* out);
+int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame, int h, int w, const float* stack, int64_t n_frames,
+                       int ny, int nx, double ref_y, double ref_x, int subpixel, double eps, double* out);
 
 /* xcorr2d (signal/corr.py:169-253) of frame pairs (a[t], b[t]); real float32 output. */
 int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx,

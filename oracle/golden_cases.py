@@ -140,3 +140,9 @@ def template_cases() -> dict[str, dict]:
     u16 = np.clip(base * 20.0, 0, 65535).astype(np.uint16)
     cases["u16_25"] = dict(template=u16[sl].copy(), image=np.roll(u16, (1, 6), axis=(0, 1)), slices=sl, subpixel=True)
     return cases
+
+
+def stack_tracking_case() -> np.ndarray:
+    """4 frames of 256^2 drifting by a random walk (speckle_stack_stats, template tracker on the 3x3 ROI grid)."""
+    stack, _ = synth.tracking_stack(4, 256, grain=8.0, seed=51, step_sigma=0.8)
+    return stack

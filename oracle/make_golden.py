@@ -58,6 +58,17 @@ def template_golden(sig, versions):
     tz = sig.tracking._zscore2d(c["template"].astype(np.float32), eps=1e-9).astype(np.float32)
     iz = sig.tracking._zscore2d(c["image"].astype(np.float32), eps=1e-9).astype(np.float32)
     store["roll_25/map"] = cv2.matchTemplate(iz, tz, method=cv2.TM_CCOEFF_NORMED)
+    # the stack aggregator with its default tracker ("template"; opencv backend, skimage is not installed here)
+    from oracle.load_reference import load_reference
+    met = load_reference().metrics
+    st = gc.stack_tracking_case()
+    res = met.speckle_stack_stats(st, metrics=("stats",), tiles=False, tracking_method="template", tracking_backend="opencv",
+                                  parallel=False, verbose=False)
+    for mode in ("abs", "inc"):
+        for k, v in res["temporal"][mode].items():
+            store[f"stack/{mode}/{k}"] = np.asarray(v)
+    store["stack/roi_size_yx"] = np.asarray(res["meta"]["tracking"]["roi_size_yx"])
+    store["stack/roi_step_yx"] = np.asarray(res["meta"]["tracking"]["roi_step_yx"])
     np.savez_compressed(os.path.join(OUT, "template.npz"), **store)
     print("template.npz", os.path.getsize(os.path.join(OUT, "template.npz")) // 1024, "KiB")
 

@@ -233,3 +233,22 @@ def test_bad_pixel_repair_bit_exact(dip, golden):
     np.testing.assert_array_equal(ffc(raw, flats=flat, darks=dark, bad_pixel_removal=True), g["stack"])
     np.testing.assert_array_equal(ffc(raw[1], flats=flat, darks=dark, scale="none", bad_pixel_removal=True), g["single"])
     assert np.count_nonzero(g["stack"] != ffc(raw, flats=flat, darks=dark)) > 0      # the repair does change pixels
+
+
+def test_speckle_stack_stats_default_template_tracker(dip, golden):
+    """speckle_stack_stats with the reference's default tracker (template matching on the 3x3 ROI grid, absolute and
+    incremental) against goldens recorded from the reference (opencv backend): displacements within 0.01 px."""
+    g = golden("template")
+    stack = gc.stack_tracking_case()
+    out = dip.metrics.speckle_stack_stats(stack, metrics=("stats",), tiles=False, tracking_method="template",
+                                          tracking_backend="opencv", verbose=False)
+    assert tuple(out["meta"]["tracking"]["roi_size_yx"]) == tuple(int(v) for v in g["stack/roi_size_yx"])
+    assert tuple(out["meta"]["tracking"]["roi_step_yx"]) == tuple(int(v) for v in g["stack/roi_step_yx"])
+    for mode in ("abs", "inc"):
+        for k in ("dx", "dy", "r", "std_dx", "std_dy", "std_r"):
+            got, want = out["temporal"][mode][k], g[f"stack/{mode}/{k}"]
+            assert got.dtype == np.float32 and got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=0, atol=0.01, err_msg=f"{mode}.{k}")
+    # the signature's own defaults (template / skimage) run too and give the same numbers
+    dflt = dip.metrics.speckle_stack_stats(stack, metrics=("stats",), tiles=False, verbose=False)
+    np.testing.assert_array_equal(dflt["temporal"]["abs"]["dx"], out["temporal"]["abs"]["dx"])
