@@ -252,3 +252,17 @@ def test_speckle_stack_stats_default_template_tracker(dip, golden):
     # the signature's own defaults (template / skimage) run too and give the same numbers
     dflt = dip.metrics.speckle_stack_stats(stack, metrics=("stats",), tiles=False, verbose=False)
     np.testing.assert_array_equal(dflt["temporal"]["abs"]["dx"], out["temporal"]["abs"]["dx"])
+
+
+def test_two_gpu_sharding_equals_single_gpu():
+    """1-GPU result == N-GPU result (tier 4): scripts/multi_gpu_check.py under torchrun with two
+    ranks over NCCL -- per-frame outputs bitwise, all-reduced temporal moments within 1e-6. Needs two GPUs."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "scripts", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "multi_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
