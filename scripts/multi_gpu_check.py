@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/multi_gpu_check.py
 Every rank holds its contiguous frame range; rank 0 additionally computes the whole stack alone and compares:
   * per-frame outputs of the fused pipeline (reductions, grain, tracking, PSD / autocorrelation maps): bitwise;
-  * temporal moments after the NCCL all-reduce of the power sums: <= 1e-6 relative (a different summation order).
+  * temporal moments after the NCCL all-reduce of the power sums: <= 1e-6 relative (a different shift map and summation order).
 Prints "multi_gpu_check ok" from rank 0 and exits 0, or raises."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -42,8 +42,13 @@ if rank == 0:
         assert torch.equal(v, one[k]), f"{k}: sharded table differs from the single-GPU one"
     assert torch.equal(local_maps[0], one["psd"][lo:hi]) and torch.equal(local_maps[1], one["autocorr"][lo:hi])
     tm1 = engine.temporal_moments(full)
-    for k in ("mean", "std", "variance", "skewness", "kurtosis"):
+    # the ranks share rank 0's shift map, which differs from the one the single-GPU run picks (other pilot frames): the
+    # fp32-over-8-frames partial sums round differently. Dimensioned maps to 1e-6 relative; the dimensionless ones
+    # (skewness, excess kurtosis; O(1), zero crossings) to 1e-5 absolute.
+    for k in ("mean", "std", "variance"):
         np.testing.assert_allclose(tm[k], tm1[k], rtol=1e-6, atol=1e-9, err_msg=k)
-    print(f"multi_gpu_check ok: {world} ranks, {T} frames of {n}^2; per-frame outputs bitwise equal, temporal moments within 1e-6")
+    for k in ("skewness", "kurtosis"):
+        np.testing.assert_allclose(tm[k], tm1[k], rtol=1e-6, atol=1e-5, err_msg=k)
+    print(f"multi_gpu_check ok: {world} ranks, {T} frames of {n}^2; per-frame outputs bitwise equal, temporal moments within 1e-6 (1e-5 absolute for skewness / kurtosis)")
 dist.barrier()
 dist.destroy_process_group()
