@@ -127,7 +127,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = args.cpu_frames or max(8, min(32, cores))
+    # bounded sample: about 400 frames in total (~2 minutes at the 3-4 frames/s this path reaches on 16 cores), so
+    # that any --steps K finishes within a few minutes; 2..32 frames per step
+    frames = args.cpu_frames or max(2, min(32, 400 // max(1, args.steps)))
     fps, sec_per_step, cores = time_cpu(args.size, frames, max(1, args.steps), min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
