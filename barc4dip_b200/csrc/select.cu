@@ -536,11 +536,23 @@ __global__ void __launch_bounds__(1024) fused_median_final_kernel(const SelFast*
                     if (p < FIN_CAP) s_keys[p] = key;
                 }
             };
-            // a warp walks a region: its count, then up to FM_REGION keys (two per lane)
-            for (int r = warp; r < regions; r += 32) {
-                const unsigned c = c3[3 * r];
-                if (lane < (int)c) take(store[(size_t)r * FM_REGION + lane]);
-                if (lane + 32 < (int)c) take(store[(size_t)r * FM_REGION + lane + 32]);
+            // a warp walks regions four at a time: their counts, then up to FM_REGION keys each (two per lane), all
+            // loads of a group in flight together (the walk is latency bound: 8192 regions per frame at 2048^2)
+            constexpr int RU = 4;
+            for (int r0 = warp * RU; r0 < regions; r0 += 32 * RU) {
+                unsigned c[RU], k0[RU], k1[RU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) c[u] = r0 + u < regions ? c3[3 * (r0 + u)] : 0u;
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    k0[u] = lane < (int)c[u] ? store[(size_t)(r0 + u) * FM_REGION + lane] : 0u;
+                    k1[u] = lane + 32 < (int)c[u] ? store[(size_t)(r0 + u) * FM_REGION + lane + 32] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    if (lane < (int)c[u]) take(k0[u]);
+                    if (lane + 32 < (int)c[u]) take(k1[u]);
+                }
             }
             for (unsigned i = threadIdx.x; i < sc; i += blockDim.x) take(store[(size_t)regions * FM_REGION + i]);
             __syncthreads();
