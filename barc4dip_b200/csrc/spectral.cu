@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
         }
         __syncthreads();
         if (tid == 0) {
-            ArgBest b = {bm, s_idx};
+            ArgBest b = {bm, s_idx == 0xffffffffu ? 0u : s_idx};     // (an all-NaN block has no maximum)
             a.best[(size_t)t * gridDim.x + blockIdx.x] = b;
         }
     }
@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(128) argmax_reduce_kernel(const ArgBest* __res
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 4; ++w) best_update(b, sb[w].v, sb[w].idx);
-        out_idx[t] = b.idx;
+        out_idx[t] = b.idx == 0xffffffffu ? 0u : b.idx;          // never hand an out-of-range index to the consumers
         out_val[t] = b.v;
     }
 }

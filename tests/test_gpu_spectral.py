@@ -331,3 +331,27 @@ def test_template_matching_stack_2048():
     np.testing.assert_allclose(tab[2, :2], want[:2], atol=0.01)
     np.testing.assert_allclose(tab[2, 2], want[2], rtol=1e-4)
     np.testing.assert_allclose(tab[2, 3], want[3], rtol=2e-3)
+
+
+def test_nan_frame_is_isolated_in_a_batch():
+    """A NaN pixel poisons its own frame's spectra (as numpy's FFT would) and nothing else: the other frames of the same
+    batched launches come out bit-identical to a run without the bad frame, and the bad frame's outputs are NaN."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    n = 256
+    stack, _ = synth.tracking_stack(4, n, grain=5.0, seed=23, integer_every=2)
+    bad = stack.copy()
+    bad[2, 100, 37] = np.nan
+    engine.PhaseTracker(stack[0], (n, n), y0=0, x0=0)
+    good = engine.stack_pipeline(engine.as_stack(stack), tail_quantiles=(0.0005, 0.9995))
+    got = engine.stack_pipeline(engine.as_stack(bad), tail_quantiles=(0.0005, 0.9995))
+    keep = [0, 1, 3]
+    for k in ("psd", "autocorr", "grain", "tracking", "reductions", "quantiles"):
+        assert torch.equal(got[k][keep], good[k][keep]), k
+    assert bool(torch.isnan(got["psd"][2]).all()) and bool(torch.isnan(got["autocorr"][2]).all())
+    assert bool(torch.isnan(got["tracking"][2, 2:]).all())
+    # the single-pass reductions skip the NaN like the reference (finite pixels only)
+    fr = got["reductions"][2].cpu().numpy()
+    want = orc.distribution_moments(bad[2])
+    np.testing.assert_allclose(fr[1], want["mean"], rtol=1e-6)
+    assert fr[0] == n * n - 1
