@@ -355,3 +355,37 @@ def test_nan_frame_is_isolated_in_a_batch():
     want = orc.distribution_moments(bad[2])
     np.testing.assert_allclose(fr[1], want["mean"], rtol=1e-6)
     assert fr[0] == n * n - 1
+
+
+@pytest.mark.parametrize("n", [256, 250])
+def test_degenerate_frames_do_not_disturb_their_batch(n):
+    """Constant, all-zero and infinite frames share batched launches with ordinary ones: no fault, and the ordinary frames'
+    maps and tables are bit-identical to a clean run (256: power-of-two kernels; 250: Bluestein path)."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    base = synth.speckle_frame(256, grain=5.0, seed=29)[:n, :n].copy()
+    rng = np.random.default_rng(3)
+    clean = np.stack([base + (5.0 * rng.standard_normal((n, n))).astype(np.float32) for _ in range(5)])
+    dirty = clean.copy()
+    dirty[1] = 7.0
+    dirty[2] = 0.0
+    dirty[3, 5, 5] = np.inf
+    keep = [0, 4]
+    a, _ = engine.autocorr2d(engine.as_stack(clean), want_grain=False)
+    b, _ = engine.autocorr2d(engine.as_stack(dirty), want_grain=False)
+    assert torch.equal(a[keep], b[keep])
+    pa, sa = engine.psd2d(engine.as_stack(clean), want_spectral=True)
+    pb, sb = engine.psd2d(engine.as_stack(dirty), want_spectral=True)
+    assert torch.equal(pa[keep], pb[keep])
+    np.testing.assert_array_equal(sa[keep], sb[keep])
+    assert float(pb[2].abs().max()) == 0.0                                   # the zero frame has a zero spectrum
+    if n == 256:
+        engine.PhaseTracker(clean[0], (n, n), y0=0, x0=0)
+        ra = engine.stack_pipeline(engine.as_stack(clean), tail_quantiles=(0.0005, 0.9995))
+        rb = engine.stack_pipeline(engine.as_stack(dirty), tail_quantiles=(0.0005, 0.9995))
+        for k in ("psd", "autocorr", "grain", "tracking", "reductions", "quantiles"):
+            assert torch.equal(ra[k][keep], rb[k][keep]), k
+        ta = engine.template_match(clean[0, 100:125, 90:115], engine.as_stack(clean), ref_center_yx=(112.0, 102.0))
+        tb = engine.template_match(clean[0, 100:125, 90:115], engine.as_stack(dirty), ref_center_yx=(112.0, 102.0))
+        np.testing.assert_array_equal(ta[keep], tb[keep])
+        np.testing.assert_allclose(ta[0, :2], 0.0, atol=0.05)
