@@ -389,3 +389,28 @@ def test_degenerate_frames_do_not_disturb_their_batch(n):
         tb = engine.template_match(clean[0, 100:125, 90:115], engine.as_stack(dirty), ref_center_yx=(112.0, 102.0))
         np.testing.assert_array_equal(ta[keep], tb[keep])
         np.testing.assert_allclose(ta[0, :2], 0.0, atol=0.05)
+
+
+def test_internal_batching_does_not_change_results():
+    """The FFT pipeline works through a stack in internal batches (b4d_set_batch_frames): 11 frames as 4 + 4 + 3, one by
+    one, or all at once give bit-identical tables and maps."""
+    import torch
+    from barc4dip_b200 import engine, synth
+    from barc4dip_b200._lib import get_context
+    n, T = 128, 11
+    stack, _ = synth.tracking_stack(T, n, grain=4.0, seed=31, integer_every=4)
+    d = engine.as_stack(stack)
+    engine.PhaseTracker(stack[0], (n, n), y0=0, x0=0)
+    ctx = get_context()
+    outs = []
+    try:
+        for b in (0, 4, 1):
+            ctx.set_batch_frames(b)
+            r = engine.stack_pipeline(d, tail_quantiles=(0.0005, 0.9995))
+            tm = engine.template_match(stack[0, 40:61, 50:71], d, ref_center_yx=(50.0, 60.0), return_device=True)
+            outs.append({k: v.clone() for k, v in r.items() if v is not None} | {"tm": tm.clone()})
+    finally:
+        ctx.set_batch_frames(0)
+    for other in outs[1:]:
+        for k, v in outs[0].items():
+            assert torch.equal(v, other[k]), k
