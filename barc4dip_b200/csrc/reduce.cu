@@ -742,6 +742,7 @@ int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, 
             if (rc) return rc;
         } else if (tails) {
             B4D_CUDA(ctx, cudaMemsetAsync(tails->nvalid_out + t0, 0xff, sizeof(int64_t) * tc, ctx->stream));   // -1: unresolved
+            B4D_CUDA(ctx, cudaMemsetAsync(tails->quant_out + 4 * t0, 0xff, sizeof(float) * 4 * tc, ctx->stream));   // NaN
         }
     }
     return B4D_OK;

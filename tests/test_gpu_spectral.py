@@ -411,6 +411,7 @@ def test_internal_batching_does_not_change_results():
             outs.append({k: v.clone() for k, v in r.items() if v is not None} | {"tm": tm.clone()})
     finally:
         ctx.set_batch_frames(0)
+    assert bool((outs[0]["n_valid"] == -1).all()) and bool(torch.isnan(outs[0]["quantiles"]).all())   # 128^2: tails left to the exact select
     for other in outs[1:]:
         for k, v in outs[0].items():
-            assert torch.equal(v, other[k]), k
+            assert torch.equal(torch.nan_to_num(v, nan=-1.0), torch.nan_to_num(other[k], nan=-1.0)), k
