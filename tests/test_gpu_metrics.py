@@ -266,3 +266,54 @@ def test_two_gpu_sharding_equals_single_gpu():
                         "127.0.0.1", "--master-port", "29577", os.path.join(root, "scripts", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "multi_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_speckle_stats_arbitrary_frame_vs_oracle(dip):
+    """A 600 x 450 frame (neither square nor a power of two; pad_to_square -> 600, Bluestein path, tiles_3x3 with 200 x 150
+    tiles) against the oracle's full-frame metrics and tiling executor."""
+    from barc4dip_b200 import synth
+    img = synth.speckle_frame(600, 450, grain=5.0, seed=37)
+    out = dip.metrics.speckle_stats(img, tiles=True, verbose=False)
+    flipped = img[::-1, :]
+    for grp, fn in (("amplitude", orc.amplitude), ("grain", orc.grain), ("bandwidth", orc.bandwidth),
+                    ("stats", orc.distribution_moments)):
+        want = fn(flipped)
+        for k, v in want.items():
+            if np.ndim(v) == 0:
+                np.testing.assert_allclose(out["full"][grp][k], v, rtol=RTOL, atol=1e-12, err_msg=f"{grp}.{k}")
+    assert out["meta"]["tile_mode"] == "tiles_3x3" and out["meta"]["tile_shape_px"] == (200, 150)
+    mode, tiles = orc.speckle_tiles(img)
+    assert mode == "tiles_3x3"
+    for grp, fields in tiles.items():
+        for k, v in fields.items():
+            np.testing.assert_allclose(out["tiles"][grp][k]["mean"], v["mean"], rtol=RTOL, atol=1e-12, err_msg=f"tiles {grp}.{k}")
+            assert np.all(np.isnan(out["tiles"][grp][k]["std"]))
+
+
+def test_stack_tiles_chunking_and_analyzer_ragged_chunks(dip):
+    """17 frames through the tiling executor (chunks of 16 frames + 1) and through StackAnalyzer with a chunk size that does
+    not divide the stack: first / last frames equal the single-frame calls."""
+    from barc4dip_b200 import synth
+    from barc4dip_b200.pipeline import StackAnalyzer
+    T, n = 17, 384                                                  # 384 // 3 = 128: tiles_3x3 of 128 px
+    stack, _ = synth.tracking_stack(T, 512, grain=5.0, seed=41)
+    stack = np.ascontiguousarray(stack[:, :n, :n])
+    shs = dip.metrics.sharpness_stack_stats(stack, metrics=("stats", "gradient", "spectral"), tiles=True, verbose=False)
+    assert shs["tiles"]["gradient"]["tenengrad"]["mean"].shape == (T, 3, 3)
+    for t in (0, 15, 16):
+        one = dip.metrics.sharpness_stats(stack[t], metrics=("stats", "gradient", "spectral"), tiles=True, verbose=False)
+        for grp, fields in one["tiles"].items():
+            for k, v in fields.items():
+                np.testing.assert_allclose(v["mean"], shs["tiles"][grp][k]["mean"][t], rtol=1e-12, err_msg=f"{t} {grp}.{k}")
+    sq = np.ascontiguousarray(stack[:, :256, :256])
+    ref = StackAnalyzer((256, 256), reference=sq[0], chunk_frames=T).run(sq)
+    for chunk in (5, 1, 32):
+        got = StackAnalyzer((256, 256), reference=sq[0], chunk_frames=chunk).run(sq)
+        np.testing.assert_array_equal(got["table"], ref["table"])
+        np.testing.assert_array_equal(got["psd"], ref["psd"])
+        np.testing.assert_array_equal(got["autocorr"], ref["autocorr"])
+        for k in ("dy", "dx", "peak", "snr"):
+            np.testing.assert_array_equal(got["tracking"][k], ref["tracking"][k])
+        np.testing.assert_array_equal(got["amplitude"]["contrast"], ref["amplitude"]["contrast"])
+    one = StackAnalyzer((256, 256), reference=sq[0]).run(sq[:1])
+    np.testing.assert_array_equal(one["table"], ref["table"][:1])
