@@ -1175,19 +1175,26 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     return B4D_OK;
 }
 
-// columns per CTA at ny = 2048 (experiment knob: B4D_COLS_CW=4|8)
-int cols_cw_2048() {
-    static int v = 0;
-    if (!v) { const char* e = getenv("B4D_COLS_CW"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 4 ? 4 : B4D_COLS_CW_2048); }
-    return v;
+// Columns per CTA of the column pass at ny = 2048. A CTA's row-major map stores (PSD, complex spectrum) are one
+// contiguous piece of CW elements per row, and the load/store pipe pays per piece: with a map to write, 8 columns (one
+// 1024-thread CTA per SM, 32-byte pieces) beat 4 (two 512-thread CTAs, 16-byte pieces) -- 2.87 vs 3.14 ms per 128 frames
+// in the fused pipeline, 1.33 vs 1.72 ms PSD only; without one, two independent CTAs per SM overlap their phases better
+// (tracker only: 1.71 vs 1.89 ms). `wide_out`: the launch writes such a map. Experiment knob: B4D_COLS_CW=4|8.
+int cols_cw(int ny, bool wide_out) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("B4D_COLS_CW"); forced = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 4 ? 4 : 0); }
+    if (ny < 2048) return TC;
+    return forced ? forced : (wide_out ? 8 : B4D_COLS_CW_2048);
 }
+int cols_tiles(int ny, int nx, bool wide_out) { return nx / 2 / cols_cw(ny, wide_out); }
+bool cols_wide_out(const ColsArgs& a) { return a.psd_out != nullptr || a.cplx_out != nullptr; }
 
 template <int NY, int CW>
 int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T);
 
 template <int NY>
 int launch_cols(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
-    if (NY >= 2048 && cols_cw_2048() == 4) return launch_cols_cw<NY, (NY >= 2048 ? 4 : TC)>(ctx, a, T);
+    if (NY >= 2048 && cols_cw(NY, cols_wide_out(a)) == 4) return launch_cols_cw<NY, (NY >= 2048 ? 4 : TC)>(ctx, a, T);
     return launch_cols_cw<NY, TC>(ctx, a, T);
 }
 
@@ -1242,9 +1249,6 @@ int launch_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& a, int64_t T, int* nblk_out)
 }
 
 // CTAs per frame of the column pass (= number of per-frame partial sums it leaves behind)
-int cols_cw_2048();
-int cols_cw(int ny) { return ny >= 2048 ? cols_cw_2048() : TC; }
-int cols_tiles(int ny, int nx) { return nx / 2 / cols_cw(ny); }
 
 int rows_inv_blocks(int nx, int ny) {
     const int tpf = nx / 16, wpg = tpf / 8, gpc = 16 / wpg, fpc = 4 * gpc;
@@ -1295,7 +1299,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->H = static_cast<float2*>(p);
     if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * T, &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
     if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * T, &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
-    const int ntiles = cols_tiles(ny, nx), nblk = ny;   // nblk: generous upper bound for rows_inv CTAs per frame
+    const int ntiles = cols_tiles(ny, nx, false), nblk = ny;   // (upper bounds: narrow tiles; rows_inv CTAs per frame)
     size_t small = 0;
     auto take = [&](size_t bytes) { size_t o = small; small += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
@@ -1769,7 +1773,7 @@ extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
         if ((rc = run_cols(ctx, c, tc, ny))) return rc;
         if (spectral) {
             double* tab = spectral + t0 * B4D_SP_NCOLS;
-            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx), tab, tc);
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx, cols_wide_out(c)), tab, tc);
             B4D_LAUNCH_CHECK(ctx);
             if (want_f95 && (rc = run_f95(ctx, map_b, ny, tc, tab))) return rc;
         }
@@ -1794,8 +1798,8 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
     if ((rc = run_cols(ctx, c, tc, ny))) return rc;
     RowsInvAcArgs r;
     memset(&r, 0, sizeof(r));
-    r.Iz = w.I2a; r.Inyq = w.I2nyq; r.ny = ny; r.ch_log2 = log2i(cols_cw(ny) / 2); r.out = out_ac;
-    r.norm = use_norm ? w.acp : nullptr; r.n_norm = cols_tiles(ny, nx); r.norm_mult = norm_mult;
+    r.Iz = w.I2a; r.Inyq = w.I2nyq; r.ny = ny; r.ch_log2 = log2i(cols_cw(ny, cols_wide_out(c)) / 2); r.out = out_ac;
+    r.norm = use_norm ? w.acp : nullptr; r.n_norm = cols_tiles(ny, nx, cols_wide_out(c)); r.norm_mult = norm_mult;
     r.scale = 1.0 / ((double)nx * (double)ny);
     r.best = grain_out ? w.bestA : nullptr;
     int nblk = 0;
@@ -2133,8 +2137,8 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
             // over the rows 0 .. ny/2; the tracker's rows go on their own (two rows per transform)
             RowsInvAcArgs ra;
             memset(&ra, 0, sizeof(ra));
-            ra.Iz = w.I2a; ra.Inyq = w.I2nyq; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny) / 2);
-            ra.out = acm; ra.norm = w.acp; ra.n_norm = cols_tiles(ny, nx); ra.norm_mult = 1.0; ra.scale = 1.0 / ((double)nx * ny);
+            ra.Iz = w.I2a; ra.Inyq = w.I2nyq; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny, cols_wide_out(c)) / 2);
+            ra.out = acm; ra.norm = w.acp; ra.n_norm = cols_tiles(ny, nx, cols_wide_out(c)); ra.norm_mult = 1.0; ra.scale = 1.0 / ((double)nx * ny);
             ra.best = grain_out ? w.bestA : nullptr;
             if ((rc = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac))) return rc;
         }
