@@ -68,6 +68,7 @@ _SIGNATURES = {
     "b4d_temporal_pilot": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "b4d_temporal_finalize": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "b4d_fft2d": [_vp, _vp, _i64, _i32, _i32, _vp],
+    "b4d_ifft2d": [_vp, _vp, _i64, _i32, _i32, _vp],
     "b4d_psd2d": [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp, _vp],
     "b4d_autocorr2d": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _f64, _vp],
     "b4d_xcorr2d": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp],

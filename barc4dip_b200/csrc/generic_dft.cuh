@@ -233,6 +233,21 @@ __global__ void __launch_bounds__(256) gen_autocorr_out_kernel(const float2* __r
     }
 }
 
+// ifftshift of a complex spectrum (in) into natural order (out), or natural order -> same with a scale (shift = 0)
+__global__ void __launch_bounds__(256) gen_unshift_kernel(const float2* __restrict__ in, float2* __restrict__ out, int ny, int nx,
+                                                           int shift, float scale) {
+    const int64_t t = blockIdx.y;
+    const int64_t npix = (int64_t)ny * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nx), x = (int)(i % nx);
+        // np.fft.ifftshift: out[k] = in[(k + n//2) % n]
+        const int sy = shift ? (y + ny / 2) % ny : y, sx = shift ? (x + nx / 2) % nx : x;
+        float2 v = in[(size_t)t * npix + (size_t)sy * nx + sx];
+        v.x *= scale; v.y *= scale;
+        out[(size_t)t * npix + i] = v;
+    }
+}
+
 // first-occurrence argmax of a (T, n) float map, one CTA per frame
 __global__ void __launch_bounds__(1024) gen_argmax_kernel(const float* __restrict__ map, int64_t n, unsigned* __restrict__ idx_out) {
     const int64_t t = blockIdx.x;

@@ -1632,6 +1632,29 @@ int gen_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx
     return B4D_OK;
 }
 
+// ifft2d (signal/fft.py:240-258): ifft2(ifftshift(F)), complex in, complex out, any sides in [2, 2048]
+int gen_ifft2d(b4d_ctx* ctx, const float2* spec, int64_t n_frames, int ny, int nx, float2* out) {
+    const int64_t B = gen_batch(ny, nx);
+    const size_t npix = (size_t)ny * nx;
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_unshift_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(spec + t0 * npix, w.A, ny, nx, 1, 1.f);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if ((rc = gen_inverse(ctx, gen_cache(ctx), tc, ny, nx, w.A, w.Bf))) return rc;
+        ProfScope ps(ctx, KC_GENERIC);
+        gen_unshift_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, out + t0 * npix, ny, nx, 0,
+                                                                               (float)(1.0 / ((double)nx * (double)ny)));
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
 int gen_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float scale_factor, int sub_mean, int zero_dc,
               float* out_psd, double* spectral) {
     const int64_t B = gen_batch(ny, nx);
@@ -2254,4 +2277,13 @@ extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame,
         B4D_LAUNCH_CHECK(ctx);
     }
     return B4D_OK;
+}
+
+extern "C" int b4d_ifft2d(b4d_ctx* ctx, const float* spec_c64, int64_t n_frames, int ny, int nx, float* out_c64) {
+    if (!ctx) return B4D_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_ifft2d: null output");
+    int rc = check_gen_args(ctx, "b4d_ifft2d", spec_c64, n_frames, ny, nx);
+    if (rc) return rc;
+    return gen_ifft2d(ctx, reinterpret_cast<const float2*>(spec_c64), n_frames, ny, nx, reinterpret_cast<float2*>(out_c64));
 }

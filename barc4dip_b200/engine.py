@@ -217,6 +217,19 @@ def fft2d(stack):
     return torch.view_as_complex(out)
 
 
+def ifft2d(spec):
+    """ifft2(ifftshift(F)) for every shifted complex64 spectrum of a (T, ny, nx) CUDA tensor -> complex64 (T, ny, nx)."""
+    torch = require_cuda()
+    T, ny, nx = spec.shape
+    if not all(2 <= n <= 2048 for n in (ny, nx)):
+        raise _lib.B4DUnsupported(f"ifft2d covers sides in [2, 2048]; got ({ny}, {nx})")
+    ctx = get_context(_dev(spec))
+    src = torch.view_as_real(spec.to(torch.complex64).contiguous())
+    out = torch.empty((T, ny, nx, 2), dtype=torch.float32, device=spec.device)
+    ctx.check(ctx.lib.b4d_ifft2d(ctx.handle, ptr(src), T, ny, nx, ptr(out)), "b4d_ifft2d")
+    return torch.view_as_complex(out)
+
+
 def psd2d(stack, *, scale_factor: float = 1.0, sub_mean: bool = False, zero_dc: bool = False,
           want_map: bool = True, want_spectral: bool = False):
     """Shifted |FFT|^2 * scale_factor per frame. Returns (psd or None, spectral table or None)."""

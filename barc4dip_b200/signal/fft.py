@@ -39,6 +39,17 @@ def fft2d(image, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
     return F, fx, fy
 
 
+def ifft2d(F):
+    """Inverse of fft2d: ifft2(ifftshift(F)) of a shifted complex spectrum (signal/fft.py:240-258)."""
+    F = np.asarray(F)
+    if F.ndim != 2:
+        raise ValueError("F must be a 2D array.")
+    torch = engine.require_cuda()
+    dev = torch.from_numpy(np.ascontiguousarray(F, dtype=np.complex64)).to(f"cuda:{engine._lib.default_device()}")
+    out = engine.ifft2d(dev[None])[0].cpu().numpy()
+    return out if F.dtype == np.complex64 else out.astype(np.complex128)
+
+
 def psd2d(image, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0, scale: bool = True):
     """P = |fftshift(fft2(image))|^2, times dx*dy/(nx*ny) when scale is True. No mean removal."""
     img = np.asarray(image)

@@ -187,6 +187,10 @@ int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, 
 /* fft2d (signal/fft.py:198-237): out = fftshift(fft2(frame)), complex64 interleaved (ny, nx). */
 int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64);
 
+/* ifft2d (signal/fft.py:240-258): out = ifft2(ifftshift(F)), complex64 in and out (ny, nx), any sides in [2, 2048]
+ * (chirp-z path; a building block and test hook, not a hot-path kernel). */
+int b4d_ifft2d(b4d_ctx* ctx, const float* spec_c64, int64_t n_frames, int ny, int nx, float* out_c64);
+
 /*
  * psd2d (signal/fft.py:261-309): out = |fftshift(fft2(frame - sub))|^2 * scale_factor, float32.
  * sub_mean != 0 subtracts the frame mean first (bandwidth / spectral_entropy call sites,

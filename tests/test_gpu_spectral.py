@@ -415,3 +415,21 @@ def test_internal_batching_does_not_change_results():
     for other in outs[1:]:
         for k, v in outs[0].items():
             assert torch.equal(torch.nan_to_num(v, nan=-1.0), torch.nan_to_num(other[k], nan=-1.0)), k
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (150, 200), (2048, 2048), (31, 64)])
+def test_ifft2d_round_trip_and_vs_numpy(sig, shape):
+    """ifft2d(fft2d(x)) returns x (to float32 FFT rounding), and ifft2d of an arbitrary shifted spectrum equals numpy's."""
+    rng = np.random.default_rng(shape[0] + 3 * shape[1])
+    img = (100.0 + 20.0 * rng.standard_normal(shape)).astype(np.float32)
+    F, _, _ = sig.fft2d(img)
+    back = sig.ifft2d(F)
+    assert back.dtype == np.complex64 and back.shape == shape
+    scale = float(np.abs(img).max())
+    assert np.max(np.abs(back.real - img)) <= 1e-5 * scale and np.max(np.abs(back.imag)) <= 1e-5 * scale
+    G = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    want = np.fft.ifft2(np.fft.ifftshift(G.astype(np.complex128)))
+    got = sig.ifft2d(G)
+    assert np.max(np.abs(got - want)) <= 1e-5 * float(np.abs(want).max())
+    with pytest.raises(ValueError):
+        sig.ifft2d(np.zeros((2, 4, 4), np.complex64))
