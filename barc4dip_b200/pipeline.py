@@ -25,7 +25,7 @@ from ._lib import FR_NCOLS, cast_to_f32, get_context, native_int_code, require_c
 
 
 class StackAnalyzer:
-    def __init__(self, frame_shape, *, reference=None, device: int | None = None, chunk_frames: int = 16,
+    def __init__(self, frame_shape, *, reference=None, device: int | None = None, chunk_frames: int = 8,
                  want_maps: bool = True, want_contrast: bool = True, saturation_value: float | None = 65535.0,
                  eps: float = 1e-6, subpixel: bool = True, flats=None, darks=None, scale: str = "flat_median",
                  flat_eps: float | None = None):

@@ -301,7 +301,7 @@ def run_b200(args):
     if not args.no_e2e:
         host = torch.empty((F, n, n), dtype=torch.float32, pin_memory=True)
         host.copy_(stack)
-        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(16, F // 4)), want_maps=True, want_contrast=True)
+        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(8, F // 4)), want_maps=True, want_contrast=True)
         ref_host = host[0].clone()
 
         def time_e2e(keep: bool):

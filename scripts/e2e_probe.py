@@ -23,7 +23,7 @@ for rep in range(3):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"bare H2D: {dt * 1e3:.1f} ms  {F * n * n * 4 / dt / 1e9:.1f} GB/s")
-for chunk in (16, 32, 8):
+for chunk in (16, 8, 4):
     an = StackAnalyzer((n, n), device=0, chunk_frames=chunk, want_maps=True, want_contrast=True)
     an.set_reference(host[0].clone())
     for rep in range(5):
