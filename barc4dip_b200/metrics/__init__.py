@@ -1,7 +1,13 @@
-from . import sharpness, speckles, statistics
-from .sharpness import sharpness_stack_stats, sharpness_stats
-from .speckles import speckle_stack_stats, speckle_stats
-from .statistics import distribution_moments
+"""
+Drop-in for ``barc4dip.metrics``: per-frame metric functions and the four aggregators (single frame / stack, speckle /
+sharpness), evaluated by batched kernels on HBM-resident stacks (``engine``, ``stack``).
+"""
 
-__all__ = ["sharpness", "sharpness_stats", "sharpness_stack_stats", "statistics", "speckles", "speckle_stats",
-           "speckle_stack_stats", "distribution_moments"]
+from . import common, sharpness, speckles, statistics
+
+distribution_moments = statistics.distribution_moments
+speckle_stats, speckle_stack_stats = speckles.speckle_stats, speckles.speckle_stack_stats
+sharpness_stats, sharpness_stack_stats = sharpness.sharpness_stats, sharpness.sharpness_stack_stats
+
+__all__ = ["statistics", "speckles", "sharpness", "common", "distribution_moments", "speckle_stats", "speckle_stack_stats",
+           "sharpness_stats", "sharpness_stack_stats"]

@@ -1,49 +1,68 @@
-"""Axis / step validation shared by fft.py and corr.py (host-side; mirrors signal/common.py of the reference)."""
+"""
+Sampling steps, shifted frequency axes and lag axes for the spectral wrappers (host side, scalar and 1-D work only).
+
+The callers may describe the sampling grid either by steps (dx, dy) or by coordinate axes (x, y); the reference accepts
+one or the other and insists on uniformly sampled, strictly monotonic axes (signal/common.py:13-87 there). The rules and
+the wording of the errors are the reference's, because user code and its tests see them.
+"""
 
 from __future__ import annotations
 
 import numpy as np
 
+_UNIFORM_TOL = 1e-6      # largest relative deviation of any spacing from the median spacing
 
-def _uniform_step(axis, name: str) -> float:
-    a = np.asarray(axis, dtype=float)
-    if a.ndim != 1 or a.size < 2:
-        raise ValueError(f"{name} must be a 1D array with at least 2 samples.")
-    d = np.diff(a)
-    if not np.all(np.isfinite(d)):
-        raise ValueError(f"{name} contains non-finite values.")
-    if not (np.all(d > 0) or np.all(d < 0)):
-        raise ValueError(f"{name} must be strictly monotonic (uniform sampling assumed).")
-    mag = np.abs(d)
-    step = float(np.median(mag))
-    if step <= 0:
-        raise ValueError(f"{name} has non-positive sampling step.")
-    rel = float(np.max(np.abs(mag - step)) / step)
-    if rel > 1e-6:
-        raise ValueError(f"{name} appears non-uniform (max relative deviation {rel:.2e}). "
+
+def step_of_axis(values, label: str) -> float:
+    """Spacing of a uniformly sampled coordinate axis; ValueError when it is not one."""
+    coords = np.asarray(values, dtype=float)
+    if coords.ndim != 1 or coords.size < 2:
+        raise ValueError(f"{label} must be a 1D array with at least 2 samples.")
+    gaps = coords[1:] - coords[:-1]
+    if not np.isfinite(gaps).all():
+        raise ValueError(f"{label} contains non-finite values.")
+    rising, falling = bool((gaps > 0).all()), bool((gaps < 0).all())
+    if not (rising or falling):
+        raise ValueError(f"{label} must be strictly monotonic (uniform sampling assumed).")
+    widths = np.abs(gaps)
+    h = float(np.median(widths))
+    if h <= 0:
+        raise ValueError(f"{label} has non-positive sampling step.")
+    spread = float(np.abs(widths - h).max() / h)
+    if spread > _UNIFORM_TOL:
+        raise ValueError(f"{label} appears non-uniform (max relative deviation {spread:.2e}). "
                          "Provide uniformly sampled axes.")
-    return step
+    return h
 
 
 def resolve_steps_2d(*, shape, x, y, dx: float, dy: float) -> tuple[float, float]:
-    """(dx, dy) from either explicit steps or uniformly sampled axes (ref: signal/common.py:58-87)."""
-    ny, nx = shape
-    if (x is None) ^ (y is None):
+    """(step along x, step along y) of an image of `shape` = (ny, nx), from steps or from axes, never both."""
+    with_axes = (x is not None, y is not None)
+    if with_axes[0] != with_axes[1]:
         raise ValueError("Provide both x and y axes, or neither.")
-    if (x is not None and dx != 1.0) or (y is not None and dy != 1.0):
+    if (with_axes[0] and dx != 1.0) or (with_axes[1] and dy != 1.0):
         raise ValueError("Provide either (x, y) or (dx, dy), not both.")
-    if x is None:
-        if dx <= 0 or dy <= 0:
+    if not with_axes[0]:
+        if min(dx, dy) <= 0:
             raise ValueError("dx and dy must be > 0.")
         return float(dx), float(dy)
-    xa, ya = np.asarray(x, dtype=float), np.asarray(y, dtype=float)
-    if xa.ndim != 1 or ya.ndim != 1:
+    axes = [np.asarray(v, dtype=float) for v in (x, y)]
+    if any(a.ndim != 1 for a in axes):
         raise ValueError("x and y must be 1D arrays.")
-    if xa.size != nx or ya.size != ny:
+    if (axes[1].size, axes[0].size) != tuple(int(n) for n in shape):
         raise ValueError("x/y sizes must match (nx, ny) of the image.")
-    return _uniform_step(xa, "x"), _uniform_step(ya, "y")
+    return step_of_axis(axes[0], "x"), step_of_axis(axes[1], "y")
+
+
+def freq_axes2d(*, shape, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
+    ny, nx = shape
+    if ny < 1 or nx < 1:
+        raise ValueError("shape must contain positive integers.")
+    sx, sy = resolve_steps_2d(shape=shape, x=x, y=y, dx=dx, dy=dy)
+    return (np.fft.fftshift(np.fft.fftfreq(int(nx), d=sx)), np.fft.fftshift(np.fft.fftfreq(int(ny), d=sy)))
 
 
 def lag_axis(n: int, step: float) -> np.ndarray:
-    """(arange(n) - n//2) * step (ref: signal/common.py:89-90)."""
-    return (np.arange(n, dtype=float) - (n // 2)) * float(step)
+    """Lags of a shifted correlation of length n: zero lag at index n // 2."""
+    centre = n // 2
+    return float(step) * (np.arange(n, dtype=float) - centre)

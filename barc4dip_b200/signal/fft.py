@@ -12,15 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import engine
-from .common import resolve_steps_2d
-
-
-def freq_axes2d(*, shape, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
-    ny, nx = shape
-    if ny < 1 or nx < 1:
-        raise ValueError("shape must contain positive integers.")
-    sx, sy = resolve_steps_2d(shape=shape, x=x, y=y, dx=dx, dy=dy)
-    return (np.fft.fftshift(np.fft.fftfreq(int(nx), d=sx)), np.fft.fftshift(np.fft.fftfreq(int(ny), d=sy)))
+from .common import freq_axes2d, resolve_steps_2d
 
 
 def _out_real_dtype(img: np.ndarray):
