@@ -10,14 +10,17 @@ extern "C" int b4d_create(int device, b4d_ctx** out) {
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || device < 0 || device >= ndev) return B4D_ERR_CUDA;
+    if (e != cudaSuccess || device < 0 || device >= ndev || device >= B4D_MAX_DEVICES) return B4D_ERR_CUDA;
+    int prev = -1;
+    cudaGetDevice(&prev);
     if (cudaSetDevice(device) != cudaSuccess) return B4D_ERR_CUDA;
     b4d_ctx* c = new (std::nothrow) b4d_ctx();
-    if (!c) return B4D_ERR_NOMEM;
+    if (!c) { if (prev >= 0) cudaSetDevice(prev); return B4D_ERR_NOMEM; }
     c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     *out = c;
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);     // the caller's current device is left as it was
     return B4D_OK;
 }
 
@@ -36,7 +39,7 @@ extern "C" int b4d_destroy(b4d_ctx* ctx) {
 
 extern "C" int b4d_set_stream(b4d_ctx* ctx, void* cuda_stream) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     return B4D_OK;
 }
@@ -55,7 +58,7 @@ extern "C" int b4d_device_sm_count(b4d_ctx* ctx) { return ctx ? ctx->sm_count : 
 
 extern "C" int b4d_profile_begin(b4d_ctx* ctx) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     for (auto& sp : ctx->prof_spans) { ctx->prof_pool.push_back(sp.a); ctx->prof_pool.push_back(sp.b); }
     ctx->prof_spans.clear();
     ctx->prof_on = true;
@@ -64,7 +67,7 @@ extern "C" int b4d_profile_begin(b4d_ctx* ctx) {
 
 extern "C" int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* launches_per_class) {
     if (!ctx || !ms_per_class || !launches_per_class) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     ctx->prof_on = false;
     B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < KC_COUNT; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
@@ -87,14 +90,14 @@ extern "C" const char* b4d_profile_class_name(int k) {
 
 extern "C" int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames) {
     if (!ctx || frames < 0) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     ctx->batch_override = frames;
     return B4D_OK;
 }
 
 extern "C" int b4d_set_fused_median(b4d_ctx* ctx, int on) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     ctx->fused_median = on != 0;
     return B4D_OK;
 }
@@ -157,7 +160,7 @@ int launch_cast(b4d_ctx* ctx, const void* src, float* dst, int64_t n) {
 
 extern "C" int b4d_cast_to_f32(b4d_ctx* ctx, const void* src, int dtype, float* dst, int64_t n) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!src || !dst || n < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_cast_to_f32: bad arguments");
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_cast_to_f32: pointers must be 16-byte aligned");

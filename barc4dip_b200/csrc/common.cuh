@@ -26,6 +26,9 @@ struct ProfSpan {
     cudaEvent_t a, b;
 };
 
+// cudaFuncSetAttribute is per device: the "already raised the shared-memory limit" flags of the launchers are too
+constexpr int B4D_MAX_DEVICES = 64;
+
 struct b4d_ctx {
     int device = 0;
     int sm_count = 148;
@@ -45,6 +48,20 @@ struct b4d_ctx {
     std::vector<cudaEvent_t> prof_pool;
     int cur_class = KC_SMALL;
     std::mutex lock;
+};
+
+// Every extern "C" entry point holds one of these: the context's lock, and the context's device made current for the
+// duration of the call (a process may drive several devices, each through its own context).
+struct B4dCall {
+    std::lock_guard<std::mutex> guard;
+    int restore = -1;
+    explicit B4dCall(b4d_ctx* c) : guard(c->lock) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device && cudaSetDevice(c->device) == cudaSuccess) restore = cur;
+    }
+    ~B4dCall() { if (restore >= 0) cudaSetDevice(restore); }
+    B4dCall(const B4dCall&) = delete;
+    B4dCall& operator=(const B4dCall&) = delete;
 };
 
 // Brackets the next launches with CUDA events when profiling is on (events live on ctx->stream).

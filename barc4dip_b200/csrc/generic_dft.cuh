@@ -272,8 +272,8 @@ template <int M>
 int launch_bluestein(b4d_ctx* ctx, const BluArgs& a) {
     constexpr int T = M / 16, FPC = 512 / T;
     constexpr size_t smem = (size_t)FPC * (padded_len(M) + 8) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(bluestein_rows_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(bluestein_rows_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     const int64_t blocks = (a.rows + FPC - 1) / FPC;
     if (blocks > 0x7fffffffLL) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "generic DFT: too many rows");
     ProfScope ps(ctx, KC_GENERIC);

@@ -640,7 +640,7 @@ extern "C" int b4d_frame_reductions(b4d_ctx* ctx, const float* stack, int64_t n_
                                     const float* gain, const float* dark, double sat_value, double zero_eps,
                                     double* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     return b4d_frame_reductions_nolock(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out);
 }
 
@@ -653,7 +653,7 @@ extern "C" int b4d_frame_reductions_tails(b4d_ctx* ctx, const float* stack, int6
                                           const float* gain, const float* dark, double sat_value, double zero_eps,
                                           double q_lo, double q_hi, double* out, float* quant_out, int64_t* nvalid_out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!quant_out || !nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions_tails: need 0 <= q_lo < q_hi <= 1 and both outputs");
     FrTails tl = {q_lo, q_hi, quant_out, nvalid_out};

@@ -831,11 +831,11 @@ unsigned b4d_tails_gcap() { return TAIL_GCAP; }
 
 int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain, const float* dark,
                            double q_lo, double q_hi, float* thr) {
-    static int attr = 0;
-    if (!attr) {
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(tails_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(SEL_SAMPLES * sizeof(unsigned))));
-        attr = 1;
+        attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_SELECT_SAMPLE);
     tails_probe_kernel<<<(unsigned)T, 1024, SEL_SAMPLES * sizeof(unsigned), ctx->stream>>>(stack, gain, dark, npix, q_lo, q_hi, thr);
@@ -845,11 +845,11 @@ int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t 
 
 int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const int* flag, const double* fr, int64_t T,
                            double q_lo, double q_hi, float* out, int64_t* nvalid_out) {
-    static int attr = 0;
-    if (!attr) {
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(tails_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(TAIL_GCAP * sizeof(unsigned))));
-        attr = 1;
+        attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_SELECT_FINAL);
     tails_final_kernel<<<(unsigned)T, 1024, TAIL_GCAP * sizeof(unsigned), ctx->stream>>>(cand, cnt, flag, fr, q_lo, q_hi, out,
@@ -899,11 +899,11 @@ int b4d_fused_median_begin(b4d_ctx* ctx, int64_t T, int regions, FusedMedian* fm
 }
 
 int b4d_fused_median_bracket(b4d_ctx* ctx, const FusedMedian& fm, const float* samples, int m, int64_t T) {
-    static int attr = 0;
+    static bool attr[B4D_MAX_DEVICES] = {};
     if (m > 32768) return b4d_fail(ctx, B4D_ERR_INVALID, "fused median: at most 32768 samples per frame");
-    if (!attr) {
+    if (!attr[ctx->device]) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(sel_bracket_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-        attr = 1;
+        attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_SELECT_SAMPLE);
     sel_bracket_samples_kernel<<<(unsigned)T, 1024, (size_t)m * sizeof(unsigned), ctx->stream>>>(samples, m, fm.q_dev, fm.st, fm.cand,
@@ -923,7 +923,7 @@ int b4d_fused_median_final(b4d_ctx* ctx, const FusedMedian& fm, int64_t T, float
 
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid) {
-    static int sample_attr = 0;
+    static bool sample_attr[B4D_MAX_DEVICES] = {};
     const bool fast = n >= SEL_FAST_MIN;
     const unsigned cap = fast ? (unsigned)(n / 8) : 0u;
     const int64_t TC = 16384;
@@ -950,10 +950,10 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
         float* o0 = out + t0 * 2 * n_q;
         long long* nv0 = n_valid ? reinterpret_cast<long long*>(n_valid) + t0 : nullptr;
         if (fast) {
-            if (!sample_attr) {
+            if (!sample_attr[ctx->device]) {
                 B4D_CUDA(ctx, cudaFuncSetAttribute(sel_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)(SEL_SAMPLES * sizeof(unsigned))));
-                sample_attr = 1;
+                sample_attr[ctx->device] = true;
             }
             { ProfScope ps(ctx, KC_SELECT_SAMPLE);
               sel_sample_kernel<<<(unsigned)tc, 1024, SEL_SAMPLES * sizeof(unsigned), ctx->stream>>>(s0, n, n_q, q_dev, use_abs, sf); }
@@ -984,7 +984,7 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
 extern "C" int b4d_select_ranks(b4d_ctx* ctx, const float* stack, int64_t n_frames, int64_t frame_elems,
                                 const double* quantiles_host, int n_q, int use_abs, float* out, int64_t* n_valid) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!stack || !out || !quantiles_host || n_frames < 1 || frame_elems < 1 || n_q < 1 || n_q > SEL_MAXQ)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_select_ranks: bad arguments (n_q must be 1..%d)", SEL_MAXQ);
     for (int i = 0; i < n_q; ++i)

@@ -1151,8 +1151,8 @@ template <int NX>
 int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     constexpr int TPF = NX / 16, FPC = 512 / TPF, ROWS = 2 * FPC;
     constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     if (a.ny % ROWS) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, ROWS);
     ProfScope ps(ctx, KC_ROWS_FWD);
     rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(a);
@@ -1164,10 +1164,10 @@ template <int NY, int CW, bool SPEC, bool AC, bool PC>
 int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     constexpr size_t smem = (size_t)padded_len(NY) * CW * sizeof(float2) +
                             (AC ? (size_t)NY * CW * sizeof(float) + (size_t)NY * sizeof(float) : 0);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(cols_kernel<NY, CW, SPEC, AC, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_COLS);
     cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(a);
@@ -1214,8 +1214,8 @@ template <int NX, int MODE, bool ABS>
 int launch_rows_inv_inst(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
     constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
     constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 8) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX, MODE, ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_kernel<NX, MODE, ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     const int rows = 2 * FPC;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     a.nblk = a.ny / rows;
@@ -1237,8 +1237,8 @@ template <int NX>
 int launch_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& a, int64_t T, int* nblk_out) {
     constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
     constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 2) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_ac_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_ac_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     const int rows = 2 * FPC, nblk = (a.ny / 2 + 1 + rows - 1) / rows;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     ProfScope ps(ctx, KC_ROWS_INV_AC);
@@ -1742,7 +1742,7 @@ void b4d_fft_release(b4d_ctx* ctx) {
 // =================================================================================================
 extern "C" int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_fft2d: null output");
     if (!pow2_sides(ny, nx)) {
         int rcg = check_gen_args(ctx, "b4d_fft2d", stack, n_frames, ny, nx);
@@ -1766,7 +1766,7 @@ extern "C" int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int
 extern "C" int b4d_psd2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float scale_factor,
                          int sub_mean, int zero_dc, float* out_psd, double* spectral) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!out_psd && !spectral) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_psd2d: nothing to compute");
     if (!pow2_sides(ny, nx)) {
         int rcg = check_gen_args(ctx, "b4d_psd2d", stack, n_frames, ny, nx);
@@ -1843,7 +1843,7 @@ int autocorr_batch(b4d_ctx* ctx, const float* stack, int64_t tc, int ny, int nx,
 extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int remove_mean,
                               int standardize, int normalize_peak, float* out_ac, double fraction, double* grain_out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     const bool generic = !pow2_sides(ny, nx);
     int rc = generic ? check_gen_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx)
                      : check_fft_args(ctx, "b4d_autocorr2d", stack, n_frames, ny, nx);
@@ -1877,7 +1877,7 @@ extern "C" int b4d_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames
 extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx, int remove_mean,
                            int standardize, int normalize_peak, float* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     int rc = check_fft_args(ctx, "b4d_xcorr2d", a, n_frames, ny, nx);
     if (rc) return rc;
     if (!b || !out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_xcorr2d: null pointer");
@@ -1926,7 +1926,7 @@ extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t
 extern "C" int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0,
                                        double eps) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     int rc = check_fft_args(ctx, "b4d_phase_set_reference", tpl, 1, ny, nx);
     if (rc) return rc;
     if (h < 1 || w < 1 || y0 < 0 || x0 < 0 || y0 + h > ny || x0 + w > nx)
@@ -2054,7 +2054,7 @@ size_t fused_scratch_floats(int ny, int nx, int ns, int64_t tc) {
 extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps,
                                double* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     int rc = check_fft_args(ctx, "b4d_phase_track", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
@@ -2100,7 +2100,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
                                   double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
                                   int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     int rc = check_fft_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
@@ -2193,7 +2193,7 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
 extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame, int h, int w, const float* stack, int64_t n_frames,
                                   int ny, int nx, double ref_y, double ref_x, int subpixel, double eps, double* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     int rc = check_fft_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
     if (rc) return rc;
     if (!tpl || !out || h < 1 || w < 1 || h > ny || w > nx)
@@ -2281,7 +2281,7 @@ extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame,
 
 extern "C" int b4d_ifft2d(b4d_ctx* ctx, const float* spec_c64, int64_t n_frames, int ny, int nx, float* out_c64) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!out_c64) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_ifft2d: null output");
     int rc = check_gen_args(ctx, "b4d_ifft2d", spec_c64, n_frames, ny, nx);
     if (rc) return rc;

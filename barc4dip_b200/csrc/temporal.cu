@@ -234,7 +234,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int b4d_temporal_accumulate(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
                                        const float* gain, const float* dark, const float* shift, double* sums) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!stack || !shift || !sums || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_temporal_accumulate: bad arguments");
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_temporal_accumulate: dark given without gain");
@@ -267,7 +267,7 @@ extern "C" int b4d_temporal_accumulate(b4d_ctx* ctx, const float* stack, int64_t
 extern "C" int b4d_temporal_pilot(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
                                   const float* gain, const float* dark, float* shift) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!stack || !shift || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_temporal_pilot: bad arguments");
     const int64_t npix = (int64_t)ny * nx;
@@ -279,7 +279,7 @@ extern "C" int b4d_temporal_pilot(b4d_ctx* ctx, const float* stack, int64_t n_fr
 extern "C" int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, int64_t n_total, int ny,
                                      int nx, double* maps) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!sums || !shift || !maps || n_total < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_temporal_finalize: bad arguments");
     const int64_t npix = (int64_t)ny * nx;
@@ -291,7 +291,7 @@ extern "C" int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const flo
 extern "C" int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frames, int ny, int nx, const float* flat,
                               const float* dark, float eps, float scale_value, int apply_scale, float* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!images || !flat || !out || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_flat_field: bad arguments");
     const int64_t npix = (int64_t)ny * nx;
@@ -307,7 +307,7 @@ extern "C" int b4d_flat_field(b4d_ctx* ctx, const float* images, int64_t n_frame
 extern "C" int b4d_bad_pixel_repair(b4d_ctx* ctx, float* frames, int64_t n_frames, int ny, int nx, const float* flat,
                                     const float* dark, float eps) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!frames || !flat || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_bad_pixel_repair: bad arguments");
     const int64_t npix = (int64_t)ny * nx;
@@ -321,7 +321,7 @@ extern "C" int b4d_bad_pixel_repair(b4d_ctx* ctx, float* frames, int64_t n_frame
 extern "C" int b4d_flat_gain(b4d_ctx* ctx, const float* flat, const float* dark, int ny, int nx, float eps,
                              float scale_value, float* gain) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!flat || !gain || ny < 1 || nx < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_flat_gain: bad arguments");
     const int64_t npix = (int64_t)ny * nx;
     flat_gain_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(flat, dark, npix, eps, scale_value, gain);
@@ -331,7 +331,7 @@ extern "C" int b4d_flat_gain(b4d_ctx* ctx, const float* flat, const float* dark,
 
 extern "C" int b4d_sub(b4d_ctx* ctx, const float* a, const float* b, int64_t n, float* out) {
     if (!ctx) return B4D_ERR_INVALID;
-    std::lock_guard<std::mutex> g(ctx->lock);
+    B4dCall g(ctx);
     if (!a || !out || n < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_sub: bad arguments");
     sub_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a, b, n, out);
     B4D_LAUNCH_CHECK(ctx);

@@ -317,3 +317,23 @@ def test_stack_tiles_chunking_and_analyzer_ragged_chunks(dip):
         np.testing.assert_array_equal(got["amplitude"]["contrast"], ref["amplitude"]["contrast"])
     one = StackAnalyzer((256, 256), reference=sq[0]).run(sq[:1])
     np.testing.assert_array_equal(one["table"], ref["table"][:1])
+
+
+def test_one_process_two_devices():
+    """One process may drive several devices, each through its own context: every ABI call makes its context's device
+    current for its duration (shared-memory limits are raised per device). Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from barc4dip_b200 import engine, synth
+    img = synth.speckle_frame(2048, grain=6.0, seed=3)[None]
+    outs = []
+    for dev in (0, 1, 0):
+        d = torch.from_numpy(img).to(f"cuda:{dev}")
+        psd, _ = engine.psd2d(d)
+        ac, g = engine.autocorr2d(d, want_grain=True)
+        outs.append((psd.cpu(), ac.cpu(), g))
+    assert torch.cuda.current_device() == 0
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+        np.testing.assert_array_equal(o[2], outs[0][2])
