@@ -248,6 +248,35 @@ __global__ void __launch_bounds__(256) gen_unshift_kernel(const float2* __restri
     }
 }
 
+// A <- A * conj(B), both (T, ny, nx) natural order spectra of mean-removed frames; DC handling as in the epilogue:
+// dc_mode 0 adds nx*ny*mean back to both DC bins first (no mean removal asked), 1 clears the product's DC bin.
+__global__ void __launch_bounds__(256) gen_cross_kernel(float2* __restrict__ A, const float2* __restrict__ Bs, const double* __restrict__ fra,
+                                                         const double* __restrict__ frb, int ny, int nx, int dc_mode) {
+    const int64_t t = blockIdx.y;
+    const int64_t npix = (int64_t)ny * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 a = A[(size_t)t * npix + i], b = Bs[(size_t)t * npix + i];
+        if (i == 0) {
+            if (dc_mode) a = make_float2(0.f, 0.f);
+            else {
+                a.x += (float)((double)npix * fra[t * B4D_FR_NCOLS + B4D_FR_MEAN]);
+                b.x += (float)((double)npix * frb[t * B4D_FR_NCOLS + B4D_FR_MEAN]);
+            }
+        }
+        A[(size_t)t * npix + i] = make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    }
+}
+
+// out = shifted Re(C) * scale (xcorr2d: real output, signal/corr.py:240-251)
+__global__ void __launch_bounds__(256) gen_real_out_kernel(const float2* __restrict__ C, int ny, int nx, float scale, float* __restrict__ out) {
+    const int64_t t = blockIdx.y;
+    const int64_t npix = (int64_t)ny * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nx), x = (int)(i % nx);
+        out[(size_t)t * npix + (size_t)((y + ny / 2) % ny) * nx + (x + nx / 2) % nx] = C[(size_t)t * npix + i].x * scale;
+    }
+}
+
 // first-occurrence argmax of a (T, n) float map, one CTA per frame
 __global__ void __launch_bounds__(1024) gen_argmax_kernel(const float* __restrict__ map, int64_t n, unsigned* __restrict__ idx_out) {
     const int64_t t = blockIdx.x;

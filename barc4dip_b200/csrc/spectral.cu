@@ -1632,6 +1632,54 @@ int gen_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx
     return B4D_OK;
 }
 
+// xcorr2d for frame sides that are not powers of two: ifft2(fft2(a) conj(fft2(b))), shifted, real part
+int gen_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx, int remove_mean, int normalize_peak,
+                float* out) {
+    int64_t B = gen_batch(ny, nx) / 2;
+    if (B < 1) B = 1;
+    const size_t npix = (size_t)ny * nx;
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        void* p = nullptr;
+        const size_t frb = (sizeof(double) * B4D_FR_NCOLS * tc + 255) & ~size_t(255);
+        if ((rc = b4d_scratch(ctx, SCR_SPEC_C, sizeof(float2) * npix * tc + frb + sizeof(float) * tc + 256, &p))) return rc;
+        float2* Sb = static_cast<float2*>(p);
+        double* fr_b = reinterpret_cast<double*>(Sb + npix * tc);
+        float* pk = reinterpret_cast<float*>(reinterpret_cast<char*>(fr_b) + frb);
+        const float* a0 = a + t0 * npix;
+        const float* b0 = b + t0 * npix;
+        float* o = out + t0 * npix;
+        // spectrum of b (mean removed) -> Sb, then spectrum of a -> A
+        if ((rc = b4d_frame_reductions_nolock(ctx, b0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), b0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        B4D_CUDA(ctx, cudaMemcpyAsync(Sb, w.A, sizeof(float2) * npix * tc, cudaMemcpyDeviceToDevice, ctx->stream));
+        B4D_CUDA(ctx, cudaMemcpyAsync(fr_b, w.fr, sizeof(double) * B4D_FR_NCOLS * tc, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = b4d_frame_reductions_nolock(ctx, a0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), a0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_cross_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, Sb, w.fr, fr_b, ny, nx, remove_mean ? 1 : 0);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if ((rc = gen_inverse(ctx, gen_cache(ctx), tc, ny, nx, w.A, w.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_real_out_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, ny, nx, (float)(1.0 / ((double)nx * (double)ny)), o);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if (normalize_peak) {
+            absmax_kernel<<<(unsigned)tc, 256, 0, ctx->stream>>>(o, (int64_t)npix, pk);
+            B4D_LAUNCH_CHECK(ctx);
+            scale_by_kernel<<<dim3(64, (unsigned)tc), 256, 0, ctx->stream>>>(o, (int64_t)npix, pk, 1);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+    }
+    return B4D_OK;
+}
+
 // ifft2d (signal/fft.py:240-258): ifft2(ifftshift(F)), complex in, complex out, any sides in [2, 2048]
 int gen_ifft2d(b4d_ctx* ctx, const float2* spec, int64_t n_frames, int ny, int nx, float2* out) {
     const int64_t B = gen_batch(ny, nx);
@@ -1878,9 +1926,15 @@ extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t
                            int standardize, int normalize_peak, float* out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
+    if (!b || !out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_xcorr2d: null pointer");
+    if (standardize && !normalize_peak)
+        return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_xcorr2d: standardize=1 with normalize='none' is applied by the host wrapper");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_xcorr2d", a, n_frames, ny, nx);
+        return rcg ? rcg : gen_xcorr2d(ctx, a, b, n_frames, ny, nx, remove_mean, normalize_peak, out);
+    }
     int rc = check_fft_args(ctx, "b4d_xcorr2d", a, n_frames, ny, nx);
     if (rc) return rc;
-    if (!b || !out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_xcorr2d: null pointer");
     const int64_t B = batch_frames(ctx, ny, nx, 3);
     const size_t per = (size_t)ny * (nx / 2);
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {

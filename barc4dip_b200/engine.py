@@ -264,7 +264,7 @@ def xcorr2d(a, b, *, remove_mean: bool = True, standardize: bool = False, normal
     T, ny, nx = a.shape
     if tuple(b.shape) != (T, ny, nx):
         raise ValueError("a and b must have the same shape.")
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(a))
     out = torch.empty((T, ny, nx), dtype=torch.float32, device=a.device)
     ctx.check(ctx.lib.b4d_xcorr2d(ctx.handle, ptr(a), ptr(b), T, ny, nx, int(bool(remove_mean)),
