@@ -277,6 +277,43 @@ __global__ void __launch_bounds__(256) gen_real_out_kernel(const float2* __restr
     }
 }
 
+// Phase correlation (signal/tracking.py:277-285) on natural-order spectra: A <- whiten(A * inv_s * Rc) with Rc the
+// conjugate spectrum of the embedded template (shared by all frames) and inv_s = 1 / (std + eps) of the frame (the frame's
+// mean was removed before the transform); DC: the exact residue of the mean removal.
+__global__ void __launch_bounds__(256) gen_phase_product_kernel(float2* __restrict__ A, const float2* __restrict__ Rc,
+                                                                 const double* __restrict__ fr, int64_t npix, float eps) {
+    const int64_t t = blockIdx.y;
+    const float inv_s = (float)(1.0 / (sqrt(fr[t * B4D_FR_NCOLS + B4D_FR_M2]) + (double)eps));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        float2 f = A[(size_t)t * npix + i];
+        f.x *= inv_s; f.y *= inv_s;
+        const float2 r = Rc[i];
+        float2 g = make_float2(f.x * r.x - f.y * r.y, f.x * r.y + f.y * r.x);
+        const float s2 = fmaf(g.x, g.x, g.y * g.y);
+        const float mag = s2 > 0.f ? sqrtf(s2) : 0.f;
+        const float inv = 1.f / (mag + eps);
+        A[(size_t)t * npix + i] = make_float2(g.x * inv, g.y * inv);
+    }
+}
+
+// conj in place (the template spectrum is stored conjugated)
+__global__ void __launch_bounds__(256) gen_conj_kernel(float2* __restrict__ A, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) A[i].y = -A[i].y;
+}
+
+// out = shifted |C| * scale (the tracker's magnitude map) or shifted Re(C) * scale
+__global__ void __launch_bounds__(256) gen_shift_out_kernel(const float2* __restrict__ C, int ny, int nx, float scale, int magnitude,
+                                                             float* __restrict__ out) {
+    const int64_t t = blockIdx.y;
+    const int64_t npix = (int64_t)ny * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nx), x = (int)(i % nx);
+        const float2 c = C[(size_t)t * npix + i];
+        const float v = magnitude ? sqrtf(c.x * c.x + c.y * c.y) : c.x;
+        out[(size_t)t * npix + (size_t)((y + ny / 2) % ny) * nx + (x + nx / 2) % nx] = v * scale;
+    }
+}
+
 // first-occurrence argmax of a (T, n) float map, one CTA per frame
 __global__ void __launch_bounds__(1024) gen_argmax_kernel(const float* __restrict__ map, int64_t n, unsigned* __restrict__ idx_out) {
     const int64_t t = blockIdx.x;

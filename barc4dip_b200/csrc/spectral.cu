@@ -44,6 +44,8 @@ struct FftPlanCache {
     int* blk_list = nullptr;     // fused median: sample row blocks first, then all the others
     int blk_n = 0, blk_ns = 0;
     void* gen = nullptr;         // GenCache*: chirp tables of the arbitrary-length path (generic_dft.cuh)
+    float2* gref = nullptr;      // tracker reference for frames that are not powers of two: conj spectrum, natural order
+    size_t gref_elems = 0;
 };
 
 namespace {
@@ -1480,7 +1482,7 @@ __global__ void __launch_bounds__(256) tm_normalise_kernel(const float* __restri
     };
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)oy * ox; i += (int64_t)gridDim.x * blockDim.x) {
         const int y = (int)(i / ox), xq = (int)(i % ox);
-        double num = (double)c[(size_t)((y + ny / 2) & (ny - 1)) * nx + ((xq + nx / 2) & (nx - 1))];
+        double num = (double)c[(size_t)((y + ny / 2) % ny) * nx + ((xq + nx / 2) % nx)];
         const double s1 = box(p1, y, xq), s2 = box(p2, y, xq);
         const double diff2 = fmax(s2 - s1 * s1 / area, 0.0);
         const double tt = diff2 <= 1.1920929e-6 * s2 ? 0.0 : sqrt(diff2) * tnorm;      // flat window: avoid rounding noise
@@ -1632,6 +1634,73 @@ int gen_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx
     return B4D_OK;
 }
 
+// phase_correlation for frame sides that are not powers of two (map-based: |corr| map, exact select for the median)
+int gen_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0, double eps) {
+    FftPlanCache* f = ctx->fft ? ctx->fft : (ctx->fft = new FftPlanCache());
+    const size_t npix = (size_t)ny * nx;
+    if (f->gref_elems != npix) {
+        if (f->gref) { B4D_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(f->gref); f->gref = nullptr; }
+        B4D_CUDA(ctx, cudaMalloc(&f->gref, sizeof(float2) * npix));
+        f->gref_elems = npix;
+    }
+    f->ref_ny = ny; f->ref_nx = nx;
+    GenWork gw;
+    int rc = gen_carve(ctx, 1, ny, nx, &gw);
+    if (rc) return rc;
+    void* p = nullptr;
+    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * npix + sizeof(double) * B4D_FR_NCOLS + 256, &p))) return rc;
+    float* padded = static_cast<float*>(p);
+    double* tfr = reinterpret_cast<double*>(padded + ((npix + 1) & ~size_t(1)));
+    if ((rc = b4d_frame_reductions_nolock(ctx, tpl, 1, h, w, nullptr, nullptr, nan(""), 0.0, tfr))) return rc;
+    embed_template_kernel<<<dim3(ctx->sm_count * 4, 1), 256, 0, ctx->stream>>>(tpl, h, w, ny, nx, y0, x0, (float)eps, tfr, padded);
+    B4D_LAUNCH_CHECK(ctx);
+    if ((rc = gen_forward(ctx, gen_cache(ctx), padded, nullptr, 1, ny, nx, gw.A, gw.Bf))) return rc;
+    gen_conj_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(gw.A, (int64_t)npix);
+    B4D_LAUNCH_CHECK(ctx);
+    B4D_CUDA(ctx, cudaMemcpyAsync(f->gref, gw.A, sizeof(float2) * npix, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B4D_OK;
+}
+
+int gen_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps, double* out) {
+    const size_t npix = (size_t)ny * nx;
+    int64_t B = gen_batch(ny, nx);
+    int rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + t0 * npix;
+        GenWork w;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &w))) return rc;
+        void* p = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * npix * tc + (sizeof(float) * 2 + sizeof(long long)) * tc + 512, &p))) return rc;
+        float* mag = static_cast<float*>(p);
+        float* med = mag + ((npix * tc + 63) & ~size_t(63));
+        long long* nvalid = reinterpret_cast<long long*>(med + ((2 * tc + 1) & ~int64_t(1)));
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, w.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), s0, w.fr, tc, ny, nx, w.A, w.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_phase_product_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, ctx->fft->gref, w.fr, (int64_t)npix, (float)eps);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if ((rc = gen_inverse(ctx, gen_cache(ctx), tc, ny, nx, w.A, w.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_shift_out_kernel<<<dim3(w.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(w.A, ny, nx, (float)(1.0 / ((double)nx * (double)ny)), 1, mag);
+            B4D_LAUNCH_CHECK(ctx);
+            gen_argmax_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(mag, (int64_t)npix, w.pk);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        void* q = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MISC, 1024, &q))) return rc;
+        static const double half_q = 0.5;
+        if ((rc = b4d_put_doubles(ctx, static_cast<double*>(q), &half_q, 1))) return rc;
+        if ((rc = b4d_select_impl(ctx, mag, tc, (int64_t)npix, static_cast<const double*>(q), 1, 1, med, reinterpret_cast<int64_t*>(nvalid)))) return rc;
+        phase_finalize_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(mag, w.pk, ny, nx, med, nvalid, subpixel, eps, out + t0 * 4, tc);
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
 // xcorr2d for frame sides that are not powers of two: ifft2(fft2(a) conj(fft2(b))), shifted, real part
 int gen_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx, int remove_mean, int normalize_peak,
                 float* out) {
@@ -1776,6 +1845,7 @@ int gen_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, i
 void b4d_fft_release(b4d_ctx* ctx) {
     if (!ctx->fft) return;
     gen_release(static_cast<GenCache*>(ctx->fft->gen));
+    if (ctx->fft->gref) cudaFree(ctx->fft->gref);
     for (int i = 0; i < 6; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
     if (ctx->fft->ref) cudaFree(ctx->fft->ref);
     if (ctx->fft->ref_nyq) cudaFree(ctx->fft->ref_nyq);
@@ -1981,10 +2051,14 @@ extern "C" int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, in
                                        double eps) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
-    int rc = check_fft_args(ctx, "b4d_phase_set_reference", tpl, 1, ny, nx);
-    if (rc) return rc;
     if (h < 1 || w < 1 || y0 < 0 || x0 < 0 || y0 + h > ny || x0 + w > nx)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_set_reference: template does not fit the frame");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_phase_set_reference", tpl, 1, ny, nx);
+        return rcg ? rcg : gen_phase_set_reference(ctx, tpl, h, w, ny, nx, y0, x0, eps);
+    }
+    int rc = check_fft_args(ctx, "b4d_phase_set_reference", tpl, 1, ny, nx);
+    if (rc) return rc;
     if (!ctx->fft) ctx->fft = new FftPlanCache();
     FftPlanCache* f = ctx->fft;
     if (f->ref_ny != ny || f->ref_nx != nx) {
@@ -2109,9 +2183,16 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
                                double* out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
+    if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_phase_track", stack, n_frames, ny, nx);
+        if (rcg) return rcg;
+        if (!ctx->fft || !ctx->fft->gref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx || ctx->fft->gref_elems != (size_t)ny * nx)
+            return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: call b4d_phase_set_reference for (%d, %d) frames first", ny, nx);
+        return gen_phase_track(ctx, stack, n_frames, ny, nx, subpixel, eps, out);
+    }
     int rc = check_fft_args(ctx, "b4d_phase_track", stack, n_frames, ny, nx);
     if (rc) return rc;
-    if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
     if (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: call b4d_phase_set_reference for (%d, %d) frames first", ny, nx);
     const int64_t B = batch_frames(ctx, ny, nx, 4);

@@ -278,7 +278,7 @@ class PhaseTracker:
     def __init__(self, template, frame_shape, *, y0: int, x0: int, eps: float = 1e-9, device: int | None = None):
         self.dev = _lib.default_device() if device is None else int(device)
         self.ny, self.nx = int(frame_shape[0]), int(frame_shape[1])
-        check_fft_shape(self.ny, self.nx)
+        check_fft_shape(self.ny, self.nx, generic_ok=True)     # sides that are not powers of two: map-based chirp-z path
         tpl = _lib.as_device_f32(template, self.dev)
         if tpl.ndim != 2:
             raise ValueError("template must be a 2D array.")

@@ -102,9 +102,7 @@ def test_unsupported_sizes_fail_loudly(sig):
         sig.psd2d(np.zeros((16, 2050), np.float32))                   # sides above 2048 are not built
     odd = gc.frame_cases()["odd150x200"]
     with pytest.raises(B4DUnsupported):
-        sig.phase_correlation(odd, odd, slices_yx=(slice(0, 150), slice(0, 200)))   # tracking: powers of two only
-    with pytest.raises(B4DUnsupported):
-        sig.template_matching(odd[:21, :21], odd)
+        sig.template_matching(odd[:21, :21], odd)                     # template matching: powers of two only
     with pytest.raises(ValueError):
         sig.psd2d(np.zeros((4, 4, 4), np.float32))
     with pytest.raises(ValueError):
@@ -431,3 +429,24 @@ def test_ifft2d_round_trip_and_vs_numpy(sig, shape):
     assert np.max(np.abs(got - want)) <= 1e-5 * float(np.abs(want).max())
     with pytest.raises(ValueError):
         sig.ifft2d(np.zeros((2, 4, 4), np.complex64))
+
+
+@pytest.mark.parametrize("shape", [(150, 200), (500, 333)])
+def test_phase_correlation_arbitrary_sides_vs_oracle(sig, shape):
+    """Phase correlation on frames that are not powers of two (chirp-z transforms, |corr| map, exact median): full-frame
+    and ROI templates against the oracle, same tolerances as the power-of-two tracker."""
+    from barc4dip_b200 import synth
+    ny, nx = shape
+    base = synth.speckle_frame(512, grain=4.0, seed=43)[:ny, :nx].copy()
+    rng = np.random.default_rng(44)
+    noise = lambda: (0.02 * float(base.mean()) * rng.standard_normal((ny, nx))).astype(np.float32)
+    ref = base + noise()
+    img = np.roll(base, (3, -4), axis=(0, 1)) + noise()
+    full = (slice(0, ny), slice(0, nx))
+    for tpl, sl in ((ref, full), (ref[20:121, 30:131], (slice(20, 121), slice(30, 131)))):
+        got = sig.phase_correlation(tpl, img, slices_yx=sl)
+        want = orc.phase_correlation(tpl, img, slices_yx=sl)
+        np.testing.assert_allclose(got[:2], want[:2], rtol=0, atol=0.01)
+        np.testing.assert_allclose(got[2], want[2], rtol=5e-4)
+        np.testing.assert_allclose(got[3], want[3], rtol=2e-3)
+    np.testing.assert_allclose(sig.phase_correlation(ref, img, slices_yx=full)[:2], (3.0, -4.0), atol=0.05)
