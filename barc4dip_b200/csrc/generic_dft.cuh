@@ -296,6 +296,16 @@ __global__ void __launch_bounds__(256) gen_phase_product_kernel(float2* __restri
     }
 }
 
+// A <- A * Rc (Rc: conjugate template spectra, one for all frames (r_stride 0) or one per frame)
+__global__ void __launch_bounds__(256) gen_mul_kernel(float2* __restrict__ A, const float2* __restrict__ Rc, size_t r_stride, int64_t npix) {
+    const int64_t t = blockIdx.y;
+    const float2* r = Rc + (size_t)t * r_stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 f = A[(size_t)t * npix + i], q = r[i];
+        A[(size_t)t * npix + i] = make_float2(f.x * q.x - f.y * q.y, f.x * q.y + f.y * q.x);
+    }
+}
+
 // conj in place (the template spectrum is stored conjugated)
 __global__ void __launch_bounds__(256) gen_conj_kernel(float2* __restrict__ A, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) A[i].y = -A[i].y;

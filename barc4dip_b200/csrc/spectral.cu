@@ -1701,6 +1701,89 @@ int gen_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, 
     return B4D_OK;
 }
 
+// template_matching for frame sides that are not powers of two: same steps as b4d_template_match with the chirp-z
+// transforms in place of the FFT kernels (numerator on the mean-removed frame, window sums on the pilot-shifted one;
+// the quotient depends on neither offset)
+int gen_template_match(b4d_ctx* ctx, const float* tpl, int per_frame, int h, int w, const float* stack, int64_t n_frames, int ny, int nx,
+                       double ref_y, double ref_x, int subpixel, double eps, double* out) {
+    const size_t npix = (size_t)ny * nx;
+    const int oy = ny - h + 1, ox = nx - w + 1;
+    const size_t nres = (size_t)oy * ox;
+    int64_t B = ((int64_t)1024 << 20) / (int64_t)(npix * (per_frame ? 48 : 40));
+    if (B < 1) B = 1;
+    if (B > n_frames) B = n_frames;
+    const int64_t nt = per_frame ? B : 1;
+    int rc;
+    void* p = nullptr;
+    if ((rc = b4d_scratch(ctx, SCR_SPEC_C, sizeof(float2) * npix * nt + sizeof(double) * B4D_FR_NCOLS * nt + 256, &p))) return rc;
+    float2* tref = static_cast<float2*>(p);
+    double* tfr = reinterpret_cast<double*>(tref + npix * nt);
+    if ((rc = b4d_scratch(ctx, SCR_MAP, sizeof(float) * (npix + nres) * B + sizeof(double) * 2 * npix * B +
+                          (sizeof(float) * 3 + sizeof(long long)) * B + 1024, &p))) return rc;
+    float* corr = static_cast<float*>(p);
+    float* res = corr + npix * B;
+    double* P1 = reinterpret_cast<double*>(res + ((nres * B + 1) & ~size_t(1)));
+    double* P2 = P1 + npix * B;
+    float* pilot = reinterpret_cast<float*>(P2 + npix * B);
+    float* med = pilot + ((B + 1) & ~int64_t(1));
+    long long* nvalid = reinterpret_cast<long long*>(med + 2 * B);
+    auto template_spectra = [&](const float* tp, int64_t count) -> int {
+        int r = b4d_frame_reductions_nolock(ctx, tp, count, h, w, nullptr, nullptr, nan(""), 0.0, tfr);
+        if (r) return r;
+        embed_template_kernel<<<dim3(ctx->sm_count * 2, (unsigned)count), 256, 0, ctx->stream>>>(tp, h, w, ny, nx, 0, 0, (float)eps, tfr, corr);
+        B4D_LAUNCH_CHECK(ctx);
+        GenWork gw;
+        if ((r = gen_carve(ctx, count, ny, nx, &gw))) return r;
+        if ((r = gen_forward(ctx, gen_cache(ctx), corr, nullptr, count, ny, nx, gw.A, gw.Bf))) return r;
+        gen_conj_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(gw.A, (int64_t)(npix * count));
+        B4D_LAUNCH_CHECK(ctx);
+        B4D_CUDA(ctx, cudaMemcpyAsync(tref, gw.A, sizeof(float2) * npix * count, cudaMemcpyDeviceToDevice, ctx->stream));
+        return B4D_OK;
+    };
+    if (!per_frame && (rc = template_spectra(tpl, 1))) return rc;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + t0 * npix;
+        if (per_frame && (rc = template_spectra(tpl + (size_t)t0 * h * w, tc))) return rc;
+        GenWork gw;
+        if ((rc = gen_carve(ctx, tc, ny, nx, &gw))) return rc;
+        if ((rc = b4d_frame_reductions_nolock(ctx, s0, tc, ny, nx, nullptr, nullptr, nan(""), 0.0, gw.fr))) return rc;
+        if ((rc = gen_forward(ctx, gen_cache(ctx), s0, gw.fr, tc, ny, nx, gw.A, gw.Bf))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_mul_kernel<<<dim3(gw.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(gw.A, tref, per_frame ? npix : 0, (int64_t)npix);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        if ((rc = gen_inverse(ctx, gen_cache(ctx), tc, ny, nx, gw.A, gw.Bf))) return rc;
+        if ((rc = b4d_frame_pilot_launch(ctx, s0, tc, (int64_t)npix, nullptr, nullptr, pilot))) return rc;
+        {
+            ProfScope ps(ctx, KC_GENERIC);
+            gen_shift_out_kernel<<<dim3(gw.nblk, (unsigned)tc), 256, 0, ctx->stream>>>(gw.A, ny, nx, (float)(1.0 / ((double)nx * (double)ny)), 0, corr);
+            B4D_LAUNCH_CHECK(ctx);
+            const int64_t rows = tc * ny;
+            tm_scan_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(s0, pilot, ny, nx, P1, P2, rows);
+            B4D_LAUNCH_CHECK(ctx);
+            tm_scan_cols_kernel<<<dim3((nx + 255) / 256, (unsigned)tc), 256, 0, ctx->stream>>>(P1, P2, ny, nx);
+            B4D_LAUNCH_CHECK(ctx);
+            int bx = (int)((nres + 2047) / 2048);
+            if (bx > 592) bx = 592;
+            tm_normalise_kernel<<<dim3(bx, (unsigned)tc), 256, 0, ctx->stream>>>(corr, P1, P2, ny, nx, h, w, tfr, per_frame ? B4D_FR_NCOLS : 0, eps, res);
+            B4D_LAUNCH_CHECK(ctx);
+            gen_argmax_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(res, (int64_t)nres, gw.pk);
+            B4D_LAUNCH_CHECK(ctx);
+        }
+        void* q = nullptr;
+        if ((rc = b4d_scratch(ctx, SCR_MISC, 1024, &q))) return rc;
+        static const double half_q = 0.5;
+        if ((rc = b4d_put_doubles(ctx, static_cast<double*>(q), &half_q, 1))) return rc;
+        if ((rc = b4d_select_impl(ctx, res, tc, (int64_t)nres, static_cast<const double*>(q), 1, 1, med, reinterpret_cast<int64_t*>(nvalid)))) return rc;
+        tm_finalize_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(res, gw.pk, oy, ox, h, w, ref_y, ref_x, med, nvalid, subpixel, eps,
+                                                                               out + t0 * 4, tc);
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
 // xcorr2d for frame sides that are not powers of two: ifft2(fft2(a) conj(fft2(b))), shifted, real part
 int gen_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, int ny, int nx, int remove_mean, int normalize_peak,
                 float* out) {
@@ -2329,10 +2412,14 @@ extern "C" int b4d_template_match(b4d_ctx* ctx, const float* tpl, int per_frame,
                                   int ny, int nx, double ref_y, double ref_x, int subpixel, double eps, double* out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
-    int rc = check_fft_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
-    if (rc) return rc;
     if (!tpl || !out || h < 1 || w < 1 || h > ny || w > nx)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_template_match: template shape (%d, %d) must fit inside image shape (%d, %d)", h, w, ny, nx);
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
+        return rcg ? rcg : gen_template_match(ctx, tpl, per_frame, h, w, stack, n_frames, ny, nx, ref_y, ref_x, subpixel, eps, out);
+    }
+    int rc = check_fft_args(ctx, "b4d_template_match", stack, n_frames, ny, nx);
+    if (rc) return rc;
     const size_t npix = (size_t)ny * nx, half = (size_t)ny * (nx / 2);
     const int oy = ny - h + 1, ox = nx - w + 1;
     const size_t nres = (size_t)oy * ox;

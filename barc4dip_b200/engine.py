@@ -309,7 +309,7 @@ def template_match(template, stack, *, ref_center_yx, subpixel: bool = True, eps
     (T, h, w) template stack frame by frame (b4d_template_match). ref_center_yx: centre of the template's reference position. -> (T, 4) = dy, dx, peak, snr."""
     torch = require_cuda()
     T, ny, nx = stack.shape
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     tpl = as_stack(template, _dev(stack)).contiguous()
     per_frame = tpl.shape[0] != 1 or getattr(template, "ndim", 2) == 3
     if per_frame and tpl.shape[0] != T:

@@ -102,7 +102,7 @@ def test_unsupported_sizes_fail_loudly(sig):
         sig.psd2d(np.zeros((16, 2050), np.float32))                   # sides above 2048 are not built
     odd = gc.frame_cases()["odd150x200"]
     with pytest.raises(B4DUnsupported):
-        sig.template_matching(odd[:21, :21], odd)                     # template matching: powers of two only
+        sig.template_matching(odd[:21, :21], np.zeros((64, 2100), np.float32))
     with pytest.raises(ValueError):
         sig.psd2d(np.zeros((4, 4, 4), np.float32))
     with pytest.raises(ValueError):
@@ -450,3 +450,28 @@ def test_phase_correlation_arbitrary_sides_vs_oracle(sig, shape):
         np.testing.assert_allclose(got[2], want[2], rtol=5e-4)
         np.testing.assert_allclose(got[3], want[3], rtol=2e-3)
     np.testing.assert_allclose(sig.phase_correlation(ref, img, slices_yx=full)[:2], (3.0, -4.0), atol=0.05)
+
+
+def test_template_matching_arbitrary_sides_vs_oracle(sig):
+    """Template matching on a 300 x 450 frame (chirp-z path) against the oracle's restatement of cv2's TM_CCOEFF_NORMED,
+    one template for a stack and one template per frame."""
+    from barc4dip_b200 import engine, synth
+    ny, nx = 300, 450
+    base = synth.speckle_frame(512, grain=4.0, seed=47)[:ny, :nx].copy()
+    rng = np.random.default_rng(48)
+    frames = np.stack([np.roll(base, s, axis=(0, 1)) + (0.02 * float(base.mean()) * rng.standard_normal((ny, nx))).astype(np.float32)
+                       for s in ((0, 0), (2, -3), (-4, 5))])
+    sl = (slice(120, 151), slice(200, 227))                      # 31 x 27 ROI
+    centre = ((sl[0].start + sl[0].stop - 1) / 2.0, (sl[1].start + sl[1].stop - 1) / 2.0)
+    tab = engine.template_match(frames[0][sl], engine.as_stack(frames), ref_center_yx=centre)
+    for t in range(3):
+        want = orc.template_matching(frames[0][sl], frames[t], slices_yx=sl)
+        np.testing.assert_allclose(tab[t, :2], want[:2], rtol=0, atol=0.01)
+        np.testing.assert_allclose(tab[t, 2], want[2], rtol=1e-4)
+        np.testing.assert_allclose(tab[t, 3], want[3], rtol=2e-3)
+    prev = np.stack([frames[0][sl], frames[0][sl], frames[1][sl]])
+    inc = engine.template_match(prev, engine.as_stack(frames), ref_center_yx=centre)
+    want = orc.template_matching(frames[1][sl], frames[2], slices_yx=sl)
+    np.testing.assert_allclose(inc[2, :2], want[:2], rtol=0, atol=0.01)
+    got = sig.template_matching(frames[0][sl], frames[1], slices_yx=sl)
+    np.testing.assert_allclose(got[:2], tab[1, :2], atol=1e-9)
