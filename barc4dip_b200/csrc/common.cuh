@@ -86,7 +86,7 @@ struct ProfScope {
 };
 
 // scratch slot ids
-enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7, SCR_NYQ = 8 };
+enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7, SCR_NYQ = 8, SCR_GEN = 9 };
 
 inline int b4d_fail(b4d_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {

@@ -306,6 +306,14 @@ __global__ void __launch_bounds__(256) gen_mul_kernel(float2* __restrict__ A, co
     }
 }
 
+// out = (raw - dark) * gain, the per-pixel affine map of the fused loaders, materialised (generic pipeline only)
+__global__ void __launch_bounds__(256) gen_apply_gain_kernel(const float* __restrict__ raw, const float* __restrict__ gain,
+                                                              const float* __restrict__ dark, int64_t npix, float* __restrict__ out) {
+    const int64_t t = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x)
+        out[(size_t)t * npix + i] = (raw[(size_t)t * npix + i] - (dark ? dark[i] : 0.f)) * gain[i];
+}
+
 // conj in place (the template spectrum is stored conjugated)
 __global__ void __launch_bounds__(256) gen_conj_kernel(float2* __restrict__ A, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) A[i].y = -A[i].y;

@@ -1923,6 +1923,52 @@ int gen_autocorr2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, i
     return B4D_OK;
 }
 
+// The stack pipeline for frame sides that are not powers of two: the same outputs, composed from the stand-alone
+// chirp-z paths (three forward transforms per frame instead of one shared; this is the compatibility path, the fused
+// kernels above are the hot one).
+int gen_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain, const float* dark,
+                       double sat_value, double zero_eps, float psd_scale, int subpixel, double eps, double q_lo, double q_hi,
+                       double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out,
+                       double* track_out) {
+    const size_t npix = (size_t)ny * nx;
+    int rc;
+    int64_t B = ((int64_t)1024 << 20) / (int64_t)(npix * 4);
+    if (B < 1) B = 1;
+    if (B > 32768) B = 32768;
+    if (!gain) B = n_frames;                            // nothing to materialise: the sub-paths batch on their own
+    for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
+        const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
+        const float* s0 = stack + t0 * npix;
+        if (gain) {
+            void* p = nullptr;
+            if ((rc = b4d_scratch(ctx, SCR_GEN, sizeof(float) * npix * tc, &p))) return rc;
+            int bx = (int)((npix + 2047) / 2048);
+            if (bx > 592) bx = 592;
+            gen_apply_gain_kernel<<<dim3(bx, (unsigned)tc), 256, 0, ctx->stream>>>(s0, gain, dark, (int64_t)npix, static_cast<float*>(p));
+            B4D_LAUNCH_CHECK(ctx);
+            s0 = static_cast<const float*>(p);
+        }
+        if (fr_out || quant_out) {
+            double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : nullptr;
+            if (!frp) {
+                void* p = nullptr;
+                if ((rc = b4d_scratch(ctx, SCR_SPEC_C, sizeof(double) * B4D_FR_NCOLS * tc, &p))) return rc;
+                frp = static_cast<double*>(p);
+            }
+            FrTails tl = {q_lo, q_hi, quant_out ? quant_out + 4 * t0 : nullptr, quant_out ? nvalid_out + t0 : nullptr};
+            if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, nullptr, nullptr, sat_value, zero_eps, frp, quant_out ? &tl : nullptr, nullptr)))
+                return rc;
+        }
+        if (psd_out && (rc = gen_psd2d(ctx, s0, tc, ny, nx, psd_scale, 0, 0, psd_out + t0 * npix, nullptr))) return rc;
+        if ((ac_out || grain_out) &&
+            (rc = gen_autocorr2d(ctx, s0, tc, ny, nx, 1, 1.0, 1, ac_out ? ac_out + t0 * npix : nullptr, 0.36787944117144233,
+                                 grain_out ? grain_out + t0 * 4 : nullptr)))
+            return rc;
+        if (track_out && (rc = gen_phase_track(ctx, s0, tc, ny, nx, subpixel, eps, track_out + t0 * 4))) return rc;
+    }
+    return B4D_OK;
+}
+
 }  // namespace
 
 void b4d_fft_release(b4d_ctx* ctx) {
@@ -2319,12 +2365,20 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
                                   int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
-    int rc = check_fft_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
-    if (rc) return rc;
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
     if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: grain widths need square frames");
     if (quant_out && (!nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0)))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tail percentiles need 0 <= q_lo < q_hi <= 1 and nvalid_out");
+    if (!pow2_sides(ny, nx)) {
+        int rcg = check_gen_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
+        if (rcg) return rcg;
+        if (track_out && (!ctx->fft || !ctx->fft->gref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx))
+            return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tracking needs b4d_phase_set_reference for (%d, %d) frames", ny, nx);
+        return gen_stack_pipeline(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
+                                  fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out);
+    }
+    int rc = check_fft_args(ctx, "b4d_stack_pipeline", stack, n_frames, ny, nx);
+    if (rc) return rc;
     const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
     if (want_pc && (!ctx->fft || !ctx->fft->ref || ctx->fft->ref_ny != ny || ctx->fft->ref_nx != nx))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: tracking needs b4d_phase_set_reference for (%d, %d) frames", ny, nx);

@@ -364,7 +364,7 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
     """
     torch = require_cuda()
     T, ny, nx = stack.shape
-    check_fft_shape(ny, nx)
+    check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(stack))
     dev = stack.device
     fr = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=dev) if want_reductions else None

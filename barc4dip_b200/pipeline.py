@@ -33,7 +33,7 @@ class StackAnalyzer:
         from ._lib import default_device
         self.dev = default_device() if device is None else int(device)
         self.ny, self.nx = int(frame_shape[0]), int(frame_shape[1])
-        engine.check_fft_shape(self.ny, self.nx)
+        engine.check_fft_shape(self.ny, self.nx, generic_ok=True)
         self.chunk = int(chunk_frames)
         self.want_maps, self.want_contrast = bool(want_maps), bool(want_contrast)
         self.sat, self.eps, self.subpixel = saturation_value, float(eps), bool(subpixel)

@@ -175,11 +175,11 @@ int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, 
 
 /* ---- 2-D FFT family ---------------------------------------------------------------------- */
 /*
- * Frame sizes. Powers of two in [B4D_FFT_MIN, B4D_FFT_MAX] run the hot-path kernels (every entry point below).
- * b4d_fft2d, b4d_ifft2d, b4d_psd2d, b4d_autocorr2d and b4d_xcorr2d also accept ANY sides in [2, B4D_FFT_MAX] (the 227 / 228-pixel sub-tiles of
- * the reference's tiling executor, metrics/common.py:278-378): those go through Bluestein's algorithm on the same FFT
- * core (csrc/generic_dft.cuh). Tracking, template matching and the fused pipeline are built for powers of two only.
- * Anything else returns B4D_ERR_UNSUPPORTED (the Python layer raises; there is no CPU fallback).
+ * Frame sizes. Powers of two in [B4D_FFT_MIN, B4D_FFT_MAX] run the hot-path kernels. Every entry point below also accepts
+ * ANY sides in [2, B4D_FFT_MAX] (the 227 / 228-pixel sub-tiles of the reference's tiling executor, metrics/common.py:278-378,
+ * detectors that are not 2^k wide): those go through Bluestein's algorithm on the same FFT core (csrc/generic_dft.cuh),
+ * with the stack pipeline composed from the stand-alone paths. Larger sides return B4D_ERR_UNSUPPORTED (the Python layer
+ * raises; there is no CPU fallback).
  */
 #define B4D_FFT_MIN 128
 #define B4D_FFT_MAX 2048

@@ -337,3 +337,36 @@ def test_one_process_two_devices():
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
         np.testing.assert_array_equal(o[2], outs[0][2])
+
+
+def test_stack_analyzer_arbitrary_frame_size_vs_oracle():
+    """StackAnalyzer on 300 x 300 frames (not a power of two: the composed chirp-z pipeline), with a flat field fused
+    into the loads: every table and map against the oracle evaluated on the corrected frames."""
+    from barc4dip_b200 import synth
+    from barc4dip_b200.pipeline import StackAnalyzer
+    n, T = 300, 4
+    stack, _ = synth.tracking_stack(T, 512, grain=5.0, seed=53, integer_every=2)
+    stack = np.ascontiguousarray(stack[:, :n, :n])
+    rng = np.random.default_rng(54)
+    flat = (1000.0 * (1.0 + 0.1 * rng.random((n, n)))).astype(np.float32)
+    dark = (100.0 + 2.0 * rng.standard_normal((n, n))).astype(np.float32)
+    raw = (stack / 1000.0 * (flat - dark) + dark).astype(np.float32)
+    corrected = orc.flat_field_correction(raw, flat, dark)
+    an = StackAnalyzer((n, n), reference=raw[0], flats=flat, darks=dark, chunk_frames=3)
+    out = an.run(raw)
+    for t in range(T):
+        m = orc.distribution_moments(corrected[t])
+        for k in ("mean", "std", "skewness", "kurtosis"):
+            np.testing.assert_allclose(out["stats"][k][t], m[k], rtol=RTOL, err_msg=k)
+        np.testing.assert_allclose(out["gradient"]["tenengrad"][t], orc.tenengrad(corrected[t])["tenengrad"], rtol=RTOL)
+        np.testing.assert_allclose(out["amplitude"]["contrast"][t], orc.amplitude(corrected[t])["contrast"], rtol=RTOL)
+        P, _, _ = orc.psd2d(corrected[t])
+        assert np.max(np.abs(out["psd"][t] - P)) <= 1e-5 * P.max()
+        g = orc.grain(corrected[t])
+        assert np.max(np.abs(out["autocorr"][t] - g["autocorr"])) <= 1e-5
+        for k in ("lx", "ly", "leq"):
+            np.testing.assert_allclose(out["grain"][k][t], g[k], rtol=RTOL, err_msg=k)
+        dy, dx, peak, snr = orc.phase_correlation(corrected[0], corrected[t], slices_yx=(slice(0, n), slice(0, n)))
+        np.testing.assert_allclose((out["tracking"]["dy"][t], out["tracking"]["dx"][t]), (dy, dx), atol=0.01)
+        if t:
+            np.testing.assert_allclose(out["tracking"]["peak"][t], peak, rtol=5e-4)
