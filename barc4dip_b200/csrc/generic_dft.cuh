@@ -22,7 +22,7 @@ struct GenCache {
     std::vector<GenPlan> plans;
 };
 
-inline bool gen_size_ok(int n) { return n >= 2 && n <= 2048; }
+inline bool gen_size_ok(int n) { return n >= 1 && n <= 2048; }   // 1: the 1-D signals of signal/fft.py, corr.py as (1, n) frames
 inline int gen_conv_len(int n) { return n <= 256 ? 512 : (n <= 512 ? 1024 : (n <= 1024 ? 2048 : 4096)); }
 
 // iterative radix-2 FFT in double precision (host; tables only)

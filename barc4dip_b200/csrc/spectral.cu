@@ -1565,7 +1565,7 @@ int check_gen_args(b4d_ctx* ctx, const char* who, const void* stack, int64_t T, 
     if (!stack || T < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "%s: bad arguments", who);
     if (!gen_size_ok(ny) || !gen_size_ok(nx) || T > ((int64_t)1 << 24))
         return b4d_fail(ctx, B4D_ERR_UNSUPPORTED,
-                        "%s: frames need sides in [2, 2048]; got T=%lld (ny, nx)=(%d, %d)",
+                        "%s: frames need sides in [1, 2048]; got T=%lld (ny, nx)=(%d, %d)",
                         who, (long long)T, ny, nx);
     return B4D_OK;
 }

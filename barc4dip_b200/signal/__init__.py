@@ -1,14 +1,13 @@
 """
 Drop-in for ``barc4dip.signal`` on the B200 path: same public names, served by the CUDA library (``csrc/spectral.cu``,
-``csrc/generic_dft.cuh``) through ``engine``. The 1-D helpers of the reference (fft1d, psd1d, xcorr1d, autocorr1d) are not
-part of the stack-analysis hot path and are not provided.
+``csrc/generic_dft.cuh``) through ``engine``. The 1-D helpers run the same kernels on (1, n) frames.
 """
 
 from . import corr, fft, tracking
 
 _EXPORTS = {
-    fft: ("freq_axes2d", "fft2d", "ifft2d", "psd2d"),
-    corr: ("xcorr2d", "autocorr2d"),
+    fft: ("freq_axis1d", "freq_axes2d", "fft1d", "ifft1d", "psd1d", "fft2d", "ifft2d", "psd2d"),
+    corr: ("xcorr1d", "autocorr1d", "xcorr2d", "autocorr2d"),
     tracking: ("track_translation", "phase_correlation", "template_matching"),
 }
 for _module, _names in _EXPORTS.items():

@@ -54,6 +54,29 @@ def resolve_steps_2d(*, shape, x, y, dx: float, dy: float) -> tuple[float, float
     return step_of_axis(axes[0], "x"), step_of_axis(axes[1], "y")
 
 
+def resolve_step_1d(*, n: int, x, dx: float, name: str = "x") -> float:
+    """Step of a 1-D signal of length n, from dx or from a uniformly sampled axis (never both)."""
+    if x is None:
+        if dx <= 0:
+            raise ValueError(f"d{name} must be > 0.")
+        return float(dx)
+    if dx != 1.0:
+        raise ValueError(f"Provide either {name} or d{name}, not both.")
+    axis = np.asarray(x, dtype=float)
+    if axis.ndim != 1:
+        raise ValueError(f"{name} must be a 1D array.")
+    if axis.size != n:
+        raise ValueError(f"{name}.size must match the signal length ({n}).")
+    return step_of_axis(axis, name)
+
+
+def freq_axis1d(*, n: int, x=None, dx: float = 1.0) -> np.ndarray:
+    """Shifted frequency axis of a 1-D signal, cycles per unit."""
+    if n < 1:
+        raise ValueError("n must be >= 1.")
+    return np.fft.fftshift(np.fft.fftfreq(int(n), d=resolve_step_1d(n=n, x=x, dx=dx)))
+
+
 def freq_axes2d(*, shape, x=None, y=None, dx: float = 1.0, dy: float = 1.0):
     ny, nx = shape
     if ny < 1 or nx < 1:

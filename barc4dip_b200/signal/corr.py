@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import engine
-from .common import lag_axis, resolve_steps_2d
+from .common import lag_axis, resolve_step_1d, resolve_steps_2d
 
 
 def _check_norm(normalize: str):
@@ -46,3 +46,25 @@ def autocorr2d(a, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0, remove_me
     ac, _ = engine.autocorr2d(engine.as_stack(aa), remove_mean=remove_mean, standardize=standardize,
                               normalize_peak=normalize == "peak")
     return ac[0].cpu().numpy().astype(np.float64), lag_axis(nx, sx), lag_axis(ny, sy)
+
+
+# ---- 1-D signals: the same kernels on (1, n) frames (signal/corr.py:45-166 of the reference) -----------------------------
+
+def xcorr1d(a, b, *, x=None, dx: float = 1.0, remove_mean: bool = True, standardize: bool = False, normalize: str = "peak"):
+    """Circular cross-correlation of two 1-D signals, zero lag at n // 2; (corr, xlag)."""
+    aa, bb = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if aa.ndim != 1 or bb.ndim != 1:
+        raise ValueError("a and b must be 1D arrays.")
+    if aa.size != bb.size:
+        raise ValueError("a and b must have the same length.")
+    n = int(aa.size)
+    xlag = lag_axis(n, resolve_step_1d(n=n, x=x, dx=dx))
+    _check_norm(normalize)
+    c = engine.xcorr2d(engine.as_stack(aa[None, :]), engine.as_stack(bb[None, :]), remove_mean=remove_mean,
+                       standardize=standardize, normalize_peak=normalize == "peak")
+    return c[0, 0].cpu().numpy().astype(np.float64), xlag
+
+
+def autocorr1d(a, *, x=None, dx: float = 1.0, remove_mean: bool = True, standardize: bool = False, normalize: str = "peak"):
+    """Circular auto-correlation of a 1-D signal; (corr, xlag)."""
+    return xcorr1d(a, a, x=x, dx=dx, remove_mean=remove_mean, standardize=standardize, normalize=normalize)

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import engine
-from .common import freq_axes2d, resolve_steps_2d
+from .common import freq_axes2d, freq_axis1d, resolve_step_1d, resolve_steps_2d
 
 
 def _out_real_dtype(img: np.ndarray):
@@ -53,3 +53,35 @@ def psd2d(image, *, x=None, y=None, dx: float = 1.0, dy: float = 1.0, scale: boo
     factor = (sx * sy) / (float(nx) * float(ny)) if scale else 1.0
     P, _ = engine.psd2d(engine.as_stack(img), scale_factor=factor)
     return P[0].cpu().numpy().astype(_out_real_dtype(img), copy=False), fx, fy
+
+
+# ---- 1-D signals: the same kernels on (1, n) frames (signal/fft.py:31-196 of the reference) ------------------------------
+
+def _signal1d(signal, name: str = "signal") -> np.ndarray:
+    s = np.asarray(signal)
+    if s.ndim != 1:
+        raise ValueError(f"{name} must be a 1D array.")
+    return s
+
+
+def fft1d(signal, *, x=None, dx: float = 1.0):
+    """fftshift(fft(signal)) and the shifted frequency axis."""
+    s = _signal1d(signal)
+    fx = freq_axis1d(n=int(s.size), x=x, dx=dx)
+    F, _, _ = fft2d(s[None, :])
+    return F[0], fx
+
+
+def ifft1d(F):
+    """ifft(ifftshift(F)) of a shifted 1-D spectrum."""
+    return ifft2d(_signal1d(F, "F")[None, :])[0]
+
+
+def psd1d(signal, *, x=None, dx: float = 1.0, scale: bool = True):
+    """|fft1d(signal)|^2, times dx / n when scale is True."""
+    s = _signal1d(signal)
+    n = int(s.size)
+    step = resolve_step_1d(n=n, x=x, dx=dx)
+    fx = freq_axis1d(n=n, x=x, dx=dx)
+    P, _ = engine.psd2d(engine.as_stack(s[None, :]), scale_factor=(step / float(n)) if scale else 1.0)
+    return P[0, 0].cpu().numpy().astype(_out_real_dtype(s), copy=False), fx

@@ -146,3 +146,11 @@ def stack_tracking_case() -> np.ndarray:
     """4 frames of 256^2 drifting by a random walk (speckle_stack_stats, template tracker on the 3x3 ROI grid)."""
     stack, _ = synth.tracking_stack(4, 256, grain=8.0, seed=51, step_sigma=0.8)
     return stack
+
+
+def signal1d_cases() -> dict[str, np.ndarray]:
+    """1-D signals for fft1d / psd1d / xcorr1d / autocorr1d: a power-of-two length and one that is not."""
+    rng = np.random.default_rng(71)
+    t = np.arange(1024)
+    a = (np.sin(2 * np.pi * t / 37.0) + 0.3 * rng.standard_normal(1024) + 2.0).astype(np.float32)
+    return {"n1024": a, "n300": a[100:400].copy()}

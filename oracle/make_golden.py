@@ -44,6 +44,26 @@ def map_digest(a, prefix, store):
     store[prefix + "_sumabs2"] = np.asarray((np.abs(a) ** 2).sum())
 
 
+def signal1d_golden(sig, versions):
+    """signal1d.npz: the reference's 1-D helpers (signal/fft.py:31-196, signal/corr.py:45-166)."""
+    store = {"versions": versions}
+    for name, a in gc.signal1d_cases().items():
+        F, fx = sig.fft.fft1d(a, dx=0.5)
+        store[f"{name}/fft"], store[f"{name}/fx"] = F, fx
+        store[f"{name}/ifft"] = sig.fft.ifft1d(F)
+        P, _ = sig.fft.psd1d(a, dx=0.5)
+        store[f"{name}/psd"] = P
+        b = np.roll(a, 7)
+        c, lag = sig.corr.xcorr1d(a, b, dx=0.5)
+        store[f"{name}/xcorr"], store[f"{name}/lag"] = np.real(c), lag
+        c2, _ = sig.corr.autocorr1d(a)
+        store[f"{name}/autocorr"] = np.real(c2)
+        c3, _ = sig.corr.autocorr1d(a, remove_mean=False, normalize="none")
+        store[f"{name}/autocorr_raw"] = np.real(c3)
+    np.savez_compressed(os.path.join(OUT, "signal1d.npz"), **store)
+    print("signal1d.npz", os.path.getsize(os.path.join(OUT, "signal1d.npz")) // 1024, "KiB")
+
+
 def template_golden(sig, versions):
     """template.npz: template_matching(backend="opencv") of the reference (cv2.matchTemplate TM_CCOEFF_NORMED)."""
     import cv2
@@ -114,6 +134,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     import scipy
     versions = np.array([np.__version__, scipy.__version__])
+    if "--only-1d" in sys.argv:
+        signal1d_golden(sig, versions)
+        return
     if "--only-template" in sys.argv:
         template_golden(sig, versions)
         return
@@ -245,6 +268,7 @@ def main():
     tiles_golden(met, versions)
     repair_golden(pre, versions)
     template_golden(sig, versions)
+    signal1d_golden(sig, versions)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

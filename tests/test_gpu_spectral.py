@@ -475,3 +475,29 @@ def test_template_matching_arbitrary_sides_vs_oracle(sig):
     np.testing.assert_allclose(inc[2, :2], want[:2], rtol=0, atol=0.01)
     got = sig.template_matching(frames[0][sl], frames[1], slices_yx=sl)
     np.testing.assert_allclose(got[:2], tab[1, :2], atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["n1024", "n300"])
+def test_signal_1d_family_vs_golden(sig, golden, name):
+    """fft1d / ifft1d / psd1d / xcorr1d / autocorr1d (the 2-D kernels on (1, n) frames) against the reference's outputs."""
+    g = golden("signal1d")
+    a = gc.signal1d_cases()[name]
+    F, fx = sig.fft1d(a, dx=0.5)
+    np.testing.assert_allclose(fx, g[f"{name}/fx"])
+    peak = float(np.abs(g[f"{name}/fft"]).max())
+    assert np.max(np.abs(F - g[f"{name}/fft"])) <= 1e-6 * peak
+    back = sig.ifft1d(F)
+    assert np.max(np.abs(back - g[f"{name}/ifft"])) <= 1e-5 * float(np.abs(a).max())
+    P, _ = sig.psd1d(a, dx=0.5)
+    assert P.dtype == g[f"{name}/psd"].dtype and np.max(np.abs(P - g[f"{name}/psd"])) <= PEAK_TOL * float(g[f"{name}/psd"].max())
+    c, lag = sig.xcorr1d(a, np.roll(a, 7), dx=0.5)
+    np.testing.assert_allclose(lag, g[f"{name}/lag"])
+    assert np.max(np.abs(c - g[f"{name}/xcorr"])) <= PEAK_TOL and int(np.argmax(c)) == int(np.argmax(g[f"{name}/xcorr"]))
+    c2, _ = sig.autocorr1d(a)
+    assert np.max(np.abs(c2 - g[f"{name}/autocorr"])) <= PEAK_TOL
+    c3, _ = sig.autocorr1d(a, remove_mean=False, normalize="none")
+    assert np.max(np.abs(c3 - g[f"{name}/autocorr_raw"])) <= PEAK_TOL * float(np.abs(g[f"{name}/autocorr_raw"]).max())
+    with pytest.raises(ValueError):
+        sig.fft1d(np.zeros((4, 4), np.float32))
+    with pytest.raises(ValueError):
+        sig.xcorr1d(a, a[:-1])
