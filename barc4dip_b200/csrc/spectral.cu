@@ -246,10 +246,11 @@ __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
 // feeds the second inverse transform, and (tile 0) the mirror exchange that unpacks the DC / Nyquist column.
 // CW (4 or 8) columns per CTA out of a layout tile of TC = 8: CW = 4 halves the footprint so that two CTAs
 // share an SM and one's loads overlap the other's butterflies.
-template <int NY, int CW, bool SPEC, bool AC, bool PC>
-__global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a) {
-    extern __shared__ float2 sm[];
-    __shared__ double red[32];
+// The body is instantiated twice: TILE0 = true for the one CTA per frame that owns the packed DC / Nyquist column
+// (thread-dependent unpacking branches at every element), false for the other tiles, whose code then carries no
+// branch at all inside the element loops.
+template <int NY, int CW, bool SPEC, bool AC, bool PC, bool TILE0>
+__device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double* red) {
     constexpr int T = NY / 16;
     constexpr int NT = T * CW;
     constexpr int PL = padded_len(NY);
@@ -262,8 +263,7 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
     const int tile = blockIdx.x, ntiles = gridDim.x;
     const int64_t t = blockIdx.y;
     const int nx = a.nx, hx = nx / 2, kx = tile * CW + c;
-    const bool TILE0 = tile == 0;                     // block-uniform: the CTA owns column 0
-    const bool nyq_owner = TILE0 && c == 0;
+    const bool nyq_owner = TILE0 && c == 0;           // TILE0: the CTA owns column 0
     // element s of this thread lives at g0 + s*GS inside a frame's blocked half spectrum
     const size_t g0 = (size_t)t * NY * hx + (size_t)(kx / TC) * NY * TC + (size_t)j * TC + (kx % TC);
 
@@ -456,6 +456,14 @@ __global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kern
             }
         }
     }
+}
+
+template <int NY, int CW, bool SPEC, bool AC, bool PC>
+__global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a) {
+    extern __shared__ float2 sm[];
+    __shared__ double red[32];
+    if (blockIdx.x == 0) cols_body<NY, CW, SPEC, AC, PC, true>(a, sm, red);
+    else cols_body<NY, CW, SPEC, AC, PC, false>(a, sm, red);
 }
 
 // =================================================================================================

@@ -244,12 +244,27 @@ def psd2d(stack, *, scale_factor: float = 1.0, sub_mean: bool = False, zero_dc: 
     return out, (spec.cpu().numpy() if spec is not None else None)
 
 
+def _std_divisors(stack):
+    """Per-frame population standard deviation on the device, 1 where it is 0 (signal/corr.py:229-235 divides only by a
+    positive std) -> float32 (T, 1, 1)."""
+    torch = require_cuda()
+    tab = frame_reductions(stack, saturation_value=None, return_device=True)
+    s = tab[:, FR["m2"]].sqrt()
+    return torch.where(s > 0, s, torch.ones_like(s)).to(torch.float32)[:, None, None]
+
+
 def autocorr2d(stack, *, remove_mean: bool = True, standardize: bool = False, normalize_peak: bool = True,
                want_map: bool = True, want_grain: bool = False, fraction: float = 1.0 / math.e):
     """Shifted circular autocorrelation per frame (+ optional grain widths table (T, 4))."""
     torch = require_cuda()
     T, ny, nx = stack.shape
     check_fft_shape(ny, nx, generic_ok=True)
+    if standardize and not normalize_peak and not remove_mean and want_map and not want_grain:
+        # the one combination the library leaves to the host: correlation is bilinear, so the /std of both factors is
+        # applied to the finished map
+        out, _ = autocorr2d(stack, remove_mean=False, standardize=False, normalize_peak=False)
+        sd = _std_divisors(stack)
+        return out.div_(sd * sd), None
     ctx = get_context(_dev(stack))
     out = torch.empty((T, ny, nx), dtype=torch.float32, device=stack.device) if want_map else None
     grain = torch.empty((T, 4), dtype=torch.float64, device=stack.device) if want_grain else None
@@ -265,6 +280,10 @@ def xcorr2d(a, b, *, remove_mean: bool = True, standardize: bool = False, normal
     if tuple(b.shape) != (T, ny, nx):
         raise ValueError("a and b must have the same shape.")
     check_fft_shape(ny, nx, generic_ok=True)
+    if standardize and not normalize_peak:
+        # left to the host by b4d_xcorr2d: correlation is bilinear, the two /std factors scale the finished map
+        out = xcorr2d(a, b, remove_mean=remove_mean, standardize=False, normalize_peak=False)
+        return out.div_(_std_divisors(a) * _std_divisors(b))
     ctx = get_context(_dev(a))
     out = torch.empty((T, ny, nx), dtype=torch.float32, device=a.device)
     ctx.check(ctx.lib.b4d_xcorr2d(ctx.handle, ptr(a), ptr(b), T, ny, nx, int(bool(remove_mean)),

@@ -501,3 +501,26 @@ def test_signal_1d_family_vs_golden(sig, golden, name):
         sig.fft1d(np.zeros((4, 4), np.float32))
     with pytest.raises(ValueError):
         sig.xcorr1d(a, a[:-1])
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (150, 200)])
+def test_xcorr_standardize_without_peak_normalisation_vs_oracle(sig, shape):
+    """standardize=True with normalize="none" (signal/corr.py:229-235): the /std factors are applied to the finished map
+    on the device; also autocorr2d(remove_mean=False, standardize=True, normalize="none")."""
+    from oracle import ref_numpy as ref
+    rng = np.random.default_rng(shape[0])
+    a = (1000.0 + 150.0 * rng.standard_normal(shape)).astype(np.float32)
+    b = (np.roll(a, (3, -5), axis=(0, 1)) + 20.0 * rng.standard_normal(shape)).astype(np.float32)
+    for rm in (True, False):
+        want, _, _ = ref.xcorr2d(a, b, remove_mean=rm, standardize=True, normalize="none")
+        got, _, _ = sig.xcorr2d(a, b, remove_mean=rm, standardize=True, normalize="none")
+        peak = float(np.max(np.abs(want)))
+        assert np.max(np.abs(got - np.real(want))) <= PEAK_TOL * peak
+    want, _, _ = ref.autocorr2d(a, remove_mean=False, standardize=True, normalize="none")
+    got, _, _ = sig.autocorr2d(a, remove_mean=False, standardize=True, normalize="none")
+    assert np.max(np.abs(got - want)) <= PEAK_TOL * float(np.max(np.abs(want)))
+    # a constant frame has std 0: the reference leaves it undivided
+    flat = np.full(shape, 7.0, np.float32)
+    got, _, _ = sig.xcorr2d(flat, b, remove_mean=False, standardize=True, normalize="none")
+    want, _, _ = ref.xcorr2d(flat, b, remove_mean=False, standardize=True, normalize="none")
+    assert np.max(np.abs(got - np.real(want))) <= 1e-4 * float(np.max(np.abs(want)))
