@@ -3,14 +3,14 @@ Sharpness metrics on the B200 path -- drop-in for barc4dip.metrics.sharpness.
 
 tenengrad (:405-476), laplacian_variance (:482-530), spectral_entropy (:536-629),
 inverse_autocorr_width (:635-746), sharpness_stats (:89-288), sharpness_stack_stats (:290-399).
-`eigenvalues` (dense SVD, :752) is outside the hot path and raises.
+`eigenvalues` (:752-861, a dense symmetric eigenproblem) is outside the hot path: it runs on the device
+through library code (cuBLAS Gram matrix + cuSOLVER symmetric eigensolver via torch.linalg), see stack.eigenvalues_block.
 """
 
 from __future__ import annotations
 
 import logging
 import math
-import warnings
 from typing import Sequence
 
 import numpy as np
@@ -31,8 +31,8 @@ _SHARPNESS_UNITS: dict[str, dict[str, str]] = {
     "autocorrelation": {"sx": "1/px", "sy": "1/px", "seq": "1/px", "r": ""},
     "eigenvalues": {"eigenvalues": "", "e1": "", "e2": "", "re": ""},
 }
+_GROUP_ORDER = ("stats", "gradient", "laplacian", "spectral", "autocorrelation", "eigenvalues")
 _ALL_SHARPNESS_GROUPS = {"stats", "gradient", "laplacian", "spectral", "autocorrelation", "eigenvalues"}
-_BUILT_GROUPS = _ALL_SHARPNESS_GROUPS - {"eigenvalues"}
 
 
 def _scalar(block: dict, t: int = 0) -> dict:
@@ -103,22 +103,19 @@ def inverse_autocorr_width(image, *, fraction: float = 1.0 / math.e, radial_meth
 
 
 def eigenvalues(image, *, k: int = 5, eps: float = 1e-30, verbose: bool = False) -> dict:
-    raise B4DUnsupported("eigenvalues (dense SVD, metrics/sharpness.py:752-861) is outside the B200 hot path")
+    """STA2: sum of the k leading eigenvalues of the covariance of the energy-normalised, mean-removed image, e1, e2, e1/e2."""
+    data = _check2d(image, "eigenvalues")
+    if not np.all(np.isfinite(data)):
+        raise ValueError("eigenvalues requires all values to be finite.")
+    out = _scalar(blocks.eigenvalues_block(engine.as_stack(np.ascontiguousarray(data)), k=k, eps=eps))
+    if verbose:
+        logger.info("> eigenvalues: %.6g | e1: %.6g | e2: %.6g | e1/e2: %.3f | k=%d", out["eigenvalues"], out["e1"], out["e2"],
+                    out["re"], min(int(k), min(data.shape)))
+    return out
 
 
 def _resolve_groups(metrics) -> set[str]:
-    """Validated group set. "all" covers every group built on the B200 path (a warning names the skipped
-    `eigenvalues`); naming `eigenvalues` explicitly raises."""
-    groups = normalize_groups(metrics, all_groups=_ALL_SHARPNESS_GROUPS, context="sharpness", param_name="metrics")
-    named = {metrics.strip()} if isinstance(metrics, str) and "," not in metrics else \
-        {g.strip() for g in (metrics.split(",") if isinstance(metrics, str) else metrics)}
-    if "eigenvalues" in named:
-        raise B4DUnsupported("sharpness group 'eigenvalues' (dense SVD) is not built on the B200 path")
-    if "eigenvalues" in groups:
-        warnings.warn("sharpness: group 'eigenvalues' is not built on the B200 path and is skipped", RuntimeWarning,
-                      stacklevel=3)
-        groups = groups - {"eigenvalues"}
-    return groups
+    return normalize_groups(metrics, all_groups=_ALL_SHARPNESS_GROUPS, context="sharpness", param_name="metrics")
 
 
 def _full_blocks(dev_stack, groups, saturation_value, eps) -> dict:
@@ -137,6 +134,8 @@ def _full_blocks(dev_stack, groups, saturation_value, eps) -> dict:
         out["spectral"] = blocks.spectral_entropy_block(dev_stack)
     if "autocorrelation" in groups:
         out["autocorrelation"] = blocks.inverse_autocorr_block(dev_stack, table=table)
+    if "eigenvalues" in groups:
+        out["eigenvalues"] = blocks.eigenvalues_block(dev_stack)
     return out
 
 
@@ -155,7 +154,7 @@ def sharpness_stats(image, *, metrics="all", tiles: bool = True, display_origin:
     out = {"meta": {"kind": "sharpness", "display_origin": display_origin, "input_shape": (int(h), int(w)),
                     "requested_groups": sorted(groups), "units": _SHARPNESS_UNITS, "tile_mode": "off"},
            "full": {}}
-    order = ("stats", "gradient", "laplacian", "spectral", "autocorrelation")
+    order = _GROUP_ORDER
     for grp in order:
         if grp in full:
             out["full"][grp] = _scalar(full[grp])
@@ -173,7 +172,7 @@ def sharpness_stats(image, *, metrics="all", tiles: bool = True, display_origin:
 def _tiles(dev_oriented, mode, groups, saturation_value, eps) -> dict:
     """{group: {field: {"mean": (T, 3, 3), "std": (T, 3, 3)}}} of a display-oriented device stack (sharpness.py:213-282)."""
     res = tiled_blocks(dev_oriented, tile_mode=mode, block_fn=lambda tl: _full_blocks(tl, groups, saturation_value, eps))
-    return {g: res[g] for g in ("stats", "gradient", "laplacian", "spectral", "autocorrelation") if g in res}
+    return {g: res[g] for g in _GROUP_ORDER if g in res}
 
 
 def sharpness_stack_stats(stack, *, metrics="all", tiles: bool = True, display_origin: str = "lower",
@@ -201,7 +200,7 @@ def sharpness_stack_stats(stack, *, metrics="all", tiles: bool = True, display_o
             "display_origin": display_origin, "requested_groups": sorted(groups), "units": _SHARPNESS_UNITS,
             "parallel": {"enabled": bool(not serial), "n_jobs": None if serial else (-1 if n_jobs is None else n_jobs)},
             }
-    out_full = {grp: full[grp] for grp in ("stats", "gradient", "laplacian", "spectral", "autocorrelation") if grp in full}
+    out_full = {grp: full[grp] for grp in _GROUP_ORDER if grp in full}
     out = {"meta": meta, "full": out_full}
     mode, _ = choose_tiling_mode(H, W, tiles=tiles)
     if mode != "off":

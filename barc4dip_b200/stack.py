@@ -143,3 +143,41 @@ def inverse_autocorr_block(stack, *, fraction: float = INV_E, table=None) -> dic
         inv = lambda v: np.where(v != 0.0, 1.0 / v, np.inf)
         return {"sx": inv(g["lx"]), "sy": inv(g["ly"]), "seq": inv(g["leq"]),
                 "r": np.where(g["ly"] != 0.0, g["lx"] / g["ly"], np.inf)}
+
+
+def eigenvalues_block(stack, *, k: int = 5, eps: float = 1e-30) -> dict:
+    """STA2 focus measure (metrics/sharpness.py:752-861) for every frame of a (T, H, W) device stack.
+
+    Outside the hot path: a dense symmetric eigenproblem, served by library code -- a float64 Gram
+    matrix J J^T (or J^T J, whichever is smaller; cuBLAS) and cuSOLVER's symmetric eigensolver through torch.linalg --
+    on the device, so that metrics="all" needs no host round trip of the stack. The eigenvalues of the Gram matrix are
+    the squared singular values the reference takes from numpy.linalg.svd."""
+    torch = require_cuda()
+    T, H, W = stack.shape
+    k_eff = int(k)
+    if k_eff < 1:
+        raise ValueError("k must be >= 1.")
+    denom = float(H * W - 1)
+    if denom <= 0.0:
+        raise ValueError("eigenvalues requires at least 2 pixels (M*N >= 2).")
+    n = min(H, W)
+    chunk = max(1, (1 << 25) // (H * W))                  # frames per batched eigensolve: ~0.8 GB of float64 working set
+    top = torch.zeros((T, max(2, min(k_eff, n))), dtype=torch.float64, device=stack.device)
+    for t0 in range(0, T, chunk):
+        x = stack[t0:t0 + chunk].to(torch.float64)
+        if not bool(torch.isfinite(x).all()):
+            raise ValueError("eigenvalues requires all values to be finite.")
+        energy = torch.sqrt((x * x).sum(dim=(1, 2), keepdim=True))
+        if bool((energy <= 0.0).any()) or not bool(torch.isfinite(energy).all()):
+            raise ValueError("eigenvalues cannot normalize an all-zero image.")
+        J = x / energy
+        J = J - J.mean(dim=(1, 2), keepdim=True)
+        G = J @ J.transpose(1, 2) if H <= W else J.transpose(1, 2) @ J
+        ev = torch.linalg.eigvalsh(G).flip(-1).clamp_min(0.0) / denom          # descending
+        m = min(top.shape[1], ev.shape[1])
+        top[t0:t0 + chunk, :m] = ev[:, :m]
+    top = top.cpu().numpy()
+    k_use = min(k_eff, n)
+    e1 = top[:, 0]
+    e2 = top[:, 1] if n >= 2 else np.zeros(T)
+    return {"eigenvalues": top[:, :k_use].sum(axis=1), "e1": e1, "e2": e2, "re": e1 / (e2 + float(eps))}

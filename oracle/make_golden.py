@@ -64,6 +64,25 @@ def signal1d_golden(sig, versions):
     print("signal1d.npz", os.path.getsize(os.path.join(OUT, "signal1d.npz")) // 1024, "KiB")
 
 
+def eigen_golden(met, versions):
+    """eigen.npz: the STA2 eigenvalues metric (metrics/sharpness.py:752-861) on the frame cases, and through
+    sharpness_stats(metrics="eigenvalues") with tiles."""
+    store = {"versions": versions}
+    for name, img in gc.frame_cases().items():
+        for k in (5, 2):
+            e = met.sharpness.eigenvalues(img, k=k)
+            store[f"{name}/k{k}"] = np.array([e["eigenvalues"], e["e1"], e["e2"], e["re"]])
+    img = gc.frame_cases()["sq512"]
+    res = met.sharpness.sharpness_stats(img, metrics="eigenvalues", tiles=True, verbose=False)
+    store["sq512/full"] = np.array([res["full"]["eigenvalues"][f] for f in ("eigenvalues", "e1", "e2", "re")])
+    for f in ("eigenvalues", "e1", "e2", "re"):
+        store[f"sq512/tiles/{f}/mean"] = np.asarray(res["tiles"]["eigenvalues"][f]["mean"])
+        store[f"sq512/tiles/{f}/std"] = np.asarray(res["tiles"]["eigenvalues"][f]["std"])
+    store["sq512/tile_mode"] = np.array(res["meta"]["tile_mode"])
+    np.savez_compressed(os.path.join(OUT, "eigen.npz"), **store)
+    print("eigen.npz", os.path.getsize(os.path.join(OUT, "eigen.npz")) // 1024, "KiB")
+
+
 def template_golden(sig, versions):
     """template.npz: template_matching(backend="opencv") of the reference (cv2.matchTemplate TM_CCOEFF_NORMED)."""
     import cv2
@@ -134,6 +153,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     import scipy
     versions = np.array([np.__version__, scipy.__version__])
+    if "--only-eigen" in sys.argv:
+        eigen_golden(met, versions)
+        return
     if "--only-1d" in sys.argv:
         signal1d_golden(sig, versions)
         return
@@ -269,6 +291,7 @@ def main():
     repair_golden(pre, versions)
     template_golden(sig, versions)
     signal1d_golden(sig, versions)
+    eigen_golden(met, versions)
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -520,6 +520,32 @@ def bandwidth(image):
             "rf": float(sfx / sfy) if sfy != 0.0 else float("inf"), "spr": float(1.0 / float(np.sum(p * p)))}
 
 
+def eigenvalues(image, k=5, eps=1e-30):
+    """STA2: sum of the k leading eigenvalues of S = J J^T / (M N - 1), J the energy-normalised, mean-removed image;
+    eigenvalues from the singular values of J.  ref: metrics/sharpness.py:752-861 (checks :811-837, svd :839-847)."""
+    data = np.asarray(image)
+    if data.ndim != 2:
+        raise ValueError(f"Expected 2D array, got ndim={data.ndim}")
+    if data.size == 0:
+        raise ValueError("eigenvalues received an empty image.")
+    if not np.all(np.isfinite(data)):
+        raise ValueError("eigenvalues requires all values to be finite.")
+    if int(k) < 1:
+        raise ValueError("k must be >= 1.")
+    x = np.asarray(data, dtype=float)
+    energy = float(np.sqrt(np.sum(x * x)))
+    if not np.isfinite(energy) or energy <= 0.0:
+        raise ValueError("eigenvalues cannot normalize an all-zero image.")
+    J = x / energy
+    J = J - float(np.mean(J))
+    if J.size < 2:
+        raise ValueError("eigenvalues requires at least 2 pixels (M*N >= 2).")
+    sv = np.linalg.svd(J, full_matrices=False, compute_uv=False)
+    eig = sv * sv / float(J.size - 1)
+    e1, e2 = float(eig[0]), float(eig[1]) if eig.size >= 2 else 0.0
+    return {"eigenvalues": float(np.sum(eig[:min(int(k), eig.size)])), "e1": e1, "e2": e2, "re": float(e1 / (e2 + float(eps)))}
+
+
 def spectral_entropy(image, eps=1e-30):
     """Normalised Shannon entropy of the unscaled PSD, DC excluded.  ref: metrics/sharpness.py:536-629.
 

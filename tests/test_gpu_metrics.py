@@ -87,14 +87,11 @@ def test_aggregator_errors_and_schema(dip):
         dip.metrics.speckle_stats(img, metrics="nope", tiles=False)
     with pytest.raises(ValueError):
         dip.metrics.sharpness_stats(img, tiles=False, display_origin="left")
-    with pytest.raises(B4DUnsupported):
-        dip.metrics.sharpness_stats(img, metrics="eigenvalues", tiles=False)
     with pytest.warns(RuntimeWarning, match="too small for tiling"):
         small = dip.metrics.speckle_stats(img, metrics="stats", tiles=True, verbose=False)   # 256//3 < 128
     assert "tiles" not in small
-    with pytest.warns(RuntimeWarning):
-        out = dip.metrics.sharpness_stats(img, tiles=False, verbose=False)                # "all" skips eigenvalues
-    assert set(out["full"]) == {"stats", "gradient", "laplacian", "spectral", "autocorrelation"}
+    out = dip.metrics.sharpness_stats(img, tiles=False, verbose=False)
+    assert set(out["full"]) == {"stats", "gradient", "laplacian", "spectral", "autocorrelation", "eigenvalues"}
     with pytest.raises(ValueError):
         dip.metrics.speckles.grain(np.ones((64, 64), np.float32))
     with pytest.raises(ValueError):
@@ -203,9 +200,9 @@ def test_tiles_vs_golden(dip, golden, name):
     assert sp["meta"]["used_subtiles"] == (name.startswith("t9"))
     assert set(sp["tiles"]) == {"amplitude", "grain", "stats", "bandwidth"}
     _check_tiles(sp["tiles"], g, f"{name}/speckle")
-    with pytest.warns(RuntimeWarning):      # "all" skips eigenvalues
-        sh = dip.metrics.sharpness_stats(img, tiles=True, verbose=False)
-    assert set(sh["tiles"]) == set(gc.SHARPNESS_TILE_GROUPS)
+    sh = dip.metrics.sharpness_stats(img, tiles=True, verbose=False)
+    assert set(sh["tiles"]) == set(gc.SHARPNESS_TILE_GROUPS) | {"eigenvalues"}
+    sh["tiles"].pop("eigenvalues")          # pinned by eigen.npz (test_eigenvalues_metric_vs_golden)
     _check_tiles(sh["tiles"], g, f"{name}/sharpness")
 
 
@@ -370,3 +367,26 @@ def test_stack_analyzer_arbitrary_frame_size_vs_oracle():
         np.testing.assert_allclose((out["tracking"]["dy"][t], out["tracking"]["dx"][t]), (dy, dx), atol=0.01)
         if t:
             np.testing.assert_allclose(out["tracking"]["peak"][t], peak, rtol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["sq256", "rect128x256", "odd150x200", "u16_128", "blur256", "sq512"])
+def test_eigenvalues_metric_vs_golden(dip, golden, name):
+    """STA2 eigenvalues metric (sharpness.py:752-861; library eigensolver on the device) against the reference."""
+    g = golden("eigen")
+    img = gc.frame_cases()[name]
+    for k in (5, 2):
+        e = dip.metrics.sharpness.eigenvalues(img, k=k)
+        np.testing.assert_allclose([e["eigenvalues"], e["e1"], e["e2"], e["re"]], g[f"{name}/k{k}"], rtol=RTOL)
+    with pytest.raises(ValueError):
+        dip.metrics.sharpness.eigenvalues(np.zeros((8, 8), np.float32))
+    with pytest.raises(ValueError):
+        dip.metrics.sharpness.eigenvalues(img, k=0)
+    if name == "sq512":
+        res = dip.metrics.sharpness_stats(img, metrics="eigenvalues", tiles=True, verbose=False)
+        assert res["meta"]["tile_mode"] == str(g["sq512/tile_mode"])
+        np.testing.assert_allclose([res["full"]["eigenvalues"][f] for f in ("eigenvalues", "e1", "e2", "re")], g["sq512/full"], rtol=RTOL)
+        for f in ("eigenvalues", "e1", "e2", "re"):
+            np.testing.assert_allclose(res["tiles"]["eigenvalues"][f]["mean"], g[f"sq512/tiles/{f}/mean"], rtol=RTOL)
+            np.testing.assert_allclose(res["tiles"]["eigenvalues"][f]["std"], g[f"sq512/tiles/{f}/std"], rtol=RTOL, atol=1e-12)
+        st = dip.metrics.sharpness_stack_stats(np.stack([img, img[::-1]]), metrics="eigenvalues", tiles=False, verbose=False)
+        np.testing.assert_allclose(st["full"]["eigenvalues"]["e1"], [g["sq512/full"][1]] * 2, rtol=RTOL)

@@ -225,3 +225,16 @@ def test_template_matching_matches_reference(golden):
         np.testing.assert_allclose(got[:2], want[:2], rtol=0, atol=5e-3, err_msg=name)
         np.testing.assert_allclose(got[2], want[2], rtol=1e-5, err_msg=name + " peak")
         np.testing.assert_allclose(got[3], want[3], rtol=1e-4, err_msg=name + " snr")
+
+
+@pytest.mark.parametrize("name", ["sq256", "rect128x256", "odd150x200", "u16_128", "blur256", "sq512"])
+def test_eigenvalues_metric(name, frames, golden):
+    """STA2 eigenvalues metric of the oracle against the reference's outputs (tests/golden/eigen.npz)."""
+    g = golden("eigen")
+    for k in (5, 2):
+        e = orc.eigenvalues(frames[name], k=k)
+        np.testing.assert_allclose([e["eigenvalues"], e["e1"], e["e2"], e["re"]], g[f"{name}/k{k}"], rtol=RT)
+    with pytest.raises(ValueError):
+        orc.eigenvalues(np.zeros((8, 8)))
+    with pytest.raises(ValueError):
+        orc.eigenvalues(frames[name], k=0)
