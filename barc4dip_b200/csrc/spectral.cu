@@ -109,6 +109,7 @@ struct RowsFwdArgs {
     const float2* tw;
     int ny;
     double* mom;          // nullable: (T, gridDim.x, 2) per-CTA sums of d = x - K and of d^2 (z-score of the tracker)
+    int pf_dist;          // L2 prefetch distance in CTAs (0 = off), set by the launcher
 };
 
 template <int NX>
@@ -137,6 +138,13 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
             vb = (vb - (a.dark ? __ldg(a.dark + pb) : 0.f)) * __ldg(a.gain + pb);
         }
         x[m] = make_float2(va - K, vb - K);
+    }
+    // the rows of the CTA that takes this SM next (pf_dist CTAs ahead in launch order; a CTA's rows are one contiguous
+    // run of 16384 floats) are pulled into L2 now, one 128-byte line per thread
+    if (a.pf_dist > 0) {
+        const size_t next = (size_t)t * gridDim.x + blockIdx.x + (size_t)a.pf_dist;
+        if (next < (size_t)gridDim.x * gridDim.y)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stack + next * (size_t)(ROWS * NX) + (size_t)tid * 32));
     }
     if (a.mom) {
         // the tracker z-scores the frame (tracking.py:308-311): its mean and standard deviation come from these sums,
@@ -185,6 +193,7 @@ struct ColsArgs {
     int nx;
     int zero_dc;                // clear F[0,0] (mean removal) for every output
     int ac_zero_dc;             // clear it for the autocorrelation branch only (fused pipeline)
+    int pf_dist;                // L2 prefetch distance in CTAs (resident CTAs of the launch; 0 = off), set by the launcher
     // plain outputs
     float2* cplx_out;           // (T, ny, nx) shifted complex spectrum (fft2d)
     float* psd_out;             // (T, ny, nx) shifted |F|^2 * psd_scale
@@ -272,6 +281,14 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         const float2* Hin = a.H + g0;
 #pragma unroll
         for (int s = 0; s < 16; ++s) x[s] = __ldcs(Hin + s * GS);
+    }
+    // CTAs start in linear order and a tile is one contiguous NY*TC run of the blocked intermediate, so the tile of the
+    // CTA that will take this SM next (pf_dist CTAs ahead) is known now: one 128-byte line per thread is pulled into L2
+    // while this CTA works, and that CTA's loads wait for an L2 hit instead of for HBM.
+    if (CW == TC && a.pf_dist > 0) {
+        const size_t next = (size_t)t * ntiles + tile + (size_t)a.pf_dist;
+        if (next < (size_t)gridDim.y * ntiles && tid < NY / 2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.H + next * ((size_t)NY * TC) + (size_t)tid * 16));
     }
     fft_regs<NY, -1, CW>(x, j, A + c, a.tw);
 
@@ -501,6 +518,7 @@ struct RowsInvArgs {
     unsigned* cnt3;         // (T, regions, 3)
     unsigned* bhist;        // (T, SEL_BINS)
     int regions;            // warp regions per frame = row blocks * 16 warps * 2
+    int pf_dist;            // L2 prefetch distance in CTAs (0 = off), set by the launcher
 };
 
 // One complex inverse transform yields rows 2p and 2p + 1 of the map. Two thread mappings: the gather uses lanes
@@ -546,6 +564,18 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
             for (int m = 0; m < 8; ++m) {
                 ga[m] = __ldcs(pa + m * tstride);
                 gb[m] = __ldcs(pa + m * tstride + TC);
+            }
+        }
+        // the rows of the CTA that takes this SM next (pf_dist CTAs ahead in launch order): RPC rows x 64 bytes in each of
+        // the nx/16 column tiles, 512 lines in all, one per thread, pulled into L2 while this CTA works
+        if (a.pf_dist > 0) {
+            const unsigned nb = blockIdx.x + (unsigned)a.pf_dist;
+            const int64_t tn = t + nb / gridDim.x;
+            const unsigned bn = nb % gridDim.x;
+            if (tn < (int64_t)gridDim.y) {
+                const int blkn = a.blk_map_pf ? a.blk_map_pf[(size_t)tn * gridDim.x + bn] : (a.blk_map ? a.blk_map[bn] : (int)bn);
+                const int q = tid / (RPC / 2), l = tid % (RPC / 2);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Ia + (size_t)tn * NY * HX + ((size_t)q * NY + (size_t)blkn * RPC) * TC + (size_t)l * 16));
             }
         }
         if (warp == 0) {
@@ -1157,6 +1187,12 @@ __global__ void f95_scan_kernel(double* __restrict__ hist, int nb, int level, co
 // -------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // -------------------------------------------------------------------------------------------------
+bool rows_prefetch_on() {                             // experiment knob: B4D_ROWS_PREFETCH=0
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B4D_ROWS_PREFETCH"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    return on == 1;
+}
+
 template <int NX>
 int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     constexpr int TPF = NX / 16, FPC = 512 / TPF, ROWS = 2 * FPC;
@@ -1165,7 +1201,9 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_fwd_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     if (a.ny % ROWS) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, ROWS);
     ProfScope ps(ctx, KC_ROWS_FWD);
-    rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(a);
+    RowsFwdArgs b = a;
+    b.pf_dist = rows_prefetch_on() ? ctx->sm_count * 2 : 0;
+    rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
@@ -1180,7 +1218,11 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
         attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_COLS);
-    cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(a);
+    static int pf_off = -1;                           // experiment knob: B4D_COLS_PREFETCH=0
+    if (pf_off < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_off = (e && atoi(e) == 0) ? 1 : 0; }
+    ColsArgs b = a;
+    b.pf_dist = pf_off ? 0 : ctx->sm_count * (1024 / (NY / 16 * CW));
+    cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
@@ -1230,6 +1272,7 @@ int launch_rows_inv_inst(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_block
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     a.nblk = a.ny / rows;
     ProfScope ps(ctx, KC_ROWS_INV);
+    a.pf_dist = rows_prefetch_on() ? ctx->sm_count * 2 : 0;
     rows_inv_kernel<NX, MODE, ABS><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
