@@ -33,6 +33,9 @@ extern "C" int b4d_destroy(b4d_ctx* ctx) {
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return B4D_OK;
 }

@@ -47,6 +47,10 @@ struct b4d_ctx {
     std::vector<ProfSpan> prof_spans;
     std::vector<cudaEvent_t> prof_pool;
     int cur_class = KC_SMALL;
+    // side stream of the fused stack pipeline: the autocorrelation branch (row pass, argmax, grain widths) runs on it
+    // next to the tracker's branch on `stream`; created on first use, non-blocking
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex lock;
 };
 

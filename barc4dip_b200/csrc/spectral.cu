@@ -1187,10 +1187,10 @@ __global__ void f95_scan_kernel(double* __restrict__ hist, int nb, int level, co
 // -------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // -------------------------------------------------------------------------------------------------
-bool rows_prefetch_on() {                             // experiment knob: B4D_ROWS_PREFETCH=0
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("B4D_ROWS_PREFETCH"); on = (e && atoi(e) == 0) ? 0 : 1; }
-    return on == 1;
+int rows_prefetch_dist(b4d_ctx* ctx) {               // experiment knob: B4D_ROWS_PREFETCH = distance in % of the resident CTAs (0 = off)
+    static int pct = -1;
+    if (pct < 0) { const char* e = getenv("B4D_ROWS_PREFETCH"); pct = e ? atoi(e) : 100; }
+    return ctx->sm_count * 2 * pct / 100;
 }
 
 template <int NX>
@@ -1202,7 +1202,7 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     if (a.ny % ROWS) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, ROWS);
     ProfScope ps(ctx, KC_ROWS_FWD);
     RowsFwdArgs b = a;
-    b.pf_dist = rows_prefetch_on() ? ctx->sm_count * 2 : 0;
+    b.pf_dist = rows_prefetch_dist(ctx);
     rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -1219,7 +1219,8 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     }
     ProfScope ps(ctx, KC_COLS);
     static int pf_pct = -1;                           // experiment knob: B4D_COLS_PREFETCH = distance in % of the resident CTAs (0 = off)
-    if (pf_pct < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_pct = e ? atoi(e) : 100; }
+    if (pf_pct < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_pct = e ? atoi(e) : 50; }
+    ColsArgs b = a;
     b.pf_dist = ctx->sm_count * (1024 / (NY / 16 * CW)) * pf_pct / 100;
     cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
@@ -1271,7 +1272,7 @@ int launch_rows_inv_inst(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_block
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     a.nblk = a.ny / rows;
     ProfScope ps(ctx, KC_ROWS_INV);
-    a.pf_dist = rows_prefetch_on() ? ctx->sm_count * 2 : 0;
+    a.pf_dist = rows_prefetch_dist(ctx);
     rows_inv_kernel<NX, MODE, ABS><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -1339,6 +1340,8 @@ struct Work {
     ArgBest* bestB = nullptr;
     unsigned* pk_idx = nullptr;
     float* pk_val = nullptr;
+    unsigned* pk_idx2 = nullptr;    // the autocorrelation branch's own peak (it may run next to the tracker's branch)
+    float* pk_val2 = nullptr;
     float* med = nullptr;
     long long* nvalid = nullptr;
 };
@@ -1357,6 +1360,7 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     const size_t o_pilot = take(sizeof(float) * T), o_acp = take(sizeof(double) * T * ntiles),
                  o_spp = take(sizeof(double) * T * ntiles * NSP), o_ba = take(sizeof(ArgBest) * T * nblk),
                  o_bb = take(sizeof(ArgBest) * T * nblk), o_pi = take(sizeof(unsigned) * T), o_pv = take(sizeof(float) * T),
+                 o_pi2 = take(sizeof(unsigned) * T), o_pv2 = take(sizeof(float) * T),
                  o_med = take(sizeof(float) * 2 * T), o_nv = take(sizeof(long long) * T),
                  o_nyq = take(sizeof(float2) * T * ny), o_mom = take(sizeof(double) * 2 * T * ny);
     rc = b4d_scratch(ctx, SCR_MISC, small + 1024, &p);
@@ -1369,6 +1373,8 @@ int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work*
     w->bestB = reinterpret_cast<ArgBest*>(base + o_bb);
     w->pk_idx = reinterpret_cast<unsigned*>(base + o_pi);
     w->pk_val = reinterpret_cast<float*>(base + o_pv);
+    w->pk_idx2 = reinterpret_cast<unsigned*>(base + o_pi2);
+    w->pk_val2 = reinterpret_cast<float*>(base + o_pv2);
     w->med = reinterpret_cast<float*>(base + o_med);
     w->nvalid = reinterpret_cast<long long*>(base + o_nv);
     w->I2nyq = reinterpret_cast<float2*>(base + o_nyq);
@@ -2409,6 +2415,21 @@ extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frame
     return B4D_OK;
 }
 
+// side stream + fork / join events of the fused pipeline (experiment knob: B4D_SIDE_STREAM=0 keeps one stream)
+bool side_stream_ready(b4d_ctx* ctx) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B4D_SIDE_STREAM"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!on) return false;
+    if (!ctx->side) {
+        int lo = 0, hi = 0;                             // highest priority: its CTAs are placed first whenever an SM has room
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->side = nullptr; return false; }
+        if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    return ctx->ev_fork && ctx->ev_join;
+}
+
 extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                   const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
                                   double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
@@ -2476,38 +2497,61 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         RowsInvArgs r;
         memset(&r, 0, sizeof(r));
         r.ny = ny;
-        int nblk = 0, nblk_ac = 0;
-        if (want_ac) {
+        int nblk = 0;
+        // After the column pass the two branches are independent. With both on, the tracker's branch (issue-bound row pass
+        // between small latency-bound kernels: sample rows, median bracket, final median, 3x3 window) goes to the
+        // high-priority side stream and the autocorrelation branch (DRAM-bound row pass, argmax, grain widths) stays on the
+        // caller's stream: the small kernels are placed as soon as an SM has room, the big row pass fills every gap they
+        // leave, and CTAs of the two row passes share the SMs. Joined before the batch ends (the scratch is reused).
+        const bool forked = want_ac && want_pc && side_stream_ready(ctx);
+        cudaStream_t main_stream = ctx->stream;
+        auto ac_branch = [&]() -> int {
             // the column pass left the autocorrelation branch packed (two real columns per transform): its own row pass
             // over the rows 0 .. ny/2; the tracker's rows go on their own (two rows per transform)
+            int nblk_ac = 0;
             RowsInvAcArgs ra;
             memset(&ra, 0, sizeof(ra));
             ra.Iz = w.I2a; ra.Inyq = w.I2nyq; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny, cols_wide_out(c)) / 2);
             ra.out = acm; ra.norm = w.acp; ra.n_norm = cols_tiles(ny, nx, cols_wide_out(c)); ra.norm_mult = 1.0; ra.scale = 1.0 / ((double)nx * ny);
             ra.best = grain_out ? w.bestA : nullptr;
-            if ((rc = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac))) return rc;
+            int r2 = run_rows_inv_ac(ctx, ra, tc, nx, &nblk_ac);
+            if (r2) return r2;
+            if (grain_out) {
+                argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac, w.pk_idx2, w.pk_val2);
+                B4D_LAUNCH_CHECK(ctx);
+                ProfScope ps(ctx, KC_GRAIN);
+                grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx2, ctx->fft->theta, 0.36787944117144233,
+                                                                     grain_out + t0 * 4);
+                B4D_LAUNCH_CHECK(ctx);
+            }
+            return B4D_OK;
+        };
+        if (grain_out && (rc = ensure_theta(ctx))) return rc;
+        if (forked) {
+            B4D_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+            B4D_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            ctx->stream = ctx->side;
         }
         if (want_pc) {
             r.Ia = w.I2b; r.outA = mag; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
             nblk = rows_inv_blocks(nx, ny);
             if (ns) {
-                if ((rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4))) return rc;
+                rc = rows_inv_track_fused(ctx, w, r, tc, ny, nx, ns, mag, subpixel, eps, track_out + t0 * 4);
             } else {
-                if ((rc = run_rows_inv(ctx, r, tc, nx))) return rc;
+                rc = run_rows_inv(ctx, r, tc, nx);
+                if (!rc) rc = track_finish(ctx, w, mag, tc, ny, nx, nblk, subpixel, eps, track_out + t0 * 4);
             }
         }
-        if (grain_out) {
-            if ((rc = ensure_theta(ctx))) return rc;
-            argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac, w.pk_idx, w.pk_val);
-            B4D_LAUNCH_CHECK(ctx);
-            ProfScope ps(ctx, KC_GRAIN);
-            grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx, ctx->fft->theta, 0.36787944117144233,
-                                                                 grain_out + t0 * 4);
-            B4D_LAUNCH_CHECK(ctx);
+        if (forked) {
+            ctx->stream = main_stream;
+            if (!rc && cudaEventRecord(ctx->ev_join, ctx->side) != cudaSuccess) rc = b4d_fail(ctx, B4D_ERR_CUDA, "cudaEventRecord failed");
         }
-        if (want_pc && !ns) {
-            if ((rc = track_finish(ctx, w, mag, tc, ny, nx, nblk, subpixel, eps, track_out + t0 * 4))) return rc;
+        if (!rc && want_ac) rc = ac_branch();
+        if (forked) {                                   // joined on every path: the side stream's work is in flight
+            cudaError_t je = cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
+            if (!rc && je != cudaSuccess) rc = b4d_fail(ctx, B4D_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(je));
         }
+        if (rc) return rc;
     }
     return B4D_OK;
 }
