@@ -1219,7 +1219,7 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     }
     ProfScope ps(ctx, KC_COLS);
     static int pf_pct = -1;                           // experiment knob: B4D_COLS_PREFETCH = distance in % of the resident CTAs (0 = off)
-    if (pf_pct < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_pct = e ? atoi(e) : 50; }
+    if (pf_pct < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_pct = e ? atoi(e) : 20; }
     ColsArgs b = a;
     b.pf_dist = ctx->sm_count * (1024 / (NY / 16 * CW)) * pf_pct / 100;
     cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b);
