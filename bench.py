@@ -216,8 +216,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        # NCCL writes its version banner to stdout when NCCL_DEBUG is set on the box; stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # this image sets NCCL_DEBUG=VERSION and NCCL then writes its version banner to stdout; stdout carries the one JSON
+        # line only (any other level the user asked for is kept)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n, F = args.size, args.frames
     ctx = get_context(local)
