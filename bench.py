@@ -219,7 +219,7 @@ def run_b200(args):
         # this image sets NCCL_DEBUG=VERSION and NCCL then writes its version banner to stdout; stdout carries the one JSON
         # line only (any other level the user asked for is kept)
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+            del os.environ["NCCL_DEBUG"]               # (WARN prints the banner as well)
         dist.init_process_group("nccl", device_id=dev)
     n, F = args.size, args.frames
     ctx = get_context(local)
