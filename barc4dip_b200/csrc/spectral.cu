@@ -285,10 +285,12 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     // CTAs start in linear order and a tile is one contiguous NY*TC run of the blocked intermediate, so the tile of the
     // CTA that will take this SM next (pf_dist CTAs ahead) is known now: one 128-byte line per thread is pulled into L2
     // while this CTA works, and that CTA's loads wait for an L2 hit instead of for HBM.
-    if (CW == TC && a.pf_dist > 0) {
+    // (CW < TC: TC / CW CTAs share a layout tile and each pulls its share of the lines.)
+    if (a.pf_dist > 0) {
+        constexpr int R = TC / CW;
         const size_t next = (size_t)t * ntiles + tile + (size_t)a.pf_dist;
-        if (next < (size_t)gridDim.y * ntiles && tid < NY / 2)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.H + next * ((size_t)NY * TC) + (size_t)tid * 16));
+        if (next < (size_t)gridDim.y * ntiles)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.H + (next / R) * ((size_t)NY * TC) + ((next % R) * NT + (size_t)tid) * 16));
     }
     fft_regs<NY, -1, CW>(x, j, A + c, a.tw);
 
