@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
             v = (r & 1) ? make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x))
                         : make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
         }
-        Hf[((size_t)tile * a.ny + y0 + r) * TC + c] = v;
+        __stcs(Hf + ((size_t)tile * a.ny + y0 + r) * TC + c, v);   // (streaming: read once, gigabytes later)
     }
 }
 
@@ -442,7 +442,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
         float2* o = a.i2_pc + g0;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
+        for (int s = 0; s < 16; ++s) __stcs(o + s * GS, x[s]);
     }
     if (AC) {
         // Inverse along y of |F|^2, kept in Bp. Its columns are real, so two of them (c2 and c2 + CW/2) share one complex
@@ -461,7 +461,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             const int pc = tile * CH + c2;
             float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + (size_t)j2 * TC + (pc % TC);
 #pragma unroll
-            for (int s = 0; s < 16; ++s) o[s * GS] = x[s];
+            for (int s = 0; s < 16; ++s) __stcs(o + s * GS, x[s]);
         } else if (TILE0 && tid < NTH + (T < 32 ? 32 : T)) {
             // (T < 32: the group is padded to a warp, the extra threads repeat the work of the first T)
             const int j3 = (tid - NTH) % T;
