@@ -812,10 +812,10 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
         const int s = (oo + 8) & 15;
         const float va = x[s].x, vb = x[s].y;
         const int mo = oo == 0 ? wrap0 : -TPF * oo;
-        if (mainA) { pA[TPF * oo] = va; mx = fmaxf(mx, va); }
-        if (mirA) pAm[mo] = va;
-        if (mainB) { pB[TPF * oo] = vb; mx = fmaxf(mx, vb); }
-        if (mirB) pBm[mo] = vb;
+        if (mainA) { __stcs(pA + TPF * oo, va); mx = fmaxf(mx, va); }          // (the map is written once: streaming stores)
+        if (mirA) __stcs(pAm + mo, va);
+        if (mainB) { __stcs(pB + TPF * oo, vb); mx = fmaxf(mx, vb); }
+        if (mirB) __stcs(pBm + mo, vb);
     }
     // ---- argmax partial: block maximum first, then the smallest linear index (of either copy) that holds it
     if (a.best) {
