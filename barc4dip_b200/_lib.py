@@ -52,6 +52,8 @@ _SIGNATURES = {
     "b4d_profile_end": [_vp, _vp, _vp],
     "b4d_profile_class_name": [_i32],
     "b4d_set_batch_frames": [_vp, _i64],
+    "b4d_set_schedule": [_vp, _i32, _i32, _i32, _i32, _i32],
+    "b4d_set_pairing": [_vp, _i32],
     "b4d_set_fused_median": [_vp, _i32],
     "b4d_malloc": [_vp, C.c_size_t, C.POINTER(_vp)],
     "b4d_free": [_vp, _vp],
@@ -149,6 +151,14 @@ class Context:
 
     def set_batch_frames(self, frames: int):
         self.check(self.lib.b4d_set_batch_frames(self.handle, int(frames)), "b4d_set_batch_frames")
+
+    def set_schedule(self, sub_frames: int = -1, lanes: int = -1, ring_slots: int = -1, keep: int = -1, use_graphs: int = -1):
+        """Frame-pipelined schedule of the fused stack pipeline (include/b4d.h, b4d_set_schedule); -1 = default."""
+        self.check(self.lib.b4d_set_schedule(self.handle, int(sub_frames), int(lanes), int(ring_slots), int(keep),
+                                             int(use_graphs)), "b4d_set_schedule")
+
+    def set_pairing(self, pair_frames: int = -1):
+        self.check(self.lib.b4d_set_pairing(self.handle, int(pair_frames)), "b4d_set_pairing")
 
     def set_fused_median(self, on: bool):
         self.check(self.lib.b4d_set_fused_median(self.handle, int(bool(on))), "b4d_set_fused_median")

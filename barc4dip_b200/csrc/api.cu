@@ -34,6 +34,11 @@ extern "C" int b4d_destroy(b4d_ctx* ctx) {
     for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    for (auto& st : ctx->lane_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (ctx->pipe) { cudaStreamSynchronize(ctx->pipe); cudaStreamDestroy(ctx->pipe); }
+    for (auto& e : ctx->lane_ev) cudaEventDestroy(e);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -95,6 +100,24 @@ extern "C" int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames) {
     if (!ctx || frames < 0) return B4D_ERR_INVALID;
     B4dCall g(ctx);
     ctx->batch_override = frames;
+    return B4D_OK;
+}
+
+extern "C" int b4d_set_schedule(b4d_ctx* ctx, int sub_frames, int lanes, int ring_slots, int keep, int use_graphs) {
+    if (!ctx || ring_slots > 8 || lanes > 8) return B4D_ERR_INVALID;
+    B4dCall g(ctx);
+    ctx->sched_sub = sub_frames;
+    ctx->sched_lanes = lanes;
+    ctx->sched_slots = ring_slots;
+    ctx->sched_keep = keep;
+    ctx->use_graphs = use_graphs;
+    return B4D_OK;
+}
+
+extern "C" int b4d_set_pairing(b4d_ctx* ctx, int pair_frames) {
+    if (!ctx) return B4D_ERR_INVALID;
+    B4dCall g(ctx);
+    ctx->sched_pair = pair_frames;
     return B4D_OK;
 }
 

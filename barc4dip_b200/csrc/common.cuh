@@ -51,6 +51,21 @@ struct b4d_ctx {
     // next to the tracker's branch on `stream`; created on first use, non-blocking
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // frame-pipelined schedule of the fused stack pipeline (spectral.cu, "lanes"): the big kernels run `sched_sub` frames
+    // at a time so that the row <-> column intermediates are consumed from L2; the autocorrelation row pass and the
+    // tracker's row passes follow the column pass on two side streams through `sched_slots` ring slots of intermediates.
+    // -1 = take the default / the environment (B4D_SUB, B4D_SLOTS, B4D_KEEP).
+    int sched_sub = -1, sched_lanes = -1, sched_slots = -1, sched_keep = -1, sched_pair = -1;
+    int keep_mode = 0;                // cache policy the FFT launchers pass to their kernels (see st_inter in spectral.cu)
+    std::vector<cudaStream_t> lane_streams;
+    std::vector<cudaEvent_t> lane_ev;
+    // CUDA graphs of the frame-pipelined schedule (spectral.cu): a batch is ~10 launches and a few event operations per
+    // step of 1 - 2 frames, more than the host can issue in the time the GPU needs for them, so the second call with the
+    // same arguments captures the whole batch and every later one replays it. use_graphs: -1 = default / B4D_GRAPHS.
+    int use_graphs = -1;
+    cudaStream_t pipe = nullptr;      // capture / replay stream (the caller's stream may be the legacy default stream)
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    void* pipe_graphs = nullptr;
     std::mutex lock;
 };
 

@@ -612,16 +612,8 @@ float float_at_least(double v) {
 
 }  // namespace
 
-struct FrTails {              // optional fused tail percentiles (amplitude contrast)
-    double q_lo, q_hi;
-    float* quant_out;          // (T, 4): (v[lo], v[hi]) of q_lo, then of q_hi
-    int64_t* nvalid_out;       // (T): non-NaN pixels, -1 = unresolved (use b4d_select_ranks for that frame)
-};
-int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
-                            float* pilot_out);
-int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                                const float* dark, double sat_value, double zero_eps, double* out);
+#include "reduce.cuh"
+
 unsigned b4d_tails_gcap();
 int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain, const float* dark,
                            double q_lo, double q_hi, float* thr);
@@ -660,90 +652,115 @@ extern "C" int b4d_frame_reductions_tails(b4d_ctx* ctx, const float* stack, int6
     return b4d_frame_reductions_ex(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out, &tl, nullptr);
 }
 
-int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
-                            float* pilot_out) {
+// The reduction pass in three steps so that the fused stack pipeline can run its streaming kernel a few frames at a
+// time (the frames it has just read are then still in L2 when the forward row pass asks for them):
+//   begin: scratch, pilot means and tail thresholds of every frame (strided samples only);
+//   range: the streaming pass + finalize of frames [t0, t0 + tc) (tc <= 32768);
+//   end:   exact tail order statistics of every frame.
+int b4d_fr_begin(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain, const float* dark,
+                 double sat_value, double zero_eps, double* out, const FrTails* tails, float* pilot_out, FrPlan* pl) {
     if (!stack || !out || n_frames < 1 || ny < 1 || nx < 1)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: bad arguments (T=%lld ny=%d nx=%d)",
                         (long long)n_frames, ny, nx);
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: dark given without gain");
-    const bool has_sat = !(sat_value != sat_value);
-    const float sat = has_sat ? float_at_least(sat_value) : 0.f;
-    const float zeps = float_at_most(zero_eps);
-    const bool vec = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(stack) & 15) == 0) &&
-                     (!gain || (reinterpret_cast<uintptr_t>(gain) & 15) == 0) &&
-                     (!dark || (reinterpret_cast<uintptr_t>(dark) & 15) == 0);
+    pl->stack = stack; pl->gain = gain; pl->dark = dark; pl->n_frames = n_frames; pl->ny = ny; pl->nx = nx; pl->out = out;
+    pl->has_tails = tails != nullptr;
+    if (tails) pl->tails = *tails;
+    pl->has_sat = !(sat_value != sat_value);
+    pl->sat = pl->has_sat ? float_at_least(sat_value) : 0.f;
+    pl->zeps = float_at_most(zero_eps);
+    pl->vec = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(stack) & 15) == 0) &&
+              (!gain || (reinterpret_cast<uintptr_t>(gain) & 15) == 0) &&
+              (!dark || (reinterpret_cast<uintptr_t>(dark) & 15) == 0);
     const int64_t npix = (int64_t)ny * nx;
     // the fused tails need the v2 kernel; frames it does not cover are reported as unresolved
-    const bool fuse_tails = tails && vec && npix >= 65536;
+    pl->fuse_tails = tails && pl->vec && npix >= 65536;
 
-    const int nstrips = vec ? (nx + F2_STRIP - 1) / F2_STRIP : (nx + FR_STRIP - 1) / FR_STRIP;
+    pl->nstrips = pl->vec ? (nx + F2_STRIP - 1) / F2_STRIP : (nx + FR_STRIP - 1) / FR_STRIP;
     const int nbands = (ny + FR_BAND - 1) / FR_BAND;
-    const int nitems = nstrips * nbands;
-    const int nblocks = (nitems + FR_WARPS - 1) / FR_WARPS;
+    pl->nitems = pl->nstrips * nbands;
+    pl->nblocks = (pl->nitems + FR_WARPS - 1) / FR_WARPS;
     static_assert(F2_BAND == FR_BAND && F2_WARPS == FR_WARPS, "the two reduce kernels share the item decomposition");
 
     void* p = nullptr;
-    const int64_t chunk_max = 32768;   // gridDim.y limit is 65535
     int rc = b4d_scratch(ctx, SCR_PILOT, sizeof(float) * 3 * (size_t)n_frames, &p);
     if (rc) return rc;
-    float* pilot = pilot_out ? pilot_out : static_cast<float*>(p);
-    float* thr = static_cast<float*>(p) + n_frames;
-    const unsigned gcap = b4d_tails_gcap();
-    const size_t part_bytes = (sizeof(double) * FR_NACC * (size_t)nblocks * (size_t)n_frames + 255) & ~size_t(255);
-    const size_t cnt_bytes = fuse_tails ? (((size_t)n_frames * 3 * sizeof(unsigned) + 255) & ~size_t(255)) : 0;
-    const size_t cand_bytes = fuse_tails ? (size_t)n_frames * 2 * gcap * sizeof(float) : 0;
+    pl->pilot = pilot_out ? pilot_out : static_cast<float*>(p);
+    pl->thr = static_cast<float*>(p) + n_frames;
+    pl->gcap = b4d_tails_gcap();
+    const size_t part_bytes = (sizeof(double) * FR_NACC * (size_t)pl->nblocks * (size_t)n_frames + 255) & ~size_t(255);
+    const size_t cnt_bytes = pl->fuse_tails ? (((size_t)n_frames * 3 * sizeof(unsigned) + 255) & ~size_t(255)) : 0;
+    const size_t cand_bytes = pl->fuse_tails ? (size_t)n_frames * 2 * pl->gcap * sizeof(float) : 0;
     rc = b4d_scratch(ctx, SCR_REDUCE, part_bytes + cnt_bytes + cand_bytes, &p);
     if (rc) return rc;
-    double* partials = static_cast<double*>(p);
-    unsigned* cnt = reinterpret_cast<unsigned*>(static_cast<char*>(p) + part_bytes);
-    int* flag = reinterpret_cast<int*>(cnt + 2 * n_frames);
-    float* cand = reinterpret_cast<float*>(static_cast<char*>(p) + part_bytes + cnt_bytes);
-    if (fuse_tails) B4D_CUDA(ctx, cudaMemsetAsync(cnt, 0, cnt_bytes, ctx->stream));
+    pl->partials = static_cast<double*>(p);
+    pl->cnt = reinterpret_cast<unsigned*>(static_cast<char*>(p) + part_bytes);
+    pl->flag = reinterpret_cast<int*>(pl->cnt + 2 * n_frames);
+    pl->cand = reinterpret_cast<float*>(static_cast<char*>(p) + part_bytes + cnt_bytes);
+    if (pl->fuse_tails) B4D_CUDA(ctx, cudaMemsetAsync(pl->cnt, 0, cnt_bytes, ctx->stream));
+    rc = b4d_frame_pilot_launch(ctx, stack, n_frames, npix, gain, dark, pl->pilot);
+    if (rc) return rc;
+    if (pl->fuse_tails && (rc = b4d_tails_probe_launch(ctx, stack, n_frames, npix, gain, dark, tails->q_lo, tails->q_hi, pl->thr))) return rc;
+    return B4D_OK;
+}
 
-    for (int64_t t0 = 0; t0 < n_frames; t0 += chunk_max) {
-        const int64_t tc = (n_frames - t0 < chunk_max) ? n_frames - t0 : chunk_max;
-        const float* s0 = stack + (size_t)t0 * ny * nx;
-        rc = b4d_frame_pilot_launch(ctx, s0, tc, npix, gain, dark, pilot + t0);
-        if (rc) return rc;
-        if (fuse_tails && (rc = b4d_tails_probe_launch(ctx, s0, tc, npix, gain, dark, tails->q_lo, tails->q_hi, thr + 2 * t0))) return rc;
-        dim3 grid((unsigned)nblocks, (unsigned)tc);
-        double* part0 = partials + (size_t)t0 * nblocks * FR_NACC;
-        if (vec) {
-            Fr2Args b;
-            b.stack = s0; b.gain = gain; b.dark = dark; b.pilot = pilot + t0; b.thr = fuse_tails ? thr + 2 * t0 : nullptr;
-            b.partials = part0; b.cand = cand + (size_t)t0 * 2 * gcap; b.cand_cnt = cnt + 2 * t0; b.flag = flag + t0; b.gcap = gcap;
-            b.ny = ny; b.nx = nx; b.nstrips = nstrips; b.nitems = nitems; b.sat = sat; b.zeps = zeps; b.has_sat = has_sat;
-            ProfScope ps(ctx, KC_FRAME_REDUCE);
-            if (gain) {
-                if (fuse_tails) frame_reduce2_kernel<true, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
-                else frame_reduce2_kernel<true, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
-            } else {
-                if (fuse_tails) frame_reduce2_kernel<false, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
-                else frame_reduce2_kernel<false, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
-            }
+int b4d_fr_range(b4d_ctx* ctx, const FrPlan& pl, int64_t t0, int64_t tc) {
+    if (t0 < 0 || tc < 1 || t0 + tc > pl.n_frames || tc > 32768)   // gridDim.y limit is 65535
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_frame_reductions: bad frame range");
+    const int ny = pl.ny, nx = pl.nx;
+    const float* s0 = pl.stack + (size_t)t0 * ny * nx;
+    dim3 grid((unsigned)pl.nblocks, (unsigned)tc);
+    double* part0 = pl.partials + (size_t)t0 * pl.nblocks * FR_NACC;
+    if (pl.vec) {
+        Fr2Args b;
+        b.stack = s0; b.gain = pl.gain; b.dark = pl.dark; b.pilot = pl.pilot + t0; b.thr = pl.fuse_tails ? pl.thr + 2 * t0 : nullptr;
+        b.partials = part0; b.cand = pl.cand + (size_t)t0 * 2 * pl.gcap; b.cand_cnt = pl.cnt + 2 * t0; b.flag = pl.flag + t0; b.gcap = pl.gcap;
+        b.ny = ny; b.nx = nx; b.nstrips = pl.nstrips; b.nitems = pl.nitems; b.sat = pl.sat; b.zeps = pl.zeps; b.has_sat = pl.has_sat;
+        ProfScope ps(ctx, KC_FRAME_REDUCE);
+        if (pl.gain) {
+            if (pl.fuse_tails) frame_reduce2_kernel<true, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+            else frame_reduce2_kernel<true, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
         } else {
-            FrArgs b;
-            b.stack = s0; b.gain = gain; b.dark = dark; b.pilot = pilot + t0; b.partials = part0;
-            b.ny = ny; b.nx = nx; b.nstrips = nstrips; b.nitems = nitems; b.sat = sat; b.zeps = zeps; b.has_sat = has_sat;
-            ProfScope ps(ctx, KC_FRAME_REDUCE);
-            frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+            if (pl.fuse_tails) frame_reduce2_kernel<false, true><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
+            else frame_reduce2_kernel<false, false><<<grid, F2_WARPS * 32, 0, ctx->stream>>>(b);
         }
+    } else {
+        FrArgs b;
+        b.stack = s0; b.gain = pl.gain; b.dark = pl.dark; b.pilot = pl.pilot + t0; b.partials = part0;
+        b.ny = ny; b.nx = nx; b.nstrips = pl.nstrips; b.nitems = pl.nitems; b.sat = pl.sat; b.zeps = pl.zeps; b.has_sat = pl.has_sat;
+        ProfScope ps(ctx, KC_FRAME_REDUCE);
+        frame_reduce_kernel<false><<<grid, FR_WARPS * 32, 0, ctx->stream>>>(b);
+    }
+    B4D_LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps2(ctx, KC_SMALL);
+        frame_finalize_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(part0, pl.nblocks, pl.pilot + t0, (double)ny * (double)nx,
+                                                                     pl.out + t0 * B4D_FR_NCOLS);
         B4D_LAUNCH_CHECK(ctx);
-        {
-            ProfScope ps2(ctx, KC_SMALL);
-            frame_finalize_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(part0, nblocks, pilot + t0, (double)ny * (double)nx,
-                                                                         out + t0 * B4D_FR_NCOLS);
-            B4D_LAUNCH_CHECK(ctx);
-        }
-        if (fuse_tails) {
-            rc = b4d_tails_final_launch(ctx, cand + (size_t)t0 * 2 * gcap, cnt + 2 * t0, flag + t0, out + t0 * B4D_FR_NCOLS, tc,
-                                        tails->q_lo, tails->q_hi, tails->quant_out + 4 * t0, tails->nvalid_out + t0);
-            if (rc) return rc;
-        } else if (tails) {
-            B4D_CUDA(ctx, cudaMemsetAsync(tails->nvalid_out + t0, 0xff, sizeof(int64_t) * tc, ctx->stream));   // -1: unresolved
-            B4D_CUDA(ctx, cudaMemsetAsync(tails->quant_out + 4 * t0, 0xff, sizeof(float) * 4 * tc, ctx->stream));   // NaN
-        }
     }
     return B4D_OK;
+}
+
+int b4d_fr_end(b4d_ctx* ctx, const FrPlan& pl) {
+    const int64_t T = pl.n_frames;
+    if (pl.fuse_tails)
+        return b4d_tails_final_launch(ctx, pl.cand, pl.cnt, pl.flag, pl.out, T, pl.tails.q_lo, pl.tails.q_hi, pl.tails.quant_out,
+                                      pl.tails.nvalid_out);
+    if (pl.has_tails) {
+        B4D_CUDA(ctx, cudaMemsetAsync(pl.tails.nvalid_out, 0xff, sizeof(int64_t) * T, ctx->stream));   // -1: unresolved
+        B4D_CUDA(ctx, cudaMemsetAsync(pl.tails.quant_out, 0xff, sizeof(float) * 4 * T, ctx->stream));   // NaN
+    }
+    return B4D_OK;
+}
+
+int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
+                            float* pilot_out) {
+    FrPlan pl;
+    int rc = b4d_fr_begin(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, out, tails, pilot_out, &pl);
+    if (rc) return rc;
+    const int64_t chunk_max = 32768;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += chunk_max)
+        if ((rc = b4d_fr_range(ctx, pl, t0, (n_frames - t0 < chunk_max) ? n_frames - t0 : chunk_max))) return rc;
+    return b4d_fr_end(ctx, pl);
 }

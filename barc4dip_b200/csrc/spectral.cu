@@ -19,20 +19,13 @@
 #include "common.cuh"
 #include "fft.cuh"
 #include "select.cuh"
+#include "reduce.cuh"
 
 using namespace b4dfft;
 
-int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
-                           const float* dark, float* pilot);
 int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, const double* q_dev, int n_q,
                     int use_abs, float* out, int64_t* n_valid);
 int b4d_put_doubles(b4d_ctx* ctx, double* dst, const double* src_host, int n);
-int b4d_frame_reductions_nolock(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                                const float* dark, double sat_value, double zero_eps, double* out);
-struct FrTails { double q_lo, q_hi; float* quant_out; int64_t* nvalid_out; };   // reduce.cu
-int b4d_frame_reductions_ex(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
-                            const float* dark, double sat_value, double zero_eps, double* out, const FrTails* tails,
-                            float* pilot_out);
 
 struct FftPlanCache {
     float2* twb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power twiddle tables: 128 ... 4096
@@ -96,9 +89,29 @@ int get_twiddle_bases(b4d_ctx* ctx, int n, const float2** out) {
 // K1: rows forward
 // =================================================================================================
 constexpr int TC = 8;     // width of a tile of the blocked intermediates [kx/TC][y][kx%TC]
+#ifndef B4D_PAIR_DEFAULT
+#define B4D_PAIR_DEFAULT 0        // frames per reduce / forward-rows pair of the whole-batch schedule (0: off)
+#endif
+#ifndef B4D_SCHED_SUB_DEFAULT
+#define B4D_SCHED_SUB_DEFAULT 0   // frames per step of the frame-pipelined schedule (0: whole batches, one kernel after the other)
+#endif
 #ifndef B4D_COLS_CW_2048
 #define B4D_COLS_CW_2048 4   // columns per K2 CTA at ny = 2048 (4: two CTAs per SM; 8: one)
 #endif
+
+// Cache policy of the row <-> column intermediates (bits of the `keep` argument of the four FFT kernels):
+//   0  streaming both ways (evict-first): the intermediates of a large batch go through HBM anyway and must not push the
+//      reference spectrum and the prefetched tiles out of L2;
+//   1  stores stay in L2 (st.global.cg): a few frames at a time, the consumer finds them there;
+//   2  loads leave the line at normal priority instead of marking it evict-first;
+//   4  the column pass drops its input tile from L2 once every thread has read it (discard.global.L2: the dead, dirty
+//      lines are neither kept nor written back to HBM).
+__device__ __forceinline__ void st_inter(float2* p, float2 v, int keep) {
+    if (keep & 1) __stcg(p, v); else __stcs(p, v);
+}
+__device__ __forceinline__ float2 ld_inter(const float2* p, int keep) {
+    return (keep & 2) ? __ldcg(p) : __ldcs(p);
+}
 
 struct RowsFwdArgs {
     const float* stack;
@@ -110,6 +123,7 @@ struct RowsFwdArgs {
     int ny;
     double* mom;          // nullable: (T, gridDim.x, 2) per-CTA sums of d = x - K and of d^2 (z-score of the tracker)
     int pf_dist;          // L2 prefetch distance in CTAs (0 = off), set by the launcher
+    int keep;             // cache policy of the intermediate (see st_inter)
 };
 
 template <int NX>
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
             v = (r & 1) ? make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x))
                         : make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
         }
-        __stcs(Hf + ((size_t)tile * a.ny + y0 + r) * TC + c, v);   // (streaming: read once, gigabytes later)
+        st_inter(Hf + ((size_t)tile * a.ny + y0 + r) * TC + c, v, a.keep);   // (streaming unless the consumer follows closely)
     }
 }
 
@@ -214,6 +228,7 @@ struct ColsArgs {
     float eps;
     const double* fr;           // frame-reduction table (mean, m2) for the z-score; nullable
     int fr_stride;
+    int keep;                   // cache policy of the intermediates (see st_inter)
 };
 
 struct SpecAcc {
@@ -280,7 +295,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     {
         const float2* Hin = a.H + g0;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) x[s] = __ldcs(Hin + s * GS);
+        for (int s = 0; s < 16; ++s) x[s] = ld_inter(Hin + s * GS, a.keep);
     }
     // CTAs start in linear order and a tile is one contiguous NY*TC run of the blocked intermediate, so the tile of the
     // CTA that will take this SM next (pf_dist CTAs ahead) is known now: one 128-byte line per thread is pulled into L2
@@ -293,6 +308,10 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.H + (next / R) * ((size_t)NY * TC) + ((next % R) * NT + (size_t)tid) * 16));
     }
     fft_regs<NY, -1, CW>(x, j, A + c, a.tw);
+    // (the transform's barriers lie between every thread's tile loads and this point) the tile is dead now: drop its lines
+    // from L2 instead of letting them be written back, one 128-byte line per thread
+    if (CW == TC && (a.keep & 4))
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.H + (size_t)t * NY * hx + (size_t)tile * NY * TC + (size_t)tid * 16) : "memory");
 
     // ---- tile 0: column 0 carries C = F[:,0] + i F[:,nx/2]; publish it so that its owners can read C[-ky]
     float2* A0 = A;                                   // natural order, [NY]
@@ -442,7 +461,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
         float2* o = a.i2_pc + g0;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) __stcs(o + s * GS, x[s]);
+        for (int s = 0; s < 16; ++s) st_inter(o + s * GS, x[s], a.keep);
     }
     if (AC) {
         // Inverse along y of |F|^2, kept in Bp. Its columns are real, so two of them (c2 and c2 + CW/2) share one complex
@@ -461,7 +480,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             const int pc = tile * CH + c2;
             float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + (size_t)j2 * TC + (pc % TC);
 #pragma unroll
-            for (int s = 0; s < 16; ++s) __stcs(o + s * GS, x[s]);
+            for (int s = 0; s < 16; ++s) st_inter(o + s * GS, x[s], a.keep);
         } else if (TILE0 && tid < NTH + (T < 32 ? 32 : T)) {
             // (T < 32: the group is padded to a warp, the extra threads repeat the work of the first T)
             const int j3 = (tid - NTH) % T;
@@ -521,6 +540,7 @@ struct RowsInvArgs {
     unsigned* bhist;        // (T, SEL_BINS)
     int regions;            // warp regions per frame = row blocks * 16 warps * 2
     int pf_dist;            // L2 prefetch distance in CTAs (0 = off), set by the launcher
+    int keep;               // cache policy of the intermediate (see st_inter)
 };
 
 // One complex inverse transform yields rows 2p and 2p + 1 of the map. Two thread mappings: the gather uses lanes
@@ -564,8 +584,8 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
             const float2* pa = Ia + ((size_t)(jg / TC) * NY + ya) * TC + (jg % TC);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                ga[m] = __ldcs(pa + m * tstride);
-                gb[m] = __ldcs(pa + m * tstride + TC);
+                ga[m] = ld_inter(pa + m * tstride, a.keep);
+                gb[m] = ld_inter(pa + m * tstride + TC, a.keep);
             }
         }
         // the rows of the CTA that takes this SM next (pf_dist CTAs ahead in launch order): RPC rows x 64 bytes in each of
@@ -706,6 +726,7 @@ struct RowsInvAcArgs {
     double norm_mult;
     double scale;
     ArgBest* best;          // (T, gridDim.x) argmax partials (nullable)
+    int keep;               // cache policy of the intermediate (see st_inter)
 };
 
 template <int NX>
@@ -739,10 +760,10 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
             const float2* p = Iz + (size_t)(jg / TC) * NY * TC + (jg % TC);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                za[m] = __ldcs(p + m * tstride + (size_t)ya * TC);
-                zam[m] = __ldcs(p + m * tstride + (size_t)ma * TC);
-                zb[m] = __ldcs(p + m * tstride + (size_t)yb * TC);
-                zbm[m] = __ldcs(p + m * tstride + (size_t)mb * TC);
+                za[m] = ld_inter(p + m * tstride + (size_t)ya * TC, a.keep);
+                zam[m] = ld_inter(p + m * tstride + (size_t)ma * TC, a.keep);
+                zb[m] = ld_inter(p + m * tstride + (size_t)yb * TC, a.keep);
+                zbm[m] = ld_inter(p + m * tstride + (size_t)mb * TC, a.keep);
             }
         }
         float nya = 0.f, nyb = 0.f;
@@ -1205,6 +1226,7 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     ProfScope ps(ctx, KC_ROWS_FWD);
     RowsFwdArgs b = a;
     b.pf_dist = rows_prefetch_dist(ctx);
+    b.keep = ctx->keep_mode;
     rows_fwd_kernel<NX><<<dim3(a.ny / ROWS, (unsigned)T), 512, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -1224,6 +1246,7 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     if (pf_pct < 0) { const char* e = getenv("B4D_COLS_PREFETCH"); pf_pct = e ? atoi(e) : 20; }
     ColsArgs b = a;
     b.pf_dist = ctx->sm_count * (1024 / (NY / 16 * CW)) * pf_pct / 100;
+    b.keep = ctx->keep_mode;
     cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -1275,6 +1298,7 @@ int launch_rows_inv_inst(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_block
     a.nblk = a.ny / rows;
     ProfScope ps(ctx, KC_ROWS_INV);
     a.pf_dist = rows_prefetch_dist(ctx);
+    a.keep = ctx->keep_mode;
     rows_inv_kernel<NX, MODE, ABS><<<dim3(grid_blocks > 0 ? grid_blocks : a.ny / rows, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
@@ -1297,6 +1321,7 @@ int launch_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& a, int64_t T, int* nblk_out)
     const int rows = 2 * FPC, nblk = (a.ny / 2 + 1 + rows - 1) / rows;
     if (a.ny % rows) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "ny=%d is not a multiple of %d rows per CTA", a.ny, rows);
     ProfScope ps(ctx, KC_ROWS_INV_AC);
+    a.keep = ctx->keep_mode;
     rows_inv_ac_kernel<NX><<<dim3(nblk, (unsigned)T), 512, smem, ctx->stream>>>(a);
     B4D_LAUNCH_CHECK(ctx);
     *nblk_out = nblk;
@@ -1348,14 +1373,15 @@ struct Work {
     long long* nvalid = nullptr;
 };
 
-int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work* w) {
+// tH / tA / tB: frames the three big intermediates are sized for (0 = T, the whole batch)
+int carve(b4d_ctx* ctx, int64_t T, int ny, int nx, bool needA, bool needB, Work* w, int64_t tH = 0, int64_t tA = 0, int64_t tB = 0) {
     const size_t per = (size_t)ny * (nx / 2) * sizeof(float2);
     void* p = nullptr;
-    int rc = b4d_scratch(ctx, SCR_SPEC_A, per * T, &p);
+    int rc = b4d_scratch(ctx, SCR_SPEC_A, per * (tH ? tH : T), &p);
     if (rc) return rc;
     w->H = static_cast<float2*>(p);
-    if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * T, &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
-    if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * T, &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
+    if (needA) { rc = b4d_scratch(ctx, SCR_SPEC_B, per * (tA ? tA : T), &p); if (rc) return rc; w->I2a = static_cast<float2*>(p); }
+    if (needB) { rc = b4d_scratch(ctx, SCR_SPEC_C, per * (tB ? tB : T), &p); if (rc) return rc; w->I2b = static_cast<float2*>(p); }
     const int ntiles = cols_tiles(ny, nx, false), nblk = ny;   // (upper bounds: narrow tiles; rows_inv CTAs per frame)
     size_t small = 0;
     auto take = [&](size_t bytes) { size_t o = small; small += (bytes + 255) & ~size_t(255); return o; };
@@ -1408,6 +1434,7 @@ int run_rows_fwd(b4d_ctx* ctx, const float* stack, int64_t T, int ny, int nx, co
     RowsFwdArgs a;
     a.stack = stack; a.gain = gain; a.dark = dark; a.pilot = use_pilot ? w.pilot : nullptr; a.H = w.H; a.ny = ny;
     a.mom = fr_moments ? w.mom : nullptr;
+    a.pf_dist = 0; a.keep = 0;
     rc = get_twiddle_bases(ctx, nx, &a.tw);
     if (rc) return rc;
     DISPATCH_N(nx, rc = launch_rows_fwd<N_>(ctx, a, T));
@@ -2029,7 +2056,10 @@ int gen_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int n
 
 }  // namespace
 
+void pipe_graphs_release(b4d_ctx* ctx);
+
 void b4d_fft_release(b4d_ctx* ctx) {
+    pipe_graphs_release(ctx);
     if (!ctx->fft) return;
     gen_release(static_cast<GenCache*>(ctx->fft->gen));
     if (ctx->fft->gref) cudaFree(ctx->fft->gref);
@@ -2307,12 +2337,24 @@ int fused_sample_blocks(int ny, int nx) {
     return ns < 1 ? 0 : ns;
 }
 
-// Inverse rows + tracker results with the |corr| map never written (fused median). `r` is set up for the full launch:
-// map A outputs as usual in pair mode; the |.| map is map B (pair) or map A (single), its argmax partials in w.bestB.
-int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int ny, int nx, int ns, float* scratch,
-                         int subpixel, double eps, double* out) {
+// Inverse rows + tracker results with the |corr| map never written (fused median), in three steps so that the row
+// passes can follow the column pass a few frames at a time:
+//   begin: scratch of the whole batch (tc frames), sample-block list;
+//   range: frames [t0, t0 + tcs) of the batch -- sample rows, bracket, census of every other row block, peak, and the
+//          three row blocks around the peak once more for the 3x3 neighbourhood. `r` is set up for a full launch over the
+//          range's frames (r.Ia = the range's first frame; map A = the |.| map, argmax partials in w.bestB, batch-wide);
+//   end:   exact medians from the candidates, results of the whole batch.
+struct TrackFused {
+    FusedMedian fm;
+    int ns, nblk, rpc, m;
+    float* samples;     // (tc, m)
+    float* window;      // (tc, 3 * rpc, nx)
+    int* blk3;          // (tc, 3)
+};
+
+int track_fused_begin(b4d_ctx* ctx, int64_t tc, int ny, int nx, int ns, float* scratch, TrackFused* tf) {
     const int nblk = rows_inv_blocks(nx, ny), rpc = ny / nblk;
-    const int m = ns * rpc * nx;
+    tf->ns = ns; tf->nblk = nblk; tf->rpc = rpc; tf->m = ns * rpc * nx;
     FftPlanCache* f = ctx->fft;
     if (f->blk_n != nblk || f->blk_ns != ns) {
         std::vector<int> h;
@@ -2324,39 +2366,64 @@ int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int n
         B4D_CUDA(ctx, cudaMemcpy(f->blk_list, h.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice));
         f->blk_n = nblk; f->blk_ns = ns;
     }
-    float* samples = scratch;                                   // (tc, m)
-    float* window = samples + (size_t)tc * m;                   // (tc, 3 * rpc, nx)
-    int* blk3 = reinterpret_cast<int*>(window + (size_t)tc * 3 * rpc * nx);   // (tc, 3)
-    FusedMedian fm;
+    tf->samples = scratch;
+    tf->window = tf->samples + (size_t)tc * tf->m;
+    tf->blk3 = reinterpret_cast<int*>(tf->window + (size_t)tc * 3 * rpc * nx);
+    return b4d_fused_median_begin(ctx, tc, nblk * 16 * 2, &tf->fm);
+}
+
+int track_fused_range(b4d_ctx* ctx, const Work& w, const TrackFused& tf, RowsInvArgs r, int64_t t0, int64_t tcs, int nx) {
+    const int nblk = tf.nblk, rpc = tf.rpc, ns = tf.ns, m = tf.m;
+    FftPlanCache* f = ctx->fft;
+    FusedMedian fm = tf.fm;
+    fm.st += t0; fm.need += t0; fm.bhist += (size_t)t0 * SEL_BINS; fm.cnt3 += (size_t)t0 * fm.regions * 3;
+    fm.cand += (size_t)t0 * ((size_t)fm.regions * FM_REGION + FM_SAMPLE_CAP);
+    float* samples = tf.samples + (size_t)t0 * m;
+    float* window = tf.window + (size_t)t0 * 3 * rpc * nx;
+    int* blk3 = tf.blk3 + t0 * 3;
+    r.bestA = w.bestB + (size_t)t0 * nblk;
     int rc;
-    if ((rc = b4d_fused_median_begin(ctx, tc, nblk * 16 * 2, &fm))) return rc;
-    // 1. sample rows: map A as usual, |.| rows into the compact sample buffer
+    // 1. sample rows: |.| rows into the compact sample buffer
     RowsInvArgs r1 = r;
     r1.blk_map = f->blk_list; r1.mag_mode = 1;
     r1.outA = samples;
-    if ((rc = run_rows_inv(ctx, r1, tc, nx, ns))) return rc;
+    if ((rc = run_rows_inv(ctx, r1, tcs, nx, ns))) return rc;
     // 2. bracket around the median + census of the sample rows
-    if ((rc = b4d_fused_median_bracket(ctx, fm, samples, m, tc))) return rc;
+    if ((rc = b4d_fused_median_bracket(ctx, fm, samples, m, tcs))) return rc;
     // 3. every other row block: census in the epilogue, no |.| map
     RowsInvArgs r2 = r;
     r2.blk_map = f->blk_list + ns; r2.mag_mode = 2;
     r2.sel = fm.st; r2.cand = fm.cand; r2.cnt3 = fm.cnt3; r2.bhist = fm.bhist; r2.regions = fm.regions;
-    if ((rc = run_rows_inv(ctx, r2, tc, nx, nblk - ns))) return rc;
+    if ((rc = run_rows_inv(ctx, r2, tcs, nx, nblk - ns))) return rc;
     // 4. peak, then the three row blocks around it once more for the 3x3 neighbourhood
-    argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestB, nblk, w.pk_idx, w.pk_val);
+    argmax_reduce_kernel<<<(unsigned)tcs, 128, 0, ctx->stream>>>(r.bestA, nblk, w.pk_idx + t0, w.pk_val + t0);
     B4D_LAUNCH_CHECK(ctx);
-    window_blocks_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(w.pk_idx, ny, nx, rpc, blk3, tc);
+    window_blocks_kernel<<<(unsigned)((tcs + 63) / 64), 64, 0, ctx->stream>>>(w.pk_idx + t0, r.ny, nx, rpc, blk3, tcs);
     B4D_LAUNCH_CHECK(ctx);
     RowsInvArgs r3 = r;
     r3.blk_map_pf = blk3; r3.mag_mode = 1; r3.bestA = nullptr;
     r3.outA = window;
-    if ((rc = run_rows_inv(ctx, r3, tc, nx, 3))) return rc;
+    return run_rows_inv(ctx, r3, tcs, nx, 3);
+}
+
+int track_fused_end(b4d_ctx* ctx, const Work& w, const TrackFused& tf, int64_t tc, int ny, int nx, int subpixel, double eps,
+                    double* out) {
     // 5. exact median from the candidates, results
-    if ((rc = b4d_fused_median_final(ctx, fm, tc, w.med, reinterpret_cast<int64_t*>(w.nvalid)))) return rc;
-    phase_finalize_window_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(window, blk3, rpc, w.pk_idx, ny, nx, w.med,
-                                                                                     w.nvalid, fm.need, subpixel, eps, out, tc);
+    int rc;
+    if ((rc = b4d_fused_median_final(ctx, tf.fm, tc, w.med, reinterpret_cast<int64_t*>(w.nvalid)))) return rc;
+    phase_finalize_window_kernel<<<(unsigned)((tc + 63) / 64), 64, 0, ctx->stream>>>(tf.window, tf.blk3, tf.rpc, w.pk_idx, ny, nx, w.med,
+                                                                                     w.nvalid, tf.fm.need, subpixel, eps, out, tc);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
+}
+
+int rows_inv_track_fused(b4d_ctx* ctx, Work& w, RowsInvArgs r, int64_t tc, int ny, int nx, int ns, float* scratch,
+                         int subpixel, double eps, double* out) {
+    TrackFused tf;
+    int rc;
+    if ((rc = track_fused_begin(ctx, tc, ny, nx, ns, scratch, &tf))) return rc;
+    if ((rc = track_fused_range(ctx, w, tf, r, 0, tc, nx))) return rc;
+    return track_fused_end(ctx, w, tf, tc, ny, nx, subpixel, eps, out);
 }
 
 size_t fused_scratch_floats(int ny, int nx, int ns, int64_t tc) {
@@ -2432,6 +2499,322 @@ bool side_stream_ready(b4d_ctx* ctx) {
     return ctx->ev_fork && ctx->ev_join;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Frame-pipelined schedule of the fused stack pipeline ("lanes")
+// -------------------------------------------------------------------------------------------------
+// A batch of 128 frames pushes 3.5 frames' worth of row <-> column intermediates per frame through HBM (2 - 4 GB per
+// batch against 126 MB of L2). Here the five big kernels run `sub` frames at a time instead, in the order
+//     reduce(s) -> rows_fwd(s) -> cols(s)                         on the caller's stream
+//                                  cols(s) -> rows_inv_ac(s)      on side stream A
+//                                  cols(s) -> tracker rows(s)     on side stream S (sample rows, bracket, census, window)
+// so that (a) the forward row pass finds the frames the reduction pass has just streamed in L2, (b) the column pass finds
+// the half spectra of the forward row pass there, (c) the two inverse row passes find the column pass's output there.
+// The intermediates live in ring slots of `sub` frames (one slot for the forward half spectra, `slots` for each inverse
+// branch) that are overwritten while still in L2; the per-frame kernels that never touch them (tail percentiles, final
+// medians, 3x3 fit, autocorrelation argmax, grain widths) run once per batch after the join, as before.
+struct Sched { int sub, lanes, slots, keep; };
+
+Sched pipeline_sched(b4d_ctx* ctx) {
+    static int e_sub = -2, e_lanes = -2, e_slots = -2, e_keep = -2;
+    if (e_sub == -2) {
+        const char* e = getenv("B4D_SUB"); e_sub = e ? atoi(e) : -1;
+        e = getenv("B4D_LANES"); e_lanes = e ? atoi(e) : -1;
+        e = getenv("B4D_SLOTS"); e_slots = e ? atoi(e) : -1;
+        e = getenv("B4D_KEEP"); e_keep = e ? atoi(e) : -1;
+    }
+    Sched sc;
+    sc.sub = ctx->sched_sub >= 0 ? ctx->sched_sub : (e_sub >= 0 ? e_sub : B4D_SCHED_SUB_DEFAULT);
+    sc.lanes = ctx->sched_lanes >= 1 ? ctx->sched_lanes : (e_lanes >= 1 ? e_lanes : 2);
+    sc.slots = ctx->sched_slots >= 1 ? ctx->sched_slots : (e_slots >= 1 ? e_slots : 1);
+    sc.keep = ctx->sched_keep >= 0 ? ctx->sched_keep : (e_keep >= 0 ? e_keep : 1);
+    if (sc.slots > 8) sc.slots = 8;
+    if (sc.lanes > 8) sc.lanes = 8;
+    return sc;
+}
+
+// streams: lane l owns lane_streams[3 l .. 3 l + 2] = (columns, autocorrelation rows, tracker rows); lane 0's first
+// stream is the caller's. events: per lane 3 slots-wide rings (columns done, autocorrelation rows done, tracker rows
+// done) + 3 joins, then one fork event.
+bool lanes_ready(b4d_ctx* ctx, int lanes, int slots) {
+    const size_t ns = 3 * (size_t)lanes;
+    while (ctx->lane_streams.size() < ns) {
+        cudaStream_t st;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // the inverse row passes drain intermediates: they go first whenever an SM has room
+        const int prio = (ctx->lane_streams.size() % 3) ? hi : lo;
+        if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess) return false;
+        ctx->lane_streams.push_back(st);
+    }
+    const size_t need = (size_t)lanes * (3 * (size_t)slots + 3) + 1;
+    while (ctx->lane_ev.size() < need) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+        ctx->lane_ev.push_back(e);
+    }
+    return true;
+}
+
+int pipeline_batch_lanes(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t tc, int ny, int nx, const float* gain,
+                         const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
+                         double q_lo, double q_hi, double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out,
+                         float* ac_out, double* grain_out, double* track_out, int ns) {
+    const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
+    const size_t npix = (size_t)ny * nx, per = (size_t)ny * (nx / 2);
+    const int64_t F = sc.sub;
+    const int NB = sc.slots, L = sc.lanes;
+    int rc;
+    Work w;
+    if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w, F * L, F * NB * L, F * NB * L))) return rc;
+    void* p = nullptr;
+    const size_t mag_floats = !want_pc ? 0 : ((fused_scratch_floats(ny, nx, ns, tc) + 63) & ~size_t(63));
+    const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) + sizeof(double) * B4D_FR_NCOLS * tc + 256;
+    if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
+    double* fr = static_cast<double*>(p);
+    float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
+    float* acm = ac_out ? ac_out : mag + mag_floats;
+    double* frp = fr_out ? fr_out : fr;
+    const bool reduced = fr_out || want_pc || quant_out;
+    if (grain_out && (rc = ensure_theta(ctx))) return rc;
+    // twiddle tables are created on first use with a blocking copy: do that before anything is in flight
+    { const float2* tw; if ((rc = get_twiddle_bases(ctx, nx, &tw)) || (rc = get_twiddle_bases(ctx, ny, &tw))) return rc; }
+
+    cudaStream_t M0 = ctx->stream;
+    const int EPL = 3 * NB + 3;                           // events per lane
+    cudaEvent_t* ev = ctx->lane_ev.data();
+    cudaEvent_t e_pre = ev[(size_t)L * EPL];
+    auto Ms = [&](int l) { return l == 0 ? M0 : ctx->lane_streams[3 * l]; };
+    auto As = [&](int l) { return ctx->lane_streams[3 * l + 1]; };
+    auto Ss = [&](int l) { return ctx->lane_streams[3 * l + 2]; };
+
+    FrPlan pl;
+    FrTails tl = {q_lo, q_hi, quant_out, nvalid_out};
+    if (reduced && (rc = b4d_fr_begin(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp, quant_out ? &tl : nullptr, w.pilot, &pl)))
+        return rc;
+    TrackFused tf;
+    if (want_pc && (rc = track_fused_begin(ctx, tc, ny, nx, ns, mag, &tf))) return rc;
+    const int64_t n_sub = (tc + F - 1) / F;
+    const int lanes_used = (int)(n_sub < L ? n_sub : L);
+    B4D_CUDA(ctx, cudaEventRecord(e_pre, M0));
+    for (int l = 0; l < lanes_used; ++l) {
+        if (l > 0) B4D_CUDA(ctx, cudaStreamWaitEvent(Ms(l), e_pre, 0));
+        if (want_ac) B4D_CUDA(ctx, cudaStreamWaitEvent(As(l), e_pre, 0));
+        if (want_pc) B4D_CUDA(ctx, cudaStreamWaitEvent(Ss(l), e_pre, 0));
+    }
+
+    const int rows_cta = ny / rows_inv_blocks(nx, ny), nblk_ac = (ny / 2 + 1 + rows_cta - 1) / rows_cta;
+    ctx->keep_mode = sc.keep;
+    auto body = [&]() -> int {
+        int r_;
+        int64_t a = 0;
+        for (int64_t s = 0; a < tc; ++s, a += F) {
+            const int64_t f = tc - a < F ? tc - a : F;
+            const int l = (int)(s % L), slot = (int)((s / L) % NB);
+            cudaStream_t M = Ms(l), A = As(l), S = Ss(l);
+            cudaEvent_t* e_cols = ev + (size_t)l * EPL;
+            cudaEvent_t* e_ac = e_cols + NB;
+            cudaEvent_t* e_tr = e_cols + 2 * NB;
+            ctx->stream = M;
+            if (reduced && (r_ = b4d_fr_range(ctx, pl, a, f))) return r_;
+            if (!(psd_out || want_ac || want_pc)) continue;
+            Work ws = w;
+            ws.pilot = w.pilot + a;
+            ws.H = w.H + (size_t)l * F * per;
+            if ((r_ = run_rows_fwd(ctx, s0 + (size_t)a * npix, f, ny, nx, gain, dark, ws, true, reduced))) return r_;
+            if (s / L >= NB) {                            // the slot's previous tenants must have been consumed
+                if (want_ac) B4D_CUDA(ctx, cudaStreamWaitEvent(M, e_ac[slot], 0));
+                if (want_pc) B4D_CUDA(ctx, cudaStreamWaitEvent(M, e_tr[slot], 0));
+            }
+            ColsArgs c = cols_defaults(ws, nx, true);
+            c.psd_out = psd_out ? psd_out + (size_t)a * npix : nullptr;
+            c.psd_scale = psd_scale;
+            const int ntl = cols_tiles(ny, nx, cols_wide_out(c));
+            float2* i2a = want_ac ? w.I2a + (size_t)(l * NB + slot) * F * per : nullptr;
+            float2* i2b = want_pc ? w.I2b + (size_t)(l * NB + slot) * F * per : nullptr;
+            if (want_ac) { c.i2_ac = i2a; c.i2_ac_nyq = w.I2nyq + (size_t)a * ny; c.ac_partials = w.acp + (size_t)a * ntl; }
+            if (want_pc) {
+                c.i2_pc = i2b;
+                c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
+                c.whiten = 1; c.eps = (float)eps; c.fr = frp + a * B4D_FR_NCOLS; c.fr_stride = B4D_FR_NCOLS;
+            }
+            c.zero_dc = 0;
+            c.ac_zero_dc = 1;
+            if ((r_ = run_cols(ctx, c, f, ny))) return r_;
+            B4D_CUDA(ctx, cudaEventRecord(e_cols[slot], M));
+            if (want_ac) {
+                B4D_CUDA(ctx, cudaStreamWaitEvent(A, e_cols[slot], 0));
+                ctx->stream = A;
+                RowsInvAcArgs ra;
+                memset(&ra, 0, sizeof(ra));
+                ra.Iz = i2a; ra.Inyq = w.I2nyq + (size_t)a * ny; ra.ny = ny; ra.ch_log2 = log2i(cols_cw(ny, cols_wide_out(c)) / 2);
+                ra.out = acm + (size_t)a * npix; ra.norm = w.acp + (size_t)a * ntl; ra.n_norm = ntl; ra.norm_mult = 1.0;
+                ra.scale = 1.0 / ((double)nx * ny);
+                ra.best = grain_out ? w.bestA + (size_t)a * nblk_ac : nullptr;
+                int nb_ = 0;
+                r_ = run_rows_inv_ac(ctx, ra, f, nx, &nb_);
+                if (!r_ && cudaEventRecord(e_ac[slot], A) != cudaSuccess) r_ = b4d_fail(ctx, B4D_ERR_CUDA, "cudaEventRecord failed");
+                if (r_) return r_;
+            }
+            if (want_pc) {
+                B4D_CUDA(ctx, cudaStreamWaitEvent(S, e_cols[slot], 0));
+                ctx->stream = S;
+                RowsInvArgs r;
+                memset(&r, 0, sizeof(r));
+                r.ny = ny; r.Ia = i2b; r.outA = nullptr; r.kindA = 1; r.scaleA = 1.0 / ((double)nx * ny); r.bestA = w.bestB;
+                r_ = track_fused_range(ctx, w, tf, r, a, f, nx);
+                if (!r_ && cudaEventRecord(e_tr[slot], S) != cudaSuccess) r_ = b4d_fail(ctx, B4D_ERR_CUDA, "cudaEventRecord failed");
+                if (r_) return r_;
+            }
+        }
+        return B4D_OK;
+    };
+    rc = body();
+    ctx->stream = M0;
+    ctx->keep_mode = 0;
+    // joined on every path: the side streams' work is in flight and the scratch is reused
+    for (int l = 0; l < lanes_used; ++l) {
+        cudaEvent_t* ej = ev + (size_t)l * EPL + 3 * NB;
+        bool ok = true;
+        if (l > 0) ok = ok && cudaEventRecord(ej[0], Ms(l)) == cudaSuccess && cudaStreamWaitEvent(M0, ej[0], 0) == cudaSuccess;
+        if (want_ac) ok = ok && cudaEventRecord(ej[1], As(l)) == cudaSuccess && cudaStreamWaitEvent(M0, ej[1], 0) == cudaSuccess;
+        if (want_pc) ok = ok && cudaEventRecord(ej[2], Ss(l)) == cudaSuccess && cudaStreamWaitEvent(M0, ej[2], 0) == cudaSuccess;
+        if (!ok && !rc) rc = b4d_fail(ctx, B4D_ERR_CUDA, "joining the lane streams failed");
+    }
+    if (rc) return rc;
+    if (reduced && (rc = b4d_fr_end(ctx, pl))) return rc;
+    if (want_pc && (rc = track_fused_end(ctx, w, tf, tc, ny, nx, subpixel, eps, track_out))) return rc;
+    if (grain_out) {
+        argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac, w.pk_idx2, w.pk_val2);
+        B4D_LAUNCH_CHECK(ctx);
+        ProfScope ps(ctx, KC_GRAIN);
+        grain_kernel<<<(unsigned)tc, 1024, 0, ctx->stream>>>(acm, ny, w.pk_idx2, ctx->fft->theta, 0.36787944117144233, grain_out);
+        B4D_LAUNCH_CHECK(ctx);
+    }
+    return B4D_OK;
+}
+
+// ---- CUDA graphs of the pipelined schedule -------------------------------------------------------------
+struct PipeKey {                      // everything the captured launches depend on (compared bytewise: zero it first)
+    const void* p[16];
+    int64_t tc;
+    double d[6];
+    float psd_scale;
+    int i[8];
+    void* scratch[10];
+};
+struct PipeGraph {
+    PipeKey key;
+    int seen = 0;
+    bool bad = false;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    uint64_t last_use = 0;
+};
+struct PipeGraphCache {
+    std::vector<PipeGraph> entries;
+    uint64_t clock = 0;
+};
+
+bool graphs_enabled(b4d_ctx* ctx) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("B4D_GRAPHS"); env = e ? atoi(e) : -1; }
+    const int v = ctx->use_graphs >= 0 ? ctx->use_graphs : (env >= 0 ? env : 1);
+    if (!v || ctx->prof_on) return false;
+    if (!ctx->pipe && cudaStreamCreateWithFlags(&ctx->pipe, cudaStreamNonBlocking) != cudaSuccess) { ctx->pipe = nullptr; return false; }
+    if (!ctx->ev_in && cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (!ctx->ev_out && cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+}
+
+void pipe_graphs_release(b4d_ctx* ctx) {
+    PipeGraphCache* c = static_cast<PipeGraphCache*>(ctx->pipe_graphs);
+    if (!c) return;
+    for (auto& e : c->entries) if (e.exec) cudaGraphExecDestroy(e.exec);
+    delete c;
+    ctx->pipe_graphs = nullptr;
+}
+
+// One batch of the pipelined schedule: directly the first time a set of arguments is seen (scratch arenas, tables and
+// function attributes are created then), captured on the second, replayed from then on.
+int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t tc, int ny, int nx, const float* gain,
+                               const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
+                               double q_lo, double q_hi, double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out,
+                               float* ac_out, double* grain_out, double* track_out, int ns) {
+    auto direct = [&]() {
+        return pipeline_batch_lanes(ctx, sc, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
+                                    fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out, ns);
+    };
+    if (!graphs_enabled(ctx)) return direct();
+    if (!ctx->pipe_graphs) ctx->pipe_graphs = new PipeGraphCache();
+    PipeGraphCache* cache = static_cast<PipeGraphCache*>(ctx->pipe_graphs);
+    PipeKey key;
+    memset(&key, 0, sizeof(key));
+    const void* ptrs[] = {s0, gain, dark, fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out,
+                          ctx->fft ? ctx->fft->ref : nullptr, ctx->fft ? ctx->fft->ref_nyq : nullptr,
+                          ctx->fft ? ctx->fft->blk_list : nullptr, ctx->fft ? ctx->fft->theta : nullptr};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
+    key.tc = tc;
+    key.d[0] = sat_value == sat_value ? sat_value : -1.2345e300; key.d[1] = zero_eps; key.d[2] = eps; key.d[3] = q_lo; key.d[4] = q_hi;
+    key.psd_scale = psd_scale;
+    key.i[0] = ny; key.i[1] = nx; key.i[2] = subpixel; key.i[3] = ns; key.i[4] = sc.sub; key.i[5] = sc.slots; key.i[6] = sc.keep; key.i[7] = sc.lanes;
+    PipeGraph* ent = nullptr;
+    auto refresh_scratch = [&](PipeKey& k) { for (int i = 0; i < 10; ++i) k.scratch[i] = ctx->scratch[i]; };
+    auto refresh_tables = [&](PipeKey& k) { k.p[12] = ctx->fft ? ctx->fft->blk_list : nullptr; k.p[13] = ctx->fft ? ctx->fft->theta : nullptr; };
+    refresh_scratch(key);
+    for (auto& e : cache->entries) if (memcmp(&e.key, &key, sizeof(key)) == 0) { ent = &e; break; }
+    if (!ent) {
+        // first sight (or the scratch arenas moved since): run directly, remember the arguments with the arenas as they
+        // are AFTER the run -- a capture must find everything allocated
+        int rc = direct();
+        if (rc) return rc;
+        refresh_scratch(key);
+        refresh_tables(key);
+        for (auto& e : cache->entries) if (memcmp(&e.key, &key, sizeof(key)) == 0) return B4D_OK;
+        if (cache->entries.size() >= 16) {
+            size_t lru = 0;
+            for (size_t i = 1; i < cache->entries.size(); ++i) if (cache->entries[i].last_use < cache->entries[lru].last_use) lru = i;
+            if (cache->entries[lru].exec) { cudaStreamSynchronize(ctx->pipe); cudaGraphExecDestroy(cache->entries[lru].exec); }
+            cache->entries.erase(cache->entries.begin() + lru);
+        }
+        PipeGraph g;
+        g.key = key; g.seen = 1; g.last_use = ++cache->clock;
+        cache->entries.push_back(g);
+        return B4D_OK;
+    }
+    ent->last_use = ++cache->clock;
+    if (ent->bad) return direct();
+    cudaStream_t M = ctx->stream;
+    if (!ent->exec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->pipe, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ent->bad = true; return direct(); }
+        const int64_t l0 = ctx->launches;
+        ctx->stream = ctx->pipe;
+        int rc = direct();
+        ctx->stream = M;
+        const cudaError_t ee = cudaStreamEndCapture(ctx->pipe, &graph);
+        bool moved = false;
+        for (int i = 0; i < 10; ++i) moved = moved || key.scratch[i] != ctx->scratch[i];
+        if (rc || ee != cudaSuccess || !graph || moved || cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ent->exec = nullptr;
+            ent->bad = true;
+            ctx->launches = l0;
+            return direct();
+        }
+        cudaGraphDestroy(graph);
+        ent->launches = ctx->launches - l0;
+        ctx->launches = l0;
+    }
+    B4D_CUDA(ctx, cudaEventRecord(ctx->ev_in, M));
+    B4D_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe, ctx->ev_in, 0));
+    B4D_CUDA(ctx, cudaGraphLaunch(ent->exec, ctx->pipe));
+    B4D_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->pipe));
+    B4D_CUDA(ctx, cudaStreamWaitEvent(M, ctx->ev_out, 0));
+    ctx->launches += ent->launches;
+    return B4D_OK;
+}
+
 extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                   const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
                                   double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
@@ -2460,12 +2843,22 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
     for (int64_t t0 = 0; t0 < n_frames; t0 += B) {
         const int64_t tc = n_frames - t0 < B ? n_frames - t0 : B;
         const float* s0 = stack + (size_t)t0 * npix;
+        // tracker: fused median (sample rows + 3x3 window instead of the |corr| map) unless the frame is too small
+        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx) : 0;
+        const Sched sc = pipeline_sched(ctx);
+        if (sc.sub > 0 && sc.sub < tc && (!want_pc || ns > 0) && lanes_ready(ctx, sc.lanes, sc.slots)) {
+            rc = pipeline_batch_lanes_graph(ctx, sc, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
+                                      fr_out ? fr_out + t0 * B4D_FR_NCOLS : nullptr, quant_out ? quant_out + 4 * t0 : nullptr,
+                                      quant_out ? nvalid_out + t0 : nullptr, psd_out ? psd_out + (size_t)t0 * npix : nullptr,
+                                      ac_out ? ac_out + (size_t)t0 * npix : nullptr, grain_out ? grain_out + t0 * 4 : nullptr,
+                                      track_out ? track_out + t0 * 4 : nullptr, ns);
+            if (rc) return rc;
+            continue;
+        }
         Work w;
         if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w))) return rc;
         // scratch maps: |corr| always, autocorr when the caller does not keep it
         void* p = nullptr;
-        // tracker: fused median (sample rows + 3x3 window instead of the |corr| map) unless the frame is too small
-        const int ns = (want_pc && ctx->fused_median) ? fused_sample_blocks(ny, nx) : 0;
         const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, ns, tc) + 63) & ~size_t(63)) : npix * tc);
         const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) +
                             sizeof(double) * B4D_FR_NCOLS * tc + 256;
@@ -2475,14 +2868,36 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
         float* acm = ac_out ? ac_out + (size_t)t0 * npix : mag + mag_floats;
         double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : fr;
         const bool reduced = fr_out || want_pc || quant_out;
+        // The reduction pass and the forward row pass both stream the frames. They alternate `pair` frames at a time, so
+        // that the row pass finds in L2 what the reduction pass has just read from HBM (one HBM read of every frame
+        // instead of two); the per-frame tail kernels of the reductions run once per batch after the last pair.
+        static int pair_env = -2;
+        if (pair_env == -2) { const char* e = getenv("B4D_PAIR"); pair_env = e ? atoi(e) : B4D_PAIR_DEFAULT; }
+        const int64_t pair = (ctx->sched_pair >= 0 ? ctx->sched_pair : pair_env);
+        const bool need_fft = psd_out || want_ac || want_pc;
         if (reduced) {
             FrTails tl = {q_lo, q_hi, quant_out ? quant_out + 4 * t0 : nullptr, quant_out ? nvalid_out + t0 : nullptr};
-            if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp, quant_out ? &tl : nullptr,
-                                              w.pilot)))
-                return rc;
-        }
-        if (!(psd_out || want_ac || want_pc)) continue;
-        if ((rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true, reduced))) return rc;
+            if (pair > 0 && pair < tc && need_fft) {
+                FrPlan pl;
+                if ((rc = b4d_fr_begin(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp, quant_out ? &tl : nullptr, w.pilot, &pl)))
+                    return rc;
+                for (int64_t a = 0; a < tc; a += pair) {
+                    const int64_t f = tc - a < pair ? tc - a : pair;
+                    if ((rc = b4d_fr_range(ctx, pl, a, f))) return rc;
+                    Work ws = w;
+                    ws.pilot = w.pilot + a;
+                    ws.H = w.H + (size_t)a * ny * (nx / 2);
+                    if ((rc = run_rows_fwd(ctx, s0 + (size_t)a * npix, f, ny, nx, gain, dark, ws, true, true))) return rc;
+                }
+                if ((rc = b4d_fr_end(ctx, pl))) return rc;
+            } else {
+                if ((rc = b4d_frame_reductions_ex(ctx, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, frp, quant_out ? &tl : nullptr,
+                                                  w.pilot)))
+                    return rc;
+                if (need_fft && (rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true, true))) return rc;
+            }
+        } else if (need_fft && (rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true, false))) return rc;
+        if (!need_fft) continue;
         ColsArgs c = cols_defaults(w, nx, true);
         c.psd_out = psd_out ? psd_out + (size_t)t0 * npix : nullptr;
         c.psd_scale = psd_scale;

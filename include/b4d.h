@@ -59,8 +59,28 @@ int b4d_device_sm_count(b4d_ctx* ctx);
 int b4d_profile_begin(b4d_ctx* ctx);
 int b4d_profile_end(b4d_ctx* ctx, double* ms_per_class, int64_t* launches_per_class);
 const char* b4d_profile_class_name(int klass);
-/* Frames per internal batch of the FFT pipeline (0 = automatic, sized so intermediates stay in L2). */
+/* Frames per internal batch of the FFT pipeline (0 = automatic: as many as a quarter of the free HBM holds, at most 128). */
 int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames);
+/*
+ * Schedule of b4d_stack_pipeline inside a batch (replaces the per-frame loop of metrics/speckles.py:300-325,347-386).
+ * sub_frames > 0: the big kernels run sub_frames frames at a time, the steps dealt round-robin to `lanes` (1..8)
+ * independent lanes; in a lane, reduce -> rows -> columns run on one stream and the two inverse row passes follow the
+ * column pass on two more, through ring_slots (1..8) ring slots of intermediates per lane, so that every intermediate
+ * is consumed from L2 instead of HBM while the lanes fill one another's launch gaps.  keep = cache-policy bits of the
+ * intermediates (1 stores stay in L2, 2 loads keep normal priority, 4 the column pass discards its consumed tiles).
+ * sub_frames = 0: whole batches, one kernel after the other.  use_graphs != 0: the second call with identical
+ * arguments captures the batch's launches in a CUDA graph and later calls replay it (the host cannot issue ~10
+ * launches per 1 - 2 frames as fast as the GPU runs them); calls bracketed by b4d_profile_begin/end always launch
+ * directly.  A negative value of any argument selects the built-in default (environment: B4D_SUB, B4D_LANES,
+ * B4D_SLOTS, B4D_KEEP, B4D_GRAPHS).  Results do not depend on the schedule.
+ */
+int b4d_set_schedule(b4d_ctx* ctx, int sub_frames, int lanes, int ring_slots, int keep, int use_graphs);
+/*
+ * Whole-batch schedule: the reduction pass and the forward row pass alternate pair_frames frames at a time, so that the
+ * second finds in L2 the frames the first has just read from HBM (0 = one pass over the whole batch each; negative =
+ * default / B4D_PAIR).  Results do not depend on it.
+ */
+int b4d_set_pairing(b4d_ctx* ctx, int pair_frames);
 
 /* Plain device-memory helpers so that a non-Python host can drive the library. */
 int b4d_malloc(b4d_ctx* ctx, size_t bytes, void** out);
