@@ -77,8 +77,13 @@ _SIGNATURES = {
     "b4d_template_match": [_vp, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _f64, _f64, _i32, _f64, _vp],
     "b4d_phase_set_reference": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64],
     "b4d_phase_track": [_vp, _vp, _i64, _i32, _i32, _i32, _f64, _vp],
+    "b4d_phase_reference_create": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, C.POINTER(_vp)],
+    "b4d_phase_reference_destroy": [_vp, _vp],
+    "b4d_phase_track_ref": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f64, _i32, _vp],
     "b4d_stack_pipeline": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64, _f64, _f64,
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "b4d_stack_pipeline_ref": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64, _f64, _f64,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b4d_frame_reductions_tails": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f64, _f64, _vp, _vp, _vp],
 }
 _RESTYPES = {"b4d_profile_class_name": C.c_char_p, "b4d_last_error": C.c_char_p, "b4d_version": C.c_char_p, "b4d_launch_count": _i64}
@@ -109,14 +114,50 @@ def load_library(path: str | None = None) -> C.CDLL:
         return lib
 
 
+# entry points that do no stream-ordered work: the bound library does not re-install the stream for them
+_NO_STREAM = {"b4d_create", "b4d_destroy", "b4d_set_stream", "b4d_last_error", "b4d_version", "b4d_launch_count",
+              "b4d_device_sm_count", "b4d_profile_class_name", "b4d_set_batch_frames", "b4d_set_schedule", "b4d_set_pairing",
+              "b4d_set_fused_median"}
+
+
+class _BoundLib:
+    """The library as one context sees it: every compute call installs the calling thread's current torch stream and
+    runs under the context's (re-entrant) Python lock, so that `set stream` + `launch` is one step even when several
+    threads share the context (the reference drives per-frame calls from joblib threads, metrics/speckles.py:323)."""
+
+    def __init__(self, ctx: "Context", raw):
+        self._ctx, self._raw, self._fns = ctx, raw, {}
+
+    def __getattr__(self, name):
+        fn = self._fns.get(name)
+        if fn is None:
+            raw_fn = getattr(self._raw, name)
+            if name in _NO_STREAM:
+                fn = raw_fn
+            else:
+                ctx, raw = self._ctx, self._raw
+
+                def fn(*args, _f=raw_fn):
+                    import torch
+                    with ctx.lock:
+                        if ctx.pin_stream is None:
+                            raw.b4d_set_stream(ctx.handle, _vp(torch.cuda.current_stream(ctx.device).cuda_stream))
+                        return _f(*args)
+            self._fns[name] = fn
+        return fn
+
+
 class Context:
     """One libb4d context = (device, stream, scratch).  Calls on one context are serialised."""
 
     def __init__(self, device: int):
-        self.lib = load_library()
+        self.raw = load_library()
+        self.lib = _BoundLib(self, self.raw)
+        self.lock = threading.RLock()
+        self.pin_stream = None      # set by use_stream(): launches go to that stream whatever torch's current stream is
         self.device = int(device)
         h = _vp()
-        rc = self.lib.b4d_create(self.device, C.byref(h))
+        rc = self.raw.b4d_create(self.device, C.byref(h))
         if rc != 0 or not h.value:
             raise B4DError(f"b4d_create(device={device}) failed with status {rc} "
                            "(is a CUDA device visible?)")
@@ -134,9 +175,11 @@ class Context:
         raise B4DError(f"{what} failed (status {rc}): {text}")
 
     def use_current_stream(self):
+        """Kept for callers of round 1: every compute call now installs the calling thread's current stream itself."""
         import torch
         s = torch.cuda.current_stream(self.device).cuda_stream
-        self.check(self.lib.b4d_set_stream(self.handle, _vp(s)), "b4d_set_stream")
+        with self.lock:
+            self.check(self.raw.b4d_set_stream(self.handle, _vp(s)), "b4d_set_stream")
 
     def profile_begin(self):
         self.check(self.lib.b4d_profile_begin(self.handle), "b4d_profile_begin")
@@ -170,7 +213,7 @@ class Context:
     def __del__(self):
         try:
             if getattr(self, "handle", None) is not None and self.handle.value:
-                self.lib.b4d_destroy(self.handle)
+                self.raw.b4d_destroy(self.handle)
                 self.handle = _vp()
         except Exception:
             pass
@@ -189,7 +232,7 @@ def require_cuda():
 
 
 def default_device() -> int:
-    """Device index: $B4D_DEVICE, else $LOCAL_RANK (torchrun), else the current torch device."""
+    """Device index: $B4D_DEVICE, else the current torch device (under torchrun: what torch.cuda.set_device(LOCAL_RANK) chose)."""
     torch = require_cuda()
     env = os.environ.get("B4D_DEVICE")
     if env is not None:
@@ -205,7 +248,6 @@ def get_context(device: int | None = None) -> Context:
         if ctx is None:
             ctx = Context(dev)
             _contexts[dev] = ctx
-    ctx.use_current_stream()
     return ctx
 
 
@@ -238,6 +280,8 @@ def as_device_f32(a, device: int | None = None):
     types (uint8/uint16/int16/int32/uint32) cross PCIe in their own width and are widened on the device."""
     torch = require_cuda()
     dev = default_device() if device is None else int(device)
+    if (isinstance(a, torch.Tensor) and a.is_complex()) or (not isinstance(a, torch.Tensor) and np.iscomplexobj(a)):
+        raise TypeError("complex input is not supported on this path (real frames only)")
     if not isinstance(a, torch.Tensor):
         arr = np.asarray(a)
         code = native_int_code(arr.dtype)

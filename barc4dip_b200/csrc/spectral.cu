@@ -2264,10 +2264,83 @@ extern "C" int b4d_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t
     return B4D_OK;
 }
 
+// A tracker reference owned by its creator (b4d_phase_reference_create): the conjugate spectrum of the z-scored,
+// embedded template, in the layout the column pass reads (powers of two) or in natural order (any other size).
+void pipe_graphs_release(b4d_ctx* ctx);
+
+struct b4d_ref {
+    float2* ref = nullptr;
+    float2* ref_nyq = nullptr;
+    float2* gref = nullptr;
+    size_t gref_elems = 0;
+    int ny = 0, nx = 0;
+};
+
+namespace {
+// Installs a reference's buffers as the context's current reference for the duration of one (locked) call.
+struct RefSwap {
+    FftPlanCache* f;
+    float2 *ref, *ref_nyq, *gref;
+    size_t gref_elems;
+    int ny, nx;
+    RefSwap(b4d_ctx* ctx, const b4d_ref* r) {
+        if (!ctx->fft) ctx->fft = new FftPlanCache();
+        f = ctx->fft;
+        ref = f->ref; ref_nyq = f->ref_nyq; gref = f->gref; gref_elems = f->gref_elems; ny = f->ref_ny; nx = f->ref_nx;
+        if (r) { f->ref = r->ref; f->ref_nyq = r->ref_nyq; f->gref = r->gref; f->gref_elems = r->gref_elems; f->ref_ny = r->ny; f->ref_nx = r->nx; }
+        else { f->ref = nullptr; f->ref_nyq = nullptr; f->gref = nullptr; f->gref_elems = 0; f->ref_ny = 0; f->ref_nx = 0; }
+    }
+    ~RefSwap() { f->ref = ref; f->ref_nyq = ref_nyq; f->gref = gref; f->gref_elems = gref_elems; f->ref_ny = ny; f->ref_nx = nx; }
+};
+}  // namespace
+
+int phase_set_reference_body(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0, double eps);
+
 extern "C" int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0,
                                        double eps) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
+    return phase_set_reference_body(ctx, tpl, h, w, ny, nx, y0, x0, eps);
+}
+
+extern "C" int b4d_phase_reference_create(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0,
+                                          double eps, b4d_ref** out) {
+    if (!ctx || !out) return B4D_ERR_INVALID;
+    B4dCall g(ctx);
+    *out = nullptr;
+    int rc;
+    b4d_ref* r = new b4d_ref();
+    {
+        RefSwap sw(ctx, nullptr);                     // the context's own reference is put aside, fresh buffers are made
+        rc = phase_set_reference_body(ctx, tpl, h, w, ny, nx, y0, x0, eps);
+        FftPlanCache* f = ctx->fft;
+        r->ref = f->ref; r->ref_nyq = f->ref_nyq; r->gref = f->gref; r->gref_elems = f->gref_elems; r->ny = f->ref_ny; r->nx = f->ref_nx;
+    }
+    if (rc) {
+        if (r->ref) cudaFree(r->ref);
+        if (r->ref_nyq) cudaFree(r->ref_nyq);
+        if (r->gref) cudaFree(r->gref);
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return B4D_OK;
+}
+
+extern "C" int b4d_phase_reference_destroy(b4d_ctx* ctx, b4d_ref* r) {
+    if (!ctx) return B4D_ERR_INVALID;
+    if (!r) return B4D_OK;
+    B4dCall g(ctx);
+    cudaDeviceSynchronize();                          // (launches that read it may be in flight on any of the context's streams)
+    pipe_graphs_release(ctx);                         // captured batches carry its pointers
+    if (r->ref) cudaFree(r->ref);
+    if (r->ref_nyq) cudaFree(r->ref_nyq);
+    if (r->gref) cudaFree(r->gref);
+    delete r;
+    return B4D_OK;
+}
+
+int phase_set_reference_body(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx, int y0, int x0, double eps) {
     if (h < 1 || w < 1 || y0 < 0 || x0 < 0 || y0 + h > ny || x0 + w > nx)
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_set_reference: template does not fit the frame");
     if (!pow2_sides(ny, nx)) {
@@ -2433,10 +2506,28 @@ size_t fused_scratch_floats(int ny, int nx, int ns, int64_t tc) {
 
 }  // namespace
 
+int phase_track_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps, double* out);
+
 extern "C" int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps,
                                double* out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
+    return phase_track_body(ctx, stack, n_frames, ny, nx, subpixel, eps, out);
+}
+
+extern "C" int b4d_phase_track_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
+                                   int subpixel, double eps, int map_median, double* out) {
+    if (!ctx || !ref) return B4D_ERR_INVALID;
+    B4dCall g(ctx);
+    RefSwap sw(ctx, ref);
+    const bool fm = ctx->fused_median;
+    if (map_median) ctx->fused_median = false;
+    const int rc = phase_track_body(ctx, stack, n_frames, ny, nx, subpixel, eps, out);
+    ctx->fused_median = fm;
+    return rc;
+}
+
+int phase_track_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, int subpixel, double eps, double* out) {
     if (!out) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_phase_track: null output");
     if (!pow2_sides(ny, nx)) {
         int rcg = check_gen_args(ctx, "b4d_phase_track", stack, n_frames, ny, nx);
@@ -2815,12 +2906,37 @@ int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, i
     return B4D_OK;
 }
 
+int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                        const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
+                        double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
+                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out);
+
 extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                   const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
                                   double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
                                   int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
+    return stack_pipeline_body(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
+                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out);
+}
+
+extern "C" int b4d_stack_pipeline_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
+                                      const float* gain, const float* dark, double sat_value, double zero_eps, float psd_scale,
+                                      int subpixel, double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
+                                      int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
+    if (!ctx) return B4D_ERR_INVALID;
+    B4dCall g(ctx);
+    if (track_out && !ref) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline_ref: tracking needs a reference");
+    RefSwap sw(ctx, ref);
+    return stack_pipeline_body(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
+                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out);
+}
+
+int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
+                        const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
+                        double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
+                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
     if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: grain widths need square frames");
     if (quant_out && (!nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0)))

@@ -292,11 +292,13 @@ def xcorr2d(a, b, *, remove_mean: bool = True, standardize: bool = False, normal
 
 
 class PhaseTracker:
-    """Phase-correlation tracker bound to one reference template (cached as a conjugate spectrum)."""
+    """Phase-correlation tracker bound to one reference template. The tracker OWNS the conjugate spectrum of its template
+    (b4d_phase_reference_create): any number of trackers may be alive on a device, none re-targets another."""
 
     def __init__(self, template, frame_shape, *, y0: int, x0: int, eps: float = 1e-9, device: int | None = None):
         self.dev = _lib.default_device() if device is None else int(device)
         self.ny, self.nx = int(frame_shape[0]), int(frame_shape[1])
+        self._ref = None
         check_fft_shape(self.ny, self.nx, generic_ok=True)     # sides that are not powers of two: map-based chirp-z path
         tpl = _lib.as_device_f32(template, self.dev)
         if tpl.ndim != 2:
@@ -306,21 +308,64 @@ class PhaseTracker:
             raise ValueError("ROI exceeds image bounds.")
         self.eps = float(eps)
         ctx = get_context(self.dev)
-        ctx.check(ctx.lib.b4d_phase_set_reference(ctx.handle, ptr(tpl), h, w, self.ny, self.nx, int(y0), int(x0),
-                                                  self.eps), "b4d_phase_set_reference")
+        ref = C.c_void_p()
+        ctx.check(ctx.lib.b4d_phase_reference_create(ctx.handle, ptr(tpl), h, w, self.ny, self.nx, int(y0), int(x0),
+                                                     self.eps, C.byref(ref)), "b4d_phase_reference_create")
+        self._ref = ref
+        _last_tracker[self.dev] = self
+
+    @property
+    def handle(self):
+        if self._ref is None or not self._ref.value:
+            raise _lib.B4DError("this PhaseTracker has been closed")
+        return self._ref
+
+    def close(self):
+        """Frees the device buffers (waits for the work that reads them)."""
+        ref, self._ref = self._ref, None
+        if ref is not None and ref.value:
+            try:
+                ctx = get_context(self.dev)
+                ctx.lib.b4d_phase_reference_destroy(ctx.handle, ref)
+            except Exception:
+                pass
+        if _last_tracker.get(self.dev) is self:
+            _last_tracker.pop(self.dev, None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def track(self, stack, *, subpixel: bool = True, return_device: bool = False):
         """(T, ny, nx) stack -> float64 table (T, 4) = dy, dx, peak, snr."""
         torch = require_cuda()
+        check_stack(stack)
         T, ny, nx = stack.shape
         if (ny, nx) != (self.ny, self.nx):
             raise ValueError("frame shape differs from the tracker's reference frame shape")
         ctx = get_context(self.dev)
         out = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
-        ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(stack), T, ny, nx, int(bool(subpixel)), self.eps,
-                                          ptr(out)), "b4d_phase_track")
-        resolve_tracking(stack, out, subpixel=subpixel, eps=self.eps)
+        ctx.check(ctx.lib.b4d_phase_track_ref(ctx.handle, self.handle, ptr(stack), T, ny, nx, int(bool(subpixel)), self.eps, 0,
+                                              ptr(out)), "b4d_phase_track_ref")
+        resolve_tracking(stack, out, self, subpixel=subpixel)
         return out if return_device else out.cpu().numpy()
+
+
+# the tracker most recently created on each device: what stack_pipeline(want_tracking=True) uses when no tracker is passed
+_last_tracker: dict[int, "PhaseTracker"] = {}
+
+
+def check_stack(stack):
+    """Device stacks are handed to the library as raw pointers: they must be float32, C-contiguous CUDA tensors."""
+    torch = require_cuda()
+    if not isinstance(stack, torch.Tensor) or stack.device.type != "cuda":
+        raise TypeError("expected a CUDA tensor (use engine.as_stack for host data)")
+    if stack.dtype != torch.float32:
+        raise TypeError(f"device stacks must be float32, got {stack.dtype} (use engine.as_stack / cast_to_f32)")
+    if not stack.is_contiguous():
+        raise ValueError("device stacks must be C-contiguous (call .contiguous())")
 
 
 def template_match(template, stack, *, ref_center_yx, subpixel: bool = True, eps: float = 1e-9, return_device: bool = False):
@@ -344,26 +389,26 @@ def template_match(template, stack, *, ref_center_yx, subpixel: bool = True, eps
     return out if return_device else out.cpu().numpy()
 
 
-def resolve_tracking(stack, track, *, subpixel: bool = True, eps: float = 1e-9, gain=None, dark=None, flat_field_fn=None):
+def resolve_tracking(stack, track, tracker: "PhaseTracker | None" = None, *, subpixel: bool = True, flat_field_fn=None):
     """Frames whose fused median bracket missed carry snr = NaN (include/b4d.h, b4d_set_fused_median): redo them through the
-    map-based exact path. `stack` holds the frames as the tracker saw them (raw when gain/dark were fused into the
-    loaders: then `flat_field_fn` materialises the corrected frames). In place; returns the number of frames redone."""
+    map-based exact path of the same tracker. `stack` holds the frames as the tracker saw them (raw when gain/dark were
+    fused into the loaders: then `flat_field_fn` materialises the corrected frames). In place; returns the number of
+    frames redone."""
     torch = require_cuda()
     bad = torch.nonzero(torch.isnan(track[:, 3])).flatten()
     if not bad.numel():
         return 0
+    tracker = tracker if tracker is not None else _last_tracker.get(_dev(stack))
+    if tracker is None:
+        raise ValueError("resolve_tracking: no tracker")
     frames = stack[bad].contiguous()
     if flat_field_fn is not None:
         frames = flat_field_fn(frames)
     ctx = get_context(_dev(stack))
     T, ny, nx = frames.shape
     redo = torch.empty((T, 4), dtype=torch.float64, device=stack.device)
-    ctx.set_fused_median(False)
-    try:
-        ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(frames), T, ny, nx, int(bool(subpixel)), float(eps), ptr(redo)),
-                  "b4d_phase_track")
-    finally:
-        ctx.set_fused_median(True)
+    ctx.check(ctx.lib.b4d_phase_track_ref(ctx.handle, tracker.handle, ptr(frames), T, ny, nx, int(bool(subpixel)),
+                                          float(tracker.eps), 1, ptr(redo)), "b4d_phase_track_ref")
     track[bad] = redo
     return int(bad.numel())
 
@@ -372,20 +417,28 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
                    psd_scale: float | None = None, subpixel: bool = True, track_eps: float = 1e-9,
                    want_reductions: bool = True, want_psd: bool = True, want_autocorr: bool = True,
                    want_grain: bool = True, want_tracking: bool = True, psd_out=None, ac_out=None,
-                   tail_quantiles=None):
-    """The fused north-star pass over an HBM-resident stack (see b4d_stack_pipeline in include/b4d.h).
+                   tail_quantiles=None, tracker: "PhaseTracker | None" = None):
+    """The fused north-star pass over an HBM-resident stack (see b4d_stack_pipeline_ref in include/b4d.h).
 
-    Tracking uses the reference most recently installed by a PhaseTracker on the same device.
+    Tracking runs against `tracker` (its own reference spectrum); without one, against the PhaseTracker most recently
+    created on the stack's device.
     tail_quantiles=(q_lo, q_hi) (fractions) adds the order statistics bracketing the two percentiles, collected in
     the reduction pass: "quantiles" (T, 4) float32 and "n_valid" (T,) int64 (-1 = unresolved frame, see
     resolve_tail_quantiles).
     Returns a dict with device tensors: reductions (T, FR_NCOLS), psd, autocorr, grain (T,4), tracking (T,4).
     """
     torch = require_cuda()
+    check_stack(stack)
     T, ny, nx = stack.shape
     check_fft_shape(ny, nx, generic_ok=True)
     ctx = get_context(_dev(stack))
     dev = stack.device
+    if want_tracking:
+        tracker = tracker if tracker is not None else _last_tracker.get(_dev(stack))
+        if tracker is None:
+            raise ValueError("stack_pipeline: tracking needs a PhaseTracker")
+        if (tracker.ny, tracker.nx) != (ny, nx):
+            raise ValueError("frame shape differs from the tracker's reference frame shape")
     fr = torch.empty((T, FR_NCOLS), dtype=torch.float64, device=dev) if want_reductions else None
     if want_psd and psd_out is None:
         psd_out = torch.empty((T, ny, nx), dtype=torch.float32, device=dev)
@@ -401,11 +454,12 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
         q_lo, q_hi = float(tail_quantiles[0]), float(tail_quantiles[1])
         quant = torch.empty((T, 4), dtype=torch.float32, device=dev)
         nvalid = torch.empty((T,), dtype=torch.int64, device=dev)
-    ctx.check(ctx.lib.b4d_stack_pipeline(ctx.handle, ptr(stack), T, ny, nx, ptr(gain), ptr(dark), sat, float(eps),
-                                         scale, int(bool(subpixel)), float(track_eps), q_lo, q_hi, ptr(fr), ptr(quant),
-                                         ptr(nvalid), ptr(psd_out if want_psd else None),
-                                         ptr(ac_out if want_autocorr else None), ptr(grain), ptr(track)),
-              "b4d_stack_pipeline")
+    ctx.check(ctx.lib.b4d_stack_pipeline_ref(ctx.handle, tracker.handle if want_tracking else None, ptr(stack), T, ny, nx,
+                                             ptr(gain), ptr(dark), sat, float(eps), scale, int(bool(subpixel)),
+                                             float(tracker.eps if want_tracking else track_eps), q_lo, q_hi, ptr(fr),
+                                             ptr(quant), ptr(nvalid), ptr(psd_out if want_psd else None),
+                                             ptr(ac_out if want_autocorr else None), ptr(grain), ptr(track)),
+              "b4d_stack_pipeline_ref")
     return {"reductions": fr, "psd": psd_out if want_psd else None, "autocorr": ac_out if want_autocorr else None,
             "grain": grain, "tracking": track, "quantiles": quant, "n_valid": nvalid}
 

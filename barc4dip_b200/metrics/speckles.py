@@ -199,7 +199,10 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     if method == "template" and tracking_backend not in ("opencv", "skimage"):
         raise ValueError("backend must be 'opencv' or 'skimage'.")
     dev = engine.as_stack(stack)
-    full = _full_blocks(dev, groups, saturation_value, eps, keep_maps=keep_autocorr)
+    # the reference runs speckle_stats(frame, display_origin=...) per frame, i.e. on the row-flipped frame for "lower":
+    # scalars do not see the flip, the returned autocorrelation maps do
+    flip_maps = keep_autocorr and normalize_display_origin(display_origin) == "lower"
+    full = _full_blocks(dev.flip(1).contiguous() if flip_maps else dev, groups, saturation_value, eps, keep_maps=keep_autocorr)
     if "grain" in full and keep_autocorr:
         full["grain"]["autocorr"] = full["grain"]["autocorr"].cpu().numpy().astype(np.float64)
         n = full["grain"]["autocorr"].shape[-1]

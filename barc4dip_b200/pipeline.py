@@ -85,15 +85,22 @@ class StackAnalyzer:
     def run_device(self, dev_stack, *, psd_out=None, ac_out=None, resolve_tails: bool = True) -> dict:
         """Analyse an HBM-resident (T, ny, nx) float32 stack; everything stays on the device."""
         q_lo, q_hi = 0.05 / 100.0, 99.95 / 100.0      # amplitude(): percentile_minmax_range defaults
+        # grain widths need square frames (the reference pads to square, metrics/speckles.py:530): the fused pass reports
+        # them for square frames only, others get NaN here (stack.grain_block pads and serves them on request)
+        square = self.ny == self.nx
         res = engine.stack_pipeline(dev_stack, gain=self.gain, dark=self.dark, saturation_value=self.sat, eps=self.eps,
                                     subpixel=self.subpixel, want_psd=self.want_maps or psd_out is not None,
-                                    want_autocorr=True, want_grain=True, want_tracking=self.tracker is not None,
+                                    want_autocorr=square or self.want_maps or ac_out is not None, want_grain=square,
+                                    want_tracking=self.tracker is not None, tracker=self.tracker,
                                     psd_out=psd_out, ac_out=ac_out,
                                     tail_quantiles=(q_lo, q_hi) if self.want_contrast else None)
+        if res["grain"] is None:
+            torch = require_cuda()
+            res["grain"] = torch.full((dev_stack.shape[0], 4), float("nan"), dtype=torch.float64, device=dev_stack.device)
         if resolve_tails and res["tracking"] is not None:
             # same contract for the tracker: snr = NaN marks a frame whose fused median bracket missed
             ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None
-            engine.resolve_tracking(dev_stack, res["tracking"], subpixel=self.subpixel, flat_field_fn=ff)
+            engine.resolve_tracking(dev_stack, res["tracking"], self.tracker, subpixel=self.subpixel, flat_field_fn=ff)
         if self.want_contrast and resolve_tails:
             # the tails are collected inside the reduction pass; a frame the sample bracket missed (n_valid == -1) is
             # redone by the stand-alone exact select (host sync: one tiny D2H per chunk)
@@ -107,15 +114,30 @@ class StackAnalyzer:
                 engine.resolve_tail_quantiles(src, res["quantiles"], nv, q_lo, q_hi)
         return res
 
-    def run(self, stack, *, keep_maps_on_device: bool = False) -> dict:
-        """(T, ny, nx) numpy (or CUDA tensor) -> dict of numpy results (maps as float32 arrays, or device tensors)."""
+    def run(self, stack, *, keep_maps_on_device: bool = False, reuse_host_buffers: bool = False) -> dict:
+        """(T, ny, nx) numpy (or CUDA tensor) -> dict of numpy results (maps as float32 arrays, or device tensors).
+
+        reuse_host_buffers=True returns the PSD / autocorrelation maps as views of pinned buffers the analyzer keeps and
+        overwrites on its next run() of the same stack length (no 34 MB-per-frame allocation per call); by default every
+        call returns maps of its own."""
         torch = require_cuda()
         is_host = not (isinstance(stack, torch.Tensor) and stack.device.type == "cuda")
         T = int(stack.shape[0])
         if tuple(stack.shape[1:]) != (self.ny, self.nx):
             raise ValueError("frame shape differs from the analyzer's")
+        if not is_host:
+            # a device stack is handed over as a raw pointer: float32, contiguous, on this analyzer's device
+            if stack.device != self.device:
+                raise ValueError(f"the stack lives on {stack.device}, the analyzer on {self.device}")
+            if stack.dtype != torch.float32 or not stack.is_contiguous():
+                stack = stack.to(torch.float32).contiguous()
         ny, nx, c = self.ny, self.nx, self.chunk
         h2d, comp, d2h = self._streams
+        # everything the caller (and this object's constructor / set_reference) queued on the current stream -- the
+        # stack itself when it is a device tensor, the gain map, the reference spectrum -- precedes the private streams
+        cur = torch.cuda.current_stream(self.device)
+        for s_ in self._streams:
+            s_.wait_stream(cur)
         st = self._buffers(True)
         code = None
         if is_host:
@@ -140,11 +162,13 @@ class StackAnalyzer:
         nv_all = torch.empty((T,), dtype=torch.int64, device=self.device) if self.want_contrast else None
         maps_host = None
         if self.want_maps and not keep_maps_on_device:
-            # pinned result buffers are cached per stack length: pinning 34 MB per frame is not free
-            cache = getattr(self, "_host_maps", None)
+            # pinning 34 MB per frame is not free: with reuse_host_buffers the pinned result buffers are cached per stack
+            # length (and the returned maps alias them until the next run)
+            cache = getattr(self, "_host_maps", None) if reuse_host_buffers else None
             if cache is None or cache["psd"].shape[0] != T:
                 cache = {k: torch.empty((T, ny, nx), dtype=torch.float32, pin_memory=True) for k in ("psd", "ac")}
-                self._host_maps = cache
+                if reuse_host_buffers:
+                    self._host_maps = cache
             maps_host = cache
         maps_dev = {k: torch.empty((T, ny, nx), dtype=torch.float32, device=self.device) for k in ("psd", "ac")} \
             if (self.want_maps and keep_maps_on_device) else None
@@ -172,7 +196,6 @@ class StackAnalyzer:
                     comp.wait_event(ev_in[s])
                 if self.want_maps and not keep_maps_on_device and i >= 2:
                     comp.wait_event(ev_out[s])              # the D2H that drained this map buffer has finished
-                ctx.use_current_stream()
                 if code is not None:
                     cast_to_f32(st["raw"][s][:n], code, frames)
                 if self.want_maps:
@@ -197,14 +220,13 @@ class StackAnalyzer:
                     ev_out[s].record(d2h)
         for s_ in self._streams:
             s_.synchronize()
-        ctx.use_current_stream()
         if track_all is not None and bool(torch.isnan(track_all[:, 3]).any()):
             # frames whose fused median bracket missed: redo them through the map-based tracker
             bad = torch.isnan(track_all[:, 3]).nonzero().flatten()
             frames = self._frames_of(stack, bad)
             sub = track_all[bad].clone()
             ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None
-            engine.resolve_tracking(frames, sub, subpixel=self.subpixel, flat_field_fn=ff)
+            engine.resolve_tracking(frames, sub, self.tracker, subpixel=self.subpixel, flat_field_fn=ff)
             track_all[bad] = sub
         if nv_all is not None and bool((nv_all < 0).any()):
             # frames whose tails the fused collection did not resolve: exact stand-alone select on those frames only

@@ -3,7 +3,8 @@ flat_field_correction on the B200 path -- drop-in for barc4dip.preprocessing.nor
 
 (I - D) / (F - D) * scale with the reference's float32 operation order (bit-identical output), bad-pixel
 mask den <= eps -> 0.  The two medians (default eps and the "flat_median" scale) are exact radix selects on
-the device.  `bad_pixel_removal=True` (3x3 median repair, :134-140) is a SURVEY.md 8(f) "next" row and raises.
+the device.  `bad_pixel_removal=True` repairs the bad pixels with the reference's 3x3 median (:134-140), in place on the
+device, bit-exact (b4d_bad_pixel_repair).
 """
 
 from __future__ import annotations

@@ -311,7 +311,7 @@ def run_b200(args):
         def time_e2e(keep: bool):
             def e2e_step():
                 an2.set_reference(ref_host)
-                return an2.run(host, keep_maps_on_device=keep)
+                return an2.run(host, keep_maps_on_device=keep, reuse_host_buffers=True)
             # two untimed calls: staging buffers, scratch arenas and the caching allocator's blocks for the result maps
             # are created on the first, reused from the second on (a result is released before the next call, as a
             # caller looping over stacks would)

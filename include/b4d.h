@@ -278,6 +278,19 @@ int b4d_phase_set_reference(b4d_ctx* ctx, const float* tpl, int h, int w, int ny
                             int y0, int x0, double eps);
 int b4d_phase_track(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx,
                     int subpixel, double eps, double* out);
+/*
+ * The same tracker with a reference its creator OWNS (signal/tracking.py:192-297 takes the template as an argument of
+ * every call; the reference's callers drive it from joblib threads, metrics/speckles.py:323): any number of
+ * references may be alive per context and frame shape, none is re-targeted by another b4d_phase_set_reference /
+ * b4d_phase_reference_create.  b4d_phase_track_ref: map_median != 0 selects the map-based median for this call only
+ * (the redo path of frames whose fused bracket missed).  Destroy a reference only after the work that reads it.
+ */
+typedef struct b4d_ref b4d_ref;
+int b4d_phase_reference_create(b4d_ctx* ctx, const float* tpl, int h, int w, int ny, int nx,
+                               int y0, int x0, double eps, b4d_ref** out);
+int b4d_phase_reference_destroy(b4d_ctx* ctx, b4d_ref* ref);
+int b4d_phase_track_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
+                        int subpixel, double eps, int map_median, double* out);
 
 /*
  * The fused stack pass of the north-star pipeline: one call per chunk of frames produces
@@ -297,6 +310,13 @@ int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int n
                        float psd_scale, int subpixel, double eps, double q_lo, double q_hi,
                        double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out,
                        double* grain_out, double* track_out);
+
+/* b4d_stack_pipeline against an owned reference (nullable when track_out is null). */
+int b4d_stack_pipeline_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
+                           const float* gain, const float* dark, double sat_value, double zero_eps,
+                           float psd_scale, int subpixel, double eps, double q_lo, double q_hi,
+                           double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out,
+                           double* grain_out, double* track_out);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ def main():
     p.add_argument("--configs", default="0:1:1:0:0,1:2:1:1:1,2:2:1:1:1,1:3:1:1:1,2:3:1:1:1")
     p.add_argument("--out", default="")
     p.add_argument("--no-track", action="store_true", help="PSD + autocorrelation + reductions only (no tracker chain)")
+    p.add_argument("--no-psd", action="store_true", help="no PSD map (autocorrelation map + tracker + reductions)")
     p.add_argument("--no-prof", action="store_true", help="no per-kernel event spans (fewer driver calls per launch)")
     a = p.parse_args()
     import torch
@@ -49,14 +50,14 @@ def main():
     for t in range(F):
         stack[t] = torch.roll(base_d, (int(shifts[t, 0]), int(shifts[t, 1])), dims=(0, 1)) + \
             sigma * torch.randn((n, n), generator=g, device=dev)
-    analyzer = StackAnalyzer((n, n), device=0, chunk_frames=F, want_maps=True, want_contrast=True)
+    analyzer = StackAnalyzer((n, n), device=0, chunk_frames=F, want_maps=not a.no_psd, want_contrast=True)
     if not a.no_track:
         analyzer.set_reference(stack[0].clone())
     psd = torch.empty((F, n, n), dtype=torch.float32, device=dev)
     ac = torch.empty((F, n, n), dtype=torch.float32, device=dev)
 
     def step():
-        return analyzer.run_device(stack, psd_out=psd, ac_out=ac, resolve_tails=False)
+        return analyzer.run_device(stack, psd_out=None if a.no_psd else psd, ac_out=ac, resolve_tails=False)
 
     def snapshot(res):
         out = {k: v.clone() for k, v in res.items() if isinstance(v, torch.Tensor) and v.numel() < 10_000_000}

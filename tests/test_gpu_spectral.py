@@ -207,7 +207,7 @@ def test_fused_median_flags_degenerate_frames_and_falls_back():
     tr = engine.PhaseTracker(stack[0], (n, n), y0=0, x0=0)
     ctx = get_context()
     raw = torch.empty((3, 4), dtype=torch.float64, device=d.device)
-    ctx.check(ctx.lib.b4d_phase_track(ctx.handle, ptr(d), 3, n, n, 1, 1e-9, ptr(raw)), "b4d_phase_track")
+    ctx.check(ctx.lib.b4d_phase_track_ref(ctx.handle, tr.handle, ptr(d), 3, n, n, 1, 1e-9, 0, ptr(raw)), "b4d_phase_track_ref")
     assert bool(torch.isnan(raw[1, 3])) and not bool(torch.isnan(raw[2, 3]))
     tab = tr.track(d)                       # wrapper resolves the flagged frame
     ctx.set_fused_median(False)
