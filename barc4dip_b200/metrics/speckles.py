@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from .. import engine, stack as blocks
+from .. import engine, parallel as _par, stack as blocks
 from .._lib import B4DUnsupported
 from ..signal.common import lag_axis
 from .common import (apply_display_origin, choose_tiling_mode, normalize_display_origin, normalize_groups, tiled_blocks,
@@ -148,6 +148,13 @@ def _tiles(dev_oriented, mode, groups, saturation_value, eps) -> dict:
     return {g: res[g] for g in ("amplitude", "grain", "stats", "bandwidth") if g in res}
 
 
+def _empty_like_block(block):
+    """The same nested block with zero frames (a rank that owns no frame still takes part in the gathers)."""
+    if isinstance(block, dict):
+        return {k: _empty_like_block(v) for k, v in block.items()}
+    return block[:0]
+
+
 def _odd_size(n: float, min_size: int = 3) -> int:
     size = max(int(math.ceil(n)), min_size)
     return size + 1 if size % 2 == 0 else size
@@ -174,8 +181,14 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
                         roi_grain_factor: float = 3.0, roi_step_factor: float = 0.5, tracking_method: str = "template",
                         tracking_backend: str = "skimage", subpixel: bool = True,
                         saturation_value: float | None = 65535.0, eps: float = 1e-6, verbose: bool = True,
-                        parallel: bool = True, n_jobs: int | None = None, keep_autocorr: bool = False) -> dict:
+                        parallel: bool = True, n_jobs: int | None = None, keep_autocorr: bool = False,
+                        sharded: bool | None = None) -> dict:
     """Per-frame speckle metrics of a (T, H, W) stack plus 3x3-ROI translation tracking (abs / inc).
+
+    Under torch.distributed (one process per GPU, torchrun; sharded=None picks it up, False ignores it) every rank
+    passes the same host stack and works on its contiguous frame range only -- widened by the one-frame halo the
+    incremental tracker needs (frame t against frame t-1, metrics/speckles.py:349,373) -- and every per-frame leaf is
+    all-gathered: all ranks return the full result, identical to the single-GPU one.
 
     Trackers: "template" (the reference's default; both of its backend names are served by the same normalised
     cross-correlation kernels, pinned against opencv) and "phase" / "internal". Difference from the reference, explicit:
@@ -198,18 +211,27 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
         raise B4DUnsupported("phase tracking on the B200 path implements tracking_backend='internal' only")
     if method == "template" and tracking_backend not in ("opencv", "skimage"):
         raise ValueError("backend must be 'opencv' or 'skimage'.")
-    dev = engine.as_stack(stack)
+    rank, world = _par.dist_info() if sharded is not False else (0, 1)
+    lo, hi = _par.frame_range(T, rank, world)
+    hlo, _ = _par.inc_halo_range(T, rank, world)
+    Tl = hi - lo
+    dev_h = engine.as_stack(stack[hlo:max(hi, hlo + 1)])          # this rank's frames + the halo frame lo - 1
+    dev = dev_h[lo - hlo:lo - hlo + Tl]
+    dev0 = dev_h[:1] if hlo == 0 else engine.as_stack(stack[:1])  # frame 0: ROI size, absolute template (every rank)
     # the reference runs speckle_stats(frame, display_origin=...) per frame, i.e. on the row-flipped frame for "lower":
     # scalars do not see the flip, the returned autocorrelation maps do
     flip_maps = keep_autocorr and normalize_display_origin(display_origin) == "lower"
-    full = _full_blocks(dev.flip(1).contiguous() if flip_maps else dev, groups, saturation_value, eps, keep_maps=keep_autocorr)
+    if Tl > 0:
+        full = _full_blocks(dev.flip(1).contiguous() if flip_maps else dev, groups, saturation_value, eps, keep_maps=keep_autocorr)
+    else:
+        full = {k: _empty_like_block(v) for k, v in _full_blocks(dev0, groups, saturation_value, eps, keep_maps=keep_autocorr).items()}
     if "grain" in full and keep_autocorr:
         full["grain"]["autocorr"] = full["grain"]["autocorr"].cpu().numpy().astype(np.float64)
         n = full["grain"]["autocorr"].shape[-1]
-        full["grain"]["xlag"] = np.tile(full["grain"]["xlag"], (T, 1))
-        full["grain"]["ylag"] = np.tile(full["grain"]["ylag"], (T, 1))
+        full["grain"]["xlag"] = np.tile(full["grain"]["xlag"], (Tl, 1))
+        full["grain"]["ylag"] = np.tile(full["grain"]["ylag"], (Tl, 1))
 
-    g0 = blocks.grain_block(dev[:1])
+    g0 = blocks.grain_block(dev0)
     l = float(np.nanmax([g0["lx"][0], g0["ly"][0], g0["leq"][0]]))
     if not np.isfinite(l) or l <= 0:
         raise ValueError("Could not infer a valid grain size from frame 0 (lx/ly/leq).")
@@ -217,32 +239,35 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     step = int(max(1, round(roi_step_factor * roi)))
     grid = _roi_grid_3x3((H, W), roi, step)
 
-    dx_abs = np.empty((T, 3, 3), np.float32)
-    dy_abs = np.empty((T, 3, 3), np.float32)
-    dx_inc = np.empty((T, 3, 3), np.float32)
-    dy_inc = np.empty((T, 3, 3), np.float32)
-    prev = np.maximum(np.arange(T) - 1, 0)
+    dx_abs = np.empty((Tl, 3, 3), np.float32)
+    dy_abs = np.empty((Tl, 3, 3), np.float32)
+    dx_inc = np.empty((Tl, 3, 3), np.float32)
+    dy_inc = np.empty((Tl, 3, 3), np.float32)
+    prev = np.maximum(np.arange(lo, hi) - 1, 0) - hlo              # index of frame t-1 (frame 0 for t = 0) inside dev_h
     for iy in range(3):
         for ix in range(3):
+            if Tl == 0:
+                break
             sy, sx = grid[iy][ix]
             if method == "template":
                 # the reference's default tracker: normalised cross-correlation of the ROI against the full frame; absolute
                 # = ROI of frame 0 against every frame, incremental = ROI of frame t-1 against frame t, both batched
                 centre = ((sy.start + sy.stop - 1) / 2.0, (sx.start + sx.stop - 1) / 2.0)
-                tab = engine.template_match(dev[0, sy, sx], dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
+                tab = engine.template_match(dev0[0, sy, sx], dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
                 dy_abs[:, iy, ix], dx_abs[:, iy, ix] = tab[:, 0], tab[:, 1]
-                tab = engine.template_match(dev[prev][:, sy, sx].contiguous(), dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
+                tab = engine.template_match(dev_h[prev][:, sy, sx].contiguous(), dev, ref_center_yx=centre, subpixel=subpixel, eps=1e-9)
                 dy_inc[:, iy, ix], dx_inc[:, iy, ix] = tab[:, 0], tab[:, 1]
                 continue
             # absolute: one reference (ROI of frame 0) against the whole stack
-            tr = engine.PhaseTracker(dev[0, sy, sx].contiguous(), (H, W), y0=sy.start, x0=sx.start, eps=1e-9)
+            tr = engine.PhaseTracker(dev0[0, sy, sx].contiguous(), (H, W), y0=sy.start, x0=sx.start, eps=1e-9)
             tab = tr.track(dev, subpixel=subpixel)
+            tr.close()
             dy_abs[:, iy, ix], dx_abs[:, iy, ix] = tab[:, 0], tab[:, 1]
             # incremental: the ROI of frame t-1 (frame 0 for t = 0) against frame t
-            for t in range(T):
-                prev = dev[t - 1 if t > 0 else 0, sy, sx].contiguous()
-                tri = engine.PhaseTracker(prev, (H, W), y0=sy.start, x0=sx.start, eps=1e-9)
+            for t in range(Tl):
+                tri = engine.PhaseTracker(dev_h[int(prev[t]), sy, sx].contiguous(), (H, W), y0=sy.start, x0=sx.start, eps=1e-9)
                 r = tri.track(dev[t:t + 1], subpixel=subpixel)[0]
+                tri.close()
                 dy_inc[t, iy, ix], dx_inc[t, iy, ix] = r[0], r[1]
 
     def summarise(dx, dy):
@@ -271,10 +296,21 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     # tiles: the reference evaluates speckle_stats(frame, tiles=...) per frame, i.e. on the display-oriented frame
     mode, _ = choose_tiling_mode(H, W, tiles=tiles)
     if mode != "off":
-        oriented = dev.flip(1) if normalize_display_origin(display_origin) == "lower" else dev
+        src = dev if Tl > 0 else dev0
+        oriented = src.flip(1) if normalize_display_origin(display_origin) == "lower" else src
         tl = _tiles(oriented, mode, groups, saturation_value, eps)
+        if Tl == 0:
+            tl = {g: _empty_like_block(f) for g, f in tl.items()}
         if tl:
             out["tiles"] = tl
+    if world > 1:
+        # every per-frame leaf back to the full stack length, in rank order; meta is identical on every rank already
+        qc = out["temporal"].pop("qc")
+        for part in ("full", "temporal", "tiles"):
+            if part in out:
+                out[part] = _par.gather_tree(out[part], T)
+        out["temporal"]["qc"] = qc
+        meta["sharding"] = {"world_size": world, "frame_range_of_rank": [list(_par.frame_range(T, r, world)) for r in range(world)]}
     if verbose:
         logger.info("> speckle_stack_stats | frames=%d | roi=%dx%d | step=%d | device=cuda", T, roi, roi, step)
     return out

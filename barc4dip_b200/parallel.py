@@ -103,6 +103,87 @@ def gather_rows(local, n_frames: int):
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
 
 
+def _comm_device():
+    """Device the collectives of the current process group run on: the current CUDA device for NCCL, the host for gloo."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_tree(tree, n_frames: int):
+    """All-gather every per-frame leaf of a nested result dict along axis 0 in rank order.
+
+    Leaves are numpy arrays or tensors whose leading axis is this rank's frame range (frame_range(n_frames, rank,
+    world)); anything else (scalars, strings, meta dicts, arrays with another leading length) is left as it is -- such
+    leaves must already be identical on every rank. Returns the same structure with (n_frames, ...) leaves, numpy
+    leaves staying numpy. No-op on one rank."""
+    rank, world = dist_info()
+    if world == 1:
+        return tree
+    import torch
+    lo, hi = frame_range(n_frames, rank, world)
+    dev = _comm_device()
+
+    def walk(node):
+        if isinstance(node, dict):
+            return {k: walk(node[k]) for k in node}                     # (insertion order is the same on every rank)
+        if isinstance(node, np.ndarray) and node.ndim >= 1 and node.shape[0] == hi - lo and node.dtype != object:
+            t = torch.from_numpy(np.ascontiguousarray(node)).to(dev)
+            return gather_rows(t, n_frames).cpu().numpy()
+        if isinstance(node, torch.Tensor) and node.ndim >= 1 and node.shape[0] == hi - lo:
+            return gather_rows(node.contiguous().to(dev), n_frames)
+        return node
+
+    return walk(tree)
+
+
+def analyze_stack_sharded(stack, *, reference=None, slices_yx=None, **analyzer_kw) -> dict:
+    """StackAnalyzer over the ranks of the current process group (one process per GPU, torchrun).
+
+    Every rank passes the same (T, ny, nx) host stack (an array, a memmap, anything sliceable along axis 0 that
+    returns a numpy array): rank r uploads and analyses only its contiguous frame range, the tracker's reference
+    frame (default: frame 0) is broadcast from its owner so that every rank builds the identical spectrum, and the
+    per-frame tables are all-gathered, so every rank returns the full (T, ...) tables. The PSD / autocorrelation maps
+    stay on the device of the rank that computed them: out["psd"], out["autocorr"] hold this rank's frames
+    out["frame_range"] = (lo, hi). On one rank this is StackAnalyzer.run with maps kept on the device.
+    Replaces the per-frame loop of metrics/speckles.py:300-325,347-386 at stack scale."""
+    import torch
+    from . import engine
+    from .pipeline import StackAnalyzer
+    rank, world = dist_info()
+    T = int(stack.shape[0])
+    ny, nx = int(stack.shape[1]), int(stack.shape[2])
+    lo, hi = frame_range(T, rank, world)
+    dev = torch.cuda.current_device()
+    analyzer = StackAnalyzer((ny, nx), device=dev, **analyzer_kw)
+    if reference is None:
+        owner = owner_of(0, T, world)
+        ref = engine.as_stack(np.asarray(stack[0:1]), dev)[0] if rank == owner else \
+            torch.empty((ny, nx), dtype=torch.float32, device=f"cuda:{dev}")
+        broadcast_reference(ref, src=owner)
+    else:
+        ref = engine.as_stack(np.asarray(reference)[None], dev)[0]
+    analyzer.set_reference(ref, slices_yx=slices_yx)
+    if hi > lo:
+        res = analyzer.run(np.asarray(stack[lo:hi]), keep_maps_on_device=True)
+    else:
+        res = analyzer.run(np.asarray(stack[0:1]), keep_maps_on_device=True)     # a rank without frames still joins the gathers
+        res = {k: (_take0(v)) for k, v in res.items()}
+    maps = {k: res.pop(k) for k in ("psd", "autocorr") if k in res}
+    out = gather_tree(res, T)
+    out.update(maps)
+    out["frame_range"] = (lo, hi)
+    return out
+
+
+def _take0(v):
+    if isinstance(v, dict):
+        return {k: _take0(x) for k, x in v.items()}
+    return v[:0]
+
+
 def sharded_temporal_moments(local_stack, n_total: int, *, gain=None, dark=None, pilot_frames: int = 16):
     """Per-pixel temporal moments of a frame-sharded stack.
 

@@ -204,6 +204,19 @@ assert acc.count == T and float(acc.sums[0, 0, 0]) == 3.0
 local = torch.arange(lo, hi, dtype=torch.float64).view(-1, 1).repeat(1, 3)
 full = parallel.gather_rows(local, T)
 assert full.shape == (T, 3) and torch.equal(full[:, 0], torch.arange(T, dtype=torch.float64))
+# gather of a nested result dict: per-frame leaves (numpy or tensor) grow to T rows in frame order, the rest is untouched
+import numpy as np
+tree = {{"full": {{"stats": {{"mean": np.arange(lo, hi, dtype=np.float64)}}, "tab": torch.arange(lo, hi).view(-1, 1) * 2}},
+        "tiles": {{"g": {{"m": {{"mean": np.tile(np.arange(lo, hi, dtype=np.float32)[:, None, None], (1, 3, 3))}}}}}},
+        "meta": {{"kind": "x", "axis": np.arange(7.0)}}}}
+g = parallel.gather_tree(tree, T)
+assert np.array_equal(g["full"]["stats"]["mean"], np.arange(T, dtype=np.float64)) and g["full"]["stats"]["mean"].dtype == np.float64
+assert torch.equal(g["full"]["tab"][:, 0], torch.arange(T) * 2)
+assert g["tiles"]["g"]["m"]["mean"].shape == (T, 3, 3) and g["tiles"]["g"]["m"]["mean"][T - 1, 2, 2] == T - 1
+assert g["meta"]["kind"] == "x" and np.array_equal(g["meta"]["axis"], np.arange(7.0))
+# incremental tracking: every rank's range with its one-frame halo covers frame t-1 for each of its frames t
+hlo, hhi = parallel.inc_halo_range(T, rank, world)
+assert hhi == hi and hlo == max(lo - 1, 0) and all(max(t - 1, 0) >= hlo for t in range(lo, hi))
 dist.destroy_process_group()
 print("ok", rank)
 '''
