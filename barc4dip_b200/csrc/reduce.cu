@@ -297,6 +297,7 @@ struct Fr2Args {
     double* partials;         // (T, blocks_per_frame, FR_NACC)
     float* cand;              // (T, 2, gcap)
     unsigned* cand_cnt;       // (T, 2), zeroed by the caller
+    unsigned* eq_cnt;         // (T, 2) pixels equal to thr_lo / thr_hi (ties at a threshold are counted, not listed), zeroed
     int* flag;                // (T) set when a staging buffer or a candidate list overflowed
     unsigned gcap;
     int ny, nx;
@@ -341,7 +342,7 @@ __device__ __forceinline__ float4 fetch2(const Fr2Args& a, const float* frame, i
 
 template <bool TAILS>
 __device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, float K, bool edge_l, bool edge_r, bool count,
-                                        float thr_lo, float thr_hi, Acc2& acc, float4* s_queue, unsigned* s_qn) {
+                                        float thr_lo, float thr_hi, Acc2& acc, float4* s_queue, unsigned* s_qn, unsigned* s_eq) {
     Win2 w;
     w.q0 = __fadd2_rn(f2(raw.x, raw.y), f2(-K, -K));
     w.q1 = __fadd2_rn(f2(raw.z, raw.w), f2(-K, -K));
@@ -387,11 +388,19 @@ __device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, floa
             }
         }
         if (TAILS) {
-            // rare (~1.6 % of the lanes): park the quad, the per-pixel tests run densely after the main loop
+            // rare (~1.6 % of the lanes): park the quad, the per-pixel tests run densely after the main loop. Pixels EQUAL to
+            // a threshold are only counted: integer detector frames tie by the thousand at 0 (masked / dark regions) or
+            // at the saturation value, and the order statistics inside a run of ties is the tie itself.
             const float mn = fminf(fminf(raw.x, raw.y), fminf(raw.z, raw.w));
             if (mn <= thr_lo || mx >= thr_hi) {
-                const unsigned p = atomicAdd(s_qn, 1u);
-                if (p < F2_QCAP) s_queue[p] = raw;
+                const unsigned el = (raw.x == thr_lo) + (raw.y == thr_lo) + (raw.z == thr_lo) + (raw.w == thr_lo);
+                const unsigned eh = (raw.x == thr_hi) + (raw.y == thr_hi) + (raw.z == thr_hi) + (raw.w == thr_hi);
+                if (el) atomicAdd(s_eq, el);
+                if (eh) atomicAdd(s_eq + 1, eh);
+                if (mn < thr_lo || mx > thr_hi) {
+                    const unsigned p = atomicAdd(s_qn, 1u);
+                    if (p < F2_QCAP) s_queue[p] = raw;
+                }
             }
         }
     }
@@ -447,12 +456,13 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
     __shared__ float s_buf[TAILS ? 2 * F2_CAP : 2];
     __shared__ float4 s_queue[TAILS ? F2_QCAP : 1];
     __shared__ unsigned s_cnt[2];
+    __shared__ unsigned s_eq[2];
     __shared__ unsigned s_base[2];
     __shared__ unsigned s_qn;
     if (TAILS) {
         thr_lo = __ldg(a.thr + 2 * t);
         thr_hi = __ldg(a.thr + 2 * t + 1);
-        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+        if (threadIdx.x < 2) { s_cnt[threadIdx.x] = 0u; s_eq[threadIdx.x] = 0u; }
         if (threadIdx.x == 2) s_qn = 0u;
         __syncthreads();
     }
@@ -475,8 +485,8 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
         const float4 rawm = fetch2<HAS_GAIN>(a, frame, r0 - 1, j0, ld_ok), raw0 = fetch2<HAS_GAIN>(a, frame, r0, j0, ld_ok);
 #pragma unroll
         for (int q = 0; q < 4; ++q) raw[q] = fetch2<HAS_GAIN>(a, frame, r0 + 1 + q, j0, ld_ok);
-        Win2 up = finish2<TAILS>(a, rawm, K, edge_l, edge_r, false, thr_lo, thr_hi, acc, s_queue, &s_qn);
-        Win2 mid = finish2<TAILS>(a, raw0, K, edge_l, edge_r, own, thr_lo, thr_hi, acc, s_queue, &s_qn);
+        Win2 up = finish2<TAILS>(a, rawm, K, edge_l, edge_r, false, thr_lo, thr_hi, acc, s_queue, &s_qn, s_eq);
+        Win2 mid = finish2<TAILS>(a, raw0, K, edge_l, edge_r, own, thr_lo, thr_hi, acc, s_queue, &s_qn, s_eq);
         for (int rb = r0; rb < r1; rb += 4) {
             // the four rows fetched one iteration ago are consumed while the next four are already in flight
             float4 cur[4];
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const Win2 nxt = finish2<TAILS>(a, cur[q], K, edge_l, edge_r, own && (rb + 1 + q < r1), thr_lo, thr_hi, acc, s_queue, &s_qn);
+                const Win2 nxt = finish2<TAILS>(a, cur[q], K, edge_l, edge_r, own && (rb + 1 + q < r1), thr_lo, thr_hi, acc, s_queue, &s_qn, s_eq);
                 if (own && rb + q < r1) stencil2(up, mid, nxt, acc);
                 up = mid;
                 mid = nxt;
@@ -526,14 +536,15 @@ __global__ void __launch_bounds__(F2_WARPS * 32, 2) frame_reduce2_kernel(Fr2Args
             const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (xs[k] <= thr_lo) { const unsigned p = atomicAdd(s_cnt, 1u); if (p < F2_CAP) s_buf[p] = xs[k]; }
-                if (xs[k] >= thr_hi) { const unsigned p = atomicAdd(s_cnt + 1, 1u); if (p < F2_CAP) s_buf[F2_CAP + p] = xs[k]; }
+                if (xs[k] < thr_lo) { const unsigned p = atomicAdd(s_cnt, 1u); if (p < F2_CAP) s_buf[p] = xs[k]; }
+                if (xs[k] > thr_hi) { const unsigned p = atomicAdd(s_cnt + 1, 1u); if (p < F2_CAP) s_buf[F2_CAP + p] = xs[k]; }
             }
         }
         __syncthreads();
         // flush the staged candidates: one reservation per CTA and tail
         if (threadIdx.x < 2) {
             if (s_qn > F2_QCAP) a.flag[t] = 1;
+            if (s_eq[threadIdx.x]) atomicAdd(a.eq_cnt + 2 * t + threadIdx.x, s_eq[threadIdx.x]);
             const unsigned n = s_cnt[threadIdx.x];
             unsigned base = 0;
             if (n > F2_CAP) a.flag[t] = 1;
@@ -617,8 +628,8 @@ float float_at_least(double v) {
 unsigned b4d_tails_gcap();
 int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain, const float* dark,
                            double q_lo, double q_hi, float* thr);
-int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const int* flag, const double* fr, int64_t T,
-                           double q_lo, double q_hi, float* out, int64_t* nvalid_out);
+int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const unsigned* eq, const float* thr, const int* flag,
+                           const double* fr, int64_t T, double q_lo, double q_hi, float* out, int64_t* nvalid_out);
 
 int b4d_frame_pilot_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t npix, const float* gain,
                            const float* dark, float* pilot) {
@@ -689,13 +700,14 @@ int b4d_fr_begin(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int
     pl->thr = static_cast<float*>(p) + n_frames;
     pl->gcap = b4d_tails_gcap();
     const size_t part_bytes = (sizeof(double) * FR_NACC * (size_t)pl->nblocks * (size_t)n_frames + 255) & ~size_t(255);
-    const size_t cnt_bytes = pl->fuse_tails ? (((size_t)n_frames * 3 * sizeof(unsigned) + 255) & ~size_t(255)) : 0;
+    const size_t cnt_bytes = pl->fuse_tails ? (((size_t)n_frames * 5 * sizeof(unsigned) + 255) & ~size_t(255)) : 0;
     const size_t cand_bytes = pl->fuse_tails ? (size_t)n_frames * 2 * pl->gcap * sizeof(float) : 0;
     rc = b4d_scratch(ctx, SCR_REDUCE, part_bytes + cnt_bytes + cand_bytes, &p);
     if (rc) return rc;
     pl->partials = static_cast<double*>(p);
     pl->cnt = reinterpret_cast<unsigned*>(static_cast<char*>(p) + part_bytes);
     pl->flag = reinterpret_cast<int*>(pl->cnt + 2 * n_frames);
+    pl->eq = pl->cnt + 3 * n_frames;
     pl->cand = reinterpret_cast<float*>(static_cast<char*>(p) + part_bytes + cnt_bytes);
     if (pl->fuse_tails) B4D_CUDA(ctx, cudaMemsetAsync(pl->cnt, 0, cnt_bytes, ctx->stream));
     rc = b4d_frame_pilot_launch(ctx, stack, n_frames, npix, gain, dark, pl->pilot);
@@ -714,7 +726,7 @@ int b4d_fr_range(b4d_ctx* ctx, const FrPlan& pl, int64_t t0, int64_t tc) {
     if (pl.vec) {
         Fr2Args b;
         b.stack = s0; b.gain = pl.gain; b.dark = pl.dark; b.pilot = pl.pilot + t0; b.thr = pl.fuse_tails ? pl.thr + 2 * t0 : nullptr;
-        b.partials = part0; b.cand = pl.cand + (size_t)t0 * 2 * pl.gcap; b.cand_cnt = pl.cnt + 2 * t0; b.flag = pl.flag + t0; b.gcap = pl.gcap;
+        b.partials = part0; b.cand = pl.cand + (size_t)t0 * 2 * pl.gcap; b.cand_cnt = pl.cnt + 2 * t0; b.eq_cnt = pl.eq + 2 * t0; b.flag = pl.flag + t0; b.gcap = pl.gcap;
         b.ny = ny; b.nx = nx; b.nstrips = pl.nstrips; b.nitems = pl.nitems; b.sat = pl.sat; b.zeps = pl.zeps; b.has_sat = pl.has_sat;
         ProfScope ps(ctx, KC_FRAME_REDUCE);
         if (pl.gain) {
@@ -744,8 +756,8 @@ int b4d_fr_range(b4d_ctx* ctx, const FrPlan& pl, int64_t t0, int64_t tc) {
 int b4d_fr_end(b4d_ctx* ctx, const FrPlan& pl) {
     const int64_t T = pl.n_frames;
     if (pl.fuse_tails)
-        return b4d_tails_final_launch(ctx, pl.cand, pl.cnt, pl.flag, pl.out, T, pl.tails.q_lo, pl.tails.q_hi, pl.tails.quant_out,
-                                      pl.tails.nvalid_out);
+        return b4d_tails_final_launch(ctx, pl.cand, pl.cnt, pl.eq, pl.thr, pl.flag, pl.out, T, pl.tails.q_lo, pl.tails.q_hi,
+                                      pl.tails.quant_out, pl.tails.nvalid_out);
     if (pl.has_tails) {
         B4D_CUDA(ctx, cudaMemsetAsync(pl.tails.nvalid_out, 0xff, sizeof(int64_t) * T, ctx->stream));   // -1: unresolved
         B4D_CUDA(ctx, cudaMemsetAsync(pl.tails.quant_out, 0xff, sizeof(float) * 4 * T, ctx->stream));   // NaN

@@ -16,7 +16,7 @@ struct FrPlan {
     double* out;
     FrTails tails; bool has_tails, fuse_tails, vec;
     float* pilot; float* thr;
-    double* partials; unsigned* cnt; int* flag; float* cand;
+    double* partials; unsigned* cnt; unsigned* eq; int* flag; float* cand;
     unsigned gcap; int nstrips, nitems, nblocks;
     float sat, zeps; int has_sat;
 };

@@ -579,7 +579,8 @@ __global__ void __launch_bounds__(1024) fused_median_final_kernel(const SelFast*
 // =================================================================================================
 // tails: thresholds for the fused tail collection of frame_reduce2_kernel, and the final order statistics
 // =================================================================================================
-// thr[t] = (thr_lo, thr_hi): every pixel <= thr_lo / >= thr_hi is a candidate. They are the sample order statistics
+// thr[t] = (thr_lo, thr_hi): every pixel < thr_lo / > thr_hi is a candidate, the pixels equal to a threshold are counted
+// (ties: masked, dark or saturated regions of integer detector frames). They are the sample order statistics
 // +-6 sigma (binomial) beyond the sample quantiles, so the wanted ranks fall inside the candidate lists unless the
 // sample was unlucky (then tails_final_kernel flags the frame).
 __global__ void __launch_bounds__(1024) tails_probe_kernel(const float* __restrict__ stack, const float* __restrict__ gain,
@@ -630,6 +631,7 @@ constexpr unsigned TAIL_GCAP = 16384;   // candidates per frame and tail (64 KB 
 // out[t] = (v[lo], v[hi]) of q_lo, (v[lo], v[hi]) of q_hi (numpy 'linear' neighbours); nvalid_out[t] = number of
 // non-NaN pixels, or -1 when the frame's candidate lists do not contain the wanted ranks.
 __global__ void __launch_bounds__(1024) tails_final_kernel(const float* __restrict__ cand, const unsigned* __restrict__ cnt,
+                                                           const unsigned* __restrict__ eq, const float* __restrict__ thr,
                                                            const int* __restrict__ flag, const double* __restrict__ fr,
                                                            double q_lo, double q_hi, float* __restrict__ out,
                                                            long long* __restrict__ nvalid_out) {
@@ -642,33 +644,49 @@ __global__ void __launch_bounds__(1024) tails_final_kernel(const float* __restri
     bool ok = nv > 0 && !flag[t];
     float res[4] = {0.f, 0.f, 0.f, 0.f};
     for (int tail = 0; tail < 2 && ok; ++tail) {
-        const unsigned c = cnt[2 * t + tail];
+        // ascending order of a tail: lower = [c candidates < thr][e ties == thr] ...; upper = ... [e ties == thr][c candidates > thr]
+        const unsigned c = cnt[2 * t + tail], e = eq[2 * t + tail];
+        const float tv = thr[2 * t + tail];
         long long lo, hi;
         target_ranks((unsigned long long)nv, tail ? q_hi : q_lo, lo, hi);
-        // ascending ranks inside the candidate list
+        // ascending ranks inside the candidate list; the run of ties sits right after it (lower) / right before it (upper)
         const long long off = tail ? nv - (long long)c : 0;
         lo -= off; hi -= off;
-        if (c == 0 || c > TAIL_GCAP || lo < 0 || hi >= (long long)c) { ok = false; break; }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_min = 0xffffffffu; s_max = 0u; }
-        __syncthreads();
-        unsigned kmin = 0xffffffffu, kmax = 0u;
-        const float* src = cand + ((size_t)t * 2 + tail) * TAIL_GCAP;
-        for (unsigned i = threadIdx.x; i < c; i += blockDim.x) {
-            const unsigned k = key_of(src[i], 0);
-            keys[i] = k;
-            kmin = min(kmin, k); kmax = max(kmax, k);
+        bool need_lo, need_hi, tie_lo, tie_hi;
+        if (!tail) {
+            need_lo = lo < (long long)c; need_hi = hi < (long long)c;
+            tie_lo = !need_lo && lo < (long long)c + (long long)e; tie_hi = !need_hi && hi < (long long)c + (long long)e;
+        } else {
+            need_lo = lo >= 0; need_hi = hi >= 0;
+            tie_lo = !need_lo && lo >= -(long long)e; tie_hi = !need_hi && hi >= -(long long)e;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        if (c > TAIL_GCAP || lo < -(long long)e || hi >= (long long)c + (tail ? 0 : (long long)e) || !(need_lo || tie_lo) || !(need_hi || tie_hi)) {
+            ok = false;
+            break;
         }
-        if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
-        __syncthreads();
-        const unsigned a = cta_bracket_select(keys, c, (unsigned)lo, s_min, s_max, hist, tmp);
-        const unsigned b = hi == lo ? a : cta_bracket_select(keys, c, (unsigned)hi, s_min, s_max, hist, tmp);
-        res[2 * tail] = value_of(a, 0);
-        res[2 * tail + 1] = value_of(b, 0);
+        unsigned ka = 0u, kb = 0u;
+        if (need_lo || need_hi) {
+            __syncthreads();
+            if (threadIdx.x == 0) { s_min = 0xffffffffu; s_max = 0u; }
+            __syncthreads();
+            unsigned kmin = 0xffffffffu, kmax = 0u;
+            const float* src = cand + ((size_t)t * 2 + tail) * TAIL_GCAP;
+            for (unsigned i = threadIdx.x; i < c; i += blockDim.x) {
+                const unsigned k = key_of(src[i], 0);
+                keys[i] = k;
+                kmin = min(kmin, k); kmax = max(kmax, k);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+            __syncthreads();
+            if (need_lo) ka = cta_bracket_select(keys, c, (unsigned)lo, s_min, s_max, hist, tmp);
+            if (need_hi) kb = (need_lo && hi == lo) ? ka : cta_bracket_select(keys, c, (unsigned)hi, s_min, s_max, hist, tmp);
+        }
+        res[2 * tail] = need_lo ? value_of(ka, 0) : tv;
+        res[2 * tail + 1] = need_hi ? value_of(kb, 0) : tv;
     }
     if (threadIdx.x == 0) {
         nvalid_out[t] = ok ? nv : -1;
@@ -843,8 +861,8 @@ int b4d_tails_probe_launch(b4d_ctx* ctx, const float* stack, int64_t T, int64_t 
     return B4D_OK;
 }
 
-int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const int* flag, const double* fr, int64_t T,
-                           double q_lo, double q_hi, float* out, int64_t* nvalid_out) {
+int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt, const unsigned* eq, const float* thr, const int* flag,
+                           const double* fr, int64_t T, double q_lo, double q_hi, float* out, int64_t* nvalid_out) {
     static bool attr[B4D_MAX_DEVICES] = {};
     if (!attr[ctx->device]) {
         B4D_CUDA(ctx, cudaFuncSetAttribute(tails_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -852,7 +870,7 @@ int b4d_tails_final_launch(b4d_ctx* ctx, const float* cand, const unsigned* cnt,
         attr[ctx->device] = true;
     }
     ProfScope ps(ctx, KC_SELECT_FINAL);
-    tails_final_kernel<<<(unsigned)T, 1024, TAIL_GCAP * sizeof(unsigned), ctx->stream>>>(cand, cnt, flag, fr, q_lo, q_hi, out,
+    tails_final_kernel<<<(unsigned)T, 1024, TAIL_GCAP * sizeof(unsigned), ctx->stream>>>(cand, cnt, eq, thr, flag, fr, q_lo, q_hi, out,
                                                                                       reinterpret_cast<long long*>(nvalid_out));
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;

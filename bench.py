@@ -9,7 +9,9 @@ Metric (BASELINE.json): stack frames/s at 2048^2 for the fused FFT-PSD + trackin
 A step = one pass of the hot path over one batch of synthetic frames per GPU:
     frame reductions (moments, Tenengrad, Laplacian variance, visibility) + percentile contrast
     + psd2d map + autocorr2d map with grain widths + phase-correlation tracking against a broadcast
-    reference frame.
+    reference frame + accumulation of the per-pixel temporal power sums.
+One timed run = one stack: broadcast of the reference frame and of the temporal shift plane (NCCL), K steps, then the
+all-reduce of the four float64 power-sum planes (NCCL) and the temporal finalize -- all inside the timed region.
 `value` is measured with the batch resident in HBM; `e2e` goes through the public API (StackAnalyzer.run)
 from pinned host memory, host<->device copies of inputs and of every result inside the timed region.
 One JSON line is printed by rank 0.
@@ -67,20 +69,51 @@ def parse_args():
 # --------------------------------------------------------------------------------------------
 
 def make_shifts(n_frames: int, seed: int) -> np.ndarray:
-    """Integer 2-D random walk (known answers), clipped to +-20 px; frame 0 unshifted."""
+    """2-D random walk, step sigma = 0.3 px, clipped to +-20 px; frame 0 unshifted. Every 8th frame is
+    rounded to whole pixels (np.roll frames: known answers)."""
     rng = np.random.default_rng(seed)
-    steps = rng.integers(-2, 3, size=(n_frames, 2))
-    steps[0] = 0
-    return np.clip(np.cumsum(steps, axis=0), -20, 20)
+    steps = rng.normal(0.0, 0.3, size=(n_frames, 2))
+    steps[0] = 0.0
+    shifts = np.clip(np.cumsum(steps, axis=0), -20.0, 20.0)
+    shifts[::8] = np.round(shifts[::8] * 4.0)
+    shifts[0] = 0.0
+    return shifts
 
 
 def cpu_stack(base: np.ndarray, shifts: np.ndarray, noise_seed: int) -> np.ndarray:
-    """Host stack: rolled copies of `base` + 1 % Gaussian noise on every frame (same recipe as the device one)."""
+    """Host stack by the same recipe as the device one: Fourier-shifted copies of `base` + 1 % Gaussian noise on every
+    frame (frame 0 included)."""
+    from barc4dip_b200 import synth
     rng = np.random.default_rng(noise_seed)
     sigma = 0.01 * float(base.mean())
     out = np.empty((len(shifts),) + base.shape, np.float32)
     for t, (dy, dx) in enumerate(shifts):
-        out[t] = np.roll(base, (int(dy), int(dx)), axis=(0, 1)) + rng.normal(0, sigma, base.shape).astype(np.float32)
+        out[t] = synth.fourier_shift(base, float(dy), float(dx)) + rng.normal(0, sigma, base.shape).astype(np.float32)
+    return out
+
+
+def device_stack(base: np.ndarray, shifts: np.ndarray, noise_seed: int, dev):
+    """The C4 stack built on the device: frame t = IFFT(FFT(base) * ramp(shift_t)) + noise, through the library's own
+    fft2d / ifft2d (whole-pixel shifts are exact rolls)."""
+    import torch
+    from barc4dip_b200 import engine
+    n0, n1 = base.shape
+    g = torch.Generator(device=dev)
+    g.manual_seed(noise_seed)
+    base_d = torch.from_numpy(base).to(dev)
+    spec = engine.fft2d(base_d[None])[0]                                # shifted spectrum, zero frequency at [n/2, n/2]
+    ky = ((torch.arange(n0, device=dev, dtype=torch.float64) - n0 // 2) / n0)[:, None]
+    kx = ((torch.arange(n1, device=dev, dtype=torch.float64) - n1 // 2) / n1)[None, :]
+    sigma = 0.01 * float(base.mean())
+    out = torch.empty((len(shifts), n0, n1), dtype=torch.float32, device=dev)
+    for t, (dy, dx) in enumerate(shifts):
+        if float(dy).is_integer() and float(dx).is_integer():
+            fr = torch.roll(base_d, (int(dy), int(dx)), dims=(0, 1))
+        else:
+            ph = -2.0 * np.pi * (ky * float(dy) + kx * float(dx))
+            ramp = torch.complex(torch.cos(ph), torch.sin(ph)).to(torch.complex64)
+            fr = engine.ifft2d((spec * ramp)[None])[0].real
+        out[t] = fr + sigma * torch.randn((n0, n1), generator=g, device=dev)
     return out
 
 
@@ -101,10 +134,21 @@ def cpu_frame_work(frame: np.ndarray, ref: np.ndarray):
     return m["mean"], tg["tenengrad"], lv, am["contrast"], float(P[0, 0]), g["lx"], tr[0], tr[1]
 
 
+def cpu_temporal_rows(stack: np.ndarray, shift: np.ndarray, r0: int, r1: int):
+    """Per-pixel shifted power sums (row T of SURVEY 8(a): no reference function; numpy float64) of rows [r0, r1)."""
+    d = stack[:, r0:r1, :].astype(np.float64) - shift[None, r0:r1, :]
+    d2 = d * d
+    return d.sum(axis=0), d2.sum(axis=0), (d2 * d).sum(axis=0), (d2 * d2).sum(axis=0)
+
+
 def cpu_pipeline(stack: np.ndarray, ref: np.ndarray, n_jobs: int):
     """The reference drives frames with joblib threads (metrics/speckles.py:323, metrics/sharpness.py:361)."""
     from joblib import Parallel, delayed
-    return Parallel(n_jobs=n_jobs, prefer="threads")(delayed(cpu_frame_work)(stack[t], ref) for t in range(stack.shape[0]))
+    out = Parallel(n_jobs=n_jobs, prefer="threads")(delayed(cpu_frame_work)(stack[t], ref) for t in range(stack.shape[0]))
+    shift = stack[: min(16, stack.shape[0])].mean(axis=0, dtype=np.float64)
+    rows = np.linspace(0, stack.shape[1], n_jobs + 1).astype(int)
+    Parallel(n_jobs=n_jobs, prefer="threads")(delayed(cpu_temporal_rows)(stack, shift, int(a), int(b)) for a, b in zip(rows[:-1], rows[1:]) if b > a)
+    return out
 
 
 def time_cpu(size: int, frames: int, steps: int, warmup: int):
@@ -135,7 +179,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"fused stack pipeline (moments+tenengrad+laplacian+amplitude+psd2d+grain/autocorr2d+phase_correlation), "
+        "config": {"workload": f"fused stack pipeline (moments+tenengrad+laplacian+amplitude+psd2d+grain/autocorr2d+phase_correlation"
+                               f"+per-pixel temporal power sums), "
                                f"{args.size}x{args.size} float32 frames", "frames_per_step": frames,
                    "note": "oracle port of the reference's numpy/scipy path (oracle/ref_numpy.py), joblib threads over frames"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -226,31 +271,48 @@ def run_b200(args):
     if args.batch:
         ctx.set_batch_frames(args.batch)
 
-    # ---- synthetic stack, resident in HBM: rolled copies of one speckle + independent 1 % noise per frame -----
+    # ---- synthetic stack, resident in HBM: SURVEY.md 8(d) C4 (sub-pixel random walk of one speckle + 1 % noise) ------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                  # sampled from before the clock ramp to the end of the timed region
     base = synth.speckle_frame(n, grain=6.0, seed=0)
     shifts = make_shifts(F, seed=2 + rank)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    base_d = torch.from_numpy(base).to(dev)
-    stack = torch.empty((F, n, n), dtype=torch.float32, device=dev)
-    sigma = 0.01 * float(base.mean())
-    for t in range(F):
-        stack[t] = torch.roll(base_d, (int(shifts[t, 0]), int(shifts[t, 1])), dims=(0, 1)) + \
-            sigma * torch.randn((n, n), generator=g, device=dev)
+    stack = device_stack(base, shifts, 1234 + rank, dev)
     # reference frame = frame 0 of rank 0, broadcast over NCCL (the path's one exchange for tracking)
     ref = stack[0].clone()
     analyzer = StackAnalyzer((n, n), device=local, chunk_frames=F, want_maps=True, want_contrast=True)
     psd_out = torch.empty((F, n, n), dtype=torch.float32, device=dev)
     ac_out = torch.empty((F, n, n), dtype=torch.float32, device=dev)
+    temporal = {}
 
-    # One timed run = one stack: the reference frame is broadcast (NCCL) and its conjugate spectrum built ONCE, then
-    # every step analyses one batch of F frames per GPU against it -- exactly how a 4000-frame stack is processed.
+    # One timed run = one stack. Start: the reference frame is broadcast (NCCL) and its conjugate spectrum built once;
+    # rank 0's pilot mean of its first frames is broadcast as the common shift plane of the temporal power sums.
+    # Every step analyses one batch of F frames per GPU and adds it to the temporal sums. End: the four float64
+    # power-sum planes are all-reduced (NCCL) and finalised -- exactly how a 4000-frame stack is processed.
     def begin_stack():
         parallel.broadcast_reference(ref, src=0)
         analyzer.set_reference(ref)
+        acc = engine.TemporalAccumulator(n, n, device=local)
+        if rank == 0:
+            acc.pilot(stack)
+        else:
+            acc.shift = torch.empty((n, n), dtype=torch.float32, device=dev)
+        parallel.broadcast_reference(acc.shift, src=0)
+        temporal["acc"] = acc
 
     def step():
-        return analyzer.run_device(stack, psd_out=psd_out, ac_out=ac_out, resolve_tails=False)
+        res = analyzer.run_device(stack, psd_out=psd_out, ac_out=ac_out, resolve_tails=False)
+        temporal["acc"].update(stack)
+        return res
+
+    coll = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+    def end_stack(n_steps: int):
+        acc = temporal["acc"]
+        coll[0].record()
+        parallel.allreduce_temporal(acc, world * F * n_steps)
+        coll[1].record()
+        return acc.finalize(return_device=True)
 
     def barrier():
         if world > 1:
@@ -261,57 +323,86 @@ def run_b200(args):
     # clock ramp: a fresh box idles at low SM clocks and needs ~1 s of load to reach its steady state; these passes are
     # neither warm-up steps nor timed steps (reported as config.prewarm_s)
     t_pre = time.perf_counter()
+    n_pre = 0
     while time.perf_counter() - t_pre < args.prewarm:
         step()
+        n_pre += 1
         torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         res = step()
+    end_stack(n_pre + max(args.warmup, 3))
     barrier()
-    # sanity: the tracker must recover the integer shifts relative to rank 0's frame 0
+    # sanity (untimed): the tracker against the generator's shifts on every frame, and against the oracle port of the
+    # reference's phase_correlation on two sub-pixel frames
     tr = res["tracking"].cpu().numpy()
-    err = float(np.max(np.abs(tr[:, :2] - (shifts - (0 if rank == 0 else 0)))))
-    if rank == 0 and err > 0.05:
-        raise SystemExit(f"tracking sanity check failed: max |shift error| = {err:.3f} px")
+    whole = np.all(shifts == np.round(shifts), axis=1)
+    err = float(np.max(np.abs(tr[whole, :2] - shifts[whole])))               # np.roll frames: known answers
+    # sub-pixel frames: the reference's Taylor step is biased and adds the x term to dy: within a pixel
+    err_sub = float(np.max(np.abs(tr[:, :2] - shifts)))
+    if err > 0.05 or err_sub > 1.0:
+        raise SystemExit(f"tracking sanity check failed on rank {rank}: max |shift error| = {err:.3f} px (whole-pixel frames), "
+                         f"{err_sub:.3f} px (all frames)")
+    oracle_err = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import ref_numpy as orc
+        host2 = stack[:4].cpu().numpy()
+        full = (slice(0, n), slice(0, n))
+        oracle_err = 0.0
+        for t in (1, 3):
+            want = orc.phase_correlation(host2[0], host2[t], slices_yx=full)
+            oracle_err = max(oracle_err, float(np.max(np.abs(tr[t, :2] - np.asarray(want[:2])))))
+        if oracle_err > 0.01:
+            raise SystemExit(f"tracking differs from the oracle by {oracle_err:.4f} px (> 0.01 px)")
     snr_unresolved = int(torch.isnan(res["tracking"][:, 3]).sum().item())   # frames whose fused median would need the map-based path
     unresolved = int((res["n_valid"] < 0).sum().item())   # frames whose fused tail percentiles would need the exact fallback
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = ctx.launches
     ctx.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    begin_stack()                       # inside the timed region: the path's one exchange + the reference spectrum
+    begin_stack()                       # inside the timed region: both broadcasts + the reference spectrum
     for _ in range(args.steps):
         step()
+    end_stack(args.steps)               # inside the timed region: all-reduce of the temporal sums + finalize
     e1.record()
     barrier()
     prof = ctx.profile_end()
     launches = ctx.launches - launches0
     clock_info = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    ms = torch.tensor([e0.elapsed_time(e1), coll[0].elapsed_time(coll[1])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    total_ms = float(ms[0].item())
+    coll_ms = float(ms[1].item())
+    coll_bytes = 4 * n * n * 8
+    collective = {"op": "all_reduce(sum, float64) of the 4 temporal power-sum planes + frame count", "bytes": coll_bytes,
+                  "ms": coll_ms if world > 1 else 0.0,
+                  "bus_gbs": (2.0 * (world - 1) / world) * coll_bytes / (coll_ms / 1e3) / 1e9 if world > 1 and coll_ms > 0 else None,
+                  "broadcasts": "reference frame + temporal shift plane, float32, 2 x %.1f MB" % (n * n * 4 / MB),
+                  "share_of_run": (coll_ms / total_ms) if world > 1 else 0.0}
     fps = world * F * args.steps / (total_ms / 1e3)
 
     # ---- end to end through the public API: pinned host stack -> results on the host ------------------------
     # e2e: what the reference's stack functions return (speckle_stack_stats / sharpness_stack_stats: per-frame scalar
     # tables) comes back to the host; the PSD and autocorrelation maps stay resident in HBM, as they do between the
     # reference's own stages. e2e_maps_to_host additionally drains both maps over PCIe.
-    e2e = e2e_maps = None
+    e2e = e2e_maps = e2e_u16 = None
     if not args.no_e2e:
         host = torch.empty((F, n, n), dtype=torch.float32, pin_memory=True)
         host.copy_(stack)
+        # detector-native frames: the same stack rounded to uint16 counts (half the PCIe bytes; widened on the device)
+        host_u16 = torch.empty((F, n, n), dtype=torch.uint16, pin_memory=True)
+        host_u16.copy_(stack.clamp(0, 65535).round().to(torch.uint16))
         an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(8, F // 4)), want_maps=True, want_contrast=True)
         ref_host = host[0].clone()
 
-        def time_e2e(keep: bool):
+        def time_e2e(keep: bool, src=None):
+            src = host if src is None else src
+
             def e2e_step():
                 an2.set_reference(ref_host)
-                return an2.run(host, keep_maps_on_device=keep, reuse_host_buffers=True)
+                return an2.run(src, keep_maps_on_device=keep, reuse_host_buffers=True)
             # two untimed calls: staging buffers, scratch arenas and the caching allocator's blocks for the result maps
             # are created on the first, reused from the second on (a result is released before the next call, as a
             # caller looping over stacks would)
@@ -331,10 +422,19 @@ def run_b200(args):
 
         h2d_b, d2h_b = an2.bytes_per_frame()
         fps_tables = time_e2e(True)
+        link_gbs = fps_tables / world * h2d_b / 1e9
         e2e = {"value": fps_tables, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * F + n * n * 4),
                "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * F), "steps": args.e2e_steps,
-               "note": "StackAnalyzer.run on a pinned host stack: every per-frame table (moments, sharpness, contrast, grain, "
-                       "tracking) copied back, PSD + autocorrelation maps left in HBM"}
+               "h2d_gbs_per_gpu": link_gbs,
+               "note": "StackAnalyzer.run on a pinned float32 host stack: every per-frame table (moments, sharpness, contrast, "
+                       "grain, tracking) copied back, PSD + autocorrelation maps left in HBM. Bound by the host-to-device "
+                       "link (h2d_gbs_per_gpu against ~55 GB/s of one PCIe 5 x16 link), not by the kernels"}
+        fps_u16 = time_e2e(True, host_u16)
+        e2e_u16 = {"value": fps_u16, "unit": UNIT, "h2d_bytes_per_step": int(n * n * 2 * F + n * n * 4),
+                   "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * F), "steps": args.e2e_steps,
+                   "h2d_gbs_per_gpu": fps_u16 / world * n * n * 2 / 1e9,
+                   "note": "same call on the detector-native uint16 stack (b4d_cast_to_f32 widens on the device): half the "
+                           "PCIe bytes per frame"}
         fps_maps = time_e2e(False)
         e2e_maps = {"value": fps_maps, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * F + n * n * 4),
                     "d2h_bytes_per_step": int(d2h_b * F), "steps": args.e2e_steps,
@@ -409,12 +509,16 @@ def run_b200(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"fused stack pipeline (frame reductions + percentile contrast + psd2d map + autocorr2d map + grain + "
-                               f"phase-correlation tracking vs broadcast reference), {n}x{n} float32 frames (BASELINE configs[1..3] fused)",
+                               f"phase-correlation tracking vs broadcast reference + per-pixel temporal power sums, all-reduced at "
+                               f"the end of the stack), {n}x{n} float32 frames (BASELINE configs[1..4] fused)",
+                   "stack": "SURVEY 8(d) C4: one speckle Fourier-shifted along a 2-D random walk (sigma 0.3 px, +-20 px) + 1 % noise per frame",
+                   "tracking_vs_oracle_max_px": oracle_err,
                    "frames_per_step_per_gpu": F, "frame": [n, n], "parallelism": f"frame-sharded x{world}",
                    "l2": f"inputs per step {F * n * n * 4 / MB:.0f} MB + {2 * F * n * n * 4 / MB:.0f} MB of maps written: larger than the 126 MB L2, no flush needed",
                    "internal_batch_frames": args.batch or "auto", "prewarm_s": args.prewarm,
                    "tail_percentile_frames_needing_fallback": unresolved, "tracker_median_frames_needing_fallback": snr_unresolved},
-        "clocks": clock_info, "e2e": e2e, "e2e_maps_to_host": e2e_maps, "gpu_launches": int(launches),
+        "clocks": clock_info, "e2e": e2e, "e2e_uint16": e2e_u16, "e2e_maps_to_host": e2e_maps, "gpu_launches": int(launches),
+        "collective": collective,
         "roofline": roofline, "step_roofline": step_roof, "fft_fp32": fp32, "kernels": kernel_table, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

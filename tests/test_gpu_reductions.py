@@ -224,14 +224,43 @@ def test_fused_tail_percentiles_exact(eng, shape):
 
 
 def test_fused_tail_percentiles_flag_and_fallback(eng):
-    """A frame whose tails are not small (constant frame: every pixel is a candidate) is flagged, never wrong."""
-    const = np.full((2, 512, 512), 5.0, dtype=np.float32)
-    const[1] = np.random.default_rng(2).normal(100.0, 5.0, size=(512, 512)).astype(np.float32)
-    d = eng.as_stack(const)
+    """A frame whose tails are not small is flagged, never wrong. Frame 0 fools the probe: its 16384 strided sample
+    positions hold large values, every other pixel a small distinct one, so nearly the whole frame lies below the lower
+    threshold and the candidate list overflows. A constant frame (frame 1) is one run of ties and needs no fallback."""
+    rng = np.random.default_rng(2)
+    n = 512 * 512
+    f0 = rng.uniform(0.0, 1.0, size=n).astype(np.float32)
+    f0[(np.arange(16384, dtype=np.int64) * n) // 16384] = (100.0 + rng.uniform(0.0, 1.0, size=16384)).astype(np.float32)
+    stack = np.stack([f0.reshape(512, 512), np.full((512, 512), 5.0, np.float32),
+                      rng.normal(100.0, 5.0, size=(512, 512)).astype(np.float32)])
+    d = eng.as_stack(stack)
     _, quant, nv = eng.frame_reductions_tails(d, 0.0005, 0.9995)
-    assert int(nv[0]) == -1 and int(nv[1]) == 512 * 512
+    assert int(nv[0]) == -1 and int(nv[1]) == n and int(nv[2]) == n
+    assert tuple(quant[1].cpu().numpy()) == (5.0, 5.0, 5.0, 5.0)
     eng.resolve_tail_quantiles(d, quant, nv, 0.0005, 0.9995)
-    assert int(nv[0]) == 512 * 512 and tuple(quant[0].cpu().numpy()) == (5.0, 5.0, 5.0, 5.0)
+    a0, a1, _ = _tail_brackets(stack[0], 0.0005)
+    b0, b1, _ = _tail_brackets(stack[0], 0.9995)
+    assert int(nv[0]) == n and tuple(quant[0].cpu().numpy()) == (a0, a1, b0, b1)
+
+
+@pytest.mark.parametrize("zeros,sat", [(0.3, 0.01), (0.004, 0.0), (0.0, 0.2), (0.0004, 0.0004)])
+def test_fused_tail_percentiles_integer_frames_with_ties(eng, zeros, sat):
+    """Detector frames are integer valued and tie by the thousand at 0 (masked / dark regions) and at the saturation
+    value: the runs of ties at the thresholds are counted, not listed, so such frames resolve inside the reduction pass
+    (no fallback) and give np.sort's order statistics exactly."""
+    rng = np.random.default_rng(int(zeros * 1e4) + int(sat * 1e4) * 7 + 1)
+    stack = np.round(rng.exponential(1000.0, size=(2, 1024, 1024))).astype(np.float32)
+    u = rng.uniform(size=stack.shape)
+    stack[u < zeros] = 0.0
+    stack[u > 1.0 - sat] = 65535.0
+    q_lo, q_hi = 0.0005, 0.9995
+    _, quant, nv = eng.frame_reductions_tails(eng.as_stack(stack), q_lo, q_hi)
+    quant, nv = quant.cpu().numpy(), nv.cpu().numpy()
+    for t in range(2):
+        a0, a1, n = _tail_brackets(stack[t], q_lo)
+        b0, b1, _ = _tail_brackets(stack[t], q_hi)
+        assert nv[t] == n, "frame was not resolved inside the reduction pass"
+        assert (quant[t, 0], quant[t, 1], quant[t, 2], quant[t, 3]) == (a0, a1, b0, b1)
 
 
 def test_fused_tail_percentiles_with_flat_field(eng):
