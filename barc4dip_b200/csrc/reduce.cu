@@ -393,10 +393,12 @@ __device__ __forceinline__ Win2 finish2(const Fr2Args& a, const float4 raw, floa
             // at the saturation value, and the order statistics inside a run of ties is the tie itself.
             const float mn = fminf(fminf(raw.x, raw.y), fminf(raw.z, raw.w));
             if (mn <= thr_lo || mx >= thr_hi) {
-                const unsigned el = (raw.x == thr_lo) + (raw.y == thr_lo) + (raw.z == thr_lo) + (raw.w == thr_lo);
-                const unsigned eh = (raw.x == thr_hi) + (raw.y == thr_hi) + (raw.z == thr_hi) + (raw.w == thr_hi);
-                if (el) atomicAdd(s_eq, el);
-                if (eh) atomicAdd(s_eq + 1, eh);
+                if (mn == thr_lo || mx == thr_hi) {
+                    const unsigned el = (raw.x == thr_lo) + (raw.y == thr_lo) + (raw.z == thr_lo) + (raw.w == thr_lo);
+                    const unsigned eh = (raw.x == thr_hi) + (raw.y == thr_hi) + (raw.z == thr_hi) + (raw.w == thr_hi);
+                    if (el) atomicAdd(s_eq, el);
+                    if (eh) atomicAdd(s_eq + 1, eh);
+                }
                 if (mn < thr_lo || mx > thr_hi) {
                     const unsigned p = atomicAdd(s_qn, 1u);
                     if (p < F2_QCAP) s_queue[p] = raw;

@@ -27,7 +27,18 @@ int b4d_select_impl(b4d_ctx* ctx, const float* stack, int64_t T, int64_t n, cons
                     int use_abs, float* out, int64_t* n_valid);
 int b4d_put_doubles(b4d_ctx* ctx, double* dst, const double* src_host, int n);
 
+struct RefBuffers {                   // device buffers of one tracker reference (see b4d_ref)
+    float2* ref = nullptr;
+    float2* ref_nyq = nullptr;
+    float2* gref = nullptr;
+    size_t gref_elems = 0;
+    int ny = 0, nx = 0;
+};
+
 struct FftPlanCache {
+    // released reference buffers, kept for the next b4d_phase_reference_create of the same frame shape (a tracker per
+    // stack, or per frame in incremental tracking, would otherwise pay a cudaMalloc / cudaFree pair of 17 MB each time)
+    std::vector<RefBuffers> ref_pool;
     float2* twb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // base-power twiddle tables: 128 ... 4096
     // tracker reference: conj spectrum of the embedded z-scored template
     float2* ref = nullptr;       // blocked (nx/2/8, ny, 8)
@@ -2061,6 +2072,12 @@ void pipe_graphs_release(b4d_ctx* ctx);
 void b4d_fft_release(b4d_ctx* ctx) {
     pipe_graphs_release(ctx);
     if (!ctx->fft) return;
+    for (auto& b : ctx->fft->ref_pool) {
+        if (b.ref) cudaFree(b.ref);
+        if (b.ref_nyq) cudaFree(b.ref_nyq);
+        if (b.gref) cudaFree(b.gref);
+    }
+    ctx->fft->ref_pool.clear();
     gen_release(static_cast<GenCache*>(ctx->fft->gen));
     if (ctx->fft->gref) cudaFree(ctx->fft->gref);
     for (int i = 0; i < 6; ++i) if (ctx->fft->twb[i]) cudaFree(ctx->fft->twb[i]);
@@ -2311,7 +2328,20 @@ extern "C" int b4d_phase_reference_create(b4d_ctx* ctx, const float* tpl, int h,
     int rc;
     b4d_ref* r = new b4d_ref();
     {
-        RefSwap sw(ctx, nullptr);                     // the context's own reference is put aside, fresh buffers are made
+        // the context's own reference is put aside; buffers of a released reference of the same shape are reused,
+        // otherwise the body allocates fresh ones
+        b4d_ref seed;
+        if (ctx->fft) {
+            auto& pool = ctx->fft->ref_pool;
+            for (size_t i = 0; i < pool.size(); ++i)
+                if (pool[i].ny == ny && pool[i].nx == nx) {
+                    seed.ref = pool[i].ref; seed.ref_nyq = pool[i].ref_nyq; seed.gref = pool[i].gref;
+                    seed.gref_elems = pool[i].gref_elems; seed.ny = ny; seed.nx = nx;
+                    pool.erase(pool.begin() + i);
+                    break;
+                }
+        }
+        RefSwap sw(ctx, seed.ny ? &seed : nullptr);
         rc = phase_set_reference_body(ctx, tpl, h, w, ny, nx, y0, x0, eps);
         FftPlanCache* f = ctx->fft;
         r->ref = f->ref; r->ref_nyq = f->ref_nyq; r->gref = f->gref; r->gref_elems = f->gref_elems; r->ny = f->ref_ny; r->nx = f->ref_nx;
@@ -2332,11 +2362,20 @@ extern "C" int b4d_phase_reference_destroy(b4d_ctx* ctx, b4d_ref* r) {
     if (!r) return B4D_OK;
     B4dCall g(ctx);
     cudaDeviceSynchronize();                          // (launches that read it may be in flight on any of the context's streams)
-    pipe_graphs_release(ctx);                         // captured batches carry its pointers
-    if (r->ref) cudaFree(r->ref);
-    if (r->ref_nyq) cudaFree(r->ref_nyq);
-    if (r->gref) cudaFree(r->gref);
+    RefBuffers b;
+    b.ref = r->ref; b.ref_nyq = r->ref_nyq; b.gref = r->gref; b.gref_elems = r->gref_elems; b.ny = r->ny; b.nx = r->nx;
     delete r;
+    if (!ctx->fft) ctx->fft = new FftPlanCache();
+    auto& pool = ctx->fft->ref_pool;
+    pool.push_back(b);
+    if (pool.size() > 4) {                            // really freed: captured batches may carry its pointers
+        pipe_graphs_release(ctx);
+        RefBuffers old = pool.front();
+        pool.erase(pool.begin());
+        if (old.ref) cudaFree(old.ref);
+        if (old.ref_nyq) cudaFree(old.ref_nyq);
+        if (old.gref) cudaFree(old.gref);
+    }
     return B4D_OK;
 }
 

@@ -330,7 +330,15 @@ def run_b200(args):
         torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         res = step()
-    end_stack(n_pre + max(args.warmup, 3))
+    # a whole untimed stack before the timed one: the end of the stack (all-reduce, finalize) and a second start warm the
+    # allocator's blocks and NCCL's channels the way any second stack of a session finds them
+    coll[0].record()                    # (the ranks ran different numbers of untimed passes: no frame-count check here)
+    parallel.allreduce_temporal(temporal["acc"])
+    coll[1].record()
+    temporal["acc"].finalize(return_device=True)
+    begin_stack()
+    step()
+    end_stack(1)
     barrier()
     # sanity (untimed): the tracker against the generator's shifts on every frame, and against the oracle port of the
     # reference's phase_correlation on two sub-pixel frames
@@ -360,21 +368,26 @@ def run_b200(args):
     ctx.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    e_b, e_s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     begin_stack()                       # inside the timed region: both broadcasts + the reference spectrum
+    e_b.record()
     for _ in range(args.steps):
         step()
+    e_s.record()
     end_stack(args.steps)               # inside the timed region: all-reduce of the temporal sums + finalize
     e1.record()
     barrier()
     prof = ctx.profile_end()
     launches = ctx.launches - launches0
     clock_info = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1), coll[0].elapsed_time(coll[1])], dtype=torch.float64, device=dev)
+    ms = torch.tensor([e0.elapsed_time(e1), coll[0].elapsed_time(coll[1]), e0.elapsed_time(e_b), e_b.elapsed_time(e_s),
+                       e_s.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms[0].item())
     coll_ms = float(ms[1].item())
+    phases = {"begin_stack_ms": float(ms[2].item()), "steps_ms": float(ms[3].item()), "end_stack_ms": float(ms[4].item())}
     coll_bytes = 4 * n * n * 8
     collective = {"op": "all_reduce(sum, float64) of the 4 temporal power-sum planes + frame count", "bytes": coll_bytes,
                   "ms": coll_ms if world > 1 else 0.0,
@@ -518,7 +531,7 @@ def run_b200(args):
                    "internal_batch_frames": args.batch or "auto", "prewarm_s": args.prewarm,
                    "tail_percentile_frames_needing_fallback": unresolved, "tracker_median_frames_needing_fallback": snr_unresolved},
         "clocks": clock_info, "e2e": e2e, "e2e_uint16": e2e_u16, "e2e_maps_to_host": e2e_maps, "gpu_launches": int(launches),
-        "collective": collective,
+        "collective": collective, "phases": phases,
         "roofline": roofline, "step_roofline": step_roof, "fft_fp32": fp32, "kernels": kernel_table, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
