@@ -202,7 +202,8 @@ def sharpness_stack_stats(stack, *, metrics="all", tiles: bool = True, display_o
             }
     out_full = {grp: full[grp] for grp in _GROUP_ORDER if grp in full}
     out = {"meta": meta, "full": out_full}
-    mode, _ = choose_tiling_mode(H, W, tiles=tiles)
+    mode, tile_shape_px = choose_tiling_mode(H, W, tiles=tiles)
+    meta.update(tiles_meta(H, W, tile_mode=mode, tile_shape_px=tile_shape_px))      # (sharpness.py:384)
     if mode != "off":
         oriented = dev.flip(1) if normalize_display_origin(display_origin) == "lower" else dev
         tl = _tiles(oriented, mode, groups, saturation_value, eps)

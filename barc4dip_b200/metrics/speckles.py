@@ -181,7 +181,7 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
                         roi_grain_factor: float = 3.0, roi_step_factor: float = 0.5, tracking_method: str = "template",
                         tracking_backend: str = "skimage", subpixel: bool = True,
                         saturation_value: float | None = 65535.0, eps: float = 1e-6, verbose: bool = True,
-                        parallel: bool = True, n_jobs: int | None = None, keep_autocorr: bool = False,
+                        parallel: bool = True, n_jobs: int | None = None, keep_autocorr: bool = True,
                         sharded: bool | None = None) -> dict:
     """Per-frame speckle metrics of a (T, H, W) stack plus 3x3-ROI translation tracking (abs / inc).
 
@@ -191,9 +191,9 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     all-gathered: all ranks return the full result, identical to the single-GPU one.
 
     Trackers: "template" (the reference's default; both of its backend names are served by the same normalised
-    cross-correlation kernels, pinned against opencv) and "phase" / "internal". Difference from the reference, explicit:
-    the per-frame (T, N, N) float64 autocorrelation stack is returned only with keep_autocorr=True (32 MB per 2048^2
-    frame on the host, SURVEY.md section 7 "hard parts").
+    cross-correlation kernels, pinned against opencv) and "phase" / "internal". Like the reference, the result carries
+    the per-frame (T, N, N) float64 autocorrelation stack in full["grain"] (32 MB per 2048^2 frame on the host, SURVEY.md
+    section 7 "hard parts"); keep_autocorr=False, the one keyword the reference does not have, leaves it out.
     """
     if not isinstance(stack, np.ndarray):
         raise TypeError("speckle_stack_stats expects a numpy.ndarray")

@@ -147,6 +147,27 @@ def tiles_golden(met, versions):
     np.savez_compressed(os.path.join(OUT, "tiles.npz"), **store)
 
 
+def schema_golden(met):
+    """schema.json: key tree / kinds / dtypes / shapes of the reference's aggregator dicts, plus the number-masked text
+    of the reference's own logbook_report on them (report/markdown.py:37)."""
+    import importlib
+    import json
+    from oracle import schema as sc
+    rep = importlib.import_module("barc4dip.report.markdown")
+    out = {}
+    for name, call in sc.schema_calls(met).items():
+        d = call()
+        entry = {"tree": sc.schema_tree(d)}
+        try:
+            entry["markdown"] = {f"complete={c}": sc.markdown_skeleton(rep.logbook_report(d, complete=c, notes=False)) for c in (False, True)}
+        except ValueError as e:                        # the stack variants have no formatter in the reference
+            entry["markdown_error"] = str(e)
+        out[name] = entry
+        print(name, len(entry["tree"]), "leaves", "markdown" if "markdown" in entry else entry["markdown_error"])
+    with open(os.path.join(OUT, "schema.json"), "w") as fh:
+        json.dump(out, fh, indent=0, sort_keys=True)
+
+
 def main():
     ref = load_reference()
     sig, met, pre = ref.signal, ref.metrics, ref.preprocessing_normalize
@@ -164,6 +185,9 @@ def main():
         return
     if "--only-repair" in sys.argv:
         repair_golden(pre, versions)
+        return
+    if "--only-schema" in sys.argv:
+        schema_golden(met)
         return
     if "--only-tiles" in sys.argv:
         tiles_golden(met, versions)
