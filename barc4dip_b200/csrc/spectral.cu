@@ -16,6 +16,8 @@
 //                 fftshifted stores, peak normalisation, argmax partials.
 // Every frame is shifted by a pilot mean K before the FFT (K*nx*ny is added back to the DC bin),
 // so fp32 rounding is relative to the fluctuations, not to the pedestal.
+#include <cuda.h>            // CUtensorMap (the driver entry point itself is fetched through the runtime)
+
 #include "common.cuh"
 #include "fft.cuh"
 #include "select.cuh"
@@ -240,7 +242,30 @@ struct ColsArgs {
     const double* fr;           // frame-reduction table (mean, m2) for the z-score; nullable
     int fr_stride;
     int keep;                   // cache policy of the intermediates (see st_inter)
+    int psd_tma;                // the PSD map leaves through TMA tensor stores (set by the launcher, see cols_body)
 };
+
+// ---- TMA (cp.async.bulk.tensor) helpers of the column pass --------------------------------------------------------
+// The PSD map is row-major (T, ny, nx) and a CTA owns 8 adjacent columns: written from registers that is one 32-byte
+// piece per row and thread, twice (the Hermitian mirror), 0.52 M of the pass's 2.4 M load/store wavefronts per frame. With
+// psd_tma the CTA instead stages the scaled |F|^2 tile in shared memory -- the exchange buffer is idle between the
+// forward transform and the first exchange of the inverse one -- as a dense [ny][8] float tile in OUTPUT row order, and
+// one thread hands it to the TMA unit as ny/256 boxes of 256 rows x 8 columns
+// (cp.async.bulk.tensor.2d.global.shared::cta): for that half of the map the load/store pipe sees 16 conflict-free STS
+// instead of 16 four-wavefront STG per thread, and the row-strided global writes are generated by the copy engine while
+// the CTA goes on with the product / inverse transform. The mirrored half stays on STG: the TMA unit wants the innermost
+// coordinate of a store 16-byte aligned (measured on B200: an unaligned one raises "illegal instruction"), the main
+// columns hx + 8 tile .. + 7 are, their mirrors hx - 8 tile - 7 .. hx - 8 tile start one float past a 16-byte boundary
+// for every tile.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int x, int y) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(s) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr int TMA_BOX_ROWS = 256;
 
 struct SpecAcc {
     double total = 0, fx2 = 0, fy2 = 0, p2 = 0, all = 0, plogp = 0;
@@ -285,7 +310,7 @@ __device__ __forceinline__ float2 whiten_if(float2 G, int whiten, float eps) {
 // (thread-dependent unpacking branches at every element), false for the other tiles, whose code then carries no
 // branch at all inside the element loops.
 template <int NY, int CW, bool SPEC, bool AC, bool PC, bool TILE0>
-__device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double* red) {
+__device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double* red, const CUtensorMap* tmap) {
     constexpr int T = NY / 16;
     constexpr int NT = T * CW;
     constexpr int PL = padded_len(NY);
@@ -323,6 +348,11 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     // from L2 instead of letting them be written back, one 128-byte line per thread
     if (CW == TC && (a.keep & 4))
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.H + (size_t)t * NY * hx + (size_t)tile * NY * TC + (size_t)tid * 16) : "memory");
+    // TMA path of the PSD map (every tile but tile 0, whose packed DC / Nyquist column has its own rules): the exchange
+    // buffer becomes the staging area of the main tile Bs[ky'][c], indexed by OUTPUT row ky' = (ky + NY/2) % NY
+    const bool tma = !TILE0 && CW == TC && NY >= TMA_BOX_ROWS && a.psd_tma && a.psd_out;
+    float* Bs = reinterpret_cast<float*>(A);
+    if (tma) __syncthreads();                         // (other threads may still be reading the last exchange)
 
     // ---- tile 0: column 0 carries C = F[:,0] + i F[:,nx/2]; publish it so that its owners can read C[-ky]
     float2* A0 = A;                                   // natural order, [NY]
@@ -376,7 +406,8 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             if (nyq_owner) unpack0(s, F, Fn, dcshift);
             const float P = F.x * F.x + F.y * F.y;
             if (psd) {
-                __stcs(psd + (ptrdiff_t)um * (ptrdiff_t)rstride, P * ps);
+                if (tma) Bs[((ky + NY / 2) & (NY - 1)) * CW + c] = P * ps;
+                else __stcs(psd + (ptrdiff_t)um * (ptrdiff_t)rstride, P * ps);
                 if (mirror) __stcs(psdm + (ptrdiff_t)ur * (ptrdiff_t)rstride, P * ps);
             }
             if (cpl) {
@@ -400,6 +431,17 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
                 Bp[tid + s * NT] = Pa;
                 if (nyq_owner) Pns[ky] = Pn;
             }
+        }
+    }
+    if (tma) {
+        fence_async_smem();                           // the staged tiles become visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            const int x_main = hx + tile * CW;
+            const int y0 = (int)t * NY;
+#pragma unroll
+            for (int b = 0; b < NY / TMA_BOX_ROWS; ++b) tma_store_2d(tmap, Bs + b * TMA_BOX_ROWS * CW, x_main, y0 + b * TMA_BOX_ROWS);
+            tma_commit();
         }
     }
     if (PC) {
@@ -465,6 +507,9 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             }
         }
     }
+    // the copy engine must have read the staged tiles before the exchange buffer is written again (or the CTA leaves):
+    // the issuing thread waits here, everybody else meets it at the next barrier (entry of the inverse transform)
+    if (tma && tid == 0) tma_wait_read_all();
     if (!PC && !AC) return;
 
     // ---- inverse along y of the product ---------------------------------------------------------
@@ -508,11 +553,11 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
 }
 
 template <int NY, int CW, bool SPEC, bool AC, bool PC>
-__global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a) {
-    extern __shared__ float2 sm[];
+__global__ void __launch_bounds__(NY / 16 * CW, 1024 / (NY / 16 * CW)) cols_kernel(ColsArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) float2 sm[];
     __shared__ double red[32];
-    if (blockIdx.x == 0) cols_body<NY, CW, SPEC, AC, PC, true>(a, sm, red);
-    else cols_body<NY, CW, SPEC, AC, PC, false>(a, sm, red);
+    if (blockIdx.x == 0) cols_body<NY, CW, SPEC, AC, PC, true>(a, sm, red, &tmap);
+    else cols_body<NY, CW, SPEC, AC, PC, false>(a, sm, red, &tmap);
 }
 
 // =================================================================================================
@@ -1243,6 +1288,39 @@ int launch_rows_fwd(b4d_ctx* ctx, const RowsFwdArgs& a, int64_t T) {
     return B4D_OK;
 }
 
+// Tensor map of a (T, ny, nx) float32 map stack viewed as a 2-D tensor [T * ny rows][nx columns], boxes of 256 rows x cw
+// columns (cuTensorMapEncodeTiled, fetched from the driver through the runtime: no link against libcuda).
+bool psd_tma_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B4D_PSD_TMA"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    return on != 0;
+}
+
+bool make_psd_tmap(float* base, int64_t T, int ny, int nx, int cw, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode || (reinterpret_cast<uintptr_t>(base) & 15) || (nx % 4)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)T * (cuuint64_t)ny};
+    const cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)TMA_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NY, int CW, bool SPEC, bool AC, bool PC>
 int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     constexpr size_t smem = (size_t)padded_len(NY) * CW * sizeof(float2) +
@@ -1258,7 +1336,11 @@ int launch_cols_inst(b4d_ctx* ctx, const ColsArgs& a, int64_t T) {
     ColsArgs b = a;
     b.pf_dist = ctx->sm_count * (1024 / (NY / 16 * CW)) * pf_pct / 100;
     b.keep = ctx->keep_mode;
-    cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    b.psd_tma = 0;
+    if (CW == TC && NY >= TMA_BOX_ROWS && a.psd_out && psd_tma_enabled() && make_psd_tmap(a.psd_out, T, NY, a.nx, CW, &tmap)) b.psd_tma = 1;
+    cols_kernel<NY, CW, SPEC, AC, PC><<<dim3(a.nx / 2 / CW, (unsigned)T), NY / 16 * CW, smem, ctx->stream>>>(b, tmap);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
