@@ -369,6 +369,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e_b, e_s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("b4d_timed")   # (ncu --nvtx --nvtx-include "b4d_timed/" profiles the timed region only)
     e0.record()
     begin_stack()                       # inside the timed region: both broadcasts + the reference spectrum
     e_b.record()
@@ -378,6 +379,7 @@ def run_b200(args):
     end_stack(args.steps)               # inside the timed region: all-reduce of the temporal sums + finalize
     e1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     prof = ctx.profile_end()
     launches = ctx.launches - launches0
     clock_info = clocks.stop() if rank == 0 else None
