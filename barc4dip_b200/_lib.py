@@ -83,7 +83,7 @@ _SIGNATURES = {
     "b4d_stack_pipeline": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64, _f64, _f64,
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b4d_stack_pipeline_ref": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f32, _i32, _f64, _f64, _f64,
-                               _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b4d_frame_reductions_tails": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _f64, _f64, _vp, _vp, _vp],
 }
 _RESTYPES = {"b4d_profile_class_name": C.c_char_p, "b4d_last_error": C.c_char_p, "b4d_version": C.c_char_p, "b4d_launch_count": _i64}

@@ -29,7 +29,7 @@ extern "C" int b4d_destroy(b4d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     b4d_fft_release(ctx);
-    for (int i = 0; i < 10; ++i)
+    for (int i = 0; i < B4D_NSCRATCH; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (auto& sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);

@@ -29,6 +29,8 @@ struct ProfSpan {
 // cudaFuncSetAttribute is per device: the "already raised the shared-memory limit" flags of the launchers are too
 constexpr int B4D_MAX_DEVICES = 64;
 
+constexpr int B4D_NSCRATCH = 12;
+
 struct b4d_ctx {
     int device = 0;
     int sm_count = 148;
@@ -36,8 +38,8 @@ struct b4d_ctx {
     std::string last_error;
     int64_t launches = 0;
     // grow-only scratch arenas (device)
-    void* scratch[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    void* scratch[B4D_NSCRATCH] = {};
+    size_t scratch_bytes[B4D_NSCRATCH] = {};
     FftPlanCache* fft = nullptr;
     int64_t batch_override = 0;       // frames per internal batch of the FFT pipeline (0 = automatic)
     size_t batch_key[4] = {0, 0, 0, 0};   // automatic batch sizes already worked out: per-frame scratch bytes -> frames
@@ -105,7 +107,7 @@ struct ProfScope {
 };
 
 // scratch slot ids
-enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7, SCR_NYQ = 8, SCR_GEN = 9 };
+enum { SCR_REDUCE = 0, SCR_PILOT = 1, SCR_SELECT = 2, SCR_SPEC_A = 3, SCR_SPEC_B = 4, SCR_SPEC_C = 5, SCR_MISC = 6, SCR_MAP = 7, SCR_NYQ = 8, SCR_GEN = 9, SCR_F95 = 10 };
 
 inline int b4d_fail(b4d_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {

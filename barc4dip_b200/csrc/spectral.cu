@@ -1371,7 +1371,9 @@ int launch_cols(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
 template <int NY, int CW>
 int launch_cols_cw(b4d_ctx* ctx, ColsArgs& a, int64_t T) {
     const bool spec = a.spec_partials != nullptr, ac = a.i2_ac != nullptr, pc = a.i2_pc != nullptr;
-    if (spec && (ac || pc)) return b4d_fail(ctx, B4D_ERR_INVALID, "cols: spectral sums cannot be combined with inverse branches");
+    if (spec && pc && !ac) return b4d_fail(ctx, B4D_ERR_INVALID, "cols: spectral sums next to the product branch need the autocorrelation branch too");
+    if (spec && ac && pc) return launch_cols_inst<NY, CW, true, true, true>(ctx, a, T);
+    if (spec && ac) return launch_cols_inst<NY, CW, true, true, false>(ctx, a, T);
     if (spec) return launch_cols_inst<NY, CW, true, false, false>(ctx, a, T);
     if (ac && pc) return launch_cols_inst<NY, CW, false, true, true>(ctx, a, T);
     if (ac) return launch_cols_inst<NY, CW, false, true, false>(ctx, a, T);
@@ -1578,7 +1580,7 @@ int64_t batch_frames(b4d_ctx* ctx, int ny, int nx, int n_intermediates) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
     size_t held = 0;                                  // scratch already owned by this context counts as available
-    for (int i = 0; i < 10; ++i) held += ctx->scratch_bytes[i];
+    for (int i = 0; i < B4D_NSCRATCH; ++i) held += ctx->scratch_bytes[i];
     int64_t b = (int64_t)(((free_b + held) / 4) / (per ? per : 1));
     if (b < 1) b = 1;
     if (b > 128) b = 128;
@@ -1715,11 +1717,11 @@ GenCache*& gen_cache(b4d_ctx* ctx) {
 }
 
 // f95 of B4D_SP_*: two-level histogram over the integer radius keys of a shifted square PSD map (tab: (tc, B4D_SP_NCOLS))
-int run_f95(b4d_ctx* ctx, const float* map_b, int n, int64_t tc, double* tab) {
+int run_f95(b4d_ctx* ctx, const float* map_b, int n, int64_t tc, double* tab, int slot = SCR_SELECT) {
     const int nb0 = ((n / 2) * (n / 2) >> 10) + 1, nb1 = 1024;
     void* p = nullptr;
     const size_t hb = sizeof(double) * (size_t)tc * (nb0 > nb1 ? nb0 : nb1);
-    int rc = b4d_scratch(ctx, SCR_SELECT, hb + (sizeof(int) + sizeof(double)) * tc + 256, &p);
+    int rc = b4d_scratch(ctx, slot, hb + (sizeof(int) + sizeof(double)) * tc + 256, &p);
     if (rc) return rc;
     double* hist = static_cast<double*>(p);
     double* below = reinterpret_cast<double*>(static_cast<char*>(p) + hb);
@@ -2770,7 +2772,7 @@ bool lanes_ready(b4d_ctx* ctx, int lanes, int slots) {
 int pipeline_batch_lanes(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t tc, int ny, int nx, const float* gain,
                          const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
                          double q_lo, double q_hi, double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out,
-                         float* ac_out, double* grain_out, double* track_out, int ns) {
+                         float* ac_out, double* grain_out, double* track_out, int ns, double* spectral_out) {
     const bool want_ac = ac_out || grain_out, want_pc = track_out != nullptr;
     const size_t npix = (size_t)ny * nx, per = (size_t)ny * (nx / 2);
     const int64_t F = sc.sub;
@@ -2780,11 +2782,14 @@ int pipeline_batch_lanes(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t
     if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w, F * L, F * NB * L, F * NB * L))) return rc;
     void* p = nullptr;
     const size_t mag_floats = !want_pc ? 0 : ((fused_scratch_floats(ny, nx, ns, tc) + 63) & ~size_t(63));
-    const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) + sizeof(double) * B4D_FR_NCOLS * tc + 256;
+    const size_t ac_floats = (want_ac && !ac_out) ? npix * tc : 0;
+    const bool psd_scratch = spectral_out && ny == nx && !psd_out;     // f95 reads the PSD map
+    const size_t need = sizeof(float) * (mag_floats + ac_floats + (psd_scratch ? npix * tc : 0)) + sizeof(double) * B4D_FR_NCOLS * tc + 256;
     if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
     double* fr = static_cast<double*>(p);
     float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
     float* acm = ac_out ? ac_out : mag + mag_floats;
+    if (psd_scratch) psd_out = mag + mag_floats + ac_floats;
     double* frp = fr_out ? fr_out : fr;
     const bool reduced = fr_out || want_pc || quant_out;
     if (grain_out && (rc = ensure_theta(ctx))) return rc;
@@ -2844,6 +2849,7 @@ int pipeline_batch_lanes(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t
             float2* i2a = want_ac ? w.I2a + (size_t)(l * NB + slot) * F * per : nullptr;
             float2* i2b = want_pc ? w.I2b + (size_t)(l * NB + slot) * F * per : nullptr;
             if (want_ac) { c.i2_ac = i2a; c.i2_ac_nyq = w.I2nyq + (size_t)a * ny; c.ac_partials = w.acp + (size_t)a * ntl; }
+            if (spectral_out) c.spec_partials = w.spp + (size_t)a * ntl * NSP;
             if (want_pc) {
                 c.i2_pc = i2b;
                 c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
@@ -2895,6 +2901,11 @@ int pipeline_batch_lanes(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t
     if (rc) return rc;
     if (reduced && (rc = b4d_fr_end(ctx, pl))) return rc;
     if (want_pc && (rc = track_fused_end(ctx, w, tf, tc, ny, nx, subpixel, eps, track_out))) return rc;
+    if (spectral_out) {
+        spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx, psd_out != nullptr), spectral_out, tc);
+        B4D_LAUNCH_CHECK(ctx);
+        if (ny == nx && (rc = run_f95(ctx, psd_out, ny, tc, spectral_out, SCR_F95))) return rc;
+    }
     if (grain_out) {
         argmax_reduce_kernel<<<(unsigned)tc, 128, 0, ctx->stream>>>(w.bestA, nblk_ac, w.pk_idx2, w.pk_val2);
         B4D_LAUNCH_CHECK(ctx);
@@ -2912,7 +2923,7 @@ struct PipeKey {                      // everything the captured launches depend
     double d[6];
     float psd_scale;
     int i[8];
-    void* scratch[10];
+    void* scratch[B4D_NSCRATCH];
 };
 struct PipeGraph {
     PipeKey key;
@@ -2951,10 +2962,10 @@ void pipe_graphs_release(b4d_ctx* ctx) {
 int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, int64_t tc, int ny, int nx, const float* gain,
                                const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel, double eps,
                                double q_lo, double q_hi, double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out,
-                               float* ac_out, double* grain_out, double* track_out, int ns) {
+                               float* ac_out, double* grain_out, double* track_out, int ns, double* spectral_out) {
     auto direct = [&]() {
         return pipeline_batch_lanes(ctx, sc, s0, tc, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
-                                    fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out, ns);
+                                    fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out, ns, spectral_out);
     };
     if (!graphs_enabled(ctx)) return direct();
     if (!ctx->pipe_graphs) ctx->pipe_graphs = new PipeGraphCache();
@@ -2963,14 +2974,14 @@ int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, i
     memset(&key, 0, sizeof(key));
     const void* ptrs[] = {s0, gain, dark, fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out,
                           ctx->fft ? ctx->fft->ref : nullptr, ctx->fft ? ctx->fft->ref_nyq : nullptr,
-                          ctx->fft ? ctx->fft->blk_list : nullptr, ctx->fft ? ctx->fft->theta : nullptr};
+                          ctx->fft ? ctx->fft->blk_list : nullptr, ctx->fft ? ctx->fft->theta : nullptr, spectral_out};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
     key.tc = tc;
     key.d[0] = sat_value == sat_value ? sat_value : -1.2345e300; key.d[1] = zero_eps; key.d[2] = eps; key.d[3] = q_lo; key.d[4] = q_hi;
     key.psd_scale = psd_scale;
     key.i[0] = ny; key.i[1] = nx; key.i[2] = subpixel; key.i[3] = ns; key.i[4] = sc.sub; key.i[5] = sc.slots; key.i[6] = sc.keep; key.i[7] = sc.lanes;
     PipeGraph* ent = nullptr;
-    auto refresh_scratch = [&](PipeKey& k) { for (int i = 0; i < 10; ++i) k.scratch[i] = ctx->scratch[i]; };
+    auto refresh_scratch = [&](PipeKey& k) { for (int i = 0; i < B4D_NSCRATCH; ++i) k.scratch[i] = ctx->scratch[i]; };
     auto refresh_tables = [&](PipeKey& k) { k.p[12] = ctx->fft ? ctx->fft->blk_list : nullptr; k.p[13] = ctx->fft ? ctx->fft->theta : nullptr; };
     refresh_scratch(key);
     for (auto& e : cache->entries) if (memcmp(&e.key, &key, sizeof(key)) == 0) { ent = &e; break; }
@@ -3005,7 +3016,7 @@ int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, i
         ctx->stream = M;
         const cudaError_t ee = cudaStreamEndCapture(ctx->pipe, &graph);
         bool moved = false;
-        for (int i = 0; i < 10; ++i) moved = moved || key.scratch[i] != ctx->scratch[i];
+        for (int i = 0; i < B4D_NSCRATCH; ++i) moved = moved || key.scratch[i] != ctx->scratch[i];
         if (rc || ee != cudaSuccess || !graph || moved || cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);
@@ -3030,7 +3041,8 @@ int pipeline_batch_lanes_graph(b4d_ctx* ctx, const Sched& sc, const float* s0, i
 int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                         const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
                         double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
-                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out);
+                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out,
+                        double* spectral_out);
 
 extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                                   const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
@@ -3039,25 +3051,31 @@ extern "C" int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_fr
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
     return stack_pipeline_body(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
-                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out);
+                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out, nullptr);
 }
 
 extern "C" int b4d_stack_pipeline_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
                                       const float* gain, const float* dark, double sat_value, double zero_eps, float psd_scale,
                                       int subpixel, double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
-                                      int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
+                                      int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out,
+                                      double* spectral_out) {
     if (!ctx) return B4D_ERR_INVALID;
     B4dCall g(ctx);
     if (track_out && !ref) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline_ref: tracking needs a reference");
     RefSwap sw(ctx, ref);
     return stack_pipeline_body(ctx, stack, n_frames, ny, nx, gain, dark, sat_value, zero_eps, psd_scale, subpixel, eps, q_lo, q_hi,
-                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out);
+                               fr_out, quant_out, nvalid_out, psd_out, ac_out, grain_out, track_out, spectral_out);
 }
 
 int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, const float* gain,
                         const float* dark, double sat_value, double zero_eps, float psd_scale, int subpixel,
                         double eps, double q_lo, double q_hi, double* fr_out, float* quant_out,
-                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out) {
+                        int64_t* nvalid_out, float* psd_out, float* ac_out, double* grain_out, double* track_out,
+                        double* spectral_out) {
+    if (spectral_out && !(ac_out || grain_out))
+        return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: the spectral sums ride on the autocorrelation branch (ask for ac_out or grain_out)");
+    if (spectral_out && !pow2_sides(ny, nx))
+        return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_stack_pipeline: spectral sums in the fused pass need power-of-two sides (use b4d_psd2d)");
     if (dark && !gain) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: dark given without gain");
     if (grain_out && ny != nx) return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_stack_pipeline: grain widths need square frames");
     if (quant_out && (!nvalid_out || !(q_lo >= 0.0 && q_lo < q_hi && q_hi <= 1.0)))
@@ -3088,21 +3106,25 @@ int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int 
                                       fr_out ? fr_out + t0 * B4D_FR_NCOLS : nullptr, quant_out ? quant_out + 4 * t0 : nullptr,
                                       quant_out ? nvalid_out + t0 : nullptr, psd_out ? psd_out + (size_t)t0 * npix : nullptr,
                                       ac_out ? ac_out + (size_t)t0 * npix : nullptr, grain_out ? grain_out + t0 * 4 : nullptr,
-                                      track_out ? track_out + t0 * 4 : nullptr, ns);
+                                      track_out ? track_out + t0 * 4 : nullptr, ns,
+                                      spectral_out ? spectral_out + t0 * B4D_SP_NCOLS : nullptr);
             if (rc) return rc;
             continue;
         }
         Work w;
         if ((rc = carve(ctx, tc, ny, nx, want_ac, want_pc, &w))) return rc;
-        // scratch maps: |corr| always, autocorr when the caller does not keep it
+        // scratch maps: |corr| always, autocorr when the caller does not keep it, PSD when only f95 reads it
         void* p = nullptr;
         const size_t mag_floats = !want_pc ? 0 : (ns ? ((fused_scratch_floats(ny, nx, ns, tc) + 63) & ~size_t(63)) : npix * tc);
-        const size_t need = sizeof(float) * (mag_floats + ((want_ac && !ac_out) ? npix * tc : 0)) +
+        const size_t ac_floats = (want_ac && !ac_out) ? npix * tc : 0;
+        const bool psd_scratch = spectral_out && ny == nx && !psd_out;
+        const size_t need = sizeof(float) * (mag_floats + ac_floats + (psd_scratch ? npix * tc : 0)) +
                             sizeof(double) * B4D_FR_NCOLS * tc + 256;
         if ((rc = b4d_scratch(ctx, SCR_MAP, need, &p))) return rc;
         double* fr = static_cast<double*>(p);
         float* mag = reinterpret_cast<float*>(fr + (size_t)B4D_FR_NCOLS * tc);
         float* acm = ac_out ? ac_out + (size_t)t0 * npix : mag + mag_floats;
+        float* psd_b = psd_out ? psd_out + (size_t)t0 * npix : (psd_scratch ? mag + mag_floats + ac_floats : nullptr);
         double* frp = fr_out ? fr_out + t0 * B4D_FR_NCOLS : fr;
         const bool reduced = fr_out || want_pc || quant_out;
         // The reduction pass and the forward row pass both stream the frames. They alternate `pair` frames at a time, so
@@ -3136,9 +3158,10 @@ int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int 
         } else if (need_fft && (rc = run_rows_fwd(ctx, s0, tc, ny, nx, gain, dark, w, true, false))) return rc;
         if (!need_fft) continue;
         ColsArgs c = cols_defaults(w, nx, true);
-        c.psd_out = psd_out ? psd_out + (size_t)t0 * npix : nullptr;
+        c.psd_out = psd_b;
         c.psd_scale = psd_scale;
         if (want_ac) { c.i2_ac = w.I2a; c.i2_ac_nyq = w.I2nyq; c.ac_partials = w.acp; }
+        if (spectral_out) c.spec_partials = w.spp;   // bandwidth / spectral-entropy sums from the same forward transform
         if (want_pc) {
             c.i2_pc = w.I2b;
             c.R = ctx->fft->ref; c.Rnyq = ctx->fft->ref_nyq; c.r_stride = 0; c.rnyq_stride = 0;
@@ -3206,6 +3229,12 @@ int stack_pipeline_body(b4d_ctx* ctx, const float* stack, int64_t n_frames, int 
             if (!rc && je != cudaSuccess) rc = b4d_fail(ctx, B4D_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(je));
         }
         if (rc) return rc;
+        if (spectral_out) {
+            double* tab = spectral_out + t0 * B4D_SP_NCOLS;
+            spec_finalize_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, ctx->stream>>>(w.spp, cols_tiles(ny, nx, cols_wide_out(c)), tab, tc);
+            B4D_LAUNCH_CHECK(ctx);
+            if (ny == nx && (rc = run_f95(ctx, psd_b, ny, tc, tab, SCR_F95))) return rc;
+        }
     }
     return B4D_OK;
 }

@@ -417,7 +417,7 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
                    psd_scale: float | None = None, subpixel: bool = True, track_eps: float = 1e-9,
                    want_reductions: bool = True, want_psd: bool = True, want_autocorr: bool = True,
                    want_grain: bool = True, want_tracking: bool = True, psd_out=None, ac_out=None,
-                   tail_quantiles=None, tracker: "PhaseTracker | None" = None):
+                   tail_quantiles=None, tracker: "PhaseTracker | None" = None, want_spectral: bool = False):
     """The fused north-star pass over an HBM-resident stack (see b4d_stack_pipeline_ref in include/b4d.h).
 
     Tracking runs against `tracker` (its own reference spectrum); without one, against the PhaseTracker most recently
@@ -425,6 +425,8 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
     tail_quantiles=(q_lo, q_hi) (fractions) adds the order statistics bracketing the two percentiles, collected in
     the reduction pass: "quantiles" (T, 4) float32 and "n_valid" (T,) int64 (-1 = unresolved frame, see
     resolve_tail_quantiles).
+    want_spectral=True adds "spectral" (T, SP_NCOLS): the sums behind bandwidth() / spectral_entropy(), taken in the column
+    pass of the same forward transform (power-of-two sides, needs the autocorrelation branch; f95 on square frames).
     Returns a dict with device tensors: reductions (T, FR_NCOLS), psd, autocorr, grain (T,4), tracking (T,4).
     """
     torch = require_cuda()
@@ -454,14 +456,15 @@ def stack_pipeline(stack, *, gain=None, dark=None, saturation_value: float | Non
         q_lo, q_hi = float(tail_quantiles[0]), float(tail_quantiles[1])
         quant = torch.empty((T, 4), dtype=torch.float32, device=dev)
         nvalid = torch.empty((T,), dtype=torch.int64, device=dev)
+    spectral = torch.full((T, SP_NCOLS), float("nan"), dtype=torch.float64, device=dev) if want_spectral else None
     ctx.check(ctx.lib.b4d_stack_pipeline_ref(ctx.handle, tracker.handle if want_tracking else None, ptr(stack), T, ny, nx,
                                              ptr(gain), ptr(dark), sat, float(eps), scale, int(bool(subpixel)),
                                              float(tracker.eps if want_tracking else track_eps), q_lo, q_hi, ptr(fr),
                                              ptr(quant), ptr(nvalid), ptr(psd_out if want_psd else None),
-                                             ptr(ac_out if want_autocorr else None), ptr(grain), ptr(track)),
+                                             ptr(ac_out if want_autocorr else None), ptr(grain), ptr(track), ptr(spectral)),
               "b4d_stack_pipeline_ref")
     return {"reductions": fr, "psd": psd_out if want_psd else None, "autocorr": ac_out if want_autocorr else None,
-            "grain": grain, "tracking": track, "quantiles": quant, "n_valid": nvalid}
+            "grain": grain, "tracking": track, "quantiles": quant, "n_valid": nvalid, "spectral": spectral}
 
 
 def frame_reductions_tails(stack, q_lo: float, q_hi: float, *, gain=None, dark=None,

@@ -122,6 +122,24 @@ def _full_blocks(dev_stack, groups, saturation_value, eps) -> dict:
     """Requested groups for an HBM-resident stack -> {group: {metric: (T,) array}}."""
     out: dict = {}
     table = None
+    if blocks.fused_available(dev_stack) and (groups & {"spectral", "autocorrelation"}):
+        # one fused pass: a single forward FFT per frame feeds the spectral entropy and the autocorrelation widths
+        fb = blocks.FusedBlocks(dev_stack, saturation_value=saturation_value, eps=eps, want_tails=False,
+                                want_spectral="spectral" in groups)
+        table = fb.table
+        if "stats" in groups:
+            out["stats"] = blocks.moments_block(table, saturation_value)
+        if "gradient" in groups:
+            out["gradient"] = blocks.gradient_block(table)
+        if "laplacian" in groups:
+            out["laplacian"] = blocks.laplacian_block(table)
+        if "spectral" in groups:
+            out["spectral"] = fb.entropy()
+        if "autocorrelation" in groups:
+            out["autocorrelation"] = fb.inverse_autocorr()
+        if "eigenvalues" in groups:
+            out["eigenvalues"] = blocks.eigenvalues_block(dev_stack)
+        return out
     if groups & {"stats", "gradient", "laplacian", "autocorrelation"}:
         table = engine.frame_reductions(dev_stack, saturation_value=saturation_value, eps=eps)
     if "stats" in groups:

@@ -83,12 +83,29 @@ def bandwidth(image, verbose: bool = False) -> dict:
 
 def _full_blocks(dev_stack, groups, saturation_value, eps, keep_maps: bool):
     out: dict = {}
+    if "grain" in groups and min(dev_stack.shape[1:]) < 128:
+        raise ValueError("image too small for speckle grain metrics (min dimension < 128).")
+    if blocks.fused_available(dev_stack) and (groups & {"grain", "bandwidth"}):
+        # one fused pass: a single forward FFT per frame feeds grain (autocorrelation) and bandwidth (spectral sums)
+        fb = blocks.FusedBlocks(dev_stack, saturation_value=saturation_value, eps=eps, keep_map=keep_maps and "grain" in groups,
+                                want_tails="amplitude" in groups, want_spectral="bandwidth" in groups)
+        if "amplitude" in groups:
+            out["amplitude"] = fb.amplitude()
+        if "grain" in groups:
+            g = fb.grain()
+            if keep_maps:
+                n = int(fb.ac.shape[-1])
+                g["autocorr"], g["xlag"], g["ylag"] = fb.ac, lag_axis(n, 1.0), lag_axis(n, 1.0)
+            out["grain"] = g
+        if "stats" in groups:
+            out["stats"] = fb.moments()
+        if "bandwidth" in groups:
+            out["bandwidth"] = fb.bandwidth()
+        return out
     table = engine.frame_reductions(dev_stack, saturation_value=saturation_value, eps=eps)
     if "amplitude" in groups:
         out["amplitude"] = blocks.amplitude_block(dev_stack, table)
     if "grain" in groups:
-        if min(dev_stack.shape[1:]) < 128:
-            raise ValueError("image too small for speckle grain metrics (min dimension < 128).")
         if keep_maps:
             g, ac = blocks.grain_block(dev_stack, table=table, return_map=True)
             n = int(ac.shape[-1])

@@ -114,6 +114,11 @@ def bandwidth_block(stack, *, table=None) -> dict:
     n = sq.shape[-1]
     _, sp = engine.psd2d(sq, scale_factor=1.0 / (float(n) * float(n)), sub_mean=True, zero_dc=True,
                          want_map=False, want_spectral=True)
+    return bandwidth_from_sums(sp)
+
+
+def bandwidth_from_sums(sp: np.ndarray) -> dict:
+    """bandwidth() metrics (metrics/speckles.py:771-805) from a spectral table (T, SP_NCOLS); invariant to the PSD's scale."""
     total = sp[:, SP["total"]]
     if np.any(~np.isfinite(total)) or np.any(total <= 0.0):
         raise ValueError("PSD energy is not positive/finite after mean/DC removal.")
@@ -127,6 +132,11 @@ def bandwidth_block(stack, *, table=None) -> dict:
 def spectral_entropy_block(stack) -> dict:
     T, ny, nx = stack.shape
     _, sp = engine.psd2d(stack, scale_factor=1.0, sub_mean=True, zero_dc=True, want_map=False, want_spectral=True)
+    return entropy_from_sums(sp, ny, nx)
+
+
+def entropy_from_sums(sp: np.ndarray, ny: int, nx: int) -> dict:
+    """spectral_entropy() (metrics/sharpness.py:611-621) from a spectral table; invariant to the PSD's scale."""
     s = sp[:, SP["all"]]
     if np.any(~np.isfinite(s)) or np.any(s <= 0.0):
         raise ValueError("PSD sum is non-positive; cannot compute spectral entropy.")
@@ -138,11 +148,79 @@ def spectral_entropy_block(stack) -> dict:
 
 
 def inverse_autocorr_block(stack, *, fraction: float = INV_E, table=None) -> dict:
-    g = grain_block(stack, fraction=fraction, standardize=True, table=table)
+    return inverse_from_grain(grain_block(stack, fraction=fraction, standardize=True, table=table))
+
+
+def inverse_from_grain(g: dict) -> dict:
     with np.errstate(divide="ignore"):
         inv = lambda v: np.where(v != 0.0, 1.0 / v, np.inf)
         return {"sx": inv(g["lx"]), "sy": inv(g["ly"]), "seq": inv(g["leq"]),
                 "r": np.where(g["ly"] != 0.0, g["lx"] / g["ly"], np.inf)}
+
+
+def fused_available(stack) -> bool:
+    """Square frames with a power-of-two side in [128, 2048]: the fused pass serves every FFT-based block at once."""
+    ny, nx = int(stack.shape[-2]), int(stack.shape[-1])
+    return ny == nx and 128 <= ny <= 2048 and (ny & (ny - 1)) == 0
+
+
+class FusedBlocks:
+    """One fused pass over an HBM-resident stack (b4d_stack_pipeline_ref without the tracker): frame reductions, tail
+    order statistics, autocorrelation with grain widths and the spectral sums of bandwidth() / spectral_entropy() all
+    come from ONE streaming read and ONE forward 2-D FFT per frame, where composing the per-metric blocks above runs a
+    forward transform per FFT-based metric (the reference's aggregators call the metric functions one after the other,
+    metrics/speckles.py:168-190, metrics/sharpness.py:183-211). The per-group dicts have the blocks' formats."""
+
+    Q = (0.05 / 100.0, 99.95 / 100.0)
+
+    def __init__(self, stack, *, saturation_value, eps: float, keep_map: bool = False, want_tails: bool = True,
+                 want_spectral: bool = True):
+        res = engine.stack_pipeline(stack, saturation_value=saturation_value, eps=eps, want_psd=False, want_autocorr=keep_map,
+                                    want_grain=True, want_tracking=False, want_spectral=want_spectral,
+                                    tail_quantiles=self.Q if want_tails else None)
+        self.stack, self.sat = stack, saturation_value
+        self.table = res["reductions"].cpu().numpy()
+        self.ac = res["autocorr"]
+        g = res["grain"].cpu().numpy()
+        self._grain = {"lx": g[:, 0], "ly": g[:, 1], "leq": g[:, 2], "r": g[:, 3]}
+        self._sp = res["spectral"].cpu().numpy() if want_spectral else None
+        self._quant, self._nv = res["quantiles"], res["n_valid"]
+
+    def moments(self) -> dict:
+        return moments_block(self.table, self.sat)
+
+    def amplitude(self) -> dict:
+        table = self.table
+        n = table[:, FR["count"]]
+        n_inf = table[:, FR["npix"]] - n - table[:, FR["nnan"]]
+        mu = np.where(n_inf > 0, np.nan, table[:, FR["mean"]])
+        if np.any(~np.isfinite(mu)) or np.any(mu <= 0.0) or np.any(n <= 0):
+            raise ValueError("Mean intensity must be positive and finite.")
+        vis = np.sqrt(table[:, FR["m2"]]) / mu
+        # frames the fused tail collection did not resolve (n_valid == -1) are redone by the exact stand-alone select
+        engine.resolve_tail_quantiles(self.stack, self._quant, self._nv, *self.Q)
+        q, nv = self._quant.cpu().numpy(), self._nv.cpu().numpy()
+        contrast = np.empty(q.shape[0])
+        for t in range(q.shape[0]):
+            vmin = engine.quantile_from_bracket(q[t, 0], q[t, 1], int(nv[t]), self.Q[0])
+            vmax = engine.quantile_from_bracket(q[t, 2], q[t, 3], int(nv[t]), self.Q[1])
+            den = vmax + vmin
+            if not np.isfinite(den) or den <= 0.0:
+                raise ValueError("Invalid percentile range for Michelson contrast.")
+            contrast[t] = (vmax - vmin) / den
+        return {"visibility": vis, "contrast": contrast}
+
+    def grain(self) -> dict:
+        return dict(self._grain)
+
+    def bandwidth(self) -> dict:
+        return bandwidth_from_sums(self._sp)
+
+    def entropy(self) -> dict:
+        return entropy_from_sums(self._sp, int(self.stack.shape[-2]), int(self.stack.shape[-1]))
+
+    def inverse_autocorr(self) -> dict:
+        return inverse_from_grain(self._grain)
 
 
 def eigenvalues_block(stack, *, k: int = 5, eps: float = 1e-30) -> dict:

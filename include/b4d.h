@@ -311,12 +311,20 @@ int b4d_stack_pipeline(b4d_ctx* ctx, const float* stack, int64_t n_frames, int n
                        double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out,
                        double* grain_out, double* track_out);
 
-/* b4d_stack_pipeline against an owned reference (nullable when track_out is null). */
+/*
+ * b4d_stack_pipeline against an owned reference (nullable when track_out is null), plus
+ *   spectral_out (n_frames, B4D_SP_NCOLS)  the spectral sums of bandwidth() / spectral_entropy() (metrics/speckles.py:740-796,
+ *                                       metrics/sharpness.py:581-629) taken in the column pass of the SAME forward transform
+ *                                       that feeds the PSD map, the autocorrelation and the tracker (nullable; needs
+ *                                       ac_out or grain_out and power-of-two sides; f95 on square frames only).  The
+ *                                       sums are of P * psd_scale with the DC bin left out; every metric derived from
+ *                                       them is invariant to that scale.
+ */
 int b4d_stack_pipeline_ref(b4d_ctx* ctx, const b4d_ref* ref, const float* stack, int64_t n_frames, int ny, int nx,
                            const float* gain, const float* dark, double sat_value, double zero_eps,
                            float psd_scale, int subpixel, double eps, double q_lo, double q_hi,
                            double* fr_out, float* quant_out, int64_t* nvalid_out, float* psd_out, float* ac_out,
-                           double* grain_out, double* track_out);
+                           double* grain_out, double* track_out, double* spectral_out);
 
 #ifdef __cplusplus
 }

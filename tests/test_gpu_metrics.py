@@ -390,3 +390,30 @@ def test_eigenvalues_metric_vs_golden(dip, golden, name):
             np.testing.assert_allclose(res["tiles"]["eigenvalues"][f]["std"], g[f"sq512/tiles/{f}/std"], rtol=RTOL, atol=1e-12)
         st = dip.metrics.sharpness_stack_stats(np.stack([img, img[::-1]]), metrics="eigenvalues", tiles=False, verbose=False)
         np.testing.assert_allclose(st["full"]["eigenvalues"]["e1"], [g["sq512/full"][1]] * 2, rtol=RTOL)
+
+
+def test_fused_blocks_equal_composed_blocks_and_use_one_forward_fft(dip):
+    """speckle_stats / sharpness_stats on square power-of-two frames take every FFT-based group from ONE fused pass
+    (b4d_stack_pipeline_ref with spectral sums): same numbers as the per-metric blocks, one forward transform per frame
+    in the launch list (reference: metrics/speckles.py:740-796, metrics/sharpness.py:581-629)."""
+    from barc4dip_b200 import engine, stack as blocks, synth
+    from barc4dip_b200._lib import get_context
+    frames = np.stack([synth.speckle_frame(512, grain=5.0, seed=s) for s in (81, 82, 83)])
+    d = engine.as_stack(frames)
+    fb = blocks.FusedBlocks(d, saturation_value=65535.0, eps=1e-6, keep_map=True)
+    table = engine.frame_reductions(d, saturation_value=65535.0, eps=1e-6)
+    np.testing.assert_array_equal(fb.table, table)
+    for got, want in ((fb.amplitude(), blocks.amplitude_block(d, table)), (fb.grain(), blocks.grain_block(d, table=table)),
+                      (fb.bandwidth(), blocks.bandwidth_block(d, table=table)), (fb.entropy(), blocks.spectral_entropy_block(d)),
+                      (fb.inverse_autocorr(), blocks.inverse_autocorr_block(d, table=table))):
+        assert set(got) == set(want)
+        for k in want:
+            np.testing.assert_allclose(got[k], want[k], rtol=2e-5, err_msg=k)
+    # launch list: one forward row pass per call, whatever the number of FFT-based groups
+    ctx = get_context()
+    for fn, kw in ((dip.metrics.speckle_stats, {}), (dip.metrics.sharpness_stats, {"metrics": ("stats", "gradient", "laplacian", "spectral", "autocorrelation")})):
+        fn(frames[0], tiles=False, verbose=False, **kw)            # warm (tables, scratch)
+        ctx.profile_begin()
+        fn(frames[0], tiles=False, verbose=False, **kw)
+        prof = ctx.profile_end()
+        assert prof["rows_fwd"][1] == 1, prof
