@@ -164,10 +164,11 @@ def sharpness_stats(image, *, metrics="all", tiles: bool = True, display_origin:
         raise TypeError("sharpness_stats expects a numpy.ndarray")
     if image.ndim != 2:
         raise ValueError(f"Expected 2D array, got ndim={image.ndim}")
-    image = apply_display_origin(image, display_origin=display_origin)
     h, w = image.shape
     groups = _resolve_groups(metrics)
     dev = engine.as_stack(np.ascontiguousarray(image))
+    if normalize_display_origin(display_origin) == "lower":      # (common.py:70-71; flipped on the device)
+        dev = dev.flip(1).contiguous()
     full = _full_blocks(dev, groups, saturation_value, eps)
     out = {"meta": {"kind": "sharpness", "display_origin": display_origin, "input_shape": (int(h), int(w)),
                     "requested_groups": sorted(groups), "units": _SHARPNESS_UNITS, "tile_mode": "off"},

@@ -128,10 +128,13 @@ def speckle_stats(image, *, metrics="all", tiles: bool = True, display_origin: s
         raise TypeError("speckle_stats expects a numpy.ndarray")
     if image.ndim != 2:
         raise ValueError(f"Expected 2D array, got ndim={image.ndim}")
-    image = apply_display_origin(image, display_origin=display_origin)
     h, w = image.shape
     groups = normalize_groups(metrics, all_groups=_ALL_SPECKLE_GROUPS, context="speckles", param_name="metrics")
+    # display_origin="lower" analyses the row-flipped frame (common.py:70-71): flipped on the device (a 17 MB host copy of a
+    # 2048^2 frame costs more than every kernel of this call together)
     dev = engine.as_stack(np.ascontiguousarray(image))
+    if normalize_display_origin(display_origin) == "lower":
+        dev = dev.flip(1).contiguous()
     full = _full_blocks(dev, groups, saturation_value, eps, keep_maps=True)
     out = {"meta": {"kind": "speckles", "display_origin": display_origin, "input_shape": (int(h), int(w)),
                     "requested_groups": sorted(groups), "units": _SPECKLE_UNITS, "tile_mode": "off"}, "full": {}}
@@ -141,7 +144,7 @@ def speckle_stats(image, *, metrics="all", tiles: bool = True, display_origin: s
         blk = {}
         for k, v in full[grp].items():
             if k == "autocorr":
-                blk[k] = v[0].cpu().numpy().astype(np.float64)
+                blk[k] = _map_to_host_f64(v[:1])[0]
             elif k in ("xlag", "ylag"):
                 blk[k] = v
             else:
@@ -163,6 +166,18 @@ def _tiles(dev_oriented, mode, groups, saturation_value, eps) -> dict:
     res = tiled_blocks(dev_oriented, tile_mode=mode,
                        block_fn=lambda tl: _full_blocks(tl, groups, saturation_value, eps, keep_maps=False))
     return {g: res[g] for g in ("amplitude", "grain", "stats", "bandwidth") if g in res}
+
+
+def _map_to_host_f64(maps, chunk: int = 8) -> np.ndarray:
+    """(T, N, N) float32 device maps -> float64 numpy (the reference returns float64 autocorrelation maps): widened on the
+    device a few frames at a time and copied straight into the result array (no float32 host copy, no host-side cast)."""
+    import torch
+    T = int(maps.shape[0])
+    out = np.empty(tuple(maps.shape), dtype=np.float64)
+    dst = torch.from_numpy(out)
+    for a in range(0, T, chunk):
+        dst[a:a + chunk].copy_(maps[a:a + chunk].double())
+    return out
 
 
 def _empty_like_block(block):
@@ -243,7 +258,7 @@ def speckle_stack_stats(stack, *, metrics="all", tiles: bool = True, display_ori
     else:
         full = {k: _empty_like_block(v) for k, v in _full_blocks(dev0, groups, saturation_value, eps, keep_maps=keep_autocorr).items()}
     if "grain" in full and keep_autocorr:
-        full["grain"]["autocorr"] = full["grain"]["autocorr"].cpu().numpy().astype(np.float64)
+        full["grain"]["autocorr"] = _map_to_host_f64(full["grain"]["autocorr"])
         n = full["grain"]["autocorr"].shape[-1]
         full["grain"]["xlag"] = np.tile(full["grain"]["xlag"], (Tl, 1))
         full["grain"]["ylag"] = np.tile(full["grain"]["ylag"], (Tl, 1))
