@@ -4,7 +4,7 @@
 //
 //   X[k] = w[k] * sum_n (x[n] w[n]) conj(w[k - n]),   w[n] = exp(-i pi n^2 / N)
 //
-// is a linear convolution, evaluated as a circular one of length M >= 2N - 1 (M = 512 ... 4096):
+// is a linear convolution, evaluated as a circular one of length M >= 2N - 1 (M = 512 ... 8192):
 // FFT_M(x w) * B, inverse FFT_M, times w[k] / M, with B = FFT_M of the wrapped conj chirp (host, double precision,
 // cached per N). One kernel performs the whole 1-D transform of a row: M/16 threads, two in-register FFTs, nothing
 // but the row itself crosses HBM. A 2-D transform is rows, transpose, rows; inverse transforms conjugate on the way
@@ -22,8 +22,9 @@ struct GenCache {
     std::vector<GenPlan> plans;
 };
 
-inline bool gen_size_ok(int n) { return n >= 1 && n <= 2048; }   // 1: the 1-D signals of signal/fft.py, corr.py as (1, n) frames
-inline int gen_conv_len(int n) { return n <= 256 ? 512 : (n <= 512 ? 1024 : (n <= 1024 ? 2048 : 4096)); }
+constexpr int GEN_MAX = 4096;   // largest side: detector frames such as 2560 x 2160 (the reference is size-agnostic, signal/fft.py:236)
+inline bool gen_size_ok(int n) { return n >= 1 && n <= GEN_MAX; }   // 1: the 1-D signals of signal/fft.py, corr.py as (1, n) frames
+inline int gen_conv_len(int n) { return n <= 256 ? 512 : (n <= 512 ? 1024 : (n <= 1024 ? 2048 : (n <= 2048 ? 4096 : 8192))); }
 
 // iterative radix-2 FFT in double precision (host; tables only)
 inline void host_fft(std::vector<double>& re, std::vector<double>& im) {
@@ -129,6 +130,80 @@ __global__ void __launch_bounds__(512) bluestein_rows_kernel(BluArgs a) {
     for (int s = 0; s < 16; ++s) {
         const int idx = j + s * T;
         if (idx < n && valid) {
+            float2 v = cmul(x[s], __ldg(a.w + idx));
+            v.x *= inv_m; v.y *= inv_m;
+            if (a.inverse) v.y = -v.y;
+            a.out[row * n + idx] = v;
+        }
+    }
+}
+
+// Sides in (2048, 4096]: M = 8192, one radix-2 step around the 4096-point register core (which tops out at three radix-16
+// stages). One row per CTA; threads 0..255 carry the even samples, 256..511 the odd ones:
+//   forward (decimation in time):      U[k] = E[k] + W^k O[k],  U[k + 4096] = E[k] - W^k O[k],   W = exp(-2 pi i / 8192)
+//   inverse (decimation in frequency): y[2m] = IFFT_4096(Y[k] + Y[k + 4096]),  y[2m + 1] = IFFT_4096((Y[k] - Y[k + 4096]) conj(W^k))
+// The 4096-point transform leaves element k = j + 256 s in slot s of thread j of EITHER half, so both halves hold the
+// same k and swap their 16 values through shared memory.
+__global__ void __launch_bounds__(512) bluestein_rows_8192_kernel(BluArgs a) {
+    constexpr int H = 4096, T = H / 16, FS = padded_len(H) + 8;
+    extern __shared__ float2 sm[];
+    float2* X = sm + 2 * FS;                           // [2][H] exchange of the two halves
+    const int tid = threadIdx.x, f = tid / T, j = tid % T;
+    const int64_t row = blockIdx.x;
+    const int n = a.n;
+    float mean = 0.f;
+    if (a.in_real && a.fr) mean = (float)a.fr[(row / a.rows_per_frame) * B4D_FR_NCOLS + B4D_FR_MEAN];
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int idx = 2 * (j + m * T) + f;           // sample index inside the zero-padded 8192 sequence
+        float2 v = make_float2(0.f, 0.f);
+        if (idx < n) {
+            if (a.in_real) v.x = a.in_real[row * n + idx] - mean;
+            else v = a.in[row * n + idx];
+            if (a.inverse) v.y = -v.y;
+            v = cmul(v, __ldg(a.w + idx));
+        }
+        x[m] = v;
+    }
+    float2* z = sm + f * FS;
+    fft_regs<H, -1, 1, 1>(x, j, z, a.tw, f);
+    // W^k of this thread's sixteen k (both halves hold the same k)
+    float2 wk[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        float sn, cs;
+        sincospif((float)(j + s * T) * (1.f / 4096.f), &sn, &cs);
+        wk[s] = make_float2(cs, -sn);
+    }
+    // forward combine, times the chirp spectrum B
+#pragma unroll
+    for (int s = 0; s < 16; ++s) X[f * H + j + s * T] = f ? cmul(x[s], wk[s]) : x[s];
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int k = j + s * T;
+        const float2 e = X[k], o = X[H + k];
+        const float2 u = f ? csub(e, o) : cadd(e, o);
+        x[s] = cmul(u, __ldg(a.B + f * H + k));
+    }
+    __syncthreads();
+    // inverse split
+#pragma unroll
+    for (int s = 0; s < 16; ++s) X[f * H + j + s * T] = x[s];
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int k = j + s * T;
+        const float2 lo = X[k], hi = X[H + k];
+        x[s] = f ? cmul(csub(lo, hi), cconj(wk[s])) : cadd(lo, hi);
+    }
+    fft_regs<H, +1, 1, 1>(x, j, z, a.tw, f);
+    const float inv_m = 1.f / 8192.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int idx = 2 * (j + s * T) + f;
+        if (idx < n) {
             float2 v = cmul(x[s], __ldg(a.w + idx));
             v.x *= inv_m; v.y *= inv_m;
             if (a.inverse) v.y = -v.y;
@@ -366,12 +441,24 @@ int launch_bluestein(b4d_ctx* ctx, const BluArgs& a) {
     return B4D_OK;
 }
 
+int launch_bluestein_8192(b4d_ctx* ctx, const BluArgs& a) {
+    constexpr size_t smem = ((size_t)2 * (padded_len(4096) + 8) + 2 * 4096) * sizeof(float2);
+    static bool attr[B4D_MAX_DEVICES] = {};
+    if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(bluestein_rows_8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
+    if (a.rows > 0x7fffffffLL) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "generic DFT: too many rows");
+    ProfScope ps(ctx, KC_GENERIC);
+    bluestein_rows_8192_kernel<<<(unsigned)a.rows, 512, smem, ctx->stream>>>(a);
+    B4D_LAUNCH_CHECK(ctx);
+    return B4D_OK;
+}
+
 int gen_rows(b4d_ctx* ctx, GenCache*& cache, BluArgs a) {
     const GenPlan* p = nullptr;
     int rc = gen_plan(ctx, cache, a.n, &p);
     if (rc) return rc;
     a.w = p->w; a.B = p->B;
-    if ((rc = get_twiddle_bases(ctx, p->M, &a.tw))) return rc;
+    if ((rc = get_twiddle_bases(ctx, p->M > 4096 ? 4096 : p->M, &a.tw))) return rc;
+    if (p->M == 8192) return launch_bluestein_8192(ctx, a);
     switch (p->M) {
         case 512: return launch_bluestein<512>(ctx, a);
         case 1024: return launch_bluestein<1024>(ctx, a);

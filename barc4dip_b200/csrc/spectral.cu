@@ -1745,7 +1745,7 @@ int check_gen_args(b4d_ctx* ctx, const char* who, const void* stack, int64_t T, 
     if (!stack || T < 1) return b4d_fail(ctx, B4D_ERR_INVALID, "%s: bad arguments", who);
     if (!gen_size_ok(ny) || !gen_size_ok(nx) || T > ((int64_t)1 << 24))
         return b4d_fail(ctx, B4D_ERR_UNSUPPORTED,
-                        "%s: frames need sides in [1, 2048]; got T=%lld (ny, nx)=(%d, %d)",
+                        "%s: frames need sides in [1, 4096]; got T=%lld (ny, nx)=(%d, %d)",
                         who, (long long)T, ny, nx);
     return B4D_OK;
 }
@@ -2012,7 +2012,7 @@ int gen_xcorr2d(b4d_ctx* ctx, const float* a, const float* b, int64_t n_frames, 
     return B4D_OK;
 }
 
-// ifft2d (signal/fft.py:240-258): ifft2(ifftshift(F)), complex in, complex out, any sides in [2, 2048]
+// ifft2d (signal/fft.py:240-258): ifft2(ifftshift(F)), complex in, complex out, any sides in [2, 4096]
 int gen_ifft2d(b4d_ctx* ctx, const float2* spec, int64_t n_frames, int ny, int nx, float2* out) {
     const int64_t B = gen_batch(ny, nx);
     const size_t npix = (size_t)ny * nx;

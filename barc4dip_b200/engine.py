@@ -38,15 +38,18 @@ def _dev(t) -> int:
     return t.device.index if t.device.index is not None else 0
 
 
+DFT_MAX = 4096      # B4D_DFT_MAX: largest side of the chirp-z path
+
+
 def check_fft_shape(ny: int, nx: int, generic_ok: bool = False):
-    """Power-of-two sides in [128, 2048] run the hot-path kernels. fft2d / psd2d / autocorr2d (generic_ok) also take any
-    sides in [1, 2048] through the Bluestein path (csrc/generic_dft.cuh); tracking and the fused pipeline do not."""
+    """Power-of-two sides in [128, 2048] run the hot-path kernels. Entry points with generic_ok also take any sides in
+    [1, 4096] through the Bluestein path (csrc/generic_dft.cuh): tiles, odd detector formats, frames wider than 2048."""
     pow2 = all(128 <= n <= _lib.FFT_MAX and (n & (n - 1)) == 0 for n in (ny, nx))
-    if pow2 or (generic_ok and all(1 <= n <= 2048 for n in (ny, nx))):
+    if pow2 or (generic_ok and all(1 <= n <= DFT_MAX for n in (ny, nx))):
         return
     raise _lib.B4DUnsupported(
         f"the sm_100a FFT kernels cover power-of-two sides in [128, {_lib.FFT_MAX}]"
-        + (" or any sides in [1, 2048]" if generic_ok else "")
+        + (f" or any sides in [1, {DFT_MAX}]" if generic_ok else "")
         + f"; got (ny, nx) = ({ny}, {nx}). There is no CPU fallback on this path.")
 
 
@@ -221,8 +224,8 @@ def ifft2d(spec):
     """ifft2(ifftshift(F)) for every shifted complex64 spectrum of a (T, ny, nx) CUDA tensor -> complex64 (T, ny, nx)."""
     torch = require_cuda()
     T, ny, nx = spec.shape
-    if not all(1 <= n <= 2048 for n in (ny, nx)):
-        raise _lib.B4DUnsupported(f"ifft2d covers sides in [2, 2048]; got ({ny}, {nx})")
+    if not all(1 <= n <= DFT_MAX for n in (ny, nx)):
+        raise _lib.B4DUnsupported(f"ifft2d covers sides in [2, {DFT_MAX}]; got ({ny}, {nx})")
     ctx = get_context(_dev(spec))
     src = torch.view_as_real(spec.to(torch.complex64).contiguous())
     out = torch.empty((T, ny, nx, 2), dtype=torch.float32, device=spec.device)

@@ -196,18 +196,20 @@ int b4d_temporal_finalize(b4d_ctx* ctx, const double* sums, const float* shift, 
 /* ---- 2-D FFT family ---------------------------------------------------------------------- */
 /*
  * Frame sizes. Powers of two in [B4D_FFT_MIN, B4D_FFT_MAX] run the hot-path kernels. Every entry point below also accepts
- * ANY sides in [2, B4D_FFT_MAX] (the 227 / 228-pixel sub-tiles of the reference's tiling executor, metrics/common.py:278-378,
- * detectors that are not 2^k wide): those go through Bluestein's algorithm on the same FFT core (csrc/generic_dft.cuh),
- * with the stack pipeline composed from the stand-alone paths. Larger sides return B4D_ERR_UNSUPPORTED (the Python layer
- * raises; there is no CPU fallback).
+ * ANY sides in [2, B4D_DFT_MAX] (the 227 / 228-pixel sub-tiles of the reference's tiling executor, metrics/common.py:278-378,
+ * detectors that are not 2^k wide or wider than 2048 pixels, e.g. 2560 x 2160; the reference is size-agnostic,
+ * signal/fft.py:236): those go through Bluestein's algorithm on the same FFT core (csrc/generic_dft.cuh), with the
+ * stack pipeline composed from the stand-alone paths. Larger sides return B4D_ERR_UNSUPPORTED (the Python layer raises;
+ * there is no CPU fallback).
  */
 #define B4D_FFT_MIN 128
 #define B4D_FFT_MAX 2048
+#define B4D_DFT_MAX 4096
 
 /* fft2d (signal/fft.py:198-237): out = fftshift(fft2(frame)), complex64 interleaved (ny, nx). */
 int b4d_fft2d(b4d_ctx* ctx, const float* stack, int64_t n_frames, int ny, int nx, float* out_c64);
 
-/* ifft2d (signal/fft.py:240-258): out = ifft2(ifftshift(F)), complex64 in and out (ny, nx), any sides in [2, 2048]
+/* ifft2d (signal/fft.py:240-258): out = ifft2(ifftshift(F)), complex64 in and out (ny, nx), any sides in [2, 4096]
  * (chirp-z path; a building block and test hook, not a hot-path kernel). */
 int b4d_ifft2d(b4d_ctx* ctx, const float* spec_c64, int64_t n_frames, int ny, int nx, float* out_c64);
 

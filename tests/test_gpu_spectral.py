@@ -529,3 +529,59 @@ def test_xcorr_standardize_without_peak_normalisation_vs_oracle(sig, shape):
     got, _, _ = sig.xcorr2d(flat, b, remove_mean=False, standardize=True, normalize="none")
     want, _, _ = ref.xcorr2d(flat, b, remove_mean=False, standardize=True, normalize="none")
     assert np.max(np.abs(got - np.real(want))) <= 1e-4 * float(np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("shape", [(2160, 2560), (4096, 4096), (2049, 3000)])
+def test_frames_wider_than_2048_vs_oracle(sig, shape):
+    """Detector formats beyond 2048 pixels a side (2560 x 2160 sCMOS, 4096^2): the chirp-z path with an 8192-point
+    convolution (one radix-2 step around the 4096-point register core). fft2d / psd2d / autocorr2d against the
+    reference's numpy evaluation at north_star's tolerances; the reference itself is size-agnostic (signal/fft.py:236)."""
+    from barc4dip_b200 import synth
+    ny, nx = shape
+    img = synth.speckle_frame(ny, nx, grain=5.0, seed=ny + nx)
+    F, fx, fy = sig.fft2d(img)
+    Fo, fxo, fyo = orc.fft2d(np.asarray(img, dtype=np.float64))
+    assert F.shape == (ny, nx) and np.array_equal(fx, fxo) and np.array_equal(fy, fyo)
+    a, b = F.copy(), Fo.copy()
+    a[ny // 2, nx // 2] = 0
+    b[ny // 2, nx // 2] = 0
+    assert np.max(np.abs(a - b)) <= PEAK_TOL * np.max(np.abs(b))
+    assert abs(F[ny // 2, nx // 2] - Fo[ny // 2, nx // 2]) <= PEAK_TOL * abs(Fo[ny // 2, nx // 2])
+    del F, Fo, a, b
+    P, _, _ = sig.psd2d(img)
+    Po, _, _ = orc.psd2d(img)
+    assert np.max(np.abs(P - Po)) <= PEAK_TOL * Po.max()
+    del P, Po
+    ac, _, _ = sig.autocorr2d(img)
+    aco = orc.autocorr2d(img)[0]
+    assert np.max(np.abs(ac - aco)) <= PEAK_TOL
+    assert abs(ac[ny // 2, nx // 2] - 1.0) < 1e-6
+
+
+def test_tracking_and_analyzer_on_2560x2160_frames():
+    """The whole stack analysis on a 2560 x 2160 detector format: tracker (map-based median on this path) against the
+    oracle, and StackAnalyzer.run end to end (reductions, grain not asked of non-square frames, PSD / autocorrelation maps)."""
+    from barc4dip_b200 import engine, synth
+    from barc4dip_b200.pipeline import StackAnalyzer
+    ny, nx = 2160, 2560
+    base = synth.speckle_frame(ny, nx, grain=6.0, seed=5)
+    rng = np.random.default_rng(6)
+    noise = lambda: (0.01 * float(base.mean()) * rng.standard_normal((ny, nx))).astype(np.float32)
+    stack = np.stack([base + noise(), np.roll(base, (3, -7), axis=(0, 1)) + noise(), synth.fourier_shift(base, -1.4, 2.3) + noise()])
+    full = (slice(0, ny), slice(0, nx))
+    tr = engine.PhaseTracker(stack[0], (ny, nx), y0=0, x0=0)
+    tab = tr.track(engine.as_stack(stack))
+    for t in (1, 2):
+        want = orc.phase_correlation(stack[0], stack[t], slices_yx=full)
+        np.testing.assert_allclose(tab[t, :2], want[:2], atol=0.01)
+        np.testing.assert_allclose(tab[t, 2], want[2], rtol=5e-4)
+        np.testing.assert_allclose(tab[t, 3], want[3], rtol=2e-3)
+    np.testing.assert_allclose(tab[1, :2], (3.0, -7.0), atol=0.05)
+    res = StackAnalyzer((ny, nx), reference=stack[0], chunk_frames=2).run(stack)
+    np.testing.assert_allclose(res["tracking"]["dy"][1:], tab[1:, 0], atol=1e-3)
+    m = orc.distribution_moments(stack[2])
+    np.testing.assert_allclose(res["stats"]["mean"][2], m["mean"], rtol=1e-6)
+    np.testing.assert_allclose(res["stats"]["std"][2], m["std"], rtol=1e-5)
+    Po, _, _ = orc.psd2d(stack[1])
+    assert np.max(np.abs(res["psd"][1] - Po)) <= PEAK_TOL * Po.max()
+    assert np.max(np.abs(res["autocorr"][1] - orc.autocorr2d(stack[1])[0])) <= PEAK_TOL
