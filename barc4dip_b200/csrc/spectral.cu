@@ -388,10 +388,13 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         const size_t rstride = (size_t)T * nx;        // elements between output rows T apart
         float* psd = a.psd_out ? a.psd_out + (size_t)t * NY * nx + (size_t)j * nx + (kx + hx) : nullptr;
         float* psdm = a.psd_out ? a.psd_out + (size_t)t * NY * nx + (size_t)(NY - j) * nx + (hx - kx) : nullptr;
-        float2* cpl = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx + (size_t)j * nx + (kx + hx) : nullptr;
-        float2* cplm = a.cplx_out ? a.cplx_out + (size_t)t * NY * nx + (size_t)(NY - j) * nx + (hx - kx) : nullptr;
-        float2* cj = a.conj_out ? a.conj_out + g0 : nullptr;
-        float2* cjn = a.conj_nyq_out ? a.conj_nyq_out + (size_t)t * NY : nullptr;
+        // the complex / conjugate spectra are outputs of the plain forward launches only (fft2d, reference spectra): with an
+        // inverse branch compiled in they are never asked for, and their per-element tests leave the loops
+        constexpr bool PLAIN = !AC && !PC;
+        float2* cpl = (PLAIN && a.cplx_out) ? a.cplx_out + (size_t)t * NY * nx + (size_t)j * nx + (kx + hx) : nullptr;
+        float2* cplm = (PLAIN && a.cplx_out) ? a.cplx_out + (size_t)t * NY * nx + (size_t)(NY - j) * nx + (hx - kx) : nullptr;
+        float2* cj = (PLAIN && a.conj_out) ? a.conj_out + g0 : nullptr;
+        float2* cjn = (PLAIN && a.conj_nyq_out) ? a.conj_nyq_out + (size_t)t * NY : nullptr;
         const bool mirror = !TILE0 || kx >= 1;
         const float wgt = mirror ? 2.f : 1.f;
         const float ps = a.psd_scale;
@@ -421,7 +424,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
                 Pn = Fn.x * Fn.x + Fn.y * Fn.y;
                 const size_t rs = (size_t)((ky + NY / 2) & (NY - 1)) * nx;
                 if (a.psd_out) __stcs(a.psd_out + (size_t)t * NY * nx + rs, Pn * ps);
-                if (a.cplx_out) __stcs(a.cplx_out + (size_t)t * NY * nx + rs, Fn);
+                if (PLAIN && a.cplx_out) __stcs(a.cplx_out + (size_t)t * NY * nx + rs, Fn);
                 if (cjn) cjn[ky] = cconj(Fn);
                 if (SPEC) spec_accumulate<NY>(sp, Pn * ps, ky, hx, nx, 1.0, false);
             }

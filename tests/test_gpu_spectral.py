@@ -104,10 +104,10 @@ def test_fft_roundtrip_and_parseval_2048():
 def test_unsupported_sizes_fail_loudly(sig):
     from barc4dip_b200._lib import B4DUnsupported
     with pytest.raises(B4DUnsupported):
-        sig.psd2d(np.zeros((16, 2050), np.float32))                   # sides above 2048 are not built
+        sig.psd2d(np.zeros((16, 4100), np.float32))                   # sides above 4096 are not built
     odd = gc.frame_cases()["odd150x200"]
     with pytest.raises(B4DUnsupported):
-        sig.template_matching(odd[:21, :21], np.zeros((64, 2100), np.float32))
+        sig.template_matching(odd[:21, :21], np.zeros((64, 4100), np.float32))
     with pytest.raises(ValueError):
         sig.psd2d(np.zeros((4, 4, 4), np.float32))
     with pytest.raises(ValueError):
