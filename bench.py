@@ -181,7 +181,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"fused stack pipeline (moments+tenengrad+laplacian+amplitude+psd2d+grain/autocorr2d+phase_correlation"
                                f"+per-pixel temporal power sums), "
-                               f"{args.size}x{args.size} float32 frames", "frames_per_step": frames,
+                               f"{args.size}x{args.size} float32 frames",
+                   "stack": "SURVEY 8(d) C4: one speckle Fourier-shifted along a 2-D random walk (sigma 0.3 px, +-20 px) + 1 % noise per frame",
+                   "frame": [args.size, args.size], "frames_per_step": frames,
                    "note": "oracle port of the reference's numpy/scipy path (oracle/ref_numpy.py), joblib threads over frames"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{frames} frames of {args.size}^2 per step, {args.steps} steps"},
