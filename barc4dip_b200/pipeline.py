@@ -86,7 +86,7 @@ class StackAnalyzer:
         """Analyse an HBM-resident (T, ny, nx) float32 stack; everything stays on the device."""
         q_lo, q_hi = 0.05 / 100.0, 99.95 / 100.0      # amplitude(): percentile_minmax_range defaults
         # grain widths need square frames (the reference pads to square, metrics/speckles.py:530): the fused pass reports
-        # them for square frames only, others get NaN here (stack.grain_block pads and serves them on request)
+        # them for square frames only, the others go through stack.grain_block below
         square = self.ny == self.nx
         res = engine.stack_pipeline(dev_stack, gain=self.gain, dark=self.dark, saturation_value=self.sat, eps=self.eps,
                                     subpixel=self.subpixel, want_psd=self.want_maps or psd_out is not None,
@@ -95,8 +95,14 @@ class StackAnalyzer:
                                     psd_out=psd_out, ac_out=ac_out,
                                     tail_quantiles=(q_lo, q_hi) if self.want_contrast else None)
         if res["grain"] is None:
+            # non-square frames: the reference pads to a square with the frame's mean (geometry/masks.py:11-56) before the
+            # autocorrelation; stack.grain_block does that (the padded side is rarely a power of two: chirp-z path)
             torch = require_cuda()
-            res["grain"] = torch.full((dev_stack.shape[0], 4), float("nan"), dtype=torch.float64, device=dev_stack.device)
+            src = dev_stack
+            if self.gain is not None:
+                src = engine.flat_field(dev_stack, self.flat, self.dark, **self._ff)
+            g = blocks.grain_block(src, table=res["reductions"].cpu().numpy())
+            res["grain"] = torch.from_numpy(np.stack([g["lx"], g["ly"], g["leq"], g["r"]], axis=1)).to(dev_stack.device)
         if resolve_tails and res["tracking"] is not None:
             # same contract for the tracker: snr = NaN marks a frame whose fused median bracket missed
             ff = (lambda fr: engine.flat_field(fr, self.flat, self.dark, **self._ff)) if self.gain is not None else None

@@ -579,6 +579,9 @@ def test_tracking_and_analyzer_on_2560x2160_frames():
     np.testing.assert_allclose(tab[1, :2], (3.0, -7.0), atol=0.05)
     res = StackAnalyzer((ny, nx), reference=stack[0], chunk_frames=2).run(stack)
     np.testing.assert_allclose(res["tracking"]["dy"][1:], tab[1:, 0], atol=1e-3)
+    g = orc.grain(stack[1])                                   # non-square: padded to 2560^2 with the frame's mean
+    for k in ("lx", "ly", "leq"):
+        np.testing.assert_allclose(res["grain"][k][1], g[k], rtol=1e-4, err_msg=k)
     m = orc.distribution_moments(stack[2])
     np.testing.assert_allclose(res["stats"]["mean"][2], m["mean"], rtol=1e-6)
     np.testing.assert_allclose(res["stats"]["std"][2], m["std"], rtol=1e-5)
