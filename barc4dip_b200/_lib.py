@@ -15,7 +15,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb4d.so")
+LIB_PATH = os.environ.get("B4D_LIB") or os.path.join(_HERE, "libb4d.so")   # B4D_LIB: A/B builds (build.py --variant)
 
 FR_NCOLS = 13
 FR = {"count": 0, "mean": 1, "m2": 2, "m3": 3, "m4": 4, "nzero": 5, "nsat": 6,

@@ -3,6 +3,8 @@ Build libb4d.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
     python -m barc4dip_b200.build          # incremental
     python -m barc4dip_b200.build --force
+    python -m barc4dip_b200.build --variant NAME [-DFLAG ...]   # A/B builds: barc4dip_b200/variants/libb4d_NAME.so
+                                                                # (picked up with B4D_LIB=<path>, see _lib.py)
 
 The .so lands next to this file (barc4dip_b200/libb4d.so) so that it travels to the GPU box
 with the repository snapshot; it is git-ignored.
@@ -43,11 +45,16 @@ def _headers_digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, defines: list[str] | None = None) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
+    OBJDIR, LIB, NVCC_FLAGS = globals()["OBJDIR"], globals()["LIB"], list(globals()["NVCC_FLAGS"])
+    if variant:
+        OBJDIR = os.path.join(HERE, "variants", "obj_" + variant)
+        LIB = os.path.join(HERE, "variants", f"libb4d_{variant}.so")
+        NVCC_FLAGS += list(defines or [])
     os.makedirs(OBJDIR, exist_ok=True)
     stamp = os.path.join(OBJDIR, "headers.sha1")
-    digest = _headers_digest()
+    digest = _headers_digest() + " ".join(defines or [])
     old = open(stamp).read() if os.path.exists(stamp) else ""
     if old != digest:
         force = True
@@ -80,5 +87,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
+                 defines=[a for a in sys.argv[1:] if a.startswith("-D")])
     print(path)

@@ -536,22 +536,17 @@ __global__ void __launch_bounds__(1024) fused_median_final_kernel(const SelFast*
                     if (p < FIN_CAP) s_keys[p] = key;
                 }
             };
-            // a warp walks regions four at a time: their counts, then up to FM_REGION keys each (two per lane), all
-            // loads of a group in flight together (the walk is latency bound: 8192 regions per frame at 2048^2)
-            constexpr int RU = 4;
-            for (int r0 = warp * RU; r0 < regions; r0 += 32 * RU) {
-                unsigned c[RU], k0[RU], k1[RU];
+            // a warp walks whole CTA regions (256 per frame at 2048^2, ~560 keys each), 128 keys per step with all four
+            // loads in flight together
+            for (int r = warp; r < regions; r += 32) {
+                const unsigned c = min(c3[3 * r], (unsigned)FM_REGION);
+                const unsigned* reg = store + (size_t)r * FM_REGION;
+                for (unsigned i0 = 0; i0 < c; i0 += 128) {
+                    unsigned k[4];
 #pragma unroll
-                for (int u = 0; u < RU; ++u) c[u] = r0 + u < regions ? c3[3 * (r0 + u)] : 0u;
+                    for (int u = 0; u < 4; ++u) k[u] = i0 + 32 * u + lane < c ? reg[i0 + 32 * u + lane] : 0u;
 #pragma unroll
-                for (int u = 0; u < RU; ++u) {
-                    k0[u] = lane < (int)c[u] ? store[(size_t)(r0 + u) * FM_REGION + lane] : 0u;
-                    k1[u] = lane + 32 < (int)c[u] ? store[(size_t)(r0 + u) * FM_REGION + lane + 32] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < RU; ++u) {
-                    if (lane < (int)c[u]) take(k0[u]);
-                    if (lane + 32 < (int)c[u]) take(k1[u]);
+                    for (int u = 0; u < 4; ++u) if (i0 + 32 * u + lane < c) take(k[u]);
                 }
             }
             for (unsigned i = threadIdx.x; i < sc; i += blockDim.x) take(store[(size_t)regions * FM_REGION + i]);

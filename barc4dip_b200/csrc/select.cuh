@@ -44,8 +44,8 @@ struct FusedMedian {                  // device scratch of one batch of the fuse
     int* need;
     unsigned* bhist;                  // (T, SEL_BINS) bracket histogram
     unsigned* cnt3;                   // (T, regions, 3): candidates, values below the bracket, valid values of a region
-    unsigned* cand;                   // (T, regions * FM_REGION + FM_SAMPLE_CAP) keys: warp regions, then the sample rows'
-    int regions;                      // warp regions per frame
+    unsigned* cand;                   // (T, regions * FM_REGION + FM_SAMPLE_CAP) keys: CTA regions, then the sample rows'
+    int regions;                      // CTA regions per frame (row blocks of rows_inv_kernel)
 };
 
 // numpy's linear method: h = n*q + (1 + q*(1-1-1)) - 1, lo = floor(h), hi = min(lo+1, n-1)
@@ -123,44 +123,61 @@ __device__ __forceinline__ void census_flush(SelFast* s, int q, const unsigned* 
     }
 }
 
-// Warp-level census into the warp's OWN region of the frame's candidate store: no reservation, no atomic whose result
-// anybody waits for. Lane counts -> one warp scan -> keys written at the scan offsets, (count, below, valid) of the
-// region stored by lane 31, bracket histogram by fire-and-forget RED. A region holds FM_REGION keys; a count above that
-// marks the frame for the map-based path. Whole warps only.
-constexpr int FM_REGION = 64;          // keys per warp and call (a warp holds 512 values, < 5 % of them inside a bracket)
+// Census of register-resident magnitudes against a frame's bracket, one value at a time and without a vote, a branch or
+// an atomic: every thread owns a column of the CTA's shared-memory stage (slot k of thread `tid` at word k * nthreads +
+// tid; the caller provides as many slots as a thread has values, so nothing can overflow) and appends d = key - L of the
+// values inside the bracket with a predicated store and a predicated pointer bump. A value outside the bracket costs five
+// issue slots: key - L, its sign bit into `below`, one unsigned compare covering both ends, the two predicated-off
+// instructions. The CTA then compacts the columns into its own region of the frame's candidate store
+// (census_stage_flush). A region holds FM_REGION keys (a CTA of rows_inv_kernel owns 16384 values, ~560 of them inside a
+// +-6 sigma bracket of 32 K samples); a count above that marks the frame for the map-based path.
+constexpr int FM_REGION = 1536;        // keys per CTA region of the candidate store
 constexpr int FM_SAMPLE_CAP = 4096;    // keys the sample rows may contribute
 
-template <int NV, int COMP>
-__device__ __forceinline__ void census_values_region(const float2 (&x)[NV], unsigned Lkey, unsigned Ukey, int shift,
-                                                     unsigned* __restrict__ region, unsigned* __restrict__ cnt3,
-                                                     unsigned* __restrict__ hist_q, int lane) {
+template <int STRIDE_BYTES>
+__device__ __forceinline__ void census_stage_value(float v, unsigned Lkey, unsigned W, unsigned& below, unsigned& slot_addr) {
     // The values are magnitudes (non-negative or NaN), so their bit patterns are the order-preserving keys and one
     // subtraction d = key - L gives both tests: below the bracket <=> bit 31 of d (keys and L are < 2^31), inside <=>
-    // d <= U - L (unsigned). The keys inside are compacted slot by slot with a warp vote: a slot nobody is inside of
-    // costs five instructions.
-    const unsigned W = min(Ukey, 0x7fffffffu) - Lkey;
-    unsigned lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    unsigned below = 0, base = 0;
+    // d <= U - L (unsigned).
+    const unsigned d = __float_as_uint(v) - Lkey;
+    below += d >> 31;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ls.u32 p, %1, %2;\n\t"
+        "@p st.shared.u32 [%0], %1;\n\t"
+        "@p add.u32 %0, %0, %3;\n\t"
+        "}" : "+r"(slot_addr) : "r"(d), "r"(W), "n"(STRIDE_BYTES) : "memory");
+}
+
+// Compaction of the CTA's stage columns (cnt entries of this thread, d = key - L each) into its region of the frame's
+// candidate store, in thread order, and into the frame's bracket histogram; cnt3 = (candidates, values below the bracket,
+// valid values) of the region. Whole CTA of NT threads (a multiple of 32, at most 1024); s_w: NT / 32 shared words;
+// below / nvalid: the CTA's totals, read by thread 0 only. Contains one barrier.
+template <int NT>
+__device__ __forceinline__ void census_stage_flush(const unsigned* stage, unsigned cnt, unsigned* s_w, unsigned below, unsigned nvalid,
+                                                   unsigned Lkey, int shift, unsigned* __restrict__ region,
+                                                   unsigned* __restrict__ cnt3, unsigned* __restrict__ hist_q) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned incl = cnt;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const unsigned d = __float_as_uint(COMP ? x[i].y : x[i].x) - Lkey;
-        below += d >> 31;
-        const bool in = d <= W;
-        if (__any_sync(0xffffffffu, in)) {
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const unsigned pos = base + __popc(m & lt);
-                if (pos < FM_REGION) region[pos] = d + Lkey;
-                atomicAdd(hist_q + min(d >> shift, (unsigned)(SEL_BINS - 1)), 1u);
-            }
-            base += __popc(m);
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
     }
-    // A NaN anywhere in the frame reaches every output of its inverse transform, so one value per lane tells whether the
-    // warp's values are valid.
-    const float v0 = COMP ? x[0].y : x[0].x;
-    const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, v0 == v0)) * (unsigned)NV;
-    below = __reduce_add_sync(0xffffffffu, below);
-    if (lane == 31) { cnt3[0] = base; cnt3[1] = below; cnt3[2] = nvalid; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned off = incl - cnt, n = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const unsigned v = s_w[w];
+        if (w < warp) off += v;
+        n += v;
+    }
+    for (unsigned k = 0; k < cnt; ++k) {
+        const unsigned d = stage[k * NT + tid];
+        if (off + k < (unsigned)FM_REGION) region[off + k] = d + Lkey;
+        atomicAdd(hist_q + min(d >> shift, (unsigned)(SEL_BINS - 1)), 1u);
+    }
+    if (tid == 0) { cnt3[0] = n; cnt3[1] = below; cnt3[2] = nvalid; }
 }

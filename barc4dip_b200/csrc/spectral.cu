@@ -597,7 +597,7 @@ struct RowsInvArgs {
     unsigned* cand;         // (T, regions * FM_REGION + FM_SAMPLE_CAP) region store
     unsigned* cnt3;         // (T, regions, 3)
     unsigned* bhist;        // (T, SEL_BINS)
-    int regions;            // warp regions per frame = row blocks * 16 warps * 2
+    int regions;            // CTA regions per frame = row blocks
     int pf_dist;            // L2 prefetch distance in CTAs (0 = off), set by the launcher
     int keep;               // cache policy of the intermediate (see st_inter)
 };
@@ -621,6 +621,8 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     __shared__ float s_scale;
     __shared__ float s_max[16];
     __shared__ unsigned s_idx;
+    __shared__ unsigned s_cen[2];                     // fused median: values below the bracket, valid values of the CTA
+    __shared__ unsigned s_wcnt[16];                   // candidates per warp
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t t = blockIdx.y;
     const int NY = a.ny;
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     unsigned Lk = 0u, Uk = 0xfffffffeu;               // fused median: the frame's bracket, fetched early
     if (MODE == 2) { Lk = a.sel[t].L[0]; Uk = a.sel[t].U[0]; }
     if (tid == 0) s_idx = 0xffffffffu;
+    if (MODE == 2 && tid < 2) s_cen[tid] = 0u;
 
     // ---- gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
     {
@@ -753,15 +756,34 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         }
     }
     if (MODE == 2) {
-        // fused median: census of the |.| values against the frame's bracket, straight from the registers, into this
-        // warp's own two regions of the frame's candidate store
-        const int shift = bracket_shift(Lk, Uk);
-        const size_t reg = ((size_t)blk * 16 + warp) * 2;
+        // fused median: census of the |.| values against the frame's bracket, straight from the registers. The exchange
+        // buffer is dead (the outputs sit in registers) and becomes the stage: 32 slot rows of 512 words, a column per
+        // thread, so that every value of a thread has a slot.
+        static_assert(FPC * FS * sizeof(float2) >= 32 * 512 * sizeof(unsigned), "stage does not fit the exchange buffer");
+        const unsigned W = min(Uk, 0x7fffffffu) - Lk;
+        __syncthreads();                              // the other transforms of the CTA may still be reading their exchanges
+        const unsigned* stage = reinterpret_cast<const unsigned*>(sm);
+        const unsigned ad0 = (unsigned)__cvta_generic_to_shared(stage + tid);
+        unsigned ad = ad0, below = 0;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            census_stage_value<2048>(x[s].x, Lk, W, below, ad);
+            census_stage_value<2048>(x[s].y, Lk, W, below, ad);
+        }
+        // A NaN anywhere in the frame reaches every output of its inverse transform, so one value per lane and row tells
+        // whether the warp's values are valid.
+        const unsigned nvalid = (unsigned)(__popc(__ballot_sync(0xffffffffu, x[0].x == x[0].x)) +
+                                           __popc(__ballot_sync(0xffffffffu, x[0].y == x[0].y))) * 16u;
+        below = __reduce_add_sync(0xffffffffu, below);
+        if (lane == 0) { atomicAdd(&s_cen[0], below); atomicAdd(&s_cen[1], nvalid); }
         unsigned* store = a.cand + (size_t)t * ((size_t)a.regions * FM_REGION + FM_SAMPLE_CAP);
-        unsigned* c3 = a.cnt3 + (size_t)t * a.regions * 3;
-        unsigned* hq = a.bhist + (size_t)t * SEL_BINS;
-        census_values_region<16, 1>(x, Lk, Uk, shift, store + reg * FM_REGION, c3 + reg * 3, hq, lane);
-        census_values_region<16, 0>(x, Lk, Uk, shift, store + (reg + 1) * FM_REGION, c3 + (reg + 1) * 3, hq, lane);
+        // (the flush's barrier lies between the atomics above and thread 0 reading the totals)
+        census_stage_flush<512>(stage, (ad - ad0) >> 11, s_wcnt, 0u, 0u, Lk, bracket_shift(Lk, Uk), store + (size_t)blk * FM_REGION,
+                                a.cnt3 + ((size_t)t * a.regions + blk) * 3, a.bhist + (size_t)t * SEL_BINS);
+        if (tid == 0) {
+            unsigned* c3 = a.cnt3 + ((size_t)t * a.regions + blk) * 3;
+            c3[1] = s_cen[0]; c3[2] = s_cen[1];
+        }
     }
 }
 
@@ -2568,7 +2590,7 @@ int track_fused_begin(b4d_ctx* ctx, int64_t tc, int ny, int nx, int ns, float* s
     tf->samples = scratch;
     tf->window = tf->samples + (size_t)tc * tf->m;
     tf->blk3 = reinterpret_cast<int*>(tf->window + (size_t)tc * 3 * rpc * nx);
-    return b4d_fused_median_begin(ctx, tc, nblk * 16 * 2, &tf->fm);
+    return b4d_fused_median_begin(ctx, tc, nblk, &tf->fm);
 }
 
 int track_fused_range(b4d_ctx* ctx, const Work& w, const TrackFused& tf, RowsInvArgs r, int64_t t0, int64_t tcs, int nx) {
