@@ -266,6 +266,7 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int TMA_BOX_ROWS = 256;
+constexpr int COLS_CM = 1;    // complex-product form of the column pass (fft.cuh: cmulv)
 
 struct SpecAcc {
     double total = 0, fx2 = 0, fy2 = 0, p2 = 0, all = 0, plogp = 0;
@@ -343,7 +344,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         if (next < (size_t)gridDim.y * ntiles)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.H + (next / R) * ((size_t)NY * TC) + ((next % R) * NT + (size_t)tid) * 16));
     }
-    fft_regs<NY, -1, CW>(x, j, A + c, a.tw);
+    fft_regs<NY, -1, CW, 0, COLS_CM>(x, j, A + c, a.tw);
     // (the transform's barriers lie between every thread's tile loads and this point) the tile is dead now: drop its lines
     // from L2 instead of letting them be written back, one 128-byte line per thread
     if (CW == TC && (a.keep & 4))
@@ -476,7 +477,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
                     }
                 }
                 F.x *= inv_s; F.y *= inv_s;
-                float2 G = whiten_if(cmul(F, Rv[i]), a.whiten, a.eps);
+                float2 G = whiten_if(cmulv<COLS_CM>(F, Rv[i]), a.whiten, a.eps);
                 if (nyq_owner) {                      // pack: column 0 <- G[:,0] + i G[:,nx/2]
                     Fn.x *= inv_s; Fn.y *= inv_s;
                     const float2 Gn = whiten_if(cmul(Fn, __ldg(Rn + ky)), a.whiten, a.eps);
@@ -517,7 +518,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
 
     // ---- inverse along y of the product ---------------------------------------------------------
     if (PC) {
-        fft_regs<NY, +1, CW>(x, j, A + c, a.tw);
+        fft_regs<NY, +1, CW, 0, COLS_CM>(x, j, A + c, a.tw);
         float2* o = a.i2_pc + g0;
 #pragma unroll
         for (int s = 0; s < 16; ++s) st_inter(o + s * GS, x[s], a.keep);
@@ -535,7 +536,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             const int c2 = tid % CH, j2 = tid / CH;
 #pragma unroll
             for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[j2 * CW + c2 + s * NT], Bp[j2 * CW + c2 + CH + s * NT]);
-            fft_regs<NY, +1, CH, 2>(x, j2, A + c2, a.tw);
+            fft_regs<NY, +1, CH, 2, COLS_CM>(x, j2, A + c2, a.tw);
             const int pc = tile * CH + c2;
             float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + (size_t)j2 * TC + (pc % TC);
 #pragma unroll
@@ -545,7 +546,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             const int j3 = (tid - NTH) % T;
 #pragma unroll
             for (int s = 0; s < 16; ++s) x[s] = make_float2(Pns[j3 + s * T], 0.f);
-            fft_regs<NY, +1, 1, 1>(x, j3, A + PL * CH, a.tw, 1);
+            fft_regs<NY, +1, 1, 1, COLS_CM>(x, j3, A + PL * CH, a.tw, 1);
             if (tid - NTH < T) {
                 float2* o = a.i2_ac_nyq + (size_t)t * NY + j3;
 #pragma unroll
