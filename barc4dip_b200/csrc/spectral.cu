@@ -119,11 +119,18 @@ constexpr int TC = 8;     // width of a tile of the blocked intermediates [kx/TC
 //   2  loads leave the line at normal priority instead of marking it evict-first;
 //   4  the column pass drops its input tile from L2 once every thread has read it (discard.global.L2: the dead, dirty
 //      lines are neither kept nor written back to HBM).
+// The bits are honoured only by experiment builds (python -m barc4dip_b200.build --variant keep -DB4D_KEEP_POLICY=1): a
+// run-time policy switch compiles into two predicated memory instructions per access -- one of them always off, each
+// taking an issue slot -- in kernels that are bound by instruction issue and by the load/store pipe. The default build
+// streams both ways (policy 0, the whole-batch schedule's).
+#ifndef B4D_KEEP_POLICY
+#define B4D_KEEP_POLICY 0
+#endif
 __device__ __forceinline__ void st_inter(float2* p, float2 v, int keep) {
-    if (keep & 1) __stcg(p, v); else __stcs(p, v);
+    if (B4D_KEEP_POLICY && (keep & 1)) __stcg(p, v); else __stcs(p, v);
 }
 __device__ __forceinline__ float2 ld_inter(const float2* p, int keep) {
-    return (keep & 2) ? __ldcg(p) : __ldcs(p);
+    return (B4D_KEEP_POLICY && (keep & 2)) ? __ldcg(p) : __ldcs(p);
 }
 
 struct RowsFwdArgs {
@@ -347,7 +354,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     fft_regs<NY, -1, CW, 0, COLS_CM>(x, j, A + c, a.tw);
     // (the transform's barriers lie between every thread's tile loads and this point) the tile is dead now: drop its lines
     // from L2 instead of letting them be written back, one 128-byte line per thread
-    if (CW == TC && (a.keep & 4))
+    if (B4D_KEEP_POLICY && CW == TC && (a.keep & 4))
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.H + (size_t)t * NY * hx + (size_t)tile * NY * TC + (size_t)tid * 16) : "memory");
     // TMA path of the PSD map (every tile but tile 0, whose packed DC / Nyquist column has its own rules): the exchange
     // buffer becomes the staging area of the main tile Bs[ky'][c], indexed by OUTPUT row ky' = (ky + NY/2) % NY
@@ -676,19 +683,28 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         }
         __syncthreads();
         const float sA = s_scale;
+        const float2 sA2 = make_float2(sA, sA);
         float2* z = sm + f * FS;
+        // Z[k] = Ga + i Gb and Z[NX - k] = conj(Ga) + i conj(Gb), k = jg + m TPF. With TPF a multiple of 16 both padded
+        // indices are a per-thread base plus a compile-time multiple of m: pad16(k) = pad16(jg) + m (TPF + TPF / 16) and
+        // pad16(NX - k) = padded_len(NX) - jg - ceil(jg / 16) - m (TPF + TPF / 16).
+        constexpr bool LIN = (TPF % 16) == 0;
+        constexpr int PS = TPF + TPF / 16;
+        float2* zk = z + pad16(jg);
+        float2* zm = z + (padded_len(NX) - jg - ((jg + 15) >> 4));
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int k = jg + m * TPF;
-            float2 g1 = ga[m], g2 = gb[m];
-            g1.x *= sA; g1.y *= sA; g2.x *= sA; g2.y *= sA;
-            if (k == 0) {
+            const float2 g1 = __fmul2_rn(ga[m], sA2), g2 = __fmul2_rn(gb[m], sA2);
+            if (m == 0 && k == 0) {
                 // packed slot: (DC, Nyquist), both real
                 z[pad16(0)] = make_float2(g1.x, g2.x);
                 z[pad16(HX)] = make_float2(g1.y, g2.y);
             } else {
-                z[pad16(k)] = make_float2(g1.x - g2.y, g1.y + g2.x);
-                z[pad16(NX - k)] = make_float2(g1.x + g2.y, g2.x - g1.y);
+                const float2 A = __fadd2_rn(g1, make_float2(-g2.y, g2.x));
+                const float2 B = __fadd2_rn(make_float2(g1.x, -g1.y), make_float2(g2.y, g2.x));
+                if (LIN) { zk[PS * m] = A; zm[-PS * m] = B; }
+                else { z[pad16(k)] = A; z[pad16(NX - k)] = B; }
             }
         }
         __syncthreads();
@@ -865,26 +881,36 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
         }
         __syncthreads();
         const float sA = s_scale, sH = 0.5f * sA;
+        const float2 sH2 = make_float2(sH, sH);
         float2* z = sm + f * FS;
-        const int chm = (1 << a.ch_log2) - 1;
+        // Column pc = jg + m TPF of the packed intermediate carries the spectrum columns ka = ka0 + 2 TPF m and kb = ka + cw/2
+        // (ka0 = jg with a zero bit inserted at position ch_log2). 2 TPF is a multiple of 16, so the four padded indices
+        // pad16(ka), pad16(kb), pad16(NX - ka), pad16(NX - kb) are per-thread bases plus compile-time multiples of m:
+        // kb = ka + cw/2 never crosses a 16-boundary, NX - kb = (NX - ka) - cw/2 crosses one iff (NX - ka) % 16 < cw/2.
+        static_assert(TPF % 8 == 0, "2 TPF must be a multiple of 16");
+        constexpr int PS2 = 2 * TPF + 2 * TPF / 16;
+        const int chm = (1 << a.ch_log2) - 1, c1 = chm + 1;
+        const int ka0 = ((jg >> a.ch_log2) << (a.ch_log2 + 1)) + (jg & chm);
+        float2* zka = z + pad16(ka0);
+        float2* zkb = zka + c1;
+        float2* zma = z + (padded_len(NX) - ka0 - ((ka0 + 15) >> 4));
+        float2* zmb = zma - c1 - ((((16 - (ka0 & 15)) & 15) < c1) ? 1 : 0);
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const int pc = jg + m * TPF;
-            const int ka = ((pc >> a.ch_log2) << (a.ch_log2 + 1)) + (pc & chm), kb = ka + chm + 1;
-            // rows ya (g1) and yb (g2) of the two columns
-            const float2 g1a = make_float2(sH * (za[m].x + zam[m].x), sH * (za[m].y - zam[m].y));
-            const float2 g1b = make_float2(sH * (za[m].y + zam[m].y), sH * (zam[m].x - za[m].x));
-            const float2 g2a = make_float2(sH * (zb[m].x + zbm[m].x), sH * (zb[m].y - zbm[m].y));
-            const float2 g2b = make_float2(sH * (zb[m].y + zbm[m].y), sH * (zbm[m].x - zb[m].x));
-            if (ka == 0) {
+            // rows ya (g1) and yb (g2) of the two columns: g_a = (z + conj zm) / 2, g_b = (z - conj zm) / (2i)
+            const float2 g1a = __fmul2_rn(__fadd2_rn(za[m], make_float2(zam[m].x, -zam[m].y)), sH2);
+            const float2 g1b = __fmul2_rn(__fadd2_rn(make_float2(za[m].y, -za[m].x), make_float2(zam[m].y, zam[m].x)), sH2);
+            const float2 g2a = __fmul2_rn(__fadd2_rn(zb[m], make_float2(zbm[m].x, -zbm[m].y)), sH2);
+            const float2 g2b = __fmul2_rn(__fadd2_rn(make_float2(zb[m].y, -zb[m].x), make_float2(zbm[m].y, zbm[m].x)), sH2);
+            if (m == 0 && ka0 == 0) {
                 z[pad16(0)] = make_float2(g1a.x, g2a.x);
                 z[pad16(HX)] = make_float2(sA * nya, sA * nyb);
             } else {
-                z[pad16(ka)] = make_float2(g1a.x - g2a.y, g1a.y + g2a.x);
-                z[pad16(NX - ka)] = make_float2(g1a.x + g2a.y, g2a.x - g1a.y);
+                zka[PS2 * m] = __fadd2_rn(g1a, make_float2(-g2a.y, g2a.x));
+                zma[-PS2 * m] = __fadd2_rn(make_float2(g1a.x, -g1a.y), make_float2(g2a.y, g2a.x));
             }
-            z[pad16(kb)] = make_float2(g1b.x - g2b.y, g1b.y + g2b.x);
-            z[pad16(NX - kb)] = make_float2(g1b.x + g2b.y, g2b.x - g1b.y);
+            zkb[PS2 * m] = __fadd2_rn(g1b, make_float2(-g2b.y, g2b.x));
+            zmb[-PS2 * m] = __fadd2_rn(make_float2(g1b.x, -g1b.y), make_float2(g2b.y, g2b.x));
         }
         __syncthreads();
     }

@@ -68,6 +68,8 @@ int b4d_set_batch_frames(b4d_ctx* ctx, int64_t frames);
  * column pass on two more, through ring_slots (1..8) ring slots of intermediates per lane, so that every intermediate
  * is consumed from L2 instead of HBM while the lanes fill one another's launch gaps.  keep = cache-policy bits of the
  * intermediates (1 stores stay in L2, 2 loads keep normal priority, 4 the column pass discards its consumed tiles).
+ * The kernels honour `keep` only in builds made with -DB4D_KEEP_POLICY=1 (the run-time switch costs issue slots in every
+ * memory access of the default schedule); the default build streams the intermediates both ways.
  * sub_frames = 0: whole batches, one kernel after the other.  use_graphs != 0: the second call with identical
  * arguments captures the batch's launches in a CUDA graph and later calls replay it (the host cannot issue ~10
  * launches per 1 - 2 frames as fast as the GPU runs them); calls bracketed by b4d_profile_begin/end always launch
