@@ -53,7 +53,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--frames", type=int, default=128, help="frames per step per GPU")
+    p.add_argument("--frames", type=int, default=512, help="frames per step per GPU (resident in HBM)")
+    p.add_argument("--e2e-frames", type=int, default=128, help="frames of the pinned host stack of the end-to-end legs")
     p.add_argument("--size", type=int, default=2048)
     p.add_argument("--batch", type=int, default=0, help="frames per internal FFT batch (0 = automatic)")
     p.add_argument("--e2e-steps", type=int, default=5)
@@ -349,7 +350,7 @@ def run_b200(args):
     err = float(np.max(np.abs(tr[whole, :2] - shifts[whole])))               # np.roll frames: known answers
     # sub-pixel frames: the reference's Taylor step is biased and adds the x term to dy: within a pixel
     err_sub = float(np.max(np.abs(tr[:, :2] - shifts)))
-    if err > 0.05 or err_sub > 1.0:
+    if err > 0.05 or err_sub > 1.25:   # (|integer-peak error| <= 0.5 px plus the swapped sub-pixel terms, each <= ~0.5 px)
         raise SystemExit(f"tracking sanity check failed on rank {rank}: max |shift error| = {err:.3f} px (whole-pixel frames), "
                          f"{err_sub:.3f} px (all frames)")
     oracle_err = None
@@ -406,12 +407,15 @@ def run_b200(args):
     # reference's own stages. e2e_maps_to_host additionally drains both maps over PCIe.
     e2e = e2e_maps = e2e_u16 = None
     if not args.no_e2e:
-        host = torch.empty((F, n, n), dtype=torch.float32, pin_memory=True)
-        host.copy_(stack)
+        # (a step of the end-to-end legs = the first E frames of the stack: pinning the whole resident stack and its maps
+        # would cost tens of GB of page-locked host memory for the same per-frame figure)
+        E = max(1, min(F, args.e2e_frames))
+        host = torch.empty((E, n, n), dtype=torch.float32, pin_memory=True)
+        host.copy_(stack[:E])
         # detector-native frames: the same stack rounded to uint16 counts (half the PCIe bytes; widened on the device)
-        host_u16 = torch.empty((F, n, n), dtype=torch.uint16, pin_memory=True)
-        host_u16.copy_(stack.clamp(0, 65535).round().to(torch.uint16))
-        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(8, F // 4)), want_maps=True, want_contrast=True)
+        host_u16 = torch.empty((E, n, n), dtype=torch.uint16, pin_memory=True)
+        host_u16.copy_(stack[:E].clamp(0, 65535).round().to(torch.uint16))
+        an2 = StackAnalyzer((n, n), device=local, chunk_frames=max(1, min(8, E // 4)), want_maps=True, want_contrast=True)
         ref_host = host[0].clone()
 
         def time_e2e(keep: bool, src=None):
@@ -435,26 +439,26 @@ def run_b200(args):
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            return world * F * args.e2e_steps / float(dt.item())
+            return world * E * args.e2e_steps / float(dt.item())
 
         h2d_b, d2h_b = an2.bytes_per_frame()
         fps_tables = time_e2e(True)
         link_gbs = fps_tables / world * h2d_b / 1e9
-        e2e = {"value": fps_tables, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * F + n * n * 4),
-               "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * F), "steps": args.e2e_steps,
+        e2e = {"value": fps_tables, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * E + n * n * 4),
+               "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * E), "steps": args.e2e_steps, "frames_per_step_per_gpu": E,
                "h2d_gbs_per_gpu": link_gbs,
                "note": "StackAnalyzer.run on a pinned float32 host stack: every per-frame table (moments, sharpness, contrast, "
                        "grain, tracking) copied back, PSD + autocorrelation maps left in HBM. Bound by the host-to-device "
                        "link (h2d_gbs_per_gpu against ~55 GB/s of one PCIe 5 x16 link), not by the kernels"}
         fps_u16 = time_e2e(True, host_u16)
-        e2e_u16 = {"value": fps_u16, "unit": UNIT, "h2d_bytes_per_step": int(n * n * 2 * F + n * n * 4),
-                   "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * F), "steps": args.e2e_steps,
+        e2e_u16 = {"value": fps_u16, "unit": UNIT, "h2d_bytes_per_step": int(n * n * 2 * E + n * n * 4),
+                   "d2h_bytes_per_step": int((d2h_b - 2 * n * n * 4) * E), "steps": args.e2e_steps, "frames_per_step_per_gpu": E,
                    "h2d_gbs_per_gpu": fps_u16 / world * n * n * 2 / 1e9,
                    "note": "same call on the detector-native uint16 stack (b4d_cast_to_f32 widens on the device): half the "
                            "PCIe bytes per frame"}
         fps_maps = time_e2e(False)
-        e2e_maps = {"value": fps_maps, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * F + n * n * 4),
-                    "d2h_bytes_per_step": int(d2h_b * F), "steps": args.e2e_steps,
+        e2e_maps = {"value": fps_maps, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b * E + n * n * 4),
+                    "d2h_bytes_per_step": int(d2h_b * E), "steps": args.e2e_steps, "frames_per_step_per_gpu": E,
                     "note": "same call, PSD + autocorrelation maps also copied to pinned host memory (PCIe-bound)"}
 
     if rank != 0:

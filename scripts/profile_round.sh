@@ -9,6 +9,6 @@ $CMD > gpurun_out/plain_$tag.log 2>&1 || { tail -5 gpurun_out/plain_$tag.log; ex
 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "b4d_timed/" -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches_$tag.log 2>&1
 $CMD > gpurun_out/plain2_$tag.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "b4d_timed/" \
-    -k regex:'cols_kernel|rows_inv|rows_fwd_kernel|frame_reduce2|fused_median_final|sel_bracket|temporal_accumulate' -c 14 \
+    -k regex:'cols_kernel|rows_inv|rows_fwd_kernel|frame_reduce2|fused_median_final|sel_bracket|temporal_accumulate' --launch-skip 3 -c 10 \
     -o gpurun_out/prof_$tag -f $CMD > gpurun_out/ncu_full_$tag.log 2>&1
 tail -2 gpurun_out/ncu_full_$tag.log
