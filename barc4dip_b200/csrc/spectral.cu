@@ -642,16 +642,21 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
     if (tid == 0) s_idx = 0xffffffffu;
     if (MODE == 2 && tid < 2) s_cen[tid] = 0u;
 
-    // ---- gather: each thread fetches Ga[k], Gb[k] for 8 values of k and writes Z[k] and Z[NX-k]
+    // ---- inputs of the transform, natural mapping (f = tid / TPF, j = tid % TPF): thread j wants Z[j + m TPF], m = 0..15.
+    //      Z[k] = Ga[k] + i Gb[k] for k < NX/2 and Z[NX - k] = conj(Ga[k]) + i conj(Gb[k]). The thread fetches the pairs
+    //      k = j + m TPF, m = 0..7: their Z[k] ARE its slots 0..7 and stay in registers; their Z[NX - k] are slots 8..15 of
+    //      thread TPF - j of the same transform and cross through shared memory -- half of what a gather of all sixteen
+    //      slots would move, and only the transform's own threads meet at the barrier.
+    const int f = tid / TPF, j = tid % TPF;
+    float2* z = sm + f * FS;
+    float2 x[16];
     {
-        const int c = lane & 7, fl = lane >> 3, jt = warp % WPG, grp = warp / WPG;
-        const int f = grp * 4 + fl, jg = jt * 8 + c;
         const int ya = y0 + 2 * f;
         float2 ga[8], gb[8];
         {
-            // k = jg + m TPF lives in tile jg/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads
+            // k = j + m TPF lives in tile j/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads
             const size_t tstride = (size_t)(TPF / TC) * NY * TC;
-            const float2* pa = Ia + ((size_t)(jg / TC) * NY + ya) * TC + (jg % TC);
+            const float2* pa = Ia + ((size_t)(j / TC) * NY + ya) * TC + (j % TC);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 ga[m] = ld_inter(pa + m * tstride, a.keep);
@@ -670,52 +675,45 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Ia + (size_t)tn * NY * HX + ((size_t)q * NY + (size_t)blkn * RPC) * TC + (size_t)l * 16));
             }
         }
-        if (warp == 0) {
-            double sc = a.scaleA;
-            if (a.normA) {
+        float sA = (float)a.scaleA;
+        if (a.normA) {
+            if (warp == 0) {
                 // fixed-order reduction of the per-tile partials: lane-strided chunks, then a shuffle tree
                 double part = 0.0;
                 for (int i = lane; i < a.n_normA; i += 32) part += a.normA[(size_t)t * a.n_normA + i];
                 part = warp_sum(part);
-                sc = part > 0.0 ? a.norm_mult / part : a.scaleA;
+                if (lane == 0) s_scale = (float)(part > 0.0 ? a.norm_mult / part : a.scaleA);
             }
-            if (lane == 0) s_scale = (float)sc;
+            __syncthreads();
+            sA = s_scale;
         }
-        __syncthreads();
-        const float sA = s_scale;
         const float2 sA2 = make_float2(sA, sA);
-        float2* z = sm + f * FS;
-        // Z[k] = Ga + i Gb and Z[NX - k] = conj(Ga) + i conj(Gb), k = jg + m TPF. With TPF a multiple of 16 both padded
-        // indices are a per-thread base plus a compile-time multiple of m: pad16(k) = pad16(jg) + m (TPF + TPF / 16) and
-        // pad16(NX - k) = padded_len(NX) - jg - ceil(jg / 16) - m (TPF + TPF / 16).
+        // With TPF a multiple of 16 the padded index of Z[NX - k] is a per-thread base plus a compile-time multiple of m:
+        // pad16(NX - j - m TPF) = padded_len(NX) - j - ceil(j / 16) - m (TPF + TPF / 16).
         constexpr bool LIN = (TPF % 16) == 0;
         constexpr int PS = TPF + TPF / 16;
-        float2* zk = z + pad16(jg);
-        float2* zm = z + (padded_len(NX) - jg - ((jg + 15) >> 4));
+        float2* zm = z + (padded_len(NX) - j - ((j + 15) >> 4));
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int k = jg + m * TPF;
             const float2 g1 = __fmul2_rn(ga[m], sA2), g2 = __fmul2_rn(gb[m], sA2);
-            if (m == 0 && k == 0) {
-                // packed slot: (DC, Nyquist), both real
-                z[pad16(0)] = make_float2(g1.x, g2.x);
-                z[pad16(HX)] = make_float2(g1.y, g2.y);
+            const float2 A = __fadd2_rn(g1, make_float2(-g2.y, g2.x));
+            const float2 B = __fadd2_rn(make_float2(g1.x, -g1.y), make_float2(g2.y, g2.x));
+            if (m == 0) {
+                // pair 0 of thread 0 is the packed slot (DC, Nyquist), both real: Z[0] and Z[NX/2]
+                x[0] = j == 0 ? make_float2(g1.x, g2.x) : A;
+                if (j == 0) z[pad16(HX)] = make_float2(g1.y, g2.y);
+                else if (LIN) zm[0] = B;
+                else z[pad16(NX - j)] = B;
             } else {
-                const float2 A = __fadd2_rn(g1, make_float2(-g2.y, g2.x));
-                const float2 B = __fadd2_rn(make_float2(g1.x, -g1.y), make_float2(g2.y, g2.x));
-                if (LIN) { zk[PS * m] = A; zm[-PS * m] = B; }
-                else { z[pad16(k)] = A; z[pad16(NX - k)] = B; }
+                x[m] = A;
+                if (LIN) zm[-PS * m] = B;
+                else z[pad16(NX - j - m * TPF)] = B;
             }
         }
-        __syncthreads();
-    }
-
-    // ---- transform (natural mapping), outputs stay in registers
-    const int f = tid / TPF, j = tid % TPF;
-    float2* z = sm + f * FS;
-    float2 x[16];
+        fft_sync<NX, (NX >= 1024), 1>(f);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
+        for (int m = 8; m < 16; ++m) x[m] = z[pad16(j + m * TPF)];
+    }
     fft_regs<NX, +1, 1, (NX >= 1024)>(x, j, z, a.tw, f);
 
     // ---- stores: real part -> row ya, imaginary part -> row ya + 1. Slot s holds x-position j + TPF s, i.e. shifted
