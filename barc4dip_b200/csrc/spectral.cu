@@ -189,31 +189,55 @@ __global__ void __launch_bounds__(512) rows_fwd_kernel(RowsFwdArgs a) {
         const double w1 = warp_sum((double)s1.x + (double)s1.y), w2 = warp_sum((double)s2.x + (double)s2.y);
         if ((tid & 31) == 0) { s_mom[tid >> 5][0] = w1; s_mom[tid >> 5][1] = w2; }
     }
-    fft_regs_to_smem<NX, -1, 1, (NX >= 1024)>(x, j, sm + f * FS, a.tw, f);
-    if (a.mom && tid < 2) {                           // (fft_regs_to_smem ends with a __syncthreads)
+    float2* z = sm + f * FS;
+    fft_regs<NX, -1, 1, (NX >= 1024)>(x, j, z, a.tw, f);
+    // Split Z = FFT(a + i b) into the half spectra of rows a and b: H_a[k] = (Z[k] + conj Z[NX - k]) / 2, H_b[k] = (Z[k] -
+    // conj Z[NX - k]) / (2i), k < NX/2. Thread j holds Z[j + s TPF], s = 0..15: its slots 0..7 ARE the Z[k] of its own
+    // eight outputs and stay in registers; the Z[NX - k] are slots 8..15 of thread TPF - j of the same transform, so only
+    // the upper halves cross shared memory (8 stores + 8 loads per thread, barriers of the transform's own threads).
+    fft_sync<NX, (NX >= 1024), 1>(f);                 // the other threads of the transform are done reading their exchanges
+    constexpr bool LIN = (TPF % 16) == 0;
+    constexpr int PS = TPF + TPF / 16;
+    if (LIN) {
+        float2* w = z + pad16(j);
+#pragma unroll
+        for (int s2 = 8; s2 < 16; ++s2) w[PS * s2] = x[s2];
+    } else {
+#pragma unroll
+        for (int s2 = 8; s2 < 16; ++s2) z[pad16(j + s2 * TPF)] = x[s2];
+    }
+    if (a.mom) __syncthreads(); else fft_sync<NX, (NX >= 1024), 1>(f);
+    if (a.mom && tid < 2) {                           // (the barrier above made every warp's partial sums visible)
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < 16; ++w) v += s_mom[w][tid];
         a.mom[((size_t)t * gridDim.x + blockIdx.x) * 2 + tid] = v;
     }
-
-    // split Z = FFT(a + i b) into the half spectra of a and b; blocked store
-    float2* Hf = a.H + (size_t)t * a.ny * (NX / 2);
-    for (int idx = tid; idx < ROWS * (NX / 2); idx += 512) {
-        const int tile = idx / (ROWS * TC), rem = idx % (ROWS * TC);
-        const int r = rem / TC, c = rem % TC, k = tile * TC + c, p = r >> 1;
-        const float2* z = sm + p * FS;
-        const float2 Z = z[pad16(k)];
-        float2 v;
-        if (k == 0) {
-            const float2 Zh = z[pad16(NX / 2)];
-            v = (r & 1) ? make_float2(Z.y, Zh.y) : make_float2(Z.x, Zh.x);
-        } else {
-            const float2 Zm = z[pad16(NX - k)];
-            v = (r & 1) ? make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x))
-                        : make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
+    {
+        // pad16(NX - j - s TPF) = padded_len(NX) - j - ceil(j / 16) - s (TPF + TPF / 16) when TPF is a multiple of 16
+        const float2* zm = z + (padded_len(NX) - j - ((j + 15) >> 4));
+        // blocked store: k = j + s TPF lives in tile j/8 + s TPF/8, rows y0 + 2f (a) and y0 + 2f + 1 (b) are 8 elements apart
+        float2* Hf = a.H + (size_t)t * a.ny * (NX / 2) + ((size_t)(j / TC) * a.ny + y0 + 2 * f) * TC + (j % TC);
+        const size_t tstride = (size_t)(TPF / TC) * a.ny * TC;
+        const float2 hh = make_float2(0.5f, 0.5f);
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) {
+            const float2 Z = x[s2];
+            float2 va, vb;
+            if (s2 == 0) {
+                // thread 0: k = 0 carries the two real samples DC and Nyquist (Z[NX/2] is its own slot 8, just written)
+                const float2 Zm = j == 0 ? z[pad16(NX / 2)] : (LIN ? zm[0] : z[pad16(NX - j)]);
+                va = __fmul2_rn(__fadd2_rn(Z, make_float2(Zm.x, -Zm.y)), hh);
+                vb = __fmul2_rn(__fadd2_rn(make_float2(Z.y, -Z.x), make_float2(Zm.y, Zm.x)), hh);
+                if (j == 0) { va = make_float2(Z.x, Zm.x); vb = make_float2(Z.y, Zm.y); }
+            } else {
+                const float2 Zm = LIN ? zm[-PS * s2] : z[pad16(NX - j - s2 * TPF)];
+                va = __fmul2_rn(__fadd2_rn(Z, make_float2(Zm.x, -Zm.y)), hh);
+                vb = __fmul2_rn(__fadd2_rn(make_float2(Z.y, -Z.x), make_float2(Zm.y, Zm.x)), hh);
+            }
+            st_inter(Hf + s2 * tstride, va, a.keep);  // (streaming unless the consumer follows closely)
+            st_inter(Hf + s2 * tstride + TC, vb, a.keep);
         }
-        st_inter(Hf + ((size_t)tile * a.ny + y0 + r) * TC + c, v, a.keep);   // (streaming unless the consumer follows closely)
     }
 }
 
