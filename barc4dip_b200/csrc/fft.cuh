@@ -206,10 +206,31 @@ __device__ __forceinline__ void apply_twiddle_powers(float2* x, float2 w1, float
     }
 }
 
+// Base powers (w, w^2, w^4, w^8) of a stage's twiddle from the table. DERIVE: only (w, w^2) are fetched -- one LDG.128 --
+// and w^4, w^8 come from squaring (two packed instructions each, and only the powers radix R needs): a table load costs
+// the load/store pipe four wavefronts per warp, and the six of a 2048-point transform were a sixth of the pass's exchange
+// traffic. The squared powers carry ~3 (w^4) and ~7 ulp (w^8) instead of 0.5, which is immaterial for the inverse
+// transforms (their inputs are whitened unit phasors or |F|^2, their outputs are compared at 1e-5 of the peak) but not for
+// the forward ones: on noise-free band-limited frames the whitening turns the rounding noise of the forward transform in
+// the empty bins into unit phasors, and the tracker's sub-pixel answer on such a frame moved by 0.1 px with derived
+// forward twiddles (the reference's own float32 / float64 paths differ by 0.03 px there). Hence: derived powers in the
+// inverse transforms (DIR > 0), table powers in the forward ones. Measured: all transforms derived 6.645 -> 6.55 ms per
+// 128 frames.
+#ifndef B4D_TW_DERIVE
+#define B4D_TW_DERIVE 1           // 0: never derive, 1: inverse transforms only, 3: every transform (experiments)
+#endif
+template <int R, bool DERIVE>
 __device__ __forceinline__ void ldg_tw4(const float2* p, float2& a, float2& b, float2& c, float2& d) {
     const float4 u = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    a = make_float2(u.x, u.y); b = make_float2(u.z, u.w); c = make_float2(v.x, v.y); d = make_float2(v.z, v.w);
+    a = make_float2(u.x, u.y); b = make_float2(u.z, u.w);
+    if (DERIVE) {
+        c = d = make_float2(0.f, 0.f);
+        if (R > 4) c = cmulv<1>(b, b);
+        if (R > 8) d = cmulv<1>(c, c);
+    } else {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        c = make_float2(v.x, v.y); d = make_float2(v.z, v.w);
+    }
 }
 
 // Barrier of the threads that share an exchange buffer. GROUP = 0: the whole CTA (__syncthreads). GROUP = 1: the N/16
@@ -231,6 +252,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
     using P = Plan<N>;
     constexpr int T = N / 16;
     constexpr bool FAST = (T % 16) == 0;
+    constexpr bool TWD = (B4D_TW_DERIVE == 3) || (B4D_TW_DERIVE == 1 && DIR > 0);
     constexpr int R2 = P::R2, NB2 = 16 / R2;
     constexpr bool HAS3 = P::R3 > 1;
     constexpr int R3 = HAS3 ? P::R3 : 2, NB3 = 16 / R3, LS3 = 16 * R2;
@@ -250,7 +272,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
     for (int b = 0; b < NB2; ++b) {
         const int k = FAST ? (j & 15) : ((j + b * T) & 15);
         if (FAST && b > 0) { b1[b] = b1[0]; b2[b] = b2[0]; b4[b] = b4[0]; b8[b] = b8[0]; }
-        else ldg_tw4(twb + 4 * k, b1[b], b2[b], b4[b], b8[b]);
+        else ldg_tw4<R2, TWD>(twb + 4 * k, b1[b], b2[b], b4[b], b8[b]);
     }
     fft_sync<N, GROUP, BATCH>(group);
 
@@ -302,7 +324,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
         }
         float2 c1[NB3], c2[NB3], c4[NB3], c8[NB3];
 #pragma unroll
-        for (int b = 0; b < NB3; ++b) ldg_tw4(twb + 64 + 4 * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
+        for (int b = 0; b < NB3; ++b) ldg_tw4<R3, TWD>(twb + 64 + 4 * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
         fft_sync<N, GROUP, BATCH>(group);
 
         // ---- stage 3: radix R3, LS = 16 R2 = N / R3: k = v = j + b T
