@@ -165,8 +165,11 @@ template <> struct Plan<128>  { static constexpr int R1 = 16, R2 = 8,  R3 = 1; }
 // Twiddles: per stage the thread loads the base powers w^1, w^2, w^4 (, w^8) of its own k from a small table
 //         (two LDG.128 issued BEFORE the exchange barrier, while x[] is dead) and forms the other powers by
 //         at most two complex multiplications (error <= 7 ulp).
-// Table layout (float2): [0, 64)            stage 2: k in [0,16)   -> (w1, w2, w4, w8), base 16*R2
-//                        [64, 64 + 4*LS3)   stage 3: k in [0,LS3)  -> (w1, w2, w4, w8 or 0),  base N
+// Table layout (float2): [0, 32)  stage 2: k in [0,16) -> (w1, w2);  [32, 64)  -> (w4, w8), base 16*R2
+//                        [64, 64 + 2*LS3)  stage 3: k in [0,LS3) -> (w1, w2);  [64 + 2*LS3, ...) -> (w4, w8), or bare w4 for a radix <= 8, base N
+//         (two arrays per stage: the 16-byte fetches of a warp's consecutive k are then contiguous -- 4 wavefronts of
+//          the load/store pipe per fetch instead of the 8 an interleaved (w1, w2, w4, w8) record costs; w4 alone is an
+//          8-byte fetch when the radix needs no w8)
 // Synchronisation: a __syncthreads() is issued on entry (z may still be read by a previous user); on return
 //         other threads may still be reading z, so the caller synchronises before writing z itself.
 // ================================================================================================
@@ -220,16 +223,18 @@ __device__ __forceinline__ void apply_twiddle_powers(float2* x, float2 w1, float
 #define B4D_TW_DERIVE 1           // 0: never derive, 1: inverse transforms only, 3: every transform (experiments)
 #endif
 template <int R, bool DERIVE>
-__device__ __forceinline__ void ldg_tw4(const float2* p, float2& a, float2& b, float2& c, float2& d) {
-    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+__device__ __forceinline__ void ldg_tw4(const float2* pa, const float2* pb, float2& a, float2& b, float2& c, float2& d) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(pa));
     a = make_float2(u.x, u.y); b = make_float2(u.z, u.w);
+    c = d = make_float2(0.f, 0.f);
     if (DERIVE) {
-        c = d = make_float2(0.f, 0.f);
         if (R > 4) c = cmulv<1>(b, b);
         if (R > 8) d = cmulv<1>(c, c);
-    } else {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    } else if (R > 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pb));
         c = make_float2(v.x, v.y); d = make_float2(v.z, v.w);
+    } else if (R > 4) {
+        c = __ldg(pb);
     }
 }
 
@@ -272,7 +277,7 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
     for (int b = 0; b < NB2; ++b) {
         const int k = FAST ? (j & 15) : ((j + b * T) & 15);
         if (FAST && b > 0) { b1[b] = b1[0]; b2[b] = b2[0]; b4[b] = b4[0]; b8[b] = b8[0]; }
-        else ldg_tw4<R2, TWD>(twb + 4 * k, b1[b], b2[b], b4[b], b8[b]);
+        else ldg_tw4<R2, TWD>(twb + 2 * k, twb + 32 + (R2 > 8 ? 2 : 1) * k, b1[b], b2[b], b4[b], b8[b]);
     }
     fft_sync<N, GROUP, BATCH>(group);
 
@@ -324,7 +329,8 @@ __device__ __forceinline__ void fft_regs(float2* x, int j, float2* __restrict__ 
         }
         float2 c1[NB3], c2[NB3], c4[NB3], c8[NB3];
 #pragma unroll
-        for (int b = 0; b < NB3; ++b) ldg_tw4<R3, TWD>(twb + 64 + 4 * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
+        for (int b = 0; b < NB3; ++b)
+            ldg_tw4<R3, TWD>(twb + 64 + 2 * (j + b * T), twb + 64 + 2 * LS3 + (R3 > 8 ? 2 : 1) * (j + b * T), c1[b], c2[b], c4[b], c8[b]);
         fft_sync<N, GROUP, BATCH>(group);
 
         // ---- stage 3: radix R3, LS = 16 R2 = N / R3: k = v = j + b T

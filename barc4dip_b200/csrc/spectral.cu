@@ -62,20 +62,26 @@ constexpr int NTHETA = 1130;   // int(2*pi*180), maths/radial.py:150
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 inline bool fft_size_ok(int n) { return n >= 128 && n <= 2048 && (n & (n - 1)) == 0; }
 
-// base powers (w, w^2, w^4, w^8) per stage and k, see fft.cuh (v2 core)
+// base powers (w, w^2, w^4, w^8) per stage and k, split into a (w, w^2) array and a (w^4, w^8) array per stage so that a
+// warp's 16-byte fetches are contiguous (layout in fft.cuh, v2 core)
 template <int N>
 void fill_twiddle_bases(std::vector<float2>& h) {
     using P = Plan<N>;
     h.assign(twiddle_base_count<N>(), make_float2(0.f, 0.f));
-    auto put = [&](size_t at, int k, double base, int npow) {
+    // (the second array holds (w^4, w^8) records for a radix-16 stage and bare w^4 for a radix-8 one: contiguous either way)
+    auto put = [&](size_t a_at, size_t b_at, int k, double base, int radix) {
+        const int npow = radix > 8 ? 4 : 3, rec = radix > 8 ? 2 : 1;
         for (int p = 0; p < npow; ++p) {
             const double a = -2.0 * 3.14159265358979323846 * (double)(1 << p) * (double)k / base;
-            h[at + p] = make_float2((float)cos(a), (float)sin(a));
+            const size_t at = p < 2 ? a_at + 2 * (size_t)k + p : b_at + (size_t)rec * k + (p - 2);
+            h[at] = make_float2((float)cos(a), (float)sin(a));
         }
     };
-    for (int k = 0; k < 16; ++k) put(4 * (size_t)k, k, 16.0 * P::R2, 4);
-    if (P::R3 > 1)
-        for (int k = 0; k < 16 * P::R2; ++k) put(64 + 4 * (size_t)k, k, (double)N, P::R3 > 8 ? 4 : 3);
+    for (int k = 0; k < 16; ++k) put(0, 32, k, 16.0 * P::R2, P::R2);
+    if (P::R3 > 1) {
+        const int ls3 = 16 * P::R2;
+        for (int k = 0; k < ls3; ++k) put(64, 64 + 2 * (size_t)ls3, k, (double)N, P::R3);
+    }
 }
 
 int get_twiddle_bases(b4d_ctx* ctx, int n, const float2** out) {
