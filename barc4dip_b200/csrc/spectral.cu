@@ -270,7 +270,7 @@ struct ColsArgs {
     float2* i2_ac_nyq;          // (T, ny) inverse-along-y of the Nyquist column's |F|^2 (packed variant only)
     double* ac_partials;        // (T, ntiles) sum of the full-spectrum |F|^2 owned by the tile
     // product branch: G = F * R (optionally whitened), inverse along y -> i2_pc
-    float2* i2_pc;
+    float2* i2_pc;              // blocked, row pairs interleaved ([kx/8][y/2][kx%8][y%2], see cols_body)
     const float2* R;            // blocked, shared by all frames (ref_stride 0) or per frame
     const float2* Rnyq;
     size_t r_stride, rnyq_stride;
@@ -556,7 +556,10 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     // ---- inverse along y of the product ---------------------------------------------------------
     if (PC) {
         fft_regs<NY, +1, CW, 0, COLS_CM>(x, j, A + c, a.tw);
-        float2* o = a.i2_pc + g0;
+        // rows 2p and 2p + 1 of a column sit next to each other in this intermediate ([kx/8][y/2][kx%8][y%2]): the row
+        // pass, which transforms such a pair in one complex transform, fetches both with one 16-byte load and every
+        // line it touches whole. (ky = j + s T with T even: the pair interleave moves the thread's base only.)
+        float2* o = a.i2_pc + (size_t)t * NY * hx + (size_t)(kx / TC) * NY * TC + ((size_t)(j >> 1) * TC + (kx % TC)) * 2 + (j & 1);
 #pragma unroll
         for (int s = 0; s < 16; ++s) st_inter(o + s * GS, x[s], a.keep);
     }
@@ -575,7 +578,8 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[j2 * CW + c2 + s * NT], Bp[j2 * CW + c2 + CH + s * NT]);
             fft_regs<NY, +1, CH, 2, COLS_CM>(x, j2, A + c2, a.tw);
             const int pc = tile * CH + c2;
-            float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + (size_t)j2 * TC + (pc % TC);
+            // (row pairs interleaved like i2_pc: [pc/8][y/2][pc%8][y%2])
+            float2* o = a.i2_ac + (size_t)t * NY * (hx / 2) + (size_t)(pc / TC) * NY * TC + ((size_t)(j2 >> 1) * TC + (pc % TC)) * 2 + (j2 & 1);
 #pragma unroll
             for (int s = 0; s < 16; ++s) st_inter(o + s * GS, x[s], a.keep);
         } else if (TILE0 && tid < NTH + (T < 32 ? 32 : T)) {
@@ -613,7 +617,7 @@ __device__ __forceinline__ void best_update(ArgBest& b, float v, unsigned idx) {
 }
 
 struct RowsInvArgs {
-    const float2* Ia;       // blocked intermediate (per frame ny*nx/2)
+    const float2* Ia;       // blocked intermediate (per frame ny*nx/2), row pairs interleaved: [kx/8][y/2][kx%8][y%2]
     const float2* tw;
     int ny;
     float* outA;            // shifted real output: (T, ny, nx) full map, or compact rows (mag_mode 1); nullable
@@ -684,13 +688,15 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
         const int ya = y0 + 2 * f;
         float2 ga[8], gb[8];
         {
-            // k = j + m TPF lives in tile j/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads
+            // k = j + m TPF lives in tile j/8 + m TPF/8: a fixed stride of (TPF/8) tiles between the thread's loads; rows
+            // ya and ya + 1 of a column are adjacent (pair-interleaved layout written by the column pass): one 16-byte load
             const size_t tstride = (size_t)(TPF / TC) * NY * TC;
-            const float2* pa = Ia + ((size_t)(j / TC) * NY + ya) * TC + (j % TC);
+            const float2* pa = Ia + (((size_t)(j / TC) * (NY / 2) + (ya >> 1)) * TC + (j % TC)) * 2;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                ga[m] = ld_inter(pa + m * tstride, a.keep);
-                gb[m] = ld_inter(pa + m * tstride + TC, a.keep);
+                const float4 g = __ldcs(reinterpret_cast<const float4*>(pa + m * tstride));
+                ga[m] = make_float2(g.x, g.y);
+                gb[m] = make_float2(g.z, g.w);
             }
         }
         // the rows of the CTA that takes this SM next (pf_dist CTAs ahead in launch order): RPC rows x 64 bytes in each of
@@ -841,7 +847,7 @@ __global__ void __launch_bounds__(512, 2) rows_inv_kernel(RowsInvArgs a) {
 // The autocorrelation is point symmetric, ac(-y, -x) = ac(y, x): only the rows y = 0 .. ny/2 are transformed (two rows
 // per complex transform, as in rows_inv_kernel) and every row is stored twice, as it is and mirrored.
 struct RowsInvAcArgs {
-    const float2* Iz;       // packed blocked intermediate (T, nx/4/TC, ny, TC)
+    const float2* Iz;       // packed blocked intermediate (T, nx/4/TC, ny/2, TC, 2): row pairs interleaved
     const float2* Inyq;     // (T, ny) inverse-along-y of the Nyquist column
     const float2* tw;
     int ny;
@@ -882,14 +888,17 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
         const int ma = (NY - ya) & (NY - 1), mb = NY - yb;
         float2 za[4], zam[4], zb[4], zbm[4];
         {
+            // element (y, c) of a tile sits at ((y / 2) * 8 + c) * 2 + y % 2 (row pairs interleaved by the column pass): rows
+            // ya (even) and yb = ya + 1 come with one 16-byte load; their mirrors -ya (even) and -yb (odd) belong to two pairs
             const size_t tstride = (size_t)(TPF / TC) * NY * TC;
-            const float2* p = Iz + (size_t)(jg / TC) * NY * TC + (jg % TC);
+            const float2* p = Iz + (size_t)(jg / TC) * NY * TC + (size_t)(jg % TC) * 2;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                za[m] = ld_inter(p + m * tstride + (size_t)ya * TC, a.keep);
-                zam[m] = ld_inter(p + m * tstride + (size_t)ma * TC, a.keep);
-                zb[m] = ld_inter(p + m * tstride + (size_t)yb * TC, a.keep);
-                zbm[m] = ld_inter(p + m * tstride + (size_t)mb * TC, a.keep);
+                const float4 g = __ldcs(reinterpret_cast<const float4*>(p + m * tstride + (size_t)(ya >> 1) * (2 * TC)));
+                za[m] = make_float2(g.x, g.y);
+                zb[m] = make_float2(g.z, g.w);
+                zam[m] = ld_inter(p + m * tstride + (size_t)(ma >> 1) * (2 * TC), a.keep);
+                zbm[m] = ld_inter(p + m * tstride + (size_t)(mb >> 1) * (2 * TC) + 1, a.keep);
             }
         }
         float nya = 0.f, nyb = 0.f;
