@@ -362,6 +362,9 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
     const int64_t t = blockIdx.y;
     const int nx = a.nx, hx = nx / 2, kx = tile * CW + c;
     const bool nyq_owner = TILE0 && c == 0;           // TILE0: the CTA owns column 0
+    // |F|^2 copy for the packed inverse transforms: the columns c and c + CW/2 that share a transform are adjacent
+    // ([ky][c % (CW/2)][c / (CW/2)]), so that the transform's threads fetch a pair with one conflict-free 8-byte load
+    const int bpw = j * CW + ((c % (CW / 2)) << 1) + c / (CW / 2);
     // element s of this thread lives at g0 + s*GS inside a frame's blocked half spectrum
     const size_t g0 = (size_t)t * NY * hx + (size_t)(kx / TC) * NY * TC + (size_t)j * TC + (kx % TC);
 
@@ -469,7 +472,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             if (AC) {
                 if (a.ac_zero_dc && nyq_owner && ky == 0) Pa = 0.f;
                 acsum += fmaf(wgt, Pa, Pn);
-                Bp[tid + s * NT] = Pa;
+                Bp[bpw + s * NT] = Pa;
                 if (nyq_owner) Pns[ky] = Pn;
             }
         }
@@ -575,7 +578,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         if (tid < NTH) {
             const int c2 = tid % CH, j2 = tid / CH;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) x[s] = make_float2(Bp[j2 * CW + c2 + s * NT], Bp[j2 * CW + c2 + CH + s * NT]);
+            for (int s = 0; s < 16; ++s) x[s] = *reinterpret_cast<const float2*>(Bp + j2 * CW + 2 * c2 + s * NT);
             fft_regs<NY, +1, CH, 2, COLS_CM>(x, j2, A + c2, a.tw);
             const int pc = tile * CH + c2;
             // (row pairs interleaved like i2_pc: [pc/8][y/2][pc%8][y%2])
@@ -867,7 +870,9 @@ __global__ void __launch_bounds__(512, 2) rows_inv_ac_kernel(RowsInvAcArgs a) {
     constexpr int WPG = TPF / 8;
     constexpr int GPC = 16 / WPG;
     constexpr int FPC = 4 * GPC;
-    constexpr int FS = padded_len(NX) + 2;            // transforms 4 words apart in bank space (the gather writes pairs)
+    constexpr int FS = padded_len(NX) + 4;            // transforms 8 words apart in bank space: a lane group of the gather writes
+                                                      // elements {0..3, 8..11} (+4 for the partner column) of its transform, so the four
+                                                      // transforms of a warp land on disjoint banks, half-warp by half-warp
     constexpr int HX = NX / 2;
     extern __shared__ float2 sm[];
     __shared__ float s_scale;
@@ -1499,7 +1504,7 @@ int launch_rows_inv(b4d_ctx* ctx, RowsInvArgs& a, int64_t T, int grid_blocks) {
 template <int NX>
 int launch_rows_inv_ac(b4d_ctx* ctx, RowsInvAcArgs& a, int64_t T, int* nblk_out) {
     constexpr int TPF = NX / 16, WPG = TPF / 8, GPC = 16 / WPG, FPC = 4 * GPC;
-    constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 2) * sizeof(float2);
+    constexpr size_t smem = (size_t)FPC * (padded_len(NX) + 4) * sizeof(float2);
     static bool attr[B4D_MAX_DEVICES] = {};
     if (!attr[ctx->device]) { B4D_CUDA(ctx, cudaFuncSetAttribute(rows_inv_ac_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[ctx->device] = true; }
     const int rows = 2 * FPC, nblk = (a.ny / 2 + 1 + rows - 1) / rows;
