@@ -477,6 +477,16 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             }
         }
     }
+    // The first half of the thread's reference-spectrum values is requested now: the barriers of the TMA hand-over and of
+    // the block reductions below are spent waiting anyway, and one 1024-thread CTA per SM has no other warps to hide an L2
+    // round trip behind. (The second half follows the first product sweep: sixteen values in flight next to x[] would spill.)
+    float2 Rv0[8];
+    const float2* R = nullptr;
+    if (PC) {
+        R = a.R + (size_t)t * a.r_stride + (g0 - (size_t)t * NY * hx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Rv0[i] = __ldg(R + i * GS);
+    }
     if (tma) {
         fence_async_smem();                           // the staged tiles become visible to the async proxy
         __syncthreads();
@@ -488,10 +498,31 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
             tma_commit();
         }
     }
+    // ---- block reductions of the scalar partials ------------------------------------------------
+    if (SPEC || AC) {
+        double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, (double)acsum};
+        const int warp = tid >> 5, lane = tid & 31, nw = (NT + 31) / 32;
+#pragma unroll
+        for (int i = SPEC ? 0 : NSP; i < NSP + 1; ++i) {
+            if (i == NSP && !AC) break;
+            double r = warp_sum(v[i]);
+            __syncthreads();
+            if (lane == 0) red[warp] = r;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < nw; ++w) tot += red[w];
+                if (i < NSP) {
+                    if (a.spec_partials) a.spec_partials[((size_t)t * ntiles + tile) * NSP + i] = tot;
+                } else {
+                    a.ac_partials[(size_t)t * ntiles + tile] = tot;
+                }
+            }
+        }
+    }
     if (PC) {
         float inv_s = 1.f;
         if (a.fr) inv_s = (float)(1.0 / (sqrt(a.fr[(size_t)t * a.fr_stride + B4D_FR_M2]) + (double)a.eps));
-        const float2* R = a.R + (size_t)t * a.r_stride + (g0 - (size_t)t * NY * hx);
         const float2* Rn = a.Rnyq + (size_t)t * a.rnyq_stride;
         // the reference spectrum is fetched eight elements at a time (a compiler barrier keeps the second half from
         // being hoisted over the first, which would spill)
@@ -499,7 +530,7 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         for (int h = 0; h < 2; ++h) {
             float2 Rv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) Rv[i] = __ldg(R + (8 * h + i) * GS);
+            for (int i = 0; i < 8; ++i) Rv[i] = h == 0 ? Rv0[i] : __ldg(R + (8 + i) * GS);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int s = 8 * h + i;
@@ -529,28 +560,6 @@ __device__ __forceinline__ void cols_body(const ColsArgs& a, float2* sm, double*
         }
     }
 
-    // ---- block reductions of the scalar partials ------------------------------------------------
-    if (SPEC || AC) {
-        double v[NSP + 1] = {sp.total, sp.fx2, sp.fy2, sp.p2, sp.all, sp.plogp, (double)acsum};
-        const int warp = tid >> 5, lane = tid & 31, nw = (NT + 31) / 32;
-#pragma unroll
-        for (int i = SPEC ? 0 : NSP; i < NSP + 1; ++i) {
-            if (i == NSP && !AC) break;
-            double r = warp_sum(v[i]);
-            __syncthreads();
-            if (lane == 0) red[warp] = r;
-            __syncthreads();
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int w = 0; w < nw; ++w) tot += red[w];
-                if (i < NSP) {
-                    if (a.spec_partials) a.spec_partials[((size_t)t * ntiles + tile) * NSP + i] = tot;
-                } else {
-                    a.ac_partials[(size_t)t * ntiles + tile] = tot;
-                }
-            }
-        }
-    }
     // the copy engine must have read the staged tiles before the exchange buffer is written again (or the CTA leaves):
     // the issuing thread waits here, everybody else meets it at the next barrier (entry of the inverse transform)
     if (tma && tid == 0) tma_wait_read_all();
