@@ -60,6 +60,9 @@ _SIGNATURES = {
     "b4d_memcpy_h2d": [_vp, _vp, _vp, C.c_size_t],
     "b4d_memcpy_d2h": [_vp, _vp, _vp, C.c_size_t],
     "b4d_cast_to_f32": [_vp, _vp, _i32, _vp, _i64],
+    "b4d_inflate_caps": [_vp, C.POINTER(_i32), C.POINTER(_i64)],
+    "b4d_inflate_batch": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64],
+    "b4d_unchunk_to_f32": [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "b4d_frame_reductions": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f64, _f64, _vp],
     "b4d_select_ranks": [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp],
     "b4d_flat_field": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _i32, _vp],
@@ -115,7 +118,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 
 # entry points that do no stream-ordered work: the bound library does not re-install the stream for them
-_NO_STREAM = {"b4d_create", "b4d_destroy", "b4d_set_stream", "b4d_last_error", "b4d_version", "b4d_launch_count",
+_NO_STREAM = {"b4d_inflate_caps", "b4d_create", "b4d_destroy", "b4d_set_stream", "b4d_last_error", "b4d_version", "b4d_launch_count",
               "b4d_device_sm_count", "b4d_profile_class_name", "b4d_set_batch_frames", "b4d_set_schedule", "b4d_set_pairing",
               "b4d_set_fused_median"}
 
@@ -273,6 +276,18 @@ def cast_to_f32(raw_bytes, code: int, out):
     ctx = get_context(out.device.index or 0)
     ctx.check(ctx.lib.b4d_cast_to_f32(ctx.handle, ptr(raw_bytes), int(code), ptr(out), int(out.numel())), "b4d_cast_to_f32")
     return out
+
+
+def inflate_caps(device: int | None = None) -> tuple[int, int]:
+    """(algorithm mask, largest stream in bytes) of the device's hardware decompression engine; mask bit 0 = deflate.
+    (0, 0) where the device or the driver has none."""
+    ctx = get_context(device)
+    mask, mx = _i32(0), _i64(0)
+    ctx.check(ctx.lib.b4d_inflate_caps(ctx.handle, C.byref(mask), C.byref(mx)), "b4d_inflate_caps")
+    return int(mask.value), int(mx.value)
+
+
+UNCHUNK_CODES = dict(NATIVE_INT_CODES, float32=5)
 
 
 def as_device_f32(a, device: int | None = None):

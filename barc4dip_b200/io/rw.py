@@ -1,9 +1,9 @@
 """
-read_image / write_image: the reference's extension dispatchers (io/rw.py:64-148, :151-189), HDF5 branch only.
+read_image / write_image: the reference's extension dispatchers (io/rw.py:64-148, :151-189): HDF5 both ways, TIFF in.
 
-TIFF and EDF are recognised (same extension tables, same argument checks in the same order) and then refused with a
-ValueError naming the format: their readers live in PIL / the EDF parser on the reference's side and sit outside the
-stack hot path (SURVEY 8(f) names HDF5 ingestion only).
+EDF input and TIFF output are recognised (same extension tables, same argument checks in the same order) and then
+refused with a ValueError naming the format: the legacy EDF parser and the display rescaling behind save_tiff sit outside
+the stack hot path (SURVEY 8(f) names HDF5 ingestion only).
 """
 
 from __future__ import annotations
@@ -14,6 +14,7 @@ from pathlib import Path
 import numpy as np
 
 from .h5 import read_h5, save_h5
+from .tiff import read_tiff
 
 _READ_EXTS = {"tif": "tiff", "tiff": "tiff", "edf": "edf", "h5": "h5", "hdf5": "h5"}
 _WRITE_EXTS = {"tif": "tiff", "tiff": "tiff", "h5": "h5", "hdf5": "h5", "edf": "edf"}
@@ -51,8 +52,11 @@ def read_image(image_path: str | Sequence[str], *, file_extension: str | None = 
     if kind != "h5":
         if image_number is not None:
             raise ValueError("image_number is only supported for HDF5 stacks (single-file .h5/.hdf5).")
-        raise ValueError(f"{kind.upper()} input is not built in barc4dip_b200 (HDF5 stacks only)")
-    data = read_h5(image_path, image_number=image_number)
+        if kind == "edf":
+            raise ValueError("EDF input is not built in barc4dip_b200 (HDF5 and TIFF only)")
+        data = read_tiff(image_path)
+    else:
+        data = read_h5(image_path, image_number=image_number)
     if mean and data.ndim == 3:
         data = data.mean(axis=0)
         if verbose:
@@ -75,7 +79,7 @@ def write_image(data: np.ndarray, output_path: str | Path, *, file_extension: st
     if kind == "edf":
         raise ValueError("Writing EDF is not supported (legacy read-only format).")
     if kind != "h5":
-        raise ValueError("TIFF output is not built in barc4dip_b200 (HDF5 stacks only)")
+        raise ValueError("TIFF output is not built in barc4dip_b200 (HDF5 only)")
     save_h5(data, out)
     if verbose:
         print(f"> image saved to {out}")

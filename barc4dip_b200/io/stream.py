@@ -7,6 +7,12 @@ frames: a reader thread inflates the chunks of block k+1 (thread pool, GIL relea
 staging buffers while `StackAnalyzer.run` uploads and analyses block k; integer detector frames stay in their own width
 until they are on the device (`b4d_cast_to_f32`). Host memory in use: two blocks, whatever the stack's length.
 
+Where the GPU has a hardware decompression engine (B200: `b4d_inflate_caps`) the host does not inflate at all
+(`DeviceInflater`): the deflate streams of a block are copied as stored into pinned staging, cross PCIe compressed, are
+inflated by the engine (`b4d_inflate_batch`, one batch per block) and one kernel (`b4d_unchunk_to_f32`) undoes the byte
+shuffle and the chunk tiling on the way to float32 frames. `inflate="auto"` takes that path whenever the file qualifies
+(builtin codec, (shuffle +) deflate pipeline, native element type, chunks within the engine's limit).
+
     res = analyze_h5_stack("scan_0001.h5")                       # reference frame = frame 0 of the file
     res = analyze_h5_stack(path, frames=parallel.frame_range(T, rank, world))   # one rank's share of a stack
 """
@@ -18,8 +24,9 @@ import threading
 
 import numpy as np
 
-from .._lib import native_int_code, require_cuda
+from .._lib import UNCHUNK_CODES, get_context, inflate_caps, native_int_code, ptr, require_cuda
 from . import h5 as _h5
+from . import hdf5 as _hdf5
 
 
 class H5StackSource:
@@ -129,6 +136,176 @@ class H5StackSource:
             th.join()
 
 
+class DeviceInflater:
+    """Frames [a, b) of a deflate-chunked dataset -> float32 CUDA frames, inflated by the GPU's decompression engine.
+
+    Per block of frames: the chunks' raw deflate streams (zlib header and Adler-32 trailer checked / dropped on the host)
+    are packed into a pinned buffer, uploaded, inflated in one batch and un-tiled + widened by one kernel. Two blocks
+    are in flight: a reader thread packs block k+1 while the GPU works on block k."""
+
+    def __init__(self, dset, *, frames: tuple[int, int] | None = None, block_frames: int = 32, device: int | None = None):
+        torch = require_cuda()
+        why = self.unsupported(dset, device)
+        if why:
+            raise _hdf5.H5Unsupported(why)
+        self.dset, self.ctx = dset, get_context(device)
+        self.device = torch.device(f"cuda:{self.ctx.device}")
+        T, self.ny, self.nx = dset.shape
+        a, b = (0, T) if frames is None else (int(frames[0]), int(frames[1]))
+        if not (0 <= a <= b <= T):
+            raise ValueError(f"frames {frames} outside a stack of {T} frames")
+        self.range, self.frame_shape = (a, b), (self.ny, self.nx)
+        self.c0, self.cy, self.cx = dset.chunks
+        self.gy, self.gx = -(-self.ny // self.cy), -(-self.nx // self.cx)
+        self.code = UNCHUNK_CODES[str(dset.dtype.newbyteorder("="))]
+        self.shuffled = dset.filters[0][0] == _hdf5.FILTER_SHUFFLE
+        self.chunk_bytes = self.c0 * self.cy * self.cx * dset.dtype.itemsize
+        blk = max(1, min(int(block_frames), max(1, b - a)))
+        if blk > self.c0:
+            blk -= blk % self.c0                                        # whole chunk rows per block where possible
+        self.block = blk
+        index = dset._chunk_index()                                     # sorted by (frame, y, x) offsets
+        per_fb = self.gy * self.gx
+        self.blocks = []
+        for lo in range(a, b, blk):
+            hi = min(b, lo + blk)
+            fb0, fb1 = lo // self.c0, (hi - 1) // self.c0
+            recs = index[fb0 * per_fb:(fb1 + 1) * per_fb]
+            self.blocks.append((lo, hi, recs))
+        self._cap_chunks = max((len(r) for _, _, r in self.blocks), default=0)
+        self._cap_bytes = max((sum(n - 6 + (-(n - 6) % 16) for _, _, n, _ in r) for _, _, r in self.blocks), default=0)
+
+    @staticmethod
+    def unsupported(dset, device: int | None = None) -> str | None:
+        """Why this dataset cannot take the device path (None: it can)."""
+        if not isinstance(dset, _hdf5.H5Dataset):
+            return "the device path reads chunks through the builtin codec"
+        if dset.ndim != 3 or dset.chunks is None:
+            return "not a chunked (N, H, W) dataset"
+        ids = [f[0] for f in dset.filters]
+        if ids not in ([_hdf5.FILTER_DEFLATE], [_hdf5.FILTER_SHUFFLE, _hdf5.FILTER_DEFLATE]):
+            return f"filter pipeline {ids} is not (shuffle +) deflate"
+        if not dset.dtype.isnative or str(dset.dtype) not in UNCHUNK_CODES:
+            return f"element type {dset.dtype} has no device cast"
+        if ids[0] == _hdf5.FILTER_SHUFFLE and dset.filters[0][1] and int(dset.filters[0][1][0]) != dset.dtype.itemsize:
+            return "shuffle filter over a different element size"
+        mask, max_bytes = inflate_caps(device)
+        if not mask & 1:
+            return "no deflate decompression engine on this device / driver"
+        if int(np.prod(dset.chunks)) * dset.dtype.itemsize > max_bytes:
+            return f"chunks exceed the engine's limit of {max_bytes} bytes"
+        index = dset._chunk_index()
+        grid = int(np.prod([-(-s // c) for s, c in zip(dset.shape, dset.chunks)]))
+        if len(index) != grid:
+            return "dataset with unallocated chunks"
+        if any(r[3] for r in index):
+            return "chunks stored with filters masked out"
+        if any(r[2] < 7 for r in index):
+            return "chunk too short to be a zlib stream"
+        return None
+
+    def _buffers(self):
+        torch = require_cuda()
+        n_frames = self.block
+        fb_max = max(((hi - 1) // self.c0 - lo // self.c0 + 1) for lo, hi, _ in self.blocks)
+        dev = self.device
+        return [{"pin": torch.empty((max(16, self._cap_bytes),), dtype=torch.uint8, pin_memory=True),
+                 "comp": torch.empty((max(16, self._cap_bytes),), dtype=torch.uint8, device=dev),
+                 "raw": torch.empty((fb_max * self.gy * self.gx * self.chunk_bytes,), dtype=torch.uint8, device=dev),
+                 "act": torch.zeros((self._cap_chunks,), dtype=torch.int32, device=dev),
+                 "frames": torch.empty((n_frames, self.ny, self.nx), dtype=torch.float32, device=dev)} for _ in range(2)]
+
+    def _pack(self, recs, pin: np.ndarray):
+        """Raw deflate streams of `recs` into the pinned buffer at 16-byte aligned offsets -> (offsets, sizes)."""
+        mm = self.dset._f._mm
+        offs, sizes = np.empty(len(recs), np.int64), np.empty(len(recs), np.int64)
+        pos = 0
+        for i, (_, addr, nbytes, _) in enumerate(recs):
+            cmf, flg = mm[addr], mm[addr + 1]
+            if (cmf & 0x0F) != 8 or ((cmf << 8) | flg) % 31 or (flg & 0x20) or addr + nbytes > len(mm):
+                raise OSError(f"chunk of '{self.dset.name}' at {addr} is not a zlib stream")
+            n = nbytes - 6                                              # minus header (2) and Adler-32 (4)
+            pin[pos:pos + n] = np.frombuffer(mm, np.uint8, n, addr + 2)
+            offs[i], sizes[i] = pos, n
+            pos += n + (-n % 16)
+        return offs, sizes, pos
+
+    def __iter__(self):
+        """Yields (first frame index, float32 CUDA tensor (n, ny, nx)) per block; the tensor is valid, and ordered after
+        its production on the current stream, until the next iteration step."""
+        torch = require_cuda()
+        if not self.blocks:
+            return
+        bufs = self._buffers()
+        pins = [b["pin"].numpy() for b in bufs]
+        s_in = torch.cuda.Stream(device=self.device)
+        free: queue.Queue = queue.Queue()
+        ready: queue.Queue = queue.Queue()
+        for i in range(2):
+            free.put((i, None))
+        stop = threading.Event()
+
+        def producer():
+            try:
+                for k, (_, _, recs) in enumerate(self.blocks):
+                    i, ev = free.get()
+                    if stop.is_set():
+                        return
+                    if ev is not None:
+                        ev.synchronize()                               # the upload that read this pinned buffer is done
+                    ready.put((k, i) + self._pack(recs, pins[i]))
+                ready.put(None)
+            except BaseException as e:
+                ready.put(e)
+
+        th = threading.Thread(target=producer, name="b4d-h5-packer", daemon=True)
+        th.start()
+        ctx, lib = self.ctx, self.ctx.lib
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def enqueue():
+            item = ready.get()
+            if item is None:
+                return None
+            if isinstance(item, BaseException):
+                raise item
+            k, i, offs, sizes, total = item
+            lo, hi, recs = self.blocks[k]
+            b = bufs[i]
+            with torch.cuda.stream(s_in):
+                s_in.wait_stream(torch.cuda.current_stream(self.device))    # set i's previous consumer is behind us
+                b["comp"][:total].copy_(b["pin"][:total], non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(s_in)
+                free.put((i, up))
+                ctx.check(lib.b4d_inflate_batch(ctx.handle, ptr(b["comp"]), offs.ctypes.data, sizes.ctypes.data, ptr(b["raw"]),
+                                                self.chunk_bytes, ptr(b["act"]), len(recs)), "b4d_inflate_batch")
+                ctx.check(lib.b4d_unchunk_to_f32(ctx.handle, ptr(b["raw"]), self.code, int(self.shuffled), hi - lo, self.ny,
+                                                 self.nx, self.c0, self.cy, self.cx, lo - (lo // self.c0) * self.c0,
+                                                 ptr(b["frames"])), "b4d_unchunk_to_f32")
+                done[i].record(s_in)
+            return k, i, lo, hi, len(recs)
+
+        try:
+            nxt = enqueue()
+            while nxt is not None:
+                cur = nxt
+                k, i, lo, hi, n = cur
+                # block k+1 goes to the copy / decompression engines before block k is handed out: its upload and
+                # inflation overlap the consumer's kernels on block k (the default stream there has nothing pending
+                # from block k-1: consumers synchronise before they return, StackAnalyzer.run does)
+                nxt = enqueue()
+                torch.cuda.current_stream(self.device).wait_event(done[i])
+                yield lo, bufs[i]["frames"][:hi - lo]
+                if not bool((bufs[i]["act"][:n] == self.chunk_bytes).all()):
+                    raise OSError(f"chunks of '{self.dset.name}' in frames [{lo}, {hi}) did not inflate to {self.chunk_bytes} bytes")
+        finally:
+            stop.set()
+            free.put((0, None))
+            th.join()
+            torch.cuda.current_stream(self.device).wait_stream(s_in)
+
+
 def concat_results(parts: list[dict]) -> dict:
     """Per-block result dicts of StackAnalyzer.run -> one dict: every array leaf concatenated along the frame axis."""
     if len(parts) == 1:
@@ -149,22 +326,52 @@ def concat_results(parts: list[dict]) -> dict:
 
 def analyze_h5_stack(path, *, reference=None, frames: tuple[int, int] | None = None, block_frames: int = 32,
                      decode_threads: int | None = None, keep_maps_on_device: bool = False, analyzer=None,
-                     **analyzer_kw) -> dict:
+                     inflate: str = "auto", **analyzer_kw) -> dict:
     """Analyse the stack stored in an HDF5 file with the fused pipeline; returns what `StackAnalyzer.run` returns for the
     same frames held in memory.
 
     reference: the tracker's reference frame (default: frame 0 of the FILE, also for a rank that reads a later range);
     frames: the frame range to analyse; analyzer: an existing StackAnalyzer to reuse (then `analyzer_kw` / `reference`
     are ignored); analyzer_kw go to StackAnalyzer (want_maps defaults to False here: the maps of a long stack do not
-    belong in host memory)."""
+    belong in host memory); inflate: "device" = the GPU's decompression engine (raises if the file or the device does
+    not qualify), "host" = zlib on the host threads, "auto" = the device when it qualifies."""
     from ..pipeline import StackAnalyzer
+
+    if inflate not in ("auto", "device", "host"):
+        raise ValueError(f"inflate must be 'auto', 'device' or 'host', got {inflate!r}")
+
+    def make_analyzer(frame_shape, first_frame):
+        analyzer_kw.setdefault("want_maps", False)
+        ref = np.asarray(first_frame()) if reference is None else reference
+        return StackAnalyzer(frame_shape, reference=ref, **analyzer_kw)
+
+    if inflate != "host":
+        f = None
+        try:
+            f = _hdf5.H5File(path)
+            dset = f[_h5.DATASET_PATH] if _h5.DATASET_PATH in f else None
+            dev = analyzer.dev if analyzer is not None else analyzer_kw.get("device")
+            why = "dataset not found" if dset is None else DeviceInflater.unsupported(dset, dev)
+            if why is None:
+                src = DeviceInflater(dset, frames=frames, block_frames=block_frames, device=dev)
+                if analyzer is None:
+                    analyzer = make_analyzer(src.frame_shape, lambda: dset[0])
+                parts = [analyzer.run(block, keep_maps_on_device=keep_maps_on_device) for _, block in src]
+                if not parts:
+                    raise ValueError("no frames to analyse")
+                return concat_results(parts)
+            if inflate == "device":
+                raise _hdf5.H5Unsupported(f"'{path}' cannot be inflated on the device: {why}")
+        except _hdf5.H5Unsupported:
+            if inflate == "device":
+                raise
+        finally:
+            if f is not None:
+                f.close()
 
     with H5StackSource(path, frames=frames, block_frames=block_frames, decode_threads=decode_threads) as src:
         if analyzer is None:
-            analyzer_kw.setdefault("want_maps", False)
-            if reference is None:
-                reference = np.asarray(src.dset[0])
-            analyzer = StackAnalyzer(src.frame_shape, reference=reference, **analyzer_kw)
+            analyzer = make_analyzer(src.frame_shape, lambda: src.dset[0])
         parts = [analyzer.run(block, keep_maps_on_device=keep_maps_on_device) for _, block in src]
     if not parts:
         raise ValueError("no frames to analyse")

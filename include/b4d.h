@@ -97,8 +97,32 @@ int b4d_memcpy_d2h(b4d_ctx* ctx, void* dst_host, const void* src, size_t bytes);
  * float64, which this path evaluates in float32 anyway). src and dst: device pointers, 16-byte
  * aligned; n elements.
  */
-enum b4d_dtype { B4D_U8 = 0, B4D_U16 = 1, B4D_I16 = 2, B4D_I32 = 3, B4D_U32 = 4 };
+enum b4d_dtype { B4D_U8 = 0, B4D_U16 = 1, B4D_I16 = 2, B4D_I32 = 3, B4D_U32 = 4, B4D_F32 = 5 /* b4d_unchunk_to_f32 only */ };
 int b4d_cast_to_f32(b4d_ctx* ctx, const void* src, int dtype, float* dst, int64_t n);
+
+/*
+ * Compressed stacks: the reference's files are HDF5 datasets of gzip-4 chunks (io/h5.py:204-210, written; :80 `dset[()]`,
+ * read and inflated on the host by h5py). Here the deflate streams are uploaded as stored and inflated by the GPU's
+ * hardware decompression engine (cuMemBatchDecompressAsync; B200: deflate / snappy / lz4, 4 MiB per stream).
+ *
+ * b4d_inflate_caps: *algo_mask = CUmemDecompressAlgorithm bits of the device (0: no engine / driver older than 12.8),
+ *   *max_bytes = largest single stream's output.
+ * b4d_inflate_batch: n RAW deflate streams (RFC 1951: a zlib stream minus its 2-byte header and 4-byte Adler-32)
+ *   at src + src_offset[i], src_bytes[i] long, inflate to dst + i * dst_stride; actual[i] receives the bytes written.
+ *   src, dst, actual: device memory from cudaMalloc (16-byte aligned offsets); src_offset, src_bytes: host arrays.
+ *   One batch is one unit of stream-ordered work on the context's stream. The engine does not verify its input: a
+ *   malformed stream surfaces as a sticky CUDA error at the next synchronisation, so callers check the zlib header
+ *   before stripping it and compare actual[] with the expected size afterwards.
+ * b4d_unchunk_to_f32: undoes the rest of the HDF5 storage on the way to float32 frames: `chunks` holds whole inflated
+ *   chunks of (c0, cy, cx) elements of `dtype` in [frame block][tile row][tile column] order (edge chunks padded, as
+ *   stored), byte-shuffled per chunk when `shuffled` (HDF5 filter 2); out[f][y][x], f < n_frames, is element
+ *   (first + f) of the frame axis of those chunks (first < c0: a frame range may start inside a chunk).
+ */
+int b4d_inflate_caps(b4d_ctx* ctx, int* algo_mask, int64_t* max_bytes);
+int b4d_inflate_batch(b4d_ctx* ctx, const void* src, const int64_t* src_offset, const int64_t* src_bytes, void* dst,
+                      int64_t dst_stride, uint32_t* actual, int64_t n);
+int b4d_unchunk_to_f32(b4d_ctx* ctx, const void* chunks, int dtype, int shuffled, int64_t n_frames, int ny, int nx, int c0,
+                       int cy, int cx, int first, float* out);
 
 /* ---- per-frame single-pass reductions ------------------------------------------------- */
 /*

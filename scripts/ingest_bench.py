@@ -2,7 +2,10 @@
 File -> GPU ingestion figures (not the headline bench): a gzip-4 chunked HDF5 stack of 2048^2 uint16 frames, written by
 io.h5.save_h5, analysed by io.stream.analyze_h5_stack. Reports, in frames/s,
   decode      the block reader alone (inflate on the host threads into pinned staging),
-  file_to_gpu analyze_h5_stack (decode of block k+1 overlapped with upload + kernels of block k),
+  file_to_gpu_host    analyze_h5_stack(inflate="host"): inflate of block k+1 on the host threads overlapped with upload +
+                      kernels of block k,
+  file_to_gpu_device  analyze_h5_stack(inflate="device"): compressed chunks over PCIe, inflated by the GPU's
+                      decompression engine, un-tiled and widened by b4d_unchunk_to_f32,
   in_memory   StackAnalyzer.run on the same frames already in pinned host memory (what the decode is measured against).
 
     python scripts/ingest_bench.py [--frames 48] [--n 2048] [--out gpurun_out/ingest.json]
@@ -55,12 +58,18 @@ def main():
             res["decode_frames_s"] = T / (time.perf_counter() - t0)
 
         an = StackAnalyzer((n, n), reference=stack[0], want_maps=False)
-        analyze_h5_stack(path, analyzer=an, block_frames=args.block)    # warm: staging buffers, plans, the page cache
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        got = analyze_h5_stack(path, analyzer=an, block_frames=args.block)
-        torch.cuda.synchronize()
-        res["file_to_gpu_frames_s"] = T / (time.perf_counter() - t0)
+        from barc4dip_b200._lib import inflate_caps
+        res["engine"] = dict(zip(("algo_mask", "max_bytes"), inflate_caps()))
+        got = None
+        for mode in ("host", "device"):
+            if mode == "device" and not res["engine"]["algo_mask"] & 1:
+                continue
+            analyze_h5_stack(path, analyzer=an, block_frames=args.block, inflate=mode)   # warm: staging, plans, page cache
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got = analyze_h5_stack(path, analyzer=an, block_frames=args.block, inflate=mode)
+            torch.cuda.synchronize()
+            res[f"file_to_gpu_{mode}_frames_s"] = T / (time.perf_counter() - t0)
 
         keep = torch.empty((stack.nbytes,), dtype=torch.uint8, pin_memory=True)
         pinned = keep.numpy().view(np.uint16).reshape(stack.shape)

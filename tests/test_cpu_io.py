@@ -363,6 +363,8 @@ def test_read_image_write_image_dispatch(tmp_path):
         read_image("x.tif", image_number=0)
     with pytest.raises(ValueError, match="not built"):
         read_image("x.edf")
+    with pytest.raises(ValueError, match="TIFF output is not built"):
+        write_image(a, tmp_path / "x.tif")
     with pytest.raises(ValueError, match="Writing EDF is not supported"):
         write_image(a, tmp_path / "x.edf")
     with pytest.raises(ValueError, match="Unsupported write extension"):
@@ -419,3 +421,34 @@ def test_concat_results_joins_every_leaf_along_frames():
     out = concat_results(parts)
     assert out["stats"]["mean"].tolist() == [0, 1, 2, 0, 1] and out["table"].shape == (5, 5)
     assert concat_results(parts[:1]) is parts[0]
+
+
+def test_read_tiff_single_files_and_sequences(tmp_path):
+    """io/tiff.py:19-70 through PIL (the reference's decoder): dtype and shape as stored, sequences stacked."""
+    Image = pytest.importorskip("PIL.Image")
+    from barc4dip_b200.io.tiff import read_tiff
+    a = _stack((3, 20, 30), "uint16", seed=8)
+    paths = []
+    for i, fr in enumerate(a):
+        paths.append(str(tmp_path / f"f_{i:04d}.tif"))
+        Image.fromarray(fr).save(paths[-1])
+    one = read_image(paths[1])
+    assert one.dtype == np.uint16
+    np.testing.assert_array_equal(one, a[1])
+    np.testing.assert_array_equal(read_image(paths), a)
+    np.testing.assert_array_equal(read_tiff(tuple(paths)), a)
+    np.testing.assert_array_equal(read_image(paths, mean=True), a.mean(axis=0))
+    f32 = _stack((20, 30), "float32", seed=9)
+    Image.fromarray(f32).save(tmp_path / "f.tiff")
+    got = read_image(str(tmp_path / "f.tiff"))
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, f32)
+    Image.fromarray(a[0][:10]).save(tmp_path / "short.tif")
+    with pytest.raises(ValueError, match="Inconsistent image shapes"):
+        read_tiff([paths[0], str(tmp_path / "short.tif")])
+    with pytest.raises(ValueError, match="empty"):
+        read_tiff([])
+    with pytest.raises(TypeError):
+        read_tiff([1])
+    with pytest.raises(TypeError):
+        read_tiff(1)
