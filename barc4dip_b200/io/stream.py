@@ -19,8 +19,10 @@ shuffle and the chunk tiling on the way to float32 frames. `inflate="auto"` take
 
 from __future__ import annotations
 
+import os
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -143,7 +145,8 @@ class DeviceInflater:
     are packed into a pinned buffer, uploaded, inflated in one batch and un-tiled + widened by one kernel. Two blocks
     are in flight: a reader thread packs block k+1 while the GPU works on block k."""
 
-    def __init__(self, dset, *, frames: tuple[int, int] | None = None, block_frames: int = 32, device: int | None = None):
+    def __init__(self, dset, *, frames: tuple[int, int] | None = None, block_frames: int = 32, device: int | None = None,
+                 pack_threads: int | None = None):
         torch = require_cuda()
         why = self.unsupported(dset, device)
         if why:
@@ -173,7 +176,9 @@ class DeviceInflater:
             recs = index[fb0 * per_fb:(fb1 + 1) * per_fb]
             self.blocks.append((lo, hi, recs))
         self._cap_chunks = max((len(r) for _, _, r in self.blocks), default=0)
-        self._cap_bytes = max((sum(n - 6 + (-(n - 6) % 16) for _, _, n, _ in r) for _, _, r in self.blocks), default=0)
+        self._cap_bytes = max((sum(16 + n + (-n % 16) for _, _, n, _ in r) for _, _, r in self.blocks), default=0)
+        self._pack_threads = max(1, min(8, os.cpu_count() or 1)) if pack_threads is None else max(1, int(pack_threads))
+        self._pool = ThreadPoolExecutor(self._pack_threads) if self._pack_threads > 1 else None
 
     @staticmethod
     def unsupported(dset, device: int | None = None) -> str | None:
@@ -216,18 +221,32 @@ class DeviceInflater:
                  "frames": torch.empty((n_frames, self.ny, self.nx), dtype=torch.float32, device=dev)} for _ in range(2)]
 
     def _pack(self, recs, pin: np.ndarray):
-        """Raw deflate streams of `recs` into the pinned buffer at 16-byte aligned offsets -> (offsets, sizes)."""
-        mm = self.dset._f._mm
-        offs, sizes = np.empty(len(recs), np.int64), np.empty(len(recs), np.int64)
+        """Stored chunks of `recs` into the pinned buffer, read with pread on a few threads (no page faults of a mapping,
+        GIL released); each chunk lands so that its raw deflate stream -- the zlib stream minus the 2-byte header, the
+        Adler-32 trailer is simply not handed to the engine -- starts on a 16-byte boundary -> (offsets, sizes, bytes)."""
+        n_rec = len(recs)
+        offs, sizes = np.empty(n_rec, np.int64), np.empty(n_rec, np.int64)
         pos = 0
-        for i, (_, addr, nbytes, _) in enumerate(recs):
-            cmf, flg = mm[addr], mm[addr + 1]
-            if (cmf & 0x0F) != 8 or ((cmf << 8) | flg) % 31 or (flg & 0x20) or addr + nbytes > len(mm):
-                raise OSError(f"chunk of '{self.dset.name}' at {addr} is not a zlib stream")
-            n = nbytes - 6                                              # minus header (2) and Adler-32 (4)
-            pin[pos:pos + n] = np.frombuffer(mm, np.uint8, n, addr + 2)
-            offs[i], sizes[i] = pos, n
-            pos += n + (-n % 16)
+        for i, (_, _, nbytes, _) in enumerate(recs):
+            offs[i], sizes[i] = pos + 16, nbytes - 6
+            pos += 16 + nbytes + (-nbytes % 16)
+        fd = self.dset._f._fh.fileno()
+
+        def load(span):
+            for i in range(*span):
+                _, addr, nbytes, _ = recs[i]
+                at = int(offs[i]) - 2
+                got = os.preadv(fd, [pin[at:at + nbytes]], addr)
+                cmf, flg = int(pin[at]), int(pin[at + 1])
+                if got != nbytes or (cmf & 0x0F) != 8 or ((cmf << 8) | flg) % 31 or (flg & 0x20):
+                    raise OSError(f"chunk of '{self.dset.name}' at {addr} is not a zlib stream")
+
+        nt = max(1, min(self._pack_threads, n_rec))
+        spans = [(n_rec * t // nt, n_rec * (t + 1) // nt) for t in range(nt)]
+        if nt == 1:
+            load(spans[0])
+        else:
+            list(self._pool.map(load, spans))
         return offs, sizes, pos
 
     def __iter__(self):
@@ -304,6 +323,17 @@ class DeviceInflater:
             free.put((0, None))
             th.join()
             torch.cuda.current_stream(self.device).wait_stream(s_in)
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def concat_results(parts: list[dict]) -> dict:

@@ -452,3 +452,33 @@ def test_read_tiff_single_files_and_sequences(tmp_path):
         read_tiff([1])
     with pytest.raises(TypeError):
         read_tiff(1)
+
+
+def test_device_path_packs_raw_deflate_streams_on_the_host(tmp_path):
+    """The host half of the device ingestion path (io.stream.DeviceInflater._pack) needs no GPU: stored chunks are read
+    into the staging buffer so that the raw deflate stream (zlib minus header / Adler-32) starts 16-byte aligned."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from barc4dip_b200.io.stream import DeviceInflater
+    a = _stack((4, 64, 64), "uint16", seed=6)
+    p = tmp_path / "s.h5"
+    hdf5.write_stack(p, a, chunks=(1, 16, 64))
+    with hdf5.H5File(p) as f:
+        d = f[PATH]
+        inf = DeviceInflater.__new__(DeviceInflater)                        # no device: only the packer is exercised
+        inf.dset, inf._pack_threads, inf._pool = d, 3, ThreadPoolExecutor(3)
+        recs = d._chunk_index()
+        pin = np.zeros(sum(16 + r[2] + (-r[2] % 16) for r in recs), np.uint8)
+        offs, sizes, total = inf._pack(recs, pin)
+        assert total == len(pin) and not (offs % 16).any()
+        raw = b"".join(zlib.decompress(pin[o:o + s].tobytes(), -15) for o, s in zip(offs, sizes))
+        np.testing.assert_array_equal(np.frombuffer(raw, np.uint16).reshape(4, 4, 16, 64).reshape(4, 64, 64), a)
+        # a chunk that is not a zlib stream is refused before anything reaches the decompression engine
+        bad = bytearray(p.read_bytes())
+        bad[recs[5][1]] = 0x00
+        (tmp_path / "bad.h5").write_bytes(bytes(bad))
+    with hdf5.H5File(tmp_path / "bad.h5") as f:
+        inf.dset = f[PATH]
+        with pytest.raises(OSError, match="not a zlib stream"):
+            inf._pack(inf.dset._chunk_index(), pin)
+    inf.close()
