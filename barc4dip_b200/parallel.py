@@ -178,6 +178,39 @@ def analyze_stack_sharded(stack, *, reference=None, slices_yx=None, **analyzer_k
     return out
 
 
+def analyze_h5_stack_sharded(path, *, reference=None, **kw) -> dict:
+    """The stack stored in an HDF5 file, analysed by the ranks of the current process group straight from the file.
+
+    Rank r reads and analyses only its contiguous frame range (io.stream.analyze_h5_stack(frames=...): compressed chunks
+    -> GPU, inflated there where the device can); no rank ever holds the stack, and nothing is broadcast: every rank
+    reads the tracker's reference (default: frame 0 of the file) itself. Per-frame tables are all-gathered, so every
+    rank returns the full (T, ...) tables; maps (want_maps=True with keep_maps_on_device=True) stay with the rank that
+    computed them; out["frame_range"] = (lo, hi). The reference loads the whole file on one host first
+    (io/rw.py:129 -> metrics/speckles.py:300-325)."""
+    from .io import h5 as h5io
+    from .io.stream import analyze_h5_stack
+    rank, world = dist_info()
+    f, dset = h5io.open_dataset(path)
+    try:
+        if dset.ndim != 3:
+            raise ValueError(f"expected a (N, H, W) stack in '{path}', got shape {dset.shape}")
+        T = int(dset.shape[0])
+        if reference is None:
+            reference = np.asarray(dset[0])
+    finally:
+        f.close()
+    lo, hi = frame_range(T, rank, world)
+    if hi > lo:
+        res = analyze_h5_stack(path, reference=reference, frames=(lo, hi), **kw)
+    else:                                                              # a rank without frames still joins the gathers
+        res = {k: _take0(v) for k, v in analyze_h5_stack(path, reference=reference, frames=(0, 1), **kw).items()}
+    maps = {k: res.pop(k) for k in ("psd", "autocorr") if k in res}
+    out = gather_tree(res, T)
+    out.update(maps)
+    out["frame_range"] = (lo, hi)
+    return out
+
+
 def _take0(v):
     if isinstance(v, dict):
         return {k: _take0(x) for k, x in v.items()}

@@ -75,6 +75,18 @@ def same_tree(a, b, path=""):
 
 
 sh = parallel.analyze_stack_sharded(stack, chunk_frames=3)
+# the same stack as a gzip-4 HDF5 file of uint16 frames, every rank reading its own frame range from the file
+import tempfile
+from barc4dip_b200.io import h5 as h5io
+u16 = np.clip(np.rint(stack / stack.max() * 60000.0), 0, 60000).astype(np.uint16)
+h5_path = os.path.join(tempfile.gettempdir(), f"b4d_mgc_{os.environ.get('MASTER_PORT', '0')}.h5")
+if rank == 0:
+    if os.path.exists(h5_path):
+        os.remove(h5_path)
+    h5io.save_h5(u16, h5_path)
+dist.barrier()
+sh_file = parallel.analyze_h5_stack_sharded(h5_path, block_frames=4, chunk_frames=3)
+dist.barrier()
 sp = {m: dip.metrics.speckle_stack_stats(stack, metrics="all", tiles=True, tracking_method=m, tracking_backend=b, verbose=False)
       for m, b in (("template", "opencv"), ("phase", "internal"))}
 if rank == 0:
@@ -84,6 +96,10 @@ if rank == 0:
         assert torch.equal(sh[k], one_a[k][lo_:hi_]), k
     same_tree({k: v for k, v in sh.items() if k not in ("psd", "autocorr", "frame_range")},
               {k: v for k, v in one_a.items() if k not in ("psd", "autocorr")}, "analyze_stack_sharded")
+    one_f = StackAnalyzer((n, n), device=local, reference=u16[0], chunk_frames=3, want_maps=False).run(u16)
+    same_tree({k: v for k, v in sh_file.items() if k != "frame_range"}, one_f, "analyze_h5_stack_sharded")
+    os.remove(h5_path)
+    print(f"file-sharded entry ok: analyze_h5_stack_sharded over {world} ranks equals the single-GPU analysis of the same uint16 frames")
     for m, b in (("template", "opencv"), ("phase", "internal")):
         one_s = dip.metrics.speckle_stack_stats(stack, metrics="all", tiles=True, tracking_method=m, tracking_backend=b,
                                                 verbose=False, sharded=False)
