@@ -461,6 +461,34 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(d2h_b * E), "steps": args.e2e_steps, "frames_per_step_per_gpu": E,
                     "note": "same call, PSD + autocorrelation maps also copied to pinned host memory (PCIe-bound)"}
 
+    # file -> results: the same uint16 frames as a gzip-4 chunked HDF5 stack (the reference's save_h5 layout), analysed by
+    # io.stream.analyze_h5_stack -- stored chunks over PCIe, inflated by the GPU's decompression engine where there is one
+    e2e_h5 = None
+    if not args.no_e2e and world == 1:
+        try:
+            import tempfile
+            from barc4dip_b200._lib import inflate_caps
+            from barc4dip_b200.io import h5 as h5io
+            from barc4dip_b200.io.stream import analyze_h5_stack
+            Eh = min(E, 64)
+            with tempfile.TemporaryDirectory() as tmp:
+                path = os.path.join(tmp, "stack.h5")
+                h5io.save_h5(host_u16[:Eh].numpy(), path)
+                an3 = StackAnalyzer((n, n), device=local, reference=ref_host, want_maps=False, want_contrast=True)
+                mode = "device" if inflate_caps(local)[0] & 1 else "host"
+                analyze_h5_stack(path, analyzer=an3, block_frames=32, inflate=mode)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    analyze_h5_stack(path, analyzer=an3, block_frames=32, inflate=mode)
+                torch.cuda.synchronize()
+                e2e_h5 = {"value": 2 * Eh / (time.perf_counter() - t0), "unit": UNIT, "inflate": mode, "frames": Eh,
+                          "file_bytes_per_frame": os.path.getsize(path) / Eh, "raw_bytes_per_frame": n * n * 2,
+                          "note": "HDF5 file (page cache) -> per-frame tables on the host; compressed chunks cross PCIe and are "
+                                  "inflated on the device (b4d_inflate_batch + b4d_unchunk_to_f32) when inflate == 'device'"}
+        except Exception as e:                                    # an extra figure must not cost the headline line
+            e2e_h5 = {"error": repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -538,7 +566,7 @@ def run_b200(args):
                    "l2": f"inputs per step {F * n * n * 4 / MB:.0f} MB + {2 * F * n * n * 4 / MB:.0f} MB of maps written: larger than the 126 MB L2, no flush needed",
                    "internal_batch_frames": args.batch or "auto", "prewarm_s": args.prewarm,
                    "tail_percentile_frames_needing_fallback": unresolved, "tracker_median_frames_needing_fallback": snr_unresolved},
-        "clocks": clock_info, "e2e": e2e, "e2e_uint16": e2e_u16, "e2e_maps_to_host": e2e_maps, "gpu_launches": int(launches),
+        "clocks": clock_info, "e2e": e2e, "e2e_uint16": e2e_u16, "e2e_maps_to_host": e2e_maps, "e2e_hdf5": e2e_h5, "gpu_launches": int(launches),
         "collective": collective, "phases": phases,
         "roofline": roofline, "step_roofline": step_roof, "fft_fp32": fp32, "kernels": kernel_table, "cpu_baseline": cpu,
     }
