@@ -73,50 +73,71 @@ template <> struct Quad<int32_t> { typedef uint4 type; };
 template <> struct Quad<uint32_t> { typedef uint4 type; };
 template <> struct Quad<float> { typedef uint4 type; };
 
-// One thread = V consecutive pixels of one output row (V = 4 when nx and cx are multiples of 4, else 1).
+// One thread = V consecutive pixels (V = 4 when nx and cx are multiples of 4, else 1) of UNCHUNK_ROWS consecutive rows: the
+// grid is (pieces of a row, groups of rows, frames), the three divisions (frame / c0, row / cy, x / cx) are paid once
+// per thread and the walk down the rows is additions -- the element index moves by cx, or to the next tile row.
+// (History, ncu on 16 frames of 2048^2 uint16: flattened 64-bit index 229 instructions per warp and row, 140 us; 3-D grid
+// with one row per thread 152, 98 us; this form: see profiles/r02_unchunk_ncu.txt.)
 // chunk order: [frame block][tile row][tile column], each chunk whole (edge chunks padded), elements (c0, cy, cx) row-major;
 // with SHUF the chunk holds sizeof(T) planes of n_elems bytes: plane k = k-th byte of every element.
+constexpr int UNCHUNK_ROWS = 8;
+
 template <typename T, int V, bool SHUF>
 __global__ void __launch_bounds__(256) unchunk_to_f32_kernel(const uint8_t* __restrict__ chunks, float* __restrict__ out,
-                                                             int64_t n_units, int ny, int nx, int c0, int cy, int cx,
-                                                             int gy, int gx, int first) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
-    const int upr = nx / V;                                  // units per row
-    const int x = (int)(u % upr) * V;
-    const int64_t fy = u / upr;
-    const int y = (int)(fy % ny);
-    const int64_t f = fy / ny;
-    const int64_t fg = f + first;
-    const int64_t fb = fg / c0;
-    const int fz = (int)(fg - fb * c0);
-    const int iy = y / cy, yy = y - iy * cy;
-    const int ix = x / cx, xx = x - ix * cx;
+                                                             int ny, int nx, int c0, int cy, int cx, int gy, int gx, int first) {
+    const unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (x >= (unsigned)nx) return;
+    const unsigned y0 = blockIdx.y * UNCHUNK_ROWS;
+    const unsigned f = blockIdx.z;
+    const unsigned fg = f + (unsigned)first;
+    const unsigned fb = fg / (unsigned)c0, fz = fg - fb * (unsigned)c0;
+    unsigned iy = y0 / (unsigned)cy, yy = y0 - iy * (unsigned)cy;
+    const unsigned ix = x / (unsigned)cx, xx = x - ix * (unsigned)cx;
     const int64_t n_elems = (int64_t)c0 * cy * cx;
-    const uint8_t* base = chunks + ((fb * gy + iy) * gx + ix) * n_elems * (int64_t)sizeof(T);
-    const int64_t e = ((int64_t)fz * cy + yy) * cx + xx;
-    T v[V];
-    if (!SHUF) {
-        if (V == 4) *reinterpret_cast<typename Quad<T>::type*>(v) = __ldcs(reinterpret_cast<const typename Quad<T>::type*>(base + e * sizeof(T)));
-        else v[0] = *reinterpret_cast<const T*>(base + e * sizeof(T));
-    } else {
-        uint8_t b[sizeof(T)][V];
+    const int64_t chunk_bytes = n_elems * (int64_t)sizeof(T);
+    const uint8_t* base = chunks + (((int64_t)fb * gy + iy) * gx + ix) * chunk_bytes;      // tile (fb, iy, ix)
+    int64_t e = ((int64_t)fz * cy + yy) * cx + xx;                                         // element inside the tile
+    float* o = out + ((int64_t)f * ny + y0) * nx + x;
+    const int rows = min(UNCHUNK_ROWS, ny - (int)y0);
+    // all loads of the thread first (UNCHUNK_ROWS independent requests in flight), then the conversions and stores
+    T v[UNCHUNK_ROWS][V];
 #pragma unroll
-        for (int k = 0; k < (int)sizeof(T); ++k) {
-            if (V == 4) *reinterpret_cast<uint32_t*>(b[k]) = __ldcs(reinterpret_cast<const uint32_t*>(base + k * n_elems + e));
-            else b[k][0] = base[k * n_elems + e];
-        }
+    for (int r = 0; r < UNCHUNK_ROWS; ++r) {
+        if (r < rows) {
+            if (!SHUF) {
+                if (V == 4) *reinterpret_cast<typename Quad<T>::type*>(v[r]) = __ldcs(reinterpret_cast<const typename Quad<T>::type*>(base + e * sizeof(T)));
+                else v[r][0] = *reinterpret_cast<const T*>(base + e * sizeof(T));
+            } else {
+                uint8_t b[sizeof(T)][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            uint8_t w[sizeof(T)];
+                for (int k = 0; k < (int)sizeof(T); ++k) {
+                    if (V == 4) *reinterpret_cast<uint32_t*>(b[k]) = __ldcs(reinterpret_cast<const uint32_t*>(base + k * n_elems + e));
+                    else b[k][0] = base[k * n_elems + e];
+                }
 #pragma unroll
-            for (int k = 0; k < (int)sizeof(T); ++k) w[k] = b[k][i];
-            memcpy(&v[i], w, sizeof(T));
+                for (int i = 0; i < V; ++i) {
+                    uint8_t w[sizeof(T)];
+#pragma unroll
+                    for (int k = 0; k < (int)sizeof(T); ++k) w[k] = b[k][i];
+                    memcpy(&v[r][i], w, sizeof(T));
+                }
+            }
+            e += cx;
+            if (++yy == (unsigned)cy) {                   // next tile row: same column of tiles, first row of the tile
+                yy = 0;
+                base += (int64_t)gx * chunk_bytes;
+                e = (int64_t)fz * cy * cx + xx;
+            }
         }
     }
-    float* o = out + (f * ny + y) * (int64_t)nx + x;
-    if (V == 4) *reinterpret_cast<float4*>(o) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-    else o[0] = (float)v[0];
+#pragma unroll
+    for (int r = 0; r < UNCHUNK_ROWS; ++r) {
+        if (r < rows) {
+            if (V == 4) *reinterpret_cast<float4*>(o) = make_float4((float)v[r][0], (float)v[r][1], (float)v[r][2], (float)v[r][3]);
+            else o[0] = (float)v[r][0];
+            o += nx;
+        }
+    }
 }
 
 template <typename T>
@@ -124,14 +145,14 @@ int launch_unchunk(b4d_ctx* ctx, const void* chunks, int shuffled, int64_t n_fra
                    int first, float* out) {
     const int gy = (ny + cy - 1) / cy, gx = (nx + cx - 1) / cx;
     const bool quad = (nx % 4 == 0) && (cx % 4 == 0);
-    const int64_t units = n_frames * ny * (int64_t)(quad ? nx / 4 : nx);
-    const unsigned blocks = (unsigned)((units + 255) / 256);
+    const int upr = quad ? nx / 4 : nx;                       // threads per row
+    const dim3 grid((unsigned)((upr + 255) / 256), (unsigned)((ny + UNCHUNK_ROWS - 1) / UNCHUNK_ROWS), (unsigned)n_frames);
     const uint8_t* src = static_cast<const uint8_t*>(chunks);
     ProfScope ps(ctx, KC_SMALL);
-    if (quad && shuffled) unchunk_to_f32_kernel<T, 4, true><<<blocks, 256, 0, ctx->stream>>>(src, out, units, ny, nx, c0, cy, cx, gy, gx, first);
-    else if (quad) unchunk_to_f32_kernel<T, 4, false><<<blocks, 256, 0, ctx->stream>>>(src, out, units, ny, nx, c0, cy, cx, gy, gx, first);
-    else if (shuffled) unchunk_to_f32_kernel<T, 1, true><<<blocks, 256, 0, ctx->stream>>>(src, out, units, ny, nx, c0, cy, cx, gy, gx, first);
-    else unchunk_to_f32_kernel<T, 1, false><<<blocks, 256, 0, ctx->stream>>>(src, out, units, ny, nx, c0, cy, cx, gy, gx, first);
+    if (quad && shuffled) unchunk_to_f32_kernel<T, 4, true><<<grid, 256, 0, ctx->stream>>>(src, out, ny, nx, c0, cy, cx, gy, gx, first);
+    else if (quad) unchunk_to_f32_kernel<T, 4, false><<<grid, 256, 0, ctx->stream>>>(src, out, ny, nx, c0, cy, cx, gy, gx, first);
+    else if (shuffled) unchunk_to_f32_kernel<T, 1, true><<<grid, 256, 0, ctx->stream>>>(src, out, ny, nx, c0, cy, cx, gy, gx, first);
+    else unchunk_to_f32_kernel<T, 1, false><<<grid, 256, 0, ctx->stream>>>(src, out, ny, nx, c0, cy, cx, gy, gx, first);
     B4D_LAUNCH_CHECK(ctx);
     return B4D_OK;
 }
@@ -193,7 +214,7 @@ extern "C" int b4d_unchunk_to_f32(b4d_ctx* ctx, const void* chunks, int dtype, i
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_unchunk_to_f32: bad arguments");
     if ((reinterpret_cast<uintptr_t>(chunks) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
         return b4d_fail(ctx, B4D_ERR_INVALID, "b4d_unchunk_to_f32: pointers must be 16-byte aligned");
-    if (n_frames * (int64_t)ny * nx > ((int64_t)1 << 40)) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_unchunk_to_f32: too many elements");
+    if (n_frames > 65535 || ny > 65535) return b4d_fail(ctx, B4D_ERR_UNSUPPORTED, "b4d_unchunk_to_f32: at most 65535 frames per call and rows per frame");
     switch (dtype) {
         case B4D_U8: return launch_unchunk<uint8_t>(ctx, chunks, shuffled, n_frames, ny, nx, c0, cy, cx, first, out);
         case B4D_U16: return launch_unchunk<uint16_t>(ctx, chunks, shuffled, n_frames, ny, nx, c0, cy, cx, first, out);
