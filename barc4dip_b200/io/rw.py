@@ -1,9 +1,10 @@
 """
-read_image / write_image: the reference's extension dispatchers (io/rw.py:64-148, :151-189): HDF5 both ways, TIFF in.
+read_image / write_image: the reference's extension dispatchers (io/rw.py:64-148, :151-189): every format it reads
+(HDF5, TIFF, EDF) and HDF5 output.
 
-EDF input and TIFF output are recognised (same extension tables, same argument checks in the same order) and then
-refused with a ValueError naming the format: the legacy EDF parser and the display rescaling behind save_tiff sit outside
-the stack hot path (SURVEY 8(f) names HDF5 ingestion only).
+TIFF output is recognised (same extension tables, same argument checks in the same order) and then refused with a
+ValueError naming the format: the display rescaling behind save_tiff (utils/dtype.py:to_uint16) is not part of the stack
+path. EDF output is refused as in the reference.
 """
 
 from __future__ import annotations
@@ -13,6 +14,7 @@ from pathlib import Path
 
 import numpy as np
 
+from .edf import read_edf
 from .h5 import read_h5, save_h5
 from .tiff import read_tiff
 
@@ -52,9 +54,7 @@ def read_image(image_path: str | Sequence[str], *, file_extension: str | None = 
     if kind != "h5":
         if image_number is not None:
             raise ValueError("image_number is only supported for HDF5 stacks (single-file .h5/.hdf5).")
-        if kind == "edf":
-            raise ValueError("EDF input is not built in barc4dip_b200 (HDF5 and TIFF only)")
-        data = read_tiff(image_path)
+        data = read_edf(image_path) if kind == "edf" else read_tiff(image_path)
     else:
         data = read_h5(image_path, image_number=image_number)
     if mean and data.ndim == 3:

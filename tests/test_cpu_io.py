@@ -361,7 +361,7 @@ def test_read_image_write_image_dispatch(tmp_path):
         read_image(["a.h5", "b.tif"])
     with pytest.raises(ValueError, match="image_number is only supported for HDF5"):
         read_image("x.tif", image_number=0)
-    with pytest.raises(ValueError, match="not built"):
+    with pytest.raises(FileNotFoundError):
         read_image("x.edf")
     with pytest.raises(ValueError, match="TIFF output is not built"):
         write_image(a, tmp_path / "x.tif")
@@ -482,3 +482,69 @@ def test_device_path_packs_raw_deflate_streams_on_the_host(tmp_path):
         with pytest.raises(OSError, match="not a zlib stream"):
             inf._pack(inf.dset._chunk_index(), pin)
     inf.close()
+
+
+def test_read_edf_against_arrays_the_reference_read(tmp_path, golden):
+    """Every EDF case of oracle/make_golden_io.py: the bytes the reference's reader was given, replayed through
+    barc4dip_b200.io.edf.read_edf -- element types, byte orders, header block sizes, CRLF, several images per file."""
+    from barc4dip_b200.io.edf import read_edf
+    g = golden("edf")
+    names = sorted({k.split("/")[0] for k in g.files} - {"sequence"})
+    assert len(names) >= 20
+    for name in names:
+        p = str(tmp_path / f"{name}.edf")
+        with open(p, "wb") as fh:
+            fh.write(g[f"{name}/file"].tobytes())
+        idx = int(g[f"{name}/index"])
+        for key, dt in (("float32", np.float32), ("float64", np.float64)):
+            got = read_edf(p, index=idx, dtype=dt)
+            want = g[f"{name}/{key}"]
+            assert got.dtype == want.dtype and got.shape == want.shape, name
+            np.testing.assert_array_equal(got, want, err_msg=name)
+        if idx == 0 and g[f"{name}/float32"].ndim == 2:
+            np.testing.assert_array_equal(read_image(p), g[f"{name}/float32"])
+    seq = [str(tmp_path / f"{n}.edf") for n in g["sequence/names"]]
+    np.testing.assert_array_equal(read_edf(seq), g["sequence/float32"])
+    np.testing.assert_array_equal(read_image(seq), g["sequence/float32"])
+    # error behaviour observed on the reference (io/edf.py:51-52, io/uti_EdfFile.py)
+    one = str(tmp_path / "le_uint16.edf")
+    with pytest.raises(ValueError, match="index must be >= 0"):
+        read_edf(one, index=-1)
+    with pytest.raises(ValueError, match="Index out of limit"):
+        read_edf(one, index=1)
+    (tmp_path / "junk.edf").write_bytes(b"hello world\n" * 10)
+    with pytest.raises(ValueError, match="Index out of limit"):
+        read_edf(str(tmp_path / "junk.edf"))
+    raw = g["le_uint16/file"].tobytes()
+    (tmp_path / "trunc.edf").write_bytes(raw[:-5])
+    with pytest.raises(ValueError):
+        read_edf(str(tmp_path / "trunc.edf"))
+    (tmp_path / "unk.edf").write_bytes(raw.replace(b"UnsignedShort", b"ComplexFloat "))
+    with pytest.raises(TypeError, match="unknown EdfType"):
+        read_edf(str(tmp_path / "unk.edf"))
+    with pytest.raises(ValueError, match="Expected a 2D EDF image"):
+        read_edf([str(tmp_path / "three_dims.edf")])
+    with pytest.raises(ValueError, match="Inconsistent image shapes"):
+        read_edf([one, str(tmp_path / "be_uint16.edf")])
+    with pytest.raises(FileNotFoundError):
+        read_edf(str(tmp_path / "missing.edf"))
+    with pytest.raises(TypeError):
+        read_edf([3])
+    with pytest.raises(ValueError, match="empty"):
+        read_edf([])
+
+
+def test_read_tiff_against_arrays_the_reference_read(tmp_path, golden):
+    pytest.importorskip("PIL.Image")
+    from barc4dip_b200.io.tiff import read_tiff
+    g = golden("tiff")
+    names = sorted({k.split("/")[0] for k in g.files} - {"sequence"})
+    for name in names:
+        p = str(tmp_path / f"{name}.tif")
+        with open(p, "wb") as fh:
+            fh.write(g[f"{name}/file"].tobytes())
+        got = read_tiff(p)
+        assert got.dtype == g[f"{name}/array"].dtype
+        np.testing.assert_array_equal(got, g[f"{name}/array"], err_msg=name)
+    seq = [str(tmp_path / f"{n}.tif") for n in g["sequence/names"]]
+    np.testing.assert_array_equal(read_image(seq), g["sequence/array"])
