@@ -138,6 +138,17 @@ class H5StackSource:
             th.join()
 
 
+_CACHE: dict = {}            # device index -> {"busy", "caps", "flat"}: the staging buffers kept between calls
+_CACHE_LOCK = threading.Lock()
+
+
+def release_buffers():
+    """Drop the cached staging buffers of the device ingestion path (pinned host + device memory)."""
+    with _CACHE_LOCK:
+        for key in [k for k, e in _CACHE.items() if not e["busy"]]:
+            del _CACHE[key]
+
+
 class DeviceInflater:
     """Frames [a, b) of a deflate-chunked dataset -> float32 CUDA frames, inflated by the GPU's decompression engine.
 
@@ -146,7 +157,7 @@ class DeviceInflater:
     are in flight: a reader thread packs block k+1 while the GPU works on block k."""
 
     def __init__(self, dset, *, frames: tuple[int, int] | None = None, block_frames: int = 32, device: int | None = None,
-                 pack_threads: int | None = None):
+                 pack_threads: int | None = None, ramp: bool = True):
         torch = require_cuda()
         why = self.unsupported(dset, device)
         if why:
@@ -169,15 +180,19 @@ class DeviceInflater:
         self.block = blk
         index = dset._chunk_index()                                     # sorted by (frame, y, x) offsets
         per_fb = self.gy * self.gx
+        # the first blocks are short (a quarter, a half of a block, in whole chunk rows): the consumer gets its first
+        # frames after a quarter of a block's pack + upload + inflate time instead of a whole one
         self.blocks = []
-        for lo in range(a, b, blk):
-            hi = min(b, lo + blk)
+        lo, size = a, max(self.c0, (blk // 4) - (blk // 4) % self.c0) if ramp else blk
+        while lo < b:
+            hi = min(b, lo + size)
             fb0, fb1 = lo // self.c0, (hi - 1) // self.c0
             recs = index[fb0 * per_fb:(fb1 + 1) * per_fb]
             self.blocks.append((lo, hi, recs))
+            lo, size = hi, min(blk, 2 * size)
         self._cap_chunks = max((len(r) for _, _, r in self.blocks), default=0)
         self._cap_bytes = max((sum(16 + n + (-n % 16) for _, _, n, _ in r) for _, _, r in self.blocks), default=0)
-        self._pack_threads = max(1, min(8, os.cpu_count() or 1)) if pack_threads is None else max(1, int(pack_threads))
+        self._pack_threads = max(1, min(12, os.cpu_count() or 1)) if pack_threads is None else max(1, int(pack_threads))
         self._pool = ThreadPoolExecutor(self._pack_threads) if self._pack_threads > 1 else None
 
     @staticmethod
@@ -210,15 +225,41 @@ class DeviceInflater:
         return None
 
     def _buffers(self):
+        """Two sets of staging buffers. Pinning a few hundred MB costs tens of milliseconds, more than a short stack takes
+        to analyse, so one pair per device is kept between calls (release_buffers() drops it)."""
         torch = require_cuda()
-        n_frames = self.block
         fb_max = max(((hi - 1) // self.c0 - lo // self.c0 + 1) for lo, hi, _ in self.blocks)
-        dev = self.device
-        return [{"pin": torch.empty((max(16, self._cap_bytes),), dtype=torch.uint8, pin_memory=True),
-                 "comp": torch.empty((max(16, self._cap_bytes),), dtype=torch.uint8, device=dev),
-                 "raw": torch.empty((fb_max * self.gy * self.gx * self.chunk_bytes,), dtype=torch.uint8, device=dev),
-                 "act": torch.zeros((self._cap_chunks,), dtype=torch.int32, device=dev),
-                 "frames": torch.empty((n_frames, self.ny, self.nx), dtype=torch.float32, device=dev)} for _ in range(2)]
+        need = {"bytes": max(16, self._cap_bytes), "raw": fb_max * self.gy * self.gx * self.chunk_bytes,
+                "act": max(1, self._cap_chunks), "frames": self.block * self.ny * self.nx}
+        dev, key = self.device, self.ctx.device
+        with _CACHE_LOCK:
+            ent = _CACHE.get(key)
+            if ent is not None and not ent["busy"] and all(ent["caps"][k] >= v for k, v in need.items()):
+                ent["busy"] = True
+            else:
+                ent = None
+        if ent is None:
+            flat = [{"pin": torch.empty((need["bytes"],), dtype=torch.uint8, pin_memory=True),
+                     "comp": torch.empty((need["bytes"],), dtype=torch.uint8, device=dev),
+                     "raw": torch.empty((need["raw"],), dtype=torch.uint8, device=dev),
+                     "act": torch.zeros((need["act"],), dtype=torch.int32, device=dev),
+                     "frames": torch.empty((need["frames"],), dtype=torch.float32, device=dev)} for _ in range(2)]
+            ent = {"busy": True, "caps": need, "flat": flat}
+            with _CACHE_LOCK:
+                old = _CACHE.get(key)
+                if old is None or not old["busy"]:
+                    _CACHE[key] = ent                                   # (a pair in use elsewhere keeps its place)
+        else:
+            torch.cuda.synchronize(dev)                                # whatever last used the pair has drained
+        self._cache_entry = ent
+        n = self.block * self.ny * self.nx
+        return [dict(f, frames=f["frames"][:n].view(self.block, self.ny, self.nx)) for f in ent["flat"]]
+
+    def _release(self):
+        ent, self._cache_entry = getattr(self, "_cache_entry", None), None
+        if ent is not None:
+            with _CACHE_LOCK:
+                ent["busy"] = False
 
     def _pack(self, recs, pin: np.ndarray):
         """Stored chunks of `recs` into the pinned buffer, read with pread on a few threads (no page faults of a mapping,
@@ -323,6 +364,7 @@ class DeviceInflater:
             free.put((0, None))
             th.join()
             torch.cuda.current_stream(self.device).wait_stream(s_in)
+            self._release()
 
     def close(self):
         if self._pool is not None:

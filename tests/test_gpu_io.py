@@ -135,8 +135,11 @@ def test_device_inflater_delivers_the_file_s_frames(tmp_path, dtype, chunks, shu
         assert DeviceInflater.unsupported(dset) is None
         for frames, block in [(None, 4), ((2, 9), 3), ((1, 2), 32)]:
             lo0 = 0 if frames is None else frames[0]
-            got = [(lo, blk.cpu().numpy()) for lo, blk in DeviceInflater(dset, frames=frames, block_frames=block)]
-            assert got[0][0] == lo0
+            src = DeviceInflater(dset, frames=frames, block_frames=block)
+            sizes = [hi - lo for lo, hi, _ in src.blocks]
+            assert max(sizes) <= block and sum(sizes) == (T if frames is None else frames[1] - frames[0])
+            got = [(lo, blk.cpu().numpy()) for lo, blk in src]
+            assert got[0][0] == lo0 and [len(g) for _, g in got] == sizes
             hi0 = T if frames is None else frames[1]
             np.testing.assert_array_equal(np.concatenate([g for _, g in got]), data[lo0:hi0].astype(np.float32))
 
