@@ -6,6 +6,7 @@ h5py / libhdf5 are not installed here, so the codec is pinned against itself (wr
 assembled by hand in this file from the format specification, and structurally (addresses, signatures, sizes).
 """
 
+import os
 import struct
 import zlib
 
@@ -548,3 +549,58 @@ def test_read_tiff_against_arrays_the_reference_read(tmp_path, golden):
         np.testing.assert_array_equal(got, g[f"{name}/array"], err_msg=name)
     seq = [str(tmp_path / f"{n}.tif") for n in g["sequence/names"]]
     np.testing.assert_array_equal(read_image(seq), g["sequence/array"])
+
+
+_SHARDED_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch.distributed as dist
+from barc4dip_b200 import parallel
+from barc4dip_b200.io import hdf5, stream
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = parallel.dist_info()
+
+# the GPU analysis replaced by a host stand-in with the same contract (per-frame leaves for frames [lo, hi) of the FILE):
+# what is under test is the host logic around it -- every rank reads its own range and the reference, tables are gathered
+calls = []
+def fake_analyze(path, *, reference=None, frames=None, **kw):
+    calls.append(frames)
+    with hdf5.H5File(path) as f:
+        blk = f["entry_0000/measurement/data"].read(*frames).astype(np.float64)
+    return {{"stats": {{"mean": blk.mean(axis=(1, 2))}}, "table": blk.reshape(len(blk), -1)[:, :3],
+            "tracking": {{"dx": (blk - np.asarray(reference, np.float64)).sum(axis=(1, 2))}}}}
+stream.analyze_h5_stack = fake_analyze
+
+for T in (7, 1):
+    path = {tmp!r} + f"/s{{T}}.h5"
+    with hdf5.H5File(path) as f:
+        full = f["entry_0000/measurement/data"].read().astype(np.float64)
+    out = parallel.analyze_h5_stack_sharded(path, block_frames=2)
+    lo, hi = parallel.frame_range(T, rank, world)
+    assert out["frame_range"] == (lo, hi) and calls[-1] == ((lo, hi) if hi > lo else (0, 1))
+    assert np.array_equal(out["stats"]["mean"], full.mean(axis=(1, 2)))
+    assert np.array_equal(out["table"], full.reshape(T, -1)[:, :3])
+    assert np.array_equal(out["tracking"]["dx"], (full - full[0]).sum(axis=(1, 2)))
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_file_sharded_entry_on_two_gloo_ranks(tmp_path):
+    """parallel.analyze_h5_stack_sharded: frame ranges per rank, the reference read by every rank, per-frame tables
+    all-gathered in frame order, a rank without frames (T = 1 on two ranks) still joining the collectives."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for T in (7, 1):
+        hdf5.write_stack(tmp_path / f"s{T}.h5", _stack((T, 12, 10), "uint16", seed=T), chunks=(2, 5, 10))
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARDED_WORKER.format(root=root, tmp=str(tmp_path)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29573")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, out
