@@ -410,7 +410,7 @@ class H5File:
             raise OSError(f"truncated or damaged HDF5 file: '{self.path}'") from e
 
     def _dataset(self, header: int, name: str) -> H5Dataset:
-        O, L = self._O, self._L
+        L = self._L
         shape = dtype = layout = None
         filters = []
         for t, _, d in self._messages(header):

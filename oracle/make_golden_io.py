@@ -14,7 +14,6 @@ TIFF: files written by PIL, read by the reference's read_tiff (io/tiff.py:19-70)
 from __future__ import annotations
 
 import importlib
-import io
 import os
 import sys
 import tempfile
