@@ -10,10 +10,11 @@ h5py's default `libver` is the "earliest" flavour of the HDF5 File Format Specif
     -> chunked storage indexed by a v1 B-tree, each chunk deflate-compressed (optionally byte-shuffled).
 
 `H5File` / `H5Dataset` read that flavour, plus what costs nothing extra (superblock v2/v3, v2 object headers with
-compact link messages, contiguous / compact layouts, layout v4 with single-chunk or implicit index, the shuffle and
-Fletcher-32 filters, big-endian element types).  `write_stack` produces the flavour above.  Anything else (dense link
-storage, fixed / extensible-array or v2-B-tree chunk indices, szip / lzf, compound types) raises `H5Unsupported` with
-the offending structure named, it is never guessed at.
+compact link messages, contiguous / compact layouts, layout v4 with single-chunk, implicit or fixed-array index (what
+`libver="latest"` writes for datasets of fixed shape), the shuffle and Fletcher-32 filters, big-endian element types).
+`write_stack` produces the flavour above.  Anything else (dense link storage, extensible-array or v2-B-tree chunk
+indices of extendible datasets, szip / lzf, compound types) raises `H5Unsupported` with the offending structure named,
+it is never guessed at.
 
 Frames are read in ranges: only the chunks that intersect frames [a, b) are inflated, on a thread pool (zlib and the
 numpy block copies release the GIL), straight into the caller's buffer -- which `io.stream` makes a pinned staging
@@ -74,6 +75,15 @@ class H5Dataset:
                 addr, nbytes, mask = lay["single"]
                 cb = int(np.prod(self.chunks)) * self.dtype.itemsize
                 self._index = [((0,) * self.ndim, addr, cb if nbytes is None else nbytes, mask)]
+            elif lay.get("farray") is not None:
+                cb = int(np.prod(self.chunks)) * self.dtype.itemsize
+                grid = tuple(-(-s // c) for s, c in zip(self.shape, self.chunks))
+                self._index = []
+                if lay["farray"] != UNDEF:
+                    for i, (addr, nbytes, mask) in enumerate(self._f._fixed_array(lay["farray"])):
+                        if addr != UNDEF and i < int(np.prod(grid)):
+                            offs = tuple(int(k) * c for k, c in zip(np.unravel_index(i, grid), self.chunks))
+                            self._index.append((offs, addr, cb if nbytes is None else nbytes, mask))
             elif lay.get("implicit") is not None:
                 cb = int(np.prod(self.chunks)) * self.dtype.itemsize
                 grid = [range(0, s, c) for s, c in zip(self.shape, self.chunks)]
@@ -516,9 +526,61 @@ class H5File:
                 return {"kind": "chunked", "chunk": chunk, "single": (addr, nbytes, mask)}
             if itype == 2:                                        # implicit: chunks back to back, never filtered
                 return {"kind": "chunked", "chunk": chunk, "implicit": self._addr_of(d, p)}
-            names = {3: "fixed array", 4: "extensible array", 5: "version-2 B-tree"}
-            raise H5Unsupported(f"chunk index type {itype} ({names.get(itype, 'unknown')}): written with libver='latest'")
+            if itype == 3:                                        # fixed array (non-extendible datasets, libver >= 1.10)
+                if fl & 0x01:
+                    raise H5Unsupported("partial edge chunks stored unfiltered (layout flag 0x01)")
+                return {"kind": "chunked", "chunk": chunk, "farray": self._addr_of(d, p + 1)}     # p: page bits (repeated in the header)
+            names = {4: "extensible array", 5: "version-2 B-tree"}
+            raise H5Unsupported(f"chunk index type {itype} ({names.get(itype, 'unknown')}): extendible dataset written with libver='latest'")
         raise H5Unsupported(f"data layout message version {ver}")
+
+    def _fixed_array(self, addr: int):
+        """Elements of a fixed-array chunk index -> [(chunk address, stored bytes or None when unfiltered, filter mask)],
+        in the row-major order of the chunk grid. Header "FAHD": version, client (0 plain / 1 filtered chunks), element
+        size, page bits, element count, data block address; data block "FADB": version, client, header address, then
+        either the elements, or -- more than 2**bits elements -- a page-initialised bitmap (MSB first) followed by
+        pages of 2**bits elements, each closed by its own checksum."""
+        mm, O, L = self._mm, self._O, self._L
+        if mm[addr:addr + 4] != b"FAHD" or mm[addr + 4] != 0:
+            raise OSError("fixed array header expected")
+        client, esize, bits = mm[addr + 5], mm[addr + 6], mm[addr + 7]
+        count = self._uint(addr + 8, L)
+        dblk = self._addr(addr + 8 + L)
+        if client not in (0, 1) or esize < O + (5 if client else 0):
+            raise OSError("damaged fixed array header")
+        if dblk == UNDEF:
+            return [(UNDEF, None, 0)] * count
+        if mm[dblk:dblk + 4] != b"FADB" or mm[dblk + 4] != 0 or mm[dblk + 5] != client:
+            raise OSError("fixed array data block expected")
+        p = dblk + 6 + O
+        nlen = esize - O - 4
+
+        def elements(pos, n):
+            out = []
+            for _ in range(n):
+                a = self._addr(pos)
+                if client:
+                    out.append((a, self._uint(pos + O, nlen), self._uint(pos + O + nlen, 4)))
+                else:
+                    out.append((a, None, 0))
+                pos += esize
+            return out
+
+        per_page = 1 << bits
+        if count <= per_page:
+            return elements(p, count)
+        npages = -(-count // per_page)
+        bitmap = mm[p:p + (npages + 7) // 8]
+        p += len(bitmap) + 4                                        # bitmap, checksum of the data block's prefix
+        out = []
+        for pg in range(npages):
+            n = min(per_page, count - pg * per_page)
+            if bitmap[pg // 8] & (0x80 >> (pg % 8)):
+                out += elements(p, n)
+            else:
+                out += [(UNDEF, None, 0)] * n                       # a page never written: no chunk of it exists
+            p += per_page * esize + 4
+        return out
 
     def _walk_chunk_btree(self, root: int, rank: int):
         """Leaves of a v1 B-tree of raw-data chunks -> [(offsets, address, stored bytes, filter mask)]."""

@@ -604,3 +604,111 @@ def test_file_sharded_entry_on_two_gloo_ranks(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, out
+
+
+def _latest_file(a: np.ndarray, chunks, *, filtered: bool, page_bits: int, drop_last_page: bool = False) -> bytes:
+    """A file as `libver="latest"` lays out a fixed-shape chunked dataset, assembled by hand: superblock v2, v2 object
+    headers with link messages, dataspace v2, filter pipeline v2, layout v4 with a fixed-array chunk index (FAHD + FADB,
+    paged when the chunk count exceeds 2**page_bits). Checksums are left zero."""
+    rank, es = a.ndim, a.dtype.itemsize
+
+    def ohdr(msgs):
+        body = b"".join(struct.pack("<BHB", t, len(d), 0) + d for t, d in msgs)
+        return b"OHDR" + bytes([2, 0x01]) + struct.pack("<H", len(body)) + body + b"\x00" * 4      # chunk-0 size in 2 bytes
+
+    def link(name, addr):
+        nm = name.encode()
+        return struct.pack("<BB", 1, 0) + bytes([len(nm)]) + nm + struct.pack("<Q", addr)            # hard link, no flags
+
+    grid = [-(-s // c) for s, c in zip(a.shape, chunks)]
+    blobs = []
+    for idx in np.ndindex(*grid):
+        blk = np.zeros(chunks, a.dtype)
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, a.shape))
+        part = a[sl]
+        blk[tuple(slice(0, n) for n in part.shape)] = part
+        blobs.append(zlib.compress(blk.tobytes(), 4) if filtered else blk.tobytes())
+    count = len(blobs)
+    nlen = 3                                                         # bytes of the stored-size field of a filtered element
+    esize = 8 + (nlen + 4 if filtered else 0)
+    per_page = 1 << page_bits
+    paged = count > per_page
+    npages = -(-count // per_page) if paged else 0
+
+    space = struct.pack("<BBBB", 2, rank, 0, 1) + struct.pack(f"<{rank}Q", *a.shape)
+    kind = a.dtype.kind
+    dtm = struct.pack("<BBBBIHHBBBBI", 0x11, 0x20, 31, 0, 4, 0, 32, 23, 8, 0, 23, 127) if kind == "f" else \
+        struct.pack("<BBBBIHH", 0x10, 0x08 if kind == "i" else 0, 0, 0, es, 0, 8 * es)
+    pipeline = struct.pack("<BB", 2, 1) + struct.pack("<HHHI", 1, 1, 1, 4)
+    def layout(addr):
+        return struct.pack("<BBBBB", 4, 2, 0, rank + 1, 4) + struct.pack(f"<{rank + 1}I", *chunks, es) + bytes([3, page_bits]) + struct.pack("<Q", addr)
+    def dset_header(addr):
+        msgs = [(hdf5.MSG_DATASPACE, space), (hdf5.MSG_DATATYPE, dtm)] + ([(hdf5.MSG_FILTERS, pipeline)] if filtered else [])
+        return ohdr(msgs + [(hdf5.MSG_LAYOUT, layout(addr))])
+
+    sb_len = 12 + 4 * 8 + 4
+    names = ("entry_0000", "measurement", "data")
+    sizes = [len(ohdr([(hdf5.MSG_LINK, link(n, 0))])) for n in names]
+    a_root = sb_len
+    a_entry, a_meas = a_root + sizes[0], a_root + sizes[0] + sizes[1]
+    a_dset = a_meas + sizes[2]
+    a_fahd = a_dset + len(dset_header(0))
+    fahd_len = 8 + 8 + 8 + 4
+    a_fadb = a_fahd + fahd_len
+    prefix = 6 + 8 + ((npages + 7) // 8 if paged else count * esize) + 4
+    pages_len = sum(per_page * esize + 4 for _ in range(npages))
+    a_data = a_fadb + prefix + pages_len
+    addrs, pos = [], a_data
+    for b in blobs:
+        addrs.append(pos)
+        pos += len(b)
+
+    def element(i):
+        e = struct.pack("<Q", addrs[i])
+        return e + (len(blobs[i]).to_bytes(nlen, "little") + struct.pack("<I", 0) if filtered else b"")
+
+    fahd = b"FAHD" + bytes([0, int(filtered), esize, page_bits]) + struct.pack("<QQ", count, a_fadb) + b"\x00" * 4
+    fadb = b"FADB" + bytes([0, int(filtered)]) + struct.pack("<Q", a_fahd)
+    if not paged:
+        fadb += b"".join(element(i) for i in range(count)) + b"\x00" * 4
+    else:
+        bits = bytearray((npages + 7) // 8)
+        for pg in range(npages - (1 if drop_last_page else 0)):
+            bits[pg // 8] |= 0x80 >> (pg % 8)
+        fadb += bytes(bits) + b"\x00" * 4
+        for pg in range(npages):
+            els = b"".join(element(i) for i in range(pg * per_page, min(count, (pg + 1) * per_page)))
+            if drop_last_page and pg == npages - 1:
+                els = b"\xff" * len(els)                              # never written: whatever the file held there
+            fadb += els + b"\x00" * (per_page * esize - len(els)) + b"\x00" * 4
+    assert len(fahd) == fahd_len and len(fadb) == prefix + pages_len
+    out = hdf5.SIGNATURE + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", 0, hdf5.UNDEF, pos, a_root) + b"\x00" * 4
+    out += ohdr([(hdf5.MSG_LINK, link("entry_0000", a_entry))]) + ohdr([(hdf5.MSG_LINK, link("measurement", a_meas))])
+    out += ohdr([(hdf5.MSG_LINK, link("data", a_dset))]) + dset_header(a_fahd) + fahd + fadb + b"".join(blobs)
+    assert len(out) == pos
+    return out
+
+
+@pytest.mark.parametrize("filtered,page_bits", [(False, 10), (True, 10), (True, 2), (False, 1)])
+def test_reader_on_hand_assembled_fixed_array_index(tmp_path, filtered, page_bits):
+    """Layout v4 + fixed-array chunk index as libver='latest' writes it for fixed-shape datasets: plain and filtered
+    elements, unpaged and paged data blocks (2**page_bits elements per page), ragged edge chunks."""
+    a = _stack((5, 20, 18), "uint16", seed=14)
+    chunks = (2, 8, 18)                                              # 3 x 3 x 1 = 9 chunks
+    p = tmp_path / "latest.h5"
+    p.write_bytes(_latest_file(a, chunks, filtered=filtered, page_bits=page_bits))
+    with hdf5.H5File(p) as f:
+        d = f[PATH]
+        assert d.shape == a.shape and d.chunks == chunks and len(d._chunk_index()) == 9
+        assert d.filters == ([(1, [4])] if filtered else [])
+        np.testing.assert_array_equal(d.read(), a)
+        np.testing.assert_array_equal(d.read(3, 5), a[3:5])
+    np.testing.assert_array_equal(h5io.read_h5(str(p), image_number=2), a[2])
+    if page_bits == 2:
+        # a page whose bit is clear was never written: its chunks (the 9th of 9, frames 4.., rows 16..) read as zeros
+        p.write_bytes(_latest_file(a, chunks, filtered=filtered, page_bits=page_bits, drop_last_page=True))
+        want = a.copy()
+        want[4:, 16:, :] = 0
+        with hdf5.H5File(p) as f:
+            assert len(f[PATH]._chunk_index()) == 8
+            np.testing.assert_array_equal(f[PATH].read(), want)
